@@ -1,0 +1,854 @@
+// sdm_b200.cu — C-ABI implementation of libsdm_b200.so (see include/sdm_b200.h).
+//
+// Host side of the B200-native semi-dense mapping path: device arena, keyframe upload, batched
+// launches of the pass-1 / pass-2 kernels (sdm_kernels.cuh), downloads, CUDA-IPC halo pulls.
+// Replaces the CPU loops of yanmin-wu/EAO-SLAM src/ProbabilityMapping.cc:348-597.
+// No CPU fallback: every entry point that computes needs a CUDA device.
+//
+// Build: nvcc -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false
+//        -Xcompiler -fPIC,-ffp-contract=off -shared   (see __graft_entry__.build()).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/sdm_b200.h"
+#include "pair_geometry.h"
+#include "sdm_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(SDM_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+constexpr int kStages = 4;
+constexpr int kMaxPeers = 16;
+
+struct KfState {
+    bool uploaded = false;
+    bool pass1_done = false;
+    int cand_count = -1;  // -1: not read back yet
+    float K[4] = {0, 0, 0, 0};
+    float Tcw[12] = {0};
+};
+
+struct Stage {
+    uint8_t* im = nullptr;
+    float* grad = nullptr;
+    float* theta = nullptr;
+    int32_t* edge = nullptr;
+    cudaEvent_t done = nullptr;
+    bool busy = false;
+};
+
+}  // namespace
+
+struct sdm_ctx {
+    sdm_config cfg;
+    sdm::DevParams P;
+    sdm::DevArena A;
+    size_t npix = 0;
+    std::vector<KfState> kf;
+    cudaStream_t s_compute = nullptr, s_copy = nullptr;
+    cudaEvent_t ev_copy = nullptr, ev_compute = nullptr;
+    cudaEvent_t ev_p1[2] = {nullptr, nullptr}, ev_p2[2] = {nullptr, nullptr};
+    bool p1_timed = false, p2_timed = false;
+    Stage stage[kStages];
+    int stage_next = 0;
+    int* h_cand_count = nullptr;  // pinned mirror of A.cand_count
+    bool counts_pending = false;
+    sdm::DevItem* d_items = nullptr;
+    sdm::DevItem* h_items = nullptr;  // pinned
+    int* d_blk_off = nullptr;
+    int* h_blk_off = nullptr;  // pinned
+    int items_cap = 0;
+    sdm::DevStats* d_stats = nullptr;
+    float2* scratch_rs = nullptr;     // snapshot plane for the intra stencils
+    float* dl_stage = nullptr;        // 2 dense float planes (download / upload_depth staging)
+    float* dbg = nullptr;             // 4 float planes + 1 byte plane (sdm_epipolar_search_plane)
+    void* peer_rs[kMaxPeers] = {nullptr};
+    long long launches = 0;
+    long long stat_candidates = 0;
+};
+
+namespace {
+
+int ensure_items(sdm_ctx* c, int n)
+{
+    if (n <= c->items_cap) return SDM_OK;
+    int cap = std::max(n, std::max(64, c->items_cap * 2));
+    if (c->d_items) cudaFree(c->d_items);
+    if (c->h_items) cudaFreeHost(c->h_items);
+    if (c->d_blk_off) cudaFree(c->d_blk_off);
+    if (c->h_blk_off) cudaFreeHost(c->h_blk_off);
+    c->d_items = nullptr; c->h_items = nullptr; c->d_blk_off = nullptr; c->h_blk_off = nullptr;
+    c->items_cap = 0;
+    CU(cudaMalloc(&c->d_items, sizeof(sdm::DevItem) * cap));
+    CU(cudaMallocHost(&c->h_items, sizeof(sdm::DevItem) * cap));
+    CU(cudaMalloc(&c->d_blk_off, sizeof(int) * (cap + 1)));
+    CU(cudaMallocHost(&c->h_blk_off, sizeof(int) * (cap + 1)));
+    c->items_cap = cap;
+    return SDM_OK;
+}
+
+bool slot_ok(const sdm_ctx* c, int s) { return s >= 0 && s < (int)c->kf.size(); }
+
+// SemiDenseLoop :424-438 per keyframe: R21/t21/F12 for every neighbour, Twc for the point set
+int build_item(sdm_ctx* c, const sdm_item& in, sdm::DevItem& out, bool need_pass1_planes)
+{
+    if (!slot_ok(c, in.kf)) return fail(SDM_ERR_ARG, "item keyframe slot %d out of range", in.kf);
+    if (in.n_nbr < 0 || in.n_nbr > SDM_MAX_NBR) return fail(SDM_ERR_ARG, "n_nbr %d out of [0,%d]", in.n_nbr, SDM_MAX_NBR);
+    const KfState& k1 = c->kf[in.kf];
+    if (!k1.uploaded) return fail(SDM_ERR_STATE, "keyframe slot %d not uploaded", in.kf);
+    if (need_pass1_planes && !k1.pass1_done) return fail(SDM_ERR_STATE, "pass 2 before pass 1 for slot %d", in.kf);
+    memset(&out, 0, offsetof(sdm::DevItem, pair));
+    out.kf = in.kf;
+    out.n_nbr = in.n_nbr;
+    out.min_depth = in.min_depth;
+    out.max_depth = in.max_depth;
+    memcpy(out.K, k1.K, sizeof(out.K));
+    sdm::pose_inverse(k1.Tcw, out.Twc);
+    for (int j = 0; j < in.n_nbr; ++j) {
+        const int s2 = in.nbr[j];
+        if (!slot_ok(c, s2)) return fail(SDM_ERR_ARG, "neighbour slot %d out of range", s2);
+        const KfState& k2 = c->kf[s2];
+        if (need_pass1_planes) {
+            if (!k2.pass1_done) return fail(SDM_ERR_STATE, "neighbour slot %d has no pass-1 planes", s2);
+        } else if (!k2.uploaded) {
+            return fail(SDM_ERR_STATE, "neighbour slot %d not uploaded", s2);
+        }
+        // the poses of a halo slot that only carries pass-1 planes are still required
+        const sdm::PairGeometry g = sdm::pair_geometry(k1.K, k1.Tcw, k2.K, k2.Tcw);
+        sdm::DevPair& p = out.pair[j];
+        memcpy(p.F, g.F12.m, sizeof(p.F));
+        memcpy(p.R, g.R21.m, sizeof(p.R));
+        memcpy(p.t, g.t21.v, sizeof(p.t));
+        p.rot = in.rot_deg[j];
+        p.slot = s2;
+    }
+    return SDM_OK;
+}
+
+// wait until the candidate counts of every uploaded keyframe are on the host
+int sync_counts(sdm_ctx* c)
+{
+    if (c->counts_pending) {
+        CU(cudaStreamSynchronize(c->s_copy));
+        c->counts_pending = false;
+        for (size_t i = 0; i < c->kf.size(); ++i)
+            if (c->kf[i].uploaded && c->kf[i].cand_count < 0) c->kf[i].cand_count = c->h_cand_count[i];
+        for (auto& st : c->stage) st.busy = false;
+    }
+    return SDM_OK;
+}
+
+// compute stream waits for everything queued on the copy stream (uploads) and vice versa
+int copy_then_compute(sdm_ctx* c)
+{
+    CU(cudaEventRecord(c->ev_copy, c->s_copy));
+    CU(cudaStreamWaitEvent(c->s_compute, c->ev_copy, 0));
+    return SDM_OK;
+}
+int compute_then_copy(sdm_ctx* c)
+{
+    CU(cudaEventRecord(c->ev_compute, c->s_compute));
+    CU(cudaStreamWaitEvent(c->s_copy, c->ev_compute, 0));
+    return SDM_OK;
+}
+
+int upload_items(sdm_ctx* c, int n, const sdm_item* items, bool pass2)
+{
+    int rc = ensure_items(c, n);
+    if (rc) return rc;
+    // the pinned item staging may still be read by the previous pass's H2D copy
+    CU(cudaStreamSynchronize(c->s_compute));
+    for (int i = 0; i < n; ++i) {
+        rc = build_item(c, items[i], c->h_items[i], pass2);
+        if (rc) return rc;
+    }
+    CU(cudaMemcpyAsync(c->d_items, c->h_items, sizeof(sdm::DevItem) * n, cudaMemcpyHostToDevice, c->s_compute));
+    return SDM_OK;
+}
+
+dim3 tile_grid(const sdm_ctx* c) { return dim3((c->cfg.width + 31) / 32, (c->cfg.height + 7) / 8); }
+
+int run_intra(sdm_ctx* c, int slot, bool check, bool grow)
+{
+    const size_t bytes = c->npix * sizeof(float2);
+    float2* plane = c->A.rs + (size_t)slot * c->npix;
+    if (check) {
+        CU(cudaMemcpyAsync(c->scratch_rs, plane, bytes, cudaMemcpyDeviceToDevice, c->s_compute));
+        sdm::k_intra_check<<<tile_grid(c), dim3(32, 8), 0, c->s_compute>>>(c->P, c->scratch_rs, plane);
+        c->launches++;
+    }
+    if (grow) {
+        CU(cudaMemcpyAsync(c->scratch_rs, plane, bytes, cudaMemcpyDeviceToDevice, c->s_compute));
+        sdm::k_intra_grow<<<tile_grid(c), dim3(32, 8), 0, c->s_compute>>>(c->P, c->scratch_rs, plane,
+                                                                          c->A.tex + (size_t)slot * c->npix);
+        c->launches++;
+    }
+    CU(cudaGetLastError());
+    return SDM_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+void sdm_default_config(sdm_config* cfg)
+{
+    if (!cfg) return;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->width = 640;
+    cfg->height = 480;
+    cfg->max_keyframes = 16;
+    cfg->lambdaG = 8;
+    cfg->lambdaL = 80;
+    cfg->lambdaTheta = 45;
+    cfg->lambdaN = 3;
+    cfg->theta = (float)0.23;
+    cfg->sigmaI = 20.0f;
+    cfg->chi2_fusion = 5.99;
+    cfg->chi2_inter = 3.84;
+    cfg->eps = 0.000001;
+    cfg->slope_max = 4.0f;
+    cfg->intra_check = 0;
+    cfg->intra_grow = 0;
+    cfg->device = 0;
+}
+
+const char* sdm_last_error(void) { return g_last_error.c_str(); }
+const char* sdm_version(void) { return "sdm_b200 0.1 (sm_100a)"; }
+
+void sdm_destroy(sdm_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->cfg.device);
+    cudaDeviceSynchronize();
+    for (int i = 0; i < kMaxPeers; ++i)
+        if (c->peer_rs[i]) cudaIpcCloseMemHandle(c->peer_rs[i]);
+    cudaFree(c->A.tex); cudaFree(c->A.ipair); cudaFree(c->A.cand); cudaFree(c->A.cand_count);
+    cudaFree(c->A.rs); cudaFree(c->A.chk); cudaFree(c->A.pts);
+    for (auto& s : c->stage) {
+        cudaFree(s.im); cudaFree(s.grad); cudaFree(s.theta); cudaFree(s.edge);
+        if (s.done) cudaEventDestroy(s.done);
+    }
+    if (c->h_cand_count) cudaFreeHost(c->h_cand_count);
+    cudaFree(c->d_items); cudaFree(c->d_blk_off); cudaFree(c->d_stats); cudaFree(c->scratch_rs);
+    cudaFree(c->dl_stage); cudaFree(c->dbg);
+    if (c->h_items) cudaFreeHost(c->h_items);
+    if (c->h_blk_off) cudaFreeHost(c->h_blk_off);
+    for (cudaEvent_t e : {c->ev_copy, c->ev_compute, c->ev_p1[0], c->ev_p1[1], c->ev_p2[0], c->ev_p2[1]})
+        if (e) cudaEventDestroy(e);
+    if (c->s_compute) cudaStreamDestroy(c->s_compute);
+    if (c->s_copy) cudaStreamDestroy(c->s_copy);
+    delete c;
+}
+
+static int create_impl(sdm_ctx* c)
+{
+    const sdm_config& cfg = c->cfg;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(SDM_ERR_CUDA, "no CUDA device: libsdm_b200 has no CPU fallback");
+    if (cfg.device < 0 || cfg.device >= ndev) return fail(SDM_ERR_ARG, "device %d out of range (%d devices)", cfg.device, ndev);
+    CU(cudaSetDevice(cfg.device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, cfg.device));
+    if (prop.major < 10) return fail(SDM_ERR_CUDA, "device sm_%d%d: this library is built for sm_100a only", prop.major, prop.minor);
+
+    const size_t P = (size_t)cfg.width * cfg.height;
+    const size_t n = (size_t)cfg.max_keyframes;
+    c->npix = P;
+    c->kf.assign(n, KfState());
+    sdm::DevParams& D = c->P;
+    D.W = cfg.width;
+    D.H = cfg.height;
+    D.lambdaG = (float)cfg.lambdaG;
+    D.lambdaL = (float)cfg.lambdaL;
+    D.lambdaTheta = (float)cfg.lambdaTheta;
+    D.lambdaN = cfg.lambdaN;
+    D.theta = cfg.theta;
+    D.inv_theta = 1 / cfg.theta;
+    D.var_num = 2 * cfg.sigmaI * cfg.sigmaI;
+    D.chi_fusion_lt = sdm::thr_lt(cfg.chi2_fusion);
+    D.chi_inter_lt = sdm::thr_lt(cfg.chi2_inter);
+    D.eps_gt = sdm::thr_gt(cfg.eps);
+    D.eps_lt = sdm::thr_lt(cfg.eps);
+    D.slope_max = cfg.slope_max;
+
+    CU(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
+    CU(cudaEventCreateWithFlags(&c->ev_compute, cudaEventDisableTiming));
+    for (int i = 0; i < 2; ++i) {
+        CU(cudaEventCreate(&c->ev_p1[i]));
+        CU(cudaEventCreate(&c->ev_p2[i]));
+    }
+    sdm::DevArena& A = c->A;
+    memset(&A, 0, sizeof(A));
+    A.P = P;
+    CU(cudaMalloc(&A.tex, n * P * sizeof(float4)));
+    CU(cudaMalloc(&A.ipair, n * P * sizeof(uchar2)));
+    CU(cudaMalloc(&A.cand, n * P * sizeof(uint32_t)));
+    CU(cudaMalloc(&A.cand_count, n * sizeof(int)));
+    CU(cudaMalloc(&A.rs, n * P * sizeof(float2)));
+    CU(cudaMalloc(&A.chk, n * P * sizeof(float)));
+    CU(cudaMalloc(&A.pts, n * P * 3 * sizeof(float)));
+    CU(cudaMemsetAsync(A.cand_count, 0, n * sizeof(int), c->s_compute));
+    CU(cudaMemsetAsync(A.rs, 0, n * P * sizeof(float2), c->s_compute));
+    CU(cudaMemsetAsync(A.chk, 0, n * P * sizeof(float), c->s_compute));
+    CU(cudaMemsetAsync(A.pts, 0, n * P * 3 * sizeof(float), c->s_compute));
+    for (auto& s : c->stage) {
+        CU(cudaMalloc(&s.im, P));
+        CU(cudaMalloc(&s.grad, P * sizeof(float)));
+        CU(cudaMalloc(&s.theta, P * sizeof(float)));
+        CU(cudaMalloc(&s.edge, P * sizeof(int32_t)));
+        CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+    }
+    CU(cudaMallocHost(&c->h_cand_count, n * sizeof(int)));
+    CU(cudaMalloc(&c->d_stats, sizeof(sdm::DevStats)));
+    CU(cudaMemsetAsync(c->d_stats, 0, sizeof(sdm::DevStats), c->s_compute));
+    CU(cudaMalloc(&c->scratch_rs, P * sizeof(float2)));
+    CU(cudaMalloc(&c->dl_stage, 2 * P * sizeof(float)));
+    CU(cudaStreamSynchronize(c->s_compute));
+    return SDM_OK;
+}
+
+int sdm_create(const sdm_config* cfg, sdm_ctx** out)
+{
+    if (!cfg || !out) return fail(SDM_ERR_ARG, "sdm_create: null argument");
+    *out = nullptr;
+    if (cfg->width < 8 || cfg->height < 8 || cfg->width > 65535 || cfg->height > 65535)
+        return fail(SDM_ERR_ARG, "image size %dx%d unsupported", cfg->width, cfg->height);
+    if (cfg->max_keyframes < 1) return fail(SDM_ERR_ARG, "max_keyframes must be >= 1");
+    if (!(cfg->theta > 0.f)) return fail(SDM_ERR_ARG, "theta must be > 0");
+    sdm_ctx* c = new (std::nothrow) sdm_ctx();
+    if (!c) return fail(SDM_ERR_NOMEM, "out of host memory");
+    c->cfg = *cfg;
+    int rc = create_impl(c);
+    if (rc != SDM_OK) {
+        std::string keep = g_last_error;
+        sdm_destroy(c);
+        g_last_error = keep;
+        return rc;
+    }
+    *out = c;
+    return SDM_OK;
+}
+
+int sdm_synchronize(sdm_ctx* c)
+{
+    if (!c) return fail(SDM_ERR_ARG, "null context");
+    CU(cudaSetDevice(c->cfg.device));
+    int rc = sync_counts(c);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(c->s_copy));
+    CU(cudaStreamSynchronize(c->s_compute));
+    return SDM_OK;
+}
+
+int sdm_get_stats(sdm_ctx* c, sdm_stats* out)
+{
+    if (!c || !out) return fail(SDM_ERR_ARG, "null argument");
+    CU(cudaSetDevice(c->cfg.device));
+    sdm::DevStats h;
+    CU(cudaMemcpyAsync(&h, c->d_stats, sizeof(h), cudaMemcpyDeviceToHost, c->s_compute));
+    CU(cudaStreamSynchronize(c->s_compute));
+    out->candidates = c->stat_candidates;
+    out->fused = (long long)h.fused;
+    out->checked = (long long)h.checked;
+    return SDM_OK;
+}
+
+int sdm_host_alloc(void** ptr, size_t bytes)
+{
+    if (!ptr) return fail(SDM_ERR_ARG, "null argument");
+    CU(cudaMallocHost(ptr, bytes));
+    return SDM_OK;
+}
+int sdm_host_free(void* ptr)
+{
+    CU(cudaFreeHost(ptr));
+    return SDM_OK;
+}
+
+// ---- keyframe planes -----------------------------------------------------------------------------
+int sdm_upload_keyframe(sdm_ctx* c, int kf, const uint8_t* im, size_t im_step, const float* grad, size_t grad_step,
+                        const float* theta, size_t theta_step, const int32_t* edge, size_t edge_step, const float K[4],
+                        const float Tcw[12])
+{
+    if (!c || !im || !grad || !theta || !K || !Tcw) return fail(SDM_ERR_ARG, "sdm_upload_keyframe: null argument");
+    if (!slot_ok(c, kf)) return fail(SDM_ERR_ARG, "keyframe slot %d out of range [0,%d)", kf, (int)c->kf.size());
+    const int W = c->cfg.width, H = c->cfg.height;
+    if (im_step < (size_t)W || grad_step < (size_t)W * 4 || theta_step < (size_t)W * 4 || (edge && edge_step < (size_t)W * 4))
+        return fail(SDM_ERR_ARG, "row step smaller than a row");
+    CU(cudaSetDevice(c->cfg.device));
+    Stage& st = c->stage[c->stage_next];
+    c->stage_next = (c->stage_next + 1) % kStages;
+    if (st.busy) CU(cudaEventSynchronize(st.done));
+    // the slot's planes may still be read by queued compute work
+    int rc = compute_then_copy(c);
+    if (rc) return rc;
+    CU(cudaMemcpy2DAsync(st.im, W, im, im_step, W, H, cudaMemcpyHostToDevice, c->s_copy));
+    CU(cudaMemcpy2DAsync(st.grad, (size_t)W * 4, grad, grad_step, (size_t)W * 4, H, cudaMemcpyHostToDevice, c->s_copy));
+    CU(cudaMemcpy2DAsync(st.theta, (size_t)W * 4, theta, theta_step, (size_t)W * 4, H, cudaMemcpyHostToDevice, c->s_copy));
+    if (edge)
+        CU(cudaMemcpy2DAsync(st.edge, (size_t)W * 4, edge, edge_step, (size_t)W * 4, H, cudaMemcpyHostToDevice, c->s_copy));
+    CU(cudaMemsetAsync(c->A.cand_count + kf, 0, sizeof(int), c->s_copy));
+    sdm::k_pack<<<tile_grid(c), dim3(32, 8), 0, c->s_copy>>>(c->A, c->P, kf, st.im, st.grad, st.theta,
+                                                             edge ? st.edge : nullptr);
+    CU(cudaGetLastError());
+    c->launches++;
+    CU(cudaMemcpyAsync(c->h_cand_count + kf, c->A.cand_count + kf, sizeof(int), cudaMemcpyDeviceToHost, c->s_copy));
+    CU(cudaEventRecord(st.done, c->s_copy));
+    st.busy = true;
+    c->counts_pending = true;
+    KfState& k = c->kf[kf];
+    k.uploaded = true;
+    k.pass1_done = false;
+    k.cand_count = -1;
+    memcpy(k.K, K, sizeof(k.K));
+    memcpy(k.Tcw, Tcw, sizeof(k.Tcw));
+    return SDM_OK;
+}
+
+int sdm_set_pose(sdm_ctx* c, int kf, const float Tcw[12])
+{
+    if (!c || !Tcw) return fail(SDM_ERR_ARG, "null argument");
+    if (!slot_ok(c, kf)) return fail(SDM_ERR_ARG, "keyframe slot %d out of range", kf);
+    memcpy(c->kf[kf].Tcw, Tcw, sizeof(float) * 12);
+    return SDM_OK;
+}
+
+int sdm_set_intrinsics(sdm_ctx* c, int kf, const float K[4])
+{
+    if (!c || !K) return fail(SDM_ERR_ARG, "null argument");
+    if (!slot_ok(c, kf)) return fail(SDM_ERR_ARG, "keyframe slot %d out of range", kf);
+    memcpy(c->kf[kf].K, K, sizeof(float) * 4);
+    return SDM_OK;
+}
+
+int sdm_candidate_count(sdm_ctx* c, int kf, int* count)
+{
+    if (!c || !count) return fail(SDM_ERR_ARG, "null argument");
+    if (!slot_ok(c, kf)) return fail(SDM_ERR_ARG, "keyframe slot %d out of range", kf);
+    if (!c->kf[kf].uploaded) return fail(SDM_ERR_STATE, "keyframe slot %d not uploaded", kf);
+    CU(cudaSetDevice(c->cfg.device));
+    int rc = sync_counts(c);
+    if (rc) return rc;
+    *count = c->kf[kf].cand_count;
+    return SDM_OK;
+}
+
+// ---- the two hot loops ---------------------------------------------------------------------------
+int sdm_pass1(sdm_ctx* c, int n, const sdm_item* items)
+{
+    if (!c || (n > 0 && !items)) return fail(SDM_ERR_ARG, "sdm_pass1: null argument");
+    if (n <= 0) return SDM_OK;
+    CU(cudaSetDevice(c->cfg.device));
+    int rc = sync_counts(c);
+    if (rc) return rc;
+    rc = upload_items(c, n, items, false);
+    if (rc) return rc;
+    long long total_blocks = 0, cands = 0;
+    for (int i = 0; i < n; ++i) {
+        c->h_blk_off[i] = (int)total_blocks;
+        const int cnt = c->kf[items[i].kf].cand_count;
+        cands += cnt;
+        total_blocks += (cnt + sdm::kPass1Warps - 1) / sdm::kPass1Warps;
+    }
+    c->h_blk_off[n] = (int)total_blocks;
+    if (total_blocks > 0x7fffffffLL) return fail(SDM_ERR_ARG, "pass-1 batch too large (%lld blocks)", total_blocks);
+    c->stat_candidates = cands;
+    CU(cudaMemcpyAsync(c->d_blk_off, c->h_blk_off, sizeof(int) * (n + 1), cudaMemcpyHostToDevice, c->s_compute));
+    CU(cudaMemsetAsync(&c->d_stats->fused, 0, sizeof(unsigned long long), c->s_compute));
+    rc = copy_then_compute(c);
+    if (rc) return rc;
+    CU(cudaEventRecord(c->ev_p1[0], c->s_compute));
+    if (total_blocks > 0) {
+        sdm::k_pass1<<<(unsigned)total_blocks, sdm::kPass1Warps * 32, 0, c->s_compute>>>(c->A, c->P, c->d_items,
+                                                                                        c->d_blk_off, n, c->d_stats);
+        CU(cudaGetLastError());
+        c->launches++;
+    }
+    if (c->cfg.intra_check || c->cfg.intra_grow)
+        for (int i = 0; i < n; ++i) {
+            rc = run_intra(c, items[i].kf, c->cfg.intra_check != 0, c->cfg.intra_grow != 0);
+            if (rc) return rc;
+        }
+    CU(cudaEventRecord(c->ev_p1[1], c->s_compute));
+    c->p1_timed = true;
+    for (int i = 0; i < n; ++i) c->kf[items[i].kf].pass1_done = true;
+    return SDM_OK;
+}
+
+static int pass2_impl(sdm_ctx* c, int n, const sdm_item* items, int points_only)
+{
+    CU(cudaSetDevice(c->cfg.device));
+    int rc = upload_items(c, n, items, points_only == 0);
+    if (rc) return rc;
+    if (!points_only) CU(cudaMemsetAsync(&c->d_stats->checked, 0, sizeof(unsigned long long), c->s_compute));
+    rc = copy_then_compute(c);
+    if (rc) return rc;
+    CU(cudaEventRecord(c->ev_p2[0], c->s_compute));
+    dim3 grid((unsigned)((c->npix + 255) / 256), (unsigned)n);
+    sdm::k_pass2<<<grid, 256, 0, c->s_compute>>>(c->A, c->P, c->d_items, c->d_stats, points_only);
+    CU(cudaGetLastError());
+    c->launches++;
+    CU(cudaEventRecord(c->ev_p2[1], c->s_compute));
+    c->p2_timed = true;
+    return SDM_OK;
+}
+
+int sdm_pass2(sdm_ctx* c, int n, const sdm_item* items)
+{
+    if (!c || (n > 0 && !items)) return fail(SDM_ERR_ARG, "sdm_pass2: null argument");
+    if (n <= 0) return SDM_OK;
+    if (n > 65535) return fail(SDM_ERR_ARG, "pass-2 batch limited to 65535 keyframes per call");
+    return pass2_impl(c, n, items, 0);
+}
+
+int sdm_update_points(sdm_ctx* c, int n, const int32_t* kfs)
+{
+    if (!c || (n > 0 && !kfs)) return fail(SDM_ERR_ARG, "sdm_update_points: null argument");
+    if (n <= 0) return SDM_OK;
+    if (n > 65535) return fail(SDM_ERR_ARG, "batch limited to 65535 keyframes per call");
+    std::vector<sdm_item> items((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        memset(&items[i], 0, sizeof(sdm_item));
+        items[i].kf = kfs[i];
+    }
+    return pass2_impl(c, n, items.data(), 1);
+}
+
+int sdm_download(sdm_ctx* c, int kf, float* depth, size_t depth_step, float* sigma, size_t sigma_step, float* checked,
+                 size_t checked_step, float* points, size_t points_step)
+{
+    if (!c) return fail(SDM_ERR_ARG, "null context");
+    if (!slot_ok(c, kf)) return fail(SDM_ERR_ARG, "keyframe slot %d out of range", kf);
+    const int W = c->cfg.width, H = c->cfg.height;
+    const size_t P = c->npix, row = (size_t)W * 4;
+    if ((depth && depth_step < row) || (sigma && sigma_step < row) || (checked && checked_step < row) ||
+        (points && points_step < 3 * row))
+        return fail(SDM_ERR_ARG, "row step smaller than a row");
+    CU(cudaSetDevice(c->cfg.device));
+    cudaStream_t s = c->s_compute;
+    if (depth || sigma) {
+        sdm::k_split_rs<<<(unsigned)((P + 255) / 256), 256, 0, s>>>(c->A.rs + (size_t)kf * P, c->dl_stage, c->dl_stage + P, P);
+        CU(cudaGetLastError());
+        c->launches++;
+        if (depth) CU(cudaMemcpy2DAsync(depth, depth_step, c->dl_stage, row, row, H, cudaMemcpyDeviceToHost, s));
+        if (sigma) CU(cudaMemcpy2DAsync(sigma, sigma_step, c->dl_stage + P, row, row, H, cudaMemcpyDeviceToHost, s));
+    }
+    if (checked) CU(cudaMemcpy2DAsync(checked, checked_step, c->A.chk + (size_t)kf * P, row, row, H, cudaMemcpyDeviceToHost, s));
+    if (points)
+        CU(cudaMemcpy2DAsync(points, points_step, c->A.pts + (size_t)kf * P * 3, 3 * row, 3 * row, H, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    return SDM_OK;
+}
+
+int sdm_upload_depth(sdm_ctx* c, int kf, const float* depth, size_t depth_step, const float* sigma, size_t sigma_step)
+{
+    if (!c || !depth || !sigma) return fail(SDM_ERR_ARG, "null argument");
+    if (!slot_ok(c, kf)) return fail(SDM_ERR_ARG, "keyframe slot %d out of range", kf);
+    const int W = c->cfg.width, H = c->cfg.height;
+    const size_t P = c->npix, row = (size_t)W * 4;
+    if (depth_step < row || sigma_step < row) return fail(SDM_ERR_ARG, "row step smaller than a row");
+    CU(cudaSetDevice(c->cfg.device));
+    cudaStream_t s = c->s_compute;
+    CU(cudaMemcpy2DAsync(c->dl_stage, row, depth, depth_step, row, H, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpy2DAsync(c->dl_stage + P, row, sigma, sigma_step, row, H, cudaMemcpyHostToDevice, s));
+    sdm::k_merge_rs<<<(unsigned)((P + 255) / 256), 256, 0, s>>>(c->A.rs + (size_t)kf * P, c->dl_stage, c->dl_stage + P, P);
+    CU(cudaGetLastError());
+    c->launches++;
+    CU(cudaStreamSynchronize(s));
+    c->kf[kf].pass1_done = true;
+    return SDM_OK;
+}
+
+// ---- multi-GPU -----------------------------------------------------------------------------------
+int sdm_depth_plane_ptr(sdm_ctx* c, int kf, void** dev_ptr, size_t* bytes)
+{
+    if (!c || !dev_ptr) return fail(SDM_ERR_ARG, "null argument");
+    if (!slot_ok(c, kf)) return fail(SDM_ERR_ARG, "keyframe slot %d out of range", kf);
+    *dev_ptr = (void*)(c->A.rs + (size_t)kf * c->npix);
+    if (bytes) *bytes = c->npix * sizeof(float2);
+    return SDM_OK;
+}
+
+int sdm_export_arena(sdm_ctx* c, void* handle64, size_t* slot_bytes)
+{
+    if (!c || !handle64) return fail(SDM_ERR_ARG, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CU(cudaSetDevice(c->cfg.device));
+    cudaIpcMemHandle_t h;
+    CU(cudaIpcGetMemHandle(&h, c->A.rs));
+    memcpy(handle64, &h, 64);
+    if (slot_bytes) *slot_bytes = c->npix * sizeof(float2);
+    return SDM_OK;
+}
+
+int sdm_import_peer_arena(sdm_ctx* c, int peer_rank, const void* handle64)
+{
+    if (!c || !handle64) return fail(SDM_ERR_ARG, "null argument");
+    if (peer_rank < 0 || peer_rank >= kMaxPeers) return fail(SDM_ERR_ARG, "peer rank %d out of [0,%d)", peer_rank, kMaxPeers);
+    CU(cudaSetDevice(c->cfg.device));
+    if (c->peer_rs[peer_rank]) {
+        CU(cudaIpcCloseMemHandle(c->peer_rs[peer_rank]));
+        c->peer_rs[peer_rank] = nullptr;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    void* p = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_rs[peer_rank] = p;
+    return SDM_OK;
+}
+
+int sdm_pull_halo(sdm_ctx* c, int n, const int32_t* local_slot, const int32_t* peer_rank, const int32_t* peer_slot)
+{
+    if (!c || (n > 0 && (!local_slot || !peer_rank || !peer_slot))) return fail(SDM_ERR_ARG, "null argument");
+    CU(cudaSetDevice(c->cfg.device));
+    const size_t bytes = c->npix * sizeof(float2);
+    for (int i = 0; i < n; ++i) {
+        if (!slot_ok(c, local_slot[i])) return fail(SDM_ERR_ARG, "local slot %d out of range", local_slot[i]);
+        const int pr = peer_rank[i];
+        if (pr < 0 || pr >= kMaxPeers || !c->peer_rs[pr]) return fail(SDM_ERR_STATE, "peer %d arena not imported", pr);
+        if (peer_slot[i] < 0) return fail(SDM_ERR_ARG, "peer slot %d negative", peer_slot[i]);
+        const char* src = (const char*)c->peer_rs[pr] + (size_t)peer_slot[i] * bytes;
+        CU(cudaMemcpyAsync(c->A.rs + (size_t)local_slot[i] * c->npix, src, bytes, cudaMemcpyDeviceToDevice, c->s_compute));
+        c->kf[local_slot[i]].pass1_done = true;
+    }
+    return SDM_OK;
+}
+
+int sdm_mark_pass1_done(sdm_ctx* c, int kf)
+{
+    if (!c) return fail(SDM_ERR_ARG, "null context");
+    if (!slot_ok(c, kf)) return fail(SDM_ERR_ARG, "keyframe slot %d out of range", kf);
+    c->kf[kf].pass1_done = true;
+    return SDM_OK;
+}
+
+// ---- per-method entry points ---------------------------------------------------------------------
+int sdm_pair_geometry(const float K1[4], const float Tcw1[12], const float K2[4], const float Tcw2[12],
+                      sdm_pair_geometry_t* out)
+{
+    if (!K1 || !Tcw1 || !K2 || !Tcw2 || !out) return fail(SDM_ERR_ARG, "null argument");
+    const sdm::PairGeometry g = sdm::pair_geometry(K1, Tcw1, K2, Tcw2);
+    memcpy(out->R21, g.R21.m, sizeof(out->R21));
+    memcpy(out->t21, g.t21.v, sizeof(out->t21));
+    memcpy(out->F12, g.F12.m, sizeof(out->F12));
+    return SDM_OK;
+}
+
+int sdm_stereo_search_constraints(const float* inv_depths, int n, float* min_depth, float* max_depth)
+{
+    if (!inv_depths || !min_depth || !max_depth || n <= 0) return fail(SDM_ERR_ARG, "bad argument");
+    sdm::stereo_search_constraints(inv_depths, n, min_depth, max_depth);
+    return SDM_OK;
+}
+
+static int single_pair_item(sdm_ctx* c, int kf1, int kf2, float mind, float maxd, float rot)
+{
+    sdm_item it;
+    memset(&it, 0, sizeof(it));
+    it.kf = kf1;
+    it.n_nbr = 1;
+    it.nbr[0] = kf2;
+    it.rot_deg[0] = rot;
+    it.min_depth = mind;
+    it.max_depth = maxd;
+    int rc = sync_counts(c);
+    if (rc) return rc;
+    rc = upload_items(c, 1, &it, false);
+    if (rc) return rc;
+    return copy_then_compute(c);
+}
+
+static int ensure_dbg(sdm_ctx* c)
+{
+    if (!c->dbg) CU(cudaMalloc(&c->dbg, c->npix * (4 * sizeof(float) + 1)));
+    return SDM_OK;
+}
+
+int sdm_search_range(sdm_ctx* c, int kf1, int kf2, int px, int py, float mind, float maxd, float* umin, float* umax)
+{
+    if (!c || !umin || !umax) return fail(SDM_ERR_ARG, "null argument");
+    CU(cudaSetDevice(c->cfg.device));
+    int rc = single_pair_item(c, kf1, kf2, mind, maxd, 0.f);
+    if (rc) return rc;
+    rc = ensure_dbg(c);
+    if (rc) return rc;
+    sdm::k_search_range<<<1, 1, 0, c->s_compute>>>(c->P, c->d_items, px, py, c->dbg);
+    CU(cudaGetLastError());
+    c->launches++;
+    float h[2];
+    CU(cudaMemcpyAsync(h, c->dbg, sizeof(h), cudaMemcpyDeviceToHost, c->s_compute));
+    CU(cudaStreamSynchronize(c->s_compute));
+    *umin = h[0];
+    *umax = h[1];
+    return SDM_OK;
+}
+
+int sdm_epipolar_search(sdm_ctx* c, int kf1, int kf2, int x, int y, float min_depth, float max_depth, float rot_deg,
+                        sdm_hypothesis* out)
+{
+    if (!c || !out) return fail(SDM_ERR_ARG, "null argument");
+    if (x < 0 || y < 0 || x >= c->cfg.width || y >= c->cfg.height) return fail(SDM_ERR_ARG, "pixel (%d,%d) outside the image", x, y);
+    CU(cudaSetDevice(c->cfg.device));
+    int rc = single_pair_item(c, kf1, kf2, min_depth, max_depth, rot_deg);
+    if (rc) return rc;
+    rc = ensure_dbg(c);
+    if (rc) return rc;
+    float* d = c->dbg;
+    uint8_t* ok = (uint8_t*)(c->dbg + 4);
+    sdm::k_pair_hypotheses<<<1, sdm::kPass1Warps * 32, 0, c->s_compute>>>(c->A, c->P, c->d_items, d, d + 1, d + 2, d + 3, ok,
+                                                                          (y << 16) | x);
+    CU(cudaGetLastError());
+    c->launches++;
+    float h[5];
+    CU(cudaMemcpyAsync(h, c->dbg, sizeof(h), cudaMemcpyDeviceToHost, c->s_compute));
+    CU(cudaStreamSynchronize(c->s_compute));
+    uint8_t okh;
+    memcpy(&okh, &h[4], 1);
+    out->depth = h[0];
+    out->sigma = h[1];
+    out->best_u = h[2];
+    out->best_v = h[3];
+    out->supported = okh ? 1 : 0;
+    return SDM_OK;
+}
+
+int sdm_epipolar_search_plane(sdm_ctx* c, int kf1, int kf2, float min_depth, float max_depth, float rot_deg,
+                              float* hyp_depth, float* hyp_sigma, float* hyp_u, uint8_t* ok)
+{
+    if (!c || !hyp_depth || !hyp_sigma || !hyp_u || !ok) return fail(SDM_ERR_ARG, "null argument");
+    CU(cudaSetDevice(c->cfg.device));
+    int rc = single_pair_item(c, kf1, kf2, min_depth, max_depth, rot_deg);
+    if (rc) return rc;
+    rc = ensure_dbg(c);
+    if (rc) return rc;
+    const size_t P = c->npix;
+    float* d = c->dbg;
+    uint8_t* dok = (uint8_t*)(c->dbg + 4 * P);
+    CU(cudaMemsetAsync(c->dbg, 0, P * (4 * sizeof(float) + 1), c->s_compute));
+    const int cnt = c->kf[kf1].cand_count;
+    if (cnt > 0) {
+        sdm::k_pair_hypotheses<<<(cnt + sdm::kPass1Warps - 1) / sdm::kPass1Warps, sdm::kPass1Warps * 32, 0, c->s_compute>>>(
+            c->A, c->P, c->d_items, d, d + P, d + 2 * P, nullptr, dok, -1);
+        CU(cudaGetLastError());
+        c->launches++;
+    }
+    CU(cudaMemcpyAsync(hyp_depth, d, P * 4, cudaMemcpyDeviceToHost, c->s_compute));
+    CU(cudaMemcpyAsync(hyp_sigma, d + P, P * 4, cudaMemcpyDeviceToHost, c->s_compute));
+    CU(cudaMemcpyAsync(hyp_u, d + 2 * P, P * 4, cudaMemcpyDeviceToHost, c->s_compute));
+    CU(cudaMemcpyAsync(ok, dok, P, cudaMemcpyDeviceToHost, c->s_compute));
+    CU(cudaStreamSynchronize(c->s_compute));
+    return SDM_OK;
+}
+
+int sdm_fuse(sdm_ctx* c, int m, int n, const float* depth, const float* sigma, const int32_t* count, float* out_depth,
+             float* out_sigma, int32_t* out_supported)
+{
+    if (!c || !depth || !sigma || !count || !out_depth || !out_sigma || !out_supported) return fail(SDM_ERR_ARG, "null argument");
+    if (m <= 0) return SDM_OK;
+    if (n < 1 || n > 32) return fail(SDM_ERR_ARG, "set size %d out of [1,32]", n);
+    for (int i = 0; i < m; ++i)
+        if (count[i] < 0 || count[i] > n) return fail(SDM_ERR_ARG, "count[%d]=%d out of [0,%d]", i, count[i], n);
+    CU(cudaSetDevice(c->cfg.device));
+    cudaStream_t s = c->s_compute;
+    float *dd = nullptr, *ds = nullptr, *od = nullptr, *os = nullptr;
+    int *dc = nullptr, *ok = nullptr;
+    const size_t mn = (size_t)m * n;
+    CU(cudaMalloc(&dd, mn * 4)); CU(cudaMalloc(&ds, mn * 4)); CU(cudaMalloc(&dc, (size_t)m * 4));
+    CU(cudaMalloc(&od, (size_t)m * 4)); CU(cudaMalloc(&os, (size_t)m * 4)); CU(cudaMalloc(&ok, (size_t)m * 4));
+    CU(cudaMemcpyAsync(dd, depth, mn * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(ds, sigma, mn * 4, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpyAsync(dc, count, (size_t)m * 4, cudaMemcpyHostToDevice, s));
+    sdm::k_fuse_sets<<<(m + 7) / 8, 256, 0, s>>>(c->P, m, n, dd, ds, dc, od, os, ok);
+    CU(cudaGetLastError());
+    c->launches++;
+    CU(cudaMemcpyAsync(out_depth, od, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(out_sigma, os, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(out_supported, ok, (size_t)m * 4, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    cudaFree(dd); cudaFree(ds); cudaFree(dc); cudaFree(od); cudaFree(os); cudaFree(ok);
+    return SDM_OK;
+}
+
+int sdm_intra_check(sdm_ctx* c, int kf)
+{
+    if (!c) return fail(SDM_ERR_ARG, "null context");
+    if (!slot_ok(c, kf)) return fail(SDM_ERR_ARG, "keyframe slot %d out of range", kf);
+    if (!c->kf[kf].pass1_done) return fail(SDM_ERR_STATE, "slot %d has no pass-1 planes", kf);
+    CU(cudaSetDevice(c->cfg.device));
+    return run_intra(c, kf, true, false);
+}
+
+int sdm_intra_grow(sdm_ctx* c, int kf)
+{
+    if (!c) return fail(SDM_ERR_ARG, "null context");
+    if (!slot_ok(c, kf)) return fail(SDM_ERR_ARG, "keyframe slot %d out of range", kf);
+    if (!c->kf[kf].pass1_done || !c->kf[kf].uploaded) return fail(SDM_ERR_STATE, "slot %d has no pass-1 planes", kf);
+    CU(cudaSetDevice(c->cfg.device));
+    int rc = copy_then_compute(c);
+    if (rc) return rc;
+    return run_intra(c, kf, false, true);
+}
+
+int sdm_inter_check(sdm_ctx* c, const sdm_item* item)
+{
+    if (!c || !item) return fail(SDM_ERR_ARG, "null argument");
+    return sdm_pass2(c, 1, item);
+}
+
+// ---- measurement ---------------------------------------------------------------------------------
+int sdm_last_pass_ms(sdm_ctx* c, float* pass1_ms, float* pass2_ms)
+{
+    if (!c) return fail(SDM_ERR_ARG, "null context");
+    CU(cudaSetDevice(c->cfg.device));
+    if (pass1_ms) {
+        *pass1_ms = 0.f;
+        if (c->p1_timed) {
+            CU(cudaEventSynchronize(c->ev_p1[1]));
+            CU(cudaEventElapsedTime(pass1_ms, c->ev_p1[0], c->ev_p1[1]));
+        }
+    }
+    if (pass2_ms) {
+        *pass2_ms = 0.f;
+        if (c->p2_timed) {
+            CU(cudaEventSynchronize(c->ev_p2[1]));
+            CU(cudaEventElapsedTime(pass2_ms, c->ev_p2[0], c->ev_p2[1]));
+        }
+    }
+    return SDM_OK;
+}
+
+long long sdm_launch_count(sdm_ctx* c) { return c ? c->launches : 0; }
+
+}  // extern "C"

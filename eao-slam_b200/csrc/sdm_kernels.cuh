@@ -1,0 +1,776 @@
+// sdm_kernels.cuh — sm_100a kernels of the semi-dense mapping path.
+//
+// Reference being replaced: yanmin-wu/EAO-SLAM src/ProbabilityMapping.cc (line numbers cited per
+// function).  The arithmetic follows the reference operation by operation (float where the
+// reference is float, double where OpenCV accumulates in double); this translation unit MUST be
+// compiled with -fmad=false and default (IEEE) division / sqrt so that results are bit-identical
+// to a non-contracting CPU evaluation.  No tensor cores: the path is a gather + reduction.
+//
+// Data layout in HBM (per keyframe slot, P = W*H):
+//   tex    float4[P]  row-pair texel {G(y,x), G(y+1,x), Th(y,x), Th(y+1,x)}  (row H-1 pairs with itself)
+//   ipair  uchar2[P]  {I(y,x), I(y+1,x)}
+//   cand   u32[P]     compacted candidate pixels (y<<16 | x), count in cand_count[slot]
+//   rs     float2[P]  {rho, sigma} = depth_map_, depth_sigma_   (pass-1 output)
+//   chk    float[P]   depth_map_checked_                          (pass-2 output)
+//   pts    float[3P]  SemiDensePointSets_                         (pass-2 output)
+// The row-pair texel makes every ylinear/yangle evaluation of the epipolar scan (:66-111) one
+// 16-byte load + one 2-byte load, coalesced across the warp's consecutive columns.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sdm_b200.h"
+
+namespace sdm {
+
+struct DevParams {
+    int W, H;
+    float lambdaG, lambdaL, lambdaTheta;
+    int lambdaN;
+    float theta;      // (float)0.23
+    float inv_theta;  // 1 / (float)0.23 (float division)
+    float var_num;    // (2 * sigmaI) * sigmaI
+    float chi_fusion_lt;  // x < this  <=>  (double)x < 5.99
+    float chi_inter_lt;   // x < this  <=>  (double)x < 3.84
+    float eps_gt;         // x > this  <=>  (double)x > 0.000001
+    float eps_lt;         // x < this  <=>  (double)x < 0.000001
+    float slope_max;
+};
+
+struct DevArena {
+    float4* tex;
+    uchar2* ipair;
+    uint32_t* cand;
+    int* cand_count;
+    float2* rs;
+    float* chk;
+    float* pts;
+    size_t P;  // pixels per plane
+};
+
+struct DevPair {
+    float F[9];
+    float R[9];
+    float t[3];
+    float rot;
+    int slot;
+    int pad[3];
+};  // 28 words
+
+struct DevItem {
+    int kf;
+    int n_nbr;
+    float min_depth, max_depth;
+    float K[4];     // fx fy cx cy
+    float Twc[12];  // rows 0..2 of the inverse pose
+    DevPair pair[SDM_MAX_NBR];
+};
+static_assert(sizeof(DevItem) % 4 == 0, "word copy");
+
+struct DevStats {
+    unsigned long long candidates, fused, checked;
+};
+
+#define SDM_FULL 0xffffffffu
+
+// ---------------------------------------------------------------------------------------------
+// cv::fastAtan2 (used at :791), float polynomial in degrees
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fast_atan2_deg(float y, float x)
+{
+    const float scale = (float)(180.0 / 3.14159265358979323846);
+    const float p1 = 0.9997878412794807f * scale;
+    const float p3 = -0.3258083974640975f * scale;
+    const float p5 = 0.1555786518463281f * scale;
+    const float p7 = -0.04432655554792128f * scale;
+    const float eps = 2.220446049250313e-16f;
+    float ax = fabsf(x), ay = fabsf(y);
+    float a, c, c2;
+    if (ax >= ay) {
+        c = ay / (ax + eps);
+        c2 = c * c;
+        a = (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    } else {
+        c = ax / (ay + eps);
+        c2 = c * c;
+        a = 90.f - (((p7 * c2 + p5) * c2 + p3) * c2 + p1) * c;
+    }
+    if (x < 0) a = 180.f - a;
+    if (y < 0) a = 360.f - a;
+    return a;
+}
+
+// ---------------------------------------------------------------------------------------------
+// interpolators on the packed planes (ylinear<float>, ylinear<uchar>, yangle<float>; :66-111)
+// ---------------------------------------------------------------------------------------------
+struct RowW {
+    int y0;
+    float w0, w1;
+};
+__device__ __forceinline__ RowW row_weights(float v)
+{
+    RowW r;
+    float fl = floorf(v);
+    r.y0 = (int)fl;
+    r.w0 = (fl + 1.0f) - v;  // y1 - y  (y1 = y0 + 1 converted to float: exact)
+    r.w1 = v - fl;           // y - y0
+    return r;
+}
+__device__ __forceinline__ float ylin_grad(const float4* __restrict__ tex, int W, float v, int u)
+{
+    RowW r = row_weights(v);
+    float4 t = __ldg(&tex[(size_t)r.y0 * W + u]);
+    return t.x * r.w0 + t.y * r.w1;
+}
+__device__ __forceinline__ float ylin_im(const uchar2* __restrict__ ip, int W, float v, int u)
+{
+    RowW r = row_weights(v);
+    uchar2 i2 = __ldg(&ip[(size_t)r.y0 * W + u]);
+    return (float)i2.x * r.w0 + (float)i2.y * r.w1;
+}
+__device__ __forceinline__ float yangle_interp(float a0, float a1, float w0, float w1)
+{
+    if (fabsf(a0 - a1) < 180.f) {
+        return a0 * w0 + a1 * w1;
+    } else {
+        if (a0 < a1) a0 += 360.f; else a1 += 360.f;
+        float inter = a0 * w0 + a1 * w1;
+        if (inter >= 360.f) inter -= 360.f;
+        return inter;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-(pixel, neighbour) set-up: epipolar line (:753-757), GetSearchRange (:1598-1631), the
+// loop-invariant fastAtan2 of :791 and the wrapped th_pi + rot of :801-803
+// ---------------------------------------------------------------------------------------------
+struct PairSetup {
+    float ab, cb;      // a/b, c/b
+    int u_lo, u_hi;    // scan bounds, already restricted to 1 <= u <= W-2 (:778-779)
+    float th_line;
+    float ang_pi_rot;
+    bool valid;
+};
+
+__device__ __forceinline__ float wrap360(float a)
+{
+    if (a >= 360.f) a -= 360.f;
+    if (a < 0.f) a += 360.f;
+    return a;
+}
+
+__device__ __forceinline__ void search_range(const DevPair& g, const float* K, int W, float xn, float yn,
+                                             float mind, float maxd, float& umin, float& umax)
+{
+    const float fx = K[0], cx = K[2];
+    // R21*xp1*d + t21 : one gemm, float dot then double scale-add (only rows 0 and 2 are used)
+    float s0 = g.R[0] * xn + g.R[1] * yn + g.R[2] * 1.0f;
+    float s2 = g.R[6] * xn + g.R[7] * yn + g.R[8] * 1.0f;
+    float x0min = (float)((double)s0 * (double)mind + (double)g.t[0]);
+    float x2min = (float)((double)s2 * (double)mind + (double)g.t[2]);
+    float x0max = (float)((double)s0 * (double)maxd + (double)g.t[0]);
+    float x2max = (float)((double)s2 * (double)maxd + (double)g.t[2]);
+    umin = fx * x0min / x2min + cx;
+    umax = fx * x0max / x2max + cx;
+    if (umin > umax) { float t = umax; umax = umin; umin = t; }
+    if (umin < 0) umin = 0;
+    if (umax < 0) umax = 0;
+    if (umin > W) umin = W - 1;
+    if (umax > W) umax = W - 1;
+}
+
+__device__ __forceinline__ PairSetup pair_setup(const DevPair& g, const float* K, const DevParams& P, int x, int y,
+                                                float xn, float yn, float mind, float maxd, float th_pi)
+{
+    PairSetup s;
+    float a = x * g.F[0] + y * g.F[3] + g.F[6];
+    float b = x * g.F[1] + y * g.F[4] + g.F[7];
+    float c = x * g.F[2] + y * g.F[5] + g.F[8];
+    s.ab = a / b;
+    s.cb = c / b;
+    s.valid = (s.ab >= -P.slope_max) && (s.ab <= P.slope_max);  // NaN -> invalid
+    float umin, umax;
+    search_range(g, K, P.W, xn, yn, mind, maxd, umin, umax);
+    s.valid = s.valid && (umin == umin) && (umax == umax);
+    int lo = (int)ceilf(umin), hi = (int)floorf(umax);
+    s.u_lo = lo < 1 ? 1 : lo;                  // uj - 1 < mnMinX -> continue
+    s.u_hi = hi > P.W - 2 ? P.W - 2 : hi;      // uj + 1 >= mnMaxX -> continue
+    if (!s.valid) { s.u_lo = 1; s.u_hi = 0; }
+    s.th_line = fast_atan2_deg(-s.ab, 1.0f);
+    s.ang_pi_rot = wrap360(th_pi + g.rot);
+    return s;
+}
+
+// one candidate column of the scan body (:772-821).  Returns false if the candidate is skipped.
+__device__ __forceinline__ bool eval_candidate(const float4* __restrict__ tex2, const uchar2* __restrict__ ip2,
+                                               const DevParams& P, float Hm1, int u, float ab, float cb,
+                                               float th_line, float ang_pi_rot, float pixel, float gradc,
+                                               float& err, float& pe, float& ge)
+{
+    const float uf = (float)u;
+    const float v = -(ab * uf + cb);
+    const float vp = -(ab * (uf + 1.0f) + cb);
+    const float vm = -(ab * (uf - 1.0f) + cb);
+    // floor(v) < 0 || ceil(v) >= rows  <=>  !(0 <= v <= rows-1), same for vj_plus / vj_minus
+    if (!(v >= 0.f && v <= Hm1 && vp >= 0.f && vp <= Hm1 && vm >= 0.f && vm <= Hm1)) return false;
+    const RowW r = row_weights(v);
+    const size_t idx = (size_t)r.y0 * P.W + u;
+    const float4 t = __ldg(&tex2[idx]);
+    const float g2 = t.x * r.w0 + t.y * r.w1;
+    if (g2 <= P.lambdaG) return false;  // condition 1
+    const float gth = yangle_interp(t.z, t.w, r.w0, r.w1);
+    float ang = gth - th_line;  // condition 2
+    if (ang >= 360.f) ang -= 360.f;
+    if (ang < 0.f) ang += 360.f;
+    if (ang > 180.f) ang = 360.f - ang;
+    if (ang > 90.f) ang = 180.f - ang;
+    if (ang >= P.lambdaL) return false;
+    float thd = gth - ang_pi_rot;  // condition 3
+    if (thd >= 360.f) thd -= 360.f;
+    if (thd < 0.f) thd += 360.f;
+    if (thd > 180.f) thd = 360.f - thd;
+    if (thd >= P.lambdaTheta) return false;
+    const uchar2 i2 = __ldg(&ip2[idx]);
+    pe = pixel - ((float)i2.x * r.w0 + (float)i2.y * r.w1);
+    ge = gradc - g2;
+    err = pe * pe + (ge * ge) / P.theta;
+    return true;
+}
+
+// GetPixelDepth, equation 8 (:1568-1596).  s2d/s0d are the double-accumulated row products.
+__device__ __forceinline__ float pixel_inv_depth(float u, double s2d, double s0d, const DevPair& g, const float* K)
+{
+    const float fx = K[0], cx = K[2];
+    float ucx = u - cx;
+    float num1 = (float)(s2d * (double)ucx);
+    float num2 = (float)(s0d * (double)fx);
+    float denom1 = -g.t[2] * ucx;
+    float denom2 = fx * g.t[0];
+    return (num1 - num2) / (denom1 + denom2);
+}
+
+// sub-pixel refinement (:823-840) + ComputeInvDepthHypothesis (:1310-1335) at the best column
+struct Hypo {
+    float depth, sigma, best_u, best_v;
+};
+__device__ __forceinline__ Hypo refine_hypothesis(const float4* __restrict__ tex2, const uchar2* __restrict__ ip2,
+                                                  const DevPair& g, const float* K, const DevParams& P, int best,
+                                                  float ab, float cb, float pe, float ge, float xn, float yn)
+{
+    const int up = best + 1, um = best - 1;
+    const float vp = -(ab * (float)up + cb);
+    const float vm = -(ab * (float)um + cb);
+    const float gI = (ylin_im(ip2, P.W, vp, up) - ylin_im(ip2, P.W, vm, um)) / 2;
+    const float q = (ylin_grad(tex2, P.W, vp, up) - ylin_grad(tex2, P.W, vm, um)) / 2;
+    const float den = gI * gI + P.inv_theta * q * q;
+    const float ustar = (float)best + (gI * pe + P.inv_theta * q * ge) / den;
+    const float var = P.var_num / den;
+    Hypo h;
+    h.best_u = ustar;
+    h.best_v = -(ab * ustar + cb);
+    // R21.row(k) * xp : 1x3 * 3x1 gemm -> double accumulation
+    const double s2d = (double)g.R[6] * (double)xn + (double)g.R[7] * (double)yn + (double)g.R[8] * 1.0;
+    const double s0d = (double)g.R[0] * (double)xn + (double)g.R[1] * (double)yn + (double)g.R[2] * 1.0;
+    const float sd = sqrtf(var);
+    const float rho = pixel_inv_depth(ustar, s2d, s0d, g, K);
+    const float rho_min = pixel_inv_depth(ustar - sd, s2d, s0d, g, K);
+    const float rho_max = pixel_inv_depth(ustar + sd, s2d, s0d, g, K);
+    const float s1 = fabsf(rho_max - rho), s2 = fabsf(rho_min - rho);
+    h.depth = rho;
+    h.sigma = (s1 < s2) ? s2 : s1;  // cv::max == std::max
+    return h;
+}
+
+// ChiTest (:1633-1645)
+__device__ __forceinline__ bool chi_compatible(float a, float b, float sa, float sb, float thr_lt)
+{
+    float num = (a - b) * (a - b);
+    float chi = num / (sa * sa) + num / (sb * sb);
+    return chi < thr_lt;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1 + K2: plane packing + candidate compaction (KeyFrame.cc:63-88 planes as device buffers;
+// the candidate test of :454-456).  One thread per pixel, 32x8 tiles; one atomic per tile so a
+// tile's candidates stay contiguous (2-D locality for the scan kernel).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_pack(DevArena A, DevParams P, int slot, const uint8_t* __restrict__ im,
+                                              const float* __restrict__ grad, const float* __restrict__ theta,
+                                              const int32_t* __restrict__ edge)
+{
+    __shared__ int s_wcount[8];
+    __shared__ int s_base;
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    const int warp = threadIdx.y, lane = threadIdx.x;
+    const bool in = (x < P.W) && (y < P.H);
+    bool is_cand = false;
+    const size_t base = (size_t)slot * A.P;
+    if (in) {
+        const int y1 = (y + 1 < P.H) ? y + 1 : P.H - 1;
+        const size_t i0 = (size_t)y * P.W + x, i1 = (size_t)y1 * P.W + x;
+        const float g0 = grad[i0], g1 = grad[i1];
+        A.tex[base + i0] = make_float4(g0, g1, theta[i0], theta[i1]);
+        A.ipair[base + i0] = make_uchar2(im[i0], im[i1]);
+        A.rs[base + i0] = make_float2(0.f, 0.f);
+        is_cand = (edge == nullptr || edge[i0] >= 0) && !(g0 <= P.lambdaG);
+    }
+    const unsigned bal = __ballot_sync(SDM_FULL, is_cand);
+    if (lane == 0) s_wcount[warp] = __popc(bal);
+    __syncthreads();
+    if (warp == 0 && lane == 0) {
+        int tot = 0;
+        for (int w = 0; w < 8; ++w) { int c = s_wcount[w]; s_wcount[w] = tot; tot += c; }
+        s_base = tot ? atomicAdd(&A.cand_count[slot], tot) : 0;
+    }
+    __syncthreads();
+    if (is_cand) {
+        const int pos = s_base + s_wcount[warp] + __popc(bal & ((1u << lane) - 1u));
+        A.cand[base + pos] = ((uint32_t)y << 16) | (uint32_t)x;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3 + K4: warp-per-pixel epipolar scan + hypothesis fusion (hot loop 1, :447-489)
+//   phase A  lane j sets up neighbour j (line, search range, invariants)
+//   phase B  for each neighbour: 32 lanes stride the columns of the search range, argmin by shuffles
+//   phase C  lane j refines neighbour j's best column into a hypothesis (rho, sigma)
+//   phase D  chi-square compatibility sets across lanes, first-largest set, weighted fusion
+// ---------------------------------------------------------------------------------------------
+constexpr int kPass1Warps = 8;
+
+__global__ void __launch_bounds__(kPass1Warps * 32)
+k_pass1(DevArena A, DevParams P, const DevItem* __restrict__ items, const int* __restrict__ blk_off, int n_items,
+        DevStats* stats)
+{
+    __shared__ DevItem s_item;
+    // block -> item (blocks never straddle items)
+    int lo = 0, hi = n_items;
+    const int bid = blockIdx.x;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (blk_off[mid] <= bid) lo = mid; else hi = mid;
+    }
+    {
+        const int* src = reinterpret_cast<const int*>(&items[lo]);
+        int* dst = reinterpret_cast<int*>(&s_item);
+        const int header = (int)(offsetof(DevItem, pair) / 4);
+        const int words = header + items[lo].n_nbr * (int)(sizeof(DevPair) / 4);
+        for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int ci = (bid - blk_off[lo]) * kPass1Warps + warp;
+    const int kf = s_item.kf;
+    if (ci >= A.cand_count[kf]) return;
+    const int N = s_item.n_nbr;
+    const uint32_t packed = A.cand[(size_t)kf * A.P + ci];
+    const int x = (int)(packed & 0xffffu), y = (int)(packed >> 16);
+
+    const float4 t1 = __ldg(&A.tex[(size_t)kf * A.P + (size_t)y * P.W + x]);
+    const float gradc = t1.x, th_pi = t1.z;
+    const float pixel = (float)__ldg(&A.ipair[(size_t)kf * A.P + (size_t)y * P.W + x]).x;
+    const float* K = s_item.K;
+    const float xn = (x - K[2]) / K[0], yn = (y - K[3]) / K[1];
+    const float Hm1 = (float)(P.H - 1);
+
+    // phase A
+    PairSetup my;
+    my.valid = false; my.u_lo = 1; my.u_hi = 0; my.ab = 0.f; my.cb = 0.f; my.th_line = 0.f; my.ang_pi_rot = 0.f;
+    if (lane < N) my = pair_setup(s_item.pair[lane], K, P, x, y, xn, yn, s_item.min_depth, s_item.max_depth, th_pi);
+
+    // phase B
+    int my_best = -1;  // lane j: best column of neighbour j (or -1)
+    for (int j = 0; j < N; ++j) {
+        const int u_lo = __shfl_sync(SDM_FULL, my.u_lo, j);
+        const int u_hi = __shfl_sync(SDM_FULL, my.u_hi, j);
+        if (u_lo > u_hi) continue;
+        const float ab = __shfl_sync(SDM_FULL, my.ab, j);
+        const float cb = __shfl_sync(SDM_FULL, my.cb, j);
+        const float th_line = __shfl_sync(SDM_FULL, my.th_line, j);
+        const float apr = __shfl_sync(SDM_FULL, my.ang_pi_rot, j);
+        const size_t nb = (size_t)s_item.pair[j].slot * A.P;
+        const float4* tex2 = A.tex + nb;
+        const uchar2* ip2 = A.ipair + nb;
+        float best_err = 100000.0f;
+        int best_u = 0x7fffffff;
+        for (int u = u_lo + lane; u <= u_hi; u += 32) {
+            float err, pe, ge;
+            if (eval_candidate(tex2, ip2, P, Hm1, u, ab, cb, th_line, apr, pixel, gradc, err, pe, ge)) {
+                if (err < best_err) { best_err = err; best_u = u; }
+            }
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const float oe = __shfl_xor_sync(SDM_FULL, best_err, off);
+            const int ou = __shfl_xor_sync(SDM_FULL, best_u, off);
+            if (oe < best_err || (oe == best_err && ou < best_u)) { best_err = oe; best_u = ou; }
+        }
+        if (lane == j && best_err < 100000.0f) my_best = best_u;
+    }
+
+    // phase C
+    float hd = 0.f, hs = 0.f;
+    bool keep = false;
+    if (my_best >= 0) {
+        const DevPair& g = s_item.pair[lane];
+        const size_t nb = (size_t)g.slot * A.P;
+        float err, pe, ge;
+        eval_candidate(A.tex + nb, A.ipair + nb, P, Hm1, my_best, my.ab, my.cb, my.th_line, my.ang_pi_rot, pixel,
+                       gradc, err, pe, ge);
+        Hypo h = refine_hypothesis(A.tex + nb, A.ipair + nb, g, K, P, my_best, my.ab, my.cb, pe, ge, xn, yn);
+        hd = h.depth;
+        hs = h.sigma;
+        keep = (1.0f / hd > 0.0f);  // :472
+    }
+
+    // phase D: InverseDepthHypothesisFusion (:978-1009)
+    const unsigned vmask = __ballot_sync(SDM_FULL, keep);
+    float out_d = 0.f, out_s = 0.f;
+    bool fused = false;
+    if (__popc(vmask) > P.lambdaN) {
+        unsigned m = 0;
+        for (unsigned rem = vmask; rem; rem &= rem - 1) {
+            const int b = __ffs(rem) - 1;
+            const float db = __shfl_sync(SDM_FULL, hd, b);
+            const float sb = __shfl_sync(SDM_FULL, hs, b);
+            if (keep && (b == lane || chi_compatible(hd, db, hs, sb, P.chi_fusion_lt))) m |= 1u << b;
+        }
+        int key = keep ? ((__popc(m) << 8) | (31 - lane)) : 0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) key = max(key, __shfl_xor_sync(SDM_FULL, key, off));
+        const int best_n = key >> 8, winner = 31 - (key & 0xff);
+        if (best_n > P.lambdaN) {
+            const unsigned wm = __shfl_sync(SDM_FULL, m, winner);
+            // GetFusion (:1669-1692): per-lane double terms, then the reference's sequential float sums
+            double q1 = 0.0, q2 = 0.0;
+            if (keep) {
+                const double s2 = (double)hs * (double)hs;
+                q1 = (double)hd / s2;
+                q2 = 1.0 / s2;
+            }
+            float pjsj = 0.f, rsj = 0.f;
+            for (unsigned rem = wm; rem; rem &= rem - 1) {
+                const int b = __ffs(rem) - 1;
+                const double t1d = __shfl_sync(SDM_FULL, q1, b);
+                const double t2d = __shfl_sync(SDM_FULL, q2, b);
+                pjsj = (float)((double)pjsj + t1d);
+                rsj = (float)((double)rsj + t2d);
+            }
+            out_d = pjsj / rsj;
+            out_s = sqrtf(1.0f / rsj);
+            fused = true;
+        }
+    }
+    if (lane == 0) {
+        A.rs[(size_t)kf * A.P + (size_t)y * P.W + x] = make_float2(out_d, out_s);
+        if (fused && stats) atomicAdd(&stats->fused, 1ULL);
+    }
+}
+
+// per-pair raw hypotheses for every candidate pixel of kf1 (granularity of one EpipolarSearch call)
+__global__ void __launch_bounds__(kPass1Warps * 32)
+k_pair_hypotheses(DevArena A, DevParams P, const DevItem* __restrict__ item, float* __restrict__ hyp_d,
+                  float* __restrict__ hyp_s, float* __restrict__ hyp_u, float* __restrict__ hyp_v,
+                  uint8_t* __restrict__ hyp_ok, int single_xy)
+{
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kf = item->kf;
+    int x, y;
+    size_t out;
+    if (single_xy >= 0) {
+        if (blockIdx.x != 0 || warp != 0) return;
+        x = single_xy & 0xffff; y = single_xy >> 16; out = 0;
+    } else {
+        const int ci = blockIdx.x * kPass1Warps + warp;
+        if (ci >= A.cand_count[kf]) return;
+        const uint32_t packed = A.cand[(size_t)kf * A.P + ci];
+        x = (int)(packed & 0xffffu); y = (int)(packed >> 16);
+        out = (size_t)y * P.W + x;
+    }
+    const DevPair g = item->pair[0];
+    const float K[4] = {item->K[0], item->K[1], item->K[2], item->K[3]};
+    const float4 t1 = __ldg(&A.tex[(size_t)kf * A.P + (size_t)y * P.W + x]);
+    const float gradc = t1.x, th_pi = t1.z;
+    const float pixel = (float)__ldg(&A.ipair[(size_t)kf * A.P + (size_t)y * P.W + x]).x;
+    const float xn = (x - K[2]) / K[0], yn = (y - K[3]) / K[1];
+    const float Hm1 = (float)(P.H - 1);
+    const PairSetup s = pair_setup(g, K, P, x, y, xn, yn, item->min_depth, item->max_depth, th_pi);
+    const size_t nb = (size_t)g.slot * A.P;
+    float best_err = 100000.0f;
+    int best_u = 0x7fffffff;
+    for (int u = s.u_lo + lane; u <= s.u_hi; u += 32) {
+        float err, pe, ge;
+        if (eval_candidate(A.tex + nb, A.ipair + nb, P, Hm1, u, s.ab, s.cb, s.th_line, s.ang_pi_rot, pixel, gradc,
+                           err, pe, ge))
+            if (err < best_err) { best_err = err; best_u = u; }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        const float oe = __shfl_xor_sync(SDM_FULL, best_err, off);
+        const int ou = __shfl_xor_sync(SDM_FULL, best_u, off);
+        if (oe < best_err || (oe == best_err && ou < best_u)) { best_err = oe; best_u = ou; }
+    }
+    if (lane != 0) return;
+    float d = 0.f, sg = 0.f, bu = 0.f, bv = 0.f;
+    uint8_t ok = 0;
+    if (best_err < 100000.0f) {
+        float err, pe, ge;
+        eval_candidate(A.tex + nb, A.ipair + nb, P, Hm1, best_u, s.ab, s.cb, s.th_line, s.ang_pi_rot, pixel, gradc,
+                       err, pe, ge);
+        Hypo h = refine_hypothesis(A.tex + nb, A.ipair + nb, g, K, P, best_u, s.ab, s.cb, pe, ge, xn, yn);
+        d = h.depth; sg = h.sigma; bu = h.best_u; bv = h.best_v;
+        ok = (1.0f / d > 0.0f) ? 2 : 1;
+    }
+    hyp_d[out] = d; hyp_s[out] = sg; hyp_u[out] = bu; hyp_ok[out] = ok;
+    if (hyp_v) hyp_v[out] = bv;
+}
+
+__global__ void k_search_range(DevParams P, const DevItem* __restrict__ item, int px, int py, float* out)
+{
+    const float* K = item->K;
+    const float xn = (px - K[2]) / K[0], yn = (py - K[3]) / K[1];
+    float umin, umax;
+    search_range(item->pair[0], K, P.W, xn, yn, item->min_depth, item->max_depth, umin, umax);
+    out[0] = umin;
+    out[1] = umax;
+}
+
+// InverseDepthHypothesisFusion for m independent sets (one warp per set)
+__global__ void __launch_bounds__(256) k_fuse_sets(DevParams P, int m, int n, const float* __restrict__ depth,
+                                                   const float* __restrict__ sigma, const int* __restrict__ count,
+                                                   float* __restrict__ out_d, float* __restrict__ out_s,
+                                                   int* __restrict__ out_ok)
+{
+    const int set = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (set >= m) return;
+    const int cnt = count[set];
+    const bool keep = lane < cnt;
+    const float hd = keep ? depth[(size_t)set * n + lane] : 0.f;
+    const float hs = keep ? sigma[(size_t)set * n + lane] : 0.f;
+    const unsigned vmask = __ballot_sync(SDM_FULL, keep);
+    float od = 0.f, os = 0.f;
+    int ok = 0;
+    unsigned mm = 0;
+    for (unsigned rem = vmask; rem; rem &= rem - 1) {
+        const int b = __ffs(rem) - 1;
+        const float db = __shfl_sync(SDM_FULL, hd, b);
+        const float sb = __shfl_sync(SDM_FULL, hs, b);
+        if (keep && (b == lane || chi_compatible(hd, db, hs, sb, P.chi_fusion_lt))) mm |= 1u << b;
+    }
+    int key = keep ? ((__popc(mm) << 8) | (31 - lane)) : 0;
+    for (int off = 16; off > 0; off >>= 1) key = max(key, __shfl_xor_sync(SDM_FULL, key, off));
+    const int best_n = key >> 8, winner = 31 - (key & 0xff);
+    if (best_n > P.lambdaN) {
+        const unsigned wm = __shfl_sync(SDM_FULL, mm, winner);
+        double q1 = 0.0, q2 = 0.0;
+        if (keep) { const double s2 = (double)hs * (double)hs; q1 = (double)hd / s2; q2 = 1.0 / s2; }
+        float pjsj = 0.f, rsj = 0.f;
+        for (unsigned rem = wm; rem; rem &= rem - 1) {
+            const int b = __ffs(rem) - 1;
+            pjsj = (float)((double)pjsj + __shfl_sync(SDM_FULL, q1, b));
+            rsj = (float)((double)rsj + __shfl_sync(SDM_FULL, q2, b));
+        }
+        od = pjsj / rsj; os = sqrtf(1.0f / rsj); ok = 1;
+    }
+    if (lane == 0) { out_d[set] = od; out_s[set] = os; out_ok[set] = ok; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K5: IntraKeyFrameDepthChecking (:866-927) and IntraKeyFrameDepthGrowing (:929-976): 3x3 Jacobi
+// stencils on the (rho, sigma) plane; src is a snapshot of the plane, dst the plane itself.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void fusion_accumulate(float d, float s, float& pjsj, float& rsj)
+{
+    const double s2 = (double)s * (double)s;
+    pjsj = (float)((double)pjsj + (double)d / s2);
+    rsj = (float)((double)rsj + 1.0 / s2);
+}
+
+__global__ void __launch_bounds__(256) k_intra_check(DevParams P, const float2* __restrict__ src, float2* __restrict__ dst)
+{
+    const int px = blockIdx.x * 32 + threadIdx.x, py = blockIdx.y * 8 + threadIdx.y;
+    if (px < 2 || py < 2 || px >= P.W - 2 || py >= P.H - 2) return;
+    const float2 c = src[(size_t)py * P.W + px];
+    if (!(c.x > P.eps_gt)) return;
+    float pjsj = 0.f, rsj = 0.f, min_sigma = 0.f;
+    int n = 0;
+    for (int y = py - 1; y <= py + 1; ++y)
+        for (int x = px - 1; x <= px + 1; ++x) {
+            if (x == px && y == py) continue;
+            const float2 q = src[(size_t)y * P.W + x];
+            if (q.x > P.eps_gt && chi_compatible(q.x, c.x, q.y, c.y, P.chi_fusion_lt)) {
+                if (n == 0) min_sigma = q.y;
+                fusion_accumulate(q.x, q.y, pjsj, rsj);
+                // pow(sigma,2) < pow(min,2) in double == |sigma| < |min|
+                if ((double)q.y * (double)q.y < (double)min_sigma * (double)min_sigma) min_sigma = q.y;
+                ++n;
+            }
+        }
+    if (n == 0) min_sigma = c.y;
+    fusion_accumulate(c.x, c.y, pjsj, rsj);  // "dont forget itself" :902 (pushed last)
+    if ((double)c.y * (double)c.y < (double)min_sigma * (double)min_sigma) min_sigma = c.y;
+    ++n;
+    if (n >= 3)
+        dst[(size_t)py * P.W + px] = make_float2(pjsj / rsj, min_sigma);
+    else
+        dst[(size_t)py * P.W + px] = make_float2(0.f, 0.f);
+}
+
+__global__ void __launch_bounds__(256) k_intra_grow(DevParams P, const float2* __restrict__ src, float2* __restrict__ dst,
+                                                    const float4* __restrict__ tex)
+{
+    const int px = blockIdx.x * 32 + threadIdx.x, py = blockIdx.y * 8 + threadIdx.y;
+    if (px < 2 || py < 2 || px >= P.W - 2 || py >= P.H - 2) return;
+    const float2 c = src[(size_t)py * P.W + px];
+    if (!(c.x < P.eps_lt)) return;
+    if (tex[(size_t)py * P.W + px].x <= P.lambdaG) return;
+    float pjsj = 0.f, rsj = 0.f, min_sigma = 0.f;
+    int n = 0;
+    for (int y = py - 1; y <= py + 1; ++y)
+        for (int x = px - 1; x <= px + 1; ++x) {
+            if (x == px && y == py) continue;
+            const float2 q = src[(size_t)y * P.W + x];
+            if (chi_compatible(q.x, c.x, q.y, c.y, P.chi_fusion_lt)) {
+                if (n == 0) min_sigma = q.y;
+                fusion_accumulate(q.x, q.y, pjsj, rsj);
+                if (q.y < min_sigma) min_sigma = q.y;
+                ++n;
+            }
+        }
+    if (n >= 2) dst[(size_t)py * P.W + px] = make_float2(pjsj / rsj, min_sigma);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K6: InterKeyFrameDepthChecking (:1121-1296) fused with UpdateSemiDensePointSet (:700-731).
+// One thread per pixel; blocks of 256 consecutive pixels of one keyframe (grid.y = item).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void write_point(const DevItem& it, const DevParams& P, float* __restrict__ pts, size_t pi,
+                                            int x, int y, float checked)
+{
+    float X = 0.f, Y = 0.f, Z = 0.f;
+    if (!(checked < P.eps_lt)) {
+        const float z = 1.0f / checked;
+        const float xc = z * (x - it.K[2]) / it.K[0];
+        const float yc = z * (y - it.K[3]) / it.K[1];
+        const float* T = it.Twc;
+        X = T[0] * xc + T[1] * yc + T[2] * z + T[3] * 1.0f;
+        Y = T[4] * xc + T[5] * yc + T[6] * z + T[7] * 1.0f;
+        Z = T[8] * xc + T[9] * yc + T[10] * z + T[11] * 1.0f;
+    }
+    pts[3 * pi + 0] = X;
+    pts[3 * pi + 1] = Y;
+    pts[3 * pi + 2] = Z;
+}
+
+__global__ void __launch_bounds__(256)
+k_pass2(DevArena A, DevParams P, const DevItem* __restrict__ items, DevStats* stats, int points_only)
+{
+    __shared__ DevItem s_item;
+    {
+        const int* src = reinterpret_cast<const int*>(&items[blockIdx.y]);
+        int* dst = reinterpret_cast<int*>(&s_item);
+        const int header = (int)(offsetof(DevItem, pair) / 4);
+        const int words = header + items[blockIdx.y].n_nbr * (int)(sizeof(DevPair) / 4);
+        for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const size_t p = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (p >= A.P) return;
+    const int py = (int)(p / P.W), px = (int)(p % P.W);
+    const int kf = s_item.kf;
+    const size_t base = (size_t)kf * A.P;
+    const int cols = P.W, rows = P.H;
+    const bool interior = (px >= 2 && py >= 2 && px < cols - 2 && py < rows - 2);
+    if (points_only) {
+        if (interior) write_point(s_item, P, A.pts + 3 * base, p, px, py, A.chk[base + p]);
+        return;
+    }
+    float checked = 0.f;
+    if (interior) {
+        const float depthp = A.rs[base + p].x;
+        if (!(depthp < P.eps_lt)) {
+            const float fx = s_item.K[0], fy = s_item.K[1], cx = s_item.K[2], cy = s_item.K[3];
+            const float xn = (px - cx) / fx, yn = (py - cy) / fy;
+            const float dp = 1.0f / depthp;
+            const double alpha = (double)(float)(1.0 / (double)depthp);  // gemm alpha is cast to float
+            int support = 0;
+            double JtR = 0.0, JtJ = 0.0;
+            const int N = s_item.n_nbr;
+            for (int j = 0; j < N; ++j) {
+                const DevPair& g = s_item.pair[j];
+                // temp = Rji*xp/depthp + tji ; Xj = K*temp ; Xj/Xj(2)
+                const float s0 = g.R[0] * xn + g.R[1] * yn + g.R[2] * 1.0f;
+                const float s1 = g.R[3] * xn + g.R[4] * yn + g.R[5] * 1.0f;
+                const float s2 = g.R[6] * xn + g.R[7] * yn + g.R[8] * 1.0f;
+                const float X0 = (float)((double)s0 * alpha + (double)g.t[0]);
+                const float X1 = (float)((double)s1 * alpha + (double)g.t[1]);
+                const float X2 = (float)((double)s2 * alpha + (double)g.t[2]);
+                const float U = fx * X0 + 0.f * X1 + cx * X2;
+                const float V = 0.f * X0 + fy * X1 + cy * X2;
+                const float Wz = 0.f * X0 + 0.f * X1 + 1.0f * X2;
+                const float iz = (float)(1.0 / (double)Wz);
+                const float xj = U * iz, yj = V * iz;
+                // Eq (12)
+                const float rz = (float)((double)g.R[6] * (double)xn + (double)g.R[7] * (double)yn + (double)g.R[8] * 1.0);
+                const float depthj = depthp / (rz + depthp * g.t[2]);
+                if (!(xj >= 0.f && xj < (float)(cols - 1) && yj >= 0.f && yj < (float)(rows - 1))) continue;
+                const int x0 = (int)floorf(xj), y0 = (int)floorf(yj);
+                const float2* nrs = A.rs + (size_t)g.slot * A.P;
+                const float2 q00 = __ldg(&nrs[(size_t)y0 * cols + x0]);
+                const float2 q10 = __ldg(&nrs[(size_t)(y0 + 1) * cols + x0]);
+                const float2 q01 = __ldg(&nrs[(size_t)y0 * cols + x0 + 1]);
+                const float2 q11 = __ldg(&nrs[(size_t)(y0 + 1) * cols + x0 + 1]);
+                const float2 q[4] = {q00, q10, q01, q11};  // (y0,x0) (y1,x0) (y0,x1) (y1,x1)
+                int nj = 0;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float d = q[k].x, sg = q[k].y;
+                    if (d > P.eps_gt) {
+                        const double dd = (double)(depthj - d);
+                        const float test = (float)((dd * dd) / ((double)sg * (double)sg));
+                        if (test < P.chi_inter_lt) {
+                            ++nj;
+                            // Gauss-Newton terms (:1274-1280), accumulated in the reference's order
+                            const float djn = 1.0f / d;
+                            const float d2sigma = djn * djn * sg;
+                            const float Ji = -rz / d2sigma;
+                            const float ri = (djn - dp * rz - g.t[2]) / d2sigma;
+                            JtR += (double)Ji * (double)ri;
+                            JtJ += (double)Ji * (double)Ji;
+                        }
+                    }
+                }
+                if (nj >= 1) ++support;
+            }
+            if (support >= P.lambdaN) {
+                const float Jtr0 = (float)(JtR * -1.0);
+                const float JtJf = (float)(JtJ * 1.0);
+                const float dpDelta = Jtr0 / JtJf;
+                checked = 1.0f / (dp + dpDelta);
+            }
+        }
+    }
+    A.chk[base + p] = checked;
+    write_point(s_item, P, A.pts + 3 * base, p, px, py, interior ? checked : 0.f);
+    if (stats) {
+        const unsigned bal = __ballot_sync(__activemask(), checked > 0.f);
+        if ((threadIdx.x & 31) == 0 && bal) atomicAdd(&stats->checked, (unsigned long long)__popc(bal));
+    }
+}
+
+// (rho, sigma) float2 plane -> two dense float planes (download staging), and back
+__global__ void k_split_rs(const float2* __restrict__ rs, float* __restrict__ d, float* __restrict__ s, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { float2 v = rs[i]; d[i] = v.x; s[i] = v.y; }
+}
+__global__ void k_merge_rs(float2* __restrict__ rs, const float* __restrict__ d, const float* __restrict__ s, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) rs[i] = make_float2(d[i], s[i]);
+}
+
+}  // namespace sdm

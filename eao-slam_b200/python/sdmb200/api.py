@@ -1,0 +1,347 @@
+"""ctypes binding of libsdm_b200.so (include/sdm_b200.h) — harness-side only.
+
+The product is the C-ABI library; this module is what tests/ and bench.py use to reach it from
+Python.  There is no CPU fallback here either: a missing library or a missing CUDA device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+SDM_MAX_NBR = 16
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "lib", "libsdm_b200.so"))
+
+
+class SdmError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"sdm error {code}: {msg}")
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("width", C.c_int), ("height", C.c_int), ("max_keyframes", C.c_int),
+        ("lambdaG", C.c_int), ("lambdaL", C.c_int), ("lambdaTheta", C.c_int), ("lambdaN", C.c_int),
+        ("theta", C.c_float), ("sigmaI", C.c_float),
+        ("chi2_fusion", C.c_double), ("chi2_inter", C.c_double), ("eps", C.c_double),
+        ("slope_max", C.c_float), ("intra_check", C.c_int), ("intra_grow", C.c_int), ("device", C.c_int),
+    ]
+
+
+class Item(C.Structure):
+    _fields_ = [
+        ("kf", C.c_int32), ("n_nbr", C.c_int32), ("nbr", C.c_int32 * SDM_MAX_NBR),
+        ("rot_deg", C.c_float * SDM_MAX_NBR), ("min_depth", C.c_float), ("max_depth", C.c_float),
+    ]
+
+
+class PairGeometry(C.Structure):
+    _fields_ = [("R21", C.c_float * 9), ("t21", C.c_float * 3), ("F12", C.c_float * 9)]
+
+
+class Hypothesis(C.Structure):
+    _fields_ = [("depth", C.c_float), ("sigma", C.c_float), ("supported", C.c_int32),
+                ("best_u", C.c_float), ("best_v", C.c_float)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("candidates", C.c_longlong), ("fused", C.c_longlong), ("checked", C.c_longlong)]
+
+
+# every symbol include/sdm_b200.h declares (checked by tests/test_abi.py)
+EXPORTS = [
+    "sdm_default_config", "sdm_create", "sdm_destroy", "sdm_last_error", "sdm_version", "sdm_synchronize",
+    "sdm_get_stats", "sdm_host_alloc", "sdm_host_free", "sdm_upload_keyframe", "sdm_set_pose",
+    "sdm_set_intrinsics", "sdm_candidate_count", "sdm_pass1", "sdm_pass2", "sdm_update_points", "sdm_download",
+    "sdm_upload_depth", "sdm_depth_plane_ptr", "sdm_export_arena", "sdm_import_peer_arena", "sdm_pull_halo",
+    "sdm_mark_pass1_done", "sdm_pair_geometry", "sdm_stereo_search_constraints", "sdm_search_range",
+    "sdm_epipolar_search", "sdm_epipolar_search_plane", "sdm_fuse", "sdm_intra_check", "sdm_intra_grow",
+    "sdm_inter_check", "sdm_last_pass_ms", "sdm_launch_count",
+]
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """dlopen the in-tree library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(f"{LIB_PATH} not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = C.CDLL(LIB_PATH)
+    vp, fp, ip = C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int32)
+    sz = C.c_size_t
+    lib.sdm_default_config.argtypes = [C.POINTER(Config)]
+    lib.sdm_default_config.restype = None
+    lib.sdm_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    lib.sdm_destroy.argtypes = [vp]
+    lib.sdm_destroy.restype = None
+    lib.sdm_last_error.restype = C.c_char_p
+    lib.sdm_version.restype = C.c_char_p
+    lib.sdm_synchronize.argtypes = [vp]
+    lib.sdm_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    lib.sdm_host_alloc.argtypes = [C.POINTER(vp), sz]
+    lib.sdm_host_free.argtypes = [vp]
+    lib.sdm_upload_keyframe.argtypes = [vp, C.c_int, vp, sz, vp, sz, vp, sz, vp, sz, fp, fp]
+    lib.sdm_set_pose.argtypes = [vp, C.c_int, fp]
+    lib.sdm_set_intrinsics.argtypes = [vp, C.c_int, fp]
+    lib.sdm_candidate_count.argtypes = [vp, C.c_int, C.POINTER(C.c_int)]
+    lib.sdm_pass1.argtypes = [vp, C.c_int, C.POINTER(Item)]
+    lib.sdm_pass2.argtypes = [vp, C.c_int, C.POINTER(Item)]
+    lib.sdm_update_points.argtypes = [vp, C.c_int, ip]
+    lib.sdm_download.argtypes = [vp, C.c_int, vp, sz, vp, sz, vp, sz, vp, sz]
+    lib.sdm_upload_depth.argtypes = [vp, C.c_int, vp, sz, vp, sz]
+    lib.sdm_depth_plane_ptr.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(sz)]
+    lib.sdm_export_arena.argtypes = [vp, vp, C.POINTER(sz)]
+    lib.sdm_import_peer_arena.argtypes = [vp, C.c_int, vp]
+    lib.sdm_pull_halo.argtypes = [vp, C.c_int, ip, ip, ip]
+    lib.sdm_mark_pass1_done.argtypes = [vp, C.c_int]
+    lib.sdm_pair_geometry.argtypes = [fp, fp, fp, fp, C.POINTER(PairGeometry)]
+    lib.sdm_stereo_search_constraints.argtypes = [fp, C.c_int, fp, fp]
+    lib.sdm_search_range.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, fp, fp]
+    lib.sdm_epipolar_search.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                                        C.POINTER(Hypothesis)]
+    lib.sdm_epipolar_search_plane.argtypes = [vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp]
+    lib.sdm_fuse.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]
+    lib.sdm_intra_check.argtypes = [vp, C.c_int]
+    lib.sdm_intra_grow.argtypes = [vp, C.c_int]
+    lib.sdm_inter_check.argtypes = [vp, C.POINTER(Item)]
+    lib.sdm_last_pass_ms.argtypes = [vp, fp, fp]
+    lib.sdm_launch_count.argtypes = [vp]
+    lib.sdm_launch_count.restype = C.c_longlong
+    _lib = lib
+    return lib
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, np.float32)
+
+
+def _fp(a: np.ndarray):
+    return a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def default_config(**over) -> Config:
+    cfg = Config()
+    load().sdm_default_config(C.byref(cfg))
+    for k, v in over.items():
+        if not hasattr(cfg, k):
+            raise AttributeError(k)
+        setattr(cfg, k, v)
+    return cfg
+
+
+def make_items(kfs, nbr_idx, rot, min_depth, max_depth, slot_of=None):
+    """Item array for keyframes `kfs` (scene indices); slot_of maps scene index -> device slot."""
+    kfs = list(kfs)
+    arr = (Item * len(kfs))()
+    f = (lambda i: int(i)) if slot_of is None else (lambda i: int(slot_of[int(i)]))
+    for a, i in zip(arr, kfs):
+        nb = nbr_idx[i]
+        a.kf = f(i)
+        a.n_nbr = len(nb)
+        for j, v in enumerate(nb):
+            a.nbr[j] = f(v)
+            a.rot_deg[j] = float(rot[i][j])
+        a.min_depth = float(min_depth[i])
+        a.max_depth = float(max_depth[i])
+    return arr
+
+
+class Context:
+    """One device context (sdm_ctx).  Methods map 1:1 onto the C entry points."""
+
+    def __init__(self, cfg: Config | None = None, **over):
+        self.lib = load()
+        self.cfg = cfg if cfg is not None else default_config(**over)
+        self.h = C.c_void_p()
+        self._chk(self.lib.sdm_create(C.byref(self.cfg), C.byref(self.h)))
+        self.W, self.H = self.cfg.width, self.cfg.height
+
+    def _chk(self, rc: int):
+        if rc != 0:
+            raise SdmError(rc, (self.lib.sdm_last_error() or b"").decode())
+
+    def close(self):
+        if getattr(self, "h", None) and self.h.value:
+            self.lib.sdm_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- planes
+    def upload_keyframe(self, slot, im, grad, theta, edge, K, Tcw):
+        """Arrays may be row-pitched views (positive strides, unit column stride)."""
+        def chk(a, dt, esz):
+            assert a.dtype == dt and a.shape == (self.H, self.W) and a.strides[1] == esz, (a.dtype, a.shape, a.strides)
+        chk(im, np.uint8, 1); chk(grad, np.float32, 4); chk(theta, np.float32, 4)
+        if edge is not None:
+            chk(edge, np.int32, 4)
+        Kf, Tf = _f32(np.asarray(K).reshape(4)), _f32(np.asarray(Tcw).reshape(-1)[:12])
+        self._chk(self.lib.sdm_upload_keyframe(
+            self.h, slot, im.ctypes.data, im.strides[0], grad.ctypes.data, grad.strides[0],
+            theta.ctypes.data, theta.strides[0],
+            edge.ctypes.data if edge is not None else None, edge.strides[0] if edge is not None else 0,
+            _fp(Kf), _fp(Tf)))
+
+    def upload_scene(self, scene, indices=None, slot_of=None):
+        idx = range(scene.n) if indices is None else indices
+        for i in idx:
+            s = i if slot_of is None else slot_of[i]
+            self.upload_keyframe(s, scene.im[i], scene.grad[i], scene.theta[i],
+                                 scene.edge[i] if scene.edge is not None else None, scene.K, scene.Tcw[i])
+
+    def set_pose(self, slot, Tcw):
+        self._chk(self.lib.sdm_set_pose(self.h, slot, _fp(_f32(np.asarray(Tcw).reshape(-1)[:12]))))
+
+    def set_intrinsics(self, slot, K):
+        self._chk(self.lib.sdm_set_intrinsics(self.h, slot, _fp(_f32(np.asarray(K).reshape(4)))))
+
+    def candidate_count(self, slot) -> int:
+        n = C.c_int()
+        self._chk(self.lib.sdm_candidate_count(self.h, slot, C.byref(n)))
+        return n.value
+
+    # ---- passes
+    def pass1(self, items):
+        self._chk(self.lib.sdm_pass1(self.h, len(items), items))
+
+    def pass2(self, items):
+        self._chk(self.lib.sdm_pass2(self.h, len(items), items))
+
+    def update_points(self, slots):
+        a = np.ascontiguousarray(slots, np.int32)
+        self._chk(self.lib.sdm_update_points(self.h, a.size, a.ctypes.data_as(C.POINTER(C.c_int32))))
+
+    def synchronize(self):
+        self._chk(self.lib.sdm_synchronize(self.h))
+
+    def download(self, slot, depth=True, sigma=True, checked=True, points=True, out=None):
+        H, W = self.H, self.W
+        out = out or {}
+        res = {}
+
+        def buf(name, want, shape):
+            if not want:
+                return None
+            a = out.get(name)
+            if a is None:
+                a = np.empty(shape, np.float32)
+            res[name] = a
+            return a
+        d, s = buf("depth", depth, (H, W)), buf("sigma", sigma, (H, W))
+        c, p = buf("checked", checked, (H, W)), buf("points", points, (H, W, 3))
+        self._chk(self.lib.sdm_download(
+            self.h, slot,
+            d.ctypes.data if d is not None else None, d.strides[0] if d is not None else 0,
+            s.ctypes.data if s is not None else None, s.strides[0] if s is not None else 0,
+            c.ctypes.data if c is not None else None, c.strides[0] if c is not None else 0,
+            p.ctypes.data if p is not None else None, p.strides[0] if p is not None else 0))
+        return res
+
+    def upload_depth(self, slot, depth, sigma):
+        d, s = _f32(depth), _f32(sigma)
+        self._chk(self.lib.sdm_upload_depth(self.h, slot, d.ctypes.data, d.strides[0], s.ctypes.data, s.strides[0]))
+
+    def stats(self) -> dict:
+        st = Stats()
+        self._chk(self.lib.sdm_get_stats(self.h, C.byref(st)))
+        return {"candidates": st.candidates, "fused": st.fused, "checked": st.checked}
+
+    def last_pass_ms(self):
+        a, b = C.c_float(), C.c_float()
+        self._chk(self.lib.sdm_last_pass_ms(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def launch_count(self) -> int:
+        return int(self.lib.sdm_launch_count(self.h))
+
+    # ---- per-method entry points
+    def search_range(self, kf1, kf2, px, py, mind, maxd):
+        a, b = C.c_float(), C.c_float()
+        self._chk(self.lib.sdm_search_range(self.h, kf1, kf2, px, py, mind, maxd, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def epipolar_search(self, kf1, kf2, x, y, mind, maxd, rot=0.0) -> Hypothesis:
+        h = Hypothesis()
+        self._chk(self.lib.sdm_epipolar_search(self.h, kf1, kf2, x, y, mind, maxd, rot, C.byref(h)))
+        return h
+
+    def epipolar_search_plane(self, kf1, kf2, mind, maxd, rot=0.0):
+        H, W = self.H, self.W
+        d, s, u = (np.empty((H, W), np.float32) for _ in range(3))
+        ok = np.empty((H, W), np.uint8)
+        self._chk(self.lib.sdm_epipolar_search_plane(self.h, kf1, kf2, mind, maxd, rot, d.ctypes.data, s.ctypes.data,
+                                                     u.ctypes.data, ok.ctypes.data))
+        return d, s, u, ok
+
+    def fuse(self, depth, sigma, count):
+        depth, sigma = _f32(depth), _f32(sigma)
+        m, n = depth.shape
+        count = np.ascontiguousarray(count, np.int32)
+        od, os_ = np.empty(m, np.float32), np.empty(m, np.float32)
+        ok = np.empty(m, np.int32)
+        self._chk(self.lib.sdm_fuse(self.h, m, n, depth.ctypes.data, sigma.ctypes.data, count.ctypes.data,
+                                    od.ctypes.data, os_.ctypes.data, ok.ctypes.data))
+        return od, os_, ok
+
+    def intra_check(self, slot):
+        self._chk(self.lib.sdm_intra_check(self.h, slot))
+
+    def intra_grow(self, slot):
+        self._chk(self.lib.sdm_intra_grow(self.h, slot))
+
+    # ---- multi-GPU plumbing
+    def depth_plane_ptr(self, slot):
+        p, n = C.c_void_p(), C.c_size_t()
+        self._chk(self.lib.sdm_depth_plane_ptr(self.h, slot, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def export_arena(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        n = C.c_size_t()
+        self._chk(self.lib.sdm_export_arena(self.h, buf, C.byref(n)))
+        return bytes(buf.raw)
+
+    def import_peer_arena(self, rank: int, handle: bytes):
+        self._chk(self.lib.sdm_import_peer_arena(self.h, rank, C.create_string_buffer(handle, 64)))
+
+    def pull_halo(self, local_slot, peer_rank, peer_slot):
+        a, b, c = (np.ascontiguousarray(v, np.int32) for v in (local_slot, peer_rank, peer_slot))
+        ip = C.POINTER(C.c_int32)
+        self._chk(self.lib.sdm_pull_halo(self.h, a.size, a.ctypes.data_as(ip), b.ctypes.data_as(ip), c.ctypes.data_as(ip)))
+
+    def mark_pass1_done(self, slot):
+        self._chk(self.lib.sdm_mark_pass1_done(self.h, slot))
+
+
+def pair_geometry(K1, Tcw1, K2, Tcw2) -> PairGeometry:
+    g = PairGeometry()
+    a, b, c, d = (_f32(np.asarray(v).reshape(-1)) for v in (K1, Tcw1, K2, Tcw2))
+    rc = load().sdm_pair_geometry(_fp(a), _fp(b[:12].copy()), _fp(c), _fp(d[:12].copy()), C.byref(g))
+    if rc:
+        raise SdmError(rc, load().sdm_last_error().decode())
+    return g
+
+
+def stereo_search_constraints(inv_depths):
+    a = _f32(inv_depths)
+    lo, hi = C.c_float(), C.c_float()
+    rc = load().sdm_stereo_search_constraints(_fp(a), a.size, C.byref(lo), C.byref(hi))
+    if rc:
+        raise SdmError(rc, load().sdm_last_error().decode())
+    return lo.value, hi.value

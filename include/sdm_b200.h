@@ -1,0 +1,193 @@
+/*
+ * sdm_b200.h — C-ABI of the B200-native semi-dense mapping library (libsdm_b200.so).
+ *
+ * This is the drop-in boundary for EAO-SLAM's ProbabilityMapping hot path.  The reference has no
+ * FFI layer: ProbabilityMapping (include/ProbabilityMapping.h:71-158) is a concrete C++ class
+ * that reads/writes public cv::Mat members of ORB_SLAM2::KeyFrame (include/KeyFrame.h:155-175).
+ * Each entry point below names the reference code it replaces; the C++ class shim that keeps the
+ * reference's method names on top of these calls is eao-slam_b200/host/ProbabilityMapping.h, and
+ * INTEGRATION.md shows the binding a maintainer adds to the reference.
+ *
+ * Conventions: extern "C", plain pointers and sizes, no C++/torch types.  Every function returns
+ * 0 on success or a negative sdm_status; sdm_last_error() gives the message of the last failure
+ * on the calling thread.  One context per CUDA device; a context is NOT thread-safe (the
+ * reference runs the whole path on its single semi-dense thread, System.cc:124).  There is no CPU
+ * fallback: without a CUDA device sdm_create fails with SDM_ERR_CUDA.
+ *
+ * All citations are relative to the reference root (yanmin-wu/EAO-SLAM).
+ */
+#ifndef SDM_B200_H
+#define SDM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SDM_MAX_NBR 16 /* covisN is 7 in the reference (ProbabilityMapping.h:45); BASELINE uses 6 and 10 */
+
+typedef enum {
+    SDM_OK = 0,
+    SDM_ERR_ARG = -1,   /* bad argument (null pointer, slot out of range, N > SDM_MAX_NBR, ...) */
+    SDM_ERR_CUDA = -2,  /* CUDA runtime error, no device */
+    SDM_ERR_STATE = -3, /* keyframe not uploaded, pass 2 before pass 1, ... */
+    SDM_ERR_NOMEM = -4
+} sdm_status;
+
+typedef struct sdm_ctx sdm_ctx;
+
+/* The #defines of include/ProbabilityMapping.h:45-56 and the literals of
+ * src/ProbabilityMapping.cc (:757 slope, :1638 5.99, :1207 3.84, :877 0.000001), made runtime. */
+typedef struct {
+    int width, height;   /* im_.cols, im_.rows: one size per context                          */
+    int max_keyframes;   /* device slots to reserve (owned + halo keyframes of this rank)      */
+    int lambdaG;         /* 8   */
+    int lambdaL;         /* 80  */
+    int lambdaTheta;     /* 45  */
+    int lambdaN;         /* 3   */
+    float theta;         /* (float)0.23 = THETA */
+    float sigmaI;        /* 20 = I_stddev, KeyFrame.cc:65 */
+    double chi2_fusion;  /* 5.99 */
+    double chi2_inter;   /* 3.84 */
+    double eps;          /* 0.000001 */
+    float slope_max;     /* 4 */
+    int intra_check;     /* 0: shipped loop (:491-494 commented out); 1: IntraKeyFrameDepthChecking on */
+    int intra_grow;      /* same for IntraKeyFrameDepthGrowing                                        */
+    int device;          /* CUDA device ordinal */
+} sdm_config;
+
+/* One keyframe's work order for a pass: the per-keyframe state SemiDenseLoop assembles at
+ * :365-438 (closestMatches, rotIs, min/max depth).  kf and nbr[] are device slots. */
+typedef struct {
+    int32_t kf;
+    int32_t n_nbr;
+    int32_t nbr[SDM_MAX_NBR];
+    float rot_deg[SDM_MAX_NBR]; /* rotIs[kf2], :406-415 */
+    float min_depth, max_depth; /* StereoSearchConstraints, :427 */
+} sdm_item;
+
+typedef struct {
+    float R21[9];
+    float t21[3];
+    float F12[9];
+} sdm_pair_geometry_t;
+
+/* replaces: depthHo (ProbabilityMapping.h:74-80) as returned by EpipolarSearch */
+typedef struct {
+    float depth; /* inverse depth */
+    float sigma;
+    int32_t supported;
+    float best_u, best_v;
+} sdm_hypothesis;
+
+/* counters of the last pass (device-side atomics; optional diagnostics) */
+typedef struct {
+    long long candidates; /* pixels passing :454-456 in the keyframes of the last sdm_pass1 */
+    long long fused;      /* pixels written at :483                                          */
+    long long checked;    /* pixels with depth_map_checked_ > 0 after the last sdm_pass2      */
+} sdm_stats;
+
+/* ---- context ------------------------------------------------------------------------------- */
+void sdm_default_config(sdm_config* cfg);            /* ProbabilityMapping.h:45-56 defaults */
+int sdm_create(const sdm_config* cfg, sdm_ctx** out); /* replaces ProbabilityMapping ctor, :195-202 */
+void sdm_destroy(sdm_ctx* ctx);
+const char* sdm_last_error(void);
+const char* sdm_version(void);
+int sdm_synchronize(sdm_ctx* ctx);
+int sdm_get_stats(sdm_ctx* ctx, sdm_stats* out);
+
+/* pinned host memory for asynchronous uploads/downloads (optional; any host pointer is accepted) */
+int sdm_host_alloc(void** ptr, size_t bytes);
+int sdm_host_free(void* ptr);
+
+/* ---- keyframe planes ----------------------------------------------------------------------- */
+/* replaces: the KeyFrame ctor's plane set-up (KeyFrame.cc:63-88) + mEdgeIndex from
+ * LineDetector::DetectEdgeMap (LineDetector.cc:843-881), as device-resident packed buffers, and the
+ * candidate test of :454-456 (compaction).  Steps are in BYTES (cv::Mat::step).  edge may be NULL
+ * (every pixel passes :454).  K = {fx, fy, cx, cy}; Tcw = rows 0..2 of the 4x4 pose, row-major.
+ * Asynchronous: host buffers must stay valid until sdm_synchronize / the next blocking call. */
+int sdm_upload_keyframe(sdm_ctx* ctx, int kf,
+                        const uint8_t* im, size_t im_step,
+                        const float* grad, size_t grad_step,
+                        const float* theta, size_t theta_step,
+                        const int32_t* edge, size_t edge_step,
+                        const float K[4], const float Tcw[12]);
+/* replaces: KeyFrame::SetPose (KeyFrame.cc:108-124) for PoseChanged refresh (:691-694) */
+int sdm_set_pose(sdm_ctx* ctx, int kf, const float Tcw[12]);
+/* calibration of a slot (KeyFrame::fx,fy,cx,cy; Frame.cc:584-590).  With sdm_set_pose this is all a
+ * halo slot needs when only its pass-1 planes arrive over NVLink (no image upload) */
+int sdm_set_intrinsics(sdm_ctx* ctx, int kf, const float K[4]);
+int sdm_candidate_count(sdm_ctx* ctx, int kf, int* count); /* blocking */
+
+/* ---- the two hot loops --------------------------------------------------------------------- */
+/* replaces: SemiDenseLoop pass 1 body, :424-497 — ComputeFundamental, the omp pixel loop with
+ * EpipolarSearch / InverseDepthHypothesisFusion, [IntraKeyFrameDepthChecking/Growing] — for n
+ * keyframes in one batched launch.  Writes depth_map_/depth_sigma_ of every item's keyframe. */
+int sdm_pass1(sdm_ctx* ctx, int n, const sdm_item* items);
+/* replaces: SemiDenseLoop pass 2 body, :550-552 — InterKeyFrameDepthChecking(kf, neighbours)
+ * (:1121-1296) + UpdateSemiDensePointSet (:700-731).  Reads the neighbours' pass-1 planes. */
+int sdm_pass2(sdm_ctx* ctx, int n, const sdm_item* items);
+/* replaces: UpdateSemiDensePointSet alone (UpdateAllSemiDensePointSet, :678-697) */
+int sdm_update_points(sdm_ctx* ctx, int n, const int32_t* kfs);
+
+/* replaces: reading KeyFrame::depth_map_, depth_sigma_, depth_map_checked_, SemiDensePointSets_.
+ * Any pointer may be NULL.  Steps in bytes.  Blocking. */
+int sdm_download(sdm_ctx* ctx, int kf,
+                 float* depth, size_t depth_step, float* sigma, size_t sigma_step,
+                 float* checked, size_t checked_step, float* points, size_t points_step);
+/* writes pass-1 planes of a keyframe (used to seed halo keyframes / tests); blocking */
+int sdm_upload_depth(sdm_ctx* ctx, int kf, const float* depth, size_t depth_step,
+                     const float* sigma, size_t sigma_step);
+
+/* ---- multi-GPU: pass-1 planes of halo keyframes over NVLink (the dependency of :1202-1249) -- */
+/* device pointer + byte size of the (rho, sigma) float2 plane of a slot, for NCCL / peer copies */
+int sdm_depth_plane_ptr(sdm_ctx* ctx, int kf, void** dev_ptr, size_t* bytes);
+/* CUDA IPC handle (64 bytes) of the whole (rho, sigma) arena, to be opened by a peer process */
+int sdm_export_arena(sdm_ctx* ctx, void* handle64, size_t* slot_bytes);
+/* open a peer's arena; afterwards sdm_pull_halo copies peer slots into local slots over NVLink */
+int sdm_import_peer_arena(sdm_ctx* ctx, int peer_rank, const void* handle64);
+int sdm_pull_halo(sdm_ctx* ctx, int n, const int32_t* local_slot, const int32_t* peer_rank,
+                  const int32_t* peer_slot);
+/* mark a slot's pass-1 planes as valid (after an external NCCL receive into sdm_depth_plane_ptr) */
+int sdm_mark_pass1_done(sdm_ctx* ctx, int kf);
+
+/* ---- per-method entry points (each named class method stays individually callable) ---------- */
+/* replaces: ComputeFundamental (:1694-1709) and the R21/t21 of :1136-1137; host arithmetic with
+ * OpenCV's evaluation rules */
+int sdm_pair_geometry(const float K1[4], const float Tcw1[12], const float K2[4], const float Tcw2[12],
+                      sdm_pair_geometry_t* out);
+/* replaces: StereoSearchConstraints (:734-747); inv_depths = KeyFrame::GetAllPointDepths */
+int sdm_stereo_search_constraints(const float* inv_depths, int n, float* min_depth, float* max_depth);
+/* replaces: GetSearchRange (:1598-1631) */
+int sdm_search_range(sdm_ctx* ctx, int kf1, int kf2, int px, int py, float mind, float maxd,
+                     float* umin, float* umax);
+/* replaces: EpipolarSearch (:749-845) for one pixel / one neighbour */
+int sdm_epipolar_search(sdm_ctx* ctx, int kf1, int kf2, int x, int y, float min_depth, float max_depth,
+                        float rot_deg, sdm_hypothesis* out);
+/* EpipolarSearch over every candidate pixel of kf1 against kf2; planes are dense W*H; ok: 0 = no
+ * hypothesis, 1 = hypothesis failing the keep test of :472, 2 = kept */
+int sdm_epipolar_search_plane(sdm_ctx* ctx, int kf1, int kf2, float min_depth, float max_depth, float rot_deg,
+                              float* hyp_depth, float* hyp_sigma, float* hyp_u, uint8_t* ok);
+/* replaces: InverseDepthHypothesisFusion (:978-1009) for m independent hypothesis sets of n each
+ * (n <= SDM_MAX_NBR; depth/sigma are [m][n]; count[m] valid entries per set) */
+int sdm_fuse(sdm_ctx* ctx, int m, int n, const float* depth, const float* sigma, const int32_t* count,
+             float* out_depth, float* out_sigma, int32_t* out_supported);
+/* replaces: IntraKeyFrameDepthChecking(cv::Mat&, cv::Mat&, cv::Mat) (:866-927) on a keyframe's planes */
+int sdm_intra_check(sdm_ctx* ctx, int kf);
+/* replaces: IntraKeyFrameDepthGrowing (:929-976) */
+int sdm_intra_grow(sdm_ctx* ctx, int kf);
+/* replaces: InterKeyFrameDepthChecking(KeyFrame*, vector<KeyFrame*>) (:1121-1296) alone */
+int sdm_inter_check(sdm_ctx* ctx, const sdm_item* item);
+
+/* ---- measurement --------------------------------------------------------------------------- */
+/* CUDA-event time (ms) of the kernels of the last sdm_pass1 / sdm_pass2 call on the context's
+ * compute stream (0 if none); number of kernel launches issued since context creation */
+int sdm_last_pass_ms(sdm_ctx* ctx, float* pass1_ms, float* pass2_ms);
+long long sdm_launch_count(sdm_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,79 @@
+"""Shared helpers of the parity tests: run the oracle and the device path on one scene, compare."""
+from __future__ import annotations
+
+import numpy as np
+
+import oracle_py as O
+from sdmb200 import api
+
+# BASELINE.json north_star tolerances
+SET_MISMATCH_MAX = 1e-3   # accepted-pixel sets: at most 0.1 % tie / boundary cases
+REL_TOL = 1e-4            # fused inverse depth and variance: 1e-4 relative
+
+
+def run_oracle(scene, intra_check=0, intra_grow=0, kind="canonical"):
+    osc = O.OracleScene(scene, kind)
+    p = O.default_params(kind, intra_check=intra_check, intra_grow=intra_grow)
+    osc.run(params=p)
+    return osc
+
+
+def run_device(scene, intra_check=0, intra_grow=0, ctx=None):
+    """Full SemiDenseLoop through the C-ABI: upload, pass 1 (all), pass 2 (all), download."""
+    H, W = scene.shape
+    own = ctx is None
+    if own:
+        ctx = api.Context(width=W, height=H, max_keyframes=scene.n, intra_check=intra_check, intra_grow=intra_grow)
+    ctx.upload_scene(scene)
+    items = api.make_items(range(scene.n), scene.nbr_idx, scene.rot, scene.min_depth, scene.max_depth)
+    ctx.pass1(items)
+    st1 = ctx.stats()
+    ctx.pass2(items)
+    st2 = ctx.stats()
+    out = {k: np.zeros((scene.n, H, W) + ((3,) if k == "points" else ()), np.float32)
+           for k in ("depth", "sigma", "checked", "points")}
+    for i in range(scene.n):
+        r = ctx.download(i)
+        for k in out:
+            out[k][i] = r[k]
+    out["stats"] = {"candidates": st1["candidates"], "fused": st1["fused"], "checked": st2["checked"]}
+    if own:
+        ctx.close()
+    return out
+
+
+def rel_err(a, b):
+    a = a.astype(np.float64)
+    b = b.astype(np.float64)
+    return np.abs(a - b) / np.maximum(np.abs(b), 1e-30)
+
+
+def compare_planes(dev, osc, what=("depth", "sigma", "checked", "points")):
+    """Returns a report dict; asserts the BASELINE tolerances."""
+    rep = {}
+    ref = {"depth": osc.depth, "sigma": osc.sigma, "checked": osc.checked, "points": osc.points}
+    for setname, key in (("pass1", "depth"), ("pass2", "checked")):
+        if key not in what:
+            continue
+        a, b = dev[key] > 0, ref[key] > 0
+        n_ref = int(b.sum())
+        mism = int((a != b).sum())
+        rep[setname + "_accepted_ref"] = n_ref
+        rep[setname + "_set_mismatch"] = mism
+        assert n_ref > 0, "oracle accepted nothing: the parity check would be vacuous"
+        assert mism <= SET_MISMATCH_MAX * n_ref, (setname, mism, n_ref)
+    for key in what:
+        a, b = dev[key], ref[key]
+        gate = "depth" if key in ("depth", "sigma") else "checked"
+        both = (dev[gate] > 0) & (ref[gate] > 0)
+        if key == "points":
+            both = both[..., None] & np.ones(3, bool)
+        if both.any():
+            e = rel_err(a[both], b[both])
+            if key == "points":  # world coordinates pass through 0: scale by the point norm instead
+                nrm = np.linalg.norm(ref["points"], axis=-1, keepdims=True).astype(np.float64)
+                e = (np.abs(a.astype(np.float64) - b) / np.maximum(nrm, 1e-30))[both]
+            rep[key + "_max_rel"] = float(e.max())
+            assert e.max() <= REL_TOL, (key, float(e.max()))
+        rep[key + "_bit_mismatch"] = int((a.view(np.uint32) != b.view(np.uint32)).sum())
+    return rep

@@ -1,0 +1,186 @@
+"""GPU parity tests: the CUDA path, called through the C-ABI, against the CPU oracle on the same
+seeded synthetic keyframes (BASELINE.json: accepted sets equal up to 0.1 %, values within 1e-4)."""
+import ctypes as C
+import json
+
+import numpy as np
+import pytest
+
+import oracle_py as O
+from helpers import REL_TOL, compare_planes, rel_err, run_device, run_oracle
+from sdmb200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def small_scene():
+    return synth.make_scene(9, 320, 240, 6, seed=11)
+
+
+@pytest.fixture(scope="module")
+def small_oracle(small_scene):
+    return run_oracle(small_scene)
+
+
+def test_candidate_compaction(small_scene):
+    sc = small_scene
+    with api.Context(width=320, height=240, max_keyframes=sc.n) as ctx:
+        ctx.upload_scene(sc)
+        for i in range(sc.n):
+            assert ctx.candidate_count(i) == int((sc.grad[i] > 8).sum())
+
+
+def test_candidate_compaction_edge_mask():
+    sc = synth.make_scene(8, 160, 120, 6, seed=5, edge_mask=True)
+    with api.Context(width=160, height=120, max_keyframes=sc.n) as ctx:
+        ctx.upload_scene(sc)
+        for i in range(sc.n):
+            assert ctx.candidate_count(i) == int(((sc.grad[i] > 8) & (sc.edge[i] >= 0)).sum())
+
+
+def test_search_range_matches_oracle(small_scene, small_oracle):
+    sc, osc = small_scene, small_oracle
+    lib = O.lib()
+    rng = np.random.default_rng(0)
+    with api.Context(width=320, height=240, max_keyframes=sc.n) as ctx:
+        ctx.upload_scene(sc)
+        for _ in range(40):
+            i = int(rng.integers(sc.n)); j = int(sc.nbr_idx[i][rng.integers(6)])
+            px, py = int(rng.integers(320)), int(rng.integers(240))
+            pr = osc.pair(i, j)
+            a, b = C.c_float(), C.c_float()
+            lib.oracle_get_search_range(C.byref(osc.kfs[i]), C.byref(pr), px, py, float(sc.min_depth[i]),
+                                        float(sc.max_depth[i]), C.byref(a), C.byref(b))
+            u0, u1 = ctx.search_range(i, j, px, py, float(sc.min_depth[i]), float(sc.max_depth[i]))
+            assert (u0, u1) == (a.value, b.value)
+
+
+def test_epipolar_search_per_pair(small_scene, small_oracle):
+    """EpipolarSearch granularity: raw hypotheses of every candidate pixel for single pairs."""
+    sc, osc = small_scene, small_oracle
+    with api.Context(width=320, height=240, max_keyframes=sc.n) as ctx:
+        ctx.upload_scene(sc)
+        for i, j in ((4, 5), (4, 1), (0, 3), (8, 6)):
+            d, s, u, ok = ctx.epipolar_search_plane(i, j, float(sc.min_depth[i]), float(sc.max_depth[i]), 0.0)
+            rd, rs, ru, rok = osc.pass1_pair(i, j, 0.0)
+            assert rok.sum() > 1000
+            assert (ok != rok).sum() <= 1e-3 * (rok > 0).sum()
+            both = (ok == 2) & (rok == 2)
+            for a, b in ((d, rd), (s, rs), (u, ru)):
+                assert rel_err(a[both], b[both]).max() <= REL_TOL
+            # single-pixel entry point agrees with the plane entry point
+            ys, xs = np.nonzero(ok == 2)
+            k = len(ys) // 2
+            h = ctx.epipolar_search(i, j, int(xs[k]), int(ys[k]), float(sc.min_depth[i]), float(sc.max_depth[i]), 0.0)
+            assert h.supported == 1 and h.depth == d[ys[k], xs[k]] and h.sigma == s[ys[k], xs[k]]
+
+
+def test_semidense_loop_small(small_scene, small_oracle):
+    dev = run_device(small_scene)
+    rep = compare_planes(dev, small_oracle)
+    print(json.dumps(rep))
+    st = small_oracle.stats.as_dict()
+    assert dev["stats"]["candidates"] == st["candidates"]
+    assert abs(dev["stats"]["fused"] - st["fused"]) <= 1e-3 * st["fused"]
+
+
+@pytest.mark.parametrize("n_nbr", [6, 7])
+def test_config1_vga(n_nbr):
+    """BASELINE config 1: SemiDenseLoop on 10 synthetic 640x480 keyframes, TUM fr3 intrinsics."""
+    sc = synth.make_scene(10, 640, 480, n_nbr, seed=1)
+    osc = run_oracle(sc)
+    dev = run_device(sc)
+    rep = compare_planes(dev, osc)
+    print(json.dumps(rep))
+    assert rep["pass1_accepted_ref"] > 100000 and rep["pass2_accepted_ref"] > 100000
+
+
+def test_rotated_pairs_and_edge_mask():
+    """non-zero rotIs (condition 3 of :801-809) and an mEdgeIndex mask."""
+    sc = synth.make_scene(8, 320, 240, 6, seed=7, edge_mask=True)
+    sc.rot[:] = np.random.default_rng(2).uniform(-8, 8, sc.rot.shape).astype(np.float32)
+    osc = run_oracle(sc)
+    dev = run_device(sc)
+    print(json.dumps(compare_planes(dev, osc)))
+
+
+def test_intra_check_and_grow():
+    sc = synth.make_scene(8, 320, 240, 6, seed=13)
+    osc = run_oracle(sc, intra_check=1, intra_grow=1)
+    dev = run_device(sc, intra_check=1, intra_grow=1)
+    print(json.dumps(compare_planes(dev, osc)))
+    # and the single-method entry points on a pass-1 result
+    osc1 = O.OracleScene(sc)
+    osc1.run(pass_mask=1)
+    with api.Context(width=320, height=240, max_keyframes=sc.n) as ctx:
+        ctx.upload_scene(sc)
+        ctx.upload_depth(3, osc1.depth[3], osc1.sigma[3])
+        ctx.intra_check(3)
+        got = ctx.download(3, checked=False, points=False)
+        d, s = osc1.depth[3].copy(), osc1.sigma[3].copy()
+        p = O.default_params()
+        O.lib().oracle_intra_check(O.fptr(d), O.fptr(s), 320, 240, C.byref(p))
+        assert np.array_equal(got["depth"].view(np.uint32), d.view(np.uint32))
+        assert np.array_equal(got["sigma"].view(np.uint32), s.view(np.uint32))
+        ctx.intra_grow(3)  # provably a no-op
+        got2 = ctx.download(3, checked=False, points=False)
+        assert np.array_equal(got2["depth"], got["depth"]) and np.array_equal(got2["sigma"], got["sigma"])
+
+
+def test_fusion_known_answers():
+    rng = np.random.default_rng(3)
+    m, n = 4000, 10
+    base = rng.uniform(0.2, 2.0, (m, 1)).astype(np.float32)
+    depth = (base + rng.normal(0, 0.02, (m, n)).astype(np.float32) * (rng.random((m, n)) < 0.8)
+             + (rng.random((m, n)) < 0.15) * rng.uniform(-1, 1, (m, n))).astype(np.float32)
+    sigma = rng.uniform(0.005, 0.05, (m, n)).astype(np.float32)
+    count = rng.integers(0, n + 1, m).astype(np.int32)
+    with api.Context(width=64, height=64, max_keyframes=1) as ctx:
+        od, os_, ok = ctx.fuse(depth, sigma, count)
+    lib, p = O.lib(), O.default_params()
+    n_ok = 0
+    for i in range(m):
+        a, b = C.c_float(), C.c_float()
+        c = int(count[i])
+        r = lib.oracle_fusion(O.fptr(depth[i, :c].copy()), O.fptr(sigma[i, :c].copy()), c, C.byref(p), C.byref(a), C.byref(b)) if c else 0
+        assert r == ok[i]
+        if r:
+            n_ok += 1
+            assert np.float32(a.value) == od[i] and np.float32(b.value) == os_[i]
+    assert n_ok > 500
+
+
+def test_pitched_upload_and_download(small_scene, small_oracle):
+    sc = small_scene
+    H, W = sc.shape
+    pad = 24
+    with api.Context(width=W, height=H, max_keyframes=sc.n) as ctx:
+        for i in range(sc.n):
+            im = np.zeros((H, W + pad), np.uint8); im[:, :W] = sc.im[i]
+            g = np.full((H, W + pad), 99, np.float32); g[:, :W] = sc.grad[i]
+            t = np.full((H, W + pad), 99, np.float32); t[:, :W] = sc.theta[i]
+            ctx.upload_keyframe(i, im[:, :W], g[:, :W], t[:, :W], None, sc.K, sc.Tcw[i])
+        items = api.make_items(range(sc.n), sc.nbr_idx, sc.rot, sc.min_depth, sc.max_depth)
+        ctx.pass1(items)
+        big = np.full((H, W + pad), -1, np.float32)
+        ctx.download(4, sigma=False, checked=False, points=False, out={"depth": big[:, :W]})
+        assert (big[:, W:] == -1).all()
+        a, b = big[:, :W] > 0, small_oracle.depth[4] > 0
+        assert (a != b).sum() <= 1e-3 * b.sum()
+
+
+def test_state_errors(small_scene):
+    sc = small_scene
+    with api.Context(width=320, height=240, max_keyframes=sc.n) as ctx:
+        items = api.make_items(range(sc.n), sc.nbr_idx, sc.rot, sc.min_depth, sc.max_depth)
+        with pytest.raises(api.SdmError) as e:
+            ctx.pass1(items)  # nothing uploaded
+        assert e.value.code == -3
+        ctx.upload_scene(sc)
+        with pytest.raises(api.SdmError) as e:
+            ctx.pass2(items)  # pass 2 before pass 1
+        assert e.value.code == -3
+        with pytest.raises(api.SdmError) as e:
+            ctx.candidate_count(sc.n + 3)
+        assert e.value.code == -1
