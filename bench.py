@@ -1,0 +1,372 @@
+#!/usr/bin/env python
+"""bench.py — semi-dense mapping throughput on B200 (BASELINE.json metric) with roofline + CPU baseline.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--kf KF_PER_GPU]
+
+One "step" = one full SemiDenseLoop (pass 1: epipolar search + fusion [+ intra checks], halo exchange,
+pass 2: inter-keyframe check + point set) over this rank's shard of a synthetic fr3_long_office-like
+trajectory.  Workload at N=1 = BASELINE config[1]: 200 keyframes, 640x480, TUM fr3 intrinsics, 6
+covisible neighbours, intra + inter depth checks.  N>1 (torchrun): weak scaling, KF_PER_GPU keyframes
+per rank, contiguous shards, halo (rho,sigma) planes pulled from peers over NVLink between the passes.
+
+`value`   : candidate pixels (edge & GradImg>8; each is searched against all N neighbours and fused)
+            per second, planes resident in HBM, CUDA-event timed on the library's compute stream.
+`e2e`     : the same through the C-ABI with pinned HOST buffers: H2D of every input plane, both passes,
+            D2H of depth_map_/depth_sigma_/depth_map_checked_/SemiDensePointSets_ inside the timed region.
+`--impl reference` : the CPU path (oracle/, a restatement of the reference's ProbabilityMapping; the
+            reference itself cannot be compiled here) on all host cores, bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "eao-slam_b200", "python"))
+
+import numpy as np  # noqa: E402
+
+from sdmb200 import shard, synth  # noqa: E402
+
+METRIC = "semi-dense pixels/sec (searched+fused) at 640x480"
+UNIT = "px/s"
+W, H = 640, 480
+L2_BYTES = 126 * 2 ** 20
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--kf", type=int, default=200, help="keyframes per GPU (BASELINE config[1]: 200)")
+    ap.add_argument("--nbr", type=int, default=6)
+    ap.add_argument("--intra", type=int, default=1, help="IntraKeyFrameDepthChecking/Growing on (config[1]: full checks)")
+    ap.add_argument("--seed", type=int, default=2)
+    ap.add_argument("--cpu-sample-kf", type=int, default=12, help="keyframes of the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# scene (cached on local disk so the two arms of one box share the render)
+# ------------------------------------------------------------------------------------------------
+def load_scene(n, first, nbr_idx, seed, tag):
+    cache = os.path.join(os.environ.get("SDM_SCENE_CACHE", "/tmp/sdm_scene_cache"),
+                         f"{tag}_s{seed}_f{first}_n{n}_{W}x{H}")
+    names = ("im", "grad", "theta", "Tcw", "min_depth", "max_depth")
+    if os.path.isdir(cache) and all(os.path.exists(os.path.join(cache, k + ".npy")) for k in names):
+        a = {k: np.load(os.path.join(cache, k + ".npy")) for k in names}
+        K = tuple(float(np.float32(v)) for v in synth.TUM3_K)
+        return synth.Scene(im=a["im"], grad=a["grad"], theta=a["theta"], edge=None, K=K, Tcw=a["Tcw"],
+                           nbr_idx=nbr_idx, rot=np.zeros(nbr_idx.shape, np.float32),
+                           min_depth=a["min_depth"], max_depth=a["max_depth"], meta={"cache": cache})
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    workers = max(1, min(16, (os.cpu_count() or 8) // world))
+    sc = synth.make_scene(n, W, H, nbr_idx.shape[1], seed=seed, first=first, workers=workers, nbr_idx=nbr_idx)
+    try:
+        os.makedirs(cache, exist_ok=True)
+        for k in names:
+            np.save(os.path.join(cache, k + ".npy"), getattr(sc, k))
+    except OSError:
+        pass
+    return sc
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md "clocks DURING the timed region")
+# ------------------------------------------------------------------------------------------------
+class Clocks:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self, t0, t1):
+        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.15 and len(r) >= 8] or [r for _, r in self.rows if len(r) >= 8]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = [float(r[1]) for r in rows]
+        reasons = [n for k, n in ((4, "hw_slowdown"), (5, "hw_thermal_slowdown"), (6, "sw_thermal_slowdown"),
+                                  (7, "sw_power_cap")) if any(r[k].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][2]), "reasons": reasons,
+                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+
+
+# ------------------------------------------------------------------------------------------------
+# byte model (DESIGN.md "Roofline")
+# ------------------------------------------------------------------------------------------------
+def bytes_pass1(n_kf, N):
+    return (17 + 9 * N) * W * H * n_kf
+
+
+def bytes_total(n_kf, N, intra):
+    return (41 + 17 * N + (16 if intra else 0)) * W * H * n_kf
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic():
+    """dram bytes per k_pass1 launch from the committed ncu --set full capture of this same command."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_pass1_dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU path (oracle) — used ONLY as cpu_baseline and as the --impl reference arm
+# ------------------------------------------------------------------------------------------------
+def cpu_run(sample_kf, nbr, seed, intra, steps, warmup):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py as O
+    nb = synth.neighbours(sample_kf, nbr)
+    sc = load_scene(sample_kf, 0, nb, seed, "cpu")
+    times, cands = [], 0
+    for it in range(warmup + steps):
+        osc = O.OracleScene(sc, "fast")
+        p = O.default_params("fast", intra_check=intra, intra_grow=intra)
+        t = osc.run(params=p)
+        cands = osc.stats.as_dict()["candidates"]
+        if it >= warmup:
+            times.append(t)
+    cores = O.lib("fast").oracle_num_threads()
+    sec = sum(times) / len(times)
+    return {"value": cands / sec, "sec_per_step": sec, "cores": cores, "candidates": cands,
+            "sample": f"full SemiDenseLoop (pass 1 + {'intra + ' if intra else ''}pass 2) over the first {sample_kf} "
+                      f"keyframes of the same synthetic trajectory, {nbr} neighbours, OpenMP over {cores} threads, "
+                      f"gcc -O3 -march=x86-64-v3; ms/KF = {1e3 * sec / sample_kf:.1f}"}
+
+
+def main_reference(a, rank):
+    if rank != 0:
+        return
+    r = cpu_run(a.cpu_sample_kf, a.nbr, a.seed, a.intra, max(1, a.steps), max(0, a.warmup))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * r["sec_per_step"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 (f64 where OpenCV accumulates in double)", "data": "synthetic",
+        "config": workload_config(a, a.kf, note=f"each step = a bounded sample ({a.cpu_sample_kf} keyframes) of the workload; CPU restatement of the "
+                                  "reference path (the reference needs OpenCV/Eigen/Boost/CGAL headers absent here)"),
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(a, kf_per_gpu, note=None):
+    c = {"workload": f"BASELINE config[1]: {kf_per_gpu}-keyframe synthetic fr3_long_office-like trajectory per GPU, "
+                     f"640x480, TUM fr3 intrinsics, {a.nbr} covisible neighbours, epipolar search + fusion"
+                     f"{' + intra-keyframe checks' if a.intra else ''} + inter-keyframe check + point set",
+         "keyframes_per_gpu": kf_per_gpu, "neighbours": a.nbr, "intra": bool(a.intra), "seed": a.seed,
+         "l2": f"inputs larger than L2: {kf_per_gpu} keyframes x 8.3 MB of packed planes read per step vs 126 MB L2",
+         "parallelism": f"keyframe shards x{a.gpus}, halo (rho,sigma) planes pulled over NVLink (CUDA IPC peer copies)"
+                        if a.gpus > 1 else "single GPU"}
+    if note:
+        c["note"] = note
+    return c
+
+
+# ------------------------------------------------------------------------------------------------
+def pinned(api_lib, shape, dtype, keep):
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    rc = api_lib.sdm_host_alloc(C.byref(p), n)
+    if rc:
+        raise RuntimeError("sdm_host_alloc failed: " + api_lib.sdm_last_error().decode())
+    keep.append(p)
+    buf = (C.c_char * n).from_address(p.value)
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+
+def main_ours(a, rank, world, local_rank):
+    dist = None
+    nb_global = synth.neighbours(a.kf * world, a.nbr)
+    plan = shard.make_plan(nb_global, a.kf, rank, world)
+    nb_local = np.where(plan.nbr_local >= 0, plan.nbr_local, 0).astype(np.int32)
+    sc = load_scene(plan.n_local, plan.lo, nb_local, a.seed, "gpu")  # before CUDA init (forks workers)
+
+    import torch
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from sdmb200 import api
+    lib = api.load()  # raises if the CUDA library is absent: there is no fallback
+    ctx = api.Context(width=W, height=H, max_keyframes=plan.n_local, intra_check=a.intra, intra_grow=a.intra,
+                      device=local_rank)
+    keep = []
+    n_loc, owned = plan.n_local, list(plan.owned_local)
+    h_im = pinned(lib, (n_loc, H, W), np.uint8, keep); h_im[:] = sc.im
+    h_g = pinned(lib, (n_loc, H, W), np.float32, keep); h_g[:] = sc.grad
+    h_t = pinned(lib, (n_loc, H, W), np.float32, keep); h_t[:] = sc.theta
+    sc.im, sc.grad, sc.theta = h_im, h_g, h_t
+    out = {k: pinned(lib, (len(owned), H, W) + ((3,) if k == "points" else ()), np.float32, keep)
+           for k in ("depth", "sigma", "checked", "points")}
+
+    if world > 1:  # exchange CUDA-IPC handles of the (rho,sigma) arenas once
+        handles = [None] * world
+        dist.all_gather_object(handles, ctx.export_arena())
+        for r in set(int(x) for x in plan.halo_rank):
+            ctx.import_peer_arena(r, handles[r])
+        for s in plan.halo_local:  # halo slots: poses/calibration known locally, planes arrive from the owner
+            pass
+
+    items = api.make_items(owned, sc.nbr_idx, sc.rot, sc.min_depth, sc.max_depth)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def upload():
+        ctx.upload_scene(sc)
+
+    def step():
+        ctx.pass1(items)
+        if world > 1:
+            ctx.synchronize(); barrier()
+            ctx.pull_halo(plan.halo_local, plan.halo_rank, plan.halo_peer_slot)
+        ctx.pass2(items)
+        if world > 1:
+            ctx.synchronize(); barrier()
+
+    def download():
+        for k, s in enumerate(owned):
+            ctx.download(s, out={n: v[k] for n, v in out.items()})
+
+    upload(); ctx.synchronize()
+    cands = sum(ctx.candidate_count(s) for s in owned)
+    for _ in range(max(3, a.warmup)):
+        step()
+    ctx.synchronize(); barrier(); torch.cuda.synchronize()
+    clocks = Clocks(local_rank)
+    if rank == 0:
+        clocks.start(); time.sleep(0.3)
+    l0, t0 = ctx.launch_count(), time.time()
+    ctx.mark(0)
+    for _ in range(a.steps):
+        step()
+    ctx.mark(1)
+    ctx.synchronize(); torch.cuda.synchronize(); barrier()
+    t1 = time.time()
+    ms = ctx.elapsed_ms(0, 1) / a.steps
+    launches = ctx.launch_count() - l0
+    timing = ctx.last_timing()
+    stats = ctx.stats()
+
+    # ---- end to end through the C-ABI with host buffers
+    e2e = None
+    if not a.no_e2e:
+        def e2e_step():
+            upload(); step(); download(); ctx.synchronize()
+        e2e_step()
+        barrier(); tt = time.perf_counter()
+        for _ in range(a.steps):
+            e2e_step()
+        barrier(); e2e_s = (time.perf_counter() - tt) / a.steps
+        e2e = {"sec": e2e_s, "h2d": int(n_loc * W * H * 9), "d2h": int(len(owned) * W * H * 24)}
+    if rank == 0:
+        clocks.stop()
+
+    tot_cands, ms_max, e2e_max = cands, ms, (e2e["sec"] if e2e else 0.0)
+    if world > 1:
+        v = torch.tensor([float(cands)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(v); tot_cands = int(v.item())
+        m = torch.tensor([ms, e2e_max], device="cuda", dtype=torch.float64)
+        dist.all_reduce(m, op=dist.ReduceOp.MAX); ms_max, e2e_max = m.tolist()
+    if rank != 0:
+        ctx.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    n_own = len(owned)
+    p1_bytes = bytes_pass1(n_own, a.nbr)
+    ach = p1_bytes / (timing["pass1_scan_ms"] * 1e-3) / 1e9
+    whole = bytes_total(n_own * world, a.nbr, a.intra) / (ms_max * 1e-3) / 1e9 / world
+    line = {
+        "metric": METRIC, "value": tot_cands / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
+        "warmup": max(3, a.warmup), "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 (f64 where OpenCV accumulates in double)", "data": "synthetic",
+        "config": workload_config(a, a.kf),
+        "candidates_per_step": tot_cands, "keyframes_per_s": n_own * world / (ms_max * 1e-3),
+        "image_px_per_s": n_own * world * W * H / (ms_max * 1e-3),
+        "fused_per_step_rank0": stats["fused"], "checked_per_step_rank0": stats["checked"],
+        "kernel_ms_rank0": timing,
+        "roofline": {"bound": "hbm", "kernel": "k_pass1 (epipolar scan + hypothesis fusion)", "achieved": ach,
+                     "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": ncu_traffic(),
+                     "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": p1_bytes,
+                     "model": "(17 + 9N) * W*H bytes per keyframe x keyframes per launch (SURVEY.md 8d)",
+                     "whole_path_achieved_per_gpu": whole, "whole_path_frac": whole / peak},
+        "clocks": clocks.summary(t0, t1),
+        "gpu_launches": int(launches),
+    }
+    if e2e:
+        line["e2e"] = {"value": tot_cands / e2e_max, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
+                       "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": 1e3 * e2e_max,
+                       "api": "sdm_upload_keyframe / sdm_pass1 / sdm_pass2 / sdm_download on pinned host planes"}
+    ctx.close()
+    if world == 1 and not a.no_cpu_baseline:
+        r = cpu_run(a.cpu_sample_kf, a.nbr, a.seed, a.intra, 1, 0)
+        line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1 and a.gpus > 1:
+        # not under torchrun: relaunch ourselves the way the driver does
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={a.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", os.environ.get("MASTER_PORT", "29531"),
+               os.path.abspath(__file__)] + sys.argv[1:]
+        sys.exit(subprocess.call(cmd))
+    a.gpus = world
+    if a.impl == "reference":
+        main_reference(a, rank)
+    else:
+        main_ours(a, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

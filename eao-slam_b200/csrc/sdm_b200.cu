@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -73,7 +74,9 @@ struct sdm_ctx {
     std::vector<KfState> kf;
     cudaStream_t s_compute = nullptr, s_copy = nullptr;
     cudaEvent_t ev_copy = nullptr, ev_compute = nullptr;
-    cudaEvent_t ev_p1[2] = {nullptr, nullptr}, ev_p2[2] = {nullptr, nullptr};
+    cudaEvent_t ev_p1[2] = {nullptr, nullptr}, ev_p2[2] = {nullptr, nullptr}, ev_p1_scan = nullptr;
+    cudaEvent_t marks[SDM_N_MARKS] = {nullptr};
+    bool mark_set[SDM_N_MARKS] = {false};
     bool p1_timed = false, p2_timed = false;
     Stage stage[kStages];
     int stage_next = 0;
@@ -91,6 +94,7 @@ struct sdm_ctx {
     void* peer_rs[kMaxPeers] = {nullptr};
     long long launches = 0;
     long long stat_candidates = 0;
+    int scan_warp_per_pixel = 0;  // developer A/B knob (env SDM_SCAN=warp): the warp-per-pixel scan kernel
 };
 
 namespace {
@@ -261,7 +265,9 @@ void sdm_destroy(sdm_ctx* c)
     cudaFree(c->dl_stage); cudaFree(c->dbg);
     if (c->h_items) cudaFreeHost(c->h_items);
     if (c->h_blk_off) cudaFreeHost(c->h_blk_off);
-    for (cudaEvent_t e : {c->ev_copy, c->ev_compute, c->ev_p1[0], c->ev_p1[1], c->ev_p2[0], c->ev_p2[1]})
+    for (cudaEvent_t e : {c->ev_copy, c->ev_compute, c->ev_p1[0], c->ev_p1[1], c->ev_p2[0], c->ev_p2[1], c->ev_p1_scan})
+        if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->marks)
         if (e) cudaEventDestroy(e);
     if (c->s_compute) cudaStreamDestroy(c->s_compute);
     if (c->s_copy) cudaStreamDestroy(c->s_copy);
@@ -283,6 +289,7 @@ static int create_impl(sdm_ctx* c)
     const size_t P = (size_t)cfg.width * cfg.height;
     const size_t n = (size_t)cfg.max_keyframes;
     c->npix = P;
+    if (const char* e = getenv("SDM_SCAN")) c->scan_warp_per_pixel = (strcmp(e, "warp") == 0);
     c->kf.assign(n, KfState());
     sdm::DevParams& D = c->P;
     D.W = cfg.width;
@@ -308,6 +315,8 @@ static int create_impl(sdm_ctx* c)
         CU(cudaEventCreate(&c->ev_p1[i]));
         CU(cudaEventCreate(&c->ev_p2[i]));
     }
+    CU(cudaEventCreate(&c->ev_p1_scan));
+    for (auto& e : c->marks) CU(cudaEventCreate(&e));
     sdm::DevArena& A = c->A;
     memset(&A, 0, sizeof(A));
     A.P = P;
@@ -479,7 +488,8 @@ int sdm_pass1(sdm_ctx* c, int n, const sdm_item* items)
         c->h_blk_off[i] = (int)total_blocks;
         const int cnt = c->kf[items[i].kf].cand_count;
         cands += cnt;
-        total_blocks += (cnt + sdm::kPass1Warps - 1) / sdm::kPass1Warps;
+        const int per_block = c->scan_warp_per_pixel ? sdm::kPass1Warps : sdm::kLaneBlock;
+        total_blocks += (cnt + per_block - 1) / per_block;
     }
     c->h_blk_off[n] = (int)total_blocks;
     if (total_blocks > 0x7fffffffLL) return fail(SDM_ERR_ARG, "pass-1 batch too large (%lld blocks)", total_blocks);
@@ -490,11 +500,16 @@ int sdm_pass1(sdm_ctx* c, int n, const sdm_item* items)
     if (rc) return rc;
     CU(cudaEventRecord(c->ev_p1[0], c->s_compute));
     if (total_blocks > 0) {
-        sdm::k_pass1<<<(unsigned)total_blocks, sdm::kPass1Warps * 32, 0, c->s_compute>>>(c->A, c->P, c->d_items,
-                                                                                        c->d_blk_off, n, c->d_stats);
+        if (c->scan_warp_per_pixel)
+            sdm::k_pass1<<<(unsigned)total_blocks, sdm::kPass1Warps * 32, 0, c->s_compute>>>(c->A, c->P, c->d_items,
+                                                                                            c->d_blk_off, n, c->d_stats);
+        else
+            sdm::k_pass1_lane<<<(unsigned)total_blocks, sdm::kLaneBlock, 0, c->s_compute>>>(c->A, c->P, c->d_items,
+                                                                                           c->d_blk_off, n, c->d_stats);
         CU(cudaGetLastError());
         c->launches++;
     }
+    CU(cudaEventRecord(c->ev_p1_scan, c->s_compute));
     if (c->cfg.intra_check || c->cfg.intra_grow)
         for (int i = 0; i < n; ++i) {
             rc = run_intra(c, items[i].kf, c->cfg.intra_check != 0, c->cfg.intra_grow != 0);
@@ -850,5 +865,43 @@ int sdm_last_pass_ms(sdm_ctx* c, float* pass1_ms, float* pass2_ms)
 }
 
 long long sdm_launch_count(sdm_ctx* c) { return c ? c->launches : 0; }
+
+int sdm_last_timing(sdm_ctx* c, sdm_timing* out)
+{
+    if (!c || !out) return fail(SDM_ERR_ARG, "null argument");
+    CU(cudaSetDevice(c->cfg.device));
+    memset(out, 0, sizeof(*out));
+    if (c->p1_timed) {
+        CU(cudaEventSynchronize(c->ev_p1[1]));
+        CU(cudaEventElapsedTime(&out->pass1_scan_ms, c->ev_p1[0], c->ev_p1_scan));
+        CU(cudaEventElapsedTime(&out->pass1_intra_ms, c->ev_p1_scan, c->ev_p1[1]));
+    }
+    if (c->p2_timed) {
+        CU(cudaEventSynchronize(c->ev_p2[1]));
+        CU(cudaEventElapsedTime(&out->pass2_ms, c->ev_p2[0], c->ev_p2[1]));
+    }
+    return SDM_OK;
+}
+
+int sdm_mark(sdm_ctx* c, int idx)
+{
+    if (!c) return fail(SDM_ERR_ARG, "null context");
+    if (idx < 0 || idx >= SDM_N_MARKS) return fail(SDM_ERR_ARG, "mark %d out of [0,%d)", idx, SDM_N_MARKS);
+    CU(cudaSetDevice(c->cfg.device));
+    CU(cudaEventRecord(c->marks[idx], c->s_compute));
+    c->mark_set[idx] = true;
+    return SDM_OK;
+}
+
+int sdm_elapsed_ms(sdm_ctx* c, int from, int to, float* ms)
+{
+    if (!c || !ms) return fail(SDM_ERR_ARG, "null argument");
+    if (from < 0 || from >= SDM_N_MARKS || to < 0 || to >= SDM_N_MARKS) return fail(SDM_ERR_ARG, "mark out of range");
+    if (!c->mark_set[from] || !c->mark_set[to]) return fail(SDM_ERR_STATE, "mark not recorded");
+    CU(cudaSetDevice(c->cfg.device));
+    CU(cudaEventSynchronize(c->marks[to]));
+    CU(cudaEventElapsedTime(ms, c->marks[from], c->marks[to]));
+    return SDM_OK;
+}
 
 }  // extern "C"

@@ -290,6 +290,14 @@ __device__ __forceinline__ bool chi_compatible(float a, float b, float sa, float
     return chi < thr_lt;
 }
 
+// one term of GetFusion (:1669-1692): float accumulators updated through double
+__device__ __forceinline__ void fusion_accumulate(float d, float s, float& pjsj, float& rsj)
+{
+    const double s2 = (double)s * (double)s;
+    pjsj = (float)((double)pjsj + (double)d / s2);
+    rsj = (float)((double)rsj + 1.0 / s2);
+}
+
 // ---------------------------------------------------------------------------------------------
 // K1 + K2: plane packing + candidate compaction (KeyFrame.cc:63-88 planes as device buffers;
 // the candidate test of :454-456).  One thread per pixel, 32x8 tiles; one atomic per tile so a
@@ -469,6 +477,144 @@ k_pass1(DevArena A, DevParams P, const DevItem* __restrict__ items, const int* _
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// K3 + K4, lane-per-pixel variant (the default).  One thread owns one candidate pixel and walks the
+// search ranges of its N neighbours column by column, exactly like the reference's inner loop
+// (:770-821); the 32 lanes of a warp hold 32 neighbouring candidates of one 32x8 tile, whose
+// epipolar lines in a neighbour keyframe are nearly parallel and one column apart, so at every
+// step of the walk the warp's 16-byte texel loads fall on a few contiguous row segments.
+// Compared with the warp-per-pixel kernel: no shuffles, no idle lanes during set-up / refinement /
+// fusion, v(u+1) is carried to the next column instead of recomputed, the best column's residuals
+// are kept instead of re-evaluated.  Hypotheses of a pixel stay in shared memory ([nbr][thread]).
+// ---------------------------------------------------------------------------------------------
+constexpr int kLaneBlock = 128;
+
+__device__ __forceinline__ bool in_rows(float v, float Hm1) { return v >= 0.f && v <= Hm1; }
+
+__global__ void __launch_bounds__(kLaneBlock)
+k_pass1_lane(DevArena A, DevParams P, const DevItem* __restrict__ items, const int* __restrict__ blk_off, int n_items,
+             DevStats* stats)
+{
+    __shared__ DevItem s_item;
+    __shared__ float2 s_h[SDM_MAX_NBR][kLaneBlock];
+    int lo = 0, hi = n_items;
+    const int bid = blockIdx.x;
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (blk_off[mid] <= bid) lo = mid; else hi = mid;
+    }
+    {
+        const int* src = reinterpret_cast<const int*>(&items[lo]);
+        int* dst = reinterpret_cast<int*>(&s_item);
+        const int header = (int)(offsetof(DevItem, pair) / 4);
+        const int words = header + items[lo].n_nbr * (int)(sizeof(DevPair) / 4);
+        for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const int tid = threadIdx.x;
+    const int ci = (bid - blk_off[lo]) * kLaneBlock + tid;
+    const int kf = s_item.kf;
+    const bool active = ci < A.cand_count[kf];
+    bool fused = false;
+    if (active) {
+        const int N = s_item.n_nbr;
+        const uint32_t packed = A.cand[(size_t)kf * A.P + ci];
+        const int x = (int)(packed & 0xffffu), y = (int)(packed >> 16);
+        const size_t own = (size_t)kf * A.P + (size_t)y * P.W + x;
+        const float4 t1 = __ldg(&A.tex[own]);
+        const float gradc = t1.x, th_pi = t1.z;
+        const float pixel = (float)__ldg(&A.ipair[own]).x;
+        const float* K = s_item.K;
+        const float xn = (x - K[2]) / K[0], yn = (y - K[3]) / K[1];
+        const float Hm1 = (float)(P.H - 1);
+        const int W = P.W;
+        int nh = 0;
+        for (int j = 0; j < N; ++j) {
+            const DevPair& g = s_item.pair[j];
+            const PairSetup s = pair_setup(g, K, P, x, y, xn, yn, s_item.min_depth, s_item.max_depth, th_pi);
+            if (s.u_lo > s.u_hi) continue;
+            const size_t nb = (size_t)g.slot * A.P;
+            const float4* __restrict__ tex2 = A.tex + nb;
+            const uchar2* __restrict__ ip2 = A.ipair + nb;
+            const float ab = s.ab, cb = s.cb;
+            float best_err = 100000.0f, best_pe = 0.f, best_ge = 0.f;
+            int best_u = -1;
+            float v_m = -(ab * (float)(s.u_lo - 1) + cb);
+            float v_c = -(ab * (float)s.u_lo + cb);
+            bool in_m = in_rows(v_m, Hm1), in_c = in_rows(v_c, Hm1);
+            for (int u = s.u_lo; u <= s.u_hi; ++u) {
+                const float v_p = -(ab * (float)(u + 1) + cb);
+                const bool in_p = in_rows(v_p, Hm1);
+                const bool inside = in_m && in_c && in_p;
+                const float v = v_c;
+                v_m = v_c; v_c = v_p; in_m = in_c; in_c = in_p;
+                if (!inside) continue;
+                const RowW r = row_weights(v);
+                const int idx = r.y0 * W + u;
+                const float4 t = __ldg(&tex2[idx]);
+                const float g2 = t.x * r.w0 + t.y * r.w1;
+                if (g2 <= P.lambdaG) continue;  // condition 1
+                const float gth = yangle_interp(t.z, t.w, r.w0, r.w1);
+                float ang = gth - s.th_line;  // condition 2
+                if (ang >= 360.f) ang -= 360.f;
+                if (ang < 0.f) ang += 360.f;
+                if (ang > 180.f) ang = 360.f - ang;
+                if (ang > 90.f) ang = 180.f - ang;
+                if (ang >= P.lambdaL) continue;
+                float thd = gth - s.ang_pi_rot;  // condition 3
+                if (thd >= 360.f) thd -= 360.f;
+                if (thd < 0.f) thd += 360.f;
+                if (thd > 180.f) thd = 360.f - thd;
+                if (thd >= P.lambdaTheta) continue;
+                const uchar2 i2 = __ldg(&ip2[idx]);
+                const float pe = pixel - ((float)i2.x * r.w0 + (float)i2.y * r.w1);
+                const float ge = gradc - g2;
+                const float err = pe * pe + (ge * ge) / P.theta;
+                if (err < best_err) { best_err = err; best_u = u; best_pe = pe; best_ge = ge; }
+            }
+            if (best_err < 100000.0f) {
+                const Hypo h = refine_hypothesis(tex2, ip2, g, K, P, best_u, ab, cb, best_pe, best_ge, xn, yn);
+                if (1.0f / h.depth > 0.0f) {  // :472
+                    s_h[nh][tid] = make_float2(h.depth, h.sigma);
+                    ++nh;
+                }
+            }
+        }
+        // InverseDepthHypothesisFusion (:978-1009) over this pixel's nh hypotheses (neighbour order)
+        float out_d = 0.f, out_s = 0.f;
+        if (nh > P.lambdaN) {
+            unsigned best_mask = 0;
+            int best_n = 0;
+            for (int a = 0; a < nh; ++a) {
+                const float2 ha = s_h[a][tid];
+                unsigned m = 1u << a;
+                for (int b = 0; b < nh; ++b) {
+                    if (b == a) continue;
+                    const float2 hb = s_h[b][tid];
+                    if (chi_compatible(ha.x, hb.x, ha.y, hb.y, P.chi_fusion_lt)) m |= 1u << b;
+                }
+                const int cnt = __popc(m);
+                if (best_n < cnt) { best_n = cnt; best_mask = m; }
+            }
+            if (best_n > P.lambdaN) {
+                float pjsj = 0.f, rsj = 0.f;
+                for (unsigned rem = best_mask; rem; rem &= rem - 1) {
+                    const float2 hb = s_h[__ffs(rem) - 1][tid];
+                    fusion_accumulate(hb.x, hb.y, pjsj, rsj);
+                }
+                out_d = pjsj / rsj;
+                out_s = sqrtf(1.0f / rsj);
+                fused = true;
+            }
+        }
+        A.rs[own] = make_float2(out_d, out_s);
+    }
+    if (stats) {
+        const unsigned bal = __ballot_sync(SDM_FULL, fused);
+        if ((threadIdx.x & 31) == 0 && bal) atomicAdd(&stats->fused, (unsigned long long)__popc(bal));
+    }
+}
+
 // per-pair raw hypotheses for every candidate pixel of kf1 (granularity of one EpipolarSearch call)
 __global__ void __launch_bounds__(kPass1Warps * 32)
 k_pair_hypotheses(DevArena A, DevParams P, const DevItem* __restrict__ item, float* __restrict__ hyp_d,
@@ -582,12 +728,6 @@ __global__ void __launch_bounds__(256) k_fuse_sets(DevParams P, int m, int n, co
 // K5: IntraKeyFrameDepthChecking (:866-927) and IntraKeyFrameDepthGrowing (:929-976): 3x3 Jacobi
 // stencils on the (rho, sigma) plane; src is a snapshot of the plane, dst the plane itself.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void fusion_accumulate(float d, float s, float& pjsj, float& rsj)
-{
-    const double s2 = (double)s * (double)s;
-    pjsj = (float)((double)pjsj + (double)d / s2);
-    rsj = (float)((double)rsj + 1.0 / s2);
-}
 
 __global__ void __launch_bounds__(256) k_intra_check(DevParams P, const float2* __restrict__ src, float2* __restrict__ dst)
 {

@@ -47,6 +47,10 @@ class Hypothesis(C.Structure):
                 ("best_u", C.c_float), ("best_v", C.c_float)]
 
 
+class Timing(C.Structure):
+    _fields_ = [("pass1_scan_ms", C.c_float), ("pass1_intra_ms", C.c_float), ("pass2_ms", C.c_float)]
+
+
 class Stats(C.Structure):
     _fields_ = [("candidates", C.c_longlong), ("fused", C.c_longlong), ("checked", C.c_longlong)]
 
@@ -59,7 +63,7 @@ EXPORTS = [
     "sdm_upload_depth", "sdm_depth_plane_ptr", "sdm_export_arena", "sdm_import_peer_arena", "sdm_pull_halo",
     "sdm_mark_pass1_done", "sdm_pair_geometry", "sdm_stereo_search_constraints", "sdm_search_range",
     "sdm_epipolar_search", "sdm_epipolar_search_plane", "sdm_fuse", "sdm_intra_check", "sdm_intra_grow",
-    "sdm_inter_check", "sdm_last_pass_ms", "sdm_launch_count",
+    "sdm_inter_check", "sdm_last_pass_ms", "sdm_launch_count", "sdm_last_timing", "sdm_mark", "sdm_elapsed_ms",
 ]
 
 _lib = None
@@ -113,6 +117,9 @@ def load() -> C.CDLL:
     lib.sdm_last_pass_ms.argtypes = [vp, fp, fp]
     lib.sdm_launch_count.argtypes = [vp]
     lib.sdm_launch_count.restype = C.c_longlong
+    lib.sdm_last_timing.argtypes = [vp, C.POINTER(Timing)]
+    lib.sdm_mark.argtypes = [vp, C.c_int]
+    lib.sdm_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, fp]
     _lib = lib
     return lib
 
@@ -266,6 +273,19 @@ class Context:
         a, b = C.c_float(), C.c_float()
         self._chk(self.lib.sdm_last_pass_ms(self.h, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def last_timing(self) -> dict:
+        t = Timing()
+        self._chk(self.lib.sdm_last_timing(self.h, C.byref(t)))
+        return {"pass1_scan_ms": t.pass1_scan_ms, "pass1_intra_ms": t.pass1_intra_ms, "pass2_ms": t.pass2_ms}
+
+    def mark(self, idx: int):
+        self._chk(self.lib.sdm_mark(self.h, idx))
+
+    def elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_float()
+        self._chk(self.lib.sdm_elapsed_ms(self.h, a, b, C.byref(ms)))
+        return ms.value
 
     def launch_count(self) -> int:
         return int(self.lib.sdm_launch_count(self.h))

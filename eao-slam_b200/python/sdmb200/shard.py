@@ -1,0 +1,67 @@
+"""Keyframe sharding over ranks.
+
+Pass 1 of a keyframe reads only immutable inputs of its neighbours; pass 2 reads the neighbours'
+pass-1 planes (ProbabilityMapping.cc:1202-1249).  So the path shards by keyframe with exactly one
+exchange step: every rank owns a contiguous range of keyframes, keeps the INPUT planes of the few
+neighbour keyframes outside its range as well (halo), and between the passes pulls the halo
+keyframes' (rho, sigma) planes from their owners over NVLink.  No reduction, no other collective.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+
+@dataclass
+class ShardPlan:
+    rank: int
+    world: int
+    per_rank: int            # owned keyframes per rank
+    lo: int                  # first global keyframe held locally (owned or halo)
+    hi: int                  # one past the last global keyframe held locally
+    own_lo: int              # owned range [own_lo, own_hi)
+    own_hi: int
+    nbr_local: np.ndarray    # [hi-lo, N] local slots of each local keyframe's neighbours (-1: not held)
+    halo_local: np.ndarray   # local slots whose pass-1 planes come from a peer
+    halo_rank: np.ndarray    # owner rank of each halo keyframe
+    halo_peer_slot: np.ndarray  # slot of that keyframe in the owner's arena
+
+    @property
+    def n_local(self) -> int:
+        return self.hi - self.lo
+
+    @property
+    def owned_local(self) -> range:
+        return range(self.own_lo - self.lo, self.own_hi - self.lo)
+
+
+def held_range(nbr_global: np.ndarray, own_lo: int, own_hi: int):
+    """Contiguous global range covering the owned keyframes and all their neighbours."""
+    nb = nbr_global[own_lo:own_hi]
+    return int(min(own_lo, nb.min())), int(max(own_hi, nb.max() + 1))
+
+
+def make_plan(nbr_global: np.ndarray, per_rank: int, rank: int, world: int) -> ShardPlan:
+    """nbr_global: [G, N] neighbour lists over the whole trajectory, G = per_rank * world."""
+    G = nbr_global.shape[0]
+    assert G == per_rank * world, (G, per_rank, world)
+    own_lo, own_hi = rank * per_rank, (rank + 1) * per_rank
+    lo, hi = held_range(nbr_global, own_lo, own_hi)
+    nbr_local = np.full((hi - lo, nbr_global.shape[1]), -1, np.int32)
+    for g in range(lo, hi):
+        for j, v in enumerate(nbr_global[g]):
+            if lo <= v < hi:
+                nbr_local[g - lo, j] = v - lo
+    halo = [g for g in range(lo, hi) if not (own_lo <= g < own_hi)]
+    # a halo keyframe is only needed if an OWNED keyframe lists it
+    needed = set(int(v) for v in nbr_global[own_lo:own_hi].reshape(-1))
+    halo = [g for g in halo if g in needed]
+    h_rank = [g // per_rank for g in halo]
+    h_slot = []
+    for g, r in zip(halo, h_rank):
+        plo, _ = held_range(nbr_global, r * per_rank, (r + 1) * per_rank)
+        h_slot.append(g - plo)
+    return ShardPlan(rank, world, per_rank, lo, hi, own_lo, own_hi, nbr_local,
+                     np.asarray([g - lo for g in halo], np.int32), np.asarray(h_rank, np.int32),
+                     np.asarray(h_slot, np.int32))

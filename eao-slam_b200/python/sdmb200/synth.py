@@ -94,12 +94,13 @@ DESK_LO = np.array([-0.8, 0.25, -0.5])
 DESK_HI = np.array([0.8, 1.3, 0.5])
 
 
-def trajectory(n: int, step_m: float = 0.05, radius: float = 1.6, phase0: float = 0.3) -> np.ndarray:
-    """Tcw [n,3,4] float32: camera circling the desk, looking at it, roll-free, y down."""
+def trajectory(n: int, step_m: float = 0.05, radius: float = 1.6, phase0: float = 0.3, first: int = 0) -> np.ndarray:
+    """Tcw [n,3,4] float32: camera circling the desk, looking at it, roll-free, y down.
+    `first` is the global index of the first pose (a slice of one long trajectory)."""
     T = np.zeros((n, 3, 4), np.float64)
     dphi = step_m / radius
     for i in range(n):
-        phi = phase0 + i * dphi
+        phi = phase0 + (first + i) * dphi
         r = radius + 0.2 * np.cos(2 * phi)
         Ow = np.array([r * np.cos(phi), -0.35 + 0.15 * np.sin(3 * phi), r * np.sin(phi)])
         target = np.array([0.1 * np.sin(phi), 0.35, 0.1 * np.cos(1.7 * phi)])
@@ -192,16 +193,44 @@ def stereo_search_constraints(inv_depths: np.ndarray):
     return np.float32(min_depth), np.float32(max_depth)
 
 
+_GEN = {}  # per-process generator state (textures, poses) for the keyframe worker
+
+
+def _make_kf(i: int):
+    g = _GEN
+    W, H, K, seed, first = g["W"], g["H"], g["K"], g["seed"], g["first"]
+    im, depth = _render(g["Tcw"][i], K, W, H, g["tex"], g["box_tex"])
+    grad, theta = gradient_planes(im)
+    pick = np.random.default_rng([seed, first + i]).integers(0, W * H, size=500)
+    rho = 1.0 / depth.reshape(-1)[pick]
+    if g["wide_range"]:  # config C4: force a wide search interval
+        rho = np.concatenate([rho, [1 / 0.4, 1 / 8.0]]).astype(np.float32)
+    mind, maxd = stereo_search_constraints(rho)
+    if mind <= 0:  # mean - 2 sigma <= 0: the reference has no guard; keep the scan bounded
+        mind = np.float32(1.0 / max(float(np.min(rho)) * 0.5, 1e-3))
+    edge = None
+    if g["edge_mask"]:  # a synthetic mEdgeIndex: segment id >= 0 on strong-gradient ridges, -1 elsewhere
+        ridge = (grad > 10) & ((grad >= np.roll(grad, 1, 0)) & (grad >= np.roll(grad, -1, 0)) |
+                               (grad >= np.roll(grad, 1, 1)) & (grad >= np.roll(grad, -1, 1)))
+        edge = np.where(ridge, (np.arange(W * H, dtype=np.int32).reshape(H, W) // 97), -1).astype(np.int32)
+    return i, im, grad, theta, (depth if g["keep_depth"] else None), mind, maxd, edge
+
+
 def make_scene(n_kf: int, W: int = 640, H: int = 480, n_nbr: int = 6, seed: int = 1,
                step_m: float = 0.05, K=None, keep_depth: bool = False, contrast: float = 0.6,
-               wide_range: bool = False, edge_mask: bool = False, phase0: float = 0.3) -> Scene:
-    """Build a keyframe set.  K defaults to TUM fr3 intrinsics scaled by W/640."""
+               wide_range: bool = False, edge_mask: bool = False, phase0: float = 0.3, first: int = 0,
+               workers: int = 1, nbr_idx: np.ndarray | None = None) -> Scene:
+    """Build a keyframe set.  K defaults to TUM fr3 intrinsics scaled by W/640.  `first` = global
+    index of keyframe 0 on the trajectory: make_scene(n, first=f) equals keyframes [f, f+n) of one
+    long trajectory through the same world (textures depend on `seed` only, the per-keyframe depth
+    samples on (seed, global index)), which is how bench.py shards a trajectory over ranks.
+    workers > 1 renders keyframes in forked worker processes (call before CUDA is initialised)."""
     rng = np.random.default_rng(seed)
     if K is None:
         s = W / 640.0
         K = tuple(float(np.float32(v * s)) for v in TUM3_K)
     tex, box_tex = _Texture(rng, contrast=contrast), _Texture(rng, contrast=contrast)
-    Tcw = trajectory(n_kf, step_m=step_m, phase0=phase0)
+    Tcw = trajectory(n_kf, step_m=step_m, phase0=phase0, first=first)
     im = np.zeros((n_kf, H, W), np.uint8)
     grad = np.zeros((n_kf, H, W), np.float32)
     theta = np.zeros((n_kf, H, W), np.float32)
@@ -209,24 +238,25 @@ def make_scene(n_kf: int, W: int = 640, H: int = 480, n_nbr: int = 6, seed: int 
     mind = np.zeros(n_kf, np.float32)
     maxd = np.zeros(n_kf, np.float32)
     edge = np.zeros((n_kf, H, W), np.int32) if edge_mask else None
-    for i in range(n_kf):
-        im[i], depth = _render(Tcw[i], K, W, H, tex, box_tex)
-        grad[i], theta[i] = gradient_planes(im[i])
+    _GEN.update(W=W, H=H, K=K, seed=seed, first=first, Tcw=Tcw, tex=tex, box_tex=box_tex,
+                wide_range=wide_range, edge_mask=edge_mask, keep_depth=keep_depth)
+    if workers > 1 and n_kf >= 2 * workers:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(workers) as pool:
+            results = pool.imap_unordered(_make_kf, range(n_kf), chunksize=2)
+            results = list(results)
+    else:
+        results = (_make_kf(i) for i in range(n_kf))
+    for i, a, g, t, d, lo, hi, e in results:
+        im[i], grad[i], theta[i], mind[i], maxd[i] = a, g, t, lo, hi
         if keep_depth:
-            dgt[i] = depth
-        pick = rng.integers(0, W * H, size=500)
-        rho = 1.0 / depth.reshape(-1)[pick]
-        if wide_range:  # config C4: force a wide search interval
-            rho = np.concatenate([rho, [1 / 0.4, 1 / 8.0]]).astype(np.float32)
-        mind[i], maxd[i] = stereo_search_constraints(rho)
-        if mind[i] <= 0:  # mean - 2 sigma <= 0: the reference has no guard; keep the scan bounded
-            mind[i] = np.float32(1.0 / max(float(np.min(rho)) * 0.5, 1e-3))
-        if edge_mask:  # a synthetic mEdgeIndex: segment id >= 0 on strong-gradient ridges, -1 elsewhere
-            g = grad[i]
-            ridge = (g > 10) & ((g >= np.roll(g, 1, 0)) & (g >= np.roll(g, -1, 0)) |
-                                (g >= np.roll(g, 1, 1)) & (g >= np.roll(g, -1, 1)))
-            edge[i] = np.where(ridge, (np.arange(W * H, dtype=np.int32).reshape(H, W) // 97), -1)
+            dgt[i] = d
+        if edge_mask:
+            edge[i] = e
+    _GEN.clear()
+    if nbr_idx is None:
+        nbr_idx = neighbours(n_kf, n_nbr)
     return Scene(im=im, grad=grad, theta=theta, edge=edge, K=K, Tcw=Tcw,
-                 nbr_idx=neighbours(n_kf, n_nbr), rot=np.zeros((n_kf, n_nbr), np.float32),
+                 nbr_idx=nbr_idx, rot=np.zeros(nbr_idx.shape, np.float32),
                  min_depth=mind, max_depth=maxd, depth_gt=dgt,
-                 meta={"seed": seed, "step_m": step_m, "planes": "cv2" if cv2 is not None else "numpy"})
+                 meta={"seed": seed, "step_m": step_m, "first": first, "planes": "cv2" if cv2 is not None else "numpy"})

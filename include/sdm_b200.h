@@ -186,6 +186,19 @@ int sdm_inter_check(sdm_ctx* ctx, const sdm_item* item);
  * compute stream (0 if none); number of kernel launches issued since context creation */
 int sdm_last_pass_ms(sdm_ctx* ctx, float* pass1_ms, float* pass2_ms);
 long long sdm_launch_count(sdm_ctx* ctx);
+/* per-kernel split of the same: the epipolar scan + fusion kernel, the optional intra stencils, pass 2
+ * (the per-stage "took ... ms" prints of ProbabilityMapping.cc:389-443, :505-508, :545-565) */
+typedef struct {
+    float pass1_scan_ms;
+    float pass1_intra_ms;
+    float pass2_ms;
+} sdm_timing;
+int sdm_last_timing(sdm_ctx* ctx, sdm_timing* out);
+/* user marks on the context's compute stream (CUDA events), for timing a whole SemiDenseLoop the way
+ * :246-254 does with clock_gettime: sdm_mark(idx) records, sdm_elapsed_ms blocks until `to` completed */
+#define SDM_N_MARKS 8
+int sdm_mark(sdm_ctx* ctx, int idx);
+int sdm_elapsed_ms(sdm_ctx* ctx, int from, int to, float* ms);
 
 #ifdef __cplusplus
 }
