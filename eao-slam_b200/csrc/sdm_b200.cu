@@ -730,7 +730,8 @@ int sdm_search_range(sdm_ctx* c, int kf1, int kf2, int px, int py, float mind, f
     return SDM_OK;
 }
 
-int sdm_epipolar_search(sdm_ctx* c, int kf1, int kf2, int x, int y, float min_depth, float max_depth, float rot_deg,
+int sdm_epipolar_search(sdm_ctx* c, int kf1, int kf2, int x, int y, float pixel, float min_depth, float max_depth,
+                        float th_pi, float rot_deg,
                         sdm_hypothesis* out)
 {
     if (!c || !out) return fail(SDM_ERR_ARG, "null argument");
@@ -743,7 +744,7 @@ int sdm_epipolar_search(sdm_ctx* c, int kf1, int kf2, int x, int y, float min_de
     float* d = c->dbg;
     uint8_t* ok = (uint8_t*)(c->dbg + 4);
     sdm::k_pair_hypotheses<<<1, sdm::kPass1Warps * 32, 0, c->s_compute>>>(c->A, c->P, c->d_items, d, d + 1, d + 2, d + 3, ok,
-                                                                          (y << 16) | x);
+                                                                          (y << 16) | x, pixel, th_pi);
     CU(cudaGetLastError());
     c->launches++;
     float h[5];
@@ -775,7 +776,7 @@ int sdm_epipolar_search_plane(sdm_ctx* c, int kf1, int kf2, float min_depth, flo
     const int cnt = c->kf[kf1].cand_count;
     if (cnt > 0) {
         sdm::k_pair_hypotheses<<<(cnt + sdm::kPass1Warps - 1) / sdm::kPass1Warps, sdm::kPass1Warps * 32, 0, c->s_compute>>>(
-            c->A, c->P, c->d_items, d, d + P, d + 2 * P, nullptr, dok, -1);
+            c->A, c->P, c->d_items, d, d + P, d + 2 * P, nullptr, dok, -1, 0.f, 0.f);
         CU(cudaGetLastError());
         c->launches++;
     }

@@ -619,7 +619,7 @@ k_pass1_lane(DevArena A, DevParams P, const DevItem* __restrict__ items, const i
 __global__ void __launch_bounds__(kPass1Warps * 32)
 k_pair_hypotheses(DevArena A, DevParams P, const DevItem* __restrict__ item, float* __restrict__ hyp_d,
                   float* __restrict__ hyp_s, float* __restrict__ hyp_u, float* __restrict__ hyp_v,
-                  uint8_t* __restrict__ hyp_ok, int single_xy)
+                  uint8_t* __restrict__ hyp_ok, int single_xy, float pixel_arg, float th_pi_arg)
 {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kf = item->kf;
@@ -638,8 +638,10 @@ k_pair_hypotheses(DevArena A, DevParams P, const DevItem* __restrict__ item, flo
     const DevPair g = item->pair[0];
     const float K[4] = {item->K[0], item->K[1], item->K[2], item->K[3]};
     const float4 t1 = __ldg(&A.tex[(size_t)kf * A.P + (size_t)y * P.W + x]);
-    const float gradc = t1.x, th_pi = t1.z;
-    const float pixel = (float)__ldg(&A.ipair[(size_t)kf * A.P + (size_t)y * P.W + x]).x;
+    const float gradc = t1.x;
+    // EpipolarSearch takes `pixel` and `th_pi` from its caller (:466-470); the plane mode reads them like :457,:466
+    const float th_pi = (single_xy >= 0) ? th_pi_arg : t1.z;
+    const float pixel = (single_xy >= 0) ? pixel_arg : (float)__ldg(&A.ipair[(size_t)kf * A.P + (size_t)y * P.W + x]).x;
     const float xn = (x - K[2]) / K[0], yn = (y - K[3]) / K[1];
     const float Hm1 = (float)(P.H - 1);
     const PairSetup s = pair_setup(g, K, P, x, y, xn, yn, item->min_depth, item->max_depth, th_pi);

@@ -108,6 +108,7 @@ def load() -> C.CDLL:
     lib.sdm_stereo_search_constraints.argtypes = [fp, C.c_int, fp, fp]
     lib.sdm_search_range.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, fp, fp]
     lib.sdm_epipolar_search.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float,
+                                        C.c_float, C.c_float,
                                         C.POINTER(Hypothesis)]
     lib.sdm_epipolar_search_plane.argtypes = [vp, C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, vp, vp, vp, vp]
     lib.sdm_fuse.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp]
@@ -296,9 +297,9 @@ class Context:
         self._chk(self.lib.sdm_search_range(self.h, kf1, kf2, px, py, mind, maxd, C.byref(a), C.byref(b)))
         return a.value, b.value
 
-    def epipolar_search(self, kf1, kf2, x, y, mind, maxd, rot=0.0) -> Hypothesis:
+    def epipolar_search(self, kf1, kf2, x, y, pixel, mind, maxd, th_pi, rot=0.0) -> Hypothesis:
         h = Hypothesis()
-        self._chk(self.lib.sdm_epipolar_search(self.h, kf1, kf2, x, y, mind, maxd, rot, C.byref(h)))
+        self._chk(self.lib.sdm_epipolar_search(self.h, kf1, kf2, x, y, pixel, mind, maxd, th_pi, rot, C.byref(h)))
         return h
 
     def epipolar_search_plane(self, kf1, kf2, mind, maxd, rot=0.0):

@@ -35,6 +35,7 @@ class Scene:
     min_depth: np.ndarray   # [n] float32
     max_depth: np.ndarray   # [n] float32
     depth_gt: np.ndarray | None = None  # [n,H,W] float32 camera-z depth
+    inv_depths: list | None = None      # per keyframe: sorted float32 inverse depths (GetAllPointDepths stand-in)
     meta: dict = field(default_factory=dict)
 
     @property
@@ -213,7 +214,7 @@ def _make_kf(i: int):
         ridge = (grad > 10) & ((grad >= np.roll(grad, 1, 0)) & (grad >= np.roll(grad, -1, 0)) |
                                (grad >= np.roll(grad, 1, 1)) & (grad >= np.roll(grad, -1, 1)))
         edge = np.where(ridge, (np.arange(W * H, dtype=np.int32).reshape(H, W) // 97), -1).astype(np.int32)
-    return i, im, grad, theta, (depth if g["keep_depth"] else None), mind, maxd, edge
+    return i, im, grad, theta, (depth if g["keep_depth"] else None), mind, maxd, edge, np.sort(rho.astype(np.float32))
 
 
 def make_scene(n_kf: int, W: int = 640, H: int = 480, n_nbr: int = 6, seed: int = 1,
@@ -247,7 +248,9 @@ def make_scene(n_kf: int, W: int = 640, H: int = 480, n_nbr: int = 6, seed: int 
             results = list(results)
     else:
         results = (_make_kf(i) for i in range(n_kf))
-    for i, a, g, t, d, lo, hi, e in results:
+    inv_depths = [None] * n_kf
+    for i, a, g, t, d, lo, hi, e, rho in results:
+        inv_depths[i] = rho
         im[i], grad[i], theta[i], mind[i], maxd[i] = a, g, t, lo, hi
         if keep_depth:
             dgt[i] = d
@@ -258,5 +261,5 @@ def make_scene(n_kf: int, W: int = 640, H: int = 480, n_nbr: int = 6, seed: int 
         nbr_idx = neighbours(n_kf, n_nbr)
     return Scene(im=im, grad=grad, theta=theta, edge=edge, K=K, Tcw=Tcw,
                  nbr_idx=nbr_idx, rot=np.zeros(nbr_idx.shape, np.float32),
-                 min_depth=mind, max_depth=maxd, depth_gt=dgt,
+                 min_depth=mind, max_depth=maxd, depth_gt=dgt, inv_depths=inv_depths,
                  meta={"seed": seed, "step_m": step_m, "first": first, "planes": "cv2" if cv2 is not None else "numpy"})

@@ -163,9 +163,12 @@ int sdm_stereo_search_constraints(const float* inv_depths, int n, float* min_dep
 /* replaces: GetSearchRange (:1598-1631) */
 int sdm_search_range(sdm_ctx* ctx, int kf1, int kf2, int px, int py, float mind, float maxd,
                      float* umin, float* umax);
-/* replaces: EpipolarSearch (:749-845) for one pixel / one neighbour */
-int sdm_epipolar_search(sdm_ctx* ctx, int kf1, int kf2, int x, int y, float min_depth, float max_depth,
-                        float rot_deg, sdm_hypothesis* out);
+/* replaces: EpipolarSearch (:749-845) for one pixel / one neighbour, same argument meaning and order as
+ * the reference (kf1, kf2, x, y, pixel, min_depth, max_depth, dh, [F12: recomputed from the poses],
+ * best_u, best_v, th_pi, rot): `pixel` = kf1->im_(y,x) and `th_pi` = kf1->GradTheta(y,x) at the
+ * reference's call site (:457, :466-470) */
+int sdm_epipolar_search(sdm_ctx* ctx, int kf1, int kf2, int x, int y, float pixel, float min_depth, float max_depth,
+                        float th_pi, float rot_deg, sdm_hypothesis* out);
 /* EpipolarSearch over every candidate pixel of kf1 against kf2; planes are dense W*H; ok: 0 = no
  * hypothesis, 1 = hypothesis failing the keep test of :472, 2 = kept */
 int sdm_epipolar_search_plane(sdm_ctx* ctx, int kf1, int kf2, float min_depth, float max_depth, float rot_deg,

@@ -77,3 +77,21 @@ def compare_planes(dev, osc, what=("depth", "sigma", "checked", "points")):
             assert e.max() <= REL_TOL, (key, float(e.max()))
         rep[key + "_bit_mismatch"] = int((a.view(np.uint32) != b.view(np.uint32)).sum())
     return rep
+
+
+def golden_scene(golden_dir):
+    """Scene + oracle outputs committed in tests/golden/oracle_small.npz (oracle/make_golden.py)."""
+    import os
+    from sdmb200 import synth
+    g = np.load(os.path.join(golden_dir, "oracle_small.npz"))
+    sc = synth.Scene(im=g["im"], grad=g["grad"], theta=g["theta"], edge=None, K=tuple(float(v) for v in g["K"]),
+                     Tcw=g["Tcw"], nbr_idx=g["nbr_idx"], rot=g["rot"], min_depth=g["min_depth"], max_depth=g["max_depth"])
+    return sc, g
+
+
+class GoldenRef:
+    """Quacks like OracleScene for compare_planes()."""
+
+    def __init__(self, g, tag):
+        self.depth, self.sigma = g[f"{tag}_depth"], g[f"{tag}_sigma"]
+        self.checked, self.points = g[f"{tag}_checked"], g[f"{tag}_points"]

@@ -1,0 +1,91 @@
+"""The C++ drop-in class (eao-slam_b200/host/ProbabilityMapping.h): builds with the reference's dialect
+(-std=c++11) against the C-ABI library, and — on a GPU — its SemiDenseLoop / per-method calls reproduce
+the oracle on the same keyframes (pitched cv::Mat-like planes, reference gating, reference argument order)."""
+import ctypes as C
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_py as O
+from helpers import compare_planes
+from sdmb200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIBDIR = os.path.join(ROOT, "eao-slam_b200", "lib")
+
+
+@pytest.fixture(scope="module")
+def shim_binary(tmp_path_factory):
+    out = str(tmp_path_factory.mktemp("shim") / "test_shim")
+    subprocess.run(["g++", "-std=c++11", "-O1", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "cpp", "test_shim.cpp"), "-o", out, "-L", LIBDIR, "-lsdm_b200",
+                    f"-Wl,-rpath,{LIBDIR}", "-lpthread"], check=True)
+    return out
+
+
+def test_shim_builds_as_cxx11(shim_binary):
+    assert os.path.exists(shim_binary)
+
+
+@pytest.mark.gpu
+def test_shim_semidense_loop_matches_oracle(shim_binary, tmp_path):
+    n, W, H, N, pad = 12, 320, 240, 6, 16
+    sc = synth.make_scene(n, W, H, N, seed=17)
+    lib = O.lib()
+    for i in range(n):  # the shim derives min/max depth from GetAllPointDepths() like :734-747
+        a, b = C.c_float(), C.c_float()
+        lib.oracle_stereo_search_constraints(O.fptr(sc.inv_depths[i]), len(sc.inv_depths[i]), C.byref(a), C.byref(b))
+        sc.min_depth[i], sc.max_depth[i] = a.value, b.value
+    osc = O.OracleScene(sc)
+    osc.run()
+    ys, xs = np.nonzero(sc.grad[5] > 8)
+    pick = np.random.default_rng(0).choice(len(ys), 24, replace=False)
+    probes = [(5, int(sc.nbr_idx[5][k % N]), int(xs[p]), int(ys[p])) for k, p in enumerate(pick)]
+    scene_path, out_path = str(tmp_path / "scene.bin"), str(tmp_path / "out.bin")
+    with open(scene_path, "wb") as f:
+        f.write(struct.pack("6i", n, W, H, N, pad, len(probes)))
+        f.write(np.asarray(sc.K, np.float32).tobytes())
+        for i in range(n):
+            f.write(np.ascontiguousarray(sc.Tcw[i], np.float32).tobytes())
+            f.write(sc.im[i].tobytes()); f.write(sc.grad[i].tobytes()); f.write(sc.theta[i].tobytes())
+            f.write(struct.pack("i", len(sc.inv_depths[i]))); f.write(sc.inv_depths[i].tobytes())
+            f.write(np.ascontiguousarray(sc.nbr_idx[i], np.int32).tobytes())
+        f.write(np.asarray(probes, np.int32).tobytes())
+    r = subprocess.run([shim_binary, scene_path, out_path], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw = np.fromfile(out_path, np.float32)
+    per = 2 + 6 * W * H
+    dev = {k: np.zeros((n, H, W) + ((3,) if k == "points" else ()), np.float32) for k in ("depth", "sigma", "checked", "points")}
+    for i in range(n):
+        blk = raw[i * per:(i + 1) * per]
+        assert tuple(blk[:2].view(np.int32)) == (1, 1)  # semidense_flag_, interKF_depth_flag_ set (:497, :554)
+        p = blk[2:]
+        dev["depth"][i] = p[:W * H].reshape(H, W); dev["sigma"][i] = p[W * H:2 * W * H].reshape(H, W)
+        dev["checked"][i] = p[2 * W * H:3 * W * H].reshape(H, W); dev["points"][i] = p[3 * W * H:].reshape(H, W, 3)
+    rep = compare_planes(dev, osc)
+    print(rep)
+    tail = raw[n * per:]
+    rec = tail[:8 * len(probes)].reshape(-1, 8)
+    for (k1, k2, x, y), got in zip(probes, rec):
+        pr = osc.pair(k1, k2)
+        a, b = C.c_float(), C.c_float()
+        lib.oracle_get_search_range(C.byref(osc.kfs[k1]), C.byref(pr), x, y, float(sc.min_depth[k1]), float(sc.max_depth[k1]), C.byref(a), C.byref(b))
+        assert (got[0], got[1]) == (sc.min_depth[k1], sc.max_depth[k1])
+        assert (got[2], got[3]) == (np.float32(a.value), np.float32(b.value))
+        d, s, u, ok = osc.pass1_pair(k1, k2, 0.0)
+        assert bool(got[6]) == bool(ok[y, x])
+        if ok[y, x]:
+            assert got[4] == d[y, x] and got[5] == s[y, x] and got[7] == u[y, x]
+    fus = tail[8 * len(probes):8 * len(probes) + 3]
+    hd = np.array([0.50, 0.51, 0.49, 0.505, 0.9, 0.495], np.float32); hs = np.array([0.02, 0.02, 0.03, 0.01, 0.02, 0.02], np.float32)
+    a, b = C.c_float(), C.c_float()
+    p = O.default_params()
+    okf = lib.oracle_fusion(O.fptr(hd), O.fptr(hs), 6, C.byref(p), C.byref(a), C.byref(b))
+    assert okf == int(fus[2]) == 1 and fus[0] == np.float32(a.value) and fus[1] == np.float32(b.value)
+    intra = tail[8 * len(probes) + 3:]
+    d2, s2 = osc.depth[2].copy(), osc.sigma[2].copy()
+    lib.oracle_intra_check(O.fptr(d2), O.fptr(s2), W, H, C.byref(p))
+    assert np.array_equal(intra[:W * H].reshape(H, W), d2) and np.array_equal(intra[W * H:2 * W * H].reshape(H, W), s2)

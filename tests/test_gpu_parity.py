@@ -72,7 +72,8 @@ def test_epipolar_search_per_pair(small_scene, small_oracle):
             # single-pixel entry point agrees with the plane entry point
             ys, xs = np.nonzero(ok == 2)
             k = len(ys) // 2
-            h = ctx.epipolar_search(i, j, int(xs[k]), int(ys[k]), float(sc.min_depth[i]), float(sc.max_depth[i]), 0.0)
+            h = ctx.epipolar_search(i, j, int(xs[k]), int(ys[k]), float(sc.im[i][ys[k], xs[k]]), float(sc.min_depth[i]),
+                                    float(sc.max_depth[i]), float(sc.theta[i][ys[k], xs[k]]), 0.0)
             assert h.supported == 1 and h.depth == d[ys[k], xs[k]] and h.sigma == s[ys[k], xs[k]]
 
 
@@ -184,3 +185,14 @@ def test_state_errors(small_scene):
         with pytest.raises(api.SdmError) as e:
             ctx.candidate_count(sc.n + 3)
         assert e.value.code == -1
+
+
+@pytest.mark.parametrize("tag,intra", [("plain", 0), ("intra", 1)])
+def test_against_committed_golden_vectors(golden_dir, tag, intra):
+    """CUDA path vs tests/golden/oracle_small.npz (no oracle involved at run time)."""
+    from helpers import GoldenRef, golden_scene
+    sc, g = golden_scene(golden_dir)
+    dev = run_device(sc, intra_check=intra, intra_grow=intra)
+    rep = compare_planes(dev, GoldenRef(g, tag))
+    print(json.dumps(rep))
+    assert dev["stats"]["candidates"] == int(g[f"{tag}_stats"][0])
