@@ -252,21 +252,87 @@ def main_ours(a, rank, world, local_rank):
         if world > 1:
             dist.barrier()
 
-    def upload():
-        ctx.upload_scene(sc)
+    def upload_one(s):
+        ctx.upload_keyframe(s, sc.im[s], sc.grad[s], sc.theta[s], None, sc.K, sc.Tcw[s])
 
-    def step():
-        ctx.pass1(items)
+    def upload():
+        for s in range(n_loc):
+            upload_one(s)
+
+    def exchange():
         if world > 1:
             ctx.synchronize(); barrier()
             ctx.pull_halo(plan.halo_local, plan.halo_rank, plan.halo_peer_slot)
+
+    dbg = os.environ.get("SDM_BENCH_DEBUG") and rank == 0
+
+    def step():
+        t = [time.perf_counter()]
+        ctx.pass1(items)
+        if dbg:
+            ctx.synchronize(); t.append(time.perf_counter())
+        exchange()
+        if dbg:
+            ctx.synchronize(); t.append(time.perf_counter())
         ctx.pass2(items)
         if world > 1:
-            ctx.synchronize(); barrier()
+            ctx.synchronize()
+            if dbg:
+                t.append(time.perf_counter())
+            barrier()
+        if dbg:
+            t.append(time.perf_counter())
+            print("step phases ms (pass1, exchange, pass2, barrier):", [round(1e3 * (b - a), 3) for a, b in zip(t, t[1:])],
+                  file=sys.stderr)
 
-    def download():
-        for k, s in enumerate(owned):
-            ctx.download(s, out={n: v[k] for n, v in out.items()})
+    # e2e: the same loop issued in chunks of keyframes so that the library's three streams overlap:
+    # H2D of chunk k+1 under pass 1 of chunk k; depth_map_/depth_sigma_ of chunk k go back to the host as soon
+    # as its pass 1 is queued; pass 2 of chunk k is queued right after pass 1 of chunk k+1 (its neighbours reach
+    # at most N/2 keyframes into chunk k+1) and its depth_map_checked_/SemiDensePointSets_ follow.  Chunks whose
+    # pass 2 needs halo planes of another rank wait for the exchange.  Raw C-ABI calls with prebuilt arguments.
+    CH = 20
+    chunks = [owned[i:i + CH] for i in range(0, len(owned), CH)]
+    chunk_items = [api.make_items(ch, sc.nbr_idx, sc.rot, sc.min_depth, sc.max_depth) for ch in chunks]
+    chunk_need = [max(ch[-1], max(int(v) for s in ch for v in sc.nbr_idx[s])) for ch in chunks]
+    halo_set = set(int(v) for v in plan.halo_local)
+    needs_halo = [any(int(v) in halo_set for s in ch for v in sc.nbr_idx[s]) for ch in chunks]
+    Kf = np.ascontiguousarray(np.asarray(sc.K, np.float32)); keep.append(Kf)
+    Tf = np.ascontiguousarray(sc.Tcw.reshape(n_loc, 12).astype(np.float32)); keep.append(Tf)
+    fp = C.POINTER(C.c_float)
+    up_args = [(ctx.h, s, sc.im[s].ctypes.data, W, sc.grad[s].ctypes.data, 4 * W, sc.theta[s].ctypes.data, 4 * W, None, 0,
+                Kf.ctypes.data_as(fp), Tf[s].ctypes.data_as(fp)) for s in range(n_loc)]
+    o0 = owned[0]
+    dl1_args = {s: (ctx.h, s, out["depth"][s - o0].ctypes.data, 4 * W, out["sigma"][s - o0].ctypes.data, 4 * W, None, 0, None, 0)
+                for s in owned}
+    dl2_args = {s: (ctx.h, s, None, 0, None, 0, out["checked"][s - o0].ctypes.data, 4 * W, out["points"][s - o0].ctypes.data, 12 * W)
+                for s in owned}
+    chk = ctx._chk
+
+    def e2e_step():
+        nxt, deferred = 0, []
+        for k in range(len(chunks)):
+            while nxt <= chunk_need[k]:
+                chk(lib.sdm_upload_keyframe(*up_args[nxt])); nxt += 1
+            chk(lib.sdm_pass1(ctx.h, len(chunk_items[k]), chunk_items[k]))
+            for s in chunks[k]:
+                chk(lib.sdm_download_async(*dl1_args[s]))
+            if k >= 1:
+                if needs_halo[k - 1]:
+                    deferred.append(k - 1)
+                else:
+                    chk(lib.sdm_pass2(ctx.h, len(chunk_items[k - 1]), chunk_items[k - 1]))
+                    for s in chunks[k - 1]:
+                        chk(lib.sdm_download_async(*dl2_args[s]))
+        while nxt < n_loc:
+            chk(lib.sdm_upload_keyframe(*up_args[nxt])); nxt += 1
+        exchange()
+        for k in deferred + [len(chunks) - 1]:
+            chk(lib.sdm_pass2(ctx.h, len(chunk_items[k]), chunk_items[k]))
+            for s in chunks[k]:
+                chk(lib.sdm_download_async(*dl2_args[s]))
+        ctx.synchronize()
+        if world > 1:
+            barrier()
 
     upload(); ctx.synchronize()
     cands = sum(ctx.candidate_count(s) for s in owned)
@@ -276,6 +342,7 @@ def main_ours(a, rank, world, local_rank):
     clocks = Clocks(local_rank)
     if rank == 0:
         clocks.start(); time.sleep(0.3)
+    barrier()  # every rank starts its timed region together (rank 0 just slept)
     l0, t0 = ctx.launch_count(), time.time()
     ctx.mark(0)
     for _ in range(a.steps):
@@ -291,8 +358,6 @@ def main_ours(a, rank, world, local_rank):
     # ---- end to end through the C-ABI with host buffers
     e2e = None
     if not a.no_e2e:
-        def e2e_step():
-            upload(); step(); download(); ctx.synchronize()
         e2e_step()
         barrier(); tt = time.perf_counter()
         for _ in range(a.steps):

@@ -1,9 +1,16 @@
 // sdm_b200.cu — C-ABI implementation of libsdm_b200.so (see include/sdm_b200.h).
 //
 // Host side of the B200-native semi-dense mapping path: device arena, keyframe upload, batched
-// launches of the pass-1 / pass-2 kernels (sdm_kernels.cuh), downloads, CUDA-IPC halo pulls.
-// Replaces the CPU loops of yanmin-wu/EAO-SLAM src/ProbabilityMapping.cc:348-597.
+// persistent launches of the pass-1 / pass-2 kernels (sdm_kernels.cuh), downloads, CUDA-IPC halo
+// pulls.  Replaces the CPU loops of yanmin-wu/EAO-SLAM src/ProbabilityMapping.cc:348-597.
 // No CPU fallback: every entry point that computes needs a CUDA device.
+//
+// Streams: uploads (H2D + k_pack) on s_copy, the passes on s_compute, downloads (k_split_rs + D2H) on
+// s_down.  Ordering between them is tracked per keyframe slot with event ids (see EventRing): an
+// upload waits for the last pass / download that touched its slot, a pass waits for the uploads of
+// every slot it references and for downloads of the slots it overwrites, a download waits for the
+// last pass on its slot.  Nothing on these paths blocks the host, so a caller can keep all three
+// streams busy by issuing upload / pass / download calls on chunks of keyframes (bench.py e2e).
 //
 // Build: nvcc -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false
 //        -Xcompiler -fPIC,-ffp-contract=off -shared   (see __graft_entry__.build()).
@@ -43,25 +50,82 @@ int fail(int code, const char* fmt, ...)
         if (e_ != cudaSuccess)                                                                     \
             return fail(SDM_ERR_CUDA, "%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
     } while (0)
+#define RC(call)                    \
+    do {                            \
+        int rc_ = (call);           \
+        if (rc_ != SDM_OK) return rc_; \
+    } while (0)
 
-constexpr int kStages = 4;
+constexpr int kUpStages = 6;    // upload staging sets (im, grad, theta, edge)
+constexpr int kDownStages = 6;  // (rho | sigma) split staging sets
+constexpr int kItemStages = 4;  // pinned work-order staging buffers
 constexpr int kMaxPeers = 16;
+constexpr int kIntraChunk = 64;  // keyframes per batched intra launch (bounds the tmp arena)
+
+// A ring of CUDA events addressed by monotonically increasing ids.  id 0 = "never".  An id that has
+// fallen out of the ring is complete by construction (its event was synchronised when recycled).
+struct EventRing {
+    std::vector<cudaEvent_t> ev;
+    uint64_t next = 1;
+    int init(int n)
+    {
+        ev.resize(n);
+        for (auto& e : ev) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        return SDM_OK;
+    }
+    void destroy()
+    {
+        for (auto e : ev)
+            if (e) cudaEventDestroy(e);
+        ev.clear();
+    }
+    int record(cudaStream_t s, uint64_t* id)
+    {
+        const uint64_t i = next++;
+        cudaEvent_t e = ev[i % ev.size()];
+        if (i > ev.size()) CU(cudaEventSynchronize(e));  // recycle: the old occupant must be complete
+        CU(cudaEventRecord(e, s));
+        *id = i;
+        return SDM_OK;
+    }
+    bool live(uint64_t id) const { return id != 0 && next - id <= ev.size(); }
+    int wait(cudaStream_t s, uint64_t id)
+    {
+        if (live(id)) CU(cudaStreamWaitEvent(s, ev[id % ev.size()], 0));
+        return SDM_OK;
+    }
+    int host_sync(uint64_t id)
+    {
+        if (live(id)) CU(cudaEventSynchronize(ev[id % ev.size()]));
+        return SDM_OK;
+    }
+    bool done(uint64_t id) { return !live(id) || cudaEventQuery(ev[id % ev.size()]) == cudaSuccess; }
+};
 
 struct KfState {
     bool uploaded = false;
     bool pass1_done = false;
-    int cand_count = -1;  // -1: not read back yet
+    bool rs_dense = false;  // (rho,sigma) plane did not come from pass 1: pass 2 must visit every pixel
     float K[4] = {0, 0, 0, 0};
     float Tcw[12] = {0};
+    uint64_t up_id = 0, comp_id = 0, down_id = 0;  // last upload / pass / download touching the slot
 };
 
-struct Stage {
+struct UpStage {
     uint8_t* im = nullptr;
     float* grad = nullptr;
     float* theta = nullptr;
     int32_t* edge = nullptr;
-    cudaEvent_t done = nullptr;
-    bool busy = false;
+    uint64_t busy = 0;  // copy-ring id of the k_pack that reads it
+};
+struct DownStage {
+    float* planes = nullptr;  // 2 * P floats
+    uint64_t busy = 0;        // down-ring id
+};
+struct ItemStage {
+    void* host = nullptr;  // pinned: DevItem[cap] followed by int aux[3 * cap]
+    int cap = 0;
+    uint64_t busy = 0;  // compute-ring id of the H2D copy that reads it
 };
 
 }  // namespace
@@ -72,61 +136,101 @@ struct sdm_ctx {
     sdm::DevArena A;
     size_t npix = 0;
     std::vector<KfState> kf;
-    cudaStream_t s_compute = nullptr, s_copy = nullptr;
-    cudaEvent_t ev_copy = nullptr, ev_compute = nullptr;
+    cudaStream_t s_compute = nullptr, s_copy = nullptr, s_down = nullptr;
+    EventRing r_copy, r_compute, r_down;
     cudaEvent_t ev_p1[2] = {nullptr, nullptr}, ev_p2[2] = {nullptr, nullptr}, ev_p1_scan = nullptr;
     cudaEvent_t marks[SDM_N_MARKS] = {nullptr};
     bool mark_set[SDM_N_MARKS] = {false};
     bool p1_timed = false, p2_timed = false;
-    Stage stage[kStages];
-    int stage_next = 0;
-    int* h_cand_count = nullptr;  // pinned mirror of A.cand_count
-    bool counts_pending = false;
+    UpStage up[kUpStages];
+    int up_next = 0;
+    DownStage down[kDownStages];
+    int down_next = 0;
+    ItemStage ist[kItemStages];
+    int ist_next = 0;
+    int* h_count = nullptr;  // pinned, sdm_candidate_count
+    // device work orders of the current pass
     sdm::DevItem* d_items = nullptr;
-    sdm::DevItem* h_items = nullptr;  // pinned
-    int* d_blk_off = nullptr;
-    int* h_blk_off = nullptr;  // pinned
+    int* d_aux = nullptr;  // slots[cap] | order_sparse[cap] | order_dense[cap]
+    int* d_chunk_off = nullptr;
+    int* d_counter = nullptr;
     int items_cap = 0;
     sdm::DevStats* d_stats = nullptr;
-    float2* scratch_rs = nullptr;     // snapshot plane for the intra stencils
-    float* dl_stage = nullptr;        // 2 dense float planes (download / upload_depth staging)
-    float* dbg = nullptr;             // 4 float planes + 1 byte plane (sdm_epipolar_search_plane)
+    float2* tmp_rs = nullptr;  // kIntraChunk planes: the other side of the intra ping-pong
+    int tmp_planes = 0;
+    float* xfer = nullptr;  // 2 dense float planes (sdm_upload_depth staging)
+    float* dbg = nullptr;   // 4 float planes + 1 byte plane (sdm_epipolar_search_plane)
     void* peer_rs[kMaxPeers] = {nullptr};
+    int grid_pass1_warp = 0, grid_pass2 = 0, n_sm = 0;  // persistent grids (blocks)
     long long launches = 0;
-    long long stat_candidates = 0;
     int scan_warp_per_pixel = 0;  // developer A/B knob (env SDM_SCAN=warp): the warp-per-pixel scan kernel
 };
 
 namespace {
 
+bool slot_ok(const sdm_ctx* c, int s) { return s >= 0 && s < (int)c->kf.size(); }
+
+// pitched plane copy; rows that are contiguous on both sides go out as ONE 1-D copy (cheaper to enqueue
+// and a single DMA descriptor), which is the common case for cv::Mat planes that are not ROIs
+int copy2d(void* dst, size_t dpitch, const void* src, size_t spitch, size_t width, size_t height, cudaMemcpyKind kind,
+           cudaStream_t s)
+{
+    if (dpitch == width && spitch == width)
+        CU(cudaMemcpyAsync(dst, src, width * height, kind, s));
+    else
+        CU(cudaMemcpy2DAsync(dst, dpitch, src, spitch, width, height, kind, s));
+    return SDM_OK;
+}
+dim3 tile_grid(const sdm_ctx* c, int z = 1) { return dim3((c->cfg.width + 31) / 32, (c->cfg.height + 7) / 8, z); }
+
 int ensure_items(sdm_ctx* c, int n)
 {
     if (n <= c->items_cap) return SDM_OK;
-    int cap = std::max(n, std::max(64, c->items_cap * 2));
-    if (c->d_items) cudaFree(c->d_items);
-    if (c->h_items) cudaFreeHost(c->h_items);
-    if (c->d_blk_off) cudaFree(c->d_blk_off);
-    if (c->h_blk_off) cudaFreeHost(c->h_blk_off);
-    c->d_items = nullptr; c->h_items = nullptr; c->d_blk_off = nullptr; c->h_blk_off = nullptr;
+    const int cap = std::max(n, std::max(64, c->items_cap * 2));
+    CU(cudaStreamSynchronize(c->s_compute));
+    cudaFree(c->d_items); cudaFree(c->d_aux); cudaFree(c->d_chunk_off);
+    c->d_items = nullptr; c->d_aux = nullptr; c->d_chunk_off = nullptr;
     c->items_cap = 0;
     CU(cudaMalloc(&c->d_items, sizeof(sdm::DevItem) * cap));
-    CU(cudaMallocHost(&c->h_items, sizeof(sdm::DevItem) * cap));
-    CU(cudaMalloc(&c->d_blk_off, sizeof(int) * (cap + 1)));
-    CU(cudaMallocHost(&c->h_blk_off, sizeof(int) * (cap + 1)));
+    CU(cudaMalloc(&c->d_aux, sizeof(int) * 3 * cap));
+    CU(cudaMalloc(&c->d_chunk_off, sizeof(int) * (cap + 1)));
     c->items_cap = cap;
     return SDM_OK;
 }
 
-bool slot_ok(const sdm_ctx* c, int s) { return s >= 0 && s < (int)c->kf.size(); }
+// a pinned staging buffer for n work orders that no in-flight copy still reads
+int acquire_item_stage(sdm_ctx* c, int n, ItemStage** out)
+{
+    ItemStage* st = nullptr;
+    for (int k = 0; k < kItemStages; ++k) {
+        ItemStage& cand = c->ist[(c->ist_next + k) % kItemStages];
+        if (c->r_compute.done(cand.busy)) { st = &cand; break; }
+    }
+    if (!st) {
+        st = &c->ist[c->ist_next];
+        RC(c->r_compute.host_sync(st->busy));
+    }
+    c->ist_next = (int)((st - c->ist) + 1) % kItemStages;
+    if (st->cap < n) {
+        if (st->host) CU(cudaFreeHost(st->host));
+        st->host = nullptr;
+        st->cap = 0;
+        const int cap = std::max(n, 64);
+        CU(cudaMallocHost(&st->host, (sizeof(sdm::DevItem) + 3 * sizeof(int)) * cap));
+        st->cap = cap;
+    }
+    *out = st;
+    return SDM_OK;
+}
 
 // SemiDenseLoop :424-438 per keyframe: R21/t21/F12 for every neighbour, Twc for the point set
-int build_item(sdm_ctx* c, const sdm_item& in, sdm::DevItem& out, bool need_pass1_planes)
+int build_item(sdm_ctx* c, const sdm_item& in, sdm::DevItem& out, bool pass2, bool points_only)
 {
     if (!slot_ok(c, in.kf)) return fail(SDM_ERR_ARG, "item keyframe slot %d out of range", in.kf);
     if (in.n_nbr < 0 || in.n_nbr > SDM_MAX_NBR) return fail(SDM_ERR_ARG, "n_nbr %d out of [0,%d]", in.n_nbr, SDM_MAX_NBR);
     const KfState& k1 = c->kf[in.kf];
     if (!k1.uploaded) return fail(SDM_ERR_STATE, "keyframe slot %d not uploaded", in.kf);
-    if (need_pass1_planes && !k1.pass1_done) return fail(SDM_ERR_STATE, "pass 2 before pass 1 for slot %d", in.kf);
+    if (pass2 && !points_only && !k1.pass1_done) return fail(SDM_ERR_STATE, "pass 2 before pass 1 for slot %d", in.kf);
     memset(&out, 0, offsetof(sdm::DevItem, pair));
     out.kf = in.kf;
     out.n_nbr = in.n_nbr;
@@ -138,12 +242,11 @@ int build_item(sdm_ctx* c, const sdm_item& in, sdm::DevItem& out, bool need_pass
         const int s2 = in.nbr[j];
         if (!slot_ok(c, s2)) return fail(SDM_ERR_ARG, "neighbour slot %d out of range", s2);
         const KfState& k2 = c->kf[s2];
-        if (need_pass1_planes) {
+        if (pass2) {
             if (!k2.pass1_done) return fail(SDM_ERR_STATE, "neighbour slot %d has no pass-1 planes", s2);
         } else if (!k2.uploaded) {
             return fail(SDM_ERR_STATE, "neighbour slot %d not uploaded", s2);
         }
-        // the poses of a halo slot that only carries pass-1 planes are still required
         const sdm::PairGeometry g = sdm::pair_geometry(k1.K, k1.Tcw, k2.K, k2.Tcw);
         sdm::DevPair& p = out.pair[j];
         memcpy(p.F, g.F12.m, sizeof(p.F));
@@ -155,65 +258,106 @@ int build_item(sdm_ctx* c, const sdm_item& in, sdm::DevItem& out, bool need_pass
     return SDM_OK;
 }
 
-// wait until the candidate counts of every uploaded keyframe are on the host
-int sync_counts(sdm_ctx* c)
-{
-    if (c->counts_pending) {
-        CU(cudaStreamSynchronize(c->s_copy));
-        c->counts_pending = false;
-        for (size_t i = 0; i < c->kf.size(); ++i)
-            if (c->kf[i].uploaded && c->kf[i].cand_count < 0) c->kf[i].cand_count = c->h_cand_count[i];
-        for (auto& st : c->stage) st.busy = false;
-    }
-    return SDM_OK;
-}
+struct Batch {
+    int n = 0;
+    int n_sparse = 0, n_dense = 0;
+    int* d_slots = nullptr;
+    int* d_order_sparse = nullptr;
+    int* d_order_dense = nullptr;
+    ItemStage* stage = nullptr;
+};
 
-// compute stream waits for everything queued on the copy stream (uploads) and vice versa
-int copy_then_compute(sdm_ctx* c)
+// Build the device work orders of a pass and make s_compute wait for everything the pass depends on.
+int prepare_batch(sdm_ctx* c, int n, const sdm_item* items, bool pass2, bool points_only, Batch* b)
 {
-    CU(cudaEventRecord(c->ev_copy, c->s_copy));
-    CU(cudaStreamWaitEvent(c->s_compute, c->ev_copy, 0));
-    return SDM_OK;
-}
-int compute_then_copy(sdm_ctx* c)
-{
-    CU(cudaEventRecord(c->ev_compute, c->s_compute));
-    CU(cudaStreamWaitEvent(c->s_copy, c->ev_compute, 0));
-    return SDM_OK;
-}
-
-int upload_items(sdm_ctx* c, int n, const sdm_item* items, bool pass2)
-{
-    int rc = ensure_items(c, n);
-    if (rc) return rc;
-    // the pinned item staging may still be read by the previous pass's H2D copy
-    CU(cudaStreamSynchronize(c->s_compute));
+    RC(ensure_items(c, n));
+    ItemStage* st;
+    RC(acquire_item_stage(c, n, &st));
+    sdm::DevItem* h_items = (sdm::DevItem*)st->host;
+    int* h_aux = (int*)(h_items + st->cap);
+    int* h_slots = h_aux;
+    int* h_sparse = h_aux + n;
+    int* h_dense = h_aux + 2 * n;
+    uint64_t need_up = 0, need_down = 0;
+    b->n = n;
     for (int i = 0; i < n; ++i) {
-        rc = build_item(c, items[i], c->h_items[i], pass2);
-        if (rc) return rc;
+        RC(build_item(c, items[i], h_items[i], pass2, points_only));
+        const KfState& k1 = c->kf[items[i].kf];
+        h_slots[i] = items[i].kf;
+        if (pass2 && (k1.rs_dense || points_only)) h_dense[b->n_dense++] = i; else h_sparse[b->n_sparse++] = i;
+        need_up = std::max(need_up, k1.up_id);
+        need_down = std::max(need_down, k1.down_id);  // the pass overwrites this slot's output planes
+        for (int j = 0; j < items[i].n_nbr; ++j) need_up = std::max(need_up, c->kf[items[i].nbr[j]].up_id);
     }
-    CU(cudaMemcpyAsync(c->d_items, c->h_items, sizeof(sdm::DevItem) * n, cudaMemcpyHostToDevice, c->s_compute));
+    RC(c->r_copy.wait(c->s_compute, need_up));
+    RC(c->r_down.wait(c->s_compute, need_down));
+    CU(cudaMemcpyAsync(c->d_items, h_items, sizeof(sdm::DevItem) * n, cudaMemcpyHostToDevice, c->s_compute));
+    CU(cudaMemcpyAsync(c->d_aux, h_aux, sizeof(int) * 3 * n, cudaMemcpyHostToDevice, c->s_compute));
+    RC(c->r_compute.record(c->s_compute, &st->busy));
+    b->d_slots = c->d_aux;
+    b->d_order_sparse = c->d_aux + n;
+    b->d_order_dense = c->d_aux + 2 * n;
+    b->stage = st;
     return SDM_OK;
 }
 
-dim3 tile_grid(const sdm_ctx* c) { return dim3((c->cfg.width + 31) / 32, (c->cfg.height + 7) / 8); }
-
-int run_intra(sdm_ctx* c, int slot, bool check, bool grow)
+// after the pass's kernels are enqueued: every referenced slot is busy until this point of s_compute
+int finish_batch(sdm_ctx* c, int n, const sdm_item* items)
 {
-    const size_t bytes = c->npix * sizeof(float2);
-    float2* plane = c->A.rs + (size_t)slot * c->npix;
-    if (check) {
-        CU(cudaMemcpyAsync(c->scratch_rs, plane, bytes, cudaMemcpyDeviceToDevice, c->s_compute));
-        sdm::k_intra_check<<<tile_grid(c), dim3(32, 8), 0, c->s_compute>>>(c->P, c->scratch_rs, plane);
-        c->launches++;
+    uint64_t id = 0;
+    RC(c->r_compute.record(c->s_compute, &id));
+    for (int i = 0; i < n; ++i) {
+        c->kf[items[i].kf].comp_id = id;
+        for (int j = 0; j < items[i].n_nbr; ++j) c->kf[items[i].nbr[j]].comp_id = id;
     }
-    if (grow) {
-        CU(cudaMemcpyAsync(c->scratch_rs, plane, bytes, cudaMemcpyDeviceToDevice, c->s_compute));
-        sdm::k_intra_grow<<<tile_grid(c), dim3(32, 8), 0, c->s_compute>>>(c->P, c->scratch_rs, plane,
-                                                                          c->A.tex + (size_t)slot * c->npix);
-        c->launches++;
+    return SDM_OK;
+}
+
+sdm::DevPlan make_plan(sdm_ctx* c, const int* d_order, int n)
+{
+    sdm::DevPlan p;
+    p.chunk_off = c->d_chunk_off;
+    p.counter = c->d_counter;
+    p.order = d_order;
+    p.n_items = n;
+    return p;
+}
+
+// batched intra stencils on the (rho,sigma) planes of `n` slots (device array d_slots)
+int run_intra(sdm_ctx* c, const int* d_slots, int n, bool check, bool grow)
+{
+    if (!check && !grow) return SDM_OK;
+    const int want = std::min(n, kIntraChunk);
+    if (c->tmp_planes < want) {
+        CU(cudaStreamSynchronize(c->s_compute));
+        cudaFree(c->tmp_rs);
+        c->tmp_rs = nullptr;
+        c->tmp_planes = 0;
+        CU(cudaMalloc(&c->tmp_rs, (size_t)want * c->npix * sizeof(float2)));
+        c->tmp_planes = want;
+    }
+    for (int i0 = 0; i0 < n; i0 += c->tmp_planes) {
+        const int m = std::min(c->tmp_planes, n - i0);
+        sdm::k_intra_check<<<tile_grid(c, m), dim3(32, 8), 0, c->s_compute>>>(c->P, c->A.rs, c->tmp_rs, d_slots + i0, c->npix,
+                                                                              check ? 0 : 1);
+        sdm::k_intra_grow<<<tile_grid(c, m), dim3(32, 8), 0, c->s_compute>>>(c->P, c->tmp_rs, c->A.rs, c->A.tex, d_slots + i0,
+                                                                             c->npix, grow ? 0 : 1);
+        c->launches += 2;
     }
     CU(cudaGetLastError());
+    return SDM_OK;
+}
+
+int single_slot_array(sdm_ctx* c, int slot, int** d_slots)
+{
+    RC(ensure_items(c, 1));
+    ItemStage* st;
+    RC(acquire_item_stage(c, 1, &st));
+    int* h = (int*)st->host;
+    h[0] = slot;
+    CU(cudaMemcpyAsync(c->d_aux, h, sizeof(int), cudaMemcpyHostToDevice, c->s_compute));
+    RC(c->r_compute.record(c->s_compute, &st->busy));
+    *d_slots = c->d_aux;
     return SDM_OK;
 }
 
@@ -245,7 +389,7 @@ void sdm_default_config(sdm_config* cfg)
 }
 
 const char* sdm_last_error(void) { return g_last_error.c_str(); }
-const char* sdm_version(void) { return "sdm_b200 0.1 (sm_100a)"; }
+const char* sdm_version(void) { return "sdm_b200 0.2 (sm_100a)"; }
 
 void sdm_destroy(sdm_ctx* c)
 {
@@ -256,21 +400,20 @@ void sdm_destroy(sdm_ctx* c)
         if (c->peer_rs[i]) cudaIpcCloseMemHandle(c->peer_rs[i]);
     cudaFree(c->A.tex); cudaFree(c->A.ipair); cudaFree(c->A.cand); cudaFree(c->A.cand_count);
     cudaFree(c->A.rs); cudaFree(c->A.chk); cudaFree(c->A.pts);
-    for (auto& s : c->stage) {
-        cudaFree(s.im); cudaFree(s.grad); cudaFree(s.theta); cudaFree(s.edge);
-        if (s.done) cudaEventDestroy(s.done);
-    }
-    if (c->h_cand_count) cudaFreeHost(c->h_cand_count);
-    cudaFree(c->d_items); cudaFree(c->d_blk_off); cudaFree(c->d_stats); cudaFree(c->scratch_rs);
-    cudaFree(c->dl_stage); cudaFree(c->dbg);
-    if (c->h_items) cudaFreeHost(c->h_items);
-    if (c->h_blk_off) cudaFreeHost(c->h_blk_off);
-    for (cudaEvent_t e : {c->ev_copy, c->ev_compute, c->ev_p1[0], c->ev_p1[1], c->ev_p2[0], c->ev_p2[1], c->ev_p1_scan})
+    for (auto& s : c->up) { cudaFree(s.im); cudaFree(s.grad); cudaFree(s.theta); cudaFree(s.edge); }
+    for (auto& s : c->down) cudaFree(s.planes);
+    for (auto& s : c->ist)
+        if (s.host) cudaFreeHost(s.host);
+    if (c->h_count) cudaFreeHost(c->h_count);
+    cudaFree(c->d_items); cudaFree(c->d_aux); cudaFree(c->d_chunk_off); cudaFree(c->d_counter); cudaFree(c->d_stats);
+    cudaFree(c->tmp_rs); cudaFree(c->xfer); cudaFree(c->dbg);
+    for (cudaEvent_t e : {c->ev_p1[0], c->ev_p1[1], c->ev_p2[0], c->ev_p2[1], c->ev_p1_scan})
         if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : c->marks)
         if (e) cudaEventDestroy(e);
-    if (c->s_compute) cudaStreamDestroy(c->s_compute);
-    if (c->s_copy) cudaStreamDestroy(c->s_copy);
+    c->r_copy.destroy(); c->r_compute.destroy(); c->r_down.destroy();
+    for (cudaStream_t s : {c->s_compute, c->s_copy, c->s_down})
+        if (s) cudaStreamDestroy(s);
     delete c;
 }
 
@@ -309,8 +452,10 @@ static int create_impl(sdm_ctx* c)
 
     CU(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
-    CU(cudaEventCreateWithFlags(&c->ev_copy, cudaEventDisableTiming));
-    CU(cudaEventCreateWithFlags(&c->ev_compute, cudaEventDisableTiming));
+    CU(cudaStreamCreateWithFlags(&c->s_down, cudaStreamNonBlocking));
+    RC(c->r_copy.init(1024));
+    RC(c->r_compute.init(1024));
+    RC(c->r_down.init(1024));
     for (int i = 0; i < 2; ++i) {
         CU(cudaEventCreate(&c->ev_p1[i]));
         CU(cudaEventCreate(&c->ev_p2[i]));
@@ -331,18 +476,25 @@ static int create_impl(sdm_ctx* c)
     CU(cudaMemsetAsync(A.rs, 0, n * P * sizeof(float2), c->s_compute));
     CU(cudaMemsetAsync(A.chk, 0, n * P * sizeof(float), c->s_compute));
     CU(cudaMemsetAsync(A.pts, 0, n * P * 3 * sizeof(float), c->s_compute));
-    for (auto& s : c->stage) {
+    for (auto& s : c->up) {
         CU(cudaMalloc(&s.im, P));
         CU(cudaMalloc(&s.grad, P * sizeof(float)));
         CU(cudaMalloc(&s.theta, P * sizeof(float)));
         CU(cudaMalloc(&s.edge, P * sizeof(int32_t)));
-        CU(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
     }
-    CU(cudaMallocHost(&c->h_cand_count, n * sizeof(int)));
+    for (auto& s : c->down) CU(cudaMalloc(&s.planes, 2 * P * sizeof(float)));
+    CU(cudaMallocHost(&c->h_count, sizeof(int)));
+    CU(cudaMalloc(&c->d_counter, sizeof(int)));
     CU(cudaMalloc(&c->d_stats, sizeof(sdm::DevStats)));
     CU(cudaMemsetAsync(c->d_stats, 0, sizeof(sdm::DevStats), c->s_compute));
-    CU(cudaMalloc(&c->scratch_rs, P * sizeof(float2)));
-    CU(cudaMalloc(&c->dl_stage, 2 * P * sizeof(float)));
+    CU(cudaMalloc(&c->xfer, 2 * P * sizeof(float)));
+    // persistent grids: every SM filled to the kernels' occupancy
+    int occ = 0;
+    c->n_sm = prop.multiProcessorCount;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sdm::k_pass1, sdm::kPass1Warps * 32, 0));
+    c->grid_pass1_warp = std::max(1, occ) * prop.multiProcessorCount;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sdm::k_pass2_cand, sdm::kLaneBlock, 0));
+    c->grid_pass2 = std::max(1, occ) * prop.multiProcessorCount;
     CU(cudaStreamSynchronize(c->s_compute));
     return SDM_OK;
 }
@@ -373,10 +525,9 @@ int sdm_synchronize(sdm_ctx* c)
 {
     if (!c) return fail(SDM_ERR_ARG, "null context");
     CU(cudaSetDevice(c->cfg.device));
-    int rc = sync_counts(c);
-    if (rc) return rc;
     CU(cudaStreamSynchronize(c->s_copy));
     CU(cudaStreamSynchronize(c->s_compute));
+    CU(cudaStreamSynchronize(c->s_down));
     return SDM_OK;
 }
 
@@ -387,7 +538,7 @@ int sdm_get_stats(sdm_ctx* c, sdm_stats* out)
     sdm::DevStats h;
     CU(cudaMemcpyAsync(&h, c->d_stats, sizeof(h), cudaMemcpyDeviceToHost, c->s_compute));
     CU(cudaStreamSynchronize(c->s_compute));
-    out->candidates = c->stat_candidates;
+    out->candidates = (long long)h.candidates;
     out->fused = (long long)h.fused;
     out->checked = (long long)h.checked;
     return SDM_OK;
@@ -416,30 +567,27 @@ int sdm_upload_keyframe(sdm_ctx* c, int kf, const uint8_t* im, size_t im_step, c
     if (im_step < (size_t)W || grad_step < (size_t)W * 4 || theta_step < (size_t)W * 4 || (edge && edge_step < (size_t)W * 4))
         return fail(SDM_ERR_ARG, "row step smaller than a row");
     CU(cudaSetDevice(c->cfg.device));
-    Stage& st = c->stage[c->stage_next];
-    c->stage_next = (c->stage_next + 1) % kStages;
-    if (st.busy) CU(cudaEventSynchronize(st.done));
-    // the slot's planes may still be read by queued compute work
-    int rc = compute_then_copy(c);
-    if (rc) return rc;
-    CU(cudaMemcpy2DAsync(st.im, W, im, im_step, W, H, cudaMemcpyHostToDevice, c->s_copy));
-    CU(cudaMemcpy2DAsync(st.grad, (size_t)W * 4, grad, grad_step, (size_t)W * 4, H, cudaMemcpyHostToDevice, c->s_copy));
-    CU(cudaMemcpy2DAsync(st.theta, (size_t)W * 4, theta, theta_step, (size_t)W * 4, H, cudaMemcpyHostToDevice, c->s_copy));
+    KfState& k = c->kf[kf];
+    UpStage& st = c->up[c->up_next];
+    c->up_next = (c->up_next + 1) % kUpStages;
+    // the staging set is free once the k_pack that read it has run (same stream: ordering is implicit);
+    // the slot's planes may still be read by a queued pass or download
+    RC(c->r_compute.wait(c->s_copy, k.comp_id));
+    RC(c->r_down.wait(c->s_copy, k.down_id));
+    RC(copy2d(st.im, W, im, im_step, W, H, cudaMemcpyHostToDevice, c->s_copy));
+    RC(copy2d(st.grad, (size_t)W * 4, grad, grad_step, (size_t)W * 4, H, cudaMemcpyHostToDevice, c->s_copy));
+    RC(copy2d(st.theta, (size_t)W * 4, theta, theta_step, (size_t)W * 4, H, cudaMemcpyHostToDevice, c->s_copy));
     if (edge)
-        CU(cudaMemcpy2DAsync(st.edge, (size_t)W * 4, edge, edge_step, (size_t)W * 4, H, cudaMemcpyHostToDevice, c->s_copy));
+        RC(copy2d(st.edge, (size_t)W * 4, edge, edge_step, (size_t)W * 4, H, cudaMemcpyHostToDevice, c->s_copy));
     CU(cudaMemsetAsync(c->A.cand_count + kf, 0, sizeof(int), c->s_copy));
-    sdm::k_pack<<<tile_grid(c), dim3(32, 8), 0, c->s_copy>>>(c->A, c->P, kf, st.im, st.grad, st.theta,
-                                                             edge ? st.edge : nullptr);
+    sdm::k_pack<<<tile_grid(c), dim3(32, 8), 0, c->s_copy>>>(c->A, c->P, kf, st.im, st.grad, st.theta, edge ? st.edge : nullptr);
     CU(cudaGetLastError());
     c->launches++;
-    CU(cudaMemcpyAsync(c->h_cand_count + kf, c->A.cand_count + kf, sizeof(int), cudaMemcpyDeviceToHost, c->s_copy));
-    CU(cudaEventRecord(st.done, c->s_copy));
-    st.busy = true;
-    c->counts_pending = true;
-    KfState& k = c->kf[kf];
+    RC(c->r_copy.record(c->s_copy, &k.up_id));
+    st.busy = k.up_id;
     k.uploaded = true;
     k.pass1_done = false;
-    k.cand_count = -1;
+    k.rs_dense = false;
     memcpy(k.K, K, sizeof(k.K));
     memcpy(k.Tcw, Tcw, sizeof(k.Tcw));
     return SDM_OK;
@@ -467,9 +615,9 @@ int sdm_candidate_count(sdm_ctx* c, int kf, int* count)
     if (!slot_ok(c, kf)) return fail(SDM_ERR_ARG, "keyframe slot %d out of range", kf);
     if (!c->kf[kf].uploaded) return fail(SDM_ERR_STATE, "keyframe slot %d not uploaded", kf);
     CU(cudaSetDevice(c->cfg.device));
-    int rc = sync_counts(c);
-    if (rc) return rc;
-    *count = c->kf[kf].cand_count;
+    CU(cudaMemcpyAsync(c->h_count, c->A.cand_count + kf, sizeof(int), cudaMemcpyDeviceToHost, c->s_copy));
+    CU(cudaStreamSynchronize(c->s_copy));
+    *count = *c->h_count;
     return SDM_OK;
 }
 
@@ -478,45 +626,42 @@ int sdm_pass1(sdm_ctx* c, int n, const sdm_item* items)
 {
     if (!c || (n > 0 && !items)) return fail(SDM_ERR_ARG, "sdm_pass1: null argument");
     if (n <= 0) return SDM_OK;
+    if (n > 65535) return fail(SDM_ERR_ARG, "pass-1 batch limited to 65535 keyframes per call");
     CU(cudaSetDevice(c->cfg.device));
-    int rc = sync_counts(c);
-    if (rc) return rc;
-    rc = upload_items(c, n, items, false);
-    if (rc) return rc;
-    long long total_blocks = 0, cands = 0;
+    Batch b;
+    RC(prepare_batch(c, n, items, false, false, &b));
     for (int i = 0; i < n; ++i) {
-        c->h_blk_off[i] = (int)total_blocks;
-        const int cnt = c->kf[items[i].kf].cand_count;
-        cands += cnt;
-        const int per_block = c->scan_warp_per_pixel ? sdm::kPass1Warps : sdm::kLaneBlock;
-        total_blocks += (cnt + per_block - 1) / per_block;
-    }
-    c->h_blk_off[n] = (int)total_blocks;
-    if (total_blocks > 0x7fffffffLL) return fail(SDM_ERR_ARG, "pass-1 batch too large (%lld blocks)", total_blocks);
-    c->stat_candidates = cands;
-    CU(cudaMemcpyAsync(c->d_blk_off, c->h_blk_off, sizeof(int) * (n + 1), cudaMemcpyHostToDevice, c->s_compute));
-    CU(cudaMemsetAsync(&c->d_stats->fused, 0, sizeof(unsigned long long), c->s_compute));
-    rc = copy_then_compute(c);
-    if (rc) return rc;
-    CU(cudaEventRecord(c->ev_p1[0], c->s_compute));
-    if (total_blocks > 0) {
-        if (c->scan_warp_per_pixel)
-            sdm::k_pass1<<<(unsigned)total_blocks, sdm::kPass1Warps * 32, 0, c->s_compute>>>(c->A, c->P, c->d_items,
-                                                                                            c->d_blk_off, n, c->d_stats);
-        else
-            sdm::k_pass1_lane<<<(unsigned)total_blocks, sdm::kLaneBlock, 0, c->s_compute>>>(c->A, c->P, c->d_items,
-                                                                                           c->d_blk_off, n, c->d_stats);
-        CU(cudaGetLastError());
-        c->launches++;
-    }
-    CU(cudaEventRecord(c->ev_p1_scan, c->s_compute));
-    if (c->cfg.intra_check || c->cfg.intra_grow)
-        for (int i = 0; i < n; ++i) {
-            rc = run_intra(c, items[i].kf, c->cfg.intra_check != 0, c->cfg.intra_grow != 0);
-            if (rc) return rc;
+        KfState& k = c->kf[items[i].kf];
+        if (k.rs_dense) {  // the slot's outputs were produced by the dense pass 2: drop stale non-candidate values
+            const size_t P = c->npix, s = (size_t)items[i].kf;
+            CU(cudaMemsetAsync(c->A.rs + s * P, 0, P * sizeof(float2), c->s_compute));
+            CU(cudaMemsetAsync(c->A.chk + s * P, 0, P * sizeof(float), c->s_compute));
+            CU(cudaMemsetAsync(c->A.pts + s * P * 3, 0, P * 3 * sizeof(float), c->s_compute));
+            k.rs_dense = false;
         }
+    }
+    CU(cudaMemsetAsync(&c->d_stats->fused, 0, sizeof(unsigned long long), c->s_compute));
+    const sdm::DevPlan plan = make_plan(c, nullptr, n);
+    sdm::k_plan<<<1, 1024, 0, c->s_compute>>>(plan, c->d_items, c->A.cand_count, c->d_stats);
+    CU(cudaEventRecord(c->ev_p1[0], c->s_compute));
+    if (c->scan_warp_per_pixel)
+        sdm::k_pass1<<<c->grid_pass1_warp, sdm::kPass1Warps * 32, 0, c->s_compute>>>(c->A, c->P, c->d_items, plan, c->d_stats);
+    else {
+        int max_n = 1;
+        for (int i = 0; i < n; ++i) max_n = std::max(max_n, (int)items[i].n_nbr);
+        const size_t smem = (size_t)max_n * sdm::kLaneBlock * sizeof(float2);
+        int occ = 0;  // persistent grid: fill every SM to this launch's occupancy
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sdm::k_pass1_lane, sdm::kLaneBlock, smem));
+        sdm::k_pass1_lane<<<std::max(1, occ) * c->n_sm, sdm::kLaneBlock, smem, c->s_compute>>>(c->A, c->P, c->d_items, plan,
+                                                                                               c->d_stats);
+    }
+    CU(cudaGetLastError());
+    c->launches += 2;
+    CU(cudaEventRecord(c->ev_p1_scan, c->s_compute));
+    RC(run_intra(c, b.d_slots, n, c->cfg.intra_check != 0, c->cfg.intra_grow != 0));
     CU(cudaEventRecord(c->ev_p1[1], c->s_compute));
     c->p1_timed = true;
+    RC(finish_batch(c, n, items));
     for (int i = 0; i < n; ++i) c->kf[items[i].kf].pass1_done = true;
     return SDM_OK;
 }
@@ -524,19 +669,26 @@ int sdm_pass1(sdm_ctx* c, int n, const sdm_item* items)
 static int pass2_impl(sdm_ctx* c, int n, const sdm_item* items, int points_only)
 {
     CU(cudaSetDevice(c->cfg.device));
-    int rc = upload_items(c, n, items, points_only == 0);
-    if (rc) return rc;
+    Batch b;
+    RC(prepare_batch(c, n, items, true, points_only != 0, &b));
     if (!points_only) CU(cudaMemsetAsync(&c->d_stats->checked, 0, sizeof(unsigned long long), c->s_compute));
-    rc = copy_then_compute(c);
-    if (rc) return rc;
     CU(cudaEventRecord(c->ev_p2[0], c->s_compute));
-    dim3 grid((unsigned)((c->npix + 255) / 256), (unsigned)n);
-    sdm::k_pass2<<<grid, 256, 0, c->s_compute>>>(c->A, c->P, c->d_items, c->d_stats, points_only);
+    if (b.n_sparse > 0) {
+        const sdm::DevPlan plan = make_plan(c, b.d_order_sparse, b.n_sparse);
+        sdm::k_plan<<<1, 1024, 0, c->s_compute>>>(plan, c->d_items, c->A.cand_count, nullptr);
+        sdm::k_pass2_cand<<<c->grid_pass2, sdm::kLaneBlock, 0, c->s_compute>>>(c->A, c->P, c->d_items, plan, c->d_stats);
+        c->launches += 2;
+    }
+    if (b.n_dense > 0) {
+        dim3 grid((unsigned)((c->npix + 255) / 256), (unsigned)b.n_dense);
+        sdm::k_pass2<<<grid, 256, 0, c->s_compute>>>(c->A, c->P, c->d_items, b.d_order_dense, points_only ? nullptr : c->d_stats,
+                                                     points_only);
+        c->launches++;
+    }
     CU(cudaGetLastError());
-    c->launches++;
     CU(cudaEventRecord(c->ev_p2[1], c->s_compute));
     c->p2_timed = true;
-    return SDM_OK;
+    return finish_batch(c, n, items);
 }
 
 int sdm_pass2(sdm_ctx* c, int n, const sdm_item* items)
@@ -560,8 +712,8 @@ int sdm_update_points(sdm_ctx* c, int n, const int32_t* kfs)
     return pass2_impl(c, n, items.data(), 1);
 }
 
-int sdm_download(sdm_ctx* c, int kf, float* depth, size_t depth_step, float* sigma, size_t sigma_step, float* checked,
-                 size_t checked_step, float* points, size_t points_step)
+int sdm_download_async(sdm_ctx* c, int kf, float* depth, size_t depth_step, float* sigma, size_t sigma_step, float* checked,
+                       size_t checked_step, float* points, size_t points_step)
 {
     if (!c) return fail(SDM_ERR_ARG, "null context");
     if (!slot_ok(c, kf)) return fail(SDM_ERR_ARG, "keyframe slot %d out of range", kf);
@@ -571,18 +723,32 @@ int sdm_download(sdm_ctx* c, int kf, float* depth, size_t depth_step, float* sig
         (points && points_step < 3 * row))
         return fail(SDM_ERR_ARG, "row step smaller than a row");
     CU(cudaSetDevice(c->cfg.device));
-    cudaStream_t s = c->s_compute;
+    KfState& k = c->kf[kf];
+    cudaStream_t s = c->s_down;
+    RC(c->r_compute.wait(s, k.comp_id));
+    RC(c->r_copy.wait(s, k.up_id));
     if (depth || sigma) {
-        sdm::k_split_rs<<<(unsigned)((P + 255) / 256), 256, 0, s>>>(c->A.rs + (size_t)kf * P, c->dl_stage, c->dl_stage + P, P);
+        DownStage& st = c->down[c->down_next];
+        c->down_next = (c->down_next + 1) % kDownStages;
+        // same stream: the previous user's D2H copies are ordered before this kernel
+        sdm::k_split_rs<<<(unsigned)((P + 255) / 256), 256, 0, s>>>(c->A.rs + (size_t)kf * P, st.planes, st.planes + P, P);
         CU(cudaGetLastError());
         c->launches++;
-        if (depth) CU(cudaMemcpy2DAsync(depth, depth_step, c->dl_stage, row, row, H, cudaMemcpyDeviceToHost, s));
-        if (sigma) CU(cudaMemcpy2DAsync(sigma, sigma_step, c->dl_stage + P, row, row, H, cudaMemcpyDeviceToHost, s));
+        if (depth) RC(copy2d(depth, depth_step, st.planes, row, row, H, cudaMemcpyDeviceToHost, s));
+        if (sigma) RC(copy2d(sigma, sigma_step, st.planes + P, row, row, H, cudaMemcpyDeviceToHost, s));
     }
-    if (checked) CU(cudaMemcpy2DAsync(checked, checked_step, c->A.chk + (size_t)kf * P, row, row, H, cudaMemcpyDeviceToHost, s));
+    if (checked) RC(copy2d(checked, checked_step, c->A.chk + (size_t)kf * P, row, row, H, cudaMemcpyDeviceToHost, s));
     if (points)
-        CU(cudaMemcpy2DAsync(points, points_step, c->A.pts + (size_t)kf * P * 3, 3 * row, 3 * row, H, cudaMemcpyDeviceToHost, s));
-    CU(cudaStreamSynchronize(s));
+        RC(copy2d(points, points_step, c->A.pts + (size_t)kf * P * 3, 3 * row, 3 * row, H, cudaMemcpyDeviceToHost, s));
+    RC(c->r_down.record(s, &k.down_id));
+    return SDM_OK;
+}
+
+int sdm_download(sdm_ctx* c, int kf, float* depth, size_t depth_step, float* sigma, size_t sigma_step, float* checked,
+                 size_t checked_step, float* points, size_t points_step)
+{
+    RC(sdm_download_async(c, kf, depth, depth_step, sigma, sigma_step, checked, checked_step, points, points_step));
+    CU(cudaStreamSynchronize(c->s_down));
     return SDM_OK;
 }
 
@@ -594,14 +760,19 @@ int sdm_upload_depth(sdm_ctx* c, int kf, const float* depth, size_t depth_step, 
     const size_t P = c->npix, row = (size_t)W * 4;
     if (depth_step < row || sigma_step < row) return fail(SDM_ERR_ARG, "row step smaller than a row");
     CU(cudaSetDevice(c->cfg.device));
+    KfState& k = c->kf[kf];
     cudaStream_t s = c->s_compute;
-    CU(cudaMemcpy2DAsync(c->dl_stage, row, depth, depth_step, row, H, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpy2DAsync(c->dl_stage + P, row, sigma, sigma_step, row, H, cudaMemcpyHostToDevice, s));
-    sdm::k_merge_rs<<<(unsigned)((P + 255) / 256), 256, 0, s>>>(c->A.rs + (size_t)kf * P, c->dl_stage, c->dl_stage + P, P);
+    RC(c->r_copy.wait(s, k.up_id));
+    RC(c->r_down.wait(s, k.down_id));
+    RC(copy2d(c->xfer, row, depth, depth_step, row, H, cudaMemcpyHostToDevice, s));
+    RC(copy2d(c->xfer + P, row, sigma, sigma_step, row, H, cudaMemcpyHostToDevice, s));
+    sdm::k_merge_rs<<<(unsigned)((P + 255) / 256), 256, 0, s>>>(c->A.rs + (size_t)kf * P, c->xfer, c->xfer + P, P);
     CU(cudaGetLastError());
     c->launches++;
+    RC(c->r_compute.record(s, &k.comp_id));
     CU(cudaStreamSynchronize(s));
-    c->kf[kf].pass1_done = true;
+    k.pass1_done = true;
+    k.rs_dense = true;
     return SDM_OK;
 }
 
@@ -654,9 +825,14 @@ int sdm_pull_halo(sdm_ctx* c, int n, const int32_t* local_slot, const int32_t* p
         const int pr = peer_rank[i];
         if (pr < 0 || pr >= kMaxPeers || !c->peer_rs[pr]) return fail(SDM_ERR_STATE, "peer %d arena not imported", pr);
         if (peer_slot[i] < 0) return fail(SDM_ERR_ARG, "peer slot %d negative", peer_slot[i]);
+        KfState& k = c->kf[local_slot[i]];
+        RC(c->r_copy.wait(c->s_compute, k.up_id));  // k_pack zeroes the plane: must not land after the pull
+        RC(c->r_down.wait(c->s_compute, k.down_id));
         const char* src = (const char*)c->peer_rs[pr] + (size_t)peer_slot[i] * bytes;
         CU(cudaMemcpyAsync(c->A.rs + (size_t)local_slot[i] * c->npix, src, bytes, cudaMemcpyDeviceToDevice, c->s_compute));
-        c->kf[local_slot[i]].pass1_done = true;
+        RC(c->r_compute.record(c->s_compute, &k.comp_id));
+        k.pass1_done = true;
+        k.rs_dense = true;
     }
     return SDM_OK;
 }
@@ -666,6 +842,7 @@ int sdm_mark_pass1_done(sdm_ctx* c, int kf)
     if (!c) return fail(SDM_ERR_ARG, "null context");
     if (!slot_ok(c, kf)) return fail(SDM_ERR_ARG, "keyframe slot %d out of range", kf);
     c->kf[kf].pass1_done = true;
+    c->kf[kf].rs_dense = true;
     return SDM_OK;
 }
 
@@ -698,11 +875,9 @@ static int single_pair_item(sdm_ctx* c, int kf1, int kf2, float mind, float maxd
     it.rot_deg[0] = rot;
     it.min_depth = mind;
     it.max_depth = maxd;
-    int rc = sync_counts(c);
-    if (rc) return rc;
-    rc = upload_items(c, 1, &it, false);
-    if (rc) return rc;
-    return copy_then_compute(c);
+    Batch b;
+    RC(prepare_batch(c, 1, &it, false, false, &b));
+    return finish_batch(c, 1, &it);  // the debug kernels follow on s_compute right away
 }
 
 static int ensure_dbg(sdm_ctx* c)
@@ -715,10 +890,8 @@ int sdm_search_range(sdm_ctx* c, int kf1, int kf2, int px, int py, float mind, f
 {
     if (!c || !umin || !umax) return fail(SDM_ERR_ARG, "null argument");
     CU(cudaSetDevice(c->cfg.device));
-    int rc = single_pair_item(c, kf1, kf2, mind, maxd, 0.f);
-    if (rc) return rc;
-    rc = ensure_dbg(c);
-    if (rc) return rc;
+    RC(single_pair_item(c, kf1, kf2, mind, maxd, 0.f));
+    RC(ensure_dbg(c));
     sdm::k_search_range<<<1, 1, 0, c->s_compute>>>(c->P, c->d_items, px, py, c->dbg);
     CU(cudaGetLastError());
     c->launches++;
@@ -731,16 +904,13 @@ int sdm_search_range(sdm_ctx* c, int kf1, int kf2, int px, int py, float mind, f
 }
 
 int sdm_epipolar_search(sdm_ctx* c, int kf1, int kf2, int x, int y, float pixel, float min_depth, float max_depth,
-                        float th_pi, float rot_deg,
-                        sdm_hypothesis* out)
+                        float th_pi, float rot_deg, sdm_hypothesis* out)
 {
     if (!c || !out) return fail(SDM_ERR_ARG, "null argument");
     if (x < 0 || y < 0 || x >= c->cfg.width || y >= c->cfg.height) return fail(SDM_ERR_ARG, "pixel (%d,%d) outside the image", x, y);
     CU(cudaSetDevice(c->cfg.device));
-    int rc = single_pair_item(c, kf1, kf2, min_depth, max_depth, rot_deg);
-    if (rc) return rc;
-    rc = ensure_dbg(c);
-    if (rc) return rc;
+    RC(single_pair_item(c, kf1, kf2, min_depth, max_depth, rot_deg));
+    RC(ensure_dbg(c));
     float* d = c->dbg;
     uint8_t* ok = (uint8_t*)(c->dbg + 4);
     sdm::k_pair_hypotheses<<<1, sdm::kPass1Warps * 32, 0, c->s_compute>>>(c->A, c->P, c->d_items, d, d + 1, d + 2, d + 3, ok,
@@ -765,21 +935,18 @@ int sdm_epipolar_search_plane(sdm_ctx* c, int kf1, int kf2, float min_depth, flo
 {
     if (!c || !hyp_depth || !hyp_sigma || !hyp_u || !ok) return fail(SDM_ERR_ARG, "null argument");
     CU(cudaSetDevice(c->cfg.device));
-    int rc = single_pair_item(c, kf1, kf2, min_depth, max_depth, rot_deg);
-    if (rc) return rc;
-    rc = ensure_dbg(c);
-    if (rc) return rc;
+    RC(single_pair_item(c, kf1, kf2, min_depth, max_depth, rot_deg));
+    RC(ensure_dbg(c));
     const size_t P = c->npix;
     float* d = c->dbg;
     uint8_t* dok = (uint8_t*)(c->dbg + 4 * P);
     CU(cudaMemsetAsync(c->dbg, 0, P * (4 * sizeof(float) + 1), c->s_compute));
-    const int cnt = c->kf[kf1].cand_count;
-    if (cnt > 0) {
-        sdm::k_pair_hypotheses<<<(cnt + sdm::kPass1Warps - 1) / sdm::kPass1Warps, sdm::kPass1Warps * 32, 0, c->s_compute>>>(
-            c->A, c->P, c->d_items, d, d + P, d + 2 * P, nullptr, dok, -1, 0.f, 0.f);
-        CU(cudaGetLastError());
-        c->launches++;
-    }
+    // upper bound of the candidate count (the kernel exits above the real one): no host round trip
+    const unsigned blocks = (unsigned)((P + sdm::kPass1Warps - 1) / sdm::kPass1Warps);
+    sdm::k_pair_hypotheses<<<blocks, sdm::kPass1Warps * 32, 0, c->s_compute>>>(c->A, c->P, c->d_items, d, d + P, d + 2 * P, nullptr,
+                                                                               dok, -1, 0.f, 0.f);
+    CU(cudaGetLastError());
+    c->launches++;
     CU(cudaMemcpyAsync(hyp_depth, d, P * 4, cudaMemcpyDeviceToHost, c->s_compute));
     CU(cudaMemcpyAsync(hyp_sigma, d + P, P * 4, cudaMemcpyDeviceToHost, c->s_compute));
     CU(cudaMemcpyAsync(hyp_u, d + 2 * P, P * 4, cudaMemcpyDeviceToHost, c->s_compute));
@@ -817,25 +984,23 @@ int sdm_fuse(sdm_ctx* c, int m, int n, const float* depth, const float* sigma, c
     return SDM_OK;
 }
 
-int sdm_intra_check(sdm_ctx* c, int kf)
+static int intra_single(sdm_ctx* c, int kf, bool check, bool grow)
 {
     if (!c) return fail(SDM_ERR_ARG, "null context");
     if (!slot_ok(c, kf)) return fail(SDM_ERR_ARG, "keyframe slot %d out of range", kf);
-    if (!c->kf[kf].pass1_done) return fail(SDM_ERR_STATE, "slot %d has no pass-1 planes", kf);
+    KfState& k = c->kf[kf];
+    if (!k.pass1_done || (grow && !k.uploaded)) return fail(SDM_ERR_STATE, "slot %d has no pass-1 planes", kf);
     CU(cudaSetDevice(c->cfg.device));
-    return run_intra(c, kf, true, false);
+    RC(c->r_copy.wait(c->s_compute, k.up_id));
+    RC(c->r_down.wait(c->s_compute, k.down_id));
+    int* d_slots;
+    RC(single_slot_array(c, kf, &d_slots));
+    RC(run_intra(c, d_slots, 1, check, grow));
+    return c->r_compute.record(c->s_compute, &k.comp_id);
 }
 
-int sdm_intra_grow(sdm_ctx* c, int kf)
-{
-    if (!c) return fail(SDM_ERR_ARG, "null context");
-    if (!slot_ok(c, kf)) return fail(SDM_ERR_ARG, "keyframe slot %d out of range", kf);
-    if (!c->kf[kf].pass1_done || !c->kf[kf].uploaded) return fail(SDM_ERR_STATE, "slot %d has no pass-1 planes", kf);
-    CU(cudaSetDevice(c->cfg.device));
-    int rc = copy_then_compute(c);
-    if (rc) return rc;
-    return run_intra(c, kf, false, true);
-}
+int sdm_intra_check(sdm_ctx* c, int kf) { return intra_single(c, kf, true, false); }
+int sdm_intra_grow(sdm_ctx* c, int kf) { return intra_single(c, kf, false, true); }
 
 int sdm_inter_check(sdm_ctx* c, const sdm_item* item)
 {

@@ -322,6 +322,10 @@ __global__ void __launch_bounds__(256) k_pack(DevArena A, DevParams P, int slot,
         A.tex[base + i0] = make_float4(g0, g1, theta[i0], theta[i1]);
         A.ipair[base + i0] = make_uchar2(im[i0], im[i1]);
         A.rs[base + i0] = make_float2(0.f, 0.f);
+        A.chk[base + i0] = 0.f;  // pass 2 only visits candidate pixels: the rest of the output planes stays 0
+        A.pts[3 * (base + i0) + 0] = 0.f;
+        A.pts[3 * (base + i0) + 1] = 0.f;
+        A.pts[3 * (base + i0) + 2] = 0.f;
         is_cand = (edge == nullptr || edge[i0] >= 0) && !(g0 <= P.lambdaG);
     }
     const unsigned bal = __ballot_sync(SDM_FULL, is_cand);
@@ -339,39 +343,113 @@ __global__ void __launch_bounds__(256) k_pack(DevArena A, DevParams P, int slot,
     }
 }
 
+__device__ __forceinline__ void load_item(DevItem& s_item, const DevItem* __restrict__ src_item)
+{
+    const int* src = reinterpret_cast<const int*>(src_item);
+    int* dst = reinterpret_cast<int*>(&s_item);
+    const int header = (int)(offsetof(DevItem, pair) / 4);
+    const int words = header + src_item->n_nbr * (int)(sizeof(DevPair) / 4);
+    for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+}
+
 // ---------------------------------------------------------------------------------------------
-// K3 + K4: warp-per-pixel epipolar scan + hypothesis fusion (hot loop 1, :447-489)
-//   phase A  lane j sets up neighbour j (line, search range, invariants)
-//   phase B  for each neighbour: 32 lanes stride the columns of the search range, argmin by shuffles
-//   phase C  lane j refines neighbour j's best column into a hypothesis (rho, sigma)
-//   phase D  chi-square compatibility sets across lanes, first-largest set, weighted fusion
+// Work plan of a pass: the candidates of the batch's keyframes are cut into chunks of kChunk
+// consecutive candidates of ONE keyframe.  k_plan builds the chunk prefix over the batch on the
+// device (candidate counts never travel to the host, so a pass can be enqueued while the uploads
+// it depends on are still in flight); the pass kernels are persistent: a fixed grid of blocks
+// pulls chunk ids from an atomic counter until the plan is exhausted.
+// ---------------------------------------------------------------------------------------------
+constexpr int kChunk = 128;
+
+struct DevPlan {
+    int* chunk_off;  // [n_items + 1] exclusive prefix of chunks per batch entry
+    int* counter;    // next chunk to hand out
+    const int* order;  // batch entry -> index into items[] (nullptr = identity)
+    int n_items;
+};
+
+__global__ void __launch_bounds__(1024)
+k_plan(DevPlan plan, const DevItem* __restrict__ items, const int* __restrict__ cand_count, DevStats* stats)
+{
+    __shared__ int s_warp[32];
+    __shared__ int s_base;
+    __shared__ unsigned long long s_cands;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) { s_base = 0; s_cands = 0ULL; *plan.counter = 0; }
+    __syncthreads();
+    for (int i0 = 0; i0 < plan.n_items; i0 += 1024) {
+        const int i = i0 + tid;
+        int cnt = 0;
+        if (i < plan.n_items) cnt = cand_count[items[plan.order ? plan.order[i] : i].kf];
+        const int chunks = (cnt + kChunk - 1) / kChunk;
+        int incl = chunks;  // inclusive warp scan
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int v = __shfl_up_sync(SDM_FULL, incl, off);
+            if (lane >= off) incl += v;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        unsigned long long c64 = (unsigned long long)cnt;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) c64 += __shfl_xor_sync(SDM_FULL, c64, off);
+        if (lane == 0 && c64) atomicAdd(&s_cands, c64);
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane];
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const int v = __shfl_up_sync(SDM_FULL, w, off);
+                if (lane >= off) w += v;
+            }
+            s_warp[lane] = w;  // inclusive over warps
+        }
+        __syncthreads();
+        const int before = s_base + (warp ? s_warp[warp - 1] : 0) + incl - chunks;
+        if (i < plan.n_items) plan.chunk_off[i] = before;
+        __syncthreads();
+        if (tid == 0) s_base += s_warp[31];
+        __syncthreads();
+    }
+    if (tid == 0) {
+        plan.chunk_off[plan.n_items] = s_base;
+        if (stats) stats->candidates = s_cands;
+    }
+}
+
+// fetch the next chunk for this block: returns false when the plan is exhausted.  On return s_item holds the
+// chunk's keyframe and first = index of the chunk's first candidate in that keyframe's list.
+__device__ __forceinline__ bool next_chunk(const DevPlan& plan, const DevItem* __restrict__ items, DevItem& s_item,
+                                           int& s_chunk, int& cur_entry, int& first)
+{
+    __syncthreads();  // everyone is done with the previous chunk (s_item, s_chunk)
+    if (threadIdx.x == 0) s_chunk = atomicAdd(plan.counter, 1);
+    __syncthreads();
+    const int chunk = s_chunk;
+    const int total = plan.chunk_off[plan.n_items];
+    if (chunk >= total) return false;
+    int lo = 0, hi = plan.n_items;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (plan.chunk_off[mid] <= chunk) lo = mid; else hi = mid;
+    }
+    if (lo != cur_entry) {
+        load_item(s_item, &items[plan.order ? plan.order[lo] : lo]);
+        cur_entry = lo;
+    }
+    __syncthreads();
+    first = (chunk - plan.chunk_off[lo]) * kChunk;
+    return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3 + K4, warp-per-pixel variant (A/B reference, env SDM_SCAN=warp): lanes stride the columns of a
+// search range, argmin by shuffles, lane j refines neighbour j, chi-square sets across lanes.
 // ---------------------------------------------------------------------------------------------
 constexpr int kPass1Warps = 8;
 
-__global__ void __launch_bounds__(kPass1Warps * 32)
-k_pass1(DevArena A, DevParams P, const DevItem* __restrict__ items, const int* __restrict__ blk_off, int n_items,
-        DevStats* stats)
+__device__ __forceinline__ bool scan_pixel_warp(const DevArena& A, const DevParams& P, const DevItem& s_item, int ci, int lane)
 {
-    __shared__ DevItem s_item;
-    // block -> item (blocks never straddle items)
-    int lo = 0, hi = n_items;
-    const int bid = blockIdx.x;
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (blk_off[mid] <= bid) lo = mid; else hi = mid;
-    }
-    {
-        const int* src = reinterpret_cast<const int*>(&items[lo]);
-        int* dst = reinterpret_cast<int*>(&s_item);
-        const int header = (int)(offsetof(DevItem, pair) / 4);
-        const int words = header + items[lo].n_nbr * (int)(sizeof(DevPair) / 4);
-        for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
-    }
-    __syncthreads();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int ci = (bid - blk_off[lo]) * kPass1Warps + warp;
     const int kf = s_item.kf;
-    if (ci >= A.cand_count[kf]) return;
     const int N = s_item.n_nbr;
     const uint32_t packed = A.cand[(size_t)kf * A.P + ci];
     const int x = (int)(packed & 0xffffu), y = (int)(packed >> 16);
@@ -383,7 +461,7 @@ k_pass1(DevArena A, DevParams P, const DevItem* __restrict__ items, const int* _
     const float xn = (x - K[2]) / K[0], yn = (y - K[3]) / K[1];
     const float Hm1 = (float)(P.H - 1);
 
-    // phase A
+    // phase A: lane j sets up neighbour j
     PairSetup my;
     my.valid = false; my.u_lo = 1; my.u_hi = 0; my.ab = 0.f; my.cb = 0.f; my.th_line = 0.f; my.ang_pi_rot = 0.f;
     if (lane < N) my = pair_setup(s_item.pair[lane], K, P, x, y, xn, yn, s_item.min_depth, s_item.max_depth, th_pi);
@@ -471,10 +549,27 @@ k_pass1(DevArena A, DevParams P, const DevItem* __restrict__ items, const int* _
             fused = true;
         }
     }
-    if (lane == 0) {
-        A.rs[(size_t)kf * A.P + (size_t)y * P.W + x] = make_float2(out_d, out_s);
-        if (fused && stats) atomicAdd(&stats->fused, 1ULL);
+    if (lane == 0) A.rs[(size_t)kf * A.P + (size_t)y * P.W + x] = make_float2(out_d, out_s);
+    return fused;
+}
+
+__global__ void __launch_bounds__(kPass1Warps * 32)
+k_pass1(DevArena A, DevParams P, const DevItem* __restrict__ items, DevPlan plan, DevStats* stats)
+{
+    __shared__ DevItem s_item;
+    __shared__ int s_chunk;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int cur_entry = -1, first = 0;
+    unsigned long long n_fused = 0;
+    while (next_chunk(plan, items, s_item, s_chunk, cur_entry, first)) {
+        const int cnt = A.cand_count[s_item.kf];
+        for (int k = warp; k < kChunk; k += kPass1Warps) {
+            const int ci = first + k;
+            if (ci >= cnt) break;
+            if (scan_pixel_warp(A, P, s_item, ci, lane)) ++n_fused;
+        }
     }
+    if (stats && lane == 0 && n_fused) atomicAdd(&stats->fused, n_fused);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -487,132 +582,181 @@ k_pass1(DevArena A, DevParams P, const DevItem* __restrict__ items, const int* _
 // fusion, v(u+1) is carried to the next column instead of recomputed, the best column's residuals
 // are kept instead of re-evaluated.  Hypotheses of a pixel stay in shared memory ([nbr][thread]).
 // ---------------------------------------------------------------------------------------------
-constexpr int kLaneBlock = 128;
+constexpr int kLaneBlock = kChunk;
 
 __device__ __forceinline__ bool in_rows(float v, float Hm1) { return v >= 0.f && v <= Hm1; }
 
-__global__ void __launch_bounds__(kLaneBlock)
-k_pass1_lane(DevArena A, DevParams P, const DevItem* __restrict__ items, const int* __restrict__ blk_off, int n_items,
-             DevStats* stats)
+// The scan body skips column u unless rows v(u-1), v(u), v(u+1) all lie in [0, H-1] (:773-785), with
+// v(k) = -((a/b)*k + c/b) evaluated in float.  Float rounding is monotone, so v(k) is monotone in k and
+// the set {k : 0 <= v(k) <= H-1} is ONE integer interval [p, q]; the admissible columns are therefore
+// [max(u_lo, p+1), min(u_hi, q-1)].  p and q are located with the exact float predicate (endpoints first:
+// in the common case the whole range is inside; otherwise a binary search on the monotone half-tests).
+__device__ __forceinline__ float line_row(float ab, float cb, int k) { return -(ab * (float)k + cb); }
+
+__device__ __forceinline__ void valid_columns(float ab, float cb, float Hm1, int u_lo, int u_hi, int& ua, int& ub)
 {
-    __shared__ DevItem s_item;
-    __shared__ float2 s_h[SDM_MAX_NBR][kLaneBlock];
-    int lo = 0, hi = n_items;
-    const int bid = blockIdx.x;
-    while (hi - lo > 1) {
-        int mid = (lo + hi) >> 1;
-        if (blk_off[mid] <= bid) lo = mid; else hi = mid;
+    const int lo = u_lo - 1, hi = u_hi + 1;
+    const float v_lo = line_row(ab, cb, lo), v_hi = line_row(ab, cb, hi);
+    if (in_rows(v_lo, Hm1) && in_rows(v_hi, Hm1)) { ua = u_lo; ub = u_hi; return; }
+    ua = 1; ub = 0;
+    if (!(v_lo == v_lo) || !(v_hi == v_hi)) return;  // NaN line: nothing is inside
+    // orient so that f(k) = s * v(k) is non-decreasing in k: rows too small on the left, too large on the right
+    const bool inc = v_hi >= v_lo;
+    // p = first k with v(k) inside the lower bound of its direction, q = last k inside the upper bound
+    int a = lo, b = hi + 1;  // first k in [lo, hi+1) with "left test" true
+    while (a < b) {
+        const int m = (a + b) >> 1;
+        const float v = line_row(ab, cb, m);
+        const bool ok = inc ? (v >= 0.f) : (v <= Hm1);
+        if (ok) b = m; else a = m + 1;
     }
-    {
-        const int* src = reinterpret_cast<const int*>(&items[lo]);
-        int* dst = reinterpret_cast<int*>(&s_item);
-        const int header = (int)(offsetof(DevItem, pair) / 4);
-        const int words = header + items[lo].n_nbr * (int)(sizeof(DevPair) / 4);
-        for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
+    const int p = a;
+    a = lo - 1; b = hi;  // last k in (lo-1, hi] with "right test" true
+    while (a < b) {
+        const int m = (a + b + 1) >> 1;
+        const float v = line_row(ab, cb, m);
+        const bool ok = inc ? (v <= Hm1) : (v >= 0.f);
+        if (ok) a = m; else b = m - 1;
     }
-    __syncthreads();
-    const int tid = threadIdx.x;
-    const int ci = (bid - blk_off[lo]) * kLaneBlock + tid;
+    const int q = a;
+    ua = max(u_lo, p + 1);
+    ub = min(u_hi, q - 1);
+}
+
+__device__ __forceinline__ bool scan_pixel_lane(const DevArena& A, const DevParams& P, const DevItem& s_item,
+                                                float2 (*s_h)[kLaneBlock], int ci, int tid)
+{
     const int kf = s_item.kf;
-    const bool active = ci < A.cand_count[kf];
-    bool fused = false;
-    if (active) {
-        const int N = s_item.n_nbr;
-        const uint32_t packed = A.cand[(size_t)kf * A.P + ci];
-        const int x = (int)(packed & 0xffffu), y = (int)(packed >> 16);
-        const size_t own = (size_t)kf * A.P + (size_t)y * P.W + x;
-        const float4 t1 = __ldg(&A.tex[own]);
-        const float gradc = t1.x, th_pi = t1.z;
-        const float pixel = (float)__ldg(&A.ipair[own]).x;
-        const float* K = s_item.K;
-        const float xn = (x - K[2]) / K[0], yn = (y - K[3]) / K[1];
-        const float Hm1 = (float)(P.H - 1);
-        const int W = P.W;
-        int nh = 0;
-        for (int j = 0; j < N; ++j) {
-            const DevPair& g = s_item.pair[j];
-            const PairSetup s = pair_setup(g, K, P, x, y, xn, yn, s_item.min_depth, s_item.max_depth, th_pi);
-            if (s.u_lo > s.u_hi) continue;
-            const size_t nb = (size_t)g.slot * A.P;
-            const float4* __restrict__ tex2 = A.tex + nb;
-            const uchar2* __restrict__ ip2 = A.ipair + nb;
-            const float ab = s.ab, cb = s.cb;
-            float best_err = 100000.0f, best_pe = 0.f, best_ge = 0.f;
-            int best_u = -1;
-            float v_m = -(ab * (float)(s.u_lo - 1) + cb);
-            float v_c = -(ab * (float)s.u_lo + cb);
-            bool in_m = in_rows(v_m, Hm1), in_c = in_rows(v_c, Hm1);
-            for (int u = s.u_lo; u <= s.u_hi; ++u) {
-                const float v_p = -(ab * (float)(u + 1) + cb);
-                const bool in_p = in_rows(v_p, Hm1);
-                const bool inside = in_m && in_c && in_p;
-                const float v = v_c;
-                v_m = v_c; v_c = v_p; in_m = in_c; in_c = in_p;
-                if (!inside) continue;
-                const RowW r = row_weights(v);
-                const int idx = r.y0 * W + u;
-                const float4 t = __ldg(&tex2[idx]);
-                const float g2 = t.x * r.w0 + t.y * r.w1;
-                if (g2 <= P.lambdaG) continue;  // condition 1
-                const float gth = yangle_interp(t.z, t.w, r.w0, r.w1);
+    const int N = s_item.n_nbr;
+    const uint32_t packed = A.cand[(size_t)kf * A.P + ci];
+    const int x = (int)(packed & 0xffffu), y = (int)(packed >> 16);
+    const size_t own = (size_t)kf * A.P + (size_t)y * P.W + x;
+    const float4 t1 = __ldg(&A.tex[own]);
+    const float gradc = t1.x, th_pi = t1.z;
+    const float pixel = (float)__ldg(&A.ipair[own]).x;
+    const float* K = s_item.K;
+    const float xn = (x - K[2]) / K[0], yn = (y - K[3]) / K[1];
+    const float Hm1 = (float)(P.H - 1);
+    int W = P.W;
+    float lamG = P.lambdaG, lamL = P.lambdaL, lamT = P.lambdaTheta, theta = P.theta;
+    asm volatile("" : "+r"(W), "+f"(lamG), "+f"(lamL), "+f"(lamT), "+f"(theta));
+    int nh = 0;
+    for (int j = 0; j < N; ++j) {
+        const DevPair& g = s_item.pair[j];
+        const PairSetup s = pair_setup(g, K, P, x, y, xn, yn, s_item.min_depth, s_item.max_depth, th_pi);
+        if (s.u_lo > s.u_hi) continue;
+        const size_t nb = (size_t)g.slot * A.P;
+        const float4* __restrict__ tex2 = A.tex + nb;
+        const uchar2* __restrict__ ip2 = A.ipair + nb;
+        const float ab = s.ab, cb = s.cb;
+        float best_err = 100000.0f, best_pe = 0.f, best_ge = 0.f;
+        int best_u = -1;
+        // columns whose three rows v(u-1), v(u), v(u+1) are inside the image (:773-785), as one interval
+        int ua, ub;
+        valid_columns(ab, cb, Hm1, s.u_lo, s.u_hi, ua, ub);
+        if (ua <= ub) {
+            // keep the loop's operands in registers (ptxas otherwise re-derives them from constant memory)
+            const char* tb = reinterpret_cast<const char*>(tex2);
+            const char* ib = reinterpret_cast<const char*>(ip2);
+            asm volatile("" : "+l"(tb), "+l"(ib));
+            // software pipeline: the texel of column u+1 is requested while column u is evaluated.  Column
+            // ub+1 is a valid address (ub <= W-2 and its row is inside the image by construction).
+            float vn = -(ab * (float)ua + cb);
+            float fl = floorf(vn);
+            float w0n = (fl + 1.0f) - vn, w1n = vn - fl;
+            unsigned idxn = (unsigned)((int)fl * W + ua);
+            float4 tn = __ldg(reinterpret_cast<const float4*>(tb + (size_t)idxn * 16));
+            for (int u = ua; u <= ub; ++u) {
+                const float4 t = tn;
+                const float w0 = w0n, w1 = w1n;
+                const unsigned idx = idxn;
+                vn = -(ab * (float)(u + 1) + cb);
+                fl = floorf(vn);
+                w0n = (fl + 1.0f) - vn;
+                w1n = vn - fl;
+                idxn = (unsigned)((int)fl * W + (u + 1));
+                tn = __ldg(reinterpret_cast<const float4*>(tb + (size_t)idxn * 16));
+                const float g2 = t.x * w0 + t.y * w1;
+                if (g2 <= lamG) continue;  // condition 1
+                const float gth = yangle_interp(t.z, t.w, w0, w1);
                 float ang = gth - s.th_line;  // condition 2
                 if (ang >= 360.f) ang -= 360.f;
                 if (ang < 0.f) ang += 360.f;
                 if (ang > 180.f) ang = 360.f - ang;
                 if (ang > 90.f) ang = 180.f - ang;
-                if (ang >= P.lambdaL) continue;
+                if (ang >= lamL) continue;
                 float thd = gth - s.ang_pi_rot;  // condition 3
                 if (thd >= 360.f) thd -= 360.f;
                 if (thd < 0.f) thd += 360.f;
                 if (thd > 180.f) thd = 360.f - thd;
-                if (thd >= P.lambdaTheta) continue;
-                const uchar2 i2 = __ldg(&ip2[idx]);
-                const float pe = pixel - ((float)i2.x * r.w0 + (float)i2.y * r.w1);
+                if (thd >= lamT) continue;
+                const uchar2 i2 = __ldg(reinterpret_cast<const uchar2*>(ib + (size_t)idx * 2));
+                const float pe = pixel - ((float)i2.x * w0 + (float)i2.y * w1);
                 const float ge = gradc - g2;
-                const float err = pe * pe + (ge * ge) / P.theta;
+                const float err = pe * pe + (ge * ge) / theta;
                 if (err < best_err) { best_err = err; best_u = u; best_pe = pe; best_ge = ge; }
             }
-            if (best_err < 100000.0f) {
-                const Hypo h = refine_hypothesis(tex2, ip2, g, K, P, best_u, ab, cb, best_pe, best_ge, xn, yn);
-                if (1.0f / h.depth > 0.0f) {  // :472
-                    s_h[nh][tid] = make_float2(h.depth, h.sigma);
-                    ++nh;
-                }
+        }
+        if (best_err < 100000.0f) {
+            const Hypo h = refine_hypothesis(tex2, ip2, g, K, P, best_u, ab, cb, best_pe, best_ge, xn, yn);
+            if (1.0f / h.depth > 0.0f) {  // :472
+                s_h[nh][tid] = make_float2(h.depth, h.sigma);
+                ++nh;
             }
         }
-        // InverseDepthHypothesisFusion (:978-1009) over this pixel's nh hypotheses (neighbour order)
-        float out_d = 0.f, out_s = 0.f;
-        if (nh > P.lambdaN) {
-            unsigned best_mask = 0;
-            int best_n = 0;
-            for (int a = 0; a < nh; ++a) {
-                const float2 ha = s_h[a][tid];
-                unsigned m = 1u << a;
-                for (int b = 0; b < nh; ++b) {
-                    if (b == a) continue;
-                    const float2 hb = s_h[b][tid];
-                    if (chi_compatible(ha.x, hb.x, ha.y, hb.y, P.chi_fusion_lt)) m |= 1u << b;
-                }
-                const int cnt = __popc(m);
-                if (best_n < cnt) { best_n = cnt; best_mask = m; }
+    }
+    // InverseDepthHypothesisFusion (:978-1009) over this pixel's nh hypotheses (neighbour order)
+    float out_d = 0.f, out_s = 0.f;
+    bool fused = false;
+    if (nh > P.lambdaN) {
+        unsigned best_mask = 0;
+        int best_n = 0;
+        for (int a = 0; a < nh; ++a) {
+            const float2 ha = s_h[a][tid];
+            unsigned m = 1u << a;
+            for (int b = 0; b < nh; ++b) {
+                if (b == a) continue;
+                const float2 hb = s_h[b][tid];
+                if (chi_compatible(ha.x, hb.x, ha.y, hb.y, P.chi_fusion_lt)) m |= 1u << b;
             }
-            if (best_n > P.lambdaN) {
-                float pjsj = 0.f, rsj = 0.f;
-                for (unsigned rem = best_mask; rem; rem &= rem - 1) {
-                    const float2 hb = s_h[__ffs(rem) - 1][tid];
-                    fusion_accumulate(hb.x, hb.y, pjsj, rsj);
-                }
-                out_d = pjsj / rsj;
-                out_s = sqrtf(1.0f / rsj);
-                fused = true;
-            }
+            const int cnt = __popc(m);
+            if (best_n < cnt) { best_n = cnt; best_mask = m; }
         }
-        A.rs[own] = make_float2(out_d, out_s);
+        if (best_n > P.lambdaN) {
+            float pjsj = 0.f, rsj = 0.f;
+            for (unsigned rem = best_mask; rem; rem &= rem - 1) {
+                const float2 hb = s_h[__ffs(rem) - 1][tid];
+                fusion_accumulate(hb.x, hb.y, pjsj, rsj);
+            }
+            out_d = pjsj / rsj;
+            out_s = sqrtf(1.0f / rsj);
+            fused = true;
+        }
     }
-    if (stats) {
-        const unsigned bal = __ballot_sync(SDM_FULL, fused);
-        if ((threadIdx.x & 31) == 0 && bal) atomicAdd(&stats->fused, (unsigned long long)__popc(bal));
+    A.rs[own] = make_float2(out_d, out_s);
+    return fused;
+}
+
+#ifndef SDM_LANE_MINB
+#define SDM_LANE_MINB 10  // 48 registers: measured optimum on B200 (latency-bound scan; 7 -> 10 blocks/SM = -18 % time)
+#endif
+__global__ void __launch_bounds__(kLaneBlock, SDM_LANE_MINB)
+k_pass1_lane(DevArena A, DevParams P, const DevItem* __restrict__ items, DevPlan plan, DevStats* stats)
+{
+    __shared__ DevItem s_item;
+    __shared__ int s_chunk;
+    extern __shared__ float2 s_h_dyn[];  // [max n_nbr of the batch][kLaneBlock]: sized at launch, leaves the rest to L1
+    float2 (*s_h)[kLaneBlock] = reinterpret_cast<float2 (*)[kLaneBlock]>(s_h_dyn);
+    const int tid = threadIdx.x;
+    int cur_entry = -1, first = 0;
+    unsigned n_fused = 0;
+    while (next_chunk(plan, items, s_item, s_chunk, cur_entry, first)) {
+        const int ci = first + tid;
+        bool fused = false;
+        if (ci < A.cand_count[s_item.kf]) fused = scan_pixel_lane(A, P, s_item, s_h, ci, tid);
+        n_fused += __popc(__ballot_sync(SDM_FULL, fused));
     }
+    if (stats && (tid & 31) == 0 && n_fused) atomicAdd(&stats->fused, (unsigned long long)n_fused);
 }
 
 // per-pair raw hypotheses for every candidate pixel of kf1 (granularity of one EpipolarSearch call)
@@ -728,66 +872,81 @@ __global__ void __launch_bounds__(256) k_fuse_sets(DevParams P, int m, int n, co
 
 // ---------------------------------------------------------------------------------------------
 // K5: IntraKeyFrameDepthChecking (:866-927) and IntraKeyFrameDepthGrowing (:929-976): 3x3 Jacobi
-// stencils on the (rho, sigma) plane; src is a snapshot of the plane, dst the plane itself.
+// stencils on the (rho, sigma) planes of a BATCH of keyframes (grid.z = keyframe).  Each kernel reads
+// one full plane and writes one full plane (changed value or copy), so "check" goes arena -> tmp and
+// "grow" goes tmp -> arena with no snapshot copies:  src/dst plane of batch entry z is
+//   arena + slots[z] * npix   or   tmp + z * npix.
+// copy_only = 1 turns a kernel into the plain plane copy needed when only one of the two is enabled.
 // ---------------------------------------------------------------------------------------------
-
-__global__ void __launch_bounds__(256) k_intra_check(DevParams P, const float2* __restrict__ src, float2* __restrict__ dst)
+__global__ void __launch_bounds__(256)
+k_intra_check(DevParams P, const float2* __restrict__ arena, float2* __restrict__ tmp, const int* __restrict__ slots,
+              size_t npix, int copy_only)
 {
     const int px = blockIdx.x * 32 + threadIdx.x, py = blockIdx.y * 8 + threadIdx.y;
-    if (px < 2 || py < 2 || px >= P.W - 2 || py >= P.H - 2) return;
-    const float2 c = src[(size_t)py * P.W + px];
-    if (!(c.x > P.eps_gt)) return;
-    float pjsj = 0.f, rsj = 0.f, min_sigma = 0.f;
-    int n = 0;
-    for (int y = py - 1; y <= py + 1; ++y)
-        for (int x = px - 1; x <= px + 1; ++x) {
-            if (x == px && y == py) continue;
-            const float2 q = src[(size_t)y * P.W + x];
-            if (q.x > P.eps_gt && chi_compatible(q.x, c.x, q.y, c.y, P.chi_fusion_lt)) {
-                if (n == 0) min_sigma = q.y;
-                fusion_accumulate(q.x, q.y, pjsj, rsj);
-                // pow(sigma,2) < pow(min,2) in double == |sigma| < |min|
-                if ((double)q.y * (double)q.y < (double)min_sigma * (double)min_sigma) min_sigma = q.y;
-                ++n;
+    if (px >= P.W || py >= P.H) return;
+    const float2* __restrict__ src = arena + (size_t)slots[blockIdx.z] * npix;
+    float2* __restrict__ dst = tmp + (size_t)blockIdx.z * npix;
+    const size_t pi = (size_t)py * P.W + px;
+    const float2 c = src[pi];
+    float2 out = c;
+    if (!copy_only && px >= 2 && py >= 2 && px < P.W - 2 && py < P.H - 2 && c.x > P.eps_gt) {
+        float pjsj = 0.f, rsj = 0.f, min_sigma = 0.f;
+        int n = 0;
+        for (int y = py - 1; y <= py + 1; ++y)
+            for (int x = px - 1; x <= px + 1; ++x) {
+                if (x == px && y == py) continue;
+                const float2 q = src[(size_t)y * P.W + x];
+                if (q.x > P.eps_gt && chi_compatible(q.x, c.x, q.y, c.y, P.chi_fusion_lt)) {
+                    if (n == 0) min_sigma = q.y;
+                    fusion_accumulate(q.x, q.y, pjsj, rsj);
+                    // pow(sigma,2) < pow(min,2) in double == |sigma| < |min|
+                    if ((double)q.y * (double)q.y < (double)min_sigma * (double)min_sigma) min_sigma = q.y;
+                    ++n;
+                }
             }
-        }
-    if (n == 0) min_sigma = c.y;
-    fusion_accumulate(c.x, c.y, pjsj, rsj);  // "dont forget itself" :902 (pushed last)
-    if ((double)c.y * (double)c.y < (double)min_sigma * (double)min_sigma) min_sigma = c.y;
-    ++n;
-    if (n >= 3)
-        dst[(size_t)py * P.W + px] = make_float2(pjsj / rsj, min_sigma);
-    else
-        dst[(size_t)py * P.W + px] = make_float2(0.f, 0.f);
+        if (n == 0) min_sigma = c.y;
+        fusion_accumulate(c.x, c.y, pjsj, rsj);  // "dont forget itself" :902 (pushed last)
+        if ((double)c.y * (double)c.y < (double)min_sigma * (double)min_sigma) min_sigma = c.y;
+        ++n;
+        out = (n >= 3) ? make_float2(pjsj / rsj, min_sigma) : make_float2(0.f, 0.f);
+    }
+    dst[pi] = out;
 }
 
-__global__ void __launch_bounds__(256) k_intra_grow(DevParams P, const float2* __restrict__ src, float2* __restrict__ dst,
-                                                    const float4* __restrict__ tex)
+__global__ void __launch_bounds__(256)
+k_intra_grow(DevParams P, const float2* __restrict__ tmp, float2* __restrict__ arena, const float4* __restrict__ tex_arena,
+             const int* __restrict__ slots, size_t npix, int copy_only)
 {
     const int px = blockIdx.x * 32 + threadIdx.x, py = blockIdx.y * 8 + threadIdx.y;
-    if (px < 2 || py < 2 || px >= P.W - 2 || py >= P.H - 2) return;
-    const float2 c = src[(size_t)py * P.W + px];
-    if (!(c.x < P.eps_lt)) return;
-    if (tex[(size_t)py * P.W + px].x <= P.lambdaG) return;
-    float pjsj = 0.f, rsj = 0.f, min_sigma = 0.f;
-    int n = 0;
-    for (int y = py - 1; y <= py + 1; ++y)
-        for (int x = px - 1; x <= px + 1; ++x) {
-            if (x == px && y == py) continue;
-            const float2 q = src[(size_t)y * P.W + x];
-            if (chi_compatible(q.x, c.x, q.y, c.y, P.chi_fusion_lt)) {
-                if (n == 0) min_sigma = q.y;
-                fusion_accumulate(q.x, q.y, pjsj, rsj);
-                if (q.y < min_sigma) min_sigma = q.y;
-                ++n;
+    if (px >= P.W || py >= P.H) return;
+    const size_t slot = (size_t)slots[blockIdx.z];
+    const float2* __restrict__ src = tmp + (size_t)blockIdx.z * npix;
+    float2* __restrict__ dst = arena + slot * npix;
+    const size_t pi = (size_t)py * P.W + px;
+    const float2 c = src[pi];
+    float2 out = c;
+    if (!copy_only && px >= 2 && py >= 2 && px < P.W - 2 && py < P.H - 2 && c.x < P.eps_lt &&
+        !(tex_arena[slot * npix + pi].x <= P.lambdaG)) {
+        float pjsj = 0.f, rsj = 0.f, min_sigma = 0.f;
+        int n = 0;
+        for (int y = py - 1; y <= py + 1; ++y)
+            for (int x = px - 1; x <= px + 1; ++x) {
+                if (x == px && y == py) continue;
+                const float2 q = src[(size_t)y * P.W + x];
+                if (chi_compatible(q.x, c.x, q.y, c.y, P.chi_fusion_lt)) {
+                    if (n == 0) min_sigma = q.y;
+                    fusion_accumulate(q.x, q.y, pjsj, rsj);
+                    if (q.y < min_sigma) min_sigma = q.y;
+                    ++n;
+                }
             }
-        }
-    if (n >= 2) dst[(size_t)py * P.W + px] = make_float2(pjsj / rsj, min_sigma);
+        if (n >= 2) out = make_float2(pjsj / rsj, min_sigma);
+    }
+    dst[pi] = out;
 }
 
 // ---------------------------------------------------------------------------------------------
 // K6: InterKeyFrameDepthChecking (:1121-1296) fused with UpdateSemiDensePointSet (:700-731).
-// One thread per pixel; blocks of 256 consecutive pixels of one keyframe (grid.y = item).
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void write_point(const DevItem& it, const DevParams& P, float* __restrict__ pts, size_t pi,
                                             int x, int y, float checked)
@@ -807,25 +966,86 @@ __device__ __forceinline__ void write_point(const DevItem& it, const DevParams& 
     pts[3 * pi + 2] = Z;
 }
 
+// one interior pixel with rho = depthp (not < eps): :1159-1293.  Returns depth_map_checked_.
+__device__ __forceinline__ float inter_check_pixel(const DevArena& A, const DevParams& P, const DevItem& it, int px, int py,
+                                                   float depthp)
+{
+    const int cols = P.W, rows = P.H;
+    const float fx = it.K[0], fy = it.K[1], cx = it.K[2], cy = it.K[3];
+    const float xn = (px - cx) / fx, yn = (py - cy) / fy;
+    const float dp = 1.0f / depthp;
+    const double alpha = (double)(float)(1.0 / (double)depthp);  // gemm alpha is cast to float
+    int support = 0;
+    double JtR = 0.0, JtJ = 0.0;
+    const int N = it.n_nbr;
+    for (int j = 0; j < N; ++j) {
+        const DevPair& g = it.pair[j];
+        // temp = Rji*xp/depthp + tji ; Xj = K*temp ; Xj/Xj(2)
+        const float s0 = g.R[0] * xn + g.R[1] * yn + g.R[2] * 1.0f;
+        const float s1 = g.R[3] * xn + g.R[4] * yn + g.R[5] * 1.0f;
+        const float s2 = g.R[6] * xn + g.R[7] * yn + g.R[8] * 1.0f;
+        const float X0 = (float)((double)s0 * alpha + (double)g.t[0]);
+        const float X1 = (float)((double)s1 * alpha + (double)g.t[1]);
+        const float X2 = (float)((double)s2 * alpha + (double)g.t[2]);
+        const float U = fx * X0 + 0.f * X1 + cx * X2;
+        const float V = 0.f * X0 + fy * X1 + cy * X2;
+        const float Wz = 0.f * X0 + 0.f * X1 + 1.0f * X2;
+        const float iz = (float)(1.0 / (double)Wz);
+        const float xj = U * iz, yj = V * iz;
+        // Eq (12)
+        const float rz = (float)((double)g.R[6] * (double)xn + (double)g.R[7] * (double)yn + (double)g.R[8] * 1.0);
+        const float depthj = depthp / (rz + depthp * g.t[2]);
+        if (!(xj >= 0.f && xj < (float)(cols - 1) && yj >= 0.f && yj < (float)(rows - 1))) continue;
+        const int x0 = (int)floorf(xj), y0 = (int)floorf(yj);
+        const float2* nrs = A.rs + (size_t)g.slot * A.P;
+        const float2 q00 = __ldg(&nrs[(size_t)y0 * cols + x0]);
+        const float2 q10 = __ldg(&nrs[(size_t)(y0 + 1) * cols + x0]);
+        const float2 q01 = __ldg(&nrs[(size_t)y0 * cols + x0 + 1]);
+        const float2 q11 = __ldg(&nrs[(size_t)(y0 + 1) * cols + x0 + 1]);
+        const float2 q[4] = {q00, q10, q01, q11};  // (y0,x0) (y1,x0) (y0,x1) (y1,x1)
+        int nj = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float d = q[k].x, sg = q[k].y;
+            if (d > P.eps_gt) {
+                const double dd = (double)(depthj - d);
+                const float test = (float)((dd * dd) / ((double)sg * (double)sg));
+                if (test < P.chi_inter_lt) {
+                    ++nj;
+                    // Gauss-Newton terms (:1274-1280), accumulated in the reference's order
+                    const float djn = 1.0f / d;
+                    const float d2sigma = djn * djn * sg;
+                    const float Ji = -rz / d2sigma;
+                    const float ri = (djn - dp * rz - g.t[2]) / d2sigma;
+                    JtR += (double)Ji * (double)ri;
+                    JtJ += (double)Ji * (double)Ji;
+                }
+            }
+        }
+        if (nj >= 1) ++support;
+    }
+    if (support < P.lambdaN) return 0.f;
+    const float Jtr0 = (float)(JtR * -1.0);
+    const float JtJf = (float)(JtJ * 1.0);
+    const float dpDelta = Jtr0 / JtJf;
+    return 1.0f / (dp + dpDelta);
+}
+
+// dense variant: one thread per pixel of the plane (grid.y = item).  Used for keyframes whose (rho,sigma)
+// plane did not come from pass 1 (sdm_upload_depth, external receives) and for points_only.
 __global__ void __launch_bounds__(256)
-k_pass2(DevArena A, DevParams P, const DevItem* __restrict__ items, DevStats* stats, int points_only)
+k_pass2(DevArena A, DevParams P, const DevItem* __restrict__ items, const int* __restrict__ order, DevStats* stats,
+        int points_only)
 {
     __shared__ DevItem s_item;
-    {
-        const int* src = reinterpret_cast<const int*>(&items[blockIdx.y]);
-        int* dst = reinterpret_cast<int*>(&s_item);
-        const int header = (int)(offsetof(DevItem, pair) / 4);
-        const int words = header + items[blockIdx.y].n_nbr * (int)(sizeof(DevPair) / 4);
-        for (int i = threadIdx.x; i < words; i += blockDim.x) dst[i] = src[i];
-    }
+    load_item(s_item, &items[order ? order[blockIdx.y] : blockIdx.y]);
     __syncthreads();
     const size_t p = (size_t)blockIdx.x * 256 + threadIdx.x;
     if (p >= A.P) return;
     const int py = (int)(p / P.W), px = (int)(p % P.W);
     const int kf = s_item.kf;
     const size_t base = (size_t)kf * A.P;
-    const int cols = P.W, rows = P.H;
-    const bool interior = (px >= 2 && py >= 2 && px < cols - 2 && py < rows - 2);
+    const bool interior = (px >= 2 && py >= 2 && px < P.W - 2 && py < P.H - 2);
     if (points_only) {
         if (interior) write_point(s_item, P, A.pts + 3 * base, p, px, py, A.chk[base + p]);
         return;
@@ -833,67 +1053,7 @@ k_pass2(DevArena A, DevParams P, const DevItem* __restrict__ items, DevStats* st
     float checked = 0.f;
     if (interior) {
         const float depthp = A.rs[base + p].x;
-        if (!(depthp < P.eps_lt)) {
-            const float fx = s_item.K[0], fy = s_item.K[1], cx = s_item.K[2], cy = s_item.K[3];
-            const float xn = (px - cx) / fx, yn = (py - cy) / fy;
-            const float dp = 1.0f / depthp;
-            const double alpha = (double)(float)(1.0 / (double)depthp);  // gemm alpha is cast to float
-            int support = 0;
-            double JtR = 0.0, JtJ = 0.0;
-            const int N = s_item.n_nbr;
-            for (int j = 0; j < N; ++j) {
-                const DevPair& g = s_item.pair[j];
-                // temp = Rji*xp/depthp + tji ; Xj = K*temp ; Xj/Xj(2)
-                const float s0 = g.R[0] * xn + g.R[1] * yn + g.R[2] * 1.0f;
-                const float s1 = g.R[3] * xn + g.R[4] * yn + g.R[5] * 1.0f;
-                const float s2 = g.R[6] * xn + g.R[7] * yn + g.R[8] * 1.0f;
-                const float X0 = (float)((double)s0 * alpha + (double)g.t[0]);
-                const float X1 = (float)((double)s1 * alpha + (double)g.t[1]);
-                const float X2 = (float)((double)s2 * alpha + (double)g.t[2]);
-                const float U = fx * X0 + 0.f * X1 + cx * X2;
-                const float V = 0.f * X0 + fy * X1 + cy * X2;
-                const float Wz = 0.f * X0 + 0.f * X1 + 1.0f * X2;
-                const float iz = (float)(1.0 / (double)Wz);
-                const float xj = U * iz, yj = V * iz;
-                // Eq (12)
-                const float rz = (float)((double)g.R[6] * (double)xn + (double)g.R[7] * (double)yn + (double)g.R[8] * 1.0);
-                const float depthj = depthp / (rz + depthp * g.t[2]);
-                if (!(xj >= 0.f && xj < (float)(cols - 1) && yj >= 0.f && yj < (float)(rows - 1))) continue;
-                const int x0 = (int)floorf(xj), y0 = (int)floorf(yj);
-                const float2* nrs = A.rs + (size_t)g.slot * A.P;
-                const float2 q00 = __ldg(&nrs[(size_t)y0 * cols + x0]);
-                const float2 q10 = __ldg(&nrs[(size_t)(y0 + 1) * cols + x0]);
-                const float2 q01 = __ldg(&nrs[(size_t)y0 * cols + x0 + 1]);
-                const float2 q11 = __ldg(&nrs[(size_t)(y0 + 1) * cols + x0 + 1]);
-                const float2 q[4] = {q00, q10, q01, q11};  // (y0,x0) (y1,x0) (y0,x1) (y1,x1)
-                int nj = 0;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float d = q[k].x, sg = q[k].y;
-                    if (d > P.eps_gt) {
-                        const double dd = (double)(depthj - d);
-                        const float test = (float)((dd * dd) / ((double)sg * (double)sg));
-                        if (test < P.chi_inter_lt) {
-                            ++nj;
-                            // Gauss-Newton terms (:1274-1280), accumulated in the reference's order
-                            const float djn = 1.0f / d;
-                            const float d2sigma = djn * djn * sg;
-                            const float Ji = -rz / d2sigma;
-                            const float ri = (djn - dp * rz - g.t[2]) / d2sigma;
-                            JtR += (double)Ji * (double)ri;
-                            JtJ += (double)Ji * (double)Ji;
-                        }
-                    }
-                }
-                if (nj >= 1) ++support;
-            }
-            if (support >= P.lambdaN) {
-                const float Jtr0 = (float)(JtR * -1.0);
-                const float JtJf = (float)(JtJ * 1.0);
-                const float dpDelta = Jtr0 / JtJf;
-                checked = 1.0f / (dp + dpDelta);
-            }
-        }
+        if (!(depthp < P.eps_lt)) checked = inter_check_pixel(A, P, s_item, px, py, depthp);
     }
     A.chk[base + p] = checked;
     write_point(s_item, P, A.pts + 3 * base, p, px, py, interior ? checked : 0.f);
@@ -901,6 +1061,37 @@ k_pass2(DevArena A, DevParams P, const DevItem* __restrict__ items, DevStats* st
         const unsigned bal = __ballot_sync(__activemask(), checked > 0.f);
         if ((threadIdx.x & 31) == 0 && bal) atomicAdd(&stats->checked, (unsigned long long)__popc(bal));
     }
+}
+
+// candidate-list variant (the default): pass 1 writes (rho,sigma) only at candidate pixels and k_pack zeroes
+// chk / pts of the whole plane, so pass 2 only has to visit the compacted candidates: one thread per
+// candidate, kLaneBlock candidates of one keyframe per block (same block -> item map as pass 1).
+__global__ void __launch_bounds__(kLaneBlock)
+k_pass2_cand(DevArena A, DevParams P, const DevItem* __restrict__ items, DevPlan plan, DevStats* stats)
+{
+    __shared__ DevItem s_item;
+    __shared__ int s_chunk;
+    int cur_entry = -1, first = 0;
+    unsigned n_checked = 0;
+    while (next_chunk(plan, items, s_item, s_chunk, cur_entry, first)) {
+        const int ci = first + threadIdx.x;
+        const int kf = s_item.kf;
+        float checked = 0.f;
+        if (ci < A.cand_count[kf]) {
+            const size_t base = (size_t)kf * A.P;
+            const uint32_t packed = A.cand[base + ci];
+            const int px = (int)(packed & 0xffffu), py = (int)(packed >> 16);
+            if (px >= 2 && py >= 2 && px < P.W - 2 && py < P.H - 2) {
+                const size_t p = (size_t)py * P.W + px;
+                const float depthp = A.rs[base + p].x;
+                if (!(depthp < P.eps_lt)) checked = inter_check_pixel(A, P, s_item, px, py, depthp);
+                A.chk[base + p] = checked;
+                write_point(s_item, P, A.pts + 3 * base, p, px, py, checked);
+            }
+        }
+        n_checked += __popc(__ballot_sync(SDM_FULL, checked > 0.f));
+    }
+    if (stats && (threadIdx.x & 31) == 0 && n_checked) atomicAdd(&stats->checked, (unsigned long long)n_checked);
 }
 
 // (rho, sigma) float2 plane -> two dense float planes (download staging), and back

@@ -12,7 +12,7 @@ import numpy as np
 
 SDM_MAX_NBR = 16
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.normpath(os.path.join(_HERE, "..", "..", "lib", "libsdm_b200.so"))
+LIB_PATH = os.environ.get("SDM_LIB") or os.path.normpath(os.path.join(_HERE, "..", "..", "lib", "libsdm_b200.so"))
 
 
 class SdmError(RuntimeError):
@@ -59,7 +59,7 @@ class Stats(C.Structure):
 EXPORTS = [
     "sdm_default_config", "sdm_create", "sdm_destroy", "sdm_last_error", "sdm_version", "sdm_synchronize",
     "sdm_get_stats", "sdm_host_alloc", "sdm_host_free", "sdm_upload_keyframe", "sdm_set_pose",
-    "sdm_set_intrinsics", "sdm_candidate_count", "sdm_pass1", "sdm_pass2", "sdm_update_points", "sdm_download",
+    "sdm_set_intrinsics", "sdm_candidate_count", "sdm_pass1", "sdm_pass2", "sdm_update_points", "sdm_download", "sdm_download_async",
     "sdm_upload_depth", "sdm_depth_plane_ptr", "sdm_export_arena", "sdm_import_peer_arena", "sdm_pull_halo",
     "sdm_mark_pass1_done", "sdm_pair_geometry", "sdm_stereo_search_constraints", "sdm_search_range",
     "sdm_epipolar_search", "sdm_epipolar_search_plane", "sdm_fuse", "sdm_intra_check", "sdm_intra_grow",
@@ -98,6 +98,7 @@ def load() -> C.CDLL:
     lib.sdm_pass2.argtypes = [vp, C.c_int, C.POINTER(Item)]
     lib.sdm_update_points.argtypes = [vp, C.c_int, ip]
     lib.sdm_download.argtypes = [vp, C.c_int, vp, sz, vp, sz, vp, sz, vp, sz]
+    lib.sdm_download_async.argtypes = [vp, C.c_int, vp, sz, vp, sz, vp, sz, vp, sz]
     lib.sdm_upload_depth.argtypes = [vp, C.c_int, vp, sz, vp, sz]
     lib.sdm_depth_plane_ptr.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(sz)]
     lib.sdm_export_arena.argtypes = [vp, vp, C.POINTER(sz)]
@@ -238,7 +239,8 @@ class Context:
     def synchronize(self):
         self._chk(self.lib.sdm_synchronize(self.h))
 
-    def download(self, slot, depth=True, sigma=True, checked=True, points=True, out=None):
+    def download(self, slot, depth=True, sigma=True, checked=True, points=True, out=None, async_=False):
+        """async_=True only enqueues the copies: the arrays are valid after synchronize()."""
         H, W = self.H, self.W
         out = out or {}
         res = {}
@@ -253,7 +255,8 @@ class Context:
             return a
         d, s = buf("depth", depth, (H, W)), buf("sigma", sigma, (H, W))
         c, p = buf("checked", checked, (H, W)), buf("points", points, (H, W, 3))
-        self._chk(self.lib.sdm_download(
+        fn = self.lib.sdm_download_async if async_ else self.lib.sdm_download
+        self._chk(fn(
             self.h, slot,
             d.ctypes.data if d is not None else None, d.strides[0] if d is not None else 0,
             s.ctypes.data if s is not None else None, s.strides[0] if s is not None else 0,

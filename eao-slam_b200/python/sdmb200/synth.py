@@ -72,17 +72,23 @@ def _fast_atan2_deg(y: np.ndarray, x: np.ndarray) -> np.ndarray:
 
 
 def gradient_planes(im: np.ndarray):
-    """GradImg, GradTheta of one u8 image: Scharr(scale 1/32) -> magnitude / phase(degrees)."""
+    """GradImg, GradTheta of one u8 image: Scharr(scale 1/32) -> magnitude / phase(degrees) (KeyFrame.cc:69-74).
+
+    Scharr/32 is exact (integer sums times 2^-5), so cv2 and the numpy form agree bit for bit.  magnitude and
+    phase are evaluated with numpy (float32 sqrt; the scalar form of cv::fastAtan2): cv2.magnitude was observed
+    to return results that differ in the last bit BETWEEN CALLS on a 24-thread host (SIMD body vs scalar tail of
+    OpenCV's parallel stripes), which would make two ranks disagree about the planes of a shared keyframe.  The
+    planes are inputs of the path, so either producer is equally valid."""
     if cv2 is not None:
         gx = cv2.Scharr(im, cv2.CV_32F, 1, 0, scale=1 / 32.0)
         gy = cv2.Scharr(im, cv2.CV_32F, 0, 1, scale=1 / 32.0)
-        return cv2.magnitude(gx, gy), cv2.phase(gx, gy, angleInDegrees=True)
-    p = np.pad(im.astype(np.int32), 1, mode="reflect")  # BORDER_REFLECT_101
-    gx = (3 * (p[:-2, 2:] - p[:-2, :-2]) + 10 * (p[1:-1, 2:] - p[1:-1, :-2]) + 3 * (p[2:, 2:] - p[2:, :-2]))
-    gy = (3 * (p[2:, :-2] - p[:-2, :-2]) + 10 * (p[2:, 1:-1] - p[:-2, 1:-1]) + 3 * (p[2:, 2:] - p[:-2, 2:]))
-    gx = (gx / 32.0).astype(np.float32)
-    gy = (gy / 32.0).astype(np.float32)
-    return np.sqrt(gx * gx + gy * gy).astype(np.float32), _fast_atan2_deg(gy, gx)
+    else:
+        p = np.pad(im.astype(np.int32), 1, mode="reflect")  # BORDER_REFLECT_101
+        gx = (3 * (p[:-2, 2:] - p[:-2, :-2]) + 10 * (p[1:-1, 2:] - p[1:-1, :-2]) + 3 * (p[2:, 2:] - p[2:, :-2]))
+        gy = (3 * (p[2:, :-2] - p[:-2, :-2]) + 10 * (p[2:, 1:-1] - p[:-2, 1:-1]) + 3 * (p[2:, 2:] - p[:-2, 2:]))
+        gx = (gx / 32.0).astype(np.float32)
+        gy = (gy / 32.0).astype(np.float32)
+    return np.sqrt(gx * gx + gy * gy, dtype=np.float32), _fast_atan2_deg(gy, gx)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -137,6 +137,12 @@ int sdm_update_points(sdm_ctx* ctx, int n, const int32_t* kfs);
 int sdm_download(sdm_ctx* ctx, int kf,
                  float* depth, size_t depth_step, float* sigma, size_t sigma_step,
                  float* checked, size_t checked_step, float* points, size_t points_step);
+/* same, but only enqueued (on the library's download stream, ordered after the last pass that wrote the
+ * slot): the host buffers are valid after the next sdm_synchronize.  Lets a caller overlap the D2H of one
+ * chunk of keyframes with the passes of the next (pinned buffers from sdm_host_alloc recommended). */
+int sdm_download_async(sdm_ctx* ctx, int kf,
+                       float* depth, size_t depth_step, float* sigma, size_t sigma_step,
+                       float* checked, size_t checked_step, float* points, size_t points_step);
 /* writes pass-1 planes of a keyframe (used to seed halo keyframes / tests); blocking */
 int sdm_upload_depth(sdm_ctx* ctx, int kf, const float* depth, size_t depth_step,
                      const float* sigma, size_t sigma_step);
