@@ -296,41 +296,49 @@ def main_ours(a, rank, world, local_rank):
     chunk_need = [max(ch[-1], max(int(v) for s in ch for v in sc.nbr_idx[s])) for ch in chunks]
     halo_set = set(int(v) for v in plan.halo_local)
     needs_halo = [any(int(v) in halo_set for s in ch for v in sc.nbr_idx[s]) for ch in chunks]
-    Kf = np.ascontiguousarray(np.asarray(sc.K, np.float32)); keep.append(Kf)
-    Tf = np.ascontiguousarray(sc.Tcw.reshape(n_loc, 12).astype(np.float32)); keep.append(Tf)
-    fp = C.POINTER(C.c_float)
-    up_args = [(ctx.h, s, sc.im[s].ctypes.data, W, sc.grad[s].ctypes.data, 4 * W, sc.theta[s].ctypes.data, 4 * W, None, 0,
-                Kf.ctypes.data_as(fp), Tf[s].ctypes.data_as(fp)) for s in range(n_loc)]
+    # one sdm_upload_desc / sdm_download_desc per keyframe, built once; a chunk is a slice of these arrays
+    up_desc = ctx.upload_descs(sc, range(n_loc))
     o0 = owned[0]
-    dl1_args = {s: (ctx.h, s, out["depth"][s - o0].ctypes.data, 4 * W, out["sigma"][s - o0].ctypes.data, 4 * W, None, 0, None, 0)
-                for s in owned}
-    dl2_args = {s: (ctx.h, s, None, 0, None, 0, out["checked"][s - o0].ctypes.data, 4 * W, out["points"][s - o0].ctypes.data, 12 * W)
-                for s in owned}
+    dl1 = (api.DownloadDesc * len(owned))()   # depth_map_, depth_sigma_   (after pass 1)
+    dl2 = (api.DownloadDesc * len(owned))()   # depth_map_checked_, SemiDensePointSets_   (after pass 2)
+    for j, s in enumerate(owned):
+        dl1[j].kf = dl2[j].kf = s
+        dl1[j].depth, dl1[j].depth_step = out["depth"][j].ctypes.data, 4 * W
+        dl1[j].sigma, dl1[j].sigma_step = out["sigma"][j].ctypes.data, 4 * W
+        dl2[j].checked, dl2[j].checked_step = out["checked"][j].ctypes.data, 4 * W
+        dl2[j].points, dl2[j].points_step = out["points"][j].ctypes.data, 12 * W
+    up_sz, dl_sz = C.sizeof(api.UploadDesc), C.sizeof(api.DownloadDesc)
+    up_ptr = lambda i: C.cast(C.byref(up_desc, i * up_sz), C.POINTER(api.UploadDesc))
+    dl_ptr = lambda arr, ch: C.cast(C.byref(arr, (ch[0] - o0) * dl_sz), C.POINTER(api.DownloadDesc))
     chk = ctx._chk
 
+    t_e2e = [0.0]
+
     def e2e_step():
+        t_e2e[0] = time.perf_counter()
         nxt, deferred = 0, []
         for k in range(len(chunks)):
-            while nxt <= chunk_need[k]:
-                chk(lib.sdm_upload_keyframe(*up_args[nxt])); nxt += 1
+            if nxt <= chunk_need[k]:
+                chk(lib.sdm_upload_keyframes(ctx.h, chunk_need[k] + 1 - nxt, up_ptr(nxt))); nxt = chunk_need[k] + 1
             chk(lib.sdm_pass1(ctx.h, len(chunk_items[k]), chunk_items[k]))
-            for s in chunks[k]:
-                chk(lib.sdm_download_async(*dl1_args[s]))
+            chk(lib.sdm_download_keyframes(ctx.h, len(chunks[k]), dl_ptr(dl1, chunks[k])))
             if k >= 1:
                 if needs_halo[k - 1]:
                     deferred.append(k - 1)
                 else:
                     chk(lib.sdm_pass2(ctx.h, len(chunk_items[k - 1]), chunk_items[k - 1]))
-                    for s in chunks[k - 1]:
-                        chk(lib.sdm_download_async(*dl2_args[s]))
-        while nxt < n_loc:
-            chk(lib.sdm_upload_keyframe(*up_args[nxt])); nxt += 1
+                    chk(lib.sdm_download_keyframes(ctx.h, len(chunks[k - 1]), dl_ptr(dl2, chunks[k - 1])))
+        if nxt < n_loc:
+            chk(lib.sdm_upload_keyframes(ctx.h, n_loc - nxt, up_ptr(nxt)))
         exchange()
         for k in deferred + [len(chunks) - 1]:
             chk(lib.sdm_pass2(ctx.h, len(chunk_items[k]), chunk_items[k]))
-            for s in chunks[k]:
-                chk(lib.sdm_download_async(*dl2_args[s]))
+            chk(lib.sdm_download_keyframes(ctx.h, len(chunks[k]), dl_ptr(dl2, chunks[k])))
+        if dbg:
+            t_issue = time.perf_counter()
         ctx.synchronize()
+        if dbg:
+            print(f"e2e issue {1e3 * (t_issue - t_e2e[0]):.2f} ms, total {1e3 * (time.perf_counter() - t_e2e[0]):.2f} ms", file=sys.stderr)
         if world > 1:
             barrier()
 
@@ -405,7 +413,7 @@ def main_ours(a, rank, world, local_rank):
     if e2e:
         line["e2e"] = {"value": tot_cands / e2e_max, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
                        "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": 1e3 * e2e_max,
-                       "api": "sdm_upload_keyframe / sdm_pass1 / sdm_pass2 / sdm_download on pinned host planes"}
+                       "api": "sdm_upload_keyframes / sdm_pass1 / sdm_pass2 / sdm_download_keyframes on pinned host planes, chunks of 20 keyframes"}
     ctx.close()
     if world == 1 and not a.no_cpu_baseline:
         r = cpu_run(a.cpu_sample_kf, a.nbr, a.seed, a.intra, 1, 0)

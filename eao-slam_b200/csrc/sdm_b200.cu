@@ -5,12 +5,13 @@
 // pulls.  Replaces the CPU loops of yanmin-wu/EAO-SLAM src/ProbabilityMapping.cc:348-597.
 // No CPU fallback: every entry point that computes needs a CUDA device.
 //
-// Streams: uploads (H2D + k_pack) on s_copy, the passes on s_compute, downloads (k_split_rs + D2H) on
-// s_down.  Ordering between them is tracked per keyframe slot with event ids (see EventRing): an
-// upload waits for the last pass / download that touched its slot, a pass waits for the uploads of
-// every slot it references and for downloads of the slots it overwrites, a download waits for the
-// last pass on its slot.  Nothing on these paths blocks the host, so a caller can keep all three
-// streams busy by issuing upload / pass / download calls on chunks of keyframes (bench.py e2e).
+// Streams: H2D copies on s_copy (into a ring of staging sets), every kernel — k_pack, the passes — on
+// s_compute, D2H copies on s_down.  The two copy streams carry DMA only, so they never compete with the
+// persistent pass kernels for SM slots.  Ordering is tracked per keyframe slot with event ids (see
+// EventRing): k_pack waits for its staging set's H2D and for downloads still reading the slot, a pass
+// waits for downloads of the planes it overwrites, a download waits for the last kernel on its slot.
+// Nothing on these paths blocks the host, so a caller keeps all three engines busy by issuing
+// upload / pass / download calls on chunks of keyframes (bench.py e2e).
 //
 // Build: nvcc -std=c++17 -O3 -gencode arch=compute_100a,code=sm_100a -lineinfo -fmad=false
 //        -Xcompiler -fPIC,-ffp-contract=off -shared   (see __graft_entry__.build()).
@@ -56,9 +57,9 @@ int fail(int code, const char* fmt, ...)
         if (rc_ != SDM_OK) return rc_; \
     } while (0)
 
-constexpr int kUpStages = 6;    // upload staging sets (im, grad, theta, edge)
+constexpr int kUpStages = 48;   // upload staging sets (im, grad, theta, edge): H2D runs this far ahead of k_pack
 constexpr int kDownStages = 6;  // (rho | sigma) split staging sets
-constexpr int kItemStages = 4;  // pinned work-order staging buffers
+constexpr int kItemStages = 32;  // pinned work-order staging buffers (how many passes the host may run ahead)
 constexpr int kMaxPeers = 16;
 constexpr int kIntraChunk = 64;  // keyframes per batched intra launch (bounds the tmp arena)
 
@@ -106,9 +107,12 @@ struct KfState {
     bool uploaded = false;
     bool pass1_done = false;
     bool rs_dense = false;  // (rho,sigma) plane did not come from pass 1: pass 2 must visit every pixel
+    bool split_stale = false;  // dpl / spl do not mirror rs (external write): downloads de-interleave rs instead
     float K[4] = {0, 0, 0, 0};
     float Tcw[12] = {0};
-    uint64_t up_id = 0, comp_id = 0, down_id = 0;  // last upload / pass / download touching the slot
+    uint64_t comp_id = 0;     // last kernel (k_pack, pass, pull) touching the slot
+    uint64_t down_ds_id = 0;  // last download of depth_map_ / depth_sigma_ (pass 1 and the intra stencils overwrite them)
+    uint64_t down_cp_id = 0;  // last download of depth_map_checked_ / points (pass 2 overwrites them)
 };
 
 struct UpStage {
@@ -116,7 +120,7 @@ struct UpStage {
     float* grad = nullptr;
     float* theta = nullptr;
     int32_t* edge = nullptr;
-    uint64_t busy = 0;  // copy-ring id of the k_pack that reads it
+    uint64_t busy = 0;  // compute-ring id of the k_pack that reads it
 };
 struct DownStage {
     float* planes = nullptr;  // 2 * P floats
@@ -278,19 +282,16 @@ int prepare_batch(sdm_ctx* c, int n, const sdm_item* items, bool pass2, bool poi
     int* h_slots = h_aux;
     int* h_sparse = h_aux + n;
     int* h_dense = h_aux + 2 * n;
-    uint64_t need_up = 0, need_down = 0;
+    uint64_t need_down = 0;
     b->n = n;
     for (int i = 0; i < n; ++i) {
         RC(build_item(c, items[i], h_items[i], pass2, points_only));
         const KfState& k1 = c->kf[items[i].kf];
         h_slots[i] = items[i].kf;
         if (pass2 && (k1.rs_dense || points_only)) h_dense[b->n_dense++] = i; else h_sparse[b->n_sparse++] = i;
-        need_up = std::max(need_up, k1.up_id);
-        need_down = std::max(need_down, k1.down_id);  // the pass overwrites this slot's output planes
-        for (int j = 0; j < items[i].n_nbr; ++j) need_up = std::max(need_up, c->kf[items[i].nbr[j]].up_id);
+        need_down = std::max(need_down, pass2 ? k1.down_cp_id : k1.down_ds_id);  // planes this pass overwrites
     }
-    RC(c->r_copy.wait(c->s_compute, need_up));
-    RC(c->r_down.wait(c->s_compute, need_down));
+    RC(c->r_down.wait(c->s_compute, need_down));  // (uploads need no wait: k_pack runs on s_compute itself)
     CU(cudaMemcpyAsync(c->d_items, h_items, sizeof(sdm::DevItem) * n, cudaMemcpyHostToDevice, c->s_compute));
     CU(cudaMemcpyAsync(c->d_aux, h_aux, sizeof(int) * 3 * n, cudaMemcpyHostToDevice, c->s_compute));
     RC(c->r_compute.record(c->s_compute, &st->busy));
@@ -340,8 +341,8 @@ int run_intra(sdm_ctx* c, const int* d_slots, int n, bool check, bool grow)
         const int m = std::min(c->tmp_planes, n - i0);
         sdm::k_intra_check<<<tile_grid(c, m), dim3(32, 8), 0, c->s_compute>>>(c->P, c->A.rs, c->tmp_rs, d_slots + i0, c->npix,
                                                                               check ? 0 : 1);
-        sdm::k_intra_grow<<<tile_grid(c, m), dim3(32, 8), 0, c->s_compute>>>(c->P, c->tmp_rs, c->A.rs, c->A.tex, d_slots + i0,
-                                                                             c->npix, grow ? 0 : 1);
+        sdm::k_intra_grow<<<tile_grid(c, m), dim3(32, 8), 0, c->s_compute>>>(c->P, c->tmp_rs, c->A.rs, c->A.dpl, c->A.spl, c->A.tex,
+                                                                             d_slots + i0, c->npix, grow ? 0 : 1);
         c->launches += 2;
     }
     CU(cudaGetLastError());
@@ -399,7 +400,7 @@ void sdm_destroy(sdm_ctx* c)
     for (int i = 0; i < kMaxPeers; ++i)
         if (c->peer_rs[i]) cudaIpcCloseMemHandle(c->peer_rs[i]);
     cudaFree(c->A.tex); cudaFree(c->A.ipair); cudaFree(c->A.cand); cudaFree(c->A.cand_count);
-    cudaFree(c->A.rs); cudaFree(c->A.chk); cudaFree(c->A.pts);
+    cudaFree(c->A.rs); cudaFree(c->A.chk); cudaFree(c->A.pts); cudaFree(c->A.dpl); cudaFree(c->A.spl);
     for (auto& s : c->up) { cudaFree(s.im); cudaFree(s.grad); cudaFree(s.theta); cudaFree(s.edge); }
     for (auto& s : c->down) cudaFree(s.planes);
     for (auto& s : c->ist)
@@ -472,6 +473,10 @@ static int create_impl(sdm_ctx* c)
     CU(cudaMalloc(&A.rs, n * P * sizeof(float2)));
     CU(cudaMalloc(&A.chk, n * P * sizeof(float)));
     CU(cudaMalloc(&A.pts, n * P * 3 * sizeof(float)));
+    CU(cudaMalloc(&A.dpl, n * P * sizeof(float)));
+    CU(cudaMalloc(&A.spl, n * P * sizeof(float)));
+    CU(cudaMemsetAsync(A.dpl, 0, n * P * sizeof(float), c->s_compute));
+    CU(cudaMemsetAsync(A.spl, 0, n * P * sizeof(float), c->s_compute));
     CU(cudaMemsetAsync(A.cand_count, 0, n * sizeof(int), c->s_compute));
     CU(cudaMemsetAsync(A.rs, 0, n * P * sizeof(float2), c->s_compute));
     CU(cudaMemsetAsync(A.chk, 0, n * P * sizeof(float), c->s_compute));
@@ -557,40 +562,81 @@ int sdm_host_free(void* ptr)
 }
 
 // ---- keyframe planes -----------------------------------------------------------------------------
+int sdm_upload_keyframes(sdm_ctx* c, int n, const sdm_upload_desc* d)
+{
+    if (!c || (n > 0 && !d)) return fail(SDM_ERR_ARG, "sdm_upload_keyframes: null argument");
+    const int W = c->cfg.width, H = c->cfg.height;
+    const size_t row = (size_t)W * 4;
+    for (int i = 0; i < n; ++i) {
+        if (!d[i].im || !d[i].grad || !d[i].theta) return fail(SDM_ERR_ARG, "sdm_upload_keyframes: null plane in entry %d", i);
+        if (!slot_ok(c, d[i].kf)) return fail(SDM_ERR_ARG, "keyframe slot %d out of range [0,%d)", d[i].kf, (int)c->kf.size());
+        if (d[i].im_step < (size_t)W || d[i].grad_step < row || d[i].theta_step < row || (d[i].edge && d[i].edge_step < row))
+            return fail(SDM_ERR_ARG, "row step smaller than a row");
+    }
+    CU(cudaSetDevice(c->cfg.device));
+    for (int i0 = 0; i0 < n; i0 += kUpStages / 2) {
+        const int m = std::min(kUpStages / 2, n - i0);
+        const int first_stage = c->up_next;
+        // H2D on the copy stream as soon as the staging sets are free (the k_packs that last read them have run) ...
+        uint64_t busy = 0, need_down = 0;
+        for (int i = 0; i < m; ++i) busy = std::max(busy, c->up[(first_stage + i) % kUpStages].busy);
+        RC(c->r_compute.wait(c->s_copy, busy));
+        for (int i = 0; i < m; ++i) {
+            const sdm_upload_desc& u = d[i0 + i];
+            UpStage& st = c->up[(first_stage + i) % kUpStages];
+            RC(copy2d(st.im, W, u.im, u.im_step, W, H, cudaMemcpyHostToDevice, c->s_copy));
+            RC(copy2d(st.grad, row, u.grad, u.grad_step, row, H, cudaMemcpyHostToDevice, c->s_copy));
+            RC(copy2d(st.theta, row, u.theta, u.theta_step, row, H, cudaMemcpyHostToDevice, c->s_copy));
+            if (u.edge) RC(copy2d(st.edge, row, u.edge, u.edge_step, row, H, cudaMemcpyHostToDevice, c->s_copy));
+            need_down = std::max(need_down, std::max(c->kf[u.kf].down_ds_id, c->kf[u.kf].down_cp_id));
+        }
+        uint64_t h2d = 0;
+        RC(c->r_copy.record(c->s_copy, &h2d));
+        // ... packing + candidate compaction on the compute stream, behind every pass already queued on the slots
+        RC(c->r_copy.wait(c->s_compute, h2d));
+        RC(c->r_down.wait(c->s_compute, need_down));
+        for (int i = 0; i < m; ++i) {
+            const sdm_upload_desc& u = d[i0 + i];
+            UpStage& st = c->up[(first_stage + i) % kUpStages];
+            CU(cudaMemsetAsync(c->A.cand_count + u.kf, 0, sizeof(int), c->s_compute));
+            sdm::k_pack<<<tile_grid(c), dim3(32, 8), 0, c->s_compute>>>(c->A, c->P, u.kf, st.im, st.grad, st.theta,
+                                                                       u.edge ? st.edge : nullptr);
+        }
+        CU(cudaGetLastError());
+        c->launches += m;
+        uint64_t id = 0;
+        RC(c->r_compute.record(c->s_compute, &id));
+        for (int i = 0; i < m; ++i) {
+            const sdm_upload_desc& u = d[i0 + i];
+            c->up[(first_stage + i) % kUpStages].busy = id;
+            KfState& k = c->kf[u.kf];
+            k.comp_id = id;
+            k.uploaded = true;
+            k.pass1_done = false;
+            k.rs_dense = false;
+            k.split_stale = false;
+            memcpy(k.K, u.K, sizeof(k.K));
+            memcpy(k.Tcw, u.Tcw, sizeof(k.Tcw));
+        }
+        c->up_next = (first_stage + m) % kUpStages;
+    }
+    return SDM_OK;
+}
+
 int sdm_upload_keyframe(sdm_ctx* c, int kf, const uint8_t* im, size_t im_step, const float* grad, size_t grad_step,
                         const float* theta, size_t theta_step, const int32_t* edge, size_t edge_step, const float K[4],
                         const float Tcw[12])
 {
     if (!c || !im || !grad || !theta || !K || !Tcw) return fail(SDM_ERR_ARG, "sdm_upload_keyframe: null argument");
-    if (!slot_ok(c, kf)) return fail(SDM_ERR_ARG, "keyframe slot %d out of range [0,%d)", kf, (int)c->kf.size());
-    const int W = c->cfg.width, H = c->cfg.height;
-    if (im_step < (size_t)W || grad_step < (size_t)W * 4 || theta_step < (size_t)W * 4 || (edge && edge_step < (size_t)W * 4))
-        return fail(SDM_ERR_ARG, "row step smaller than a row");
-    CU(cudaSetDevice(c->cfg.device));
-    KfState& k = c->kf[kf];
-    UpStage& st = c->up[c->up_next];
-    c->up_next = (c->up_next + 1) % kUpStages;
-    // the staging set is free once the k_pack that read it has run (same stream: ordering is implicit);
-    // the slot's planes may still be read by a queued pass or download
-    RC(c->r_compute.wait(c->s_copy, k.comp_id));
-    RC(c->r_down.wait(c->s_copy, k.down_id));
-    RC(copy2d(st.im, W, im, im_step, W, H, cudaMemcpyHostToDevice, c->s_copy));
-    RC(copy2d(st.grad, (size_t)W * 4, grad, grad_step, (size_t)W * 4, H, cudaMemcpyHostToDevice, c->s_copy));
-    RC(copy2d(st.theta, (size_t)W * 4, theta, theta_step, (size_t)W * 4, H, cudaMemcpyHostToDevice, c->s_copy));
-    if (edge)
-        RC(copy2d(st.edge, (size_t)W * 4, edge, edge_step, (size_t)W * 4, H, cudaMemcpyHostToDevice, c->s_copy));
-    CU(cudaMemsetAsync(c->A.cand_count + kf, 0, sizeof(int), c->s_copy));
-    sdm::k_pack<<<tile_grid(c), dim3(32, 8), 0, c->s_copy>>>(c->A, c->P, kf, st.im, st.grad, st.theta, edge ? st.edge : nullptr);
-    CU(cudaGetLastError());
-    c->launches++;
-    RC(c->r_copy.record(c->s_copy, &k.up_id));
-    st.busy = k.up_id;
-    k.uploaded = true;
-    k.pass1_done = false;
-    k.rs_dense = false;
-    memcpy(k.K, K, sizeof(k.K));
-    memcpy(k.Tcw, Tcw, sizeof(k.Tcw));
-    return SDM_OK;
+    sdm_upload_desc u;
+    u.kf = kf;
+    u.im = im; u.im_step = im_step;
+    u.grad = grad; u.grad_step = grad_step;
+    u.theta = theta; u.theta_step = theta_step;
+    u.edge = edge; u.edge_step = edge_step;
+    memcpy(u.K, K, sizeof(u.K));
+    memcpy(u.Tcw, Tcw, sizeof(u.Tcw));
+    return sdm_upload_keyframes(c, 1, &u);
 }
 
 int sdm_set_pose(sdm_ctx* c, int kf, const float Tcw[12])
@@ -615,8 +661,8 @@ int sdm_candidate_count(sdm_ctx* c, int kf, int* count)
     if (!slot_ok(c, kf)) return fail(SDM_ERR_ARG, "keyframe slot %d out of range", kf);
     if (!c->kf[kf].uploaded) return fail(SDM_ERR_STATE, "keyframe slot %d not uploaded", kf);
     CU(cudaSetDevice(c->cfg.device));
-    CU(cudaMemcpyAsync(c->h_count, c->A.cand_count + kf, sizeof(int), cudaMemcpyDeviceToHost, c->s_copy));
-    CU(cudaStreamSynchronize(c->s_copy));
+    CU(cudaMemcpyAsync(c->h_count, c->A.cand_count + kf, sizeof(int), cudaMemcpyDeviceToHost, c->s_compute));
+    CU(cudaStreamSynchronize(c->s_compute));
     *count = *c->h_count;
     return SDM_OK;
 }
@@ -635,9 +681,12 @@ int sdm_pass1(sdm_ctx* c, int n, const sdm_item* items)
         if (k.rs_dense) {  // the slot's outputs were produced by the dense pass 2: drop stale non-candidate values
             const size_t P = c->npix, s = (size_t)items[i].kf;
             CU(cudaMemsetAsync(c->A.rs + s * P, 0, P * sizeof(float2), c->s_compute));
+            CU(cudaMemsetAsync(c->A.dpl + s * P, 0, P * sizeof(float), c->s_compute));
+            CU(cudaMemsetAsync(c->A.spl + s * P, 0, P * sizeof(float), c->s_compute));
             CU(cudaMemsetAsync(c->A.chk + s * P, 0, P * sizeof(float), c->s_compute));
             CU(cudaMemsetAsync(c->A.pts + s * P * 3, 0, P * 3 * sizeof(float), c->s_compute));
             k.rs_dense = false;
+            k.split_stale = false;
         }
     }
     CU(cudaMemsetAsync(&c->d_stats->fused, 0, sizeof(unsigned long long), c->s_compute));
@@ -712,36 +761,62 @@ int sdm_update_points(sdm_ctx* c, int n, const int32_t* kfs)
     return pass2_impl(c, n, items.data(), 1);
 }
 
+int sdm_download_keyframes(sdm_ctx* c, int n, const sdm_download_desc* d)
+{
+    if (!c || (n > 0 && !d)) return fail(SDM_ERR_ARG, "sdm_download_keyframes: null argument");
+    const int W = c->cfg.width, H = c->cfg.height;
+    const size_t P = c->npix, row = (size_t)W * 4;
+    uint64_t need = 0;
+    for (int i = 0; i < n; ++i) {
+        if (!slot_ok(c, d[i].kf)) return fail(SDM_ERR_ARG, "keyframe slot %d out of range", d[i].kf);
+        if ((d[i].depth && d[i].depth_step < row) || (d[i].sigma && d[i].sigma_step < row) ||
+            (d[i].checked && d[i].checked_step < row) || (d[i].points && d[i].points_step < 3 * row))
+            return fail(SDM_ERR_ARG, "row step smaller than a row");
+        need = std::max(need, c->kf[d[i].kf].comp_id);
+    }
+    if (n <= 0) return SDM_OK;
+    CU(cudaSetDevice(c->cfg.device));
+    cudaStream_t s = c->s_down;
+    RC(c->r_compute.wait(s, need));
+    for (int i = 0; i < n; ++i) {
+        const sdm_download_desc& q = d[i];
+        const KfState& k = c->kf[q.kf];
+        const size_t off = (size_t)q.kf * P;
+        if ((q.depth || q.sigma) && !k.split_stale) {
+            if (q.depth) RC(copy2d(q.depth, q.depth_step, c->A.dpl + off, row, row, H, cudaMemcpyDeviceToHost, s));
+            if (q.sigma) RC(copy2d(q.sigma, q.sigma_step, c->A.spl + off, row, row, H, cudaMemcpyDeviceToHost, s));
+        } else if (q.depth || q.sigma) {  // (rho,sigma) written from outside: de-interleave on the fly
+            DownStage& st = c->down[c->down_next];
+            c->down_next = (c->down_next + 1) % kDownStages;
+            // same stream: the previous user's D2H copies are ordered before this kernel
+            sdm::k_split_rs<<<(unsigned)((P + 255) / 256), 256, 0, s>>>(c->A.rs + off, st.planes, st.planes + P, P);
+            CU(cudaGetLastError());
+            c->launches++;
+            if (q.depth) RC(copy2d(q.depth, q.depth_step, st.planes, row, row, H, cudaMemcpyDeviceToHost, s));
+            if (q.sigma) RC(copy2d(q.sigma, q.sigma_step, st.planes + P, row, row, H, cudaMemcpyDeviceToHost, s));
+        }
+        if (q.checked) RC(copy2d(q.checked, q.checked_step, c->A.chk + off, row, row, H, cudaMemcpyDeviceToHost, s));
+        if (q.points) RC(copy2d(q.points, q.points_step, c->A.pts + off * 3, 3 * row, 3 * row, H, cudaMemcpyDeviceToHost, s));
+    }
+    uint64_t id = 0;
+    RC(c->r_down.record(s, &id));
+    for (int i = 0; i < n; ++i) {
+        if (d[i].depth || d[i].sigma) c->kf[d[i].kf].down_ds_id = id;
+        if (d[i].checked || d[i].points) c->kf[d[i].kf].down_cp_id = id;
+    }
+    return SDM_OK;
+}
+
 int sdm_download_async(sdm_ctx* c, int kf, float* depth, size_t depth_step, float* sigma, size_t sigma_step, float* checked,
                        size_t checked_step, float* points, size_t points_step)
 {
-    if (!c) return fail(SDM_ERR_ARG, "null context");
-    if (!slot_ok(c, kf)) return fail(SDM_ERR_ARG, "keyframe slot %d out of range", kf);
-    const int W = c->cfg.width, H = c->cfg.height;
-    const size_t P = c->npix, row = (size_t)W * 4;
-    if ((depth && depth_step < row) || (sigma && sigma_step < row) || (checked && checked_step < row) ||
-        (points && points_step < 3 * row))
-        return fail(SDM_ERR_ARG, "row step smaller than a row");
-    CU(cudaSetDevice(c->cfg.device));
-    KfState& k = c->kf[kf];
-    cudaStream_t s = c->s_down;
-    RC(c->r_compute.wait(s, k.comp_id));
-    RC(c->r_copy.wait(s, k.up_id));
-    if (depth || sigma) {
-        DownStage& st = c->down[c->down_next];
-        c->down_next = (c->down_next + 1) % kDownStages;
-        // same stream: the previous user's D2H copies are ordered before this kernel
-        sdm::k_split_rs<<<(unsigned)((P + 255) / 256), 256, 0, s>>>(c->A.rs + (size_t)kf * P, st.planes, st.planes + P, P);
-        CU(cudaGetLastError());
-        c->launches++;
-        if (depth) RC(copy2d(depth, depth_step, st.planes, row, row, H, cudaMemcpyDeviceToHost, s));
-        if (sigma) RC(copy2d(sigma, sigma_step, st.planes + P, row, row, H, cudaMemcpyDeviceToHost, s));
-    }
-    if (checked) RC(copy2d(checked, checked_step, c->A.chk + (size_t)kf * P, row, row, H, cudaMemcpyDeviceToHost, s));
-    if (points)
-        RC(copy2d(points, points_step, c->A.pts + (size_t)kf * P * 3, 3 * row, 3 * row, H, cudaMemcpyDeviceToHost, s));
-    RC(c->r_down.record(s, &k.down_id));
-    return SDM_OK;
+    sdm_download_desc q;
+    q.kf = kf;
+    q.depth = depth; q.depth_step = depth_step;
+    q.sigma = sigma; q.sigma_step = sigma_step;
+    q.checked = checked; q.checked_step = checked_step;
+    q.points = points; q.points_step = points_step;
+    return sdm_download_keyframes(c, 1, &q);
 }
 
 int sdm_download(sdm_ctx* c, int kf, float* depth, size_t depth_step, float* sigma, size_t sigma_step, float* checked,
@@ -762,8 +837,7 @@ int sdm_upload_depth(sdm_ctx* c, int kf, const float* depth, size_t depth_step, 
     CU(cudaSetDevice(c->cfg.device));
     KfState& k = c->kf[kf];
     cudaStream_t s = c->s_compute;
-    RC(c->r_copy.wait(s, k.up_id));
-    RC(c->r_down.wait(s, k.down_id));
+    RC(c->r_down.wait(s, k.down_ds_id));
     RC(copy2d(c->xfer, row, depth, depth_step, row, H, cudaMemcpyHostToDevice, s));
     RC(copy2d(c->xfer + P, row, sigma, sigma_step, row, H, cudaMemcpyHostToDevice, s));
     sdm::k_merge_rs<<<(unsigned)((P + 255) / 256), 256, 0, s>>>(c->A.rs + (size_t)kf * P, c->xfer, c->xfer + P, P);
@@ -773,6 +847,7 @@ int sdm_upload_depth(sdm_ctx* c, int kf, const float* depth, size_t depth_step, 
     CU(cudaStreamSynchronize(s));
     k.pass1_done = true;
     k.rs_dense = true;
+    k.split_stale = true;
     return SDM_OK;
 }
 
@@ -826,13 +901,13 @@ int sdm_pull_halo(sdm_ctx* c, int n, const int32_t* local_slot, const int32_t* p
         if (pr < 0 || pr >= kMaxPeers || !c->peer_rs[pr]) return fail(SDM_ERR_STATE, "peer %d arena not imported", pr);
         if (peer_slot[i] < 0) return fail(SDM_ERR_ARG, "peer slot %d negative", peer_slot[i]);
         KfState& k = c->kf[local_slot[i]];
-        RC(c->r_copy.wait(c->s_compute, k.up_id));  // k_pack zeroes the plane: must not land after the pull
-        RC(c->r_down.wait(c->s_compute, k.down_id));
+        RC(c->r_down.wait(c->s_compute, k.down_ds_id));  // (k_pack of the slot is earlier on this same stream)
         const char* src = (const char*)c->peer_rs[pr] + (size_t)peer_slot[i] * bytes;
         CU(cudaMemcpyAsync(c->A.rs + (size_t)local_slot[i] * c->npix, src, bytes, cudaMemcpyDeviceToDevice, c->s_compute));
         RC(c->r_compute.record(c->s_compute, &k.comp_id));
         k.pass1_done = true;
         k.rs_dense = true;
+        k.split_stale = true;
     }
     return SDM_OK;
 }
@@ -843,6 +918,7 @@ int sdm_mark_pass1_done(sdm_ctx* c, int kf)
     if (!slot_ok(c, kf)) return fail(SDM_ERR_ARG, "keyframe slot %d out of range", kf);
     c->kf[kf].pass1_done = true;
     c->kf[kf].rs_dense = true;
+    c->kf[kf].split_stale = true;
     return SDM_OK;
 }
 
@@ -991,11 +1067,11 @@ static int intra_single(sdm_ctx* c, int kf, bool check, bool grow)
     KfState& k = c->kf[kf];
     if (!k.pass1_done || (grow && !k.uploaded)) return fail(SDM_ERR_STATE, "slot %d has no pass-1 planes", kf);
     CU(cudaSetDevice(c->cfg.device));
-    RC(c->r_copy.wait(c->s_compute, k.up_id));
-    RC(c->r_down.wait(c->s_compute, k.down_id));
+    RC(c->r_down.wait(c->s_compute, k.down_ds_id));
     int* d_slots;
     RC(single_slot_array(c, kf, &d_slots));
     RC(run_intra(c, d_slots, 1, check, grow));
+    k.split_stale = false;  // the second stencil stage rewrites dpl / spl from the final (rho,sigma) plane
     return c->r_compute.record(c->s_compute, &k.comp_id);
 }
 

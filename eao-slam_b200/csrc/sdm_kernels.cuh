@@ -46,6 +46,8 @@ struct DevArena {
     float2* rs;
     float* chk;
     float* pts;
+    float* dpl;  // dense depth_map_ plane   } copies of rs.x / rs.y kept for the D2H path, so a download is
+    float* spl;  // dense depth_sigma_ plane } pure DMA (no de-interleave kernel competing for SMs)
     size_t P;  // pixels per plane
 };
 
@@ -322,6 +324,8 @@ __global__ void __launch_bounds__(256) k_pack(DevArena A, DevParams P, int slot,
         A.tex[base + i0] = make_float4(g0, g1, theta[i0], theta[i1]);
         A.ipair[base + i0] = make_uchar2(im[i0], im[i1]);
         A.rs[base + i0] = make_float2(0.f, 0.f);
+        A.dpl[base + i0] = 0.f;
+        A.spl[base + i0] = 0.f;
         A.chk[base + i0] = 0.f;  // pass 2 only visits candidate pixels: the rest of the output planes stays 0
         A.pts[3 * (base + i0) + 0] = 0.f;
         A.pts[3 * (base + i0) + 1] = 0.f;
@@ -549,7 +553,14 @@ __device__ __forceinline__ bool scan_pixel_warp(const DevArena& A, const DevPara
             fused = true;
         }
     }
-    if (lane == 0) A.rs[(size_t)kf * A.P + (size_t)y * P.W + x] = make_float2(out_d, out_s);
+    if (lane == 0) {
+        const size_t own = (size_t)kf * A.P + (size_t)y * P.W + x;
+        A.rs[own] = make_float2(out_d, out_s);
+    A.dpl[own] = out_d;
+    A.spl[own] = out_s;
+        A.dpl[own] = out_d;
+        A.spl[own] = out_s;
+    }
     return fused;
 }
 
@@ -734,6 +745,8 @@ __device__ __forceinline__ bool scan_pixel_lane(const DevArena& A, const DevPara
         }
     }
     A.rs[own] = make_float2(out_d, out_s);
+    A.dpl[own] = out_d;
+    A.spl[own] = out_s;
     return fused;
 }
 
@@ -914,8 +927,9 @@ k_intra_check(DevParams P, const float2* __restrict__ arena, float2* __restrict_
 }
 
 __global__ void __launch_bounds__(256)
-k_intra_grow(DevParams P, const float2* __restrict__ tmp, float2* __restrict__ arena, const float4* __restrict__ tex_arena,
-             const int* __restrict__ slots, size_t npix, int copy_only)
+k_intra_grow(DevParams P, const float2* __restrict__ tmp, float2* __restrict__ arena, float* __restrict__ dpl_arena,
+             float* __restrict__ spl_arena, const float4* __restrict__ tex_arena, const int* __restrict__ slots, size_t npix,
+             int copy_only)
 {
     const int px = blockIdx.x * 32 + threadIdx.x, py = blockIdx.y * 8 + threadIdx.y;
     if (px >= P.W || py >= P.H) return;
@@ -943,6 +957,8 @@ k_intra_grow(DevParams P, const float2* __restrict__ tmp, float2* __restrict__ a
         if (n >= 2) out = make_float2(pjsj / rsj, min_sigma);
     }
     dst[pi] = out;
+    dpl_arena[slot * npix + pi] = out.x;
+    spl_arena[slot * npix + pi] = out.y;
 }
 
 // ---------------------------------------------------------------------------------------------

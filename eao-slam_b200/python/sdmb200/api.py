@@ -47,6 +47,18 @@ class Hypothesis(C.Structure):
                 ("best_u", C.c_float), ("best_v", C.c_float)]
 
 
+class UploadDesc(C.Structure):
+    _fields_ = [("kf", C.c_int32), ("im", C.c_void_p), ("im_step", C.c_size_t), ("grad", C.c_void_p), ("grad_step", C.c_size_t),
+                ("theta", C.c_void_p), ("theta_step", C.c_size_t), ("edge", C.c_void_p), ("edge_step", C.c_size_t),
+                ("K", C.c_float * 4), ("Tcw", C.c_float * 12)]
+
+
+class DownloadDesc(C.Structure):
+    _fields_ = [("kf", C.c_int32), ("depth", C.c_void_p), ("depth_step", C.c_size_t), ("sigma", C.c_void_p),
+                ("sigma_step", C.c_size_t), ("checked", C.c_void_p), ("checked_step", C.c_size_t),
+                ("points", C.c_void_p), ("points_step", C.c_size_t)]
+
+
 class Timing(C.Structure):
     _fields_ = [("pass1_scan_ms", C.c_float), ("pass1_intra_ms", C.c_float), ("pass2_ms", C.c_float)]
 
@@ -59,7 +71,7 @@ class Stats(C.Structure):
 EXPORTS = [
     "sdm_default_config", "sdm_create", "sdm_destroy", "sdm_last_error", "sdm_version", "sdm_synchronize",
     "sdm_get_stats", "sdm_host_alloc", "sdm_host_free", "sdm_upload_keyframe", "sdm_set_pose",
-    "sdm_set_intrinsics", "sdm_candidate_count", "sdm_pass1", "sdm_pass2", "sdm_update_points", "sdm_download", "sdm_download_async",
+    "sdm_set_intrinsics", "sdm_candidate_count", "sdm_pass1", "sdm_pass2", "sdm_update_points", "sdm_download", "sdm_download_async", "sdm_upload_keyframes", "sdm_download_keyframes",
     "sdm_upload_depth", "sdm_depth_plane_ptr", "sdm_export_arena", "sdm_import_peer_arena", "sdm_pull_halo",
     "sdm_mark_pass1_done", "sdm_pair_geometry", "sdm_stereo_search_constraints", "sdm_search_range",
     "sdm_epipolar_search", "sdm_epipolar_search_plane", "sdm_fuse", "sdm_intra_check", "sdm_intra_grow",
@@ -99,6 +111,8 @@ def load() -> C.CDLL:
     lib.sdm_update_points.argtypes = [vp, C.c_int, ip]
     lib.sdm_download.argtypes = [vp, C.c_int, vp, sz, vp, sz, vp, sz, vp, sz]
     lib.sdm_download_async.argtypes = [vp, C.c_int, vp, sz, vp, sz, vp, sz, vp, sz]
+    lib.sdm_upload_keyframes.argtypes = [vp, C.c_int, C.POINTER(UploadDesc)]
+    lib.sdm_download_keyframes.argtypes = [vp, C.c_int, C.POINTER(DownloadDesc)]
     lib.sdm_upload_depth.argtypes = [vp, C.c_int, vp, sz, vp, sz]
     lib.sdm_depth_plane_ptr.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(sz)]
     lib.sdm_export_arena.argtypes = [vp, vp, C.POINTER(sz)]
@@ -207,12 +221,33 @@ class Context:
             edge.ctypes.data if edge is not None else None, edge.strides[0] if edge is not None else 0,
             _fp(Kf), _fp(Tf)))
 
+    def upload_descs(self, scene, indices, slot_of=None):
+        """sdm_upload_desc array for keyframes `indices` of a scene (arrays must stay alive until synchronize)."""
+        idx = list(indices)
+        arr = (UploadDesc * len(idx))()
+        for a, i in zip(arr, idx):
+            a.kf = int(i if slot_of is None else slot_of[i])
+            a.im, a.im_step = scene.im[i].ctypes.data, scene.im[i].strides[0]
+            a.grad, a.grad_step = scene.grad[i].ctypes.data, scene.grad[i].strides[0]
+            a.theta, a.theta_step = scene.theta[i].ctypes.data, scene.theta[i].strides[0]
+            if scene.edge is not None:
+                a.edge, a.edge_step = scene.edge[i].ctypes.data, scene.edge[i].strides[0]
+            for j, v in enumerate(scene.K):
+                a.K[j] = float(v)
+            for j, v in enumerate(np.asarray(scene.Tcw[i], np.float32).reshape(-1)[:12]):
+                a.Tcw[j] = float(v)
+        return arr
+
+    def upload_keyframes(self, descs):
+        self._chk(self.lib.sdm_upload_keyframes(self.h, len(descs), descs))
+
+    def download_keyframes(self, descs):
+        """enqueue only: the host arrays are valid after synchronize()"""
+        self._chk(self.lib.sdm_download_keyframes(self.h, len(descs), descs))
+
     def upload_scene(self, scene, indices=None, slot_of=None):
         idx = range(scene.n) if indices is None else indices
-        for i in idx:
-            s = i if slot_of is None else slot_of[i]
-            self.upload_keyframe(s, scene.im[i], scene.grad[i], scene.theta[i],
-                                 scene.edge[i] if scene.edge is not None else None, scene.K, scene.Tcw[i])
+        self.upload_keyframes(self.upload_descs(scene, idx, slot_of))
 
     def set_pose(self, slot, Tcw):
         self._chk(self.lib.sdm_set_pose(self.h, slot, _fp(_f32(np.asarray(Tcw).reshape(-1)[:12]))))

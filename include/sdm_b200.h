@@ -114,6 +114,18 @@ int sdm_upload_keyframe(sdm_ctx* ctx, int kf,
                         const float* theta, size_t theta_step,
                         const int32_t* edge, size_t edge_step,
                         const float K[4], const float Tcw[12]);
+/* the same for n keyframes in one call (one work order per keyframe): fewer host calls and one
+ * stream hand-over per batch.  This is what a host loop over all keyframes should use. */
+typedef struct {
+    int32_t kf;
+    const uint8_t* im;    size_t im_step;
+    const float* grad;    size_t grad_step;
+    const float* theta;   size_t theta_step;
+    const int32_t* edge;  size_t edge_step; /* edge may be NULL */
+    float K[4];
+    float Tcw[12];
+} sdm_upload_desc;
+int sdm_upload_keyframes(sdm_ctx* ctx, int n, const sdm_upload_desc* desc);
 /* replaces: KeyFrame::SetPose (KeyFrame.cc:108-124) for PoseChanged refresh (:691-694) */
 int sdm_set_pose(sdm_ctx* ctx, int kf, const float Tcw[12]);
 /* calibration of a slot (KeyFrame::fx,fy,cx,cy; Frame.cc:584-590).  With sdm_set_pose this is all a
@@ -143,6 +155,15 @@ int sdm_download(sdm_ctx* ctx, int kf,
 int sdm_download_async(sdm_ctx* ctx, int kf,
                        float* depth, size_t depth_step, float* sigma, size_t sigma_step,
                        float* checked, size_t checked_step, float* points, size_t points_step);
+/* sdm_download_async for n keyframes in one call (any plane pointer of an entry may be NULL) */
+typedef struct {
+    int32_t kf;
+    float* depth;    size_t depth_step;
+    float* sigma;    size_t sigma_step;
+    float* checked;  size_t checked_step;
+    float* points;   size_t points_step;
+} sdm_download_desc;
+int sdm_download_keyframes(sdm_ctx* ctx, int n, const sdm_download_desc* desc);
 /* writes pass-1 planes of a keyframe (used to seed halo keyframes / tests); blocking */
 int sdm_upload_depth(sdm_ctx* ctx, int kf, const float* depth, size_t depth_step,
                      const float* sigma, size_t sigma_step);
