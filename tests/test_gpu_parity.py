@@ -196,3 +196,43 @@ def test_against_committed_golden_vectors(golden_dir, tag, intra):
     rep = compare_planes(dev, GoldenRef(g, tag))
     print(json.dumps(rep))
     assert dev["stats"]["candidates"] == int(g[f"{tag}_stats"][0])
+
+
+def test_config4_1280x960_ten_neighbours_wide_range():
+    """BASELINE config 4: 1280x960 keyframes, 10 neighbours, wide inverse-depth search range (long scans)."""
+    sc = synth.make_scene(12, 1280, 960, 10, seed=4, wide_range=True, workers=4)
+    osc = run_oracle(sc)
+    dev = run_device(sc)
+    rep = compare_planes(dev, osc)
+    st = osc.stats.as_dict()
+    print(json.dumps(rep), "mean scan length", st["scanned"] / (st["candidates"] * 10.0))
+    assert st["scanned"] / (st["candidates"] * 10.0) > 100, "config 4 is the long-scan regime"
+    assert rep["pass1_accepted_ref"] > 100000
+
+
+def test_batch_upload_download_and_async_overlap(small_scene, small_oracle):
+    """sdm_upload_keyframes / sdm_download_keyframes in chunks with passes interleaved (the e2e issue order of
+    bench.py) give the same planes as the one-shot loop."""
+    sc, osc = small_scene, small_oracle
+    H, W = sc.shape
+    n = sc.n
+    out = {k: np.zeros((n, H, W) + ((3,) if k == "points" else ()), np.float32) for k in ("depth", "sigma", "checked", "points")}
+    with api.Context(width=W, height=H, max_keyframes=n) as ctx:
+        up = ctx.upload_descs(sc, range(n))
+        dl = (api.DownloadDesc * n)()
+        for i in range(n):
+            dl[i].kf = i
+            dl[i].depth, dl[i].depth_step = out["depth"][i].ctypes.data, 4 * W
+            dl[i].sigma, dl[i].sigma_step = out["sigma"][i].ctypes.data, 4 * W
+            dl[i].checked, dl[i].checked_step = out["checked"][i].ctypes.data, 4 * W
+            dl[i].points, dl[i].points_step = out["points"][i].ctypes.data, 12 * W
+        for rep_ in range(3):  # repeated: exercises the re-upload / overwrite hazards between streams
+            ctx.upload_keyframes(up)
+            for lo in range(0, n, 3):
+                ctx.pass1(api.make_items(range(lo, min(n, lo + 3)), sc.nbr_idx, sc.rot, sc.min_depth, sc.max_depth))
+            for lo in range(0, n, 3):
+                ctx.pass2(api.make_items(range(lo, min(n, lo + 3)), sc.nbr_idx, sc.rot, sc.min_depth, sc.max_depth))
+            ctx.download_keyframes(dl)
+            ctx.synchronize()
+            rep = compare_planes(out, osc)
+            assert rep["depth_bit_mismatch"] == 0 and rep["checked_bit_mismatch"] == 0 and rep["points_bit_mismatch"] == 0
