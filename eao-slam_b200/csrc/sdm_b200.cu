@@ -165,7 +165,7 @@ struct sdm_ctx {
     float* xfer = nullptr;  // 2 dense float planes (sdm_upload_depth staging)
     float* dbg = nullptr;   // 4 float planes + 1 byte plane (sdm_epipolar_search_plane)
     void* peer_rs[kMaxPeers] = {nullptr};
-    int grid_pass1_warp = 0, grid_pass2 = 0, n_sm = 0;  // persistent grids (blocks)
+    int grid_pass1_warp = 0, grid_pass2 = 0, grid_intra = 0, n_sm = 0;  // persistent grids (blocks)
     long long launches = 0;
     int scan_warp_per_pixel = 0;  // developer A/B knob (env SDM_SCAN=warp): the warp-per-pixel scan kernel
 };
@@ -400,7 +400,7 @@ void sdm_destroy(sdm_ctx* c)
     for (int i = 0; i < kMaxPeers; ++i)
         if (c->peer_rs[i]) cudaIpcCloseMemHandle(c->peer_rs[i]);
     cudaFree(c->A.tex); cudaFree(c->A.ipair); cudaFree(c->A.cand); cudaFree(c->A.cand_count);
-    cudaFree(c->A.rs); cudaFree(c->A.chk); cudaFree(c->A.pts); cudaFree(c->A.dpl); cudaFree(c->A.spl);
+    cudaFree(c->A.rs); cudaFree(c->A.chk); cudaFree(c->A.pts); cudaFree(c->A.dpl); cudaFree(c->A.spl); cudaFree(c->A.rs2);
     for (auto& s : c->up) { cudaFree(s.im); cudaFree(s.grad); cudaFree(s.theta); cudaFree(s.edge); }
     for (auto& s : c->down) cudaFree(s.planes);
     for (auto& s : c->ist)
@@ -477,6 +477,10 @@ static int create_impl(sdm_ctx* c)
     CU(cudaMalloc(&A.spl, n * P * sizeof(float)));
     CU(cudaMemsetAsync(A.dpl, 0, n * P * sizeof(float), c->s_compute));
     CU(cudaMemsetAsync(A.spl, 0, n * P * sizeof(float), c->s_compute));
+    if (cfg.intra_check || cfg.intra_grow) {  // second plane of the intra ping-pong (candidate-list stencils)
+        CU(cudaMalloc(&A.rs2, n * P * sizeof(float2)));
+        CU(cudaMemsetAsync(A.rs2, 0, n * P * sizeof(float2), c->s_compute));
+    }
     CU(cudaMemsetAsync(A.cand_count, 0, n * sizeof(int), c->s_compute));
     CU(cudaMemsetAsync(A.rs, 0, n * P * sizeof(float2), c->s_compute));
     CU(cudaMemsetAsync(A.chk, 0, n * P * sizeof(float), c->s_compute));
@@ -500,6 +504,8 @@ static int create_impl(sdm_ctx* c)
     c->grid_pass1_warp = std::max(1, occ) * prop.multiProcessorCount;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sdm::k_pass2_cand, sdm::kLaneBlock, 0));
     c->grid_pass2 = std::max(1, occ) * prop.multiProcessorCount;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sdm::k_intra_cand, sdm::kChunk, 0));
+    c->grid_intra = std::max(1, occ) * prop.multiProcessorCount;
     CU(cudaStreamSynchronize(c->s_compute));
     return SDM_OK;
 }
@@ -700,14 +706,25 @@ int sdm_pass1(sdm_ctx* c, int n, const sdm_item* items)
         for (int i = 0; i < n; ++i) max_n = std::max(max_n, (int)items[i].n_nbr);
         const size_t smem = (size_t)max_n * sdm::kLaneBlock * sizeof(float2);
         int occ = 0;  // persistent grid: fill every SM to this launch's occupancy
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sdm::k_pass1_lane, sdm::kLaneBlock, smem));
-        sdm::k_pass1_lane<<<std::max(1, occ) * c->n_sm, sdm::kLaneBlock, smem, c->s_compute>>>(c->A, c->P, c->d_items, plan,
-                                                                                               c->d_stats);
+        // the exact short forms of the two direction gates exist for the reference's thresholds only
+        const bool fast = (c->cfg.lambdaL == 80 && c->cfg.lambdaTheta == 45);
+        auto kern = fast ? sdm::k_pass1_lane<true> : sdm::k_pass1_lane<false>;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, sdm::kLaneBlock, smem));
+        kern<<<std::max(1, occ) * c->n_sm, sdm::kLaneBlock, smem, c->s_compute>>>(c->A, c->P, c->d_items, plan, c->d_stats);
     }
     CU(cudaGetLastError());
     c->launches += 2;
     CU(cudaEventRecord(c->ev_p1_scan, c->s_compute));
-    RC(run_intra(c, b.d_slots, n, c->cfg.intra_check != 0, c->cfg.intra_grow != 0));
+    if (c->cfg.intra_check || c->cfg.intra_grow) {
+        // candidate-list stencils over the same work plan: check rs -> rs2, grow rs2 -> rs (+ dense copies)
+        for (int stage = 0; stage < 2; ++stage) {
+            CU(cudaMemsetAsync(c->d_counter, 0, sizeof(int), c->s_compute));
+            const int copy_only = stage == 0 ? !c->cfg.intra_check : !c->cfg.intra_grow;
+            sdm::k_intra_cand<<<c->grid_intra, sdm::kChunk, 0, c->s_compute>>>(c->A, c->P, c->d_items, plan, stage, copy_only);
+        }
+        CU(cudaGetLastError());
+        c->launches += 2;
+    }
     CU(cudaEventRecord(c->ev_p1[1], c->s_compute));
     c->p1_timed = true;
     RC(finish_batch(c, n, items));

@@ -48,6 +48,7 @@ struct DevArena {
     float* pts;
     float* dpl;  // dense depth_map_ plane   } copies of rs.x / rs.y kept for the D2H path, so a download is
     float* spl;  // dense depth_sigma_ plane } pure DMA (no de-interleave kernel competing for SMs)
+    float2* rs2;  // second (rho,sigma) plane of the intra ping-pong: zero outside the candidate pixels
     size_t P;  // pixels per plane
 };
 
@@ -326,6 +327,7 @@ __global__ void __launch_bounds__(256) k_pack(DevArena A, DevParams P, int slot,
         A.rs[base + i0] = make_float2(0.f, 0.f);
         A.dpl[base + i0] = 0.f;
         A.spl[base + i0] = 0.f;
+        if (A.rs2) A.rs2[base + i0] = make_float2(0.f, 0.f);
         A.chk[base + i0] = 0.f;  // pass 2 only visits candidate pixels: the rest of the output planes stays 0
         A.pts[3 * (base + i0) + 0] = 0.f;
         A.pts[3 * (base + i0) + 1] = 0.f;
@@ -634,6 +636,7 @@ __device__ __forceinline__ void valid_columns(float ab, float cb, float Hm1, int
     ub = min(u_hi, q - 1);
 }
 
+template <bool kFastGates>
 __device__ __forceinline__ bool scan_pixel_lane(const DevArena& A, const DevParams& P, const DevItem& s_item,
                                                 float2 (*s_h)[kLaneBlock], int ci, int tid)
 {
@@ -677,10 +680,11 @@ __device__ __forceinline__ bool scan_pixel_lane(const DevArena& A, const DevPara
             float w0n = (fl + 1.0f) - vn, w1n = vn - fl;
             unsigned idxn = (unsigned)((int)fl * W + ua);
             float4 tn = __ldg(reinterpret_cast<const float4*>(tb + (size_t)idxn * 16));
+            // unrolled by two so that the pipeline registers (current / next texel) swap roles instead of being copied
+#pragma unroll 2
             for (int u = ua; u <= ub; ++u) {
                 const float4 t = tn;
                 const float w0 = w0n, w1 = w1n;
-                const unsigned idx = idxn;
                 vn = -(ab * (float)(u + 1) + cb);
                 fl = floorf(vn);
                 w0n = (fl + 1.0f) - vn;
@@ -693,14 +697,22 @@ __device__ __forceinline__ bool scan_pixel_lane(const DevArena& A, const DevPara
                 float ang = gth - s.th_line;  // condition 2
                 if (ang >= 360.f) ang -= 360.f;
                 if (ang < 0.f) ang += 360.f;
-                if (ang > 180.f) ang = 360.f - ang;
-                if (ang > 90.f) ang = 180.f - ang;
-                if (ang >= lamL) continue;
                 float thd = gth - s.ang_pi_rot;  // condition 3
                 if (thd >= 360.f) thd -= 360.f;
                 if (thd < 0.f) thd += 360.f;
-                if (thd > 180.f) thd = 360.f - thd;
-                if (thd >= lamT) continue;
+                if (kFastGates) {
+                    // exact short forms of the fold sequences for lambdaL = 80, lambdaTheta = 45, checked over all
+                    // 2^32 float bit patterns (tools/verify_gate_algebra.py): same decision, NaN included
+                    if (fabsf(fabsf(ang - 180.f) - 90.f) <= 10.f) continue;
+                    if (thd >= 45.f && thd <= 315.f) continue;
+                } else {
+                    if (ang > 180.f) ang = 360.f - ang;
+                    if (ang > 90.f) ang = 180.f - ang;
+                    if (ang >= lamL) continue;
+                    if (thd > 180.f) thd = 360.f - thd;
+                    if (thd >= lamT) continue;
+                }
+                const unsigned idx = (unsigned)((int)floorf(-(ab * (float)u + cb)) * W + u);
                 const uchar2 i2 = __ldg(reinterpret_cast<const uchar2*>(ib + (size_t)idx * 2));
                 const float pe = pixel - ((float)i2.x * w0 + (float)i2.y * w1);
                 const float ge = gradc - g2;
@@ -753,6 +765,7 @@ __device__ __forceinline__ bool scan_pixel_lane(const DevArena& A, const DevPara
 #ifndef SDM_LANE_MINB
 #define SDM_LANE_MINB 10  // 48 registers: measured optimum on B200 (latency-bound scan; 7 -> 10 blocks/SM = -18 % time)
 #endif
+template <bool kFastGates>
 __global__ void __launch_bounds__(kLaneBlock, SDM_LANE_MINB)
 k_pass1_lane(DevArena A, DevParams P, const DevItem* __restrict__ items, DevPlan plan, DevStats* stats)
 {
@@ -766,7 +779,7 @@ k_pass1_lane(DevArena A, DevParams P, const DevItem* __restrict__ items, DevPlan
     while (next_chunk(plan, items, s_item, s_chunk, cur_entry, first)) {
         const int ci = first + tid;
         bool fused = false;
-        if (ci < A.cand_count[s_item.kf]) fused = scan_pixel_lane(A, P, s_item, s_h, ci, tid);
+        if (ci < A.cand_count[s_item.kf]) fused = scan_pixel_lane<kFastGates>(A, P, s_item, s_h, ci, tid);
         n_fused += __popc(__ballot_sync(SDM_FULL, fused));
     }
     if (stats && (tid & 31) == 0 && n_fused) atomicAdd(&stats->fused, (unsigned long long)n_fused);
@@ -885,12 +898,63 @@ __global__ void __launch_bounds__(256) k_fuse_sets(DevParams P, int m, int n, co
 
 // ---------------------------------------------------------------------------------------------
 // K5: IntraKeyFrameDepthChecking (:866-927) and IntraKeyFrameDepthGrowing (:929-976): 3x3 Jacobi
-// stencils on the (rho, sigma) planes of a BATCH of keyframes (grid.z = keyframe).  Each kernel reads
-// one full plane and writes one full plane (changed value or copy), so "check" goes arena -> tmp and
-// "grow" goes tmp -> arena with no snapshot copies:  src/dst plane of batch entry z is
-//   arena + slots[z] * npix   or   tmp + z * npix.
-// copy_only = 1 turns a kernel into the plain plane copy needed when only one of the two is enabled.
+// stencils on the (rho, sigma) planes.  Two stages that ping-pong between two planes (no snapshot
+// copies): "check" reads plane A and writes plane B, "grow" reads B and writes A (+ the dense
+// depth / sigma copies).  copy_only = 1 turns a stage into a plain copy (only one of the two enabled).
+//   * candidate-list kernels (default, planes produced by pass 1): (rho,sigma) is non-zero only at
+//     candidate pixels, so both stages visit the compacted candidates of the batch (dense warps, same
+//     work plan as pass 1); plane B is the slot's own second plane rs2, zero outside the candidates.
+//     Growing is evaluated on the candidates only: a non-candidate pixel holds (0,0), and a centre with
+//     sigma = 0 can never pass ChiTest (num/0 is inf or NaN), so it cannot grow.
+//   * dense kernels (planes written from outside: sdm_upload_depth, single-method entry points):
+//     every pixel of the plane, grid.z = keyframe, plane B = tmp + z * npix.
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 intra_check_pixel(const DevParams& P, const float2* __restrict__ src, int px, int py, float2 c)
+{
+    float pjsj = 0.f, rsj = 0.f, min_sigma = 0.f;
+    int n = 0;
+    for (int y = py - 1; y <= py + 1; ++y)
+        for (int x = px - 1; x <= px + 1; ++x) {
+            if (x == px && y == py) continue;
+            const float2 q = src[(size_t)y * P.W + x];
+            if (q.x > P.eps_gt && chi_compatible(q.x, c.x, q.y, c.y, P.chi_fusion_lt)) {
+                if (n == 0) min_sigma = q.y;
+                fusion_accumulate(q.x, q.y, pjsj, rsj);
+                // pow(sigma,2) < pow(min,2) in double == |sigma| < |min|
+                if ((double)q.y * (double)q.y < (double)min_sigma * (double)min_sigma) min_sigma = q.y;
+                ++n;
+            }
+        }
+    if (n == 0) min_sigma = c.y;
+    fusion_accumulate(c.x, c.y, pjsj, rsj);  // "dont forget itself" :902 (pushed last)
+    if ((double)c.y * (double)c.y < (double)min_sigma * (double)min_sigma) min_sigma = c.y;
+    ++n;
+    return (n >= 3) ? make_float2(pjsj / rsj, min_sigma) : make_float2(0.f, 0.f);
+}
+
+__device__ __forceinline__ float2 intra_grow_pixel(const DevParams& P, const float2* __restrict__ src, int px, int py, float2 c)
+{
+    float pjsj = 0.f, rsj = 0.f, min_sigma = 0.f;
+    int n = 0;
+    for (int y = py - 1; y <= py + 1; ++y)
+        for (int x = px - 1; x <= px + 1; ++x) {
+            if (x == px && y == py) continue;
+            const float2 q = src[(size_t)y * P.W + x];
+            if (chi_compatible(q.x, c.x, q.y, c.y, P.chi_fusion_lt)) {
+                if (n == 0) min_sigma = q.y;
+                fusion_accumulate(q.x, q.y, pjsj, rsj);
+                if (q.y < min_sigma) min_sigma = q.y;
+                ++n;
+            }
+        }
+    return (n >= 2) ? make_float2(pjsj / rsj, min_sigma) : c;
+}
+
+__device__ __forceinline__ bool interior2(const DevParams& P, int px, int py)
+{
+    return px >= 2 && py >= 2 && px < P.W - 2 && py < P.H - 2;
+}
+
 __global__ void __launch_bounds__(256)
 k_intra_check(DevParams P, const float2* __restrict__ arena, float2* __restrict__ tmp, const int* __restrict__ slots,
               size_t npix, int copy_only)
@@ -902,27 +966,7 @@ k_intra_check(DevParams P, const float2* __restrict__ arena, float2* __restrict_
     const size_t pi = (size_t)py * P.W + px;
     const float2 c = src[pi];
     float2 out = c;
-    if (!copy_only && px >= 2 && py >= 2 && px < P.W - 2 && py < P.H - 2 && c.x > P.eps_gt) {
-        float pjsj = 0.f, rsj = 0.f, min_sigma = 0.f;
-        int n = 0;
-        for (int y = py - 1; y <= py + 1; ++y)
-            for (int x = px - 1; x <= px + 1; ++x) {
-                if (x == px && y == py) continue;
-                const float2 q = src[(size_t)y * P.W + x];
-                if (q.x > P.eps_gt && chi_compatible(q.x, c.x, q.y, c.y, P.chi_fusion_lt)) {
-                    if (n == 0) min_sigma = q.y;
-                    fusion_accumulate(q.x, q.y, pjsj, rsj);
-                    // pow(sigma,2) < pow(min,2) in double == |sigma| < |min|
-                    if ((double)q.y * (double)q.y < (double)min_sigma * (double)min_sigma) min_sigma = q.y;
-                    ++n;
-                }
-            }
-        if (n == 0) min_sigma = c.y;
-        fusion_accumulate(c.x, c.y, pjsj, rsj);  // "dont forget itself" :902 (pushed last)
-        if ((double)c.y * (double)c.y < (double)min_sigma * (double)min_sigma) min_sigma = c.y;
-        ++n;
-        out = (n >= 3) ? make_float2(pjsj / rsj, min_sigma) : make_float2(0.f, 0.f);
-    }
+    if (!copy_only && interior2(P, px, py) && c.x > P.eps_gt) out = intra_check_pixel(P, src, px, py, c);
     dst[pi] = out;
 }
 
@@ -939,26 +983,45 @@ k_intra_grow(DevParams P, const float2* __restrict__ tmp, float2* __restrict__ a
     const size_t pi = (size_t)py * P.W + px;
     const float2 c = src[pi];
     float2 out = c;
-    if (!copy_only && px >= 2 && py >= 2 && px < P.W - 2 && py < P.H - 2 && c.x < P.eps_lt &&
-        !(tex_arena[slot * npix + pi].x <= P.lambdaG)) {
-        float pjsj = 0.f, rsj = 0.f, min_sigma = 0.f;
-        int n = 0;
-        for (int y = py - 1; y <= py + 1; ++y)
-            for (int x = px - 1; x <= px + 1; ++x) {
-                if (x == px && y == py) continue;
-                const float2 q = src[(size_t)y * P.W + x];
-                if (chi_compatible(q.x, c.x, q.y, c.y, P.chi_fusion_lt)) {
-                    if (n == 0) min_sigma = q.y;
-                    fusion_accumulate(q.x, q.y, pjsj, rsj);
-                    if (q.y < min_sigma) min_sigma = q.y;
-                    ++n;
-                }
-            }
-        if (n >= 2) out = make_float2(pjsj / rsj, min_sigma);
-    }
+    if (!copy_only && interior2(P, px, py) && c.x < P.eps_lt && !(tex_arena[slot * npix + pi].x <= P.lambdaG))
+        out = intra_grow_pixel(P, src, px, py, c);
     dst[pi] = out;
     dpl_arena[slot * npix + pi] = out.x;
     spl_arena[slot * npix + pi] = out.y;
+}
+
+// candidate-list stages; stage = 0: check (rs -> rs2), stage = 1: grow (rs2 -> rs, dpl, spl)
+__global__ void __launch_bounds__(kChunk)
+k_intra_cand(DevArena A, DevParams P, const DevItem* __restrict__ items, DevPlan plan, int stage, int copy_only)
+{
+    __shared__ DevItem s_item;
+    __shared__ int s_chunk;
+    int cur_entry = -1, first = 0;
+    while (next_chunk(plan, items, s_item, s_chunk, cur_entry, first)) {
+        const int ci = first + threadIdx.x;
+        const int kf = s_item.kf;
+        if (ci >= A.cand_count[kf]) continue;
+        const size_t base = (size_t)kf * A.P;
+        const uint32_t packed = A.cand[base + ci];
+        const int px = (int)(packed & 0xffffu), py = (int)(packed >> 16);
+        const size_t pi = (size_t)py * P.W + px;
+        if (stage == 0) {
+            const float2* __restrict__ src = A.rs + base;
+            const float2 c = src[pi];
+            float2 out = c;
+            if (!copy_only && interior2(P, px, py) && c.x > P.eps_gt) out = intra_check_pixel(P, src, px, py, c);
+            A.rs2[base + pi] = out;
+        } else {
+            const float2* __restrict__ src = A.rs2 + base;
+            const float2 c = src[pi];
+            float2 out = c;
+            // (GradImg > lambdaG holds for every candidate, :942)
+            if (!copy_only && interior2(P, px, py) && c.x < P.eps_lt) out = intra_grow_pixel(P, src, px, py, c);
+            A.rs[base + pi] = out;
+            A.dpl[base + pi] = out.x;
+            A.spl[base + pi] = out.y;
+        }
+    }
 }
 
 // ---------------------------------------------------------------------------------------------

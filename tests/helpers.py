@@ -11,19 +11,19 @@ SET_MISMATCH_MAX = 1e-3   # accepted-pixel sets: at most 0.1 % tie / boundary ca
 REL_TOL = 1e-4            # fused inverse depth and variance: 1e-4 relative
 
 
-def run_oracle(scene, intra_check=0, intra_grow=0, kind="canonical"):
+def run_oracle(scene, intra_check=0, intra_grow=0, kind="canonical", **params):
     osc = O.OracleScene(scene, kind)
-    p = O.default_params(kind, intra_check=intra_check, intra_grow=intra_grow)
+    p = O.default_params(kind, intra_check=intra_check, intra_grow=intra_grow, **params)
     osc.run(params=p)
     return osc
 
 
-def run_device(scene, intra_check=0, intra_grow=0, ctx=None):
+def run_device(scene, intra_check=0, intra_grow=0, ctx=None, **cfg):
     """Full SemiDenseLoop through the C-ABI: upload, pass 1 (all), pass 2 (all), download."""
     H, W = scene.shape
     own = ctx is None
     if own:
-        ctx = api.Context(width=W, height=H, max_keyframes=scene.n, intra_check=intra_check, intra_grow=intra_grow)
+        ctx = api.Context(width=W, height=H, max_keyframes=scene.n, intra_check=intra_check, intra_grow=intra_grow, **cfg)
     ctx.upload_scene(scene)
     items = api.make_items(range(scene.n), scene.nbr_idx, scene.rot, scene.min_depth, scene.max_depth)
     ctx.pass1(items)

@@ -236,3 +236,14 @@ def test_batch_upload_download_and_async_overlap(small_scene, small_oracle):
             ctx.synchronize()
             rep = compare_planes(out, osc)
             assert rep["depth_bit_mismatch"] == 0 and rep["checked_bit_mismatch"] == 0 and rep["points_bit_mismatch"] == 0
+
+
+def test_non_default_thresholds(small_scene):
+    """Run-time versions of the #defines (ProbabilityMapping.h:45-56): other lambdaG / lambdaL / lambdaTheta / lambdaN /
+    chi-square values take the generic gate code path (the exact short forms only exist for 80 / 45)."""
+    over = dict(lambdaG=10, lambdaL=70, lambdaTheta=30, lambdaN=2, chi2_fusion=4.5, chi2_inter=3.0)
+    osc = run_oracle(small_scene, **over)
+    dev = run_device(small_scene, **over)
+    rep = compare_planes(dev, osc)
+    print(json.dumps(rep))
+    assert rep["depth_bit_mismatch"] == 0 and rep["checked_bit_mismatch"] == 0
