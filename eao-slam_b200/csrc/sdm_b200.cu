@@ -605,7 +605,7 @@ int sdm_upload_keyframes(sdm_ctx* c, int n, const sdm_upload_desc* d)
             const sdm_upload_desc& u = d[i0 + i];
             UpStage& st = c->up[(first_stage + i) % kUpStages];
             CU(cudaMemsetAsync(c->A.cand_count + u.kf, 0, sizeof(int), c->s_compute));
-            sdm::k_pack<<<tile_grid(c), dim3(32, 8), 0, c->s_compute>>>(c->A, c->P, u.kf, st.im, st.grad, st.theta,
+            sdm::k_pack<<<dim3((c->cfg.width + sdm::kTileW - 1) / sdm::kTileW, (c->cfg.height + sdm::kTileH - 1) / sdm::kTileH), dim3(32, 8), 0, c->s_compute>>>(c->A, c->P, u.kf, st.im, st.grad, st.theta,
                                                                        u.edge ? st.edge : nullptr);
         }
         CU(cudaGetLastError());

@@ -306,15 +306,21 @@ __device__ __forceinline__ void fusion_accumulate(float d, float s, float& pjsj,
 // the candidate test of :454-456).  One thread per pixel, 32x8 tiles; one atomic per tile so a
 // tile's candidates stay contiguous (2-D locality for the scan kernel).
 // ---------------------------------------------------------------------------------------------
+#ifndef SDM_TILE_W
+#define SDM_TILE_W 32
+#endif
+constexpr int kTileW = SDM_TILE_W, kTileH = 256 / SDM_TILE_W;
+
 __global__ void __launch_bounds__(256) k_pack(DevArena A, DevParams P, int slot, const uint8_t* __restrict__ im,
                                               const float* __restrict__ grad, const float* __restrict__ theta,
                                               const int32_t* __restrict__ edge)
 {
     __shared__ int s_wcount[8];
     __shared__ int s_base;
-    const int x = blockIdx.x * 32 + threadIdx.x;
-    const int y = blockIdx.y * 8 + threadIdx.y;
+    // a block packs one tile of kTileW x kTileH pixels; a warp covers kTileW x (32 / kTileW) of them
     const int warp = threadIdx.y, lane = threadIdx.x;
+    const int x = blockIdx.x * kTileW + (lane % kTileW);
+    const int y = blockIdx.y * kTileH + warp * (32 / kTileW) + (lane / kTileW);
     const bool in = (x < P.W) && (y < P.H);
     bool is_cand = false;
     const size_t base = (size_t)slot * A.P;
@@ -1145,7 +1151,10 @@ k_pass2(DevArena A, DevParams P, const DevItem* __restrict__ items, const int* _
 // candidate-list variant (the default): pass 1 writes (rho,sigma) only at candidate pixels and k_pack zeroes
 // chk / pts of the whole plane, so pass 2 only has to visit the compacted candidates: one thread per
 // candidate, kLaneBlock candidates of one keyframe per block (same block -> item map as pass 1).
-__global__ void __launch_bounds__(kLaneBlock)
+#ifndef SDM_P2_MINB
+#define SDM_P2_MINB 10  // 48 registers: -8 % vs 72 registers (occupancy-bound gathers)
+#endif
+__global__ void __launch_bounds__(kLaneBlock, SDM_P2_MINB)
 k_pass2_cand(DevArena A, DevParams P, const DevItem* __restrict__ items, DevPlan plan, DevStats* stats)
 {
     __shared__ DevItem s_item;
