@@ -299,7 +299,7 @@ def main_ours(a, rank, world, local_rank):
     # as its pass 1 is queued; pass 2 of chunk k is queued right after pass 1 of chunk k+1 (its neighbours reach
     # at most N/2 keyframes into chunk k+1) and its depth_map_checked_/SemiDensePointSets_ follow.  Chunks whose
     # pass 2 needs halo planes of another rank wait for the exchange.  Raw C-ABI calls with prebuilt arguments.
-    CH = 20
+    CH = int(os.environ.get("SDM_BENCH_CHUNK", "10"))
     chunks = [owned[i:i + CH] for i in range(0, len(owned), CH)]
     chunk_items = [api.make_items(ch, sc.nbr_idx, sc.rot, sc.min_depth, sc.max_depth) for ch in chunks]
     chunk_need = [max(ch[-1], max(int(v) for s in ch for v in sc.nbr_idx[s])) for ch in chunks]
@@ -431,7 +431,7 @@ def main_ours(a, rank, world, local_rank):
     if e2e:
         line["e2e"] = {"value": tot_cands / e2e_max, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
                        "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": 1e3 * e2e_max,
-                       "api": "sdm_upload_keyframes / sdm_pass1 / sdm_pass2 / sdm_download_keyframes on pinned host planes, chunks of 20 keyframes"}
+                       "api": "sdm_upload_keyframes / sdm_pass1 / sdm_pass2 / sdm_download_keyframes on pinned host planes, chunks of " + str(CH) + " keyframes"}
     ctx.close()
     if world == 1 and not a.no_cpu_baseline:
         r = cpu_run(a.cpu_sample_kf, a.nbr, a.seed, a.intra, 1, 0)
