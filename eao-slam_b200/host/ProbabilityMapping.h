@@ -147,15 +147,20 @@ public:
             kf->SetEraseSemiDense();
         }
         if (!items.empty()) {
-            if (!Check(sdm_pass1(mCtx, (int)items.size(), items.data()), "sdm_pass1")) return;
+            if (!Flush() || !Check(sdm_pass1(mCtx, (int)items.size(), items.data()), "sdm_pass1")) return;
+            // depth_map_ / depth_sigma_ of the whole batch come back with one call (DMA straight from dense planes)
+            std::vector<sdm_download_desc> dl(owners.size());
             for (size_t i = 0; i < owners.size(); i++) {
                 KeyFrame* kf = owners[i];
-                const int s = mSlot[kf];
-                Check(sdm_download(mCtx, s, kf->depth_map_.ptr<float>(0), (size_t)kf->depth_map_.step,
-                                   kf->depth_sigma_.ptr<float>(0), (size_t)kf->depth_sigma_.step, NULL, 0, NULL, 0),
-                      "sdm_download");
-                kf->semidense_flag_ = true;  // :497
+                std::memset(&dl[i], 0, sizeof(dl[i]));
+                dl[i].kf = mSlot[kf];
+                dl[i].depth = kf->depth_map_.ptr<float>(0);   dl[i].depth_step = (size_t)kf->depth_map_.step;
+                dl[i].sigma = kf->depth_sigma_.ptr<float>(0); dl[i].sigma_step = (size_t)kf->depth_sigma_.step;
             }
+            if (!Check(sdm_download_keyframes(mCtx, (int)dl.size(), dl.data()), "sdm_download_keyframes") ||
+                !Check(sdm_synchronize(mCtx), "sdm_synchronize"))
+                return;
+            for (size_t i = 0; i < owners.size(); i++) owners[i]->semidense_flag_ = true;  // :497
         }
 
         // ---- pass 2 (:512-596)
@@ -182,15 +187,25 @@ public:
             kf->SetEraseSemiDense();
         }
         if (!items.empty()) {
-            if (!Check(sdm_pass2(mCtx, (int)items.size(), items.data()), "sdm_pass2")) return;
-            for (size_t i = 0; i < owners.size(); i++) {
-                KeyFrame* kf = owners[i];
-                std::unique_lock<std::mutex> lk(kf->mMutexSemiDensePoints);  // :701
-                Check(sdm_download(mCtx, mSlot[kf], NULL, 0, NULL, 0, kf->depth_map_checked_.ptr<float>(0),
-                                   (size_t)kf->depth_map_checked_.step, kf->SemiDensePointSets_.ptr<float>(0),
-                                   (size_t)kf->SemiDensePointSets_.step),
-                      "sdm_download");
-                kf->interKF_depth_flag_ = true;  // :554
+            if (!Flush() || !Check(sdm_pass2(mCtx, (int)items.size(), items.data()), "sdm_pass2")) return;
+            // depth_map_checked_ / SemiDensePointSets_ in groups of 16 keyframes, each group under the keyframes'
+            // mMutexSemiDensePoints like UpdateSemiDensePointSet (:701) so the viewer never sees a half-written set
+            for (size_t i0 = 0; i0 < owners.size(); i0 += 16) {
+                const size_t m = std::min<size_t>(16, owners.size() - i0);
+                std::vector<std::unique_lock<std::mutex> > locks;
+                std::vector<sdm_download_desc> dl(m);
+                for (size_t i = 0; i < m; i++) {
+                    KeyFrame* kf = owners[i0 + i];
+                    locks.emplace_back(kf->mMutexSemiDensePoints);
+                    std::memset(&dl[i], 0, sizeof(dl[i]));
+                    dl[i].kf = mSlot[kf];
+                    dl[i].checked = kf->depth_map_checked_.ptr<float>(0); dl[i].checked_step = (size_t)kf->depth_map_checked_.step;
+                    dl[i].points = kf->SemiDensePointSets_.ptr<float>(0); dl[i].points_step = (size_t)kf->SemiDensePointSets_.step;
+                }
+                if (!Check(sdm_download_keyframes(mCtx, (int)m, dl.data()), "sdm_download_keyframes") ||
+                    !Check(sdm_synchronize(mCtx), "sdm_synchronize"))
+                    return;
+                for (size_t i = 0; i < m; i++) owners[i0 + i]->interKF_depth_flag_ = true;  // :554
             }
         }
     }
@@ -270,7 +285,7 @@ public:
     void UpdateSemiDensePointSet(KeyFrame* kf)
     {
         std::unique_lock<std::mutex> lock(kf->mMutexSemiDensePoints);
-        if (!EnsureUploaded(kf)) return;
+        if (!EnsureUploaded(kf) || !Flush()) return;
         const int32_t s = mSlot[kf];
         float Tcw[12];
         PoseOf(kf, Tcw);
@@ -318,6 +333,8 @@ public:
             sdm_destroy(mCtx);
             mCtx = NULL;
             mSlot.clear();
+            mPending.clear();
+            mPendingKFs.clear();
             mCapacity = 0;
             mbResetRequested = false;
         }
@@ -348,6 +365,8 @@ private:
         sdm_destroy(mCtx);
         mCtx = NULL;
         mSlot.clear();
+        mPending.clear();
+        mPendingKFs.clear();
         mCfg.width = W;
         mCfg.height = H;
         mCfg.max_keyframes = capacity;
@@ -369,6 +388,8 @@ private:
 
     bool EnsureScratchContext() { return mCtx || CreateContext(64, 64, 1); }
 
+    // Reserve a device slot for kf and queue its planes for upload; the queue goes out as ONE
+    // sdm_upload_keyframes call (Flush) before the next library call that needs the planes.
     bool EnsureUploaded(KeyFrame* kf)
     {
         if (!mCtx && !CreateContext(kf->im_.cols, kf->im_.rows, 64)) return false;
@@ -377,25 +398,38 @@ private:
             std::cerr << "ProbabilityMapping(sdm_b200): device arena full (" << mCapacity << " keyframes)" << std::endl;
             return false;
         }
-        const int s = (int)mSlot.size();
-        const float K[4] = {kf->fx, kf->fy, kf->cx, kf->cy};
-        float Tcw[12];
-        PoseOf(kf, Tcw);
-        const bool edge = !kf->mEdgeIndex.empty();
-        if (!Check(sdm_upload_keyframe(mCtx, s, kf->im_.ptr<uint8_t>(0), (size_t)kf->im_.step,
-                                       kf->GradImg.ptr<float>(0), (size_t)kf->GradImg.step,
-                                       kf->GradTheta.ptr<float>(0), (size_t)kf->GradTheta.step,
-                                       edge ? kf->mEdgeIndex.ptr<int32_t>(0) : NULL, edge ? (size_t)kf->mEdgeIndex.step : 0, K, Tcw),
-                   "sdm_upload_keyframe"))
-            return false;
-        mSlot[kf] = s;
-        if (kf->semidense_flag_) PushDepth(kf);  // mapped in an earlier loop: its pass-1 planes are in the cv::Mats
+        sdm_upload_desc u;
+        std::memset(&u, 0, sizeof(u));
+        u.kf = (int32_t)mSlot.size();
+        u.im = kf->im_.ptr<uint8_t>(0);        u.im_step = (size_t)kf->im_.step;
+        u.grad = kf->GradImg.ptr<float>(0);    u.grad_step = (size_t)kf->GradImg.step;
+        u.theta = kf->GradTheta.ptr<float>(0); u.theta_step = (size_t)kf->GradTheta.step;
+        if (!kf->mEdgeIndex.empty()) { u.edge = kf->mEdgeIndex.ptr<int32_t>(0); u.edge_step = (size_t)kf->mEdgeIndex.step; }
+        u.K[0] = kf->fx; u.K[1] = kf->fy; u.K[2] = kf->cx; u.K[3] = kf->cy;
+        PoseOf(kf, u.Tcw);
+        mSlot[kf] = u.kf;
+        mPending.push_back(u);
+        mPendingKFs.push_back(kf);
+        return true;
+    }
+
+    bool Flush()
+    {
+        if (mPending.empty()) return true;
+        const bool ok = Check(sdm_upload_keyframes(mCtx, (int)mPending.size(), mPending.data()), "sdm_upload_keyframes");
+        std::vector<KeyFrame*> kfs;
+        kfs.swap(mPendingKFs);
+        mPending.clear();
+        if (!ok) return false;
+        // keyframes mapped in an earlier loop: their pass-1 planes live in the cv::Mats
+        for (size_t i = 0; i < kfs.size(); i++)
+            if (kfs[i]->semidense_flag_) PushDepth(kfs[i]);
         return true;
     }
 
     void PushDepth(KeyFrame* kf)
     {
-        if (!EnsureUploaded(kf)) return;
+        if (!EnsureUploaded(kf) || !Flush()) return;
         Check(sdm_upload_depth(mCtx, mSlot[kf], kf->depth_map_.ptr<float>(0), (size_t)kf->depth_map_.step,
                                kf->depth_sigma_.ptr<float>(0), (size_t)kf->depth_sigma_.step),
               "sdm_upload_depth");
@@ -403,7 +437,7 @@ private:
 
     bool SlotsFor(KeyFrame* a, KeyFrame* b, int& sa, int& sb)
     {
-        if (!EnsureUploaded(a) || !EnsureUploaded(b)) return false;
+        if (!EnsureUploaded(a) || !EnsureUploaded(b) || !Flush()) return false;
         sa = mSlot[a];
         sb = mSlot[b];
         return true;
@@ -483,6 +517,8 @@ private:
     sdm_config mCfg;
     int mN, mW, mH, mCapacity;
     std::unordered_map<KeyFrame*, int> mSlot;
+    std::vector<sdm_upload_desc> mPending;   // queued uploads (EnsureUploaded / Flush)
+    std::vector<KeyFrame*> mPendingKFs;
     bool mbFinishRequested, mbFinished, mbResetRequested;
     std::mutex mMutexFinish, mMutexReset;
 };

@@ -200,7 +200,7 @@ def test_against_committed_golden_vectors(golden_dir, tag, intra):
 
 def test_config4_1280x960_ten_neighbours_wide_range():
     """BASELINE config 4: 1280x960 keyframes, 10 neighbours, wide inverse-depth search range (long scans)."""
-    sc = synth.make_scene(12, 1280, 960, 10, seed=4, wide_range=True, workers=4)
+    sc = synth.make_scene(12, 1280, 960, 10, seed=4, wide_range=True)
     osc = run_oracle(sc)
     dev = run_device(sc)
     rep = compare_planes(dev, osc)
