@@ -1,0 +1,102 @@
+"""Edge cases of the path, CUDA (through the C-ABI) vs oracle: image sizes that are not multiples of the tile,
+keyframes without candidates, duplicate / degenerate poses (NaN epipolar lines), the largest neighbour count the ABI
+accepts, planes with out-of-range and non-finite values, ragged batches, slot re-use.  The reference has no tests for
+any of these; the oracle defines the behaviour (it never indexes out of bounds where the reference would)."""
+import json
+
+import numpy as np
+import pytest
+
+from helpers import compare_planes, run_device, run_oracle
+from sdmb200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _bit_equal(dev, osc, keys=("depth", "sigma", "checked", "points")):
+    ref = {"depth": osc.depth, "sigma": osc.sigma, "checked": osc.checked, "points": osc.points}
+    return {k: int((dev[k].view(np.uint32) != ref[k].view(np.uint32)).sum()) for k in keys}
+
+
+@pytest.mark.parametrize("W,H", [(333, 217), (64, 48), (17, 9)])
+def test_odd_image_sizes(W, H):
+    sc = synth.make_scene(8, W, H, 6, seed=3, contrast=0.9)
+    osc, dev = run_oracle(sc), run_device(sc)
+    assert _bit_equal(dev, osc) == {"depth": 0, "sigma": 0, "checked": 0, "points": 0}
+    assert dev["stats"]["candidates"] == osc.stats.as_dict()["candidates"]
+
+
+def test_keyframes_without_candidates_and_flat_neighbours():
+    """a flat keyframe has no candidate pixel (ragged batch); a flat neighbour never passes condition 1"""
+    sc = synth.make_scene(8, 160, 120, 6, seed=9)
+    for i in (2, 5):
+        sc.im[i][:] = 77
+        sc.grad[i][:] = 0
+        sc.theta[i][:] = 0
+    osc, dev = run_oracle(sc), run_device(sc)
+    assert _bit_equal(dev, osc) == {"depth": 0, "sigma": 0, "checked": 0, "points": 0}
+    assert (dev["depth"][2] == 0).all() and (dev["checked"][5] == 0).all()
+    assert (osc.depth[0] > 0).sum() > 100  # the other keyframes still reconstruct
+
+
+def test_duplicate_poses_give_nan_lines_not_faults():
+    """two keyframes at the same pose: t12 = 0, F12 = 0, a/b = NaN -> EpipolarSearch yields nothing for that pair"""
+    sc = synth.make_scene(8, 160, 120, 6, seed=10)
+    sc.Tcw[3] = sc.Tcw[4]
+    osc, dev = run_oracle(sc), run_device(sc)
+    assert _bit_equal(dev, osc) == {"depth": 0, "sigma": 0, "checked": 0, "points": 0}
+    assert np.isfinite(dev["depth"]).all()
+
+
+def test_sixteen_neighbours():
+    sc = synth.make_scene(18, 128, 96, api.SDM_MAX_NBR, seed=12, contrast=0.9)
+    osc, dev = run_oracle(sc), run_device(sc)
+    rep = compare_planes(dev, osc)
+    print(json.dumps(rep))
+    assert rep["depth_bit_mismatch"] == 0 and rep["checked_bit_mismatch"] == 0
+    with api.Context(width=128, height=96, max_keyframes=sc.n) as ctx:
+        ctx.upload_scene(sc)
+        items = api.make_items([0], sc.nbr_idx, sc.rot, sc.min_depth, sc.max_depth)
+        items[0].n_nbr = api.SDM_MAX_NBR + 1
+        with pytest.raises(api.SdmError) as e:
+            ctx.pass1(items)
+        assert e.value.code == -1
+
+
+def test_out_of_range_and_non_finite_planes():
+    """GradTheta outside [0,360), huge / NaN gradient magnitudes, extreme depth bounds: same decisions, no faults"""
+    sc = synth.make_scene(8, 160, 120, 6, seed=14)
+    rng = np.random.default_rng(0)
+    sc.theta[1] += 360.0                       # every angle one turn too large
+    sc.theta[2] -= 400.0
+    m = rng.random(sc.grad[3].shape) < 0.02
+    sc.grad[3][m] = np.nan
+    sc.theta[3][rng.random(sc.grad[3].shape) < 0.02] = np.inf
+    sc.grad[6][rng.random(sc.grad[6].shape) < 0.01] = 3e38
+    sc.min_depth[4], sc.max_depth[4] = 1e6, 1e-6     # search range = the whole epipolar line
+    sc.min_depth[5] = -2.0                           # mean - 2 sigma < 0 (no guard in the reference, Appendix A.9)
+    osc, dev = run_oracle(sc), run_device(sc)
+    diff = _bit_equal(dev, osc)
+    # NaN payloads may differ in their mantissa bits: compare NaN-ness there and bits elsewhere
+    for k, ref in (("depth", osc.depth), ("sigma", osc.sigma), ("checked", osc.checked)):
+        a, b = dev[k], ref
+        assert np.array_equal(np.isnan(a), np.isnan(b)), k
+        ok = ~np.isnan(b)
+        assert np.array_equal(a[ok].view(np.uint32), b[ok].view(np.uint32)), (k, diff)
+
+
+def test_slot_reuse_and_partial_batches():
+    """re-uploading other keyframes into used slots and running the passes keyframe by keyframe in arbitrary order"""
+    a = synth.make_scene(8, 160, 120, 6, seed=15)
+    b = synth.make_scene(8, 160, 120, 6, seed=16)
+    ob = run_oracle(b)
+    with api.Context(width=160, height=120, max_keyframes=8) as ctx:
+        run_device(a, ctx=ctx)                         # fills every slot and every output plane
+        ctx.upload_scene(b)                            # same slots, different keyframes
+        order = [5, 0, 7, 2, 1, 6, 3, 4]
+        for i in order:
+            ctx.pass1(api.make_items([i], b.nbr_idx, b.rot, b.min_depth, b.max_depth))
+        for i in reversed(order):
+            ctx.pass2(api.make_items([i], b.nbr_idx, b.rot, b.min_depth, b.max_depth))
+        dev = {k: np.stack([ctx.download(i)[k] for i in range(8)]) for k in ("depth", "sigma", "checked", "points")}
+    assert _bit_equal(dev, ob) == {"depth": 0, "sigma": 0, "checked": 0, "points": 0}
