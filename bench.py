@@ -390,6 +390,41 @@ def main_ours(a, rank, world, local_rank):
             e2e_step()
         barrier(); e2e_s = (time.perf_counter() - tt) / a.steps
         e2e = {"sec": e2e_s, "h2d": int(n_loc * W * H * 9), "d2h": int(len(owned) * W * H * 24)}
+        # the same loop for consumers that only need the surviving points (SaveSemiDensePoints / DrawSemiDense / CARV:
+        # sigma <= 0.02 and checked > 1e-6): upload + both passes + sdm_export_points instead of the dense downloads
+        if world == 1:
+            owned_arr = np.ascontiguousarray(owned, np.int32)
+            pts_buf = pinned(lib, (len(owned) * 40000,), np.dtype([("x", "f4"), ("y", "f4"), ("z", "f4"), ("pixel", "u4")]), keep)
+            tot = C.c_uint64()
+
+            t_x = [0.0]
+            # larger chunks than the dense-download loop: nothing slow hides the ramp-up / tail of small launches here
+            XCH = int(os.environ.get("SDM_BENCH_XCHUNK", "50"))
+            xchunks = [owned[i:i + XCH] for i in range(0, len(owned), XCH)]
+            xitems = [api.make_items(ch, sc.nbr_idx, sc.rot, sc.min_depth, sc.max_depth) for ch in xchunks]
+            xneed = [max(ch[-1], max(int(v) for s in ch for v in sc.nbr_idx[s])) for ch in xchunks]
+
+            def export_step():
+                t_x[0] = time.perf_counter()
+                nxt = 0
+                for k in range(len(xchunks)):  # uploads run ahead of pass 1, chunk by chunk
+                    if nxt <= xneed[k]:
+                        chk(lib.sdm_upload_keyframes(ctx.h, xneed[k] + 1 - nxt, up_ptr(nxt))); nxt = xneed[k] + 1
+                    chk(lib.sdm_pass1(ctx.h, len(xitems[k]), xitems[k]))
+                if nxt < n_loc:
+                    chk(lib.sdm_upload_keyframes(ctx.h, n_loc - nxt, up_ptr(nxt)))
+                chk(lib.sdm_pass2(ctx.h, len(items), items))
+                if dbg:
+                    t_a = time.perf_counter(); ctx.synchronize(); t_b = time.perf_counter()
+                    print(f"export_step: issue {1e3 * (t_a - t_x[0]):.2f} ms, passes done {1e3 * (t_b - t_x[0]):.2f} ms", file=sys.stderr)
+                chk(lib.sdm_export_points(ctx.h, owned_arr.size, owned_arr.ctypes.data_as(C.POINTER(C.c_int32)), 0.02,
+                                          pts_buf.ctypes.data, pts_buf.size, None, C.byref(tot)))
+            export_step()
+            tt = time.perf_counter()
+            for _ in range(a.steps):
+                export_step()
+            e2e["export_sec"] = (time.perf_counter() - tt) / a.steps
+            e2e["export_points"] = int(tot.value)
     if rank == 0:
         clocks.stop()
 
@@ -432,6 +467,11 @@ def main_ours(a, rank, world, local_rank):
         line["e2e"] = {"value": tot_cands / e2e_max, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
                        "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": 1e3 * e2e_max,
                        "api": "sdm_upload_keyframes / sdm_pass1 / sdm_pass2 / sdm_download_keyframes on pinned host planes, chunks of " + str(CH) + " keyframes"}
+        if "export_sec" in e2e:
+            line["e2e_point_export"] = {"value": tot_cands / e2e["export_sec"], "unit": UNIT, "ms_per_step": 1e3 * e2e["export_sec"],
+                                        "points_per_step": e2e["export_points"], "d2h_bytes_per_step": 16 * e2e["export_points"],
+                                        "note": "same loop, but the result leaves as the compacted point cloud of "
+                                                "sdm_export_points (sigma <= 0.02, checked > 1e-6) instead of four dense planes"}
     ctx.close()
     if world == 1 and not a.no_cpu_baseline:
         r = cpu_run(a.cpu_sample_kf, a.nbr, a.seed, a.intra, 1, 0)

@@ -103,6 +103,13 @@ struct EventRing {
     bool done(uint64_t id) { return !live(id) || cudaEventQuery(ev[id % ev.size()]) == cudaSuccess; }
 };
 
+// developer timeline (env SDM_TRACE=1): timing events around H2D batches / packs / passes, printed by sdm_synchronize
+struct TraceRec {
+    const char* what;
+    int n;
+    cudaEvent_t a, b;
+};
+
 struct KfState {
     bool uploaded = false;
     bool pass1_done = false;
@@ -126,10 +133,15 @@ struct DownStage {
     float* planes = nullptr;  // 2 * P floats
     uint64_t busy = 0;        // down-ring id
 };
+// Work orders of one pass: pinned host staging + its own device copy.  The H2D goes out on the COPY stream at
+// call time (in host order, i.e. ahead of the bulk uploads of later chunks; on the compute stream it would sit in
+// the copy engine behind them until the previous pass finished); the pass's kernels wait for it by event.
 struct ItemStage {
     void* host = nullptr;  // pinned: DevItem[cap] followed by int aux[3 * cap]
+    sdm::DevItem* d_items = nullptr;  // = the current pass's ItemStage buffers
+    int* d_aux = nullptr;
     int cap = 0;
-    uint64_t busy = 0;  // compute-ring id of the H2D copy that reads it
+    uint64_t busy = 0;  // compute-ring id after the last kernel that reads the device copy
 };
 
 }  // namespace
@@ -154,8 +166,8 @@ struct sdm_ctx {
     int ist_next = 0;
     int* h_count = nullptr;  // pinned, sdm_candidate_count
     // device work orders of the current pass
-    sdm::DevItem* d_items = nullptr;
-    int* d_aux = nullptr;  // slots[cap] | order_sparse[cap] | order_dense[cap]
+    sdm::DevItem* d_items = nullptr;  // = the current pass's ItemStage buffers
+    int* d_aux = nullptr;
     int* d_chunk_off = nullptr;
     int* d_counter = nullptr;
     int items_cap = 0;
@@ -164,15 +176,51 @@ struct sdm_ctx {
     int tmp_planes = 0;
     float* xfer = nullptr;  // 2 dense float planes (sdm_upload_depth staging)
     float* dbg = nullptr;   // 4 float planes + 1 byte plane (sdm_epipolar_search_plane)
+    void* exp_buf = nullptr;  // sdm_export_points: block counts | offsets | keyframe totals, then the compacted points
+    size_t exp_cap = 0;
+    sdm_point* exp_pts = nullptr;
+    size_t exp_pts_cap = 0;
     void* peer_rs[kMaxPeers] = {nullptr};
     int grid_pass1_warp = 0, grid_pass2 = 0, grid_intra = 0, n_sm = 0;  // persistent grids (blocks)
     long long launches = 0;
+    bool trace = false;
+    cudaEvent_t trace_base = nullptr;
+    std::vector<TraceRec> trace_recs;
     int scan_warp_per_pixel = 0;  // developer A/B knob (env SDM_SCAN=warp): the warp-per-pixel scan kernel
 };
 
 namespace {
 
 bool slot_ok(const sdm_ctx* c, int s) { return s >= 0 && s < (int)c->kf.size(); }
+
+void trace_begin(sdm_ctx* c, cudaStream_t s, const char* what, int n)
+{
+    if (!c->trace) return;
+    TraceRec r{what, n, nullptr, nullptr};
+    cudaEventCreate(&r.a);
+    cudaEventCreate(&r.b);
+    cudaEventRecord(r.a, s);
+    c->trace_recs.push_back(r);
+}
+void trace_end(sdm_ctx* c, cudaStream_t s)
+{
+    if (!c->trace) return;
+    cudaEventRecord(c->trace_recs.back().b, s);
+}
+void trace_dump(sdm_ctx* c)
+{
+    if (!c->trace || c->trace_recs.empty()) return;
+    for (auto& r : c->trace_recs) {
+        float t0 = 0, t1 = 0;
+        cudaEventElapsedTime(&t0, c->trace_base, r.a);
+        cudaEventElapsedTime(&t1, c->trace_base, r.b);
+        fprintf(stderr, "[sdm trace] %-8s n=%3d  %9.3f -> %9.3f ms\n", r.what, r.n, t0, t1);
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    c->trace_recs.clear();
+    cudaEventRecord(c->trace_base, c->s_compute);
+}
 
 // pitched plane copy; rows that are contiguous on both sides go out as ONE 1-D copy (cheaper to enqueue
 // and a single DMA descriptor), which is the common case for cv::Mat planes that are not ROIs
@@ -192,17 +240,15 @@ int ensure_items(sdm_ctx* c, int n)
     if (n <= c->items_cap) return SDM_OK;
     const int cap = std::max(n, std::max(64, c->items_cap * 2));
     CU(cudaStreamSynchronize(c->s_compute));
-    cudaFree(c->d_items); cudaFree(c->d_aux); cudaFree(c->d_chunk_off);
-    c->d_items = nullptr; c->d_aux = nullptr; c->d_chunk_off = nullptr;
+    cudaFree(c->d_chunk_off);
+    c->d_chunk_off = nullptr;
     c->items_cap = 0;
-    CU(cudaMalloc(&c->d_items, sizeof(sdm::DevItem) * cap));
-    CU(cudaMalloc(&c->d_aux, sizeof(int) * 3 * cap));
     CU(cudaMalloc(&c->d_chunk_off, sizeof(int) * (cap + 1)));
     c->items_cap = cap;
     return SDM_OK;
 }
 
-// a pinned staging buffer for n work orders that no in-flight copy still reads
+// staging for n work orders whose previous user (a pass) has finished
 int acquire_item_stage(sdm_ctx* c, int n, ItemStage** out)
 {
     ItemStage* st = nullptr;
@@ -217,10 +263,14 @@ int acquire_item_stage(sdm_ctx* c, int n, ItemStage** out)
     c->ist_next = (int)((st - c->ist) + 1) % kItemStages;
     if (st->cap < n) {
         if (st->host) CU(cudaFreeHost(st->host));
-        st->host = nullptr;
+        cudaFree(st->d_items);
+        cudaFree(st->d_aux);
+        st->host = nullptr; st->d_items = nullptr; st->d_aux = nullptr;
         st->cap = 0;
-        const int cap = std::max(n, 64);
+        const int cap = std::max(n, 32);
         CU(cudaMallocHost(&st->host, (sizeof(sdm::DevItem) + 3 * sizeof(int)) * cap));
+        CU(cudaMalloc(&st->d_items, sizeof(sdm::DevItem) * cap));
+        CU(cudaMalloc(&st->d_aux, sizeof(int) * 3 * cap));
         st->cap = cap;
     }
     *out = st;
@@ -292,9 +342,13 @@ int prepare_batch(sdm_ctx* c, int n, const sdm_item* items, bool pass2, bool poi
         need_down = std::max(need_down, pass2 ? k1.down_cp_id : k1.down_ds_id);  // planes this pass overwrites
     }
     RC(c->r_down.wait(c->s_compute, need_down));  // (uploads need no wait: k_pack runs on s_compute itself)
-    CU(cudaMemcpyAsync(c->d_items, h_items, sizeof(sdm::DevItem) * n, cudaMemcpyHostToDevice, c->s_compute));
-    CU(cudaMemcpyAsync(c->d_aux, h_aux, sizeof(int) * 3 * n, cudaMemcpyHostToDevice, c->s_compute));
-    RC(c->r_compute.record(c->s_compute, &st->busy));
+    CU(cudaMemcpyAsync(st->d_items, h_items, sizeof(sdm::DevItem) * n, cudaMemcpyHostToDevice, c->s_copy));
+    CU(cudaMemcpyAsync(st->d_aux, h_aux, sizeof(int) * 3 * n, cudaMemcpyHostToDevice, c->s_copy));
+    uint64_t h2d = 0;
+    RC(c->r_copy.record(c->s_copy, &h2d));
+    RC(c->r_copy.wait(c->s_compute, h2d));
+    c->d_items = st->d_items;
+    c->d_aux = st->d_aux;
     b->d_slots = c->d_aux;
     b->d_order_sparse = c->d_aux + n;
     b->d_order_dense = c->d_aux + 2 * n;
@@ -302,11 +356,13 @@ int prepare_batch(sdm_ctx* c, int n, const sdm_item* items, bool pass2, bool poi
     return SDM_OK;
 }
 
-// after the pass's kernels are enqueued: every referenced slot is busy until this point of s_compute
-int finish_batch(sdm_ctx* c, int n, const sdm_item* items)
+// after the pass's kernels are enqueued: every referenced slot (and the work-order staging) is busy until this
+// point of s_compute
+int finish_batch(sdm_ctx* c, int n, const sdm_item* items, const Batch& b)
 {
     uint64_t id = 0;
     RC(c->r_compute.record(c->s_compute, &id));
+    b.stage->busy = id;
     for (int i = 0; i < n; ++i) {
         c->kf[items[i].kf].comp_id = id;
         for (int j = 0; j < items[i].n_nbr; ++j) c->kf[items[i].nbr[j]].comp_id = id;
@@ -349,16 +405,18 @@ int run_intra(sdm_ctx* c, const int* d_slots, int n, bool check, bool grow)
     return SDM_OK;
 }
 
-int single_slot_array(sdm_ctx* c, int slot, int** d_slots)
+int single_slot_array(sdm_ctx* c, int slot, int** d_slots, ItemStage** stage)
 {
-    RC(ensure_items(c, 1));
     ItemStage* st;
     RC(acquire_item_stage(c, 1, &st));
     int* h = (int*)st->host;
     h[0] = slot;
-    CU(cudaMemcpyAsync(c->d_aux, h, sizeof(int), cudaMemcpyHostToDevice, c->s_compute));
-    RC(c->r_compute.record(c->s_compute, &st->busy));
-    *d_slots = c->d_aux;
+    CU(cudaMemcpyAsync(st->d_aux, h, sizeof(int), cudaMemcpyHostToDevice, c->s_copy));
+    uint64_t h2d = 0;
+    RC(c->r_copy.record(c->s_copy, &h2d));
+    RC(c->r_copy.wait(c->s_compute, h2d));
+    *d_slots = st->d_aux;
+    *stage = st;
     return SDM_OK;
 }
 
@@ -403,11 +461,14 @@ void sdm_destroy(sdm_ctx* c)
     cudaFree(c->A.rs); cudaFree(c->A.chk); cudaFree(c->A.pts); cudaFree(c->A.dpl); cudaFree(c->A.spl); cudaFree(c->A.rs2);
     for (auto& s : c->up) { cudaFree(s.im); cudaFree(s.grad); cudaFree(s.theta); cudaFree(s.edge); }
     for (auto& s : c->down) cudaFree(s.planes);
-    for (auto& s : c->ist)
+    for (auto& s : c->ist) {
         if (s.host) cudaFreeHost(s.host);
+        cudaFree(s.d_items);
+        cudaFree(s.d_aux);
+    }
     if (c->h_count) cudaFreeHost(c->h_count);
-    cudaFree(c->d_items); cudaFree(c->d_aux); cudaFree(c->d_chunk_off); cudaFree(c->d_counter); cudaFree(c->d_stats);
-    cudaFree(c->tmp_rs); cudaFree(c->xfer); cudaFree(c->dbg);
+    cudaFree(c->d_chunk_off); cudaFree(c->d_counter); cudaFree(c->d_stats);
+    cudaFree(c->tmp_rs); cudaFree(c->xfer); cudaFree(c->dbg); cudaFree(c->exp_buf); cudaFree(c->exp_pts);
     for (cudaEvent_t e : {c->ev_p1[0], c->ev_p1[1], c->ev_p2[0], c->ev_p2[1], c->ev_p1_scan})
         if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : c->marks)
@@ -434,6 +495,7 @@ static int create_impl(sdm_ctx* c)
     const size_t n = (size_t)cfg.max_keyframes;
     c->npix = P;
     if (const char* e = getenv("SDM_SCAN")) c->scan_warp_per_pixel = (strcmp(e, "warp") == 0);
+    if (const char* e = getenv("SDM_TRACE")) c->trace = (e[0] == '1');
     c->kf.assign(n, KfState());
     sdm::DevParams& D = c->P;
     D.W = cfg.width;
@@ -507,6 +569,10 @@ static int create_impl(sdm_ctx* c)
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sdm::k_intra_cand, sdm::kChunk, 0));
     c->grid_intra = std::max(1, occ) * prop.multiProcessorCount;
     CU(cudaStreamSynchronize(c->s_compute));
+    if (c->trace) {
+        CU(cudaEventCreate(&c->trace_base));
+        CU(cudaEventRecord(c->trace_base, c->s_compute));
+    }
     return SDM_OK;
 }
 
@@ -539,6 +605,7 @@ int sdm_synchronize(sdm_ctx* c)
     CU(cudaStreamSynchronize(c->s_copy));
     CU(cudaStreamSynchronize(c->s_compute));
     CU(cudaStreamSynchronize(c->s_down));
+    trace_dump(c);
     return SDM_OK;
 }
 
@@ -587,6 +654,7 @@ int sdm_upload_keyframes(sdm_ctx* c, int n, const sdm_upload_desc* d)
         uint64_t busy = 0, need_down = 0;
         for (int i = 0; i < m; ++i) busy = std::max(busy, c->up[(first_stage + i) % kUpStages].busy);
         RC(c->r_compute.wait(c->s_copy, busy));
+        trace_begin(c, c->s_copy, "h2d", m);
         for (int i = 0; i < m; ++i) {
             const sdm_upload_desc& u = d[i0 + i];
             UpStage& st = c->up[(first_stage + i) % kUpStages];
@@ -596,11 +664,13 @@ int sdm_upload_keyframes(sdm_ctx* c, int n, const sdm_upload_desc* d)
             if (u.edge) RC(copy2d(st.edge, row, u.edge, u.edge_step, row, H, cudaMemcpyHostToDevice, c->s_copy));
             need_down = std::max(need_down, std::max(c->kf[u.kf].down_ds_id, c->kf[u.kf].down_cp_id));
         }
+        trace_end(c, c->s_copy);
         uint64_t h2d = 0;
         RC(c->r_copy.record(c->s_copy, &h2d));
         // ... packing + candidate compaction on the compute stream, behind every pass already queued on the slots
         RC(c->r_copy.wait(c->s_compute, h2d));
         RC(c->r_down.wait(c->s_compute, need_down));
+        trace_begin(c, c->s_compute, "pack", m);
         for (int i = 0; i < m; ++i) {
             const sdm_upload_desc& u = d[i0 + i];
             UpStage& st = c->up[(first_stage + i) % kUpStages];
@@ -609,6 +679,7 @@ int sdm_upload_keyframes(sdm_ctx* c, int n, const sdm_upload_desc* d)
                                                                        u.edge ? st.edge : nullptr);
         }
         CU(cudaGetLastError());
+        trace_end(c, c->s_compute);
         c->launches += m;
         uint64_t id = 0;
         RC(c->r_compute.record(c->s_compute, &id));
@@ -699,6 +770,7 @@ int sdm_pass1(sdm_ctx* c, int n, const sdm_item* items)
     const sdm::DevPlan plan = make_plan(c, nullptr, n);
     sdm::k_plan<<<1, 1024, 0, c->s_compute>>>(plan, c->d_items, c->A.cand_count, c->d_stats);
     CU(cudaEventRecord(c->ev_p1[0], c->s_compute));
+    trace_begin(c, c->s_compute, "pass1", n);
     if (c->scan_warp_per_pixel)
         sdm::k_pass1<<<c->grid_pass1_warp, sdm::kPass1Warps * 32, 0, c->s_compute>>>(c->A, c->P, c->d_items, plan, c->d_stats);
     else {
@@ -726,8 +798,9 @@ int sdm_pass1(sdm_ctx* c, int n, const sdm_item* items)
         c->launches += 2;
     }
     CU(cudaEventRecord(c->ev_p1[1], c->s_compute));
+    trace_end(c, c->s_compute);
     c->p1_timed = true;
-    RC(finish_batch(c, n, items));
+    RC(finish_batch(c, n, items, b));
     for (int i = 0; i < n; ++i) c->kf[items[i].kf].pass1_done = true;
     return SDM_OK;
 }
@@ -754,7 +827,7 @@ static int pass2_impl(sdm_ctx* c, int n, const sdm_item* items, int points_only)
     CU(cudaGetLastError());
     CU(cudaEventRecord(c->ev_p2[1], c->s_compute));
     c->p2_timed = true;
-    return finish_batch(c, n, items);
+    return finish_batch(c, n, items, b);
 }
 
 int sdm_pass2(sdm_ctx* c, int n, const sdm_item* items)
@@ -868,6 +941,76 @@ int sdm_upload_depth(sdm_ctx* c, int kf, const float* depth, size_t depth_step, 
     return SDM_OK;
 }
 
+// ---- point-cloud export --------------------------------------------------------------------------
+int sdm_export_points(sdm_ctx* c, int n, const int32_t* kfs, double sigma_max, sdm_point* out, size_t capacity,
+                      uint64_t* counts, uint64_t* total)
+{
+    if (!c || (n > 0 && !kfs) || !total || (capacity > 0 && !out)) return fail(SDM_ERR_ARG, "sdm_export_points: null argument");
+    *total = 0;
+    if (n <= 0) return SDM_OK;
+    uint64_t need = 0;
+    for (int i = 0; i < n; ++i) {
+        if (!slot_ok(c, kfs[i])) return fail(SDM_ERR_ARG, "keyframe slot %d out of range", kfs[i]);
+        if (!c->kf[kfs[i]].pass1_done) return fail(SDM_ERR_STATE, "slot %d has no depth planes", kfs[i]);
+        need = std::max(need, c->kf[kfs[i]].comp_id);
+    }
+    CU(cudaSetDevice(c->cfg.device));
+    cudaStream_t s = c->s_down;  // reads only; ordered after the last kernel on the slots
+    RC(c->r_compute.wait(s, need));
+    const int bpk = (int)((c->npix + sdm::kExportBlock - 1) / sdm::kExportBlock);
+    const size_t nb = (size_t)n * bpk;
+    if (nb > 0x7fffffffULL) return fail(SDM_ERR_ARG, "export batch too large");
+    // scratch layout: slots[n] | counts[nb] | offsets[nb + 1] (u64) | kf_totals[n] (u64)
+    const size_t off_counts = ((size_t)n * 4 + 7) & ~(size_t)7;
+    const size_t off_offsets = (off_counts + nb * 4 + 7) & ~(size_t)7;
+    const size_t off_totals = off_offsets + (nb + 1) * 8;
+    const size_t bytes = off_totals + (size_t)n * 8;
+    if (c->exp_cap < bytes) {
+        CU(cudaStreamSynchronize(s));
+        cudaFree(c->exp_buf);
+        c->exp_buf = nullptr; c->exp_cap = 0;
+        CU(cudaMalloc(&c->exp_buf, bytes));
+        c->exp_cap = bytes;
+    }
+    char* base = (char*)c->exp_buf;
+    int* d_slots = (int*)base;
+    int* d_counts = (int*)(base + off_counts);
+    unsigned long long* d_offsets = (unsigned long long*)(base + off_offsets);
+    unsigned long long* d_totals = (unsigned long long*)(base + off_totals);
+    const float sigma_gt = sdm::thr_gt(sigma_max);
+    CU(cudaMemcpyAsync(d_slots, kfs, (size_t)n * 4, cudaMemcpyHostToDevice, s));
+    sdm::k_export_count<<<(unsigned)nb, sdm::kExportBlock, 0, s>>>(c->A, c->P, d_slots, sigma_gt, bpk, d_counts);
+    sdm::k_export_scan<<<1, 1024, 0, s>>>(d_counts, (int)nb, bpk, d_offsets, d_totals);
+    CU(cudaGetLastError());
+    c->launches += 2;
+    std::vector<unsigned long long> h_tot((size_t)n + 1);
+    CU(cudaMemcpyAsync(h_tot.data(), d_totals, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(&h_tot[n], d_offsets + nb, 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    *total = (uint64_t)h_tot[n];
+    if (counts)
+        for (int i = 0; i < n; ++i) counts[i] = (uint64_t)h_tot[i];
+    const size_t m = (size_t)std::min<uint64_t>(*total, capacity);
+    if (m > 0) {
+        if (c->exp_pts_cap < m) {
+            cudaFree(c->exp_pts);
+            c->exp_pts = nullptr; c->exp_pts_cap = 0;
+            CU(cudaMalloc(&c->exp_pts, m * sizeof(sdm_point)));
+            c->exp_pts_cap = m;
+        }
+        sdm::k_export_scatter<<<(unsigned)nb, sdm::kExportBlock, 0, s>>>(c->A, c->P, d_slots, sigma_gt, bpk, d_offsets, c->exp_pts,
+                                                                        (unsigned long long)m);
+        CU(cudaGetLastError());
+        c->launches++;
+        CU(cudaMemcpyAsync(out, c->exp_pts, m * sizeof(sdm_point), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+    }
+    uint64_t id = 0;
+    RC(c->r_down.record(s, &id));
+    for (int i = 0; i < n; ++i) c->kf[kfs[i]].down_ds_id = c->kf[kfs[i]].down_cp_id = id;
+    return SDM_OK;
+}
+
 // ---- multi-GPU -----------------------------------------------------------------------------------
 int sdm_depth_plane_ptr(sdm_ctx* c, int kf, void** dev_ptr, size_t* bytes)
 {
@@ -970,7 +1113,7 @@ static int single_pair_item(sdm_ctx* c, int kf1, int kf2, float mind, float maxd
     it.max_depth = maxd;
     Batch b;
     RC(prepare_batch(c, 1, &it, false, false, &b));
-    return finish_batch(c, 1, &it);  // the debug kernels follow on s_compute right away
+    return finish_batch(c, 1, &it, b);  // the debug kernels follow on s_compute right away (callers synchronise)
 }
 
 static int ensure_dbg(sdm_ctx* c)
@@ -1086,10 +1229,13 @@ static int intra_single(sdm_ctx* c, int kf, bool check, bool grow)
     CU(cudaSetDevice(c->cfg.device));
     RC(c->r_down.wait(c->s_compute, k.down_ds_id));
     int* d_slots;
-    RC(single_slot_array(c, kf, &d_slots));
+    ItemStage* st;
+    RC(single_slot_array(c, kf, &d_slots, &st));
     RC(run_intra(c, d_slots, 1, check, grow));
     k.split_stale = false;  // the second stencil stage rewrites dpl / spl from the final (rho,sigma) plane
-    return c->r_compute.record(c->s_compute, &k.comp_id);
+    RC(c->r_compute.record(c->s_compute, &k.comp_id));
+    st->busy = k.comp_id;
+    return SDM_OK;
 }
 
 int sdm_intra_check(sdm_ctx* c, int kf) { return intra_single(c, kf, true, false); }

@@ -1182,6 +1182,124 @@ k_pass2_cand(DevArena A, DevParams P, const DevItem* __restrict__ items, DevPlan
     if (stats && (threadIdx.x & 31) == 0 && n_checked) atomicAdd(&stats->checked, (unsigned long long)n_checked);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Point-cloud export: the filter every consumer of the semi-dense map applies —
+// SaveSemiDensePoints (:167-168), MapDrawer::DrawSemiDense (MapDrawer.cc:104-106), the CARV entry
+// (SFMTranscriptInterface_ORBSLAM.cpp:272) — `skip if depth_sigma_ > sigma_max; keep if
+// depth_map_checked_ > 0.000001`, as a stream compaction on the device: keyframes in list order,
+// pixels in raster order (the order the reference's loops emit), so only the surviving points
+// cross PCIe instead of four dense planes.  Three steps: per-block counts, one-block exclusive scan,
+// ordered scatter.  A block handles kExportBlock consecutive pixels of one keyframe.
+// ---------------------------------------------------------------------------------------------
+constexpr int kExportBlock = 1024;
+
+__device__ __forceinline__ bool export_keep(const DevArena& A, const DevParams& P, size_t base, size_t p, float sigma_gt)
+{
+    const float sg = A.rs[base + p].y;
+    if (sg > sigma_gt) return false;  // (double)sigma > sigma_max, as a float threshold
+    return A.chk[base + p] > P.eps_gt;
+}
+
+__global__ void __launch_bounds__(kExportBlock)
+k_export_count(DevArena A, DevParams P, const int* __restrict__ slots, float sigma_gt, int blocks_per_kf, int* __restrict__ counts)
+{
+    __shared__ int s_warp[32];
+    const int kfi = blockIdx.x / blocks_per_kf, blk = blockIdx.x % blocks_per_kf;
+    const size_t base = (size_t)slots[kfi] * A.P;
+    const size_t p = (size_t)blk * kExportBlock + threadIdx.x;
+    const bool keep = p < A.P && export_keep(A, P, base, p, sigma_gt);
+    const unsigned bal = __ballot_sync(SDM_FULL, keep);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int v = s_warp[threadIdx.x];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(SDM_FULL, v, off);
+        if (threadIdx.x == 0) counts[blockIdx.x] = v;
+    }
+}
+
+// exclusive scan of n block counts (one block); offsets[n] = total; per-keyframe totals
+__global__ void __launch_bounds__(1024)
+k_export_scan(const int* __restrict__ counts, int n, int blocks_per_kf, unsigned long long* __restrict__ offsets,
+              unsigned long long* __restrict__ kf_totals)
+{
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_base;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_base = 0ULL;
+    __syncthreads();
+    for (int i0 = 0; i0 < n; i0 += 1024) {
+        const int i = i0 + tid;
+        const unsigned long long c = i < n ? (unsigned long long)counts[i] : 0ULL;
+        unsigned long long incl = c;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const unsigned long long v = __shfl_up_sync(SDM_FULL, incl, off);
+            if (lane >= off) incl += v;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = s_warp[lane];
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const unsigned long long v = __shfl_up_sync(SDM_FULL, w, off);
+                if (lane >= off) w += v;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        if (i < n) offsets[i] = s_base + (warp ? s_warp[warp - 1] : 0ULL) + incl - c;
+        __syncthreads();
+        if (tid == 0) s_base += s_warp[31];
+        __syncthreads();
+    }
+    if (tid == 0) offsets[n] = s_base;
+    __syncthreads();
+    // per-keyframe totals from the offsets of each keyframe's first block
+    const int n_kf = n / blocks_per_kf;
+    for (int k = tid; k < n_kf; k += 1024)
+        kf_totals[k] = offsets[(k + 1) * blocks_per_kf] - offsets[k * blocks_per_kf];
+}
+
+__global__ void __launch_bounds__(kExportBlock)
+k_export_scatter(DevArena A, DevParams P, const int* __restrict__ slots, float sigma_gt, int blocks_per_kf,
+                 const unsigned long long* __restrict__ offsets, sdm_point* __restrict__ out, unsigned long long capacity)
+{
+    __shared__ int s_warp[32];
+    const int kfi = blockIdx.x / blocks_per_kf, blk = blockIdx.x % blocks_per_kf;
+    const size_t base = (size_t)slots[kfi] * A.P;
+    const size_t p = (size_t)blk * kExportBlock + threadIdx.x;
+    const bool keep = p < A.P && export_keep(A, P, base, p, sigma_gt);
+    const unsigned bal = __ballot_sync(SDM_FULL, keep);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int v = s_warp[threadIdx.x];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int o = __shfl_up_sync(SDM_FULL, v, off);
+            if (lane >= off) v += o;
+        }
+        s_warp[threadIdx.x] = v;  // inclusive over warps
+    }
+    __syncthreads();
+    if (keep) {
+        const unsigned long long pos = offsets[blockIdx.x] + (unsigned long long)((warp ? s_warp[warp - 1] : 0) +
+                                                                                   __popc(bal & ((1u << lane) - 1u)));
+        if (pos < capacity) {
+            sdm_point q;
+            q.x = A.pts[3 * (base + p) + 0];
+            q.y = A.pts[3 * (base + p) + 1];
+            q.z = A.pts[3 * (base + p) + 2];
+            q.pixel = ((uint32_t)(p / P.W) << 16) | (uint32_t)(p % P.W);
+            out[pos] = q;
+        }
+    }
+}
+
 // (rho, sigma) float2 plane -> two dense float planes (download staging), and back
 __global__ void k_split_rs(const float2* __restrict__ rs, float* __restrict__ d, float* __restrict__ s, size_t n)
 {

@@ -71,7 +71,7 @@ class Stats(C.Structure):
 EXPORTS = [
     "sdm_default_config", "sdm_create", "sdm_destroy", "sdm_last_error", "sdm_version", "sdm_synchronize",
     "sdm_get_stats", "sdm_host_alloc", "sdm_host_free", "sdm_upload_keyframe", "sdm_set_pose",
-    "sdm_set_intrinsics", "sdm_candidate_count", "sdm_pass1", "sdm_pass2", "sdm_update_points", "sdm_download", "sdm_download_async", "sdm_upload_keyframes", "sdm_download_keyframes",
+    "sdm_set_intrinsics", "sdm_candidate_count", "sdm_pass1", "sdm_pass2", "sdm_update_points", "sdm_download", "sdm_download_async", "sdm_upload_keyframes", "sdm_download_keyframes", "sdm_export_points",
     "sdm_upload_depth", "sdm_depth_plane_ptr", "sdm_export_arena", "sdm_import_peer_arena", "sdm_pull_halo",
     "sdm_mark_pass1_done", "sdm_pair_geometry", "sdm_stereo_search_constraints", "sdm_search_range",
     "sdm_epipolar_search", "sdm_epipolar_search_plane", "sdm_fuse", "sdm_intra_check", "sdm_intra_grow",
@@ -113,6 +113,7 @@ def load() -> C.CDLL:
     lib.sdm_download_async.argtypes = [vp, C.c_int, vp, sz, vp, sz, vp, sz, vp, sz]
     lib.sdm_upload_keyframes.argtypes = [vp, C.c_int, C.POINTER(UploadDesc)]
     lib.sdm_download_keyframes.argtypes = [vp, C.c_int, C.POINTER(DownloadDesc)]
+    lib.sdm_export_points.argtypes = [vp, C.c_int, ip, C.c_double, vp, sz, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.sdm_upload_depth.argtypes = [vp, C.c_int, vp, sz, vp, sz]
     lib.sdm_depth_plane_ptr.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(sz)]
     lib.sdm_export_arena.argtypes = [vp, vp, C.POINTER(sz)]
@@ -298,6 +299,21 @@ class Context:
             c.ctypes.data if c is not None else None, c.strides[0] if c is not None else 0,
             p.ctypes.data if p is not None else None, p.strides[0] if p is not None else 0))
         return res
+
+    def export_points(self, slots, sigma_max=0.02, capacity=None):
+        """compacted point cloud of keyframes `slots`: structured array (x, y, z, pixel), per-keyframe counts"""
+        a = np.ascontiguousarray(slots, np.int32)
+        counts = np.zeros(a.size, np.uint64)
+        total = C.c_uint64()
+        ip, up = C.POINTER(C.c_int32), C.POINTER(C.c_uint64)
+        if capacity is None:  # count first
+            self._chk(self.lib.sdm_export_points(self.h, a.size, a.ctypes.data_as(ip), sigma_max, None, 0,
+                                                 counts.ctypes.data_as(up), C.byref(total)))
+            capacity = int(total.value)
+        pts = np.zeros(max(capacity, 1), np.dtype([("x", "f4"), ("y", "f4"), ("z", "f4"), ("pixel", "u4")]))
+        self._chk(self.lib.sdm_export_points(self.h, a.size, a.ctypes.data_as(ip), sigma_max, pts.ctypes.data, capacity,
+                                             counts.ctypes.data_as(up), C.byref(total)))
+        return pts[:min(capacity, int(total.value))], counts, int(total.value)
 
     def upload_depth(self, slot, depth, sigma):
         d, s = _f32(depth), _f32(sigma)

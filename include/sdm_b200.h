@@ -168,6 +168,21 @@ int sdm_download_keyframes(sdm_ctx* ctx, int n, const sdm_download_desc* desc);
 int sdm_upload_depth(sdm_ctx* ctx, int kf, const float* depth, size_t depth_step,
                      const float* sigma, size_t sigma_step);
 
+/* ---- point-cloud export ---------------------------------------------------- */
+/* replaces: the filter loop of SaveSemiDensePoints (ProbabilityMapping.cc:159-186), MapDrawer::DrawSemiDense
+ * (MapDrawer.cc:99-117) and the CARV point entry (SFMTranscriptInterface_ORBSLAM.cpp:268-290): for the n
+ * keyframes in list order and their pixels in raster order, `if (depth_sigma_ > sigma_max) continue;
+ * if (depth_map_checked_ > 0.000001) emit SemiDensePointSets_(y,x)`.  Compacted on the device, so only the
+ * surviving points cross PCIe.  `pixel` = (y << 16) | x lets the caller fetch the colour from its own rgb_.
+ * Writes min(total, capacity) points to out (out may be NULL with capacity 0 to count only), the surviving
+ * count of every keyframe to counts[n] (may be NULL) and their sum to *total.  Blocking. */
+typedef struct {
+    float x, y, z;
+    uint32_t pixel;
+} sdm_point;
+int sdm_export_points(sdm_ctx* ctx, int n, const int32_t* kfs, double sigma_max, sdm_point* out, size_t capacity,
+                      uint64_t* counts, uint64_t* total);
+
 /* ---- multi-GPU: pass-1 planes of halo keyframes over NVLink (the dependency of :1202-1249) -- */
 /* device pointer + byte size of the (rho, sigma) float2 plane of a slot, for NCCL / peer copies */
 int sdm_depth_plane_ptr(sdm_ctx* ctx, int kf, void** dev_ptr, size_t* bytes);

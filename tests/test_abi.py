@@ -42,14 +42,16 @@ def test_struct_layouts_match_header():
     prog = r'''
 #include <stdio.h>
 #include "sdm_b200.h"
-int main(void){ printf("%zu %zu %zu %zu %zu %zu\n", sizeof(sdm_config), sizeof(sdm_item), sizeof(sdm_pair_geometry_t),
- sizeof(sdm_hypothesis), sizeof(sdm_stats), sizeof(sdm_timing)); return 0; }'''
+int main(void){ printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(sdm_config), sizeof(sdm_item), sizeof(sdm_pair_geometry_t),
+ sizeof(sdm_hypothesis), sizeof(sdm_stats), sizeof(sdm_timing), sizeof(sdm_upload_desc), sizeof(sdm_download_desc),
+ sizeof(sdm_point)); return 0; }'''
     with tempfile.TemporaryDirectory() as d:
         open(os.path.join(d, "t.c"), "w").write(prog)
         subprocess.run(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"),
                         os.path.join(d, "t.c")], check=True)
         out = subprocess.run([os.path.join(d, "t")], capture_output=True, text=True, check=True).stdout.split()
-    want = [C.sizeof(x) for x in (api.Config, api.Item, api.PairGeometry, api.Hypothesis, api.Stats, api.Timing)]
+    want = [C.sizeof(x) for x in (api.Config, api.Item, api.PairGeometry, api.Hypothesis, api.Stats, api.Timing,
+                                  api.UploadDesc, api.DownloadDesc)] + [16]
     assert [int(v) for v in out] == want
 
 

@@ -247,3 +247,29 @@ def test_non_default_thresholds(small_scene):
     rep = compare_planes(dev, osc)
     print(json.dumps(rep))
     assert rep["depth_bit_mismatch"] == 0 and rep["checked_bit_mismatch"] == 0
+
+
+def test_point_cloud_export_matches_the_consumers_filter(small_scene, small_oracle):
+    """sdm_export_points == the loop of SaveSemiDensePoints (:159-186) / DrawSemiDense over the oracle's planes:
+    keyframes in list order, raster order inside, `sigma > s -> skip`, `checked > 1e-6 -> emit`."""
+    sc, osc = small_scene, small_oracle
+    H, W = sc.shape
+    with api.Context(width=W, height=H, max_keyframes=sc.n) as ctx:
+        run_device(sc, ctx=ctx)
+        order = [4, 0, 7, 2]
+        for smax in (0.02, 0.005, 1e9):
+            pts, counts, total = ctx.export_points(order, smax)
+            exp_xyz, exp_pix, exp_counts = [], [], []
+            for i in order:
+                keep = ~(osc.sigma[i].astype(np.float64) > smax) & (osc.checked[i].astype(np.float64) > 0.000001)
+                ys, xs = np.nonzero(keep)  # raster order
+                exp_xyz.append(osc.points[i][ys, xs]); exp_pix.append((ys.astype(np.uint32) << 16) | xs.astype(np.uint32))
+                exp_counts.append(len(ys))
+            exp_xyz, exp_pix = np.concatenate(exp_xyz), np.concatenate(exp_pix)
+            assert total == len(exp_pix) and list(counts) == exp_counts
+            got = np.stack([pts["x"], pts["y"], pts["z"]], axis=1)
+            assert np.array_equal(got.view(np.uint32), exp_xyz.view(np.uint32)) and np.array_equal(pts["pixel"], exp_pix)
+        assert exp_counts[0] > 1000
+        # a too-small buffer is filled to capacity and the full count is still reported
+        pts, counts, total = ctx.export_points(order, 0.02, capacity=100)
+        assert len(pts) == 100 and total > 100
