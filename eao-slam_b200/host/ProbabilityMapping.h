@@ -310,6 +310,36 @@ public:
         }
     }
 
+    // The point filter of SaveSemiDensePoints (:156-186), MapDrawer::DrawSemiDense (MapDrawer.cc:88-117) and the CARV
+    // entry: finished keyframes in Map order, pixels in raster order, `sigma > s -> skip; checked > 1e-6 -> emit`,
+    // compacted on the device.  pts[k].pixel = (y << 16) | x indexes the keyframe's rgb_ for the colour; counts[i] is
+    // the number of points of kfs[i].  Returns the number of points.
+    size_t ExportSemiDensePoints(double sigma, std::vector<sdm_point>& pts, std::vector<KeyFrame*>* kfs_out = NULL,
+                                 std::vector<uint64_t>* counts_out = NULL)
+    {
+        pts.clear();
+        std::vector<KeyFrame*> vpKFs = mpMap->GetAllKeyFrames(), kfs;
+        std::vector<int32_t> slots;
+        for (size_t i = 0; i < vpKFs.size(); i++) {
+            KeyFrame* kf = vpKFs[i];
+            if (kf->isBad() || !kf->semidense_flag_ || !kf->interKF_depth_flag_ || !mSlot.count(kf)) continue;  // :159
+            kfs.push_back(kf);
+            slots.push_back(mSlot[kf]);
+        }
+        if (slots.empty() || !mCtx || !Flush()) return 0;
+        std::vector<uint64_t> counts(slots.size());
+        uint64_t total = 0;
+        if (!Check(sdm_export_points(mCtx, (int)slots.size(), slots.data(), sigma, NULL, 0, counts.data(), &total), "sdm_export_points"))
+            return 0;
+        pts.resize((size_t)total);
+        if (total && !Check(sdm_export_points(mCtx, (int)slots.size(), slots.data(), sigma, pts.data(), pts.size(), counts.data(), &total),
+                            "sdm_export_points"))
+            pts.clear();
+        if (kfs_out) kfs_out->swap(kfs);
+        if (counts_out) counts_out->swap(counts);
+        return pts.size();
+    }
+
     // ProbabilityMapping.cc:847-864 (hash join instead of the O(n1*n2) pointer scan; same multiset)
     std::vector<float> GetRotInPlane(KeyFrame* kf1, KeyFrame* kf2) { return sdm_host::RotInPlane(kf1, kf2); }
 

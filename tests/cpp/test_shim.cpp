@@ -109,6 +109,15 @@ int main(int argc, char** argv)
         for (int y = 0; y < H; y++) fwrite(d.ptr<float>(y), 4, W, o);
         for (int y = 0; y < H; y++) fwrite(s.ptr<float>(y), 4, W, o);
     }
+    {   // the exporters' point filter (SaveSemiDensePoints / DrawSemiDense), compacted on the device
+        std::vector<sdm_point> pts;
+        std::vector<uint64_t> counts;
+        const size_t np = pm.ExportSemiDensePoints(0.02, pts, NULL, &counts);
+        float hdr2[2] = {(float)np, (float)counts.size()};
+        fwrite(hdr2, 4, 2, o);
+        for (size_t i = 0; i < counts.size(); i++) { float c = (float)counts[i]; fwrite(&c, 4, 1, o); }
+        fwrite(pts.data(), sizeof(sdm_point), np, o);
+    }
     fclose(o);
     sdm_timing t = pm.LastTiming();
     printf("shim ok: pass1 scan %.3f ms, pass2 %.3f ms\n", t.pass1_scan_ms, t.pass2_ms);

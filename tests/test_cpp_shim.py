@@ -89,3 +89,17 @@ def test_shim_semidense_loop_matches_oracle(shim_binary, tmp_path):
     d2, s2 = osc.depth[2].copy(), osc.sigma[2].copy()
     lib.oracle_intra_check(O.fptr(d2), O.fptr(s2), W, H, C.byref(p))
     assert np.array_equal(intra[:W * H].reshape(H, W), d2) and np.array_equal(intra[W * H:2 * W * H].reshape(H, W), s2)
+    # ExportSemiDensePoints == the filter loop of SaveSemiDensePoints (:159-186) over the oracle's planes
+    ex = intra[2 * W * H:]
+    n_pts, n_kf = int(ex[0]), int(ex[1])
+    counts = ex[2:2 + n_kf].astype(np.int64)
+    rec = ex[2 + n_kf:2 + n_kf + 4 * n_pts].reshape(n_pts, 4)
+    exp_xyz, exp_pix, exp_counts = [], [], []
+    for i in range(n):
+        keep = ~(osc.sigma[i].astype(np.float64) > 0.02) & (osc.checked[i].astype(np.float64) > 0.000001)
+        ys, xs = np.nonzero(keep)
+        exp_xyz.append(osc.points[i][ys, xs]); exp_pix.append((ys.astype(np.uint32) << 16) | xs.astype(np.uint32))
+        exp_counts.append(len(ys))
+    assert n_kf == n and list(counts) == exp_counts and n_pts == sum(exp_counts) > 1000
+    assert np.array_equal(rec[:, :3].view(np.uint32), np.concatenate(exp_xyz).view(np.uint32))
+    assert np.array_equal(rec[:, 3].copy().view(np.uint32), np.concatenate(exp_pix))
