@@ -175,3 +175,30 @@ class OracleScene:
                                          float(s.min_depth[i]), float(s.max_depth[i]), C.byref(p),
                                          fptr(d), fptr(sg), fptr(u), ok.ctypes.data_as(C.POINTER(C.c_uint8)))
         return d, sg, u, ok
+
+
+def _bind_extra(l):
+    l.oracle_inter_check.argtypes = [C.POINTER(OracleKF), C.c_int, C.POINTER(C.POINTER(OracleKF)), C.POINTER(OracleParams),
+                                     C.POINTER(OracleStats)]
+    l.oracle_update_points.argtypes = [C.POINTER(OracleKF), C.POINTER(OracleParams)]
+    return l
+
+
+def inter_check(osc: "OracleScene", i: int, params: OracleParams | None = None):
+    """InterKeyFrameDepthChecking (:1121-1296) + UpdateSemiDensePointSet (:700-731) of keyframe i alone."""
+    l = _bind_extra(lib(osc.kind))
+    p = params or default_params(osc.kind)
+    nb = osc.scene.nbr_idx[i]
+    arr = (C.POINTER(OracleKF) * len(nb))(*[C.pointer(osc.kfs[int(j)]) for j in nb])
+    l.oracle_inter_check(C.byref(osc.kfs[i]), len(nb), arr, C.byref(p), None)
+    l.oracle_update_points(C.byref(osc.kfs[i]), C.byref(p))
+
+
+def update_points(osc: "OracleScene", i: int, Tcw=None, params: OracleParams | None = None):
+    """UpdateSemiDensePointSet (:700-731) of keyframe i, optionally after KeyFrame::SetPose(Tcw)."""
+    l = _bind_extra(lib(osc.kind))
+    p = params or default_params(osc.kind)
+    if Tcw is not None:
+        for j, v in enumerate(np.asarray(Tcw, np.float32).reshape(-1)[:12]):
+            osc.kfs[i].Tcw[j] = float(v)
+    l.oracle_update_points(C.byref(osc.kfs[i]), C.byref(p))

@@ -1,0 +1,2 @@
+// stand-in: see ../cvstub.h
+#include "../../cvstub.h"

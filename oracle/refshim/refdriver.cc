@@ -1,0 +1,122 @@
+// refdriver.cc — C entry point that runs the REFERENCE'S OWN ProbabilityMapping::SemiDenseLoop()
+// (/root/reference/src/ProbabilityMapping.cc, compiled where it lies against the stand-in headers of this directory)
+// on caller-supplied keyframes.  TEST INFRASTRUCTURE ONLY: built into oracle/_ref/libref_pm.so by oracle/Makefile,
+// used by tests/test_ref_vs_oracle.py to validate the C restatement (oracle/sdm_oracle.c) against the reference text.
+#include <cstdint>
+#include <iostream>
+#include <memory>
+#include <sstream>
+#include <vector>
+
+#include "KeyFrame.h"
+#include "Map.h"
+#include "MapPoint.h"
+#include "ProbabilityMapping.h"  // the reference's header (include/ProbabilityMapping.h)
+
+long unsigned int ORB_SLAM2::KeyFrame::nNextMappingId = 1;  // (0 in KeyFrame.cc:30: the first keyframe is then never "Mapped")
+
+static cv::Mat wrap_copy(const void* src, int rows, int cols, int type)
+{
+    cv::Mat m(rows, cols, type);
+    memcpy(m.data, src, (size_t)rows * cols * m.elemSize());
+    return m;
+}
+
+extern "C" {
+
+int ref_covisN(void) { return covisN; }
+
+// Runs SemiDenseLoop() over n keyframes (dense row-major planes).  nbr_idx: [n][covisN] covisibility lists in
+// order.  The in-plane rotation of a pair comes out of the reference's own GetRotInPlane + median (:406-415): the
+// driver gives keyframe k ORB keypoints of angle kp_angle[k] on one map point per unordered covisible pair, so
+// rotIs[kf2] = kp_angle[kf2] - kp_angle[kf] in float.  inv_depths: [n][n_inv] sorted inverse depths per keyframe
+// (GetAllPointDepths).  Outputs: the four planes of every keyframe and the flags.
+int ref_semidense_loop(int n, int W, int H, const uint8_t* im, const float* grad, const float* theta, const int32_t* edge,
+                       const float* K4, const float* Tcw12, const int32_t* nbr_idx, const float* kp_angle,
+                       const float* inv_depths, int n_inv, float* depth, float* sigma, float* checked, float* points,
+                       int32_t* flags)
+{
+    using namespace ORB_SLAM2;
+    std::ostringstream sink;
+    std::streambuf* old = std::cout.rdbuf(sink.rdbuf());  // the loop narrates to stdout
+    const size_t P = (size_t)W * H;
+    KeyFrame::nNextMappingId = 1;
+    std::vector<std::unique_ptr<KeyFrame> > kfs;
+    std::vector<std::unique_ptr<MapPoint> > mps;
+    Map map;
+    for (int i = 0; i < n; i++) {
+        kfs.emplace_back(new KeyFrame());
+        KeyFrame* kf = kfs.back().get();
+        kf->fx = K4[0]; kf->fy = K4[1]; kf->cx = K4[2]; kf->cy = K4[3];
+        kf->mK = cv::Mat::zeros(3, 3, CV_32F);
+        kf->mK.at<float>(0, 0) = K4[0]; kf->mK.at<float>(1, 1) = K4[1];
+        kf->mK.at<float>(0, 2) = K4[2]; kf->mK.at<float>(1, 2) = K4[3]; kf->mK.at<float>(2, 2) = 1.0f;
+        kf->mnMinX = 0; kf->mnMinY = 0; kf->mnMaxX = W; kf->mnMaxY = H;  // Frame.cc:584-590 without distortion
+        cv::Mat T = cv::Mat::zeros(4, 4, CV_32F);
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 4; c++) T.at<float>(r, c) = Tcw12[(size_t)i * 12 + r * 4 + c];
+        T.at<float>(3, 3) = 1.0f;
+        kf->SetPose(T);
+        // KeyFrame.cc:63-88
+        kf->im_ = wrap_copy(im + i * P, H, W, CV_8U);
+        kf->GradImg = wrap_copy(grad + i * P, H, W, CV_32F);
+        kf->GradTheta = wrap_copy(theta + i * P, H, W, CV_32F);
+        kf->mEdgeIndex = edge ? wrap_copy(edge + i * P, H, W, CV_32S) : cv::Mat::zeros(H, W, CV_32S);
+        kf->depth_map_ = cv::Mat::zeros(H, W, CV_32F);
+        kf->depth_sigma_ = cv::Mat::zeros(H, W, CV_32F);
+        kf->depth_map_checked_ = cv::Mat::zeros(H, W, CV_32F);
+        kf->SemiDensePointSets_ = cv::Mat::zeros(H, W * 3, CV_32F);
+        kf->mvInvDepths.assign(inv_depths + (size_t)i * n_inv, inv_depths + (size_t)(i + 1) * n_inv);
+        kf->IncreaseMappingId();
+        map.mvKFs.push_back(kf);
+    }
+    KeyFrame::nNextMappingId += 11;  // MappingIdDelay(): more than 10 keyframes mapped after each of ours
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < covisN; j++) kfs[i]->mvpOrderedConnectedKeyFrames.push_back(kfs[nbr_idx[(size_t)i * covisN + j]].get());
+    // one shared map point per unordered covisible pair
+    std::vector<std::vector<char> > linked(n, std::vector<char>(n, 0));
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < covisN; j++) {
+            const int k = nbr_idx[(size_t)i * covisN + j];
+            if (linked[i][k]) continue;
+            linked[i][k] = linked[k][i] = 1;
+            mps.emplace_back(new MapPoint());
+            for (int q : {i, k}) {
+                kfs[q]->mvpMapPoints.push_back(mps.back().get());
+                cv::KeyPoint kp;
+                kp.angle = kp_angle[q];
+                kfs[q]->mvKeysUn.push_back(kp);
+            }
+        }
+
+    ProbabilityMapping pm(&map);
+    pm.SemiDenseLoop();
+
+    for (int i = 0; i < n; i++) {
+        KeyFrame* kf = kfs[i].get();
+        memcpy(depth + i * P, kf->depth_map_.data, P * 4);
+        memcpy(sigma + i * P, kf->depth_sigma_.data, P * 4);
+        memcpy(checked + i * P, kf->depth_map_checked_.data, P * 4);
+        memcpy(points + i * P * 3, kf->SemiDensePointSets_.data, P * 12);
+        flags[2 * i] = kf->semidense_flag_;
+        flags[2 * i + 1] = kf->interKF_depth_flag_;
+    }
+    std::cout.rdbuf(old);
+    return 0;
+}
+
+// IntraKeyFrameDepthChecking / IntraKeyFrameDepthGrowing (:866-976; public, commented out of the shipped loop at
+// :491-494) of the reference on caller planes, in place.  which: 0 = checking, 1 = growing.
+int ref_intra(int which, int W, int H, float* depth, float* sigma, const float* grad)
+{
+    ORB_SLAM2::Map map;
+    ProbabilityMapping pm(&map);
+    const size_t P = (size_t)W * H;
+    cv::Mat d = wrap_copy(depth, H, W, CV_32F), s = wrap_copy(sigma, H, W, CV_32F), g = wrap_copy(grad, H, W, CV_32F);
+    if (which == 0) pm.IntraKeyFrameDepthChecking(d, s, g); else pm.IntraKeyFrameDepthGrowing(d, s, g);
+    memcpy(depth, d.data, P * 4);
+    memcpy(sigma, s.data, P * 4);
+    return 0;
+}
+
+}  // extern "C"

@@ -5,14 +5,22 @@
  * the product path (eao-slam_b200/, include/) may include, link or call it; only tests/,
  * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs do.
  *
- * PARITY STATUS: "parity unpinned" by the reference's own tests — the reference ships no test,
- * golden vector or fixture for this path and cannot be compiled here because
- * OpenCV C++/Eigen/Boost/CGAL headers are absent.  What IS pinned:
- *   - every OpenCV primitive this file restates (small gemm forms, invert, LU solve, fastAtan2)
- *     is checked bit-exactly against real cv2 4.13 outputs committed in tests/golden/cv2_kats.npz
- *     (generator: oracle/pin_cv2.py);
- *   - where oracle/_ref (the reference's own ProbabilityMapping.cc compiled against a stub
- *     cv::Mat, see oracle/refshim/) is built, the per-function outputs are compared with it.
+ * PARITY STATUS: pinned against the reference's own source, with one stated caveat.
+ *   - The reference ships no test, golden vector or fixture for this path and its build needs
+ *     OpenCV C++, Eigen, Boost and CGAL, none present here.  Instead, oracle/Makefile (target `ref`) compiles
+ *     /root/reference/src/ProbabilityMapping.cc WHERE IT LIES against stand-in headers (oracle/refshim/: a minimal
+ *     cv::Mat / MatExpr, ORB_SLAM2::KeyFrame / Map with the reference's member names, no-op LineDetector / Modeler)
+ *     into oracle/_ref/libref_pm.so, and tests/test_ref_vs_oracle.py runs the reference's SemiDenseLoop(),
+ *     IntraKeyFrameDepthChecking and IntraKeyFrameDepthGrowing on the same keyframes: this file reproduces their
+ *     planes bit for bit (0 differing words; also committed as tests/golden/ref_loop_small.npz).
+ *   - Caveat: the arithmetic INSIDE cv::Mat expressions is the stand-in's, not OpenCV's.  Those evaluation rules
+ *     (small gemm forms, A*B^T, 1xn*nx1, invert, LU solve, convertTo scale, fastAtan2) are pinned bit-exactly
+ *     against real cv2 4.13 (tests/golden/cv2_kats.npz, generator oracle/pin_cv2.py), and the composed pair geometry
+ *     (R21, t21, F12) against real cv2 calls in MatExpr evaluation order (tests/golden/pair_geometry_cv2.npz).
+ *   - The end-to-end outputs of this file on a small scene are committed (tests/golden/oracle_small.npz) so the
+ *     oracle cannot drift silently.
+ * cpu_baseline.kind stays "port": timing the reference text through a stand-in cv::Mat would not be the reference's
+ * real cost (OpenCV's allocator and locks dominate it).
  *
  * Every function cites the reference file:line it follows (paths relative to /root/reference).
  */

@@ -1,0 +1,104 @@
+"""The single-method / bookkeeping entry points of the C-ABI that the batch tests do not reach: sdm_inter_check on
+planes written from outside (dense pass-2 kernel), sdm_update_points after sdm_set_pose (PoseChanged refresh,
+ProbabilityMapping.cc:678-697), sdm_set_intrinsics / sdm_mark_pass1_done / sdm_depth_plane_ptr for halo slots,
+pinned host memory, timing and statistics calls."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_py as O
+from helpers import run_oracle
+from sdmb200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def scene():
+    return synth.make_scene(9, 320, 240, 6, seed=23)
+
+
+def _bits(a, b):
+    return int((np.ascontiguousarray(a).view(np.uint32) != np.ascontiguousarray(b).view(np.uint32)).sum())
+
+
+def test_inter_check_on_external_planes(scene):
+    """InterKeyFrameDepthChecking(kf, neighbours) as a single call: every (rho,sigma) plane arrives through
+    sdm_upload_depth (like cv::Mat planes of an earlier loop), so pass 2 runs its every-pixel kernel."""
+    sc = scene
+    osc = O.OracleScene(sc)
+    osc.run(pass_mask=1)                       # pass-1 planes of every keyframe
+    O.inter_check(osc, 4)
+    with api.Context(width=320, height=240, max_keyframes=sc.n) as ctx:
+        ctx.upload_scene(sc)
+        for i in range(sc.n):
+            ctx.upload_depth(i, osc.depth[i], osc.sigma[i])
+        item = api.make_items([4], sc.nbr_idx, sc.rot, sc.min_depth, sc.max_depth)
+        ctx._chk(ctx.lib.sdm_inter_check(ctx.h, item))
+        got = ctx.download(4)
+    assert (osc.checked[4] > 0).sum() > 5000
+    assert _bits(got["checked"], osc.checked[4]) == 0 and _bits(got["points"], osc.points[4]) == 0
+    assert _bits(got["depth"], osc.depth[4]) == 0 and _bits(got["sigma"], osc.sigma[4]) == 0  # de-interleave path
+
+
+def test_update_points_after_pose_change(scene):
+    sc = scene
+    osc = run_oracle(sc)
+    with api.Context(width=320, height=240, max_keyframes=sc.n) as ctx:
+        ctx.upload_scene(sc)
+        items = api.make_items(range(sc.n), sc.nbr_idx, sc.rot, sc.min_depth, sc.max_depth)
+        ctx.pass1(items); ctx.pass2(items)
+        T = sc.Tcw[2].copy()
+        T[:, 3] += np.array([0.03, -0.02, 0.05], np.float32)   # loop closure moved the keyframe
+        ctx.set_pose(2, T)
+        ctx.update_points([2, 6])
+        O.update_points(osc, 2, T)
+        O.update_points(osc, 6)
+        for i in (2, 6):
+            got = ctx.download(i)
+            assert _bits(got["points"], osc.points[i]) == 0 and _bits(got["checked"], osc.checked[i]) == 0
+        assert np.abs(osc.points[2]).max() > 0
+
+
+def test_halo_slot_without_images(scene):
+    """a halo slot may carry only calibration, pose and (rho,sigma) received from outside: enough for pass 2"""
+    sc = scene
+    osc = run_oracle(sc)
+    with api.Context(width=320, height=240, max_keyframes=sc.n) as ctx:
+        nb = [int(j) for j in sc.nbr_idx[4]]
+        for i in [4] + nb[:3]:
+            ctx.upload_keyframe(i, sc.im[i], sc.grad[i], sc.theta[i], None, sc.K, sc.Tcw[i])
+        for i in nb[3:]:                                      # no image planes for these
+            ctx.set_intrinsics(i, sc.K); ctx.set_pose(i, sc.Tcw[i])
+        for i in [4] + nb:
+            ctx.upload_depth(i, osc.depth[i], osc.sigma[i])
+        ptr, nbytes = ctx.depth_plane_ptr(nb[4])
+        assert ptr and nbytes == 320 * 240 * 8
+        ctx.mark_pass1_done(nb[4])
+        ctx.pass2(api.make_items([4], sc.nbr_idx, sc.rot, sc.min_depth, sc.max_depth))
+        got = ctx.download(4, depth=False, sigma=False)
+    assert _bits(got["checked"], osc.checked[4]) == 0
+
+
+def test_pinned_memory_timing_and_stats(scene):
+    sc = scene
+    lib = api.load()
+    p = C.c_void_p()
+    assert lib.sdm_host_alloc(C.byref(p), 1 << 20) == 0 and p.value
+    assert lib.sdm_host_free(p) == 0
+    assert b"sm_100a" in lib.sdm_version()
+    with api.Context(width=320, height=240, max_keyframes=sc.n) as ctx:
+        ctx.upload_scene(sc)
+        items = api.make_items(range(sc.n), sc.nbr_idx, sc.rot, sc.min_depth, sc.max_depth)
+        l0 = ctx.launch_count()
+        ctx.mark(0); ctx.pass1(items); ctx.pass2(items); ctx.mark(1)
+        total = ctx.elapsed_ms(0, 1)
+        p1, p2 = ctx.last_pass_ms()
+        t = ctx.last_timing()
+        assert 0 < p1 <= total and 0 < p2 <= total and abs(t["pass1_scan_ms"] + t["pass1_intra_ms"] - p1) < 0.05
+        assert ctx.launch_count() - l0 == 4               # k_plan + scan, k_plan + pass 2
+        st = ctx.stats()
+        assert st["candidates"] == int((sc.grad > 8).sum()) and 0 < st["checked"] <= st["fused"] <= st["candidates"]
+        with pytest.raises(api.SdmError):
+            ctx.elapsed_ms(2, 3)                           # marks never recorded

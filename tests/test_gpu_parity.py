@@ -273,3 +273,18 @@ def test_point_cloud_export_matches_the_consumers_filter(small_scene, small_orac
         # a too-small buffer is filled to capacity and the full count is still reported
         pts, counts, total = ctx.export_points(order, 0.02, capacity=100)
         assert len(pts) == 100 and total > 100
+
+
+def test_cuda_path_equals_the_reference_source_output(golden_dir):
+    """tests/golden/ref_loop_small.npz holds the planes that the reference's OWN src/ProbabilityMapping.cc produced
+    (compiled against the stand-in headers of oracle/refshim/, see tests/test_ref_vs_oracle.py): covisN = 7 neighbours,
+    the reference's gating, non-zero in-plane rotations.  The CUDA path must reproduce them."""
+    import os
+    import test_ref_vs_oracle as R
+    g = np.load(os.path.join(golden_dir, "ref_loop_small.npz"))
+    sc, _ = R._scene()
+    assert np.array_equal(sc.im, g["im"])
+    dev = run_device(sc)
+    for k in ("depth", "sigma", "checked", "points"):
+        assert np.array_equal(dev[k].view(np.uint32), g[k].view(np.uint32)), k
+    assert (g["depth"] > 0).sum() > 30000 and (g["checked"] > 0).sum() > 25000

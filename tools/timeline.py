@@ -1,5 +1,6 @@
-"""Developer probe: upload-only / passes-only / chunked upload+pass timing (pinned host planes)."""
+"""Developer probe: per-stream timeline (SDM_TRACE=1) of a chunked upload / pass-1 / pass-2 loop, printed by the library."""
 import os, sys, time, ctypes as C
+os.environ["SDM_TRACE"] = "1"
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "eao-slam_b200", "python")); sys.path.insert(0, ROOT)
 import numpy as np
@@ -14,14 +15,6 @@ for k in ("im", "grad", "theta"):
     a = getattr(sc, k); h = bench.pinned(lib, a.shape, a.dtype, keep); h[:] = a; setattr(sc, k, h)
 up = ctx.upload_descs(sc, range(n))
 items = api.make_items(range(n), sc.nbr_idx, sc.rot, sc.min_depth, sc.max_depth)
-def T(f, reps=5):
-    f(); ctx.synchronize(); t = time.perf_counter()
-    for _ in range(reps):
-        f()
-    ctx.synchronize(); return 1e3 * (time.perf_counter() - t) / reps
-print("upload only          ms", T(lambda: ctx.upload_keyframes(up)))
-print("pass1+pass2 only     ms", T(lambda: (ctx.pass1(items), ctx.pass2(items))))
-print("upload,pass1,pass2   ms", T(lambda: (ctx.upload_keyframes(up), ctx.pass1(items), ctx.pass2(items))))
 CH = 25
 chunks = [list(range(i, min(n, i + CH))) for i in range(0, n, CH)]
 citems = [api.make_items(ch, sc.nbr_idx, sc.rot, sc.min_depth, sc.max_depth) for ch in chunks]
@@ -35,10 +28,6 @@ def chunked():
             ctx._chk(lib.sdm_upload_keyframes(ctx.h, need[k] + 1 - nxt, uptr(nxt))); nxt = need[k] + 1
         ctx.pass1(citems[k])
     ctx.pass2(items)
-print("chunked upload/pass1 ms", T(chunked))
-def all_up_then_chunked_pass():
-    ctx.upload_keyframes(up)
-    for k in range(len(chunks)):
-        ctx.pass1(citems[k])
-    ctx.pass2(items)
-print("upload all, chunked pass1 ms", T(all_up_then_chunked_pass))
+chunked(); ctx.synchronize()
+print("---- second iteration ----", file=sys.stderr)
+chunked(); ctx.synchronize()
