@@ -187,7 +187,45 @@ def main_reference(a, rank):
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    src = reference_source_timing(a)
+    if src:
+        line["reference_source"] = src
     print(json.dumps(line), file=_REAL_STDOUT, flush=True)
+
+
+def reference_source_timing(a):
+    """How conservative is the port as a baseline?  oracle/_ref/libref_pm.so is the reference's OWN
+    src/ProbabilityMapping.cc (compiled against the stand-in cv::Mat of oracle/refshim/; covisN is compiled in as 7 and
+    the intra checks are commented out of its loop, so it cannot run the 6-neighbour workload itself).  Time its
+    SemiDenseLoop() and the port on the same 12-keyframe, 7-neighbour sample."""
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle_py as O
+        import ref_py
+        if not ref_py.available(build=False):
+            return None
+        n = max(12, a.cpu_sample_kf)
+        nb = synth.neighbours(n, 7)
+        sc = synth.make_scene(n, W, H, 7, seed=a.seed, nbr_idx=nb, workers=1)
+        lib = O.lib("fast")
+        for i in range(n):
+            lo, hi = C.c_float(), C.c_float()
+            lib.oracle_stereo_search_constraints(O.fptr(sc.inv_depths[i]), len(sc.inv_depths[i]), C.byref(lo), C.byref(hi))
+            sc.min_depth[i], sc.max_depth[i] = lo.value, hi.value
+        t = time.perf_counter()
+        ref = ref_py.run_reference_loop(sc, np.full(n, 50.0, np.float32))
+        t_ref = time.perf_counter() - t
+        osc = O.OracleScene(sc, "fast")
+        t_port = osc.run(params=O.default_params("fast"))
+        cands = osc.stats.as_dict()["candidates"]
+        same = bool(((ref["checked"] > 0) == (osc.checked > 0)).mean() > 0.999)
+        return {"value": cands / t_ref, "unit": UNIT, "ms_per_keyframe": 1e3 * t_ref / n, "port_ms_per_keyframe": 1e3 * t_port / n,
+                "port_speedup_over_reference_source": t_ref / t_port, "same_accepted_set": same,
+                "sample": f"{n} keyframes, 7 neighbours (the reference's compiled-in covisN), no intra stage, "
+                          f"{O.lib('fast').oracle_num_threads()} OpenMP threads; cv::Mat is a stand-in, so this is the reference's "
+                          "control flow and per-pixel allocation pattern, not OpenCV's allocator"}
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": str(e)[:200]}
 
 
 def workload_config(a, kf_per_gpu, note=None):
