@@ -10,11 +10,16 @@
 //   tex    float4[P]  row-pair texel {G(y,x), G(y+1,x), Th(y,x), Th(y+1,x)}  (row H-1 pairs with itself)
 //   ipair  uchar2[P]  {I(y,x), I(y+1,x)}
 //   cand   u32[P]     compacted candidate pixels (y<<16 | x), count in cand_count[slot]
-//   rs     float2[P]  {rho, sigma} = depth_map_, depth_sigma_   (pass-1 output)
+//   rs     float2[P]  {rho, sigma} = depth_map_, depth_sigma_   (pass-1 output; the plane neighbours and peers read)
+//   rs2    float2[P]  second plane of the intra check / grow ping-pong (only with the intra stage)
+//   dpl    float[P]   } dense copies of rho / sigma for the D2H path
+//   spl    float[P]   }
 //   chk    float[P]   depth_map_checked_                          (pass-2 output)
 //   pts    float[3P]  SemiDensePointSets_                         (pass-2 output)
 // The row-pair texel makes every ylinear/yangle evaluation of the epipolar scan (:66-111) one
 // 16-byte load + one 2-byte load, coalesced across the warp's consecutive columns.
+// Kernels: k_pack, k_plan, k_pass1_lane (default scan) / k_pass1 (warp-per-pixel A/B),
+// k_intra_cand / k_intra_check / k_intra_grow, k_pass2_cand / k_pass2, k_export_*, single-method helpers.
 #pragma once
 
 #include <cuda_runtime.h>
@@ -59,7 +64,7 @@ struct DevPair {
     float rot;
     int slot;
     int pad[3];
-};  // 28 words
+};  // 26 words
 
 struct DevItem {
     int kf;
