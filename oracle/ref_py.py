@@ -36,13 +36,14 @@ def lib():
     return _lib
 
 
-def run_reference_loop(scene, kp_angle):
-    """SemiDenseLoop() of the reference over a synth.Scene with covisN (= 7) neighbours per keyframe.
+def run_reference_loop(scene, kp_angle, first_id=1, extra_ids=11, bad=None):
+    """SemiDenseLoop() of the reference over a synth.Scene whose covisibility lists (scene.nbr_idx) hold at least
+    covisN (= 7) keyframes.  first_id / extra_ids / bad drive the reference's own gating (mapping ids, isBad()).
     Returns dict(depth, sigma, checked, points, flags)."""
     l = lib()
     n, H, W = scene.im.shape
     N = l.ref_covisN()
-    assert scene.nbr_idx.shape == (n, N), f"the reference is compiled with covisN = {N}"
+    assert scene.nbr_idx.shape[0] == n and scene.nbr_idx.shape[1] >= N, f"the reference is compiled with covisN = {N}"
     inv = np.ascontiguousarray(np.stack(scene.inv_depths).astype(np.float32))
     out = {k: np.zeros((n, H, W) + ((3,) if k == "points" else ()), np.float32) for k in ("depth", "sigma", "checked", "points")}
     flags = np.zeros((n, 2), np.int32)
@@ -53,13 +54,15 @@ def run_reference_loop(scene, kp_angle):
     T = c(scene.Tcw.reshape(n, 12), np.float32)
     nb = c(scene.nbr_idx, np.int32)
     ang = c(kp_angle, np.float32)
-    rc = l.ref_semidense_loop(n, W, H, args[0].ctypes.data_as(C.c_void_p), args[1].ctypes.data_as(C.c_void_p),
-                              args[2].ctypes.data_as(C.c_void_p), edge.ctypes.data_as(C.c_void_p) if edge is not None else None,
-                              K.ctypes.data_as(C.c_void_p), T.ctypes.data_as(C.c_void_p), nb.ctypes.data_as(C.c_void_p),
-                              ang.ctypes.data_as(C.c_void_p), inv.ctypes.data_as(C.c_void_p), inv.shape[1],
-                              out["depth"].ctypes.data_as(C.c_void_p), out["sigma"].ctypes.data_as(C.c_void_p),
-                              out["checked"].ctypes.data_as(C.c_void_p), out["points"].ctypes.data_as(C.c_void_p),
-                              flags.ctypes.data_as(C.c_void_p))
+    badv = c(bad, np.int32) if bad is not None else np.zeros(n, np.int32)
+    rc = l.ref_semidense_loop_ex(n, W, H, args[0].ctypes.data_as(C.c_void_p), args[1].ctypes.data_as(C.c_void_p),
+                                 args[2].ctypes.data_as(C.c_void_p), edge.ctypes.data_as(C.c_void_p) if edge is not None else None,
+                                 K.ctypes.data_as(C.c_void_p), T.ctypes.data_as(C.c_void_p), int(nb.shape[1]),
+                                 nb.ctypes.data_as(C.c_void_p), ang.ctypes.data_as(C.c_void_p), inv.ctypes.data_as(C.c_void_p),
+                                 inv.shape[1], int(first_id), int(extra_ids), badv.ctypes.data_as(C.c_void_p),
+                                 out["depth"].ctypes.data_as(C.c_void_p), out["sigma"].ctypes.data_as(C.c_void_p),
+                                 out["checked"].ctypes.data_as(C.c_void_p), out["points"].ctypes.data_as(C.c_void_p),
+                                 flags.ctypes.data_as(C.c_void_p))
     assert rc == 0
     out["flags"] = flags
     return out

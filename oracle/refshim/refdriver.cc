@@ -31,16 +31,20 @@ int ref_covisN(void) { return covisN; }
 // driver gives keyframe k ORB keypoints of angle kp_angle[k] on one map point per unordered covisible pair, so
 // rotIs[kf2] = kp_angle[kf2] - kp_angle[kf] in float.  inv_depths: [n][n_inv] sorted inverse depths per keyframe
 // (GetAllPointDepths).  Outputs: the four planes of every keyframe and the flags.
-int ref_semidense_loop(int n, int W, int H, const uint8_t* im, const float* grad, const float* theta, const int32_t* edge,
-                       const float* K4, const float* Tcw12, const int32_t* nbr_idx, const float* kp_angle,
-                       const float* inv_depths, int n_inv, float* depth, float* sigma, float* checked, float* points,
-                       int32_t* flags)
+// _ex: n_cov = length of every covisibility list (>= covisN; the reference takes the first covisN GOOD ones, :365-384),
+// first_id = value of KeyFrame::nNextMappingId before the first keyframe is mapped (0 in the reference: that keyframe
+// is then never "Mapped", KeyFrame.cc:796-806), extra_ids = keyframes mapped after ours (MappingIdDelay needs > 10
+// newer ones, :789-794), bad[n] = isBad() per keyframe.
+int ref_semidense_loop_ex(int n, int W, int H, const uint8_t* im, const float* grad, const float* theta, const int32_t* edge,
+                          const float* K4, const float* Tcw12, int n_cov, const int32_t* nbr_idx, const float* kp_angle,
+                          const float* inv_depths, int n_inv, int first_id, int extra_ids, const int32_t* bad, float* depth,
+                          float* sigma, float* checked, float* points, int32_t* flags)
 {
     using namespace ORB_SLAM2;
     std::ostringstream sink;
     std::streambuf* old = std::cout.rdbuf(sink.rdbuf());  // the loop narrates to stdout
     const size_t P = (size_t)W * H;
-    KeyFrame::nNextMappingId = 1;
+    KeyFrame::nNextMappingId = (long unsigned int)first_id;
     std::vector<std::unique_ptr<KeyFrame> > kfs;
     std::vector<std::unique_ptr<MapPoint> > mps;
     Map map;
@@ -67,17 +71,18 @@ int ref_semidense_loop(int n, int W, int H, const uint8_t* im, const float* grad
         kf->depth_map_checked_ = cv::Mat::zeros(H, W, CV_32F);
         kf->SemiDensePointSets_ = cv::Mat::zeros(H, W * 3, CV_32F);
         kf->mvInvDepths.assign(inv_depths + (size_t)i * n_inv, inv_depths + (size_t)(i + 1) * n_inv);
+        kf->mbBad = bad && bad[i];
         kf->IncreaseMappingId();
         map.mvKFs.push_back(kf);
     }
-    KeyFrame::nNextMappingId += 11;  // MappingIdDelay(): more than 10 keyframes mapped after each of ours
+    KeyFrame::nNextMappingId += (long unsigned int)extra_ids;
     for (int i = 0; i < n; i++)
-        for (int j = 0; j < covisN; j++) kfs[i]->mvpOrderedConnectedKeyFrames.push_back(kfs[nbr_idx[(size_t)i * covisN + j]].get());
+        for (int j = 0; j < n_cov; j++) kfs[i]->mvpOrderedConnectedKeyFrames.push_back(kfs[nbr_idx[(size_t)i * n_cov + j]].get());
     // one shared map point per unordered covisible pair
     std::vector<std::vector<char> > linked(n, std::vector<char>(n, 0));
     for (int i = 0; i < n; i++)
-        for (int j = 0; j < covisN; j++) {
-            const int k = nbr_idx[(size_t)i * covisN + j];
+        for (int j = 0; j < n_cov; j++) {
+            const int k = nbr_idx[(size_t)i * n_cov + j];
             if (linked[i][k]) continue;
             linked[i][k] = linked[k][i] = 1;
             mps.emplace_back(new MapPoint());
@@ -103,6 +108,16 @@ int ref_semidense_loop(int n, int W, int H, const uint8_t* im, const float* grad
     }
     std::cout.rdbuf(old);
     return 0;
+}
+
+int ref_semidense_loop(int n, int W, int H, const uint8_t* im, const float* grad, const float* theta, const int32_t* edge,
+                       const float* K4, const float* Tcw12, const int32_t* nbr_idx, const float* kp_angle,
+                       const float* inv_depths, int n_inv, float* depth, float* sigma, float* checked, float* points,
+                       int32_t* flags)
+{
+    // every keyframe eligible: ids 1..n, 11 newer keyframes, nobody bad, lists of exactly covisN
+    return ref_semidense_loop_ex(n, W, H, im, grad, theta, edge, K4, Tcw12, covisN, nbr_idx, kp_angle, inv_depths, n_inv, 1, 11,
+                                 NULL, depth, sigma, checked, points, flags);
 }
 
 // IntraKeyFrameDepthChecking / IntraKeyFrameDepthGrowing (:866-976; public, commented out of the shipped loop at

@@ -23,9 +23,13 @@ int main(int argc, char** argv)
     if (argc < 3) { fprintf(stderr, "usage: test_shim scene.bin out.bin\n"); return 2; }
     FILE* f = fopen(argv[1], "rb");
     if (!f) { perror("scene"); return 2; }
-    int32_t hdr[6];  // n, W, H, N, pitch_pad, n_probe
+    // n, W, H, covisN, pitch_pad, n_probe, n_cov (covisibility list length >= covisN), first mapping id, keyframes
+    // mapped after ours (the reference's gating: KeyFrame.cc:789-806)
+    int32_t hdr[9];
     rd(f, hdr, sizeof(hdr));
     const int n = hdr[0], W = hdr[1], H = hdr[2], N = hdr[3], pad = hdr[4], n_probe = hdr[5];
+    const int n_cov = hdr[6], first_id = hdr[7], extra_ids = hdr[8];
+    KeyFrame::nNextMappingId() = (unsigned long)first_id;
     float K[4];
     rd(f, K, sizeof(K));
     std::vector<std::unique_ptr<KeyFrame>> kfs;
@@ -49,8 +53,11 @@ int main(int argc, char** argv)
         rd(f, &nd, 4);
         kf->mvInvDepths.resize(nd);
         rd(f, kf->mvInvDepths.data(), (size_t)nd * 4);
-        nbr[i].resize(N);
-        rd(f, nbr[i].data(), (size_t)N * 4);
+        nbr[i].resize(n_cov);
+        rd(f, nbr[i].data(), (size_t)n_cov * 4);
+        int32_t bad;
+        rd(f, &bad, 4);
+        kf->mbBad = bad != 0;
         kf->IncreaseMappingId();
         map.AddKeyFrame(kf);
     }
@@ -58,10 +65,10 @@ int main(int argc, char** argv)
     rd(f, probes.data(), probes.size() * 4);
     fclose(f);
     for (int i = 0; i < n; i++)
-        for (int j = 0; j < N; j++) kfs[i]->mvpOrderedConnectedKeyFrames.push_back(kfs[nbr[i][j]].get());
-    {   // 11 more keyframes "mapped" after ours so that MappingIdDelay() holds for all (KeyFrame.cc:789-794)
+        for (int j = 0; j < n_cov; j++) kfs[i]->mvpOrderedConnectedKeyFrames.push_back(kfs[nbr[i][j]].get());
+    {   // keyframes "mapped" after ours: MappingIdDelay() needs more than 10 newer ones (KeyFrame.cc:789-794)
         KeyFrame dummy;
-        for (int i = 0; i < 11; i++) dummy.IncreaseMappingId();
+        for (int i = 0; i < extra_ids; i++) dummy.IncreaseMappingId();
     }
 
     ProbabilityMapping pm(&map);

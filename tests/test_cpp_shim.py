@@ -30,6 +30,55 @@ def test_shim_builds_as_cxx11(shim_binary):
     assert os.path.exists(shim_binary)
 
 
+def _write_scene(path, sc, N, pad, probes, first_id=1, extra_ids=11, bad=None):
+    n, (H, W) = sc.n, sc.shape
+    with open(path, "wb") as f:
+        f.write(struct.pack("9i", n, W, H, N, pad, len(probes), sc.nbr_idx.shape[1], first_id, extra_ids))
+        f.write(np.asarray(sc.K, np.float32).tobytes())
+        for i in range(n):
+            f.write(np.ascontiguousarray(sc.Tcw[i], np.float32).tobytes())
+            f.write(sc.im[i].tobytes()); f.write(sc.grad[i].tobytes()); f.write(sc.theta[i].tobytes())
+            f.write(struct.pack("i", len(sc.inv_depths[i]))); f.write(sc.inv_depths[i].tobytes())
+            f.write(np.ascontiguousarray(sc.nbr_idx[i], np.int32).tobytes())
+            f.write(struct.pack("i", int(bad[i]) if bad is not None else 0))
+        f.write(np.asarray(probes, np.int32).reshape(-1).tobytes())
+
+
+@pytest.mark.gpu
+def test_shim_gating_matches_the_reference_source(shim_binary, tmp_path):
+    """The class shim against the REFERENCE'S OWN SemiDenseLoop() (oracle/_ref, tests/test_ref_vs_oracle.py) in a
+    scenario where the gating matters: the first keyframe gets mapping id 0 and is never "Mapped" (KeyFrame.cc:796-806),
+    only keyframes with more than 10 newer mapped ones are processed (:789-794), one keyframe is bad, and every
+    covisibility list is longer than covisN so that the first seven GOOD entries are taken (:365-384, :523-542).
+    Same flags, same planes."""
+    import ref_py
+    if not ref_py.available():
+        pytest.skip("needs /root/reference or a prebuilt oracle/_ref/libref_pm.so")
+    n, W, H, N, n_cov = 24, 96, 72, 7, 11
+    sc = synth.make_scene(n, W, H, n_cov, seed=61, contrast=0.9)
+    bad = np.zeros(n, np.int32); bad[5] = 1
+    first_id, extra_ids = 0, 3          # ids 0..23, then 3 more: MappingIdDelay holds for ids 1..15
+    ref = ref_py.run_reference_loop(sc, np.full(n, 50.0, np.float32), first_id=first_id, extra_ids=extra_ids, bad=bad)
+    scene_path, out_path = str(tmp_path / "scene.bin"), str(tmp_path / "out.bin")
+    _write_scene(scene_path, sc, N, 0, [], first_id=first_id, extra_ids=extra_ids, bad=bad)
+    r = subprocess.run([shim_binary, scene_path, out_path], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw = np.fromfile(out_path, np.float32)
+    per = 2 + 6 * W * H
+    flags = np.zeros((n, 2), np.int32)
+    for i in range(n):
+        blk = raw[i * per:(i + 1) * per]
+        flags[i] = blk[:2].view(np.int32)
+        p = blk[2:]
+        assert np.array_equal(p[:W * H].reshape(H, W).view(np.uint32), ref["depth"][i].view(np.uint32)), i
+        assert np.array_equal(p[W * H:2 * W * H].reshape(H, W).view(np.uint32), ref["sigma"][i].view(np.uint32)), i
+        assert np.array_equal(p[2 * W * H:3 * W * H].reshape(H, W).view(np.uint32), ref["checked"][i].view(np.uint32)), i
+        assert np.array_equal(p[3 * W * H:].reshape(H, W, 3).view(np.uint32), ref["points"][i].view(np.uint32)), i
+    assert np.array_equal(flags, ref["flags"])
+    done = ref["flags"][:, 0] == 1
+    assert 5 <= done.sum() < n and not done[0] and not done[5] and not done[-1], ref["flags"].T
+
+
 @pytest.mark.gpu
 def test_shim_semidense_loop_matches_oracle(shim_binary, tmp_path):
     n, W, H, N, pad = 12, 320, 240, 6, 16
@@ -45,15 +94,7 @@ def test_shim_semidense_loop_matches_oracle(shim_binary, tmp_path):
     pick = np.random.default_rng(0).choice(len(ys), 24, replace=False)
     probes = [(5, int(sc.nbr_idx[5][k % N]), int(xs[p]), int(ys[p])) for k, p in enumerate(pick)]
     scene_path, out_path = str(tmp_path / "scene.bin"), str(tmp_path / "out.bin")
-    with open(scene_path, "wb") as f:
-        f.write(struct.pack("6i", n, W, H, N, pad, len(probes)))
-        f.write(np.asarray(sc.K, np.float32).tobytes())
-        for i in range(n):
-            f.write(np.ascontiguousarray(sc.Tcw[i], np.float32).tobytes())
-            f.write(sc.im[i].tobytes()); f.write(sc.grad[i].tobytes()); f.write(sc.theta[i].tobytes())
-            f.write(struct.pack("i", len(sc.inv_depths[i]))); f.write(sc.inv_depths[i].tobytes())
-            f.write(np.ascontiguousarray(sc.nbr_idx[i], np.int32).tobytes())
-        f.write(np.asarray(probes, np.int32).tobytes())
+    _write_scene(scene_path, sc, N, pad, probes)
     r = subprocess.run([shim_binary, scene_path, out_path], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     raw = np.fromfile(out_path, np.float32)
