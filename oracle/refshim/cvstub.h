@@ -139,8 +139,10 @@ inline float f_at(const Mat& m, int r, int c) { return m.at<float>(r, c); }
 // cv::gemm(A, B, alpha, C, beta, D, flags) for CV_32F.  alpha/beta reach the kernels as FLOAT (hal::gemm32f).
 inline Mat gemm_eval(const Mat& A, const Mat& B, double alpha, const Mat& C, double beta, int flags)
 {
+#ifndef CVSTUB_GEMM_ALPHA_DOUBLE  // OpenCV >= 3.3 (hal::gemm32f takes float alpha/beta; measured on cv2 4.13).  3.2.0 kept doubles.
     alpha = (double)(float)alpha;
     beta = (double)(float)beta;
+#endif
     const bool at = flags & GEMM_1_T, bt = flags & GEMM_2_T;
     const int M = at ? A.cols : A.rows, len = at ? A.rows : A.cols, N = bt ? B.rows : B.cols;
     Mat D(M, N, CV_32F);
