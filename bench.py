@@ -442,7 +442,10 @@ def main_ours(a, rank, world, local_rank):
             xitems = [api.make_items(ch, sc.nbr_idx, sc.rot, sc.min_depth, sc.max_depth) for ch in xchunks]
             xneed = [max(ch[-1], max(int(v) for s in ch for v in sc.nbr_idx[s])) for ch in xchunks]
 
-            def export_step():
+            up_img = ctx.upload_descs(sc, range(n_loc), images_only=True)  # grad = theta = NULL: planes made on the device
+            img_ptr = lambda i: C.cast(C.byref(up_img, i * up_sz), C.POINTER(api.UploadDesc))
+
+            def export_step(up_ptr=up_ptr):
                 t_x[0] = time.perf_counter()
                 nxt = 0
                 for k in range(len(xchunks)):  # uploads run ahead of pass 1, chunk by chunk
@@ -463,6 +466,15 @@ def main_ours(a, rank, world, local_rank):
                 export_step()
             e2e["export_sec"] = (time.perf_counter() - tt) / a.steps
             e2e["export_points"] = int(tot.value)
+            # ... and with only im_ uploaded (1 B/px instead of 9): GradImg / GradTheta produced on the device
+            export_step(img_ptr)
+            tt = time.perf_counter()
+            for _ in range(a.steps):
+                export_step(img_ptr)
+            e2e["image_sec"] = (time.perf_counter() - tt) / a.steps
+            e2e["image_points"] = int(tot.value)
+            if e2e["image_points"] != e2e["export_points"]:
+                print(f"WARNING: device-produced planes gave {e2e['image_points']} points, uploaded planes {e2e['export_points']}", file=sys.stderr)
     if rank == 0:
         clocks.stop()
 
@@ -510,6 +522,14 @@ def main_ours(a, rank, world, local_rank):
                                         "points_per_step": e2e["export_points"], "d2h_bytes_per_step": 16 * e2e["export_points"],
                                         "note": "same loop, but the result leaves as the compacted point cloud of "
                                                 "sdm_export_points (sigma <= 0.02, checked > 1e-6) instead of four dense planes"}
+        if "image_sec" in e2e:
+            line["e2e_image_in_points_out"] = {
+                "value": tot_cands / e2e["image_sec"], "unit": UNIT, "ms_per_step": 1e3 * e2e["image_sec"],
+                "points_per_step": e2e["image_points"], "h2d_bytes_per_step": int(n_loc * W * H),
+                "d2h_bytes_per_step": 16 * e2e["image_points"],
+                "note": "as e2e_point_export, but only im_ is uploaded: GradImg / GradTheta (KeyFrame.cc:69-74) are "
+                        "produced on the device by k_pack_image"}
+    line["scan_generation"] = ctx.scan_generation()
     ctx.close()
     if world == 1 and not a.no_cpu_baseline:
         r = cpu_run(a.cpu_sample_kf, a.nbr, a.seed, a.intra, 1, 0)

@@ -458,6 +458,7 @@ void sdm_destroy(sdm_ctx* c)
     for (int i = 0; i < kMaxPeers; ++i)
         if (c->peer_rs[i]) cudaIpcCloseMemHandle(c->peer_rs[i]);
     cudaFree(c->A.tex); cudaFree(c->A.ipair); cudaFree(c->A.cand); cudaFree(c->A.cand_count);
+    cudaFree(c->A.plane_irregular);
     cudaFree(c->A.rs); cudaFree(c->A.chk); cudaFree(c->A.pts); cudaFree(c->A.dpl); cudaFree(c->A.spl); cudaFree(c->A.rs2);
     for (auto& s : c->up) { cudaFree(s.im); cudaFree(s.grad); cudaFree(s.theta); cudaFree(s.edge); }
     for (auto& s : c->down) cudaFree(s.planes);
@@ -532,6 +533,8 @@ static int create_impl(sdm_ctx* c)
     CU(cudaMalloc(&A.ipair, n * P * sizeof(uchar2)));
     CU(cudaMalloc(&A.cand, n * P * sizeof(uint32_t)));
     CU(cudaMalloc(&A.cand_count, n * sizeof(int)));
+    CU(cudaMalloc(&A.plane_irregular, n * sizeof(int)));
+    CU(cudaMemsetAsync(A.plane_irregular, 0, n * sizeof(int), c->s_compute));
     CU(cudaMalloc(&A.rs, n * P * sizeof(float2)));
     CU(cudaMalloc(&A.chk, n * P * sizeof(float)));
     CU(cudaMalloc(&A.pts, n * P * 3 * sizeof(float)));
@@ -568,6 +571,21 @@ static int create_impl(sdm_ctx* c)
     c->grid_pass2 = std::max(1, occ) * prop.multiProcessorCount;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sdm::k_intra_cand, sdm::kChunk, 0));
     c->grid_intra = std::max(1, occ) * prop.multiProcessorCount;
+    // second-generation scan loop (scan_pixel_lane<2>): the reference's constants only, and only if its reciprocal
+    // form of x / 0.23f is IEEE-exact over the whole range the loop can produce (checked here, ~2 ms)
+    D.scan2 = 0;
+    const char* scan_env = getenv("SDM_SCAN");
+    if (cfg.lambdaG == 8 && cfg.lambdaL == 80 && cfg.lambdaTheta == 45 && cfg.theta == sdm::kTheta2 &&
+        !(scan_env && strcmp(scan_env, "lane1") == 0)) {
+        unsigned long long* d_bad = reinterpret_cast<unsigned long long*>(&c->d_stats->checked);
+        sdm::k_verify_div<<<c->n_sm * 8, 256, 0, c->s_compute>>>(d_bad);
+        CU(cudaGetLastError());
+        unsigned long long bad = 1;
+        CU(cudaMemcpyAsync(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, c->s_compute));
+        CU(cudaStreamSynchronize(c->s_compute));
+        CU(cudaMemsetAsync(d_bad, 0, sizeof(bad), c->s_compute));
+        D.scan2 = (bad == 0);
+    }
     CU(cudaStreamSynchronize(c->s_compute));
     if (c->trace) {
         CU(cudaEventCreate(&c->trace_base));
@@ -609,6 +627,8 @@ int sdm_synchronize(sdm_ctx* c)
     return SDM_OK;
 }
 
+int sdm_scan_generation(sdm_ctx* c) { return c ? (c->P.scan2 ? 2 : 1) : 0; }
+
 int sdm_get_stats(sdm_ctx* c, sdm_stats* out)
 {
     if (!c || !out) return fail(SDM_ERR_ARG, "null argument");
@@ -641,9 +661,11 @@ int sdm_upload_keyframes(sdm_ctx* c, int n, const sdm_upload_desc* d)
     const int W = c->cfg.width, H = c->cfg.height;
     const size_t row = (size_t)W * 4;
     for (int i = 0; i < n; ++i) {
-        if (!d[i].im || !d[i].grad || !d[i].theta) return fail(SDM_ERR_ARG, "sdm_upload_keyframes: null plane in entry %d", i);
+        if (!d[i].im || (d[i].grad == nullptr) != (d[i].theta == nullptr))
+            return fail(SDM_ERR_ARG, "sdm_upload_keyframes: entry %d needs im and either both or neither of grad / theta", i);
         if (!slot_ok(c, d[i].kf)) return fail(SDM_ERR_ARG, "keyframe slot %d out of range [0,%d)", d[i].kf, (int)c->kf.size());
-        if (d[i].im_step < (size_t)W || d[i].grad_step < row || d[i].theta_step < row || (d[i].edge && d[i].edge_step < row))
+        if (d[i].im_step < (size_t)W || (d[i].grad && (d[i].grad_step < row || d[i].theta_step < row)) ||
+            (d[i].edge && d[i].edge_step < row))
             return fail(SDM_ERR_ARG, "row step smaller than a row");
     }
     CU(cudaSetDevice(c->cfg.device));
@@ -659,8 +681,10 @@ int sdm_upload_keyframes(sdm_ctx* c, int n, const sdm_upload_desc* d)
             const sdm_upload_desc& u = d[i0 + i];
             UpStage& st = c->up[(first_stage + i) % kUpStages];
             RC(copy2d(st.im, W, u.im, u.im_step, W, H, cudaMemcpyHostToDevice, c->s_copy));
-            RC(copy2d(st.grad, row, u.grad, u.grad_step, row, H, cudaMemcpyHostToDevice, c->s_copy));
-            RC(copy2d(st.theta, row, u.theta, u.theta_step, row, H, cudaMemcpyHostToDevice, c->s_copy));
+            if (u.grad) {
+                RC(copy2d(st.grad, row, u.grad, u.grad_step, row, H, cudaMemcpyHostToDevice, c->s_copy));
+                RC(copy2d(st.theta, row, u.theta, u.theta_step, row, H, cudaMemcpyHostToDevice, c->s_copy));
+            }
             if (u.edge) RC(copy2d(st.edge, row, u.edge, u.edge_step, row, H, cudaMemcpyHostToDevice, c->s_copy));
             need_down = std::max(need_down, std::max(c->kf[u.kf].down_ds_id, c->kf[u.kf].down_cp_id));
         }
@@ -675,8 +699,12 @@ int sdm_upload_keyframes(sdm_ctx* c, int n, const sdm_upload_desc* d)
             const sdm_upload_desc& u = d[i0 + i];
             UpStage& st = c->up[(first_stage + i) % kUpStages];
             CU(cudaMemsetAsync(c->A.cand_count + u.kf, 0, sizeof(int), c->s_compute));
-            sdm::k_pack<<<dim3((c->cfg.width + sdm::kTileW - 1) / sdm::kTileW, (c->cfg.height + sdm::kTileH - 1) / sdm::kTileH), dim3(32, 8), 0, c->s_compute>>>(c->A, c->P, u.kf, st.im, st.grad, st.theta,
-                                                                       u.edge ? st.edge : nullptr);
+            CU(cudaMemsetAsync(c->A.plane_irregular + u.kf, 0, sizeof(int), c->s_compute));
+            if (u.grad)
+                sdm::k_pack<<<dim3((c->cfg.width + sdm::kTileW - 1) / sdm::kTileW, (c->cfg.height + sdm::kTileH - 1) / sdm::kTileH),
+                              dim3(32, 8), 0, c->s_compute>>>(c->A, c->P, u.kf, st.im, st.grad, st.theta, u.edge ? st.edge : nullptr);
+            else  // GradImg / GradTheta produced on the device from im_ (KeyFrame.cc:69-74)
+                sdm::k_pack_image<<<tile_grid(c), dim3(32, 8), 0, c->s_compute>>>(c->A, c->P, u.kf, st.im, u.edge ? st.edge : nullptr);
         }
         CU(cudaGetLastError());
         trace_end(c, c->s_compute);
@@ -704,7 +732,7 @@ int sdm_upload_keyframe(sdm_ctx* c, int kf, const uint8_t* im, size_t im_step, c
                         const float* theta, size_t theta_step, const int32_t* edge, size_t edge_step, const float K[4],
                         const float Tcw[12])
 {
-    if (!c || !im || !grad || !theta || !K || !Tcw) return fail(SDM_ERR_ARG, "sdm_upload_keyframe: null argument");
+    if (!c || !im || !K || !Tcw) return fail(SDM_ERR_ARG, "sdm_upload_keyframe: null argument");
     sdm_upload_desc u;
     u.kf = kf;
     u.im = im; u.im_step = im_step;
@@ -914,6 +942,28 @@ int sdm_download(sdm_ctx* c, int kf, float* depth, size_t depth_step, float* sig
 {
     RC(sdm_download_async(c, kf, depth, depth_step, sigma, sigma_step, checked, checked_step, points, points_step));
     CU(cudaStreamSynchronize(c->s_down));
+    return SDM_OK;
+}
+
+int sdm_download_planes(sdm_ctx* c, int kf, float* grad, size_t grad_step, float* theta, size_t theta_step)
+{
+    if (!c || !grad || !theta) return fail(SDM_ERR_ARG, "null argument");
+    if (!slot_ok(c, kf)) return fail(SDM_ERR_ARG, "keyframe slot %d out of range", kf);
+    if (!c->kf[kf].uploaded) return fail(SDM_ERR_STATE, "keyframe slot %d not uploaded", kf);
+    const int W = c->cfg.width, H = c->cfg.height;
+    const size_t P = c->npix, row = (size_t)W * 4;
+    if (grad_step < row || theta_step < row) return fail(SDM_ERR_ARG, "row step smaller than a row");
+    CU(cudaSetDevice(c->cfg.device));
+    cudaStream_t s = c->s_down;
+    RC(c->r_compute.wait(s, c->kf[kf].comp_id));
+    DownStage& st = c->down[c->down_next];
+    c->down_next = (c->down_next + 1) % kDownStages;
+    sdm::k_split_tex<<<(unsigned)((P + 255) / 256), 256, 0, s>>>(c->A.tex + (size_t)kf * P, st.planes, st.planes + P, P);
+    CU(cudaGetLastError());
+    c->launches++;
+    RC(copy2d(grad, grad_step, st.planes, row, row, H, cudaMemcpyDeviceToHost, s));
+    RC(copy2d(theta, theta_step, st.planes + P, row, row, H, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
     return SDM_OK;
 }
 

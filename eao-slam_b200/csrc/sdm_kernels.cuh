@@ -41,6 +41,7 @@ struct DevParams {
     float eps_gt;         // x > this  <=>  (double)x > 0.000001
     float eps_lt;         // x < this  <=>  (double)x < 0.000001
     float slope_max;
+    int scan2;        // second-generation scan loop enabled (reference thresholds + verified reciprocal division)
 };
 
 struct DevArena {
@@ -48,6 +49,7 @@ struct DevArena {
     uchar2* ipair;
     uint32_t* cand;
     int* cand_count;
+    int* plane_irregular;  // per slot: != 0 if an uploaded plane breaks scan_columns2's preconditions (k_pack)
     float2* rs;
     float* chk;
     float* pts;
@@ -81,6 +83,9 @@ struct DevStats {
 };
 
 #define SDM_FULL 0xffffffffu
+
+// constants of the second-generation scan loop (scan_columns2)
+constexpr float kTheta2 = 0.23f, kRTheta2 = 1.0f / 0.23f, kLambdaG2 = 8.0f, kGradMax2 = 0x1p40f;
 
 // ---------------------------------------------------------------------------------------------
 // cv::fastAtan2 (used at :791), float polynomial in degrees
@@ -327,13 +332,15 @@ __global__ void __launch_bounds__(256) k_pack(DevArena A, DevParams P, int slot,
     const int x = blockIdx.x * kTileW + (lane % kTileW);
     const int y = blockIdx.y * kTileH + warp * (32 / kTileW) + (lane / kTileW);
     const bool in = (x < P.W) && (y < P.H);
-    bool is_cand = false;
+    bool is_cand = false, irregular = false;
     const size_t base = (size_t)slot * A.P;
     if (in) {
         const int y1 = (y + 1 < P.H) ? y + 1 : P.H - 1;
         const size_t i0 = (size_t)y * P.W + x, i1 = (size_t)y1 * P.W + x;
         const float g0 = grad[i0], g1 = grad[i1];
-        A.tex[base + i0] = make_float4(g0, g1, theta[i0], theta[i1]);
+        const float th0 = theta[i0];
+        irregular = !(th0 >= 0.f && th0 <= 360.f) || !(g0 <= kGradMax2);
+        A.tex[base + i0] = make_float4(g0, g1, th0, theta[i1]);
         A.ipair[base + i0] = make_uchar2(im[i0], im[i1]);
         A.rs[base + i0] = make_float2(0.f, 0.f);
         A.dpl[base + i0] = 0.f;
@@ -344,6 +351,89 @@ __global__ void __launch_bounds__(256) k_pack(DevArena A, DevParams P, int slot,
         A.pts[3 * (base + i0) + 1] = 0.f;
         A.pts[3 * (base + i0) + 2] = 0.f;
         is_cand = (edge == nullptr || edge[i0] >= 0) && !(g0 <= P.lambdaG);
+    }
+    const unsigned bal = __ballot_sync(SDM_FULL, is_cand);
+    // scan_pixel_lane<2> relies on orientations in [0, 360] (what cv::phase produces) and finite gradients; anything
+    // else selects the first-generation loop for the keyframes that touch this slot
+    if (__any_sync(SDM_FULL, irregular) && lane == 0) atomicOr(&A.plane_irregular[slot], 1);
+    if (lane == 0) s_wcount[warp] = __popc(bal);
+    __syncthreads();
+    if (warp == 0 && lane == 0) {
+        int tot = 0;
+        for (int w = 0; w < 8; ++w) { int c = s_wcount[w]; s_wcount[w] = tot; tot += c; }
+        s_base = tot ? atomicAdd(&A.cand_count[slot], tot) : 0;
+    }
+    __syncthreads();
+    if (is_cand) {
+        const int pos = s_base + s_wcount[warp] + __popc(bal & ((1u << lane) - 1u));
+        A.cand[base + pos] = ((uint32_t)y << 16) | (uint32_t)x;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K1', plane producers on the device: GradImg / GradTheta of KeyFrame.cc:69-74 from im_
+// alone, then the same packing + candidate compaction as k_pack.  cv::Scharr(.., CV_32F, 1|0, 0|1, 1/32.0)
+// with BORDER_REFLECT_101 is exact (integer sums times 2^-5).  magnitude = sqrtf(gx*gx + gy*gy) and
+// phase = the scalar cv::fastAtan2(gy, gx): OpenCV's SIMD magnitude / phase differ from these scalar forms by
+// <= 1 ulp / 3e-5 deg (and are not reproducible between calls on a multi-threaded host), so the planes
+// are as valid as a host run's, not bit-identical to a particular one.  One block = one 32x8 tile; the
+// (G, theta) of rows y0 .. y0+8 are staged in shared memory because a texel pairs row y with row y+1.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int reflect101(int i, int n) { return i < 0 ? -i : (i >= n ? 2 * n - 2 - i : i); }
+
+__device__ __forceinline__ float2 scharr_mag_phase(const uint8_t* __restrict__ im, int W, int H, int x, int y)
+{
+    const int xm = reflect101(x - 1, W), xp = reflect101(x + 1, W);
+    const int ym = reflect101(y - 1, H), yp = reflect101(y + 1, H);
+    const uint8_t* r0 = im + (size_t)ym * W;
+    const uint8_t* r1 = im + (size_t)y * W;
+    const uint8_t* r2 = im + (size_t)yp * W;
+    const int a00 = r0[xm], a01 = r0[x], a02 = r0[xp];
+    const int a10 = r1[xm], a12 = r1[xp];
+    const int a20 = r2[xm], a21 = r2[x], a22 = r2[xp];
+    const int igx = 3 * (a02 - a00) + 10 * (a12 - a10) + 3 * (a22 - a20);
+    const int igy = 3 * (a20 - a00) + 10 * (a21 - a01) + 3 * (a22 - a02);
+    const float gx = (float)igx * 0.03125f, gy = (float)igy * 0.03125f;  // exact
+    return make_float2(sqrtf(gx * gx + gy * gy), fast_atan2_deg(gy, gx));
+}
+
+__global__ void __launch_bounds__(256)
+k_pack_image(DevArena A, DevParams P, int slot, const uint8_t* __restrict__ im, const int32_t* __restrict__ edge)
+{
+    __shared__ float2 s_gt[9][32];
+    __shared__ int s_wcount[8];
+    __shared__ int s_base;
+    const int lane = threadIdx.x, warp = threadIdx.y;
+    const int x = blockIdx.x * 32 + lane;
+    const int y0 = blockIdx.y * 8;
+    const int y = y0 + warp;
+    const bool in = (x < P.W) && (y < P.H);
+    if (x < P.W) {
+        if (y < P.H) s_gt[warp][lane] = scharr_mag_phase(im, P.W, P.H, x, y);
+        if (warp == 0) {  // row y0 + 8: the lower half of the last row's texels (clamped to the last image row)
+            const int yl = min(y0 + 8, P.H - 1);
+            s_gt[8][lane] = scharr_mag_phase(im, P.W, P.H, x, yl);
+        }
+    }
+    __syncthreads();
+    bool is_cand = false;
+    const size_t base = (size_t)slot * A.P;
+    if (in) {
+        const int y1 = (y + 1 < P.H) ? y + 1 : P.H - 1;
+        const size_t i0 = (size_t)y * P.W + x;
+        const float2 g0 = s_gt[warp][lane];
+        const float2 g1 = s_gt[y1 - y0][lane];
+        A.tex[base + i0] = make_float4(g0.x, g1.x, g0.y, g1.y);
+        A.ipair[base + i0] = make_uchar2(im[i0], im[(size_t)y1 * P.W + x]);
+        A.rs[base + i0] = make_float2(0.f, 0.f);
+        A.dpl[base + i0] = 0.f;
+        A.spl[base + i0] = 0.f;
+        if (A.rs2) A.rs2[base + i0] = make_float2(0.f, 0.f);
+        A.chk[base + i0] = 0.f;
+        A.pts[3 * (base + i0) + 0] = 0.f;
+        A.pts[3 * (base + i0) + 1] = 0.f;
+        A.pts[3 * (base + i0) + 2] = 0.f;
+        is_cand = (edge == nullptr || edge[i0] >= 0) && !(g0.x <= P.lambdaG);
     }
     const unsigned bal = __ballot_sync(SDM_FULL, is_cand);
     if (lane == 0) s_wcount[warp] = __popc(bal);
@@ -358,6 +448,13 @@ __global__ void __launch_bounds__(256) k_pack(DevArena A, DevParams P, int slot,
         const int pos = s_base + s_wcount[warp] + __popc(bal & ((1u << lane) - 1u));
         A.cand[base + pos] = ((uint32_t)y << 16) | (uint32_t)x;
     }
+}
+
+// GradImg / GradTheta of a slot back as dense planes (what KeyFrame::GradImg / GradTheta would hold)
+__global__ void k_split_tex(const float4* __restrict__ tex, float* __restrict__ g, float* __restrict__ t, size_t n)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { float4 v = tex[i]; g[i] = v.x; t[i] = v.z; }
 }
 
 __device__ __forceinline__ void load_item(DevItem& s_item, const DevItem* __restrict__ src_item)
@@ -647,10 +744,103 @@ __device__ __forceinline__ void valid_columns(float ab, float cb, float Hm1, int
     ub = min(u_hi, q - 1);
 }
 
-template <bool kFastGates>
+// ---------------------------------------------------------------------------------------------
+// Second-generation column loop of the lane-per-pixel scan (kMode 2), for the reference's constants
+// (lambdaG = 8, lambdaL = 80, lambdaTheta = 45, THETA = 0.23f; ProbabilityMapping.h:45-56).  Same arithmetic results
+// as the loop in scan_pixel_lane, fewer issued instructions per column (the scan is issue-bound: profiles/README.md):
+//  * no int<->float conversions: the column is carried as a float (exact below 2^24); floor(v) comes from ONE
+//    round-down add, r = v (+)RD 2^23 = 2^23 + floor(v) for 0 <= v < 2^23 (valid_columns guarantees 0 <= v <= H-1
+//    for every column touched, the prefetched one included), so floor(v) = r - 2^23 as a float (exact) and the row
+//    index is the low mantissa of r: texel index = bits(r) * W + (u - 0x4B000000 * W) modulo 2^32.
+//    w1 = v - floor(v) is exact (Sterbenz), hence 1 - w1 and the reference's (floor(v) + 1) - v (:66-84) are roundings
+//    of the same real number: w0 = 1 - w1.  [v = -0 gives w1 = -0 instead of +0: no product, sum or comparison
+//    downstream can tell the two apart.]
+//  * gates 2 and 3 on the RAW difference d = gth - c (c = th_line, ang_pi_rot): the `>= 360` wrap step is dropped and
+//    gate 3 needs no wrap at all; exact for d < 400, every negative d and NaN (tools/verify_gate_algebra2.py, all
+//    2^32 floats).  gth <= 360.0001 when the orientation planes hold [0, 360], and 0 <= c <= 360 when |rot| <= 360.
+//  * x / THETA for x = ge*ge by the correctly rounded reciprocal and two fused steps (Markstein): q0 = x*r,
+//    q = fma(fma(-q0, THETA, x), r, q0), == the IEEE quotient for x = 0 and every x in [2^-80, 2^80] (k_verify_div
+//    runs over that whole range when a context is created and disables this loop on any mismatch).  ge = G1 - G2
+//    with both gradients in (8, 2^40] is 0 or a multiple of 2^-20 below 2^40, so x is always inside.
+//  * only (err, column) of the best column are tracked; its residuals are re-evaluated once after the loop.
+// The preconditions on the planes (orientation in [0, 360], gradient magnitude <= 2^40, no NaN) are checked per
+// keyframe slot by k_pack (plane_irregular); k_pass1_lane falls back to the first-generation loop otherwise.
+// ---------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ float div_by_theta2(float x)
+{
+    const float q0 = __fmul_rn(x, kRTheta2);
+    return __fmaf_rn(__fmaf_rn(-q0, kTheta2, x), kRTheta2, q0);
+}
+
+__global__ void k_verify_div(unsigned long long* mismatches)
+{
+    // x = 0 and every float in [2^-80, 2^80]: bit patterns 0x17800000 .. 0x67800000
+    const unsigned lo = 0x17800000u, hi = 0x67800000u;
+    unsigned long long bad = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) bad += (__float_as_uint(div_by_theta2(0.f)) != 0u);
+    for (unsigned long long b = lo + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b <= hi;
+         b += (unsigned long long)gridDim.x * blockDim.x) {
+        const float x = __uint_as_float((unsigned)b);
+        bad += (__float_as_uint(div_by_theta2(x)) != __float_as_uint(__fdiv_rn(x, kTheta2)));
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+__device__ __forceinline__ void scan_columns2(const float4* __restrict__ tex2, const uchar2* __restrict__ ip2, int W,
+                                              int ua, int ub, float ab, float cb, float th_line, float ang_pi_rot,
+                                              float pixel, float gradc, float& best_err, int& best_n)
+{
+    constexpr float kMagic = 8388608.0f;
+    constexpr float kT2 = -0x1.67fff8p+5f;  // -(45 - 2^-16): fl(d + 360) > 315  <=>  d > kT2
+    const char* tb = reinterpret_cast<const char*>(tex2);
+    const char* ib = reinterpret_cast<const char*>(ip2);
+    unsigned Wm = (unsigned)W;
+    asm volatile("" : "+l"(tb), "+l"(ib), "+r"(Wm));
+    unsigned ubias = (unsigned)ua - 0x4B000000u * Wm;
+    float uf = (float)ua;
+    float vn = -(ab * uf + cb);
+    float r = __fadd_rd(vn, kMagic);
+    float w1n = vn - (r - kMagic);
+    unsigned idxn = __float_as_uint(r) * Wm + ubias;
+    float4 tn = __ldg(reinterpret_cast<const float4*>(tb + (size_t)idxn * 16));
+#pragma unroll 2
+    for (int n = ub - ua + 1; n > 0; --n) {
+        const float4 t = tn;
+        const float w1 = w1n, w0 = 1.0f - w1n;
+        const unsigned idx = idxn;
+        uf += 1.0f;
+        ubias += 1u;
+        vn = -(ab * uf + cb);
+        r = __fadd_rd(vn, kMagic);
+        w1n = vn - (r - kMagic);
+        idxn = __float_as_uint(r) * Wm + ubias;
+        tn = __ldg(reinterpret_cast<const float4*>(tb + (size_t)idxn * 16));
+        const float g2 = t.x * w0 + t.y * w1;
+        if (g2 <= kLambdaG2) continue;  // condition 1
+        const float gth = yangle_interp(t.z, t.w, w0, w1);
+        const float d2 = gth - th_line;  // condition 2
+        const float ang = d2 < 0.f ? d2 + 360.f : d2;
+        if (fabsf(fabsf(ang - 180.f) - 90.f) <= 10.f) continue;
+        const float d3 = gth - ang_pi_rot;  // condition 3
+        if ((d3 >= 45.f || d3 <= kT2) && fabsf(d3) <= 315.f) continue;
+        const uchar2 i2 = __ldg(reinterpret_cast<const uchar2*>(ib + (size_t)idx * 2));
+        const float pe = pixel - ((float)i2.x * w0 + (float)i2.y * w1);
+        const float ge = gradc - g2;
+        const float err = pe * pe + div_by_theta2(ge * ge);
+        if (err < best_err) { best_err = err; best_n = n; }
+    }
+}
+
+// kMode 0: gates for any thresholds; 1: exact short gate forms for lambdaL = 80, lambdaTheta = 45;
+// 2: second-generation column loop (below), same decisions and values as 1 under its two preconditions:
+//    (i) regular planes and |rot| <= 360 (checked per keyframe: k_pack's plane_irregular flags / k_pass1_lane),
+//    (ii) the reference's constants and div_by_theta2 exact (checked when the context is created: k_verify_div).
+template <int kMode>
 __device__ __forceinline__ bool scan_pixel_lane(const DevArena& A, const DevParams& P, const DevItem& s_item,
                                                 float2 (*s_h)[kLaneBlock], int ci, int tid)
 {
+    constexpr bool kFastGates = kMode >= 1;
     const int kf = s_item.kf;
     const int N = s_item.n_nbr;
     const uint32_t packed = A.cand[(size_t)kf * A.P + ci];
@@ -679,7 +869,18 @@ __device__ __forceinline__ bool scan_pixel_lane(const DevArena& A, const DevPara
         // columns whose three rows v(u-1), v(u), v(u+1) are inside the image (:773-785), as one interval
         int ua, ub;
         valid_columns(ab, cb, Hm1, s.u_lo, s.u_hi, ua, ub);
-        if (ua <= ub) {
+        if (kMode == 2) {
+            if (ua <= ub) {
+                int best_n = 0;
+                scan_columns2(tex2, ip2, W, ua, ub, ab, cb, s.th_line, s.ang_pi_rot, pixel, gradc, best_err, best_n);
+                if (best_n > 0) {  // residuals of the best column, same expressions as in the loop
+                    best_u = ub + 1 - best_n;
+                    const float vb = -(ab * (float)best_u + cb);
+                    best_pe = pixel - ylin_im(ip2, W, vb, best_u);
+                    best_ge = gradc - ylin_grad(tex2, W, vb, best_u);
+                }
+            }
+        } else if (ua <= ub) {
             // keep the loop's operands in registers (ptxas otherwise re-derives them from constant memory)
             const char* tb = reinterpret_cast<const char*>(tex2);
             const char* ib = reinterpret_cast<const char*>(ip2);
@@ -776,6 +977,17 @@ __device__ __forceinline__ bool scan_pixel_lane(const DevArena& A, const DevPara
 #ifndef SDM_LANE_MINB
 #define SDM_LANE_MINB 10  // 48 registers: measured optimum on B200 (latency-bound scan; 7 -> 10 blocks/SM = -18 % time)
 #endif
+// scan_pixel_lane<2>'s precondition (i) for the keyframe of s_item (block-uniform)
+__device__ __forceinline__ bool item_regular(const DevArena& A, const DevItem& s_item)
+{
+    int irr = A.plane_irregular[s_item.kf];
+    for (int j = 0; j < s_item.n_nbr; ++j) {
+        const float rot = s_item.pair[j].rot;
+        irr |= A.plane_irregular[s_item.pair[j].slot] | !(rot >= -360.f && rot <= 360.f);
+    }
+    return irr == 0;
+}
+
 template <bool kFastGates>
 __global__ void __launch_bounds__(kLaneBlock, SDM_LANE_MINB)
 k_pass1_lane(DevArena A, DevParams P, const DevItem* __restrict__ items, DevPlan plan, DevStats* stats)
@@ -790,7 +1002,10 @@ k_pass1_lane(DevArena A, DevParams P, const DevItem* __restrict__ items, DevPlan
     while (next_chunk(plan, items, s_item, s_chunk, cur_entry, first)) {
         const int ci = first + tid;
         bool fused = false;
-        if (ci < A.cand_count[s_item.kf]) fused = scan_pixel_lane<kFastGates>(A, P, s_item, s_h, ci, tid);
+        if (ci < A.cand_count[s_item.kf]) {
+            if (kFastGates && P.scan2 && item_regular(A, s_item)) fused = scan_pixel_lane<2>(A, P, s_item, s_h, ci, tid);
+            else fused = scan_pixel_lane<kFastGates ? 1 : 0>(A, P, s_item, s_h, ci, tid);
+        }
         n_fused += __popc(__ballot_sync(SDM_FULL, fused));
     }
     if (stats && (tid & 31) == 0 && n_fused) atomicAdd(&stats->fused, (unsigned long long)n_fused);

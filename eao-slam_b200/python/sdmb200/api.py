@@ -70,8 +70,8 @@ class Stats(C.Structure):
 # every symbol include/sdm_b200.h declares (checked by tests/test_abi.py)
 EXPORTS = [
     "sdm_default_config", "sdm_create", "sdm_destroy", "sdm_last_error", "sdm_version", "sdm_synchronize",
-    "sdm_get_stats", "sdm_host_alloc", "sdm_host_free", "sdm_upload_keyframe", "sdm_set_pose",
-    "sdm_set_intrinsics", "sdm_candidate_count", "sdm_pass1", "sdm_pass2", "sdm_update_points", "sdm_download", "sdm_download_async", "sdm_upload_keyframes", "sdm_download_keyframes", "sdm_export_points",
+    "sdm_get_stats", "sdm_scan_generation", "sdm_host_alloc", "sdm_host_free", "sdm_upload_keyframe", "sdm_set_pose",
+    "sdm_set_intrinsics", "sdm_candidate_count", "sdm_pass1", "sdm_pass2", "sdm_update_points", "sdm_download", "sdm_download_async", "sdm_upload_keyframes", "sdm_download_keyframes", "sdm_export_points", "sdm_download_planes",
     "sdm_upload_depth", "sdm_depth_plane_ptr", "sdm_export_arena", "sdm_import_peer_arena", "sdm_pull_halo",
     "sdm_mark_pass1_done", "sdm_pair_geometry", "sdm_stereo_search_constraints", "sdm_search_range",
     "sdm_epipolar_search", "sdm_epipolar_search_plane", "sdm_fuse", "sdm_intra_check", "sdm_intra_grow",
@@ -100,6 +100,7 @@ def load() -> C.CDLL:
     lib.sdm_version.restype = C.c_char_p
     lib.sdm_synchronize.argtypes = [vp]
     lib.sdm_get_stats.argtypes = [vp, C.POINTER(Stats)]
+    lib.sdm_scan_generation.argtypes = [vp]
     lib.sdm_host_alloc.argtypes = [C.POINTER(vp), sz]
     lib.sdm_host_free.argtypes = [vp]
     lib.sdm_upload_keyframe.argtypes = [vp, C.c_int, vp, sz, vp, sz, vp, sz, vp, sz, fp, fp]
@@ -113,6 +114,7 @@ def load() -> C.CDLL:
     lib.sdm_download_async.argtypes = [vp, C.c_int, vp, sz, vp, sz, vp, sz, vp, sz]
     lib.sdm_upload_keyframes.argtypes = [vp, C.c_int, C.POINTER(UploadDesc)]
     lib.sdm_download_keyframes.argtypes = [vp, C.c_int, C.POINTER(DownloadDesc)]
+    lib.sdm_download_planes.argtypes = [vp, C.c_int, vp, sz, vp, sz]
     lib.sdm_export_points.argtypes = [vp, C.c_int, ip, C.c_double, vp, sz, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.sdm_upload_depth.argtypes = [vp, C.c_int, vp, sz, vp, sz]
     lib.sdm_depth_plane_ptr.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(sz)]
@@ -212,25 +214,30 @@ class Context:
         """Arrays may be row-pitched views (positive strides, unit column stride)."""
         def chk(a, dt, esz):
             assert a.dtype == dt and a.shape == (self.H, self.W) and a.strides[1] == esz, (a.dtype, a.shape, a.strides)
-        chk(im, np.uint8, 1); chk(grad, np.float32, 4); chk(theta, np.float32, 4)
+        chk(im, np.uint8, 1)
+        if grad is not None or theta is not None:
+            chk(grad, np.float32, 4); chk(theta, np.float32, 4)
         if edge is not None:
             chk(edge, np.int32, 4)
         Kf, Tf = _f32(np.asarray(K).reshape(4)), _f32(np.asarray(Tcw).reshape(-1)[:12])
         self._chk(self.lib.sdm_upload_keyframe(
-            self.h, slot, im.ctypes.data, im.strides[0], grad.ctypes.data, grad.strides[0],
-            theta.ctypes.data, theta.strides[0],
+            self.h, slot, im.ctypes.data, im.strides[0],
+            grad.ctypes.data if grad is not None else None, grad.strides[0] if grad is not None else 0,
+            theta.ctypes.data if theta is not None else None, theta.strides[0] if theta is not None else 0,
             edge.ctypes.data if edge is not None else None, edge.strides[0] if edge is not None else 0,
             _fp(Kf), _fp(Tf)))
 
-    def upload_descs(self, scene, indices, slot_of=None):
-        """sdm_upload_desc array for keyframes `indices` of a scene (arrays must stay alive until synchronize)."""
+    def upload_descs(self, scene, indices, slot_of=None, images_only=False):
+        """sdm_upload_desc array for keyframes `indices` of a scene (arrays must stay alive until synchronize).
+        images_only: leave grad / theta NULL so that the planes are produced on the device."""
         idx = list(indices)
         arr = (UploadDesc * len(idx))()
         for a, i in zip(arr, idx):
             a.kf = int(i if slot_of is None else slot_of[i])
             a.im, a.im_step = scene.im[i].ctypes.data, scene.im[i].strides[0]
-            a.grad, a.grad_step = scene.grad[i].ctypes.data, scene.grad[i].strides[0]
-            a.theta, a.theta_step = scene.theta[i].ctypes.data, scene.theta[i].strides[0]
+            if not images_only:
+                a.grad, a.grad_step = scene.grad[i].ctypes.data, scene.grad[i].strides[0]
+                a.theta, a.theta_step = scene.theta[i].ctypes.data, scene.theta[i].strides[0]
             if scene.edge is not None:
                 a.edge, a.edge_step = scene.edge[i].ctypes.data, scene.edge[i].strides[0]
             for j, v in enumerate(scene.K):
@@ -315,9 +322,17 @@ class Context:
                                              counts.ctypes.data_as(up), C.byref(total)))
         return pts[:min(capacity, int(total.value))], counts, int(total.value)
 
+    def download_planes(self, slot):
+        g, t = np.empty((self.H, self.W), np.float32), np.empty((self.H, self.W), np.float32)
+        self._chk(self.lib.sdm_download_planes(self.h, slot, g.ctypes.data, g.strides[0], t.ctypes.data, t.strides[0]))
+        return g, t
+
     def upload_depth(self, slot, depth, sigma):
         d, s = _f32(depth), _f32(sigma)
         self._chk(self.lib.sdm_upload_depth(self.h, slot, d.ctypes.data, d.strides[0], s.ctypes.data, s.strides[0]))
+
+    def scan_generation(self) -> int:
+        return int(self.lib.sdm_scan_generation(self.h))
 
     def stats(self) -> dict:
         st = Stats()

@@ -97,6 +97,11 @@ const char* sdm_last_error(void);
 const char* sdm_version(void);
 int sdm_synchronize(sdm_ctx* ctx);
 int sdm_get_stats(sdm_ctx* ctx, sdm_stats* out);
+/* which column loop sdm_pass1 runs for keyframes with regular planes: 2 = second generation (reference thresholds
+ * lambdaL = 80 / lambdaTheta = 45 and the reciprocal form of x / theta verified for this theta at sdm_create),
+ * 1 = first generation (any thresholds; also used per keyframe when an orientation plane holds values outside
+ * [0, 360] or |rot| > 360; env SDM_SCAN=lane1 forces it).  Results are bit-identical either way. */
+int sdm_scan_generation(sdm_ctx* ctx);
 
 /* pinned host memory for asynchronous uploads/downloads (optional; any host pointer is accepted) */
 int sdm_host_alloc(void** ptr, size_t bytes);
@@ -107,6 +112,11 @@ int sdm_host_free(void* ptr);
  * LineDetector::DetectEdgeMap (LineDetector.cc:843-881), as device-resident packed buffers, and the
  * candidate test of :454-456 (compaction).  Steps are in BYTES (cv::Mat::step).  edge may be NULL
  * (every pixel passes :454).  K = {fx, fy, cx, cy}; Tcw = rows 0..2 of the 4x4 pose, row-major.
+ * grad and theta may BOTH be NULL: GradImg / GradTheta are then produced on the device from im (SURVEY.md
+ * 8f-1; replaces KeyFrame.cc:69-74: cv::Scharr x2 with scale 1/32 [exact], magnitude = sqrtf(gx*gx + gy*gy),
+ * phase = the scalar cv::fastAtan2 in degrees).  OpenCV's SIMD magnitude / phase differ from these scalar forms
+ * by <= 1 ulp / 3e-5 deg and are not reproducible between calls on a multi-threaded host, so device-produced
+ * planes are as valid as a host run's but not bit-identical to a particular one; sdm_download_planes returns them.
  * Asynchronous: host buffers must stay valid until sdm_synchronize / the next blocking call. */
 int sdm_upload_keyframe(sdm_ctx* ctx, int kf,
                         const uint8_t* im, size_t im_step,
@@ -126,6 +136,8 @@ typedef struct {
     float Tcw[12];
 } sdm_upload_desc;
 int sdm_upload_keyframes(sdm_ctx* ctx, int n, const sdm_upload_desc* desc);
+/* GradImg / GradTheta of a slot as dense planes (what KeyFrame::GradImg / GradTheta hold, KeyFrame.h:160); blocking */
+int sdm_download_planes(sdm_ctx* ctx, int kf, float* grad, size_t grad_step, float* theta, size_t theta_step);
 /* replaces: KeyFrame::SetPose (KeyFrame.cc:108-124) for PoseChanged refresh (:691-694) */
 int sdm_set_pose(sdm_ctx* ctx, int kf, const float Tcw[12]);
 /* calibration of a slot (KeyFrame::fx,fy,cx,cy; Frame.cc:584-590).  With sdm_set_pose this is all a

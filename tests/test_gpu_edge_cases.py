@@ -100,3 +100,42 @@ def test_slot_reuse_and_partial_batches():
             ctx.pass2(api.make_items([i], b.nbr_idx, b.rot, b.min_depth, b.max_depth))
         dev = {k: np.stack([ctx.download(i)[k] for i in range(8)]) for k in ("depth", "sigma", "checked", "points")}
     assert _bit_equal(dev, ob) == {"depth": 0, "sigma": 0, "checked": 0, "points": 0}
+
+
+def test_scan_generations_agree(monkeypatch):
+    """the second-generation column loop (default for the reference's constants) and the first-generation one
+    (SDM_SCAN=lane1, or any other threshold set) give the oracle's bits"""
+    sc = synth.make_scene(10, 320, 240, 6, seed=21, contrast=0.9)
+    osc = run_oracle(sc)
+    zero = {"depth": 0, "sigma": 0, "checked": 0, "points": 0}
+    with api.Context(width=320, height=240, max_keyframes=sc.n) as ctx:
+        assert ctx.scan_generation() == 2          # k_verify_div passed for THETA = 0.23f
+        assert _bit_equal(run_device(sc, ctx=ctx), osc) == zero
+    monkeypatch.setenv("SDM_SCAN", "lane1")
+    with api.Context(width=320, height=240, max_keyframes=sc.n) as ctx:
+        assert ctx.scan_generation() == 1
+        assert _bit_equal(run_device(sc, ctx=ctx), osc) == zero
+    monkeypatch.delenv("SDM_SCAN")
+    with api.Context(width=320, height=240, max_keyframes=sc.n, lambdaG=9) as ctx:
+        assert ctx.scan_generation() == 1          # not the reference's constants
+
+
+def test_gate_boundaries_and_irregular_rot():
+    """orientation planes quantised to 5 degrees (with exact 0 and 360 entries) make the raw differences of gates 2 / 3
+    land exactly on 45, 315, -45, -315, 80, 100 ...: the short gate forms of scan_columns2 must decide like the
+    reference's fold sequences there.  A relative roll outside [-360, 360] sends its keyframe through the
+    first-generation loop (same bits)."""
+    sc = synth.make_scene(8, 200, 150, 6, seed=22, contrast=0.9)
+    q = np.round(sc.theta / 5.0) * 5.0
+    q[q > 360.0] = 360.0
+    sc.theta[:] = q.astype(np.float32)
+    assert (sc.theta == 360.0).any() and (sc.theta == 0.0).any()
+    zero = {"depth": 0, "sigma": 0, "checked": 0, "points": 0}
+    osc, dev = run_oracle(sc), run_device(sc)
+    assert _bit_equal(dev, osc) == zero
+    assert (osc.depth > 0).sum() > 1000
+    sc.rot[2][:] = 45.0                    # regular: gate 3 against th_pi + 45
+    sc.rot[4][:] = -315.0
+    sc.rot[5][:] = 725.0                   # irregular: first-generation loop for keyframe 5
+    osc, dev = run_oracle(sc), run_device(sc)
+    assert _bit_equal(dev, osc) == zero

@@ -102,3 +102,29 @@ def test_pinned_memory_timing_and_stats(scene):
         assert st["candidates"] == int((sc.grad > 8).sum()) and 0 < st["checked"] <= st["fused"] <= st["candidates"]
         with pytest.raises(api.SdmError):
             ctx.elapsed_ms(2, 3)                           # marks never recorded
+
+
+def test_planes_produced_on_the_device(scene):
+    """sdm_upload_keyframes with grad = theta = NULL: Scharr/32 + sqrt + scalar fastAtan2 on the device reproduce
+    the scalar-form planes of the generator bit for bit, so the whole loop gives the same planes as the upload of
+    host-produced GradImg / GradTheta (and H2D shrinks from 9 to 1 byte per pixel)."""
+    sc = scene
+    osc = run_oracle(sc)
+    H, W = sc.shape
+    with api.Context(width=W, height=H, max_keyframes=sc.n) as ctx:
+        ctx.upload_keyframes(ctx.upload_descs(sc, range(sc.n), images_only=True))
+        for i in (0, 4, sc.n - 1):
+            g, t = ctx.download_planes(i)
+            assert _bits(g, sc.grad[i]) == 0 and _bits(t, sc.theta[i]) == 0
+            assert ctx.candidate_count(i) == int((sc.grad[i] > 8).sum())
+        items = api.make_items(range(sc.n), sc.nbr_idx, sc.rot, sc.min_depth, sc.max_depth)
+        ctx.pass1(items); ctx.pass2(items)
+        for i in range(sc.n):
+            got = ctx.download(i)
+            assert _bits(got["depth"], osc.depth[i]) == 0 and _bits(got["checked"], osc.checked[i]) == 0
+    # odd size: borders (BORDER_REFLECT_101) and partial tiles
+    sc2 = synth.make_scene(2, 45, 19, 1, seed=3, contrast=0.9)
+    with api.Context(width=45, height=19, max_keyframes=2) as ctx:
+        ctx.upload_keyframe(0, sc2.im[0], None, None, None, sc2.K, sc2.Tcw[0])
+        g, t = ctx.download_planes(0)
+        assert _bits(g, sc2.grad[0]) == 0 and _bits(t, sc2.theta[0]) == 0

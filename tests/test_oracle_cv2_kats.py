@@ -104,3 +104,11 @@ def test_scharr_numpy_matches_cv2(kat):
     assert np.array_equal(gy.astype(np.float32), kat["sch_gy"])
     g, t = synth.gradient_planes(im)
     assert g.shape == im.shape and t.shape == im.shape
+
+
+def test_numpy_fast_atan2_matches_cv2(kat):
+    """the generator's scalar-form phase (synth._fast_atan2_deg, also what the device plane producer computes)
+    == cv2.fastAtan2 on the known-answer inputs"""
+    from sdmb200 import synth
+    out = synth._fast_atan2_deg(kat["atan_y"].astype(np.float32), kat["atan_x"].astype(np.float32))
+    assert np.array_equal(bits(out), bits(kat["atan_out"]))
