@@ -787,6 +787,10 @@ __global__ void k_verify_div(unsigned long long* mismatches)
     if (bad) atomicAdd(mismatches, bad);
 }
 
+#ifndef SDM_SCAN2_UNROLL
+#define SDM_SCAN2_UNROLL 2
+#endif
+constexpr int kScan2Unroll = SDM_SCAN2_UNROLL;
 __device__ __forceinline__ void scan_columns2(const float4* __restrict__ tex2, const uchar2* __restrict__ ip2, int W,
                                               int ua, int ub, float ab, float cb, float th_line, float ang_pi_rot,
                                               float pixel, float gradc, float& best_err, int& best_n)
@@ -804,7 +808,7 @@ __device__ __forceinline__ void scan_columns2(const float4* __restrict__ tex2, c
     float w1n = vn - (r - kMagic);
     unsigned idxn = __float_as_uint(r) * Wm + ubias;
     float4 tn = __ldg(reinterpret_cast<const float4*>(tb + (size_t)idxn * 16));
-#pragma unroll 2
+#pragma unroll kScan2Unroll
     for (int n = ub - ua + 1; n > 0; --n) {
         const float4 t = tn;
         const float w1 = w1n, w0 = 1.0f - w1n;
@@ -946,6 +950,24 @@ __device__ __forceinline__ bool scan_pixel_lane(const DevArena& A, const DevPara
     if (nh > P.lambdaN) {
         unsigned best_mask = 0;
         int best_n = 0;
+        if (nh <= 8) {
+            // ChiTest is symmetric bit for bit ((a-b)^2 == (b-a)^2, float + commutes): each unordered pair once,
+            // compatibility matrix in 64 bits (row a = bits 8a .. 8a+7)
+            unsigned long long M = 0ULL;
+            for (int a = 0; a + 1 < nh; ++a) {
+                const float2 ha = s_h[a][tid];
+                for (int b = a + 1; b < nh; ++b) {
+                    const float2 hb = s_h[b][tid];
+                    if (chi_compatible(ha.x, hb.x, ha.y, hb.y, P.chi_fusion_lt))
+                        M |= (1ULL << (8 * a + b)) | (1ULL << (8 * b + a));
+                }
+            }
+            for (int a = 0; a < nh; ++a) {
+                const unsigned m = ((unsigned)(M >> (8 * a)) & 0xffu) | (1u << a);
+                const int cnt = __popc(m);
+                if (best_n < cnt) { best_n = cnt; best_mask = m; }
+            }
+        } else
         for (int a = 0; a < nh; ++a) {
             const float2 ha = s_h[a][tid];
             unsigned m = 1u << a;
@@ -975,7 +997,8 @@ __device__ __forceinline__ bool scan_pixel_lane(const DevArena& A, const DevPara
 }
 
 #ifndef SDM_LANE_MINB
-#define SDM_LANE_MINB 10  // 48 registers: measured optimum on B200 (latency-bound scan; 7 -> 10 blocks/SM = -18 % time)
+#define SDM_LANE_MINB 12  // 40 registers, 48 warps / SM: measured optimum on B200 with the second-generation loop
+                          // (blocks/SM 9: 11.09 ms, 10: 10.71, 12: 10.32, 16: 10.50 per 200 keyframes; the spills are outside the loop)
 #endif
 // scan_pixel_lane<2>'s precondition (i) for the keyframe of s_item (block-uniform)
 __device__ __forceinline__ bool item_regular(const DevArena& A, const DevItem& s_item)
