@@ -273,6 +273,7 @@ def main_ours(a, rank, world, local_rank):
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from sdmb200 import api
+    os.environ.setdefault("SDM_SCATTER_THREADS", str(max(2, min(6, (os.cpu_count() or 8) // world - 1))))
     lib = api.load()  # raises if the CUDA library is absent: there is no fallback
     ctx = api.Context(width=W, height=H, max_keyframes=plan.n_local, intra_check=a.intra, intra_grow=a.intra,
                       device=local_rank)
@@ -361,26 +362,41 @@ def main_ours(a, rank, world, local_rank):
 
     t_e2e = [0.0]
 
-    def e2e_step():
+    # dl4: all four planes of a keyframe in one descriptor, for sdm_scatter_keyframes (sparse records + host scatter)
+    dl4 = (api.DownloadDesc * len(owned))()
+    for j, s in enumerate(owned):
+        dl4[j].kf = s
+        dl4[j].depth, dl4[j].depth_step = dl1[j].depth, 4 * W
+        dl4[j].sigma, dl4[j].sigma_step = dl1[j].sigma, 4 * W
+        dl4[j].checked, dl4[j].checked_step = dl2[j].checked, 4 * W
+        dl4[j].points, dl4[j].points_step = dl2[j].points, 12 * W
+
+    def e2e_step(sparse=False):
         t_e2e[0] = time.perf_counter()
         nxt, deferred = 0, []
+
+        def results(k):  # pass 2 of chunk k, then its results to the host planes
+            chk(lib.sdm_pass2(ctx.h, len(chunk_items[k]), chunk_items[k]))
+            if sparse:
+                chk(lib.sdm_scatter_keyframes(ctx.h, len(chunks[k]), dl_ptr(dl4, chunks[k])))
+            else:
+                chk(lib.sdm_download_keyframes(ctx.h, len(chunks[k]), dl_ptr(dl2, chunks[k])))
         for k in range(len(chunks)):
             if nxt <= chunk_need[k]:
                 chk(lib.sdm_upload_keyframes(ctx.h, chunk_need[k] + 1 - nxt, up_ptr(nxt))); nxt = chunk_need[k] + 1
             chk(lib.sdm_pass1(ctx.h, len(chunk_items[k]), chunk_items[k]))
-            chk(lib.sdm_download_keyframes(ctx.h, len(chunks[k]), dl_ptr(dl1, chunks[k])))
+            if not sparse:
+                chk(lib.sdm_download_keyframes(ctx.h, len(chunks[k]), dl_ptr(dl1, chunks[k])))
             if k >= 1:
                 if needs_halo[k - 1]:
                     deferred.append(k - 1)
                 else:
-                    chk(lib.sdm_pass2(ctx.h, len(chunk_items[k - 1]), chunk_items[k - 1]))
-                    chk(lib.sdm_download_keyframes(ctx.h, len(chunks[k - 1]), dl_ptr(dl2, chunks[k - 1])))
+                    results(k - 1)
         if nxt < n_loc:
             chk(lib.sdm_upload_keyframes(ctx.h, n_loc - nxt, up_ptr(nxt)))
         exchange()
         for k in deferred + [len(chunks) - 1]:
-            chk(lib.sdm_pass2(ctx.h, len(chunk_items[k]), chunk_items[k]))
-            chk(lib.sdm_download_keyframes(ctx.h, len(chunks[k]), dl_ptr(dl2, chunks[k])))
+            results(k)
         if dbg:
             t_issue = time.perf_counter()
         ctx.synchronize()
@@ -428,6 +444,22 @@ def main_ours(a, rank, world, local_rank):
             e2e_step()
         barrier(); e2e_s = (time.perf_counter() - tt) / a.steps
         e2e = {"sec": e2e_s, "h2d": int(n_loc * W * H * 9), "d2h": int(len(owned) * W * H * 24)}
+        # the same loop with sdm_scatter_keyframes: the planes start zero-initialised like KeyFrame.cc:78-81 leaves them
+        # and only the candidate pixels' records cross PCIe.  Checked against the dense result on every 7th keyframe.
+        ref = {k: out[k][::7].copy() for k in out}
+        for k in out:
+            out[k][:] = 0
+        e2e_step(sparse=True)
+        same = all(np.array_equal(out[k][::7].view(np.uint32), ref[k].view(np.uint32)) for k in out)
+        if not same:
+            print("WARNING: sdm_scatter_keyframes planes differ from sdm_download_keyframes planes", file=sys.stderr)
+        barrier(); tt = time.perf_counter()
+        for _ in range(a.steps):
+            e2e_step(sparse=True)
+        barrier()
+        e2e["sparse_sec"] = (time.perf_counter() - tt) / a.steps
+        e2e["sparse_same"] = bool(same)
+        e2e["sparse_d2h"] = int(28 * cands)
         # the same loop for consumers that only need the surviving points (SaveSemiDensePoints / DrawSemiDense / CARV:
         # sigma <= 0.02 and checked > 1e-6): upload + both passes + sdm_export_points instead of the dense downloads
         if world == 1:
@@ -479,11 +511,13 @@ def main_ours(a, rank, world, local_rank):
         clocks.stop()
 
     tot_cands, ms_max, e2e_max = cands, ms, (e2e["sec"] if e2e else 0.0)
+    sparse_max, sparse_same = (e2e["sparse_sec"] if e2e else 0.0), (1.0 if (e2e and e2e["sparse_same"]) else 0.0)
     if world > 1:
         v = torch.tensor([float(cands)], device="cuda", dtype=torch.float64)
         dist.all_reduce(v); tot_cands = int(v.item())
-        m = torch.tensor([ms, e2e_max], device="cuda", dtype=torch.float64)
-        dist.all_reduce(m, op=dist.ReduceOp.MAX); ms_max, e2e_max = m.tolist()
+        m = torch.tensor([ms, e2e_max, sparse_max, -sparse_same], device="cuda", dtype=torch.float64)
+        dist.all_reduce(m, op=dist.ReduceOp.MAX); ms_max, e2e_max, sparse_max, sparse_same = m.tolist()
+        sparse_same = -sparse_same
     if rank != 0:
         ctx.close()
         if world > 1:
@@ -514,9 +548,21 @@ def main_ours(a, rank, world, local_rank):
         "gpu_launches": int(launches),
     }
     if e2e:
-        line["e2e"] = {"value": tot_cands / e2e_max, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
-                       "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": 1e3 * e2e_max,
-                       "api": "sdm_upload_keyframes / sdm_pass1 / sdm_pass2 / sdm_download_keyframes on pinned host planes, chunks of " + str(CH) + " keyframes"}
+        dense = {"value": tot_cands / e2e_max, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
+                 "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": 1e3 * e2e_max,
+                 "api": "sdm_upload_keyframes / sdm_pass1 / sdm_pass2 / sdm_download_keyframes on pinned host planes, chunks of " + str(CH) + " keyframes"}
+        sparse = {"value": tot_cands / sparse_max, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
+                  "d2h_bytes_per_step": e2e["sparse_d2h"], "ms_per_step": 1e3 * sparse_max,
+                  "identical_to_dense_download": bool(sparse_same > 0.5),
+                  "scatter_threads": int(os.environ.get("SDM_SCATTER_THREADS", "6")),
+                  "api": "sdm_upload_keyframes / sdm_pass1 / sdm_pass2 / sdm_scatter_keyframes: the four output planes of every "
+                         "keyframe in pinned host memory, zero-initialised as KeyFrame.cc:78-81 leaves them; the candidate "
+                         "pixels' records cross PCIe and the library's worker threads write them into the planes; chunks of "
+                         + str(CH) + " keyframes"}
+        # headline = the dense download (no assumption about the destination planes).  The sparse path moves 3.7x fewer
+        # bytes over PCIe but its host-side scatter touches nearly every cache line of the planes at this candidate
+        # density (23 %), so it is host-memory bound and slower here; reported as a variant.
+        line["e2e"], line["e2e_scatter"] = dense, sparse
         if "export_sec" in e2e:
             line["e2e_point_export"] = {"value": tot_cands / e2e["export_sec"], "unit": UNIT, "ms_per_step": 1e3 * e2e["export_sec"],
                                         "points_per_step": e2e["export_points"], "d2h_bytes_per_step": 16 * e2e["export_points"],

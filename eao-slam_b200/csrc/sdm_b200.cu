@@ -18,12 +18,16 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <deque>
+#include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/sdm_b200.h"
@@ -120,6 +124,7 @@ struct KfState {
     uint64_t comp_id = 0;     // last kernel (k_pack, pass, pull) touching the slot
     uint64_t down_ds_id = 0;  // last download of depth_map_ / depth_sigma_ (pass 1 and the intra stencils overwrite them)
     uint64_t down_cp_id = 0;  // last download of depth_map_checked_ / points (pass 2 overwrites them)
+    uint64_t count_id = 0;    // compute-ring id after which h_cand[slot] holds the slot's candidate count
 };
 
 struct UpStage {
@@ -144,6 +149,79 @@ struct ItemStage {
     uint64_t busy = 0;  // compute-ring id after the last kernel that reads the device copy
 };
 
+// sdm_scatter_keyframes: sparse D2H + host-side scatter.  The calling thread enqueues k_gather_sparse and ONE
+// contiguous D2H per keyframe into a ring of staging buffers; worker threads wait for the copy's event and write
+// the records into the caller's planes.
+constexpr int kScatStages = 16;
+struct ScatStage {
+    uint32_t* dev = nullptr;
+    uint32_t* host = nullptr;  // pinned
+    cudaEvent_t ev = nullptr;
+    bool free_ = true;
+};
+struct ScatJob {
+    int stage;
+    int n;
+    int W;
+    sdm_download_desc d;
+};
+struct Scatter {
+    ScatStage st[kScatStages];
+    std::vector<std::thread> workers;
+    std::mutex mu;
+    std::condition_variable cv_job, cv_free, cv_idle;
+    std::deque<ScatJob> jobs;
+    int next = 0;
+    long pending = 0;
+    bool stop = false;
+    std::string err;
+};
+
+void scatter_records(const ScatJob& j, const uint32_t* rec)
+{
+    const size_t n = (size_t)j.n;
+    const uint32_t* pix = rec;
+    const float* f = reinterpret_cast<const float*>(rec);
+    const float *rho = f + n, *sig = f + 2 * n, *chk = f + 3 * n, *pts = f + 4 * n;
+    const sdm_download_desc& d = j.d;
+    for (size_t i = 0; i < n; ++i) {
+        const uint32_t p = pix[i];
+        const size_t x = p & 0xffffu, y = p >> 16;
+        if (d.depth) *reinterpret_cast<float*>(reinterpret_cast<char*>(d.depth) + y * d.depth_step + 4 * x) = rho[i];
+        if (d.sigma) *reinterpret_cast<float*>(reinterpret_cast<char*>(d.sigma) + y * d.sigma_step + 4 * x) = sig[i];
+        if (d.checked) *reinterpret_cast<float*>(reinterpret_cast<char*>(d.checked) + y * d.checked_step + 4 * x) = chk[i];
+        if (d.points) {
+            float* q = reinterpret_cast<float*>(reinterpret_cast<char*>(d.points) + y * d.points_step + 12 * x);
+            q[0] = pts[3 * i]; q[1] = pts[3 * i + 1]; q[2] = pts[3 * i + 2];
+        }
+    }
+}
+
+void scatter_worker(Scatter* S, int device)
+{
+    cudaSetDevice(device);
+    for (;;) {
+        ScatJob j;
+        {
+            std::unique_lock<std::mutex> lk(S->mu);
+            S->cv_job.wait(lk, [&] { return S->stop || !S->jobs.empty(); });
+            if (S->jobs.empty()) return;  // stop requested and nothing left
+            j = S->jobs.front();
+            S->jobs.pop_front();
+        }
+        const cudaError_t e = cudaEventSynchronize(S->st[j.stage].ev);
+        if (e == cudaSuccess) scatter_records(j, S->st[j.stage].host);
+        {
+            std::lock_guard<std::mutex> lk(S->mu);
+            if (e != cudaSuccess && S->err.empty()) S->err = cudaGetErrorString(e);
+            S->st[j.stage].free_ = true;
+            --S->pending;
+        }
+        S->cv_free.notify_all();
+        S->cv_idle.notify_all();
+    }
+}
+
 }  // namespace
 
 struct sdm_ctx {
@@ -165,6 +243,8 @@ struct sdm_ctx {
     ItemStage ist[kItemStages];
     int ist_next = 0;
     int* h_count = nullptr;  // pinned, sdm_candidate_count
+    int* h_cand = nullptr;   // pinned + device-visible: candidate count per slot, published by k_publish_counts
+    Scatter* scat = nullptr;  // created by the first sdm_scatter_keyframes
     // device work orders of the current pass
     sdm::DevItem* d_items = nullptr;  // = the current pass's ItemStage buffers
     int* d_aux = nullptr;
@@ -467,7 +547,22 @@ void sdm_destroy(sdm_ctx* c)
         cudaFree(s.d_items);
         cudaFree(s.d_aux);
     }
+    if (c->scat) {
+        {
+            std::lock_guard<std::mutex> lk(c->scat->mu);
+            c->scat->stop = true;
+        }
+        c->scat->cv_job.notify_all();
+        for (auto& t : c->scat->workers) t.join();
+        for (auto& st : c->scat->st) {
+            cudaFree(st.dev);
+            if (st.host) cudaFreeHost(st.host);
+            if (st.ev) cudaEventDestroy(st.ev);
+        }
+        delete c->scat;
+    }
     if (c->h_count) cudaFreeHost(c->h_count);
+    if (c->h_cand) cudaFreeHost(c->h_cand);
     cudaFree(c->d_chunk_off); cudaFree(c->d_counter); cudaFree(c->d_stats);
     cudaFree(c->tmp_rs); cudaFree(c->xfer); cudaFree(c->dbg); cudaFree(c->exp_buf); cudaFree(c->exp_pts);
     for (cudaEvent_t e : {c->ev_p1[0], c->ev_p1[1], c->ev_p2[0], c->ev_p2[1], c->ev_p1_scan})
@@ -558,6 +653,8 @@ static int create_impl(sdm_ctx* c)
     }
     for (auto& s : c->down) CU(cudaMalloc(&s.planes, 2 * P * sizeof(float)));
     CU(cudaMallocHost(&c->h_count, sizeof(int)));
+    CU(cudaMallocHost(&c->h_cand, n * sizeof(int)));
+    memset(c->h_cand, 0, n * sizeof(int));
     CU(cudaMalloc(&c->d_counter, sizeof(int)));
     CU(cudaMalloc(&c->d_stats, sizeof(sdm::DevStats)));
     CU(cudaMemsetAsync(c->d_stats, 0, sizeof(sdm::DevStats), c->s_compute));
@@ -623,6 +720,15 @@ int sdm_synchronize(sdm_ctx* c)
     CU(cudaStreamSynchronize(c->s_copy));
     CU(cudaStreamSynchronize(c->s_compute));
     CU(cudaStreamSynchronize(c->s_down));
+    if (c->scat) {  // host-side scatters of sdm_scatter_keyframes
+        std::unique_lock<std::mutex> lk(c->scat->mu);
+        c->scat->cv_idle.wait(lk, [&] { return c->scat->pending == 0; });
+        if (!c->scat->err.empty()) {
+            const std::string e = c->scat->err;
+            c->scat->err.clear();
+            return fail(SDM_ERR_CUDA, "scatter worker: %s", e.c_str());
+        }
+    }
     trace_dump(c);
     return SDM_OK;
 }
@@ -706,9 +812,13 @@ int sdm_upload_keyframes(sdm_ctx* c, int n, const sdm_upload_desc* d)
             else  // GradImg / GradTheta produced on the device from im_ (KeyFrame.cc:69-74)
                 sdm::k_pack_image<<<tile_grid(c), dim3(32, 8), 0, c->s_compute>>>(c->A, c->P, u.kf, st.im, u.edge ? st.edge : nullptr);
         }
+        static_assert(kUpStages / 2 <= sdm::kSlotList, "slot list of k_publish_counts");
+        sdm::SlotList sl;
+        for (int i = 0; i < m; ++i) sl.s[i] = d[i0 + i].kf;
+        sdm::k_publish_counts<<<1, 32, 0, c->s_compute>>>(c->A.cand_count, sl, m, c->h_cand);
         CU(cudaGetLastError());
         trace_end(c, c->s_compute);
-        c->launches += m;
+        c->launches += m + 1;
         uint64_t id = 0;
         RC(c->r_compute.record(c->s_compute, &id));
         for (int i = 0; i < m; ++i) {
@@ -716,6 +826,7 @@ int sdm_upload_keyframes(sdm_ctx* c, int n, const sdm_upload_desc* d)
             c->up[(first_stage + i) % kUpStages].busy = id;
             KfState& k = c->kf[u.kf];
             k.comp_id = id;
+            k.count_id = id;
             k.uploaded = true;
             k.pass1_done = false;
             k.rs_dense = false;
@@ -921,6 +1032,79 @@ int sdm_download_keyframes(sdm_ctx* c, int n, const sdm_download_desc* d)
     for (int i = 0; i < n; ++i) {
         if (d[i].depth || d[i].sigma) c->kf[d[i].kf].down_ds_id = id;
         if (d[i].checked || d[i].points) c->kf[d[i].kf].down_cp_id = id;
+    }
+    return SDM_OK;
+}
+
+static int scatter_init(sdm_ctx* c)
+{
+    Scatter* S = new (std::nothrow) Scatter();
+    if (!S) return fail(SDM_ERR_NOMEM, "out of host memory");
+    c->scat = S;
+    const size_t bytes = 28 * c->npix;  // worst case: every pixel a candidate
+    for (auto& st : S->st) {
+        CU(cudaMalloc(&st.dev, bytes));
+        CU(cudaMallocHost(&st.host, bytes));
+        CU(cudaEventCreateWithFlags(&st.ev, cudaEventDisableTiming | cudaEventBlockingSync));
+    }
+    int nt = 6;
+    if (const char* e = getenv("SDM_SCATTER_THREADS")) nt = std::max(1, std::min(64, atoi(e)));
+    for (int i = 0; i < nt; ++i) S->workers.emplace_back(scatter_worker, S, c->cfg.device);
+    return SDM_OK;
+}
+
+int sdm_scatter_keyframes(sdm_ctx* c, int n, const sdm_download_desc* d)
+{
+    if (!c || (n > 0 && !d)) return fail(SDM_ERR_ARG, "sdm_scatter_keyframes: null argument");
+    const int W = c->cfg.width;
+    const size_t row = (size_t)W * 4;
+    for (int i = 0; i < n; ++i) {
+        if (!slot_ok(c, d[i].kf)) return fail(SDM_ERR_ARG, "keyframe slot %d out of range", d[i].kf);
+        if ((d[i].depth && d[i].depth_step < row) || (d[i].sigma && d[i].sigma_step < row) ||
+            (d[i].checked && d[i].checked_step < row) || (d[i].points && d[i].points_step < 3 * row))
+            return fail(SDM_ERR_ARG, "row step smaller than a row");
+        const KfState& k = c->kf[d[i].kf];
+        if (!k.uploaded || !k.pass1_done) return fail(SDM_ERR_STATE, "keyframe slot %d has no results", d[i].kf);
+        if (k.rs_dense || k.split_stale)
+            return fail(SDM_ERR_STATE, "slot %d holds planes written from outside (not confined to the candidate pixels): "
+                                        "use sdm_download_keyframes", d[i].kf);
+    }
+    if (n <= 0) return SDM_OK;
+    CU(cudaSetDevice(c->cfg.device));
+    if (!c->scat) RC(scatter_init(c));
+    Scatter* S = c->scat;
+    cudaStream_t s = c->s_down;
+    for (int i = 0; i < n; ++i) {
+        const sdm_download_desc& q = d[i];
+        KfState& k = c->kf[q.kf];
+        RC(c->r_compute.host_sync(k.count_id));  // k_pack of the slot has run (it is far behind the caller's issue point)
+        const int cnt = c->h_cand[q.kf];
+        if (cnt <= 0) continue;
+        int stage;
+        {
+            std::unique_lock<std::mutex> lk(S->mu);
+            stage = S->next;
+            S->cv_free.wait(lk, [&] { return S->st[stage].free_; });
+            S->st[stage].free_ = false;
+            S->next = (stage + 1) % kScatStages;
+        }
+        ScatStage& st = S->st[stage];
+        RC(c->r_compute.wait(s, k.comp_id));
+        sdm::k_gather_sparse<<<(cnt + 255) / 256, 256, 0, s>>>(c->A, c->P, q.kf, cnt, st.dev);
+        CU(cudaGetLastError());
+        c->launches++;
+        CU(cudaMemcpyAsync(st.host, st.dev, (size_t)cnt * 28, cudaMemcpyDeviceToHost, s));
+        CU(cudaEventRecord(st.ev, s));
+        uint64_t id = 0;
+        RC(c->r_down.record(s, &id));
+        k.down_ds_id = id;
+        k.down_cp_id = id;
+        {
+            std::lock_guard<std::mutex> lk(S->mu);
+            S->jobs.push_back(ScatJob{stage, cnt, W, q});
+            ++S->pending;
+        }
+        S->cv_job.notify_one();
     }
     return SDM_OK;
 }

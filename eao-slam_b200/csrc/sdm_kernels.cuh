@@ -1544,6 +1544,42 @@ k_export_scatter(DevArena A, DevParams P, const int* __restrict__ slots, float s
 }
 
 // (rho, sigma) float2 plane -> two dense float planes (download staging), and back
+// ---------------------------------------------------------------------------------------------
+// Sparse result of a slot for sdm_scatter_keyframes: SemiDenseLoop only ever writes the candidate pixels of a
+// keyframe's four output planes non-zero (:483-484, :1290, :725-727 all sit behind the candidate test of
+// :454-456 / depth_map_ > 0), so the n candidates' values are the whole result.  SoA record block:
+// pix[n] (y << 16 | x) | rho[n] | sigma[n] | checked[n] | points[3n].
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_gather_sparse(DevArena A, DevParams P, int slot, int n, uint32_t* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t base = (size_t)slot * A.P;
+    const uint32_t p = A.cand[base + i];
+    const size_t pi = base + (size_t)(p >> 16) * P.W + (p & 0xffffu);
+    const float2 rs = A.rs[pi];
+    float* f = reinterpret_cast<float*>(out);
+    out[i] = p;
+    f[(size_t)n + i] = rs.x;
+    f[2 * (size_t)n + i] = rs.y;
+    f[3 * (size_t)n + i] = A.chk[pi];
+    f[4 * (size_t)n + 3 * (size_t)i + 0] = A.pts[3 * pi + 0];
+    f[4 * (size_t)n + 3 * (size_t)i + 1] = A.pts[3 * pi + 1];
+    f[4 * (size_t)n + 3 * (size_t)i + 2] = A.pts[3 * pi + 2];
+}
+
+// candidate counts of freshly packed slots into host-mapped pinned memory (no DMA engine involved)
+constexpr int kSlotList = 24;
+struct SlotList {
+    int s[kSlotList];
+};
+__global__ void k_publish_counts(const int* __restrict__ cand_count, SlotList slots, int m, int* host_counts)
+{
+    const int i = threadIdx.x;
+    if (i < m) host_counts[slots.s[i]] = cand_count[slots.s[i]];
+    __threadfence_system();
+}
+
 __global__ void k_split_rs(const float2* __restrict__ rs, float* __restrict__ d, float* __restrict__ s, size_t n)
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -71,7 +71,7 @@ class Stats(C.Structure):
 EXPORTS = [
     "sdm_default_config", "sdm_create", "sdm_destroy", "sdm_last_error", "sdm_version", "sdm_synchronize",
     "sdm_get_stats", "sdm_scan_generation", "sdm_host_alloc", "sdm_host_free", "sdm_upload_keyframe", "sdm_set_pose",
-    "sdm_set_intrinsics", "sdm_candidate_count", "sdm_pass1", "sdm_pass2", "sdm_update_points", "sdm_download", "sdm_download_async", "sdm_upload_keyframes", "sdm_download_keyframes", "sdm_export_points", "sdm_download_planes",
+    "sdm_set_intrinsics", "sdm_candidate_count", "sdm_pass1", "sdm_pass2", "sdm_update_points", "sdm_download", "sdm_download_async", "sdm_upload_keyframes", "sdm_download_keyframes", "sdm_scatter_keyframes", "sdm_export_points", "sdm_download_planes",
     "sdm_upload_depth", "sdm_depth_plane_ptr", "sdm_export_arena", "sdm_import_peer_arena", "sdm_pull_halo",
     "sdm_mark_pass1_done", "sdm_pair_geometry", "sdm_stereo_search_constraints", "sdm_search_range",
     "sdm_epipolar_search", "sdm_epipolar_search_plane", "sdm_fuse", "sdm_intra_check", "sdm_intra_grow",
@@ -114,6 +114,7 @@ def load() -> C.CDLL:
     lib.sdm_download_async.argtypes = [vp, C.c_int, vp, sz, vp, sz, vp, sz, vp, sz]
     lib.sdm_upload_keyframes.argtypes = [vp, C.c_int, C.POINTER(UploadDesc)]
     lib.sdm_download_keyframes.argtypes = [vp, C.c_int, C.POINTER(DownloadDesc)]
+    lib.sdm_scatter_keyframes.argtypes = [vp, C.c_int, C.POINTER(DownloadDesc)]
     lib.sdm_download_planes.argtypes = [vp, C.c_int, vp, sz, vp, sz]
     lib.sdm_export_points.argtypes = [vp, C.c_int, ip, C.c_double, vp, sz, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.sdm_upload_depth.argtypes = [vp, C.c_int, vp, sz, vp, sz]
@@ -252,6 +253,26 @@ class Context:
     def download_keyframes(self, descs):
         """enqueue only: the host arrays are valid after synchronize()"""
         self._chk(self.lib.sdm_download_keyframes(self.h, len(descs), descs))
+
+    def scatter_keyframes(self, descs):
+        """sparse form of download_keyframes for zero-initialised planes: enqueue only, valid after synchronize()"""
+        self._chk(self.lib.sdm_scatter_keyframes(self.h, len(descs), descs))
+
+    def scatter_all(self, slots, dtype_zero=True):
+        """zero-initialised planes (as KeyFrame.cc:78-81) filled through sdm_scatter_keyframes; returns dict of stacks"""
+        n = len(slots)
+        out = {k: np.zeros((n, self.H, self.W) + ((3,) if k == "points" else ()), np.float32)
+               for k in ("depth", "sigma", "checked", "points")}
+        descs = (DownloadDesc * n)()
+        for j, s in enumerate(slots):
+            descs[j].kf = int(s)
+            descs[j].depth, descs[j].depth_step = out["depth"][j].ctypes.data, 4 * self.W
+            descs[j].sigma, descs[j].sigma_step = out["sigma"][j].ctypes.data, 4 * self.W
+            descs[j].checked, descs[j].checked_step = out["checked"][j].ctypes.data, 4 * self.W
+            descs[j].points, descs[j].points_step = out["points"][j].ctypes.data, 12 * self.W
+        self.scatter_keyframes(descs)
+        self.synchronize()
+        return out
 
     def upload_scene(self, scene, indices=None, slot_of=None):
         idx = range(scene.n) if indices is None else indices

@@ -176,6 +176,15 @@ typedef struct {
     float* points;   size_t points_step;
 } sdm_download_desc;
 int sdm_download_keyframes(sdm_ctx* ctx, int n, const sdm_download_desc* desc);
+/* Sparse form of sdm_download_keyframes for planes that are ZERO-INITIALISED the way KeyFrame's constructors leave
+ * them (KeyFrame.cc:78-81): SemiDenseLoop only ever writes a non-zero value at a keyframe's candidate pixels
+ * (the stores of :483-484, :1290 and :725-727 all sit behind the candidate test of :454-456), so only those
+ * pixels' records (28 bytes each instead of 24 bytes for every pixel) cross PCIe, and worker threads of the library
+ * (env SDM_SCATTER_THREADS, default 6) write them into the caller's planes; every other element is left untouched.
+ * On zero-initialised planes the result is identical to sdm_download_keyframes.  Asynchronous: the planes are
+ * complete after sdm_synchronize.  Slots whose planes were written from outside (sdm_upload_depth) are refused
+ * (SDM_ERR_STATE).  Blocks the caller only until the slot's candidate count is known (its upload has been packed). */
+int sdm_scatter_keyframes(sdm_ctx* ctx, int n, const sdm_download_desc* desc);
 /* writes pass-1 planes of a keyframe (used to seed halo keyframes / tests); blocking */
 int sdm_upload_depth(sdm_ctx* ctx, int kf, const float* depth, size_t depth_step,
                      const float* sigma, size_t sigma_step);

@@ -128,3 +128,37 @@ def test_planes_produced_on_the_device(scene):
         ctx.upload_keyframe(0, sc2.im[0], None, None, None, sc2.K, sc2.Tcw[0])
         g, t = ctx.download_planes(0)
         assert _bits(g, sc2.grad[0]) == 0 and _bits(t, sc2.theta[0]) == 0
+
+
+def test_scatter_download_equals_dense_download(scene):
+    """sdm_scatter_keyframes (candidate records over PCIe + host-side scatter by the library's worker threads) into
+    zero-initialised planes == sdm_download_keyframes == the oracle, bit for bit; row-pitched destination planes;
+    pass-1-only call; refused for slots whose planes came from outside"""
+    sc = scene
+    osc = run_oracle(sc)
+    H, W = sc.shape
+    with api.Context(width=W, height=H, max_keyframes=sc.n) as ctx:
+        ctx.upload_scene(sc)
+        items = api.make_items(range(sc.n), sc.nbr_idx, sc.rot, sc.min_depth, sc.max_depth)
+        ctx.pass1(items)
+        # pass-1 planes only, into a pitched destination (ROI of a wider array)
+        wide = np.zeros((2, H, W + 24), np.float32)
+        d = (api.DownloadDesc * 1)()
+        d[0].kf = 3
+        d[0].depth, d[0].depth_step = wide[0, :, 8:].ctypes.data, wide.strides[1]
+        d[0].sigma, d[0].sigma_step = wide[1, :, 8:].ctypes.data, wide.strides[1]
+        ctx.scatter_keyframes(d); ctx.synchronize()
+        assert _bits(wide[0, :, 8:8 + W], osc.depth[3]) == 0 and _bits(wide[1, :, 8:8 + W], osc.sigma[3]) == 0
+        assert not wide[:, :, :8].any() and not wide[:, :, 8 + W:].any()
+        ctx.pass2(items)
+        for rep in range(2):  # twice: staging ring re-use, same planes overwritten
+            got = ctx.scatter_all(list(range(sc.n)))
+            for k, ref in (("depth", osc.depth), ("sigma", osc.sigma), ("checked", osc.checked), ("points", osc.points)):
+                assert _bits(got[k], ref) == 0, k
+        dense = ctx.download(2)
+        assert all(_bits(got[k][2], dense[k]) == 0 for k in ("depth", "sigma", "checked", "points"))
+        ctx.upload_depth(1, osc.depth[1], osc.sigma[1])
+        d[0].kf = 1
+        with pytest.raises(api.SdmError) as e:
+            ctx.scatter_keyframes(d)
+        assert e.value.code == -3  # SDM_ERR_STATE
