@@ -605,6 +605,8 @@ static int create_impl(sdm_ctx* c)
     D.var_num = 2 * cfg.sigmaI * cfg.sigmaI;
     D.chi_fusion_lt = sdm::thr_lt(cfg.chi2_fusion);
     D.chi_inter_lt = sdm::thr_lt(cfg.chi2_inter);
+    D.chi_inter_lo = D.chi_inter_lt * (1.0f - 0x1p-16f);
+    D.chi_inter_hi = D.chi_inter_lt * (1.0f + 0x1p-16f);
     D.eps_gt = sdm::thr_gt(cfg.eps);
     D.eps_lt = sdm::thr_lt(cfg.eps);
     D.slope_max = cfg.slope_max;
@@ -1353,6 +1355,29 @@ static int single_pair_item(sdm_ctx* c, int kf1, int kf2, float mind, float maxd
 static int ensure_dbg(sdm_ctx* c)
 {
     if (!c->dbg) CU(cudaMalloc(&c->dbg, c->npix * (4 * sizeof(float) + 1)));
+    return SDM_OK;
+}
+
+int sdm_inter_chi_test(sdm_ctx* c, int n, const float* diff, const float* sigma, uint8_t* accept)
+{
+    if (!c || (n > 0 && (!diff || !sigma || !accept))) return fail(SDM_ERR_ARG, "null argument");
+    if (n <= 0) return SDM_OK;
+    CU(cudaSetDevice(c->cfg.device));
+    float* d = nullptr;
+    CU(cudaMalloc(&d, (size_t)n * 9));
+    uint8_t* da = reinterpret_cast<uint8_t*>(d + 2 * (size_t)n);
+    cudaStream_t s = c->s_compute;
+    cudaError_t e = cudaMemcpyAsync(d, diff, (size_t)n * 4, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + n, sigma, (size_t)n * 4, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) {
+        sdm::k_chi_inter<<<(n + 255) / 256, 256, 0, s>>>(c->P, n, d, d + n, da);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(accept, da, (size_t)n, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(d);
+    c->launches++;
+    if (e != cudaSuccess) return fail(SDM_ERR_CUDA, "sdm_inter_chi_test: %s", cudaGetErrorString(e));
     return SDM_OK;
 }
 

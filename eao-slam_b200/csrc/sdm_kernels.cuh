@@ -38,6 +38,7 @@ struct DevParams {
     float var_num;    // (2 * sigmaI) * sigmaI
     float chi_fusion_lt;  // x < this  <=>  (double)x < 5.99
     float chi_inter_lt;   // x < this  <=>  (double)x < 3.84
+    float chi_inter_lo, chi_inter_hi;  // chi_inter_lt * (1 -+ 2^-16): the float shortcut of chi_inter_accept
     float eps_gt;         // x > this  <=>  (double)x > 0.000001
     float eps_lt;         // x < this  <=>  (double)x < 0.000001
     float slope_max;
@@ -1169,14 +1170,14 @@ __device__ __forceinline__ float2 intra_check_pixel(const DevParams& P, const fl
             if (q.x > P.eps_gt && chi_compatible(q.x, c.x, q.y, c.y, P.chi_fusion_lt)) {
                 if (n == 0) min_sigma = q.y;
                 fusion_accumulate(q.x, q.y, pjsj, rsj);
-                // pow(sigma,2) < pow(min,2) in double == |sigma| < |min|
-                if ((double)q.y * (double)q.y < (double)min_sigma * (double)min_sigma) min_sigma = q.y;
+                // pow(sigma,2) < pow(min,2) in double (squares of floats are exact there)  <=>  |sigma| < |min|
+                if (fabsf(q.y) < fabsf(min_sigma)) min_sigma = q.y;
                 ++n;
             }
         }
     if (n == 0) min_sigma = c.y;
     fusion_accumulate(c.x, c.y, pjsj, rsj);  // "dont forget itself" :902 (pushed last)
-    if ((double)c.y * (double)c.y < (double)min_sigma * (double)min_sigma) min_sigma = c.y;
+    if (fabsf(c.y) < fabsf(min_sigma)) min_sigma = c.y;
     ++n;
     return (n >= 3) ? make_float2(pjsj / rsj, min_sigma) : make_float2(0.f, 0.f);
 }
@@ -1276,6 +1277,31 @@ k_intra_cand(DevArena A, DevParams P, const DevItem* __restrict__ items, DevPlan
 // ---------------------------------------------------------------------------------------------
 // K6: InterKeyFrameDepthChecking (:1121-1296) fused with UpdateSemiDensePointSet (:700-731).
 // ---------------------------------------------------------------------------------------------
+// The chi-square gate of InterKeyFrameDepthChecking (:1204-1211 and its three copies):
+//     test = (float)(dd*dd / (sigma*sigma))  evaluated in double with dd = (double)(float)(depthj - d);  accept iff test < 3.84.
+// Decided in float whenever the float evaluation is at least 2^-16 (relative) away from the threshold: with a2 = a*a and
+// s2 = sigma*sigma both normal (in [2^-100, 2^100]) the float products are within 3 * 2^-24 of the exact quotient test
+// and the reference's own value is within 2^-24 + 2^-53 of it, so `a2 < T(1 - 2^-16) * s2` implies acceptance and
+// `a2 > T(1 + 2^-16) * s2` implies rejection.  Anything closer, out of range or NaN takes the reference's double form.
+__device__ __forceinline__ bool chi_inter_accept(float a, float sg, const DevParams& P)
+{
+    const float a2 = a * a, s2 = sg * sg;
+    if (fminf(a2, s2) >= 0x1p-100f && fmaxf(a2, s2) <= 0x1p100f) {
+        if (a2 < P.chi_inter_lo * s2) return true;
+        if (a2 > P.chi_inter_hi * s2) return false;
+    }
+    const double dd = (double)a;
+    const float test = (float)((dd * dd) / ((double)sg * (double)sg));
+    return test < P.chi_inter_lt;
+}
+
+__global__ void k_chi_inter(DevParams P, int n, const float* __restrict__ diff, const float* __restrict__ sigma,
+                            uint8_t* __restrict__ accept)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) accept[i] = chi_inter_accept(diff[i], sigma[i], P) ? 1 : 0;
+}
+
 __device__ __forceinline__ void write_point(const DevItem& it, const DevParams& P, float* __restrict__ pts, size_t pi,
                                             int x, int y, float checked)
 {
@@ -1302,7 +1328,7 @@ __device__ __forceinline__ float inter_check_pixel(const DevArena& A, const DevP
     const float fx = it.K[0], fy = it.K[1], cx = it.K[2], cy = it.K[3];
     const float xn = (px - cx) / fx, yn = (py - cy) / fy;
     const float dp = 1.0f / depthp;
-    const double alpha = (double)(float)(1.0 / (double)depthp);  // gemm alpha is cast to float
+    const double alpha = (double)dp;  // gemm alpha = (float)(1.0 / (double)depthp) == 1.0f / depthp (same argument as iz below)
     int support = 0;
     double JtR = 0.0, JtJ = 0.0;
     const int N = it.n_nbr;
@@ -1318,7 +1344,9 @@ __device__ __forceinline__ float inter_check_pixel(const DevArena& A, const DevP
         const float U = fx * X0 + 0.f * X1 + cx * X2;
         const float V = 0.f * X0 + fy * X1 + cy * X2;
         const float Wz = 0.f * X0 + 0.f * X1 + 1.0f * X2;
-        const float iz = (float)(1.0 / (double)Wz);
+        // (float)(1.0 / (double)Wz) == 1.0f / Wz: rounding a double quotient of two floats to float cannot differ
+        // from the float quotient (53 >= 2*24 + 2: double rounding is innocuous for division, Figueroa 1995)
+        const float iz = 1.0f / Wz;
         const float xj = U * iz, yj = V * iz;
         // Eq (12)
         const float rz = (float)((double)g.R[6] * (double)xn + (double)g.R[7] * (double)yn + (double)g.R[8] * 1.0);
@@ -1336,9 +1364,7 @@ __device__ __forceinline__ float inter_check_pixel(const DevArena& A, const DevP
         for (int k = 0; k < 4; ++k) {
             const float d = q[k].x, sg = q[k].y;
             if (d > P.eps_gt) {
-                const double dd = (double)(depthj - d);
-                const float test = (float)((dd * dd) / ((double)sg * (double)sg));
-                if (test < P.chi_inter_lt) {
+                if (chi_inter_accept(depthj - d, sg, P)) {
                     ++nj;
                     // Gauss-Newton terms (:1274-1280), accumulated in the reference's order
                     const float djn = 1.0f / d;

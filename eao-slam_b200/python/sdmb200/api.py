@@ -73,7 +73,7 @@ EXPORTS = [
     "sdm_get_stats", "sdm_scan_generation", "sdm_host_alloc", "sdm_host_free", "sdm_upload_keyframe", "sdm_set_pose",
     "sdm_set_intrinsics", "sdm_candidate_count", "sdm_pass1", "sdm_pass2", "sdm_update_points", "sdm_download", "sdm_download_async", "sdm_upload_keyframes", "sdm_download_keyframes", "sdm_scatter_keyframes", "sdm_export_points", "sdm_download_planes",
     "sdm_upload_depth", "sdm_depth_plane_ptr", "sdm_export_arena", "sdm_import_peer_arena", "sdm_pull_halo",
-    "sdm_mark_pass1_done", "sdm_pair_geometry", "sdm_stereo_search_constraints", "sdm_search_range",
+    "sdm_mark_pass1_done", "sdm_pair_geometry", "sdm_stereo_search_constraints", "sdm_search_range", "sdm_inter_chi_test",
     "sdm_epipolar_search", "sdm_epipolar_search_plane", "sdm_fuse", "sdm_intra_check", "sdm_intra_grow",
     "sdm_inter_check", "sdm_last_pass_ms", "sdm_launch_count", "sdm_last_timing", "sdm_mark", "sdm_elapsed_ms",
 ]
@@ -115,6 +115,7 @@ def load() -> C.CDLL:
     lib.sdm_upload_keyframes.argtypes = [vp, C.c_int, C.POINTER(UploadDesc)]
     lib.sdm_download_keyframes.argtypes = [vp, C.c_int, C.POINTER(DownloadDesc)]
     lib.sdm_scatter_keyframes.argtypes = [vp, C.c_int, C.POINTER(DownloadDesc)]
+    lib.sdm_inter_chi_test.argtypes = [vp, C.c_int, vp, vp, vp]
     lib.sdm_download_planes.argtypes = [vp, C.c_int, vp, sz, vp, sz]
     lib.sdm_export_points.argtypes = [vp, C.c_int, ip, C.c_double, vp, sz, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.sdm_upload_depth.argtypes = [vp, C.c_int, vp, sz, vp, sz]
@@ -351,6 +352,12 @@ class Context:
     def upload_depth(self, slot, depth, sigma):
         d, s = _f32(depth), _f32(sigma)
         self._chk(self.lib.sdm_upload_depth(self.h, slot, d.ctypes.data, d.strides[0], s.ctypes.data, s.strides[0]))
+
+    def inter_chi_test(self, diff, sigma):
+        d, s = _f32(np.ravel(diff)), _f32(np.ravel(sigma))
+        out = np.empty(d.size, np.uint8)
+        self._chk(self.lib.sdm_inter_chi_test(self.h, d.size, d.ctypes.data, s.ctypes.data, out.ctypes.data))
+        return out.astype(bool)
 
     def scan_generation(self) -> int:
         return int(self.lib.sdm_scan_generation(self.h))

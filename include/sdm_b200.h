@@ -223,6 +223,9 @@ int sdm_pair_geometry(const float K1[4], const float Tcw1[12], const float K2[4]
                       sdm_pair_geometry_t* out);
 /* replaces: StereoSearchConstraints (:734-747); inv_depths = KeyFrame::GetAllPointDepths */
 int sdm_stereo_search_constraints(const float* inv_depths, int n, float* min_depth, float* max_depth);
+/* the chi-square gate of InterKeyFrameDepthChecking alone (:1204-1211 and its three copies): accept[i] = 1 iff
+ * (float)(dd*dd / (sigma*sigma)) < 3.84 with dd = (double)diff[i], diff = depthj - depth_map_(neighbour) as a float */
+int sdm_inter_chi_test(sdm_ctx* ctx, int n, const float* diff, const float* sigma, uint8_t* accept);
 /* replaces: GetSearchRange (:1598-1631) */
 int sdm_search_range(sdm_ctx* ctx, int kf1, int kf2, int px, int py, float mind, float maxd,
                      float* umin, float* umax);

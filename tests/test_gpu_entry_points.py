@@ -162,3 +162,29 @@ def test_scatter_download_equals_dense_download(scene):
         with pytest.raises(api.SdmError) as e:
             ctx.scatter_keyframes(d)
         assert e.value.code == -3  # SDM_ERR_STATE
+
+
+def test_inter_chi_gate_float_shortcut_is_exact():
+    """chi_inter_accept decides in float unless the value is within 2^-16 of 3.84; the decision must equal the
+    reference's double evaluation `(float)(dd*dd / (sigma*sigma)) < 3.84` everywhere: random inputs, inputs placed
+    within a few ulp of the threshold, zeros, subnormal / huge squares, infinities and NaN."""
+    rng = np.random.default_rng(7)
+    n = 400000
+    sg = np.exp(rng.uniform(np.log(1e-4), np.log(0.5), n)).astype(np.float32)
+    chi = np.empty(n)
+    chi[:n // 2] = np.exp(rng.uniform(np.log(1e-3), np.log(1e3), n // 2))
+    # the other half hugs the threshold: 3.84 * (1 + eps), |eps| from 1e-9 to 1e-3, both signs
+    eps = np.exp(rng.uniform(np.log(1e-9), np.log(1e-3), n - n // 2)) * rng.choice([-1.0, 1.0], n - n // 2)
+    chi[n // 2:] = 3.84 * (1.0 + eps)
+    diff = (np.sqrt(chi) * sg.astype(np.float64) * rng.choice([-1.0, 1.0], n)).astype(np.float32)
+    extra_d = np.array([0, 0, 1e-30, 1e-30, 1e25, 1e25, np.inf, 1.0, np.nan, 1.0, 1e-20, 3e19, -0.0, 1e-44], np.float32)
+    extra_s = np.array([0, 1, 1e-30, 1e-25, 1e25, 1e20, 1.0, np.inf, 1.0, np.nan, 1e-20, 3e19, 1e-44, 1e-44], np.float32)
+    diff, sg = np.concatenate([diff, extra_d]), np.concatenate([sg, extra_s])
+    with np.errstate(all="ignore"):
+        dd = diff.astype(np.float64)
+        ref = ((dd * dd) / (sg.astype(np.float64) * sg.astype(np.float64))).astype(np.float32) < np.float64(3.84)
+    with api.Context(width=64, height=48, max_keyframes=1) as ctx:
+        got = ctx.inter_chi_test(diff, sg)
+    assert np.array_equal(got, ref), np.flatnonzero(got != ref)[:10]
+    near = np.abs(chi[n // 2:] / 3.84 - 1.0) < 2.0 ** -16
+    assert near.sum() > 1000 and (~near).sum() > 1000   # both the double fallback and the float shortcut were exercised
