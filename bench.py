@@ -300,12 +300,9 @@ def main_ours(a, rank, world, local_rank):
         if world > 1:
             dist.barrier()
 
-    def upload_one(s):
-        ctx.upload_keyframe(s, sc.im[s], sc.grad[s], sc.theta[s], None, sc.K, sc.Tcw[s])
-
     def upload():
-        for s in range(n_loc):
-            upload_one(s)
+        descs = ctx.upload_descs(sc, range(n_loc))
+        ctx.upload_keyframes(descs)
 
     def exchange():
         if world > 1:
@@ -462,51 +459,52 @@ def main_ours(a, rank, world, local_rank):
         e2e["sparse_d2h"] = int(28 * cands)
         # the same loop for consumers that only need the surviving points (SaveSemiDensePoints / DrawSemiDense / CARV:
         # sigma <= 0.02 and checked > 1e-6): upload + both passes + sdm_export_points instead of the dense downloads
-        if world == 1:
-            owned_arr = np.ascontiguousarray(owned, np.int32)
-            pts_buf = pinned(lib, (len(owned) * 40000,), np.dtype([("x", "f4"), ("y", "f4"), ("z", "f4"), ("pixel", "u4")]), keep)
-            tot = C.c_uint64()
+        owned_arr = np.ascontiguousarray(owned, np.int32)
+        pts_buf = pinned(lib, (len(owned) * 40000,), np.dtype([("x", "f4"), ("y", "f4"), ("z", "f4"), ("pixel", "u4")]), keep)
+        tot = C.c_uint64()
 
-            t_x = [0.0]
-            # larger chunks than the dense-download loop: nothing slow hides the ramp-up / tail of small launches here
-            XCH = int(os.environ.get("SDM_BENCH_XCHUNK", "50"))
-            xchunks = [owned[i:i + XCH] for i in range(0, len(owned), XCH)]
-            xitems = [api.make_items(ch, sc.nbr_idx, sc.rot, sc.min_depth, sc.max_depth) for ch in xchunks]
-            xneed = [max(ch[-1], max(int(v) for s in ch for v in sc.nbr_idx[s])) for ch in xchunks]
+        t_x = [0.0]
+        # larger chunks than the dense-download loop: nothing slow hides the ramp-up / tail of small launches here
+        XCH = int(os.environ.get("SDM_BENCH_XCHUNK", "50"))
+        xchunks = [owned[i:i + XCH] for i in range(0, len(owned), XCH)]
+        xitems = [api.make_items(ch, sc.nbr_idx, sc.rot, sc.min_depth, sc.max_depth) for ch in xchunks]
+        xneed = [max(ch[-1], max(int(v) for s in ch for v in sc.nbr_idx[s])) for ch in xchunks]
 
-            up_img = ctx.upload_descs(sc, range(n_loc), images_only=True)  # grad = theta = NULL: planes made on the device
-            img_ptr = lambda i: C.cast(C.byref(up_img, i * up_sz), C.POINTER(api.UploadDesc))
+        up_img = ctx.upload_descs(sc, range(n_loc), images_only=True)  # grad = theta = NULL: planes made on the device
+        img_ptr = lambda i: C.cast(C.byref(up_img, i * up_sz), C.POINTER(api.UploadDesc))
 
-            def export_step(up_ptr=up_ptr):
-                t_x[0] = time.perf_counter()
-                nxt = 0
-                for k in range(len(xchunks)):  # uploads run ahead of pass 1, chunk by chunk
-                    if nxt <= xneed[k]:
-                        chk(lib.sdm_upload_keyframes(ctx.h, xneed[k] + 1 - nxt, up_ptr(nxt))); nxt = xneed[k] + 1
-                    chk(lib.sdm_pass1(ctx.h, len(xitems[k]), xitems[k]))
-                if nxt < n_loc:
-                    chk(lib.sdm_upload_keyframes(ctx.h, n_loc - nxt, up_ptr(nxt)))
-                chk(lib.sdm_pass2(ctx.h, len(items), items))
-                if dbg:
-                    t_a = time.perf_counter(); ctx.synchronize(); t_b = time.perf_counter()
-                    print(f"export_step: issue {1e3 * (t_a - t_x[0]):.2f} ms, passes done {1e3 * (t_b - t_x[0]):.2f} ms", file=sys.stderr)
-                chk(lib.sdm_export_points(ctx.h, owned_arr.size, owned_arr.ctypes.data_as(C.POINTER(C.c_int32)), 0.02,
-                                          pts_buf.ctypes.data, pts_buf.size, None, C.byref(tot)))
+        def export_step(up_ptr=up_ptr):
+            t_x[0] = time.perf_counter()
+            nxt = 0
+            for k in range(len(xchunks)):  # uploads run ahead of pass 1, chunk by chunk
+                if nxt <= xneed[k]:
+                    chk(lib.sdm_upload_keyframes(ctx.h, xneed[k] + 1 - nxt, up_ptr(nxt))); nxt = xneed[k] + 1
+                chk(lib.sdm_pass1(ctx.h, len(xitems[k]), xitems[k]))
+            if nxt < n_loc:
+                chk(lib.sdm_upload_keyframes(ctx.h, n_loc - nxt, up_ptr(nxt)))
+            exchange()
+            chk(lib.sdm_pass2(ctx.h, len(items), items))
+            if dbg:
+                t_a = time.perf_counter(); ctx.synchronize(); t_b = time.perf_counter()
+                print(f"export_step: issue {1e3 * (t_a - t_x[0]):.2f} ms, passes done {1e3 * (t_b - t_x[0]):.2f} ms", file=sys.stderr)
+            chk(lib.sdm_export_points(ctx.h, owned_arr.size, owned_arr.ctypes.data_as(C.POINTER(C.c_int32)), 0.02,
+                                      pts_buf.ctypes.data, pts_buf.size, None, C.byref(tot)))
+            barrier()
+        export_step()
+        barrier(); tt = time.perf_counter()
+        for _ in range(a.steps):
             export_step()
-            tt = time.perf_counter()
-            for _ in range(a.steps):
-                export_step()
-            e2e["export_sec"] = (time.perf_counter() - tt) / a.steps
-            e2e["export_points"] = int(tot.value)
-            # ... and with only im_ uploaded (1 B/px instead of 9): GradImg / GradTheta produced on the device
+        e2e["export_sec"] = (time.perf_counter() - tt) / a.steps
+        e2e["export_points"] = int(tot.value)
+        # ... and with only im_ uploaded (1 B/px instead of 9): GradImg / GradTheta produced on the device
+        export_step(img_ptr)
+        barrier(); tt = time.perf_counter()
+        for _ in range(a.steps):
             export_step(img_ptr)
-            tt = time.perf_counter()
-            for _ in range(a.steps):
-                export_step(img_ptr)
-            e2e["image_sec"] = (time.perf_counter() - tt) / a.steps
-            e2e["image_points"] = int(tot.value)
-            if e2e["image_points"] != e2e["export_points"]:
-                print(f"WARNING: device-produced planes gave {e2e['image_points']} points, uploaded planes {e2e['export_points']}", file=sys.stderr)
+        e2e["image_sec"] = (time.perf_counter() - tt) / a.steps
+        e2e["image_points"] = int(tot.value)
+        if e2e["image_points"] != e2e["export_points"]:
+            print(f"WARNING: device-produced planes gave {e2e['image_points']} points, uploaded planes {e2e['export_points']}", file=sys.stderr)
     if rank == 0:
         clocks.stop()
 
@@ -515,9 +513,15 @@ def main_ours(a, rank, world, local_rank):
     if world > 1:
         v = torch.tensor([float(cands)], device="cuda", dtype=torch.float64)
         dist.all_reduce(v); tot_cands = int(v.item())
-        m = torch.tensor([ms, e2e_max, sparse_max, -sparse_same], device="cuda", dtype=torch.float64)
-        dist.all_reduce(m, op=dist.ReduceOp.MAX); ms_max, e2e_max, sparse_max, sparse_same = m.tolist()
+        xs = [e2e.get("export_sec", 0.0), e2e.get("image_sec", 0.0)] if e2e else [0.0, 0.0]
+        m = torch.tensor([ms, e2e_max, sparse_max, -sparse_same] + xs, device="cuda", dtype=torch.float64)
+        dist.all_reduce(m, op=dist.ReduceOp.MAX); ms_max, e2e_max, sparse_max, sparse_same, x_sec, i_sec = m.tolist()
         sparse_same = -sparse_same
+        if e2e and "export_sec" in e2e:
+            pv = torch.tensor([float(e2e["export_points"]), float(e2e["image_points"])], device="cuda", dtype=torch.float64)
+            dist.all_reduce(pv)
+            e2e["export_sec"], e2e["image_sec"] = x_sec, i_sec
+            e2e["export_points"], e2e["image_points"] = int(pv[0].item()), int(pv[1].item())
     if rank != 0:
         ctx.close()
         if world > 1:
@@ -571,7 +575,7 @@ def main_ours(a, rank, world, local_rank):
         if "image_sec" in e2e:
             line["e2e_image_in_points_out"] = {
                 "value": tot_cands / e2e["image_sec"], "unit": UNIT, "ms_per_step": 1e3 * e2e["image_sec"],
-                "points_per_step": e2e["image_points"], "h2d_bytes_per_step": int(n_loc * W * H),
+                "points_per_step": e2e["image_points"], "h2d_bytes_per_step_per_rank": int(n_loc * W * H),
                 "d2h_bytes_per_step": 16 * e2e["image_points"],
                 "note": "as e2e_point_export, but only im_ is uploaded: GradImg / GradTheta (KeyFrame.cc:69-74) are "
                         "produced on the device by k_pack_image"}
