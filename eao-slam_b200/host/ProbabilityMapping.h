@@ -90,7 +90,7 @@ public:
     };
 
     explicit ProbabilityMapping(Map* pMap)
-        : mMutexSemiDense(), mpMap(pMap), mCtx(NULL), mN(covisN), mW(0), mH(0), mCapacity(0), mbFinishRequested(false),
+        : mMutexSemiDense(), mpMap(pMap), mCtx(NULL), mN(covisN), mW(0), mH(0), mCapacity(0), mDevicePlanes(false), mOnline(false), mbFinishRequested(false),
           mbFinished(false), mbResetRequested(false)
     {
         sdm_default_config(&mCfg);
@@ -100,12 +100,23 @@ public:
     // run-time versions of the #defines of ProbabilityMapping.h:45-56; call before the first loop
     sdm_config& Config() { return mCfg; }
     void SetCovisN(int n) { mN = n; }
+    // upload im_ only and let the device produce GradImg / GradTheta (KeyFrame.cc:69-74: scalar-form magnitude / phase,
+    // <= 1 ulp / 3e-5 deg from OpenCV's SIMD kernels) instead of uploading the keyframe's own planes; 1 B/px instead of 9
+    void SetProducePlanesOnDevice(bool on) { mDevicePlanes = on; }
 
-    // ProbabilityMapping.cc:204-300 (offline mode: idle until finish is requested, then one loop)
+    // ProbabilityMapping.cc:204-300.  Offline mode (the reference's build, `#define OnlineLoop` commented out at
+    // ProbabilityMapping.h:42): idle until finish is requested, then one loop.  Online mode (:223-234): every 5 ms the
+    // keyframes that became eligible are processed (the gating of SemiDenseLoop skips finished ones, their planes stay
+    // resident on the device) and the point sets of keyframes whose pose changed are refreshed.
+    void SetOnline(bool on) { mOnline = on; }
     void Run()
     {
         while (true) {
             if (CheckFinish()) break;
+            if (mOnline) {
+                SemiDenseLoop();
+                UpdateAllSemiDensePointSet();  // make point position dependent to kf position (:226)
+            }
             ResetIfRequested();
             std::this_thread::sleep_for(std::chrono::milliseconds(5));
         }
@@ -432,8 +443,10 @@ private:
         std::memset(&u, 0, sizeof(u));
         u.kf = (int32_t)mSlot.size();
         u.im = kf->im_.ptr<uint8_t>(0);        u.im_step = (size_t)kf->im_.step;
-        u.grad = kf->GradImg.ptr<float>(0);    u.grad_step = (size_t)kf->GradImg.step;
-        u.theta = kf->GradTheta.ptr<float>(0); u.theta_step = (size_t)kf->GradTheta.step;
+        if (!mDevicePlanes) {
+            u.grad = kf->GradImg.ptr<float>(0);    u.grad_step = (size_t)kf->GradImg.step;
+            u.theta = kf->GradTheta.ptr<float>(0); u.theta_step = (size_t)kf->GradTheta.step;
+        }
         if (!kf->mEdgeIndex.empty()) { u.edge = kf->mEdgeIndex.ptr<int32_t>(0); u.edge_step = (size_t)kf->mEdgeIndex.step; }
         u.K[0] = kf->fx; u.K[1] = kf->fy; u.K[2] = kf->cx; u.K[3] = kf->cy;
         PoseOf(kf, u.Tcw);
@@ -546,6 +559,7 @@ private:
     sdm_ctx* mCtx;
     sdm_config mCfg;
     int mN, mW, mH, mCapacity;
+    bool mDevicePlanes, mOnline;
     std::unordered_map<KeyFrame*, int> mSlot;
     std::vector<sdm_upload_desc> mPending;   // queued uploads (EnsureUploaded / Flush)
     std::vector<KeyFrame*> mPendingKFs;

@@ -73,6 +73,7 @@ int main(int argc, char** argv)
 
     ProbabilityMapping pm(&map);
     pm.SetCovisN(N);
+    if (const char* e = getenv("SDM_SHIM_DEVICE_PLANES")) pm.SetProducePlanesOnDevice(e[0] == '1');
     pm.RequestFinish();
     pm.Run();  // = SemiDenseLoop() once, as in the reference's offline mode
     if (!pm.isFinished()) return 3;

@@ -108,6 +108,13 @@ def test_shim_semidense_loop_matches_oracle(shim_binary, tmp_path):
         dev["checked"][i] = p[2 * W * H:3 * W * H].reshape(H, W); dev["points"][i] = p[3 * W * H:].reshape(H, W, 3)
     rep = compare_planes(dev, osc)
     print(rep)
+    # SetProducePlanesOnDevice(true): im_ only goes up, the device makes GradImg / GradTheta -> the same planes
+    out2 = str(tmp_path / "out2.bin")
+    r2 = subprocess.run([shim_binary, scene_path, out2], capture_output=True, text=True,
+                        env=dict(os.environ, SDM_SHIM_DEVICE_PLANES="1"))
+    assert r2.returncode == 0, r2.stdout + r2.stderr
+    raw2 = np.fromfile(out2, np.float32)
+    assert np.array_equal(raw2[:n * per].view(np.uint32), raw[:n * per].view(np.uint32))
     tail = raw[n * per:]
     rec = tail[:8 * len(probes)].reshape(-1, 8)
     for (k1, k2, x, y), got in zip(probes, rec):
