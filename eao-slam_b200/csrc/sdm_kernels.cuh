@@ -788,6 +788,22 @@ __global__ void k_verify_div(unsigned long long* mismatches)
     if (bad) atomicAdd(mismatches, bad);
 }
 
+#ifndef SDM_SCAN2_PACKED
+#define SDM_SCAN2_PACKED 1
+#endif
+// yangle_interp with the two products of each branch as one packed multiply
+__device__ __forceinline__ float yangle_interp2(float a0, float a1, float2 w01)
+{
+    if (__builtin_expect(fabsf(a0 - a1) < 180.f, 1)) {
+        const float2 p = __fmul2_rn(make_float2(a0, a1), w01);
+        return p.x + p.y;
+    }
+    if (a0 < a1) a0 += 360.f; else a1 += 360.f;
+    float inter = a0 * w01.x + a1 * w01.y;
+    if (inter >= 360.f) inter -= 360.f;
+    return inter;
+}
+
 #ifndef SDM_SCAN2_UNROLL
 #define SDM_SCAN2_UNROLL 2
 #endif
@@ -821,18 +837,39 @@ __device__ __forceinline__ void scan_columns2(const float4* __restrict__ tex2, c
         w1n = vn - (r - kMagic);
         idxn = __float_as_uint(r) * Wm + ubias;
         tn = __ldg(reinterpret_cast<const float4*>(tb + (size_t)idxn * 16));
+#if SDM_SCAN2_PACKED
+        // Blackwell packed fp32x2 multiplies (FMUL2: two independent RN products per issue slot)
+        const float2 w01 = make_float2(w0, w1);
+        const float2 gp = __fmul2_rn(make_float2(t.x, t.y), w01);
+        const float g2 = gp.x + gp.y;
+        if (g2 <= kLambdaG2) continue;  // condition 1
+        const float gth = yangle_interp2(t.z, t.w, w01);
+#else
         const float g2 = t.x * w0 + t.y * w1;
         if (g2 <= kLambdaG2) continue;  // condition 1
         const float gth = yangle_interp(t.z, t.w, w0, w1);
-        const float d2 = gth - th_line;  // condition 2
-        const float ang = d2 < 0.f ? d2 + 360.f : d2;
+#endif
+#if SDM_SCAN2_PACKED
+        const float2 dd = __fadd2_rn(make_float2(gth, gth), make_float2(-th_line, -ang_pi_rot));
+        const float d2 = dd.x, d3 = dd.y;
+#else
+        const float d2 = gth - th_line, d3 = gth - ang_pi_rot;
+#endif
+        const float ang = d2 < 0.f ? d2 + 360.f : d2;  // condition 2
         if (fabsf(fabsf(ang - 180.f) - 90.f) <= 10.f) continue;
-        const float d3 = gth - ang_pi_rot;  // condition 3
-        if ((d3 >= 45.f || d3 <= kT2) && fabsf(d3) <= 315.f) continue;
+        if ((d3 >= 45.f || d3 <= kT2) && fabsf(d3) <= 315.f) continue;  // condition 3
         const uchar2 i2 = __ldg(reinterpret_cast<const uchar2*>(ib + (size_t)idx * 2));
+#if SDM_SCAN2_PACKED
+        const float2 ip = __fmul2_rn(make_float2((float)i2.x, (float)i2.y), w01);
+        // {pe, ge} = {pixel, gradc} - {I2, G2} and their squares as packed operations
+        const float2 res = __fadd2_rn(make_float2(pixel, gradc), make_float2(-(ip.x + ip.y), -g2));
+        const float2 sq = __fmul2_rn(res, res);
+        const float err = sq.x + div_by_theta2(sq.y);
+#else
         const float pe = pixel - ((float)i2.x * w0 + (float)i2.y * w1);
         const float ge = gradc - g2;
         const float err = pe * pe + div_by_theta2(ge * ge);
+#endif
         if (err < best_err) { best_err = err; best_n = n; }
     }
 }
