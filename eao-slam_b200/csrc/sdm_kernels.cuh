@@ -1278,7 +1278,10 @@ k_intra_grow(DevParams P, const float2* __restrict__ tmp, float2* __restrict__ a
 }
 
 // candidate-list stages; stage = 0: check (rs -> rs2), stage = 1: grow (rs2 -> rs, dpl, spl)
-__global__ void __launch_bounds__(kChunk)
+#ifndef SDM_INTRA_MINB
+#define SDM_INTRA_MINB 16  // 32 registers, full occupancy: the stencil gathers are latency-bound (1.22 -> 0.94 ms per 200 keyframes)
+#endif
+__global__ void __launch_bounds__(kChunk, SDM_INTRA_MINB)
 k_intra_cand(DevArena A, DevParams P, const DevItem* __restrict__ items, DevPlan plan, int stage, int copy_only)
 {
     __shared__ DevItem s_item;
@@ -1458,7 +1461,7 @@ k_pass2(DevArena A, DevParams P, const DevItem* __restrict__ items, const int* _
 // chk / pts of the whole plane, so pass 2 only has to visit the compacted candidates: one thread per
 // candidate, kLaneBlock candidates of one keyframe per block (same block -> item map as pass 1).
 #ifndef SDM_P2_MINB
-#define SDM_P2_MINB 10  // 48 registers: -8 % vs 72 registers (occupancy-bound gathers)
+#define SDM_P2_MINB 16  // 32 registers, full occupancy (occupancy-bound gathers; 72 / 48 / 40 / 32 registers: 1.49 / 1.37 / 1.33 / 1.33 ms)
 #endif
 __global__ void __launch_bounds__(kLaneBlock, SDM_P2_MINB)
 k_pass2_cand(DevArena A, DevParams P, const DevItem* __restrict__ items, DevPlan plan, DevStats* stats)
