@@ -1200,10 +1200,22 @@ __device__ __forceinline__ float2 intra_check_pixel(const DevParams& P, const fl
 {
     float pjsj = 0.f, rsj = 0.f, min_sigma = 0.f;
     int n = 0;
+    float2 nb[8];  // the eight neighbours requested up front: the stencil is latency-bound
+    {
+        int k = 0;
+#pragma unroll
+        for (int y = py - 1; y <= py + 1; ++y)
+#pragma unroll
+            for (int x = px - 1; x <= px + 1; ++x)
+                if (!(x == px && y == py)) nb[k++] = src[(size_t)y * P.W + x];
+    }
+    int k = 0;
+#pragma unroll
     for (int y = py - 1; y <= py + 1; ++y)
+#pragma unroll
         for (int x = px - 1; x <= px + 1; ++x) {
             if (x == px && y == py) continue;
-            const float2 q = src[(size_t)y * P.W + x];
+            const float2 q = nb[k++];
             if (q.x > P.eps_gt && chi_compatible(q.x, c.x, q.y, c.y, P.chi_fusion_lt)) {
                 if (n == 0) min_sigma = q.y;
                 fusion_accumulate(q.x, q.y, pjsj, rsj);
@@ -1223,10 +1235,22 @@ __device__ __forceinline__ float2 intra_grow_pixel(const DevParams& P, const flo
 {
     float pjsj = 0.f, rsj = 0.f, min_sigma = 0.f;
     int n = 0;
+    float2 nb[8];
+    {
+        int k = 0;
+#pragma unroll
+        for (int y = py - 1; y <= py + 1; ++y)
+#pragma unroll
+            for (int x = px - 1; x <= px + 1; ++x)
+                if (!(x == px && y == py)) nb[k++] = src[(size_t)y * P.W + x];
+    }
+    int k = 0;
+#pragma unroll
     for (int y = py - 1; y <= py + 1; ++y)
+#pragma unroll
         for (int x = px - 1; x <= px + 1; ++x) {
             if (x == px && y == py) continue;
-            const float2 q = src[(size_t)y * P.W + x];
+            const float2 q = nb[k++];
             if (chi_compatible(q.x, c.x, q.y, c.y, P.chi_fusion_lt)) {
                 if (n == 0) min_sigma = q.y;
                 fusion_accumulate(q.x, q.y, pjsj, rsj);
