@@ -667,8 +667,6 @@ __device__ __forceinline__ bool scan_pixel_warp(const DevArena& A, const DevPara
     if (lane == 0) {
         const size_t own = (size_t)kf * A.P + (size_t)y * P.W + x;
         A.rs[own] = make_float2(out_d, out_s);
-    A.dpl[own] = out_d;
-    A.spl[own] = out_s;
         A.dpl[own] = out_d;
         A.spl[own] = out_s;
     }
