@@ -537,7 +537,7 @@ void sdm_destroy(sdm_ctx* c)
     cudaDeviceSynchronize();
     for (int i = 0; i < kMaxPeers; ++i)
         if (c->peer_rs[i]) cudaIpcCloseMemHandle(c->peer_rs[i]);
-    cudaFree(c->A.tex); cudaFree(c->A.ipair); cudaFree(c->A.cand); cudaFree(c->A.cand_count);
+    cudaFree(c->A.tex); cudaFree(c->A.ipair); cudaFree(c->A.texw); cudaFree(c->A.cand); cudaFree(c->A.cand_count);
     cudaFree(c->A.plane_irregular);
     cudaFree(c->A.rs); cudaFree(c->A.chk); cudaFree(c->A.pts); cudaFree(c->A.dpl); cudaFree(c->A.spl); cudaFree(c->A.rs2);
     for (auto& s : c->up) { cudaFree(s.im); cudaFree(s.grad); cudaFree(s.theta); cudaFree(s.edge); }
@@ -628,6 +628,7 @@ static int create_impl(sdm_ctx* c)
     A.P = P;
     CU(cudaMalloc(&A.tex, n * P * sizeof(float4)));
     CU(cudaMalloc(&A.ipair, n * P * sizeof(uchar2)));
+    CU(cudaMalloc(&A.texw, n * P * sizeof(float4)));
     CU(cudaMalloc(&A.cand, n * P * sizeof(uint32_t)));
     CU(cudaMalloc(&A.cand_count, n * sizeof(int)));
     CU(cudaMalloc(&A.plane_irregular, n * sizeof(int)));

@@ -139,3 +139,38 @@ def test_gate_boundaries_and_irregular_rot():
     sc.rot[5][:] = 725.0                   # irregular: first-generation loop for keyframe 5
     osc, dev = run_oracle(sc), run_device(sc)
     assert _bit_equal(dev, osc) == zero
+
+
+def test_wrap_encoded_orientation_pairs():
+    """scan_columns2 reads texels whose orientation pair is pre-processed for yangle (:83-111): pairs more than 180
+    degrees apart carry the `+ 360` of the smaller angle and a sign flag (encode_theta_pair).  Planes built to stress
+    exactly that: most vertical pairs straddle the 0/360 seam, with exact 0, -0, 360, the floats next to 360 and to
+    180 apart, and pairs exactly 180 apart (the reference's `< 180` test is strict).  Own-pixel orientations (th_pi of
+    gate 3) come from the same planes, so candidates whose own texel is wrapped are covered too."""
+    sc = synth.make_scene(8, 200, 150, 6, seed=23, contrast=0.9)
+    rng = np.random.default_rng(5)
+    H, W = sc.shape
+    near0 = np.float32([0.0, -0.0, 1e-30, 3e-5, 0.5, 7.25, 44.99999, 90.0, 179.99998, 180.0])
+    near360 = np.float32([360.0, 359.99997, 359.5, 352.75, 315.00003, 270.0, 180.00002, 180.0])
+    for i in range(sc.n):
+        seam = rng.random((H, W)) < 0.6                      # pixels moved next to the seam
+        hi_row = (np.arange(H)[:, None] + rng.integers(0, 2)) % 2 == 0
+        lo = rng.choice(near0, size=(H, W))
+        hi = rng.choice(near360, size=(H, W))
+        jitter = (rng.random((H, W)) * 20).astype(np.float32)
+        lo = np.where(rng.random((H, W)) < 0.5, lo, jitter)
+        hi = np.where(rng.random((H, W)) < 0.5, hi, np.float32(360.0) - jitter)
+        sc.theta[i] = np.where(seam, np.where(hi_row, hi, lo), sc.theta[i]).astype(np.float32)
+    assert sc.theta.min() >= 0 and sc.theta.max() <= 360
+    d = np.abs(sc.theta[:, 1:] - sc.theta[:, :-1])
+    assert (d >= 180).mean() > 0.2 and (d == 180).any()
+    zero = {"depth": 0, "sigma": 0, "checked": 0, "points": 0}
+    with api.Context(width=W, height=H, max_keyframes=sc.n) as ctx:
+        assert ctx.scan_generation() == 2
+        osc, dev = run_oracle(sc), run_device(sc, ctx=ctx)
+    assert _bit_equal(dev, osc) == zero
+    assert (osc.depth > 0).sum() > 300
+    sc.rot[1][:] = 90.0
+    sc.rot[3][:] = -180.0
+    osc, dev = run_oracle(sc), run_device(sc)
+    assert _bit_equal(dev, osc) == zero
