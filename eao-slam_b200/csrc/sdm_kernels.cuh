@@ -1246,6 +1246,11 @@ __device__ __forceinline__ float2 intra_check_pixel(const DevParams& P, const fl
 
 __device__ __forceinline__ float2 intra_grow_pixel(const DevParams& P, const float2* __restrict__ src, int px, int py, float2 c)
 {
+    // A centre with sigma = +-0 cannot grow, whatever its neighbours hold: ChiTest (:1641-1645) adds num / (0 * 0),
+    // which is +inf (num > 0) or NaN (num = 0 or NaN), to a term that is >= 0, +inf or NaN, and neither inf nor NaN
+    // is < 5.99.  Every empty pixel that pass 1 / the check stage leave behind is (0, 0), so the
+    // stage keeps its stencil for centres with a non-zero sigma only; exact for any plane contents.
+    if (c.y == 0.f) return c;
     float pjsj = 0.f, rsj = 0.f, min_sigma = 0.f;
     int n = 0;
     float2 nb[8];

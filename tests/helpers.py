@@ -95,3 +95,20 @@ class GoldenRef:
     def __init__(self, g, tag):
         self.depth, self.sigma = g[f"{tag}_depth"], g[f"{tag}_sigma"]
         self.checked, self.points = g[f"{tag}_checked"], g[f"{tag}_points"]
+
+
+def planes_that_grow(depth, sigma, seed):
+    """(rho, sigma) planes on which IntraKeyFrameDepthGrowing (:929-976) is NOT a no-op: holes punched into a pass-1
+    result keep a non-zero sigma (the invariant `rho = 0 => sigma = 0` of the shipped pipeline is broken on purpose),
+    some with rho just below the 1e-6 threshold, some with sigma = +-0 (those can never grow)."""
+    rng = np.random.default_rng(seed)
+    d, s = depth.copy(), sigma.copy()
+    filled = d > 0
+    hole = filled & (rng.random(d.shape) < 0.25)
+    kind = rng.integers(0, 4, d.shape)
+    s = np.where(hole & (kind == 0), np.float32(0.0), s)
+    s = np.where(hole & (kind == 1), np.float32(-0.0), s)
+    s = np.where(hole & (kind == 2), s * np.float32(3.0), s)        # wide sigma: neighbours become compatible
+    s = np.where(hole & (kind == 3), np.float32(0.5), s)
+    d = np.where(hole, np.where(rng.random(d.shape) < 0.5, np.float32(0.0), np.float32(9.9e-7)), d)
+    return np.ascontiguousarray(d, np.float32), np.ascontiguousarray(s, np.float32)

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 
 import oracle_py as O
-from helpers import run_oracle
+from helpers import planes_that_grow as _planes_that_grow, run_oracle
 from sdmb200 import api, synth
 
 pytestmark = pytest.mark.gpu
@@ -188,3 +188,27 @@ def test_inter_chi_gate_float_shortcut_is_exact():
     assert np.array_equal(got, ref), np.flatnonzero(got != ref)[:10]
     near = np.abs(chi[n // 2:] / 3.84 - 1.0) < 2.0 ** -16
     assert near.sum() > 1000 and (~near).sum() > 1000   # both the double fallback and the float shortcut were exercised
+
+
+def test_growing_stage_where_it_does_grow(scene):
+    """IntraKeyFrameDepthGrowing (:929-976) is a no-op on the planes the shipped pipeline produces (an empty pixel is
+    (0, 0) and a centre with sigma = 0 fails every ChiTest); the kernel uses exactly that as an early exit.  Planes
+    that break the invariant on purpose - holes that keep a non-zero sigma, rho just under 1e-6, sigma = +-0 next to
+    them - must still grow like the reference (tests/test_ref_vs_oracle.py pins the oracle on the same construction)."""
+    sc = scene
+    osc = O.OracleScene(sc)
+    osc.run(pass_mask=1)
+    H, W = sc.shape
+    p = O.default_params()
+    with api.Context(width=W, height=H, max_keyframes=sc.n) as ctx:
+        ctx.upload_scene(sc)
+        for i in (2, 5):
+            d, s = _planes_that_grow(osc.depth[i], osc.sigma[i], seed=60 + i)
+            ctx.upload_depth(i, d, s)
+            ctx.intra_grow(i)
+            got = ctx.download(i, checked=False, points=False)
+            d2, s2 = d.copy(), s.copy()
+            O.lib().oracle_intra_grow(O.fptr(d2), O.fptr(s2), O.fptr(np.ascontiguousarray(sc.grad[i])), W, H, C.byref(p))
+            assert np.array_equal(got["depth"].view(np.uint32), d2.view(np.uint32))
+            assert np.array_equal(got["sigma"].view(np.uint32), s2.view(np.uint32))
+            assert ((d2 != d) | (s2 != s)).sum() > 50

@@ -13,6 +13,7 @@ import pytest
 
 import oracle_py as O
 import ref_py
+from helpers import planes_that_grow as _planes_that_grow
 from sdmb200 import synth
 
 
@@ -84,6 +85,23 @@ def test_intra_check_and_grow_match_the_reference_source():
         O.lib().oracle_intra_grow(O.fptr(d2), O.fptr(s2), O.fptr(np.ascontiguousarray(sc.grad[i])), sc.shape[1], sc.shape[0], C.byref(p))
         assert np.array_equal(gd.view(np.uint32), d2.view(np.uint32)) and np.array_equal(gs.view(np.uint32), s2.view(np.uint32))
         assert np.array_equal(gd, d)                                   # growing is a no-op
+
+
+@pytest.mark.skipif(not ref_py.available(), reason="needs /root/reference or a prebuilt oracle/_ref/libref_pm.so")
+def test_growing_stage_where_it_does_grow_matches_the_reference_source():
+    sc, _ = _scene()
+    osc = O.OracleScene(sc)
+    osc.run(pass_mask=1)
+    p = O.default_params()
+    for i in (2, 6):
+        d, s = _planes_that_grow(osc.depth[i], osc.sigma[i], seed=40 + i)
+        gd, gs = ref_py.run_reference_intra(1, d, s, sc.grad[i])
+        d2, s2 = d.copy(), s.copy()
+        O.lib().oracle_intra_grow(O.fptr(d2), O.fptr(s2), O.fptr(np.ascontiguousarray(sc.grad[i])), sc.shape[1], sc.shape[0], C.byref(p))
+        assert np.array_equal(gd.view(np.uint32), d2.view(np.uint32)) and np.array_equal(gs.view(np.uint32), s2.view(np.uint32))
+        grown = (gd != d) | (gs != s)
+        assert grown.sum() > 50                                            # the stage did something
+        assert not grown[(s == 0) & (d < 1e-6)].any()                      # ... but never where the centre's sigma is +-0
 
 
 def test_oracle_matches_committed_reference_output(golden_dir):
