@@ -335,7 +335,7 @@ def main_ours(a, rank, world, local_rank):
     # as its pass 1 is queued; pass 2 of chunk k is queued right after pass 1 of chunk k+1 (its neighbours reach
     # at most N/2 keyframes into chunk k+1) and its depth_map_checked_/SemiDensePointSets_ follow.  Chunks whose
     # pass 2 needs halo planes of another rank wait for the exchange.  Raw C-ABI calls with prebuilt arguments.
-    CH = int(os.environ.get("SDM_BENCH_CHUNK", "10"))
+    CH = int(os.environ.get("SDM_BENCH_CHUNK", "4"))  # 4 / 6 / 10 / 16 keyframes per chunk: 33.9 / 34.4 / 34.6 / 35.1 ms per loop
     chunks = [owned[i:i + CH] for i in range(0, len(owned), CH)]
     chunk_items = [api.make_items(ch, sc.nbr_idx, sc.rot, sc.min_depth, sc.max_depth) for ch in chunks]
     chunk_need = [max(ch[-1], max(int(v) for s in ch for v in sc.nbr_idx[s])) for ch in chunks]
