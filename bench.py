@@ -102,24 +102,51 @@ class Clocks:
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
+        # nvidia-smi delivers a row every ~100 ms at best, i.e. one or two inside a 5-step timed region: NVML is polled
+        # directly as well (every 10 ms, same fields) and its rows are the ones reported when it works
+        self.nvml_rows, self.nvml_on = [], True
+        threading.Thread(target=self._poll_nvml, daemon=True).start()
+
+    def _poll_nvml(self):
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(self.idx)
+            mx = N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM)
+            get_reasons = getattr(N, "nvmlDeviceGetCurrentClocksEventReasons", None) or N.nvmlDeviceGetCurrentClocksThrottleReasons
+            bits = (N.nvmlClocksThrottleReasonHwSlowdown, N.nvmlClocksThrottleReasonHwThermalSlowdown,
+                    N.nvmlClocksThrottleReasonSwThermalSlowdown, N.nvmlClocksThrottleReasonSwPowerCap)
+            while self.nvml_on:
+                r = get_reasons(h)
+                row = [str(self.idx), str(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)), str(mx),
+                       str(N.nvmlDeviceGetPowerUsage(h) / 1000.0)] + ["Active" if r & b else "Not Active" for b in bits]
+                self.nvml_rows.append((time.time(), row))
+                time.sleep(0.01)
+        except Exception as e:  # noqa: BLE001  (no NVML, unsupported query: the nvidia-smi rows remain)
+            self.nvml_error = repr(e)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
+        self.nvml_on = False
         if self.proc:
             self.proc.terminate()
 
     def summary(self, t0, t1):
-        rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.15 and len(r) >= 8] or [r for _, r in self.rows if len(r) >= 8]
+        source = "nvml, polled every 10 ms during the timed region"
+        rows = [r for t, r in getattr(self, "nvml_rows", []) if t0 <= t <= t1]
+        if len(rows) < 2:
+            source = "nvidia-smi -lms 100"
+            rows = [r for t, r in self.rows if t0 <= t <= t1 + 0.15 and len(r) >= 8] or [r for _, r in self.rows if len(r) >= 8]
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         sm = [float(r[1]) for r in rows]
         reasons = [n for k, n in ((4, "hw_slowdown"), (5, "hw_thermal_slowdown"), (6, "sw_thermal_slowdown"),
                                   (7, "sw_power_cap")) if any(r[k].lower().startswith("active") for r in rows)]
         return {"sm_mhz": statistics.median(sm), "sm_max_mhz": float(rows[0][2]), "reasons": reasons,
-                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows)}
+                "samples": len(rows), "power_w_max": max(float(r[3]) for r in rows), "source": source}
 
 
 # ------------------------------------------------------------------------------------------------
