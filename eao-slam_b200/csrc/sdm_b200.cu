@@ -61,6 +61,9 @@ int fail(int code, const char* fmt, ...)
         if (rc_ != SDM_OK) return rc_; \
     } while (0)
 
+#ifndef SDM_DEFAULT_SCAN_GEN
+#define SDM_DEFAULT_SCAN_GEN 3  // scan loop generation of a context when env SDM_SCAN does not say (lane1 | lane2 | lane3 | warp)
+#endif
 constexpr int kUpStages = 48;   // upload staging sets (im, grad, theta, edge): H2D runs this far ahead of k_pack
 constexpr int kDownStages = 6;  // (rho | sigma) split staging sets
 constexpr int kItemStages = 32;  // pinned work-order staging buffers (how many passes the host may run ahead)
@@ -125,6 +128,7 @@ struct KfState {
     uint64_t down_ds_id = 0;  // last download of depth_map_ / depth_sigma_ (pass 1 and the intra stencils overwrite them)
     uint64_t down_cp_id = 0;  // last download of depth_map_checked_ / points (pass 2 overwrites them)
     uint64_t count_id = 0;    // compute-ring id after which h_cand[slot] holds the slot's candidate count
+    uint64_t pull_id = 0;     // compute-ring id of a halo pull (sdm_exchange) into the slot, recorded on the halo stream
 };
 
 struct UpStage {
@@ -261,6 +265,16 @@ struct sdm_ctx {
     sdm_point* exp_pts = nullptr;
     size_t exp_pts_cap = 0;
     void* peer_rs[kMaxPeers] = {nullptr};
+    // sdm_exchange: flag blocks (own + IPC-mapped peers), halo plan, step counter
+    sdm::XFlags* xflags = nullptr;
+    sdm::XFlags* peer_flags[kMaxPeers] = {nullptr};
+    void* peer_rs2[kMaxPeers] = {nullptr};  // peers' (rho,sigma) arenas opened by sdm_import_peer
+    int peer_nslots[kMaxPeers] = {0};
+    int my_rank = -1;
+    unsigned xstep = 0, acks_waited = 0;
+    std::vector<int32_t> halo_local, halo_rank, halo_slot;
+    std::vector<char> is_halo;  // per slot
+    cudaStream_t s_halo = nullptr;
     int grid_pass1_warp = 0, grid_pass2 = 0, grid_intra = 0, n_sm = 0;  // persistent grids (blocks)
     long long launches = 0;
     bool trace = false;
@@ -535,10 +549,15 @@ void sdm_destroy(sdm_ctx* c)
     if (!c) return;
     cudaSetDevice(c->cfg.device);
     cudaDeviceSynchronize();
-    for (int i = 0; i < kMaxPeers; ++i)
+    for (int i = 0; i < kMaxPeers; ++i) {
         if (c->peer_rs[i]) cudaIpcCloseMemHandle(c->peer_rs[i]);
+        if (c->peer_rs2[i]) cudaIpcCloseMemHandle(c->peer_rs2[i]);
+        if (c->peer_flags[i]) cudaIpcCloseMemHandle(c->peer_flags[i]);
+    }
+    cudaFree(c->xflags);
+    if (c->s_halo) cudaStreamDestroy(c->s_halo);
     cudaFree(c->A.tex); cudaFree(c->A.ipair); cudaFree(c->A.texw); cudaFree(c->A.cand); cudaFree(c->A.cand_count);
-    cudaFree(c->A.plane_irregular);
+    cudaFree(c->A.plane_irregular); cudaFree(c->A.skip);
     cudaFree(c->A.rs); cudaFree(c->A.chk); cudaFree(c->A.pts); cudaFree(c->A.dpl); cudaFree(c->A.spl); cudaFree(c->A.rs2);
     for (auto& s : c->up) { cudaFree(s.im); cudaFree(s.grad); cudaFree(s.theta); cudaFree(s.edge); }
     for (auto& s : c->down) cudaFree(s.planes);
@@ -614,6 +633,10 @@ static int create_impl(sdm_ctx* c)
     CU(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->s_down, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->s_halo, cudaStreamNonBlocking));
+    CU(cudaMalloc(&c->xflags, sizeof(sdm::XFlags)));
+    CU(cudaMemset(c->xflags, 0, sizeof(sdm::XFlags)));
+    c->is_halo.assign(n, 0);
     RC(c->r_copy.init(1024));
     RC(c->r_compute.init(1024));
     RC(c->r_down.init(1024));
@@ -628,7 +651,6 @@ static int create_impl(sdm_ctx* c)
     A.P = P;
     CU(cudaMalloc(&A.tex, n * P * sizeof(float4)));
     CU(cudaMalloc(&A.ipair, n * P * sizeof(uchar2)));
-    CU(cudaMalloc(&A.texw, n * P * sizeof(float4)));
     CU(cudaMalloc(&A.cand, n * P * sizeof(uint32_t)));
     CU(cudaMalloc(&A.cand_count, n * sizeof(int)));
     CU(cudaMalloc(&A.plane_irregular, n * sizeof(int)));
@@ -684,8 +706,18 @@ static int create_impl(sdm_ctx* c)
         CU(cudaMemcpyAsync(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, c->s_compute));
         CU(cudaStreamSynchronize(c->s_compute));
         CU(cudaMemsetAsync(d_bad, 0, sizeof(bad), c->s_compute));
-        D.scan2 = (bad == 0);
+        D.scan2 = (bad == 0) ? 2 : 0;
+        // third generation: second-generation arithmetic on the columns the skip planes (k_skip) leave.  Its row-exit
+        // estimate is sized for images up to 8192 x 8192 (scan_columns3)
+        const bool want3 = SDM_DEFAULT_SCAN_GEN == 3 ? !(scan_env && strcmp(scan_env, "lane2") == 0)
+                                                     : (scan_env && strcmp(scan_env, "lane3") == 0);
+        if (D.scan2 && want3 && cfg.width <= 8192 && cfg.height <= 8192) {
+            CU(cudaMalloc(&A.skip, n * P * sdm::kSkipBins));
+            D.scan2 = 3;
+        }
     }
+    // the wrap-encoded texel plane of the second / third generation (irregular keyframes run the first generation on tex)
+    if (D.scan2) CU(cudaMalloc(&A.texw, n * P * sizeof(float4)));
     CU(cudaStreamSynchronize(c->s_compute));
     if (c->trace) {
         CU(cudaEventCreate(&c->trace_base));
@@ -723,6 +755,16 @@ int sdm_synchronize(sdm_ctx* c)
     CU(cudaStreamSynchronize(c->s_copy));
     CU(cudaStreamSynchronize(c->s_compute));
     CU(cudaStreamSynchronize(c->s_down));
+    CU(cudaStreamSynchronize(c->s_halo));
+    if (c->xstep) {  // a device-side wait of sdm_exchange / sdm_pass1 that gave up
+        unsigned err = 0;
+        CU(cudaMemcpy(&err, &c->xflags->err, sizeof(err), cudaMemcpyDeviceToHost));
+        if (err) {
+            CU(cudaMemset(&c->xflags->err, 0, sizeof(err)));
+            return fail(SDM_ERR_STATE, "sdm_exchange: device-side wait for %s timed out (a peer did not reach the same step)",
+                        err == 1 ? "an owner's pass-1 planes" : "the pullers' acknowledgements");
+        }
+    }
     if (c->scat) {  // host-side scatters of sdm_scatter_keyframes
         std::unique_lock<std::mutex> lk(c->scat->mu);
         c->scat->cv_idle.wait(lk, [&] { return c->scat->pending == 0; });
@@ -736,7 +778,7 @@ int sdm_synchronize(sdm_ctx* c)
     return SDM_OK;
 }
 
-int sdm_scan_generation(sdm_ctx* c) { return c ? (c->P.scan2 ? 2 : 1) : 0; }
+int sdm_scan_generation(sdm_ctx* c) { return c ? (c->P.scan2 ? c->P.scan2 : 1) : 0; }
 
 int sdm_get_stats(sdm_ctx* c, sdm_stats* out)
 {
@@ -814,6 +856,10 @@ int sdm_upload_keyframes(sdm_ctx* c, int n, const sdm_upload_desc* d)
                               dim3(32, 8), 0, c->s_compute>>>(c->A, c->P, u.kf, st.im, st.grad, st.theta, u.edge ? st.edge : nullptr);
             else  // GradImg / GradTheta produced on the device from im_ (KeyFrame.cc:69-74)
                 sdm::k_pack_image<<<tile_grid(c), dim3(32, 8), 0, c->s_compute>>>(c->A, c->P, u.kf, st.im, u.edge ? st.edge : nullptr);
+            if (c->A.skip) {  // skip distances of the third-generation scan loop, from the texels just packed
+                sdm::k_skip<<<(H + sdm::kSkipWarps - 1) / sdm::kSkipWarps, 32 * sdm::kSkipWarps, 0, c->s_compute>>>(c->A, c->P, u.kf);
+                c->launches++;
+            }
         }
         static_assert(kUpStages / 2 <= sdm::kSlotList, "slot list of k_publish_counts");
         sdm::SlotList sl;
@@ -908,6 +954,12 @@ int sdm_pass1(sdm_ctx* c, int n, const sdm_item* items)
             k.split_stale = false;
         }
     }
+    if (c->xstep && c->acks_waited != c->xstep) {
+        // the planes about to be overwritten may still be read by peers pulling the previous step (sdm_exchange)
+        sdm::k_xwait_acks<<<1, 32, 0, c->s_compute>>>(c->xflags, c->xstep);
+        c->acks_waited = c->xstep;
+        c->launches++;
+    }
     CU(cudaMemsetAsync(&c->d_stats->fused, 0, sizeof(unsigned long long), c->s_compute));
     const sdm::DevPlan plan = make_plan(c, nullptr, n);
     sdm::k_plan<<<1, 1024, 0, c->s_compute>>>(plan, c->d_items, c->A.cand_count, c->d_stats);
@@ -922,7 +974,7 @@ int sdm_pass1(sdm_ctx* c, int n, const sdm_item* items)
         int occ = 0;  // persistent grid: fill every SM to this launch's occupancy
         // the exact short forms of the two direction gates exist for the reference's thresholds only
         const bool fast = (c->cfg.lambdaL == 80 && c->cfg.lambdaTheta == 45);
-        auto kern = fast ? sdm::k_pass1_lane<true> : sdm::k_pass1_lane<false>;
+        auto kern = !fast ? sdm::k_pass1_lane<false, 2> : (c->P.scan2 == 3 ? sdm::k_pass1_lane<true, 3> : sdm::k_pass1_lane<true, 2>);
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, sdm::kLaneBlock, smem));
         kern<<<std::max(1, occ) * c->n_sm, sdm::kLaneBlock, smem, c->s_compute>>>(c->A, c->P, c->d_items, plan, c->d_stats);
     }
@@ -947,13 +999,14 @@ int sdm_pass1(sdm_ctx* c, int n, const sdm_item* items)
     return SDM_OK;
 }
 
-static int pass2_impl(sdm_ctx* c, int n, const sdm_item* items, int points_only)
+// continuation = second half of a pass split around a halo pull (sdm_pass2): keeps the counters and the start event
+static int pass2_impl(sdm_ctx* c, int n, const sdm_item* items, int points_only, bool continuation = false)
 {
     CU(cudaSetDevice(c->cfg.device));
     Batch b;
     RC(prepare_batch(c, n, items, true, points_only != 0, &b));
-    if (!points_only) CU(cudaMemsetAsync(&c->d_stats->checked, 0, sizeof(unsigned long long), c->s_compute));
-    CU(cudaEventRecord(c->ev_p2[0], c->s_compute));
+    if (!points_only && !continuation) CU(cudaMemsetAsync(&c->d_stats->checked, 0, sizeof(unsigned long long), c->s_compute));
+    if (!continuation) CU(cudaEventRecord(c->ev_p2[0], c->s_compute));
     if (b.n_sparse > 0) {
         const sdm::DevPlan plan = make_plan(c, b.d_order_sparse, b.n_sparse);
         sdm::k_plan<<<1, 1024, 0, c->s_compute>>>(plan, c->d_items, c->A.cand_count, nullptr);
@@ -977,7 +1030,27 @@ int sdm_pass2(sdm_ctx* c, int n, const sdm_item* items)
     if (!c || (n > 0 && !items)) return fail(SDM_ERR_ARG, "sdm_pass2: null argument");
     if (n <= 0) return SDM_OK;
     if (n > 65535) return fail(SDM_ERR_ARG, "pass-2 batch limited to 65535 keyframes per call");
-    return pass2_impl(c, n, items, 0);
+    // keyframes that read a plane still being pulled from a peer (sdm_exchange) go second, behind the pull;
+    // the others run at once, so the NVLink copies overlap pass 2 of the interior keyframes
+    uint64_t need_pull = 0;
+    std::vector<sdm_item> indep, dep;
+    for (int i = 0; i < n; ++i) {
+        bool d = false;
+        if (items[i].n_nbr >= 0 && items[i].n_nbr <= SDM_MAX_NBR)
+            for (int j = -1; j < items[i].n_nbr; ++j) {
+                const int slot = j < 0 ? items[i].kf : items[i].nbr[j];
+                if (!slot_ok(c, slot)) continue;  // reported by build_item
+                const uint64_t id = c->kf[slot].pull_id;
+                if (id && !c->r_compute.done(id)) { d = true; need_pull = std::max(need_pull, id); }
+            }
+        if (need_pull == 0) continue;  // nothing in flight so far: no copies needed yet
+        if (indep.empty() && dep.empty()) indep.assign(items, items + i);
+        (d ? dep : indep).push_back(items[i]);
+    }
+    if (need_pull == 0) return pass2_impl(c, n, items, 0);
+    if (!indep.empty()) RC(pass2_impl(c, (int)indep.size(), indep.data(), 0));
+    RC(c->r_compute.wait(c->s_compute, need_pull));
+    return pass2_impl(c, (int)dep.size(), dep.data(), 0, !indep.empty());
 }
 
 int sdm_update_points(sdm_ctx* c, int n, const int32_t* kfs)
@@ -1317,6 +1390,221 @@ int sdm_mark_pass1_done(sdm_ctx* c, int kf)
     c->kf[kf].rs_dense = true;
     c->kf[kf].split_stale = true;
     return SDM_OK;
+}
+
+// ---- exchange ordered on the devices --------------------------------------------------------------
+namespace {
+struct PeerHandleLayout {
+    cudaIpcMemHandle_t rs, flags;
+    int32_t n_slots, rank;
+    uint64_t slot_bytes;
+};
+static_assert(sizeof(PeerHandleLayout) <= SDM_PEER_HANDLE_BYTES, "sdm_peer_handle too small");
+}  // namespace
+
+int sdm_export_peer_handle(sdm_ctx* c, int my_rank, sdm_peer_handle* out)
+{
+    if (!c || !out) return fail(SDM_ERR_ARG, "null argument");
+    if (my_rank < 0 || my_rank >= kMaxPeers) return fail(SDM_ERR_ARG, "rank %d out of [0,%d)", my_rank, kMaxPeers);
+    CU(cudaSetDevice(c->cfg.device));
+    PeerHandleLayout h;
+    memset(&h, 0, sizeof(h));
+    CU(cudaIpcGetMemHandle(&h.rs, c->A.rs));
+    CU(cudaIpcGetMemHandle(&h.flags, c->xflags));
+    h.n_slots = (int32_t)c->kf.size();
+    h.rank = my_rank;
+    h.slot_bytes = c->npix * sizeof(float2);
+    memset(out, 0, sizeof(*out));
+    memcpy(out->bytes, &h, sizeof(h));
+    c->my_rank = my_rank;
+    return SDM_OK;
+}
+
+int sdm_import_peer(sdm_ctx* c, int peer_rank, const sdm_peer_handle* handle)
+{
+    if (!c || !handle) return fail(SDM_ERR_ARG, "null argument");
+    if (peer_rank < 0 || peer_rank >= kMaxPeers) return fail(SDM_ERR_ARG, "peer rank %d out of [0,%d)", peer_rank, kMaxPeers);
+    if (c->my_rank < 0) return fail(SDM_ERR_STATE, "sdm_import_peer before sdm_export_peer_handle (this rank's number is unknown)");
+    PeerHandleLayout h;
+    memcpy(&h, handle->bytes, sizeof(h));
+    if (h.rank != peer_rank) return fail(SDM_ERR_ARG, "handle belongs to rank %d, not %d", h.rank, peer_rank);
+    if (h.slot_bytes != c->npix * sizeof(float2)) return fail(SDM_ERR_ARG, "peer %d uses another image size", peer_rank);
+    CU(cudaSetDevice(c->cfg.device));
+    if (c->peer_rs2[peer_rank]) { CU(cudaIpcCloseMemHandle(c->peer_rs2[peer_rank])); c->peer_rs2[peer_rank] = nullptr; }
+    if (c->peer_flags[peer_rank]) { CU(cudaIpcCloseMemHandle(c->peer_flags[peer_rank])); c->peer_flags[peer_rank] = nullptr; }
+    void *p = nullptr, *f = nullptr;
+    CU(cudaIpcOpenMemHandle(&p, h.rs, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_rs2[peer_rank] = p;
+    CU(cudaIpcOpenMemHandle(&f, h.flags, cudaIpcMemLazyEnablePeerAccess));
+    c->peer_flags[peer_rank] = (sdm::XFlags*)f;
+    c->peer_nslots[peer_rank] = h.n_slots;
+    // tell the owner that this rank pulls from it: its next pass 1 waits for our acknowledgement
+    sdm::k_xregister<<<1, 1, 0, c->s_compute>>>(c->peer_flags[peer_rank], c->my_rank);
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(c->s_compute));
+    return SDM_OK;
+}
+
+int sdm_set_halo(sdm_ctx* c, int n, const int32_t* local_slot, const int32_t* peer_rank, const int32_t* peer_slot)
+{
+    if (!c || (n > 0 && (!local_slot || !peer_rank || !peer_slot))) return fail(SDM_ERR_ARG, "null argument");
+    for (int i = 0; i < n; ++i) {
+        if (!slot_ok(c, local_slot[i])) return fail(SDM_ERR_ARG, "local slot %d out of range", local_slot[i]);
+        const int pr = peer_rank[i];
+        if (pr < 0 || pr >= kMaxPeers || !c->peer_flags[pr]) return fail(SDM_ERR_STATE, "peer %d not imported (sdm_import_peer)", pr);
+        if (peer_slot[i] < 0 || peer_slot[i] >= c->peer_nslots[pr])
+            return fail(SDM_ERR_ARG, "peer slot %d out of [0,%d) of rank %d", peer_slot[i], c->peer_nslots[pr], pr);
+    }
+    c->halo_local.assign(local_slot, local_slot + std::max(n, 0));
+    c->halo_rank.assign(peer_rank, peer_rank + std::max(n, 0));
+    c->halo_slot.assign(peer_slot, peer_slot + std::max(n, 0));
+    std::fill(c->is_halo.begin(), c->is_halo.end(), 0);
+    for (int i = 0; i < n; ++i) c->is_halo[local_slot[i]] = 1;
+    return SDM_OK;
+}
+
+int sdm_exchange(sdm_ctx* c)
+{
+    if (!c) return fail(SDM_ERR_ARG, "null context");
+    if (c->my_rank < 0) return SDM_OK;  // single GPU: nothing to exchange
+    CU(cudaSetDevice(c->cfg.device));
+    const unsigned step = ++c->xstep;
+    // everything queued on the compute stream so far (pass 1 of this step) precedes the flag
+    sdm::k_xpublish<<<1, 1, 0, c->s_compute>>>(c->xflags, step);
+    c->launches++;
+    const int n = (int)c->halo_local.size();
+    if (n == 0) { CU(cudaGetLastError()); return SDM_OK; }
+    cudaStream_t s = c->s_halo;
+    uint64_t need_c = 0, need_d = 0;
+    unsigned peers = 0;
+    for (int i = 0; i < n; ++i) {
+        const KfState& k = c->kf[c->halo_local[i]];
+        need_c = std::max(need_c, k.comp_id);   // last kernel that read the slot (pass 2 of the previous step) or packed it
+        need_d = std::max(need_d, k.down_ds_id);
+        peers |= 1u << c->halo_rank[i];
+    }
+    RC(c->r_compute.wait(s, need_c));
+    RC(c->r_down.wait(s, need_d));
+    for (int r = 0; r < kMaxPeers; ++r)
+        if (peers >> r & 1u) { sdm::k_xwait_done<<<1, 1, 0, s>>>(c->peer_flags[r], step, c->xflags); c->launches++; }
+    const size_t bytes = c->npix * sizeof(float2);
+    for (int i = 0; i < n; ++i) {
+        const char* src = (const char*)c->peer_rs2[c->halo_rank[i]] + (size_t)c->halo_slot[i] * bytes;
+        CU(cudaMemcpyAsync(c->A.rs + (size_t)c->halo_local[i] * c->npix, src, bytes, cudaMemcpyDeviceToDevice, s));
+    }
+    for (int r = 0; r < kMaxPeers; ++r)
+        if (peers >> r & 1u) { sdm::k_xack<<<1, 1, 0, s>>>(c->peer_flags[r], c->my_rank, step); c->launches++; }
+    CU(cudaGetLastError());
+    uint64_t id = 0;
+    RC(c->r_compute.record(s, &id));
+    for (int i = 0; i < n; ++i) {
+        KfState& k = c->kf[c->halo_local[i]];
+        k.comp_id = id;
+        k.pull_id = id;
+        k.pass1_done = true;
+        k.rs_dense = true;
+        k.split_stale = true;
+    }
+    return SDM_OK;
+}
+
+// ---- one SemiDenseLoop as a pipeline ---------------------------------------------------------------
+int sdm_run_loop(sdm_ctx* c, const sdm_loop* L)
+{
+    if (!c || !L) return fail(SDM_ERR_ARG, "sdm_run_loop: null argument");
+    if ((L->n_upload > 0 && !L->upload) || (L->n_pass1 > 0 && !L->pass1) || (L->n_pass2 > 0 && !L->pass2))
+        return fail(SDM_ERR_ARG, "sdm_run_loop: null array");
+    const int CH = L->chunk > 0 ? L->chunk : 4;
+    const int n1 = std::max(L->n_pass1, 0), n2 = std::max(L->n_pass2, 0), nu = std::max(L->n_upload, 0);
+    const int nslots = (int)c->kf.size();
+    std::vector<int> up_pos(nslots, -1), p1_pos(nslots, -1);
+    for (int i = 0; i < nu; ++i) {
+        if (!slot_ok(c, L->upload[i].kf)) return fail(SDM_ERR_ARG, "upload slot %d out of range", L->upload[i].kf);
+        up_pos[L->upload[i].kf] = i;
+    }
+    auto slots_ok = [&](const sdm_item& it) {
+        if (!slot_ok(c, it.kf) || it.n_nbr < 0 || it.n_nbr > SDM_MAX_NBR) return false;
+        for (int j = 0; j < it.n_nbr; ++j)
+            if (!slot_ok(c, it.nbr[j])) return false;
+        return true;
+    };
+    for (int i = 0; i < n1; ++i) {
+        if (!slots_ok(L->pass1[i])) return fail(SDM_ERR_ARG, "pass-1 work order %d names a slot out of range", i);
+        p1_pos[L->pass1[i].kf] = i;
+    }
+    // pass-2 work order i may be queued once pass 1 of work order ready[i] has been (-1: at once); work orders that
+    // read a halo plane wait for the exchange
+    std::vector<int> ready(n2), order(n2);
+    std::vector<char> after_x(n2, 0);
+    for (int i = 0; i < n2; ++i) {
+        const sdm_item& it = L->pass2[i];
+        if (!slots_ok(it)) return fail(SDM_ERR_ARG, "pass-2 work order %d names a slot out of range", i);
+        int r = p1_pos[it.kf];
+        bool halo = L->exchange && c->is_halo[it.kf];
+        for (int j = 0; j < it.n_nbr; ++j) {
+            r = std::max(r, p1_pos[it.nbr[j]]);
+            halo = halo || (L->exchange && c->is_halo[it.nbr[j]]);
+        }
+        ready[i] = r;
+        after_x[i] = halo;
+        order[i] = i;
+    }
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return ready[a] < ready[b]; });
+    std::vector<sdm_item> batch;
+    std::vector<sdm_download_desc> dl;
+    std::vector<int> deferred;
+    int next2 = 0, next_up = 0;
+    auto run2 = [&](const std::vector<int>& idx) -> int {
+        for (size_t i0 = 0; i0 < idx.size(); i0 += (size_t)CH) {
+            const size_t m = std::min<size_t>(CH, idx.size() - i0);
+            batch.clear(); dl.clear();
+            for (size_t i = 0; i < m; ++i) {
+                batch.push_back(L->pass2[idx[i0 + i]]);
+                if (L->down2) dl.push_back(L->down2[idx[i0 + i]]);
+            }
+            RC(sdm_pass2(c, (int)m, batch.data()));
+            if (!dl.empty()) RC(sdm_download_keyframes(c, (int)dl.size(), dl.data()));
+        }
+        return SDM_OK;
+    };
+    std::vector<int> now;
+    for (int i0 = 0; i0 < n1 || i0 == 0; i0 += CH) {
+        const int m = std::min(CH, n1 - i0);
+        if (m > 0) {
+            int need = -1;  // uploads go out in list order up to the last one this chunk needs
+            for (int i = 0; i < m; ++i) {
+                const sdm_item& it = L->pass1[i0 + i];
+                need = std::max(need, up_pos[it.kf]);
+                for (int j = 0; j < it.n_nbr; ++j) need = std::max(need, up_pos[it.nbr[j]]);
+            }
+            if (need >= next_up) {
+                RC(sdm_upload_keyframes(c, need + 1 - next_up, L->upload + next_up));
+                next_up = need + 1;
+            }
+            RC(sdm_pass1(c, m, L->pass1 + i0));
+            if (L->down1) RC(sdm_download_keyframes(c, m, L->down1 + i0));
+        }
+        // pass 2 of the work orders whose pass-1 inputs are all queued, one chunk behind: the newest chunk's pass 1 is
+        // queued first so that the SMs never wait for a download
+        now.clear();
+        const int done_before = i0;  // pass-1 work orders [0, i0) were queued before this chunk
+        while (next2 < n2 && ready[order[next2]] < done_before) {
+            const int i = order[next2++];
+            if (after_x[i]) deferred.push_back(i); else now.push_back(i);
+        }
+        RC(run2(now));
+        if (m <= 0) break;
+    }
+    if (next_up < nu) RC(sdm_upload_keyframes(c, nu - next_up, L->upload + next_up));
+    if (L->exchange) RC(sdm_exchange(c));
+    now.clear();
+    while (next2 < n2) {
+        const int i = order[next2++];
+        if (after_x[i]) deferred.push_back(i); else now.push_back(i);
+    }
+    RC(run2(now));
+    std::sort(deferred.begin(), deferred.end());
+    return run2(deferred);
 }
 
 // ---- per-method entry points ---------------------------------------------------------------------

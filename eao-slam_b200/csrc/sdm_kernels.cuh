@@ -45,8 +45,11 @@ struct DevParams {
     float eps_gt;         // x > this  <=>  (double)x > 0.000001
     float eps_lt;         // x < this  <=>  (double)x < 0.000001
     float slope_max;
-    int scan2;        // second-generation scan loop enabled (reference thresholds + verified reciprocal division)
+    int scan2;        // scan loop generation: 0 = first (any thresholds), 2 = second (reference thresholds + verified
+                      // reciprocal division), 3 = third (second + skip-distance planes, scan_columns3)
 };
+
+constexpr int kSkipBins = 8;  // orientation bins of the skip-distance planes (k_skip, scan_columns3)
 
 struct DevArena {
     float4* tex;
@@ -61,6 +64,7 @@ struct DevArena {
     float* dpl;  // dense depth_map_ plane   } copies of rs.x / rs.y kept for the D2H path, so a download is
     float* spl;  // dense depth_sigma_ plane } pure DMA (no de-interleave kernel competing for SMs)
     float2* rs2;  // second (rho,sigma) plane of the intra ping-pong: zero outside the candidate pixels
+    uint8_t* skip;  // [slot][kSkipBins][P] skip distances of the third-generation scan loop (k_skip); nullptr = not built
     size_t P;  // pixels per plane
 };
 
@@ -272,7 +276,8 @@ __device__ __forceinline__ float pixel_inv_depth(float u, double s2d, double s0d
 struct Hypo {
     float depth, sigma, best_u, best_v;
 };
-__device__ __forceinline__ Hypo refine_hypothesis(const float4* __restrict__ tex2, const uchar2* __restrict__ ip2,
+template <class TG, class TI>
+__device__ __forceinline__ Hypo refine_hypothesis(const TG* __restrict__ tex2, const TI* __restrict__ ip2,
                                                   const DevPair& g, const float* K, const DevParams& P, int best,
                                                   float ab, float cb, float pe, float ge, float xn, float yn)
 {
@@ -363,7 +368,7 @@ __global__ void __launch_bounds__(256) k_pack(DevArena A, DevParams P, int slot,
         A.tex[base + i0] = make_float4(g0, g1, th0, th1);
         A.ipair[base + i0] = make_uchar2(p0, p1);
         const float2 tw = encode_theta_pair(th0, th1);
-        A.texw[base + i0] = make_float4(g0, g1, tw.x, tw.y);
+        if (A.texw) A.texw[base + i0] = make_float4(g0, g1, tw.x, tw.y);
         A.rs[base + i0] = make_float2(0.f, 0.f);
         A.dpl[base + i0] = 0.f;
         A.spl[base + i0] = 0.f;
@@ -449,7 +454,7 @@ k_pack_image(DevArena A, DevParams P, int slot, const uint8_t* __restrict__ im, 
         A.tex[base + i0] = make_float4(g0.x, g1.x, g0.y, g1.y);
         A.ipair[base + i0] = make_uchar2(p0, p1);
         const float2 tw = encode_theta_pair(g0.y, g1.y);
-        A.texw[base + i0] = make_float4(g0.x, g1.x, tw.x, tw.y);
+        if (A.texw) A.texw[base + i0] = make_float4(g0.x, g1.x, tw.x, tw.y);
         A.rs[base + i0] = make_float2(0.f, 0.f);
         A.dpl[base + i0] = 0.f;
         A.spl[base + i0] = 0.f;
@@ -480,6 +485,60 @@ __global__ void k_split_tex(const float4* __restrict__ tex, float* __restrict__ 
 {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) { float4 v = tex[i]; g[i] = v.x; t[i] = v.z; }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Skip-distance planes of the third-generation scan loop (scan_columns3).  For every texel (row pair y / y+1, column x)
+// and each of kSkipBins orientation bins q, M_q(y,x) = 1 if a candidate column that lands on this texel MAY survive
+// conditions 1 and 3 of the scan body (:788, :801-809) for a pixel whose th_pi + rot lies in bin q:
+//   condition 1: fl(G0*w0) + fl(G1*w1) <= 8 whenever G0 <= 8 and G1 <= 8 (w0 + w1 rounds to <= 1: both products are
+//                <= 8*w, the sum is <= 8*fl(w0 + w1) = 8), so "G0 > 8 or G1 > 8" is necessary;
+//   condition 3: the interpolated orientation lies on the short arc between the texel's two orientations (through the
+//                0/360 seam when they are >= 180 apart, :83-111) up to float rounding (< 1e-3 deg), and the gate passes
+//                only within 45 deg (+ 2^-16) of th_pi + rot, which lies in [45q, 45q + 45]: the arc, widened by a
+//                0.05 deg margin, must meet (45q - 45, 45q + 90).
+// The plane stores S_q(y,x) = distance to the next column x' > x of the SAME row with M_q(y,x') = 1 (capped at 255):
+// a lane that has evaluated column x of row y may jump S_q columns ahead as long as its line stays in row y.
+// One block per image row, one warp per bin; right-to-left over 32-column chunks.
+// ---------------------------------------------------------------------------------------------
+constexpr float kSkipBinDeg = 360.0f / kSkipBins;
+
+constexpr int kSkipWarps = 4;
+__global__ void __launch_bounds__(32 * kSkipWarps) k_skip(DevArena A, DevParams P, int slot)
+{
+    const int lane = threadIdx.x & 31;
+    const int y = blockIdx.x * kSkipWarps + (threadIdx.x >> 5);
+    if (y >= P.H) return;
+    const float4* __restrict__ row = A.tex + (size_t)slot * A.P + (size_t)y * P.W;
+    uint8_t* __restrict__ out = A.skip + (size_t)slot * kSkipBins * A.P + (size_t)y * P.W;  // + q * A.P: plane of bin q
+    int carry[kSkipBins];  // per bin: distance from the first column right of the current chunk to the next set texel
+#pragma unroll
+    for (int q = 0; q < kSkipBins; ++q) carry[q] = 255;
+    for (int c0 = ((P.W - 1) / 32) * 32; c0 >= 0; c0 -= 32) {
+        const int x = c0 + lane;
+        bool g1 = false;
+        float c = 0.f, h = 0.f;
+        if (x < P.W) {
+            const float4 t = row[x];
+            const float d = fabsf(t.z - t.w);
+            c = (t.z + t.w) * 0.5f;
+            h = d * 0.5f;
+            if (!(d < 180.f)) { c += 180.f; h = (360.f - d) * 0.5f; }
+            g1 = t.x > kLambdaG2 || t.y > kLambdaG2;
+        }
+#pragma unroll
+        for (int q = 0; q < kSkipBins; ++q) {
+            float dist = fabsf(c - ((float)q + 0.5f) * kSkipBinDeg);  // c in [0, 540), bin centre in (0, 360)
+            if (dist > 360.f) dist -= 360.f;
+            if (dist > 180.f) dist = 360.f - dist;
+            const bool m = g1 && (dist < h + (0.5f * kSkipBinDeg + 45.f + 0.05f));
+            const unsigned bal = __ballot_sync(SDM_FULL, m);
+            const unsigned higher = (bal >> lane) >> 1;
+            const int sd = min(higher ? __ffs(higher) : 32 - lane + carry[q], 255);
+            if (x < P.W) out[(size_t)q * A.P + x] = (uint8_t)sd;
+            carry[q] = bal ? __ffs(bal) - 1 : min(carry[q] + 32, 255);
+        }
+    }
 }
 
 __device__ __forceinline__ void load_item(DevItem& s_item, const DevItem* __restrict__ src_item)
@@ -877,6 +936,89 @@ __device__ __forceinline__ int scan_columns2(const float4* __restrict__ texw2, c
     return best_n > 0 ? ub + 1 - best_n : -1;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Third-generation column loop (kMode 3): scan_columns2's arithmetic on the columns that can matter.  The loop of
+// scan_columns2 is bound by instruction issue and evaluates every column of the search range although 53 % of them
+// fail condition 1 and 57 % of the rest fail condition 3; a warp pays for a column as soon as one lane needs it, so
+// what helps is fewer columns per LANE.  After evaluating column u in row pair y, the lane reads S = skip[q][y][u]
+// (k_skip: no texel of row y in columns u+1 .. u+S-1 can survive conditions 1 and 3 for this pixel's orientation bin q)
+// and m = the number of following columns whose line position certainly stays in row pair y, and advances by
+// max(1, min(S, m + 1)).  Skipped columns would have been skipped by the reference's `continue`s, so best_err /
+// best column are untouched: same bits as scan_columns2.  The first column of a search range and the first column
+// after every row change are evaluated unconditionally (a superset is all that exactness needs).
+//   m: with rem = distance of v(u) to the row boundary the line is heading for (1 - w1 if v grows with u, else w1),
+//   the columns u + i with i * |a/b| <= rem - 2^-8 stay in the row: v is evaluated as -fl(fl(ab*u) + cb), each
+//   rounding <= 2^-13 for |values| < 4096 (2^-11 below 16384: the loop is used for images up to 8192 columns / rows),
+//   so two evaluations differ from the real line by < 2^-10 rows, a quarter of the 2^-8 margin; 1/|a/b| is scaled by
+//   1 - 2^-10 and capped at 2^20 so that the float product cannot exceed the real quotient.
+// CPU sizing of the design: tools/sim_mask_walk2.py / DESIGN.md section 5.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int scan_columns3(const float4* __restrict__ texw2, const uchar2* __restrict__ ip2,
+                                             const uint8_t* __restrict__ skip2, int W, int ua, int ub, float ab, float cb,
+                                             float th_line, float ang_pi_rot, float pixel, float gradc, float& best_err)
+{
+    constexpr float kMagic = 8388608.0f;
+    constexpr float kT2 = -0x1.67fff8p+5f;  // -(45 - 2^-16)
+    const char* tb = reinterpret_cast<const char*>(texw2);
+    const char* ib = reinterpret_cast<const char*>(ip2);
+    const char* sb = reinterpret_cast<const char*>(skip2);  // the plane of this pixel's orientation bin
+    unsigned Wm = (unsigned)W;
+    asm volatile("" : "+l"(tb), "+l"(ib), "+l"(sb), "+r"(Wm));
+    const float inv = fminf((1.0f - 0x1p-10f) / fabsf(ab), 0x1p20f);
+    const float dinv1 = 0x1p-8f * inv - 1.0f;  // floor(rem * inv - dinv1) = m + 1
+    const bool up = ab < 0.f;                  // v grows with u: the line leaves the row pair through its upper boundary
+    unsigned k = (unsigned)ua - 0x4B000000u * Wm;
+    int best_n = 0;
+    int n = ub - ua + 1;
+    float uf = (float)ua;
+    float vn = -(ab * uf + cb);
+    float r = __fadd_rd(vn, kMagic);
+    float w1n = vn - (r - kMagic);
+    unsigned idxn = __float_as_uint(r) * Wm + k;
+    float4 tn = __ldg(reinterpret_cast<const float4*>(tb + (size_t)idxn * 16));
+    unsigned sn = __ldg(reinterpret_cast<const uint8_t*>(sb + (size_t)idxn));
+#pragma unroll kScan2Unroll
+    while (n > 0) {
+        const float4 t = tn;
+        const float w1 = w1n, w0 = 1.0f - w1n;
+        const unsigned idx = idxn;
+        const int ncur = n;
+        // advance: as far as the skip byte and the row allow, never past column ub + 1 (the last valid address)
+        const float rem = up ? w0 : w1;
+        const int m1 = __float2int_rd(rem * inv - dinv1);
+        const int step = max(1, min(min((int)sn, m1), ncur));
+        n -= step;
+        k += (unsigned)step;
+        uf += (float)step;
+        vn = -(ab * uf + cb);
+        r = __fadd_rd(vn, kMagic);
+        w1n = vn - (r - kMagic);
+        idxn = __float_as_uint(r) * Wm + k;
+        tn = __ldg(reinterpret_cast<const float4*>(tb + (size_t)idxn * 16));
+        sn = __ldg(reinterpret_cast<const uint8_t*>(sb + (size_t)idxn));
+        const float2 w01 = make_float2(w0, w1);
+        const float2 gp = __fmul2_rn(make_float2(t.x, t.y), w01);
+        const float g2 = gp.x + gp.y;
+        if (g2 <= kLambdaG2) continue;  // condition 1
+        const float2 tp = __fmul2_rn(make_float2(t.z, t.w), w01);
+        float gs = tp.x + tp.y;
+        if (gs <= -360.f) gs += 360.f;
+        const float gth = fabsf(gs);
+        const float d3 = gth - ang_pi_rot;
+        if ((d3 >= 45.f || d3 <= kT2) && fabsf(d3) <= 315.f) continue;  // condition 3
+        const float d2 = gth - th_line;
+        const float ang = d2 < 0.f ? d2 + 360.f : d2;  // condition 2
+        if (fabsf(fabsf(ang - 180.f) - 90.f) <= 10.f) continue;
+        const uchar2 i2 = __ldg(reinterpret_cast<const uchar2*>(ib + (size_t)idx * 2));
+        const float2 ip = __fmul2_rn(make_float2((float)i2.x, (float)i2.y), w01);
+        const float2 res = __fadd2_rn(make_float2(pixel, gradc), make_float2(-(ip.x + ip.y), -g2));
+        const float2 sq = __fmul2_rn(res, res);
+        const float err = sq.x + div_by_theta2(sq.y);
+        if (err < best_err) { best_err = err; best_n = ncur; }
+    }
+    return best_n > 0 ? ub + 1 - best_n : -1;
+}
+
 // kMode 0: gates for any thresholds; 1: exact short gate forms for lambdaL = 80, lambdaTheta = 45;
 // 2: second-generation column loop (below), same decisions and values as 1 under its two preconditions:
 //    (i) regular planes and |rot| <= 360 (checked per keyframe: k_pack's plane_irregular flags / k_pass1_lane),
@@ -892,7 +1034,7 @@ __device__ __forceinline__ bool scan_pixel_lane(const DevArena& A, const DevPara
     const int x = (int)(packed & 0xffffu), y = (int)(packed >> 16);
     const size_t own = (size_t)kf * A.P + (size_t)y * P.W + x;
     float gradc, th_pi, pixel;
-    if (kMode == 2) {  // the planes the column loop reads anyway (the raw orientation only where the pair is wrapped)
+    if (kMode >= 2) {  // the planes the column loop reads anyway (the raw orientation only where the pair is wrapped)
         const float4 t1 = __ldg(&A.texw[own]);
         gradc = t1.x;
         th_pi = t1.z;
@@ -924,9 +1066,14 @@ __device__ __forceinline__ bool scan_pixel_lane(const DevArena& A, const DevPara
         // columns whose three rows v(u-1), v(u), v(u+1) are inside the image (:773-785), as one interval
         int ua, ub;
         valid_columns(ab, cb, Hm1, s.u_lo, s.u_hi, ua, ub);
-        if (kMode == 2) {
+        if (kMode >= 2) {
             if (ua <= ub) {
                 const float4* __restrict__ texw2 = A.texw + nb;
+                if (kMode == 3) {
+                    const int q = min(kSkipBins - 1, (int)(s.ang_pi_rot * (1.0f / kSkipBinDeg)));
+                    const uint8_t* __restrict__ skip2 = A.skip + ((size_t)g.slot * kSkipBins + q) * A.P;
+                    best_u = scan_columns3(texw2, ip2, skip2, W, ua, ub, ab, cb, s.th_line, s.ang_pi_rot, pixel, gradc, best_err);
+                } else
                 best_u = scan_columns2(texw2, ip2, W, ua, ub, ab, cb, s.th_line, s.ang_pi_rot, pixel, gradc, best_err);
                 if (best_u >= 0) {  // residuals of the best column, same expressions as in the loop
                     const float vb = -(ab * (float)best_u + cb);
@@ -988,7 +1135,7 @@ __device__ __forceinline__ bool scan_pixel_lane(const DevArena& A, const DevPara
         }
         if (best_err < 100000.0f) {
             // the gradient halves of tex and texw are the same: mode 2 stays on the plane its column loop has in cache
-            const Hypo h = refine_hypothesis(kMode == 2 ? A.texw + nb : tex2, ip2, g, K, P, best_u, ab, cb, best_pe, best_ge, xn, yn);
+            const Hypo h = refine_hypothesis(kMode >= 2 ? A.texw + nb : tex2, ip2, g, K, P, best_u, ab, cb, best_pe, best_ge, xn, yn);
             if (1.0f / h.depth > 0.0f) {  // :472
                 s_h[nh][tid] = make_float2(h.depth, h.sigma);
                 ++nh;
@@ -1062,8 +1209,12 @@ __device__ __forceinline__ bool item_regular(const DevArena& A, const DevItem& s
     return irr == 0;
 }
 
-template <bool kFastGates>
-__global__ void __launch_bounds__(kLaneBlock, SDM_LANE_MINB)
+#ifndef SDM_LANE3_MINB
+#define SDM_LANE3_MINB 10  // 48 registers: the skip walk carries three plane pointers; 12 blocks (40 registers) spill inside the loop (8.68 vs 8.04 ms)
+#endif
+// kGen = 3: keyframes that qualify for the second-generation loop run the third-generation one (skip planes built)
+template <bool kFastGates, int kGen = 2>
+__global__ void __launch_bounds__(kLaneBlock, kGen == 3 ? SDM_LANE3_MINB : SDM_LANE_MINB)
 k_pass1_lane(DevArena A, DevParams P, const DevItem* __restrict__ items, DevPlan plan, DevStats* stats)
 {
     __shared__ DevItem s_item;
@@ -1077,7 +1228,7 @@ k_pass1_lane(DevArena A, DevParams P, const DevItem* __restrict__ items, DevPlan
         const int ci = first + tid;
         bool fused = false;
         if (ci < A.cand_count[s_item.kf]) {
-            if (kFastGates && P.scan2 && item_regular(A, s_item)) fused = scan_pixel_lane<2>(A, P, s_item, s_h, ci, tid);
+            if (kFastGates && P.scan2 && item_regular(A, s_item)) fused = scan_pixel_lane<kGen>(A, P, s_item, s_h, ci, tid);
             else fused = scan_pixel_lane<kFastGates ? 1 : 0>(A, P, s_item, s_h, ci, tid);
         }
         n_fused += __popc(__ballot_sync(SDM_FULL, fused));
@@ -1677,6 +1828,65 @@ __global__ void __launch_bounds__(256) k_gather_sparse(DevArena A, DevParams P, 
 }
 
 // candidate counts of freshly packed slots into host-mapped pinned memory (no DMA engine involved)
+// ---------------------------------------------------------------------------------------------
+// Cross-GPU ordering of the inter-pass exchange without the host (sdm_exchange).  Every rank owns one XFlags block
+// in device memory that its peers map through CUDA IPC.  Owner: `done` = number of the last step whose pass-1 planes
+// are complete (written by a kernel that follows pass 1 on the compute stream).  A peer that pulls halo planes
+// spins on the owner's `done`, copies, then stores the step number into ack[its rank] of the owner; the owner's NEXT
+// pass 1 spins on the acks of every registered puller before it overwrites the planes (sdm_pass1).
+// Spins sleep between polls and give up after kXWaitNs (the context reports SDM_ERR_STATE at the next synchronise).
+// ---------------------------------------------------------------------------------------------
+constexpr int kXPeers = 16;
+struct XFlags {
+    unsigned done;
+    unsigned puller_mask;
+    unsigned ack[kXPeers];
+    unsigned err;  // != 0: a wait of THIS rank timed out
+    unsigned pad[13];
+};
+constexpr unsigned long long kXWaitNs = 20ULL * 1000 * 1000 * 1000;
+
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ bool spin_until_geq(const volatile unsigned* w, unsigned want)
+{
+    const unsigned long long t0 = global_ns();
+    // (int) difference: robust against wrap-around of the step counter
+    while ((int)(*w - want) < 0) {
+        __nanosleep(500);
+        if (global_ns() - t0 > kXWaitNs) return false;
+    }
+    __threadfence_system();
+    return true;
+}
+__global__ void k_xpublish(XFlags* mine, unsigned step)
+{
+    __threadfence_system();
+    *(volatile unsigned*)&mine->done = step;
+    __threadfence_system();
+}
+__global__ void k_xwait_done(const XFlags* peer, unsigned step, XFlags* mine)
+{
+    if (!spin_until_geq(&peer->done, step)) mine->err = 1;
+}
+__global__ void k_xack(XFlags* peer, int my_rank, unsigned step)
+{
+    __threadfence_system();
+    *(volatile unsigned*)&peer->ack[my_rank] = step;
+    __threadfence_system();
+}
+__global__ void k_xwait_acks(XFlags* mine, unsigned step)
+{
+    const int r = threadIdx.x;
+    if (r < kXPeers && ((*(volatile unsigned*)&mine->puller_mask >> r) & 1u))
+        if (!spin_until_geq(&mine->ack[r], step)) mine->err = 2;
+}
+__global__ void k_xregister(XFlags* peer, int my_rank) { atomicOr_system(&peer->puller_mask, 1u << my_rank); }
+
 constexpr int kSlotList = 24;
 struct SlotList {
     int s[kSlotList];

@@ -59,6 +59,15 @@ class DownloadDesc(C.Structure):
                 ("points", C.c_void_p), ("points_step", C.c_size_t)]
 
 
+class Loop(C.Structure):
+    _fields_ = [("n_upload", C.c_int32), ("upload", C.POINTER(UploadDesc)), ("n_pass1", C.c_int32), ("pass1", C.POINTER(Item)),
+                ("down1", C.POINTER(DownloadDesc)), ("n_pass2", C.c_int32), ("pass2", C.POINTER(Item)),
+                ("down2", C.POINTER(DownloadDesc)), ("chunk", C.c_int32), ("exchange", C.c_int32)]
+
+
+SDM_PEER_HANDLE_BYTES = 192
+
+
 class Timing(C.Structure):
     _fields_ = [("pass1_scan_ms", C.c_float), ("pass1_intra_ms", C.c_float), ("pass2_ms", C.c_float)]
 
@@ -73,7 +82,8 @@ EXPORTS = [
     "sdm_get_stats", "sdm_scan_generation", "sdm_host_alloc", "sdm_host_free", "sdm_upload_keyframe", "sdm_set_pose",
     "sdm_set_intrinsics", "sdm_candidate_count", "sdm_pass1", "sdm_pass2", "sdm_update_points", "sdm_download", "sdm_download_async", "sdm_upload_keyframes", "sdm_download_keyframes", "sdm_scatter_keyframes", "sdm_export_points", "sdm_download_planes",
     "sdm_upload_depth", "sdm_depth_plane_ptr", "sdm_export_arena", "sdm_import_peer_arena", "sdm_pull_halo",
-    "sdm_mark_pass1_done", "sdm_pair_geometry", "sdm_stereo_search_constraints", "sdm_search_range", "sdm_inter_chi_test",
+    "sdm_mark_pass1_done", "sdm_export_peer_handle", "sdm_import_peer", "sdm_set_halo", "sdm_exchange", "sdm_run_loop",
+    "sdm_pair_geometry", "sdm_stereo_search_constraints", "sdm_search_range", "sdm_inter_chi_test",
     "sdm_epipolar_search", "sdm_epipolar_search_plane", "sdm_fuse", "sdm_intra_check", "sdm_intra_grow",
     "sdm_inter_check", "sdm_last_pass_ms", "sdm_launch_count", "sdm_last_timing", "sdm_mark", "sdm_elapsed_ms",
 ]
@@ -124,6 +134,11 @@ def load() -> C.CDLL:
     lib.sdm_import_peer_arena.argtypes = [vp, C.c_int, vp]
     lib.sdm_pull_halo.argtypes = [vp, C.c_int, ip, ip, ip]
     lib.sdm_mark_pass1_done.argtypes = [vp, C.c_int]
+    lib.sdm_export_peer_handle.argtypes = [vp, C.c_int, vp]
+    lib.sdm_import_peer.argtypes = [vp, C.c_int, vp]
+    lib.sdm_set_halo.argtypes = [vp, C.c_int, ip, ip, ip]
+    lib.sdm_exchange.argtypes = [vp]
+    lib.sdm_run_loop.argtypes = [vp, C.POINTER(Loop)]
     lib.sdm_pair_geometry.argtypes = [fp, fp, fp, fp, C.POINTER(PairGeometry)]
     lib.sdm_stereo_search_constraints.argtypes = [fp, C.c_int, fp, fp]
     lib.sdm_search_range.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_float, C.c_float, fp, fp]
@@ -445,6 +460,38 @@ class Context:
 
     def mark_pass1_done(self, slot):
         self._chk(self.lib.sdm_mark_pass1_done(self.h, slot))
+
+    # exchange ordered on the devices (no host barrier per step)
+    def export_peer_handle(self, my_rank: int) -> bytes:
+        buf = C.create_string_buffer(SDM_PEER_HANDLE_BYTES)
+        self._chk(self.lib.sdm_export_peer_handle(self.h, my_rank, buf))
+        return bytes(buf.raw)
+
+    def import_peer(self, rank: int, handle: bytes):
+        self._chk(self.lib.sdm_import_peer(self.h, rank, C.create_string_buffer(handle, SDM_PEER_HANDLE_BYTES)))
+
+    def set_halo(self, local_slot, peer_rank, peer_slot):
+        a, b, c = (np.ascontiguousarray(v, np.int32) for v in (local_slot, peer_rank, peer_slot))
+        ip = C.POINTER(C.c_int32)
+        self._chk(self.lib.sdm_set_halo(self.h, a.size, a.ctypes.data_as(ip), b.ctypes.data_as(ip), c.ctypes.data_as(ip)))
+
+    def exchange(self):
+        self._chk(self.lib.sdm_exchange(self.h))
+
+    def run_loop(self, upload=None, pass1=None, down1=None, pass2=None, down2=None, chunk=0, exchange=False):
+        """sdm_run_loop: ctypes arrays (UploadDesc / Item / DownloadDesc) or None; enqueue only"""
+        L = Loop()
+        L.n_upload = len(upload) if upload is not None else 0
+        L.upload = upload if upload is not None else None
+        L.n_pass1 = len(pass1) if pass1 is not None else 0
+        L.pass1 = pass1 if pass1 is not None else None
+        L.down1 = down1 if down1 is not None else None
+        L.n_pass2 = len(pass2) if pass2 is not None else 0
+        L.pass2 = pass2 if pass2 is not None else None
+        L.down2 = down2 if down2 is not None else None
+        L.chunk, L.exchange = int(chunk), int(bool(exchange))
+        self._keep_loop = (upload, pass1, down1, pass2, down2)
+        self._chk(self.lib.sdm_run_loop(self.h, C.byref(L)))
 
 
 def pair_geometry(K1, Tcw1, K2, Tcw2) -> PairGeometry:

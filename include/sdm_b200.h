@@ -97,10 +97,11 @@ const char* sdm_last_error(void);
 const char* sdm_version(void);
 int sdm_synchronize(sdm_ctx* ctx);
 int sdm_get_stats(sdm_ctx* ctx, sdm_stats* out);
-/* which column loop sdm_pass1 runs for keyframes with regular planes: 2 = second generation (reference thresholds
- * lambdaL = 80 / lambdaTheta = 45 and the reciprocal form of x / theta verified for this theta at sdm_create),
- * 1 = first generation (any thresholds; also used per keyframe when an orientation plane holds values outside
- * [0, 360] or |rot| > 360; env SDM_SCAN=lane1 forces it).  Results are bit-identical either way. */
+/* which column loop sdm_pass1 runs for keyframes with regular planes: 3 = third generation (the second generation's
+ * arithmetic, but a lane jumps over columns that its skip-distance planes rule out), 2 = second generation (reference
+ * thresholds lambdaL = 80 / lambdaTheta = 45 and the reciprocal form of x / theta verified for this theta at
+ * sdm_create), 1 = first generation (any thresholds; also used per keyframe when an orientation plane holds values
+ * outside [0, 360] or |rot| > 360).  env SDM_SCAN=lane1 | lane2 | lane3 forces one.  Results are bit-identical. */
 int sdm_scan_generation(sdm_ctx* ctx);
 
 /* pinned host memory for asynchronous uploads/downloads (optional; any host pointer is accepted) */
@@ -215,6 +216,59 @@ int sdm_pull_halo(sdm_ctx* ctx, int n, const int32_t* local_slot, const int32_t*
                   const int32_t* peer_slot);
 /* mark a slot's pass-1 planes as valid (after an external NCCL receive into sdm_depth_plane_ptr) */
 int sdm_mark_pass1_done(sdm_ctx* ctx, int kf);
+/* PROTOCOL of the three calls above (sdm_export_arena / sdm_import_peer_arena / sdm_pull_halo): they carry no ordering
+ * between ranks.  The caller must (1) sdm_synchronize() + a cross-rank barrier after its sdm_pass1 and before anybody's
+ * sdm_pull_halo, and (2) sdm_synchronize() + a barrier after the pulls and before the next sdm_pass1 / upload on an
+ * owning rank; peer_slot is not range-checked (the peer's slot count is unknown).  sdm_exchange below needs neither. */
+
+/* ---- multi-GPU exchange ordered on the devices (SURVEY.md 8b `sdm_exchange`, 8e-ii) ------------------------------
+ * The only cross-keyframe dependency of the path is "pass 1 of all neighbours before pass 2 of a keyframe"
+ * (ProbabilityMapping.cc:1202-1249).  With keyframes sharded over GPUs, each rank pulls the (rho, sigma) planes of its
+ * halo keyframes from their owners between the passes.  One-time set-up per rank:
+ *     sdm_export_peer_handle(ctx, my_rank, &h)   -> all-gather the handles by any transport
+ *     sdm_import_peer(ctx, r, &handle_of_r)      for every rank r this rank pulls from
+ *     sdm_set_halo(ctx, n, local_slot, peer_rank, peer_slot)   (peer_slot is validated against the peer's slot count)
+ *     [one host barrier: every import done before the first step]
+ * Per step, on every rank, with NO host synchronisation or barrier:
+ *     sdm_pass1(...); sdm_exchange(ctx); sdm_pass2(...);
+ * sdm_exchange publishes "my pass-1 planes of step s are complete" with a kernel behind pass 1, and on a separate
+ * stream waits (device-side spin on the owner's flag over NVLink) for each owner, copies the halo planes peer-to-peer
+ * and acknowledges to the owner.  sdm_pass2 launches the keyframes that do not read a halo plane at once and the
+ * others behind the pull (the pull overlaps pass 2 of the interior keyframes); the next sdm_pass1 waits on the device
+ * for the acknowledgements of every rank that pulls from this one before it overwrites the planes.  All ranks must call
+ * sdm_exchange the same number of times.  A wait that exceeds 20 s flags an error that the next sdm_synchronize
+ * returns as SDM_ERR_STATE.  With an empty halo plan (single GPU) sdm_exchange is a no-op. */
+#define SDM_PEER_HANDLE_BYTES 192
+typedef struct {
+    unsigned char bytes[SDM_PEER_HANDLE_BYTES]; /* IPC handles of the (rho,sigma) arena and the flag block, slot count, rank */
+} sdm_peer_handle;
+int sdm_export_peer_handle(sdm_ctx* ctx, int my_rank, sdm_peer_handle* out);
+int sdm_import_peer(sdm_ctx* ctx, int peer_rank, const sdm_peer_handle* handle);
+int sdm_set_halo(sdm_ctx* ctx, int n, const int32_t* local_slot, const int32_t* peer_rank, const int32_t* peer_slot);
+int sdm_exchange(sdm_ctx* ctx);
+
+/* ---- one whole SemiDenseLoop as a pipeline (ProbabilityMapping.cc:348-597) --------------------------------------
+ * Issues uploads, pass 1, the downloads of depth_map_/depth_sigma_, [the exchange], pass 2 and the downloads of
+ * depth_map_checked_/SemiDensePointSets_ in chunks of `chunk` keyframes, in the order that keeps the copy engines and
+ * the SMs busy at the same time: the planes of chunk k+1 go up while pass 1 of chunk k runs, a chunk's pass-1 planes
+ * leave as soon as its pass 1 is queued, and a keyframe's pass 2 is queued as soon as pass 1 of all its neighbours is.
+ * pass1[] and pass2[] are the work orders of the two passes in processing order (they differ when the gating of
+ * :365-384 and :523-542 differs); down1[i] / down2[i] receive the planes of pass1[i].kf / pass2[i].kf (either array
+ * may be NULL, as may any plane pointer).  upload[] lists the keyframes whose planes are not resident yet, in the
+ * order of first use.  Asynchronous like its parts: host buffers are valid after sdm_synchronize. */
+typedef struct {
+    int32_t n_upload;
+    const sdm_upload_desc* upload;
+    int32_t n_pass1;
+    const sdm_item* pass1;
+    const sdm_download_desc* down1;
+    int32_t n_pass2;
+    const sdm_item* pass2;
+    const sdm_download_desc* down2;
+    int32_t chunk;    /* keyframes per pipeline chunk; <= 0: 4 (measured optimum on B200 + PCIe 5) */
+    int32_t exchange; /* != 0: sdm_exchange between the passes; pass-2 work orders that read halo planes wait for it */
+} sdm_loop;
+int sdm_run_loop(sdm_ctx* ctx, const sdm_loop* loop);
 
 /* ---- per-method entry points (each named class method stays individually callable) ---------- */
 /* replaces: ComputeFundamental (:1694-1709) and the R21/t21 of :1136-1137; host arithmetic with

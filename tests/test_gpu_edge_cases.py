@@ -103,18 +103,20 @@ def test_slot_reuse_and_partial_batches():
 
 
 def test_scan_generations_agree(monkeypatch):
-    """the second-generation column loop (default for the reference's constants) and the first-generation one
-    (SDM_SCAN=lane1, or any other threshold set) give the oracle's bits"""
+    """the three generations of the column loop (SDM_SCAN=lane1 | lane2 | lane3; the first is also what any other
+    threshold set runs) give the oracle's bits"""
     sc = synth.make_scene(10, 320, 240, 6, seed=21, contrast=0.9)
     osc = run_oracle(sc)
     zero = {"depth": 0, "sigma": 0, "checked": 0, "points": 0}
+    monkeypatch.delenv("SDM_SCAN", raising=False)
     with api.Context(width=320, height=240, max_keyframes=sc.n) as ctx:
-        assert ctx.scan_generation() == 2          # k_verify_div passed for THETA = 0.23f
+        assert ctx.scan_generation() in (2, 3)     # k_verify_div passed for THETA = 0.23f
         assert _bit_equal(run_device(sc, ctx=ctx), osc) == zero
-    monkeypatch.setenv("SDM_SCAN", "lane1")
-    with api.Context(width=320, height=240, max_keyframes=sc.n) as ctx:
-        assert ctx.scan_generation() == 1
-        assert _bit_equal(run_device(sc, ctx=ctx), osc) == zero
+    for env, gen in (("lane1", 1), ("lane2", 2), ("lane3", 3)):
+        monkeypatch.setenv("SDM_SCAN", env)
+        with api.Context(width=320, height=240, max_keyframes=sc.n) as ctx:
+            assert ctx.scan_generation() == gen
+            assert _bit_equal(run_device(sc, ctx=ctx), osc) == zero
     monkeypatch.delenv("SDM_SCAN")
     with api.Context(width=320, height=240, max_keyframes=sc.n, lambdaG=9) as ctx:
         assert ctx.scan_generation() == 1          # not the reference's constants
@@ -166,7 +168,7 @@ def test_wrap_encoded_orientation_pairs():
     assert (d >= 180).mean() > 0.2 and (d == 180).any()
     zero = {"depth": 0, "sigma": 0, "checked": 0, "points": 0}
     with api.Context(width=W, height=H, max_keyframes=sc.n) as ctx:
-        assert ctx.scan_generation() == 2
+        assert ctx.scan_generation() >= 2
         osc, dev = run_oracle(sc), run_device(sc, ctx=ctx)
     assert _bit_equal(dev, osc) == zero
     assert (osc.depth > 0).sum() > 300

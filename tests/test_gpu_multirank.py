@@ -1,6 +1,11 @@
-"""Two ranks (two processes, gloo rendezvous) sharing cuda:0: keyframe shards + CUDA-IPC halo pulls
-(sdm_export_arena / sdm_import_peer_arena / sdm_pull_halo) must reproduce the single-context result,
-i.e. the oracle over the whole trajectory, on every owned keyframe."""
+"""Two ranks (two processes, gloo rendezvous): keyframe shards + CUDA-IPC halo pulls must reproduce the single-context
+result, i.e. the oracle over the whole trajectory, on every owned keyframe.  The ranks use two GPUs when the box has
+them (`gpurun --gpus 2`: the planes then cross NVLink) and share cuda:0 otherwise.  Two protocols:
+  * host-ordered: sdm_export_arena / sdm_import_peer_arena / sdm_pull_halo between synchronize + barrier pairs;
+  * device-ordered: sdm_export_peer_handle / sdm_import_peer / sdm_set_halo once, then sdm_pass1 / sdm_exchange /
+    sdm_pass2 per step with no host synchronisation or barrier in between (flags in peer memory), run for several
+    steps so that the acknowledgement path (the next pass 1 waits for the pullers) is exercised, and once more through
+    sdm_run_loop(exchange = 1)."""
 import os
 import socket
 import sys
@@ -17,7 +22,7 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, per_rank, q):
+def _worker(rank, world, port, per_rank, q, mode="host"):
     try:
         for p in (os.path.join(ROOT, "eao-slam_b200", "python"), os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
             sys.path.insert(0, p)
@@ -32,19 +37,39 @@ def _worker(rank, world, port, per_rank, q):
         plan = shard.make_plan(nb_global, per_rank, rank, world)
         nb_local = np.where(plan.nbr_local >= 0, plan.nbr_local, 0).astype(np.int32)
         sc = synth.make_scene(plan.n_local, W, H, N, seed=41, first=plan.lo, nbr_idx=nb_local)
-        ctx = api.Context(width=W, height=H, max_keyframes=plan.n_local, device=0)
-        ctx.upload_scene(sc)
-        handles = [None] * world
-        dist.all_gather_object(handles, ctx.export_arena())
-        for r in set(int(x) for x in plan.halo_rank):
-            ctx.import_peer_arena(r, handles[r])
+        import torch
+        ndev = torch.cuda.device_count()
+        ctx = api.Context(width=W, height=H, max_keyframes=plan.n_local, device=rank % max(1, ndev))
         owned = list(plan.owned_local)
         items = api.make_items(owned, sc.nbr_idx, sc.rot, sc.min_depth, sc.max_depth)
-        ctx.pass1(items)
-        ctx.synchronize(); dist.barrier()            # every rank's pass 1 is complete
-        ctx.pull_halo(plan.halo_local, plan.halo_rank, plan.halo_peer_slot)
-        ctx.pass2(items)
-        ctx.synchronize(); dist.barrier()            # nobody frees / overwrites planes a peer still reads
+        handles = [None] * world
+        if mode == "host":
+            ctx.upload_scene(sc)
+            dist.all_gather_object(handles, ctx.export_arena())
+            for r in set(int(x) for x in plan.halo_rank):
+                ctx.import_peer_arena(r, handles[r])
+            ctx.pass1(items)
+            ctx.synchronize(); dist.barrier()            # every rank's pass 1 is complete
+            ctx.pull_halo(plan.halo_local, plan.halo_rank, plan.halo_peer_slot)
+            ctx.pass2(items)
+            ctx.synchronize(); dist.barrier()            # nobody frees / overwrites planes a peer still reads
+        else:
+            dist.all_gather_object(handles, ctx.export_peer_handle(rank))
+            for r in set(int(x) for x in plan.halo_rank):
+                ctx.import_peer(r, handles[r])
+            ctx.set_halo(plan.halo_local, plan.halo_rank, plan.halo_peer_slot)
+            dist.barrier()                               # every import (puller registration) is done: the only barrier
+            if mode == "device":
+                for step in range(3):                    # re-upload + both passes: no host sync, no barrier per step
+                    ctx.upload_scene(sc)
+                    ctx.pass1(items)
+                    ctx.exchange()
+                    ctx.pass2(items)
+            else:                                        # the same through the library's pipelined loop
+                for step in range(2):
+                    ctx.run_loop(upload=ctx.upload_descs(sc, range(plan.n_local)), pass1=items, pass2=items, chunk=3,
+                                 exchange=True)
+            ctx.synchronize()
         dev = {k: np.zeros((len(owned), H, W) + ((3,) if k == "points" else ()), np.float32)
                for k in ("depth", "sigma", "checked", "points")}
         for j, s in enumerate(owned):
@@ -73,12 +98,13 @@ def _worker(rank, world, port, per_rank, q):
         q.put((rank, "error", traceback.format_exc(), 0))
 
 
-def test_two_ranks_one_gpu_halo_exchange():
+@pytest.mark.parametrize("mode", ["host", "device", "run_loop"])
+def test_two_ranks_halo_exchange(mode):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, 10, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, 10, q, mode)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=600) for _ in procs]
