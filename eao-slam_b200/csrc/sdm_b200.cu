@@ -237,6 +237,8 @@ struct sdm_ctx {
     cudaStream_t s_compute = nullptr, s_copy = nullptr, s_down = nullptr;
     EventRing r_copy, r_compute, r_down;
     cudaEvent_t ev_p1[2] = {nullptr, nullptr}, ev_p2[2] = {nullptr, nullptr}, ev_p1_scan = nullptr;
+    std::vector<cudaEvent_t> ev_pack;  // start / stop pairs around the pack kernels of the last sdm_upload_keyframes
+    int n_pack_ev = 0;
     cudaEvent_t marks[SDM_N_MARKS] = {nullptr};
     bool mark_set[SDM_N_MARKS] = {false};
     bool p1_timed = false, p2_timed = false;
@@ -588,6 +590,7 @@ void sdm_destroy(sdm_ctx* c)
         if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : c->marks)
         if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : c->ev_pack) cudaEventDestroy(e);
     c->r_copy.destroy(); c->r_compute.destroy(); c->r_down.destroy();
     for (cudaStream_t s : {c->s_compute, c->s_copy, c->s_down})
         if (s) cudaStreamDestroy(s);
@@ -820,6 +823,7 @@ int sdm_upload_keyframes(sdm_ctx* c, int n, const sdm_upload_desc* d)
             return fail(SDM_ERR_ARG, "row step smaller than a row");
     }
     CU(cudaSetDevice(c->cfg.device));
+    c->n_pack_ev = 0;
     for (int i0 = 0; i0 < n; i0 += kUpStages / 2) {
         const int m = std::min(kUpStages / 2, n - i0);
         const int first_stage = c->up_next;
@@ -846,6 +850,12 @@ int sdm_upload_keyframes(sdm_ctx* c, int n, const sdm_upload_desc* d)
         RC(c->r_copy.wait(c->s_compute, h2d));
         RC(c->r_down.wait(c->s_compute, need_down));
         trace_begin(c, c->s_compute, "pack", m);
+        while ((int)c->ev_pack.size() < c->n_pack_ev + 2) {
+            cudaEvent_t e;
+            CU(cudaEventCreate(&e));
+            c->ev_pack.push_back(e);
+        }
+        CU(cudaEventRecord(c->ev_pack[c->n_pack_ev], c->s_compute));
         for (int i = 0; i < m; ++i) {
             const sdm_upload_desc& u = d[i0 + i];
             UpStage& st = c->up[(first_stage + i) % kUpStages];
@@ -866,6 +876,8 @@ int sdm_upload_keyframes(sdm_ctx* c, int n, const sdm_upload_desc* d)
         for (int i = 0; i < m; ++i) sl.s[i] = d[i0 + i].kf;
         sdm::k_publish_counts<<<1, 32, 0, c->s_compute>>>(c->A.cand_count, sl, m, c->h_cand);
         CU(cudaGetLastError());
+        CU(cudaEventRecord(c->ev_pack[c->n_pack_ev + 1], c->s_compute));
+        c->n_pack_ev += 2;
         trace_end(c, c->s_compute);
         c->launches += m + 1;
         uint64_t id = 0;
@@ -970,13 +982,15 @@ int sdm_pass1(sdm_ctx* c, int n, const sdm_item* items)
     else {
         int max_n = 1;
         for (int i = 0; i < n; ++i) max_n = std::max(max_n, (int)items[i].n_nbr);
-        const size_t smem = (size_t)max_n * sdm::kLaneBlock * sizeof(float2);
+        // per warp: the work order with max_n neighbour records (16-byte aligned); then the hypotheses [max_n][block]
+        const int item_bytes = (int)((offsetof(sdm::DevItem, pair) + (size_t)max_n * sizeof(sdm::DevPair) + 15) & ~(size_t)15);
+        const size_t smem = (size_t)(sdm::kLaneBlock / 32) * item_bytes + (size_t)max_n * sdm::kLaneBlock * sizeof(float2);
         int occ = 0;  // persistent grid: fill every SM to this launch's occupancy
         // the exact short forms of the two direction gates exist for the reference's thresholds only
         const bool fast = (c->cfg.lambdaL == 80 && c->cfg.lambdaTheta == 45);
         auto kern = !fast ? sdm::k_pass1_lane<false, 2> : (c->P.scan2 == 3 ? sdm::k_pass1_lane<true, 3> : sdm::k_pass1_lane<true, 2>);
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, sdm::kLaneBlock, smem));
-        kern<<<std::max(1, occ) * c->n_sm, sdm::kLaneBlock, smem, c->s_compute>>>(c->A, c->P, c->d_items, plan, c->d_stats);
+        kern<<<std::max(1, occ) * c->n_sm, sdm::kLaneBlock, smem, c->s_compute>>>(c->A, c->P, c->d_items, plan, c->d_stats, item_bytes);
     }
     CU(cudaGetLastError());
     c->launches += 2;
@@ -1248,6 +1262,24 @@ int sdm_upload_depth(sdm_ctx* c, int kf, const float* depth, size_t depth_step, 
     k.pass1_done = true;
     k.rs_dense = true;
     k.split_stale = true;
+    return SDM_OK;
+}
+
+int sdm_upload_checked(sdm_ctx* c, int kf, const float* checked, size_t checked_step)
+{
+    if (!c || !checked) return fail(SDM_ERR_ARG, "null argument");
+    if (!slot_ok(c, kf)) return fail(SDM_ERR_ARG, "keyframe slot %d out of range", kf);
+    const int W = c->cfg.width, H = c->cfg.height;
+    const size_t P = c->npix, row = (size_t)W * 4;
+    if (checked_step < row) return fail(SDM_ERR_ARG, "row step smaller than a row");
+    CU(cudaSetDevice(c->cfg.device));
+    KfState& k = c->kf[kf];
+    cudaStream_t s = c->s_compute;
+    RC(c->r_down.wait(s, k.down_cp_id));
+    RC(copy2d(c->A.chk + (size_t)kf * P, row, checked, checked_step, row, H, cudaMemcpyHostToDevice, s));
+    RC(c->r_compute.record(s, &k.comp_id));
+    CU(cudaStreamSynchronize(s));
+    k.rs_dense = true;  // the plane is not confined to the slot's candidate pixels: pass 2 / the point set visit every pixel
     return SDM_OK;
 }
 
@@ -1832,6 +1864,20 @@ int sdm_last_timing(sdm_ctx* c, sdm_timing* out)
     if (c->p2_timed) {
         CU(cudaEventSynchronize(c->ev_p2[1]));
         CU(cudaEventElapsedTime(&out->pass2_ms, c->ev_p2[0], c->ev_p2[1]));
+    }
+    return SDM_OK;
+}
+
+int sdm_last_pack_ms(sdm_ctx* c, float* pack_ms)
+{
+    if (!c || !pack_ms) return fail(SDM_ERR_ARG, "null argument");
+    CU(cudaSetDevice(c->cfg.device));
+    *pack_ms = 0.f;
+    for (int i = 0; i + 1 < c->n_pack_ev; i += 2) {
+        float ms = 0.f;
+        CU(cudaEventSynchronize(c->ev_pack[i + 1]));
+        CU(cudaEventElapsedTime(&ms, c->ev_pack[i], c->ev_pack[i + 1]));
+        *pack_ms += ms;
     }
     return SDM_OK;
 }

@@ -977,11 +977,18 @@ __device__ __forceinline__ int scan_columns3(const float4* __restrict__ texw2, c
     unsigned idxn = __float_as_uint(r) * Wm + k;
     float4 tn = __ldg(reinterpret_cast<const float4*>(tb + (size_t)idxn * 16));
     unsigned sn = __ldg(reinterpret_cast<const uint8_t*>(sb + (size_t)idxn));
+#ifdef SDM_SCAN3_PREFETCH_IM
+    uchar2 in = __ldg(reinterpret_cast<const uchar2*>(ib + (size_t)idxn * 2));
+#endif
 #pragma unroll kScan2Unroll
     while (n > 0) {
         const float4 t = tn;
         const float w1 = w1n, w0 = 1.0f - w1n;
+#ifdef SDM_SCAN3_PREFETCH_IM
+        const uchar2 i2 = in;
+#else
         const unsigned idx = idxn;
+#endif
         const int ncur = n;
         // advance: as far as the skip byte and the row allow, never past column ub + 1 (the last valid address)
         const float rem = up ? w0 : w1;
@@ -996,6 +1003,9 @@ __device__ __forceinline__ int scan_columns3(const float4* __restrict__ texw2, c
         idxn = __float_as_uint(r) * Wm + k;
         tn = __ldg(reinterpret_cast<const float4*>(tb + (size_t)idxn * 16));
         sn = __ldg(reinterpret_cast<const uint8_t*>(sb + (size_t)idxn));
+#ifdef SDM_SCAN3_PREFETCH_IM
+        in = __ldg(reinterpret_cast<const uchar2*>(ib + (size_t)idxn * 2));
+#endif
         const float2 w01 = make_float2(w0, w1);
         const float2 gp = __fmul2_rn(make_float2(t.x, t.y), w01);
         const float g2 = gp.x + gp.y;
@@ -1009,7 +1019,9 @@ __device__ __forceinline__ int scan_columns3(const float4* __restrict__ texw2, c
         const float d2 = gth - th_line;
         const float ang = d2 < 0.f ? d2 + 360.f : d2;  // condition 2
         if (fabsf(fabsf(ang - 180.f) - 90.f) <= 10.f) continue;
+#ifndef SDM_SCAN3_PREFETCH_IM
         const uchar2 i2 = __ldg(reinterpret_cast<const uchar2*>(ib + (size_t)idx * 2));
+#endif
         const float2 ip = __fmul2_rn(make_float2((float)i2.x, (float)i2.y), w01);
         const float2 res = __fadd2_rn(make_float2(pixel, gradc), make_float2(-(ip.x + ip.y), -g2));
         const float2 sq = __fmul2_rn(res, res);
@@ -1213,27 +1225,62 @@ __device__ __forceinline__ bool item_regular(const DevArena& A, const DevItem& s
 #define SDM_LANE3_MINB 10  // 48 registers: the skip walk carries three plane pointers; 12 blocks (40 registers) spill inside the loop (8.68 vs 8.04 ms)
 #endif
 // kGen = 3: keyframes that qualify for the second-generation loop run the third-generation one (skip planes built)
+// Work distribution of the scan kernel: every WARP pulls pieces of 32 consecutive candidates (a quarter of a plan
+// chunk) from the plan's counter and keeps its own copy of the keyframe's work order in shared memory, so the kernel
+// has no block-wide barrier: with one chunk per block and a __syncthreads per chunk, 8 % of the resident warp time
+// was spent waiting for the block's slowest warp (ncu: stall_barrier 1.05 of 13.4 warp-cycles per issue).
+constexpr int kPiecesPerChunk = kChunk / 32;
+__device__ __forceinline__ int item_words(int n_nbr) { return (int)(offsetof(DevItem, pair) / 4) + n_nbr * (int)(sizeof(DevPair) / 4); }
+
+__device__ __forceinline__ bool next_piece(const DevPlan& plan, const DevItem* __restrict__ items, DevItem& w_item, int lane,
+                                           int& cur_entry, int& first)
+{
+    int id = 0;
+    if (lane == 0) id = atomicAdd(plan.counter, 1);
+    id = __shfl_sync(SDM_FULL, id, 0);
+    const int chunk = id / kPiecesPerChunk;
+    if (chunk >= plan.chunk_off[plan.n_items]) return false;
+    int lo = 0, hi = plan.n_items;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (plan.chunk_off[mid] <= chunk) lo = mid; else hi = mid;
+    }
+    if (lo != cur_entry) {
+        __syncwarp();  // every lane is done with the previous work order
+        const DevItem* src_item = &items[plan.order ? plan.order[lo] : lo];
+        const int* src = reinterpret_cast<const int*>(src_item);
+        int* dst = reinterpret_cast<int*>(&w_item);
+        const int words = item_words(src_item->n_nbr);
+        for (int i = lane; i < words; i += 32) dst[i] = src[i];
+        cur_entry = lo;
+        __syncwarp();
+    }
+    first = (chunk - plan.chunk_off[lo]) * kChunk + (id % kPiecesPerChunk) * 32;
+    return true;
+}
+
 template <bool kFastGates, int kGen = 2>
 __global__ void __launch_bounds__(kLaneBlock, kGen == 3 ? SDM_LANE3_MINB : SDM_LANE_MINB)
-k_pass1_lane(DevArena A, DevParams P, const DevItem* __restrict__ items, DevPlan plan, DevStats* stats)
+k_pass1_lane(DevArena A, DevParams P, const DevItem* __restrict__ items, DevPlan plan, DevStats* stats, int item_bytes)
 {
-    __shared__ DevItem s_item;
-    __shared__ int s_chunk;
-    extern __shared__ float2 s_h_dyn[];  // [max n_nbr of the batch][kLaneBlock]: sized at launch, leaves the rest to L1
-    float2 (*s_h)[kLaneBlock] = reinterpret_cast<float2 (*)[kLaneBlock]>(s_h_dyn);
-    const int tid = threadIdx.x;
+    // dynamic shared memory, sized at launch for the largest neighbour count of the batch (the rest stays L1):
+    // [kLaneBlock / 32 warps][item_bytes] work orders, then [max n_nbr][kLaneBlock] hypotheses
+    extern __shared__ __align__(16) unsigned char s_dyn[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    DevItem& w_item = *reinterpret_cast<DevItem*>(s_dyn + (size_t)warp * item_bytes);
+    float2 (*s_h)[kLaneBlock] = reinterpret_cast<float2 (*)[kLaneBlock]>(s_dyn + (size_t)(kLaneBlock / 32) * item_bytes);
     int cur_entry = -1, first = 0;
     unsigned n_fused = 0;
-    while (next_chunk(plan, items, s_item, s_chunk, cur_entry, first)) {
-        const int ci = first + tid;
+    while (next_piece(plan, items, w_item, lane, cur_entry, first)) {
+        const int ci = first + lane;
         bool fused = false;
-        if (ci < A.cand_count[s_item.kf]) {
-            if (kFastGates && P.scan2 && item_regular(A, s_item)) fused = scan_pixel_lane<kGen>(A, P, s_item, s_h, ci, tid);
-            else fused = scan_pixel_lane<kFastGates ? 1 : 0>(A, P, s_item, s_h, ci, tid);
+        if (ci < A.cand_count[w_item.kf]) {
+            if (kFastGates && P.scan2 && item_regular(A, w_item)) fused = scan_pixel_lane<kGen>(A, P, w_item, s_h, ci, tid);
+            else fused = scan_pixel_lane<kFastGates ? 1 : 0>(A, P, w_item, s_h, ci, tid);
         }
         n_fused += __popc(__ballot_sync(SDM_FULL, fused));
     }
-    if (stats && (tid & 31) == 0 && n_fused) atomicAdd(&stats->fused, (unsigned long long)n_fused);
+    if (stats && lane == 0 && n_fused) atomicAdd(&stats->fused, (unsigned long long)n_fused);
 }
 
 // per-pair raw hypotheses for every candidate pixel of kf1 (granularity of one EpipolarSearch call)

@@ -11,20 +11,30 @@
 //
 // Two build modes:
 //   * inside EAO-SLAM: define SDM_HOST_WITH_ORBSLAM2 before including; KeyFrame / Map / cv::Mat are
-//     the reference's own types (INTEGRATION.md shows the three-line change to System.cc);
+//     the reference's own types (INTEGRATION.md shows the three-line change to System.cc); the class then also owns
+//     the Modeler and the LineDetector like the reference's (:195-202) and drives them where the reference does
+//     (edge map + line segments per keyframe inside pass 1, :394-397; the consumers after the loop, :256-297).
+//     tests/test_shim_orbslam2_mode.py compiles this mode against the stand-in headers of oracle/refshim/;
 //   * stand-alone (this repository, no OpenCV available): host_types.h supplies minimal stand-ins
 //     with the same member names, which is what tests/cpp/test_shim.cpp compiles against.
 #pragma once
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstring>
+#include <ctime>
+#include <fstream>
+#include <functional>
 #include <iostream>
 #include <map>
 #include <mutex>
+#include <string>
 #include <thread>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
+#include <sys/stat.h>
 
 #include "../../include/sdm_b200.h"
 
@@ -33,6 +43,8 @@
 #include "KeyFrame.h"
 #include "Map.h"
 #include "MapPoint.h"
+#include "Modeler.h"        // the consumers the reference's class owns / drives after the loop (:195-202, :256-297):
+#include "LineDetector.h"   // unchanged reference code, called at the same places
 namespace sdm_host {
 typedef cv::Mat Mat;
 typedef ORB_SLAM2::KeyFrame KeyFrame;
@@ -71,6 +83,7 @@ std::vector<float> RotInPlane(KF* kf1, KF* kf2)
 }
 }  // namespace sdm_host
 
+
 #ifndef covisN
 #define covisN 7   // ProbabilityMapping.h:45 (runtime-overridable through SetCovisN for BASELINE's 6 / 10)
 #endif
@@ -90,10 +103,14 @@ public:
     };
 
     explicit ProbabilityMapping(Map* pMap)
-        : mMutexSemiDense(), mpMap(pMap), mCtx(NULL), mN(covisN), mW(0), mH(0), mCapacity(0), mDevicePlanes(false), mOnline(false), mbFinishRequested(false),
-          mbFinished(false), mbResetRequested(false)
+        : mMutexSemiDense(), mpMap(pMap), mCtx(NULL), mN(covisN), mW(0), mH(0), mCapacity(0), mChunk(0), mHeadroom(-1), mDevicePlanes(false),
+          mOnline(false), mbFinishRequested(false), mbFinished(false), mbResetRequested(false)
     {
         sdm_default_config(&mCfg);
+#ifdef SDM_HOST_WITH_ORBSLAM2
+        mpModeler = new Modeler(mpMap);  // :195-202
+        mpMap->SetModeler(mpModeler);
+#endif
     }
     ~ProbabilityMapping() { sdm_destroy(mCtx); }
 
@@ -103,11 +120,24 @@ public:
     // upload im_ only and let the device produce GradImg / GradTheta (KeyFrame.cc:69-74: scalar-form magnitude / phase,
     // <= 1 ulp / 3e-5 deg from OpenCV's SIMD kernels) instead of uploading the keyframe's own planes; 1 B/px instead of 9
     void SetProducePlanesOnDevice(bool on) { mDevicePlanes = on; }
+    // keyframes per chunk of the pipelined loop (sdm_run_loop); 0 = the library's default
+    void SetPipelineChunk(int n) { mChunk = n; }
+    // device slots reserved beyond the keyframes of the map when an arena is created; < 0 = half the map + 16.  A slot
+    // costs 78-86 bytes per pixel, a larger arena is created (and finished keyframes re-seeded) when the map outgrows it
+    void SetArenaHeadroom(int slots) { mHeadroom = slots; }
+    // What the reference does per keyframe right before its pixel loop (:394-397): mLineDetector.DetectEdgeMap(kf) fills
+    // kf->mEdgeIndex (the candidate mask of :454), DetectLineSegments(kf) feeds the line fitting.  With
+    // SDM_HOST_WITH_ORBSLAM2 the class calls its own mLineDetector exactly there; a hook replaces that call (stand-alone
+    // builds have no LineDetector: without a hook mEdgeIndex is used as the caller left it, empty = every pixel passes).
+    void SetEdgeMapHook(const std::function<void(KeyFrame*)>& f) { mEdgeHook = f; }
+    // where SaveSemiDensePoints / WriteModel put their files; default "results_line_segments/<date-time>" (:138, :121)
+    void SetResultsDir(const std::string& d) { mResultsDir = d; }
 
     // ProbabilityMapping.cc:204-300.  Offline mode (the reference's build, `#define OnlineLoop` commented out at
-    // ProbabilityMapping.h:42): idle until finish is requested, then one loop.  Online mode (:223-234): every 5 ms the
-    // keyframes that became eligible are processed (the gating of SemiDenseLoop skips finished ones, their planes stay
-    // resident on the device) and the point sets of keyframes whose pose changed are refreshed.
+    // ProbabilityMapping.cc:42): idle until finish is requested, then one loop and the consumers of :256-297.  Online
+    // mode (:223-234): every 5 ms the keyframes that became eligible are processed (the gating of SemiDenseLoop skips
+    // finished ones, their planes stay resident on the device) and the point sets of keyframes whose pose changed are
+    // refreshed.
     void SetOnline(bool on) { mOnline = on; }
     void Run()
     {
@@ -116,17 +146,42 @@ public:
             if (mOnline) {
                 SemiDenseLoop();
                 UpdateAllSemiDensePointSet();  // make point position dependent to kf position (:226)
+#ifdef SDM_HOST_WITH_ORBSLAM2
+                if (mpModeler->CheckNewTranscriptEntry()) { mpModeler->RunRemainder(); mpModeler->UpdateModel(); }
+#endif
             }
             ResetIfRequested();
             std::this_thread::sleep_for(std::chrono::milliseconds(5));
         }
+        const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
         SemiDenseLoop();
+        const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        const size_t nkf = mpMap->GetAllKeyFrames().size();
+        std::cout << "semi dense mapping took total: " << ms << "ms  avg:" << (nkf ? ms / nkf : 0.0) << "ms  #KF:" << nkf << std::endl;  // :254
+        SaveSemiDensePoints();  // :256
+#ifdef SDM_HOST_WITH_ORBSLAM2
+        {   // the line / surface consumers of :258-295, unchanged reference code
+            std::vector<KeyFrame*> vpKFs = mpMap->GetAllKeyFrames();
+            mLineDetector.RunLine3Dpp(vpKFs);
+            mLineDetector.LineFittingEDLinesOffline(vpKFs);
+            if (!mOnline) {
+                mLineDetector.LineFittingOffline(vpKFs, mpModeler);
+                for (size_t i = 0; i < vpKFs.size(); i++) mpModeler->AddLineSegmentKeyFrameEntry(vpKFs[i]);
+            }
+            mLineDetector.SaveAllLineSegments();
+            mLineDetector.SaveClusteredSegments();
+            if (mpModeler->CheckNewTranscriptEntry()) { mpModeler->RunOnce(); mpModeler->UpdateModel(); }
+            mLineDetector.Summary();
+        }
+#endif
         SetFinish();
     }
 
-    // ProbabilityMapping.cc:348-597.  Same gating, same two passes; the per-keyframe bodies of each pass
-    // are collected and launched as ONE batch (pass 1 of a keyframe reads only immutable inputs of its
-    // neighbours, pass 2 only pass-1 planes, so the batching does not change any result).
+    // ProbabilityMapping.cc:348-597.  Same gating, same two passes.  Pass 1 of a keyframe reads only immutable inputs of
+    // its neighbours and pass 2 only pass-1 planes (:1202-1249), and which keyframes pass 2 will process follows from
+    // the flags pass 1 is going to set (:497), so both gating loops run first, on the host, and the device work of the
+    // whole loop - uploads, pass 1, depth_map_/depth_sigma_ back, pass 2, depth_map_checked_/SemiDensePointSets_ back -
+    // goes to the library as ONE pipelined call (sdm_run_loop) whose copies overlap its kernels.
     void SemiDenseLoop()
     {
         std::unique_lock<std::mutex> lock(mMutexSemiDense);
@@ -134,91 +189,31 @@ public:
         if (vpKFs.size() < 10) return;  // :351
         if (!EnsureContext(vpKFs)) return;
 
-        // ---- pass 1 (:353-510)
-        std::vector<sdm_item> items;
-        std::vector<KeyFrame*> owners;
+        // ---- gating of pass 1 (:353-384) and, with the flags pass 1 will leave, of pass 2 (:512-542)
+        std::vector<Work> w1, w2;
+        std::unordered_set<KeyFrame*> will_be_mapped;
         for (size_t i = 0; i < vpKFs.size(); i++) {
             KeyFrame* kf = vpKFs[i];
-            kf->SetNotEraseSemiDense();
-            if (kf->isBad() || kf->semidense_flag_ || !kf->MappingIdDelay()) {  // :359
-                kf->SetEraseSemiDense();
-                continue;
-            }
-            std::vector<KeyFrame*> closestMatches;
-            if (!ClosestMatches(kf, false, closestMatches)) {  // :365-384
-                kf->SetEraseSemiDense();
-                continue;
-            }
-            sdm_item it;
-            if (BuildItem(kf, closestMatches, true, it)) {
-                items.push_back(it);
-                owners.push_back(kf);
-            }
-            for (size_t j = 0; j < closestMatches.size(); j++) closestMatches[j]->SetEraseSemiDense();
-            kf->SetEraseSemiDense();
+            Pin(kf);
+            if (kf->isBad() || kf->semidense_flag_ || !kf->MappingIdDelay()) continue;  // :359
+            Work w;
+            w.kf = kf;
+            if (!ClosestMatches(kf, false, will_be_mapped, w.nbrs)) continue;  // :365-384
+            DetectEdgeMap(kf);                                                 // :394-397
+            w1.push_back(w);
         }
-        if (!items.empty()) {
-            if (!Flush() || !Check(sdm_pass1(mCtx, (int)items.size(), items.data()), "sdm_pass1")) return;
-            // depth_map_ / depth_sigma_ of the whole batch come back with one call (DMA straight from dense planes)
-            std::vector<sdm_download_desc> dl(owners.size());
-            for (size_t i = 0; i < owners.size(); i++) {
-                KeyFrame* kf = owners[i];
-                std::memset(&dl[i], 0, sizeof(dl[i]));
-                dl[i].kf = mSlot[kf];
-                dl[i].depth = kf->depth_map_.ptr<float>(0);   dl[i].depth_step = (size_t)kf->depth_map_.step;
-                dl[i].sigma = kf->depth_sigma_.ptr<float>(0); dl[i].sigma_step = (size_t)kf->depth_sigma_.step;
-            }
-            if (!Check(sdm_download_keyframes(mCtx, (int)dl.size(), dl.data()), "sdm_download_keyframes") ||
-                !Check(sdm_synchronize(mCtx), "sdm_synchronize"))
-                return;
-            for (size_t i = 0; i < owners.size(); i++) owners[i]->semidense_flag_ = true;  // :497
-        }
-
-        // ---- pass 2 (:512-596)
-        items.clear();
-        owners.clear();
+        for (size_t i = 0; i < w1.size(); i++) will_be_mapped.insert(w1[i].kf);
         for (size_t i = 0; i < vpKFs.size(); i++) {
             KeyFrame* kf = vpKFs[i];
-            kf->SetNotEraseSemiDense();
-            if (kf->isBad() || kf->interKF_depth_flag_ || !kf->MappingIdDelay() || !kf->semidense_flag_) {  // :518
-                kf->SetEraseSemiDense();
-                continue;
-            }
-            std::vector<KeyFrame*> closestMatches;
-            if (!ClosestMatches(kf, true, closestMatches)) {  // :523-542
-                kf->SetEraseSemiDense();
-                continue;
-            }
-            sdm_item it;
-            if (BuildItem(kf, closestMatches, false, it)) {
-                items.push_back(it);
-                owners.push_back(kf);
-            }
-            for (size_t j = 0; j < closestMatches.size(); j++) closestMatches[j]->SetEraseSemiDense();
-            kf->SetEraseSemiDense();
+            const bool mapped = kf->semidense_flag_ || will_be_mapped.count(kf);
+            if (kf->isBad() || kf->interKF_depth_flag_ || !kf->MappingIdDelay() || !mapped) continue;  // :518
+            Work w;
+            w.kf = kf;
+            if (!ClosestMatches(kf, true, will_be_mapped, w.nbrs)) continue;  // :523-542
+            w2.push_back(w);
         }
-        if (!items.empty()) {
-            if (!Flush() || !Check(sdm_pass2(mCtx, (int)items.size(), items.data()), "sdm_pass2")) return;
-            // depth_map_checked_ / SemiDensePointSets_ in groups of 16 keyframes, each group under the keyframes'
-            // mMutexSemiDensePoints like UpdateSemiDensePointSet (:701) so the viewer never sees a half-written set
-            for (size_t i0 = 0; i0 < owners.size(); i0 += 16) {
-                const size_t m = std::min<size_t>(16, owners.size() - i0);
-                std::vector<std::unique_lock<std::mutex> > locks;
-                std::vector<sdm_download_desc> dl(m);
-                for (size_t i = 0; i < m; i++) {
-                    KeyFrame* kf = owners[i0 + i];
-                    locks.emplace_back(kf->mMutexSemiDensePoints);
-                    std::memset(&dl[i], 0, sizeof(dl[i]));
-                    dl[i].kf = mSlot[kf];
-                    dl[i].checked = kf->depth_map_checked_.ptr<float>(0); dl[i].checked_step = (size_t)kf->depth_map_checked_.step;
-                    dl[i].points = kf->SemiDensePointSets_.ptr<float>(0); dl[i].points_step = (size_t)kf->SemiDensePointSets_.step;
-                }
-                if (!Check(sdm_download_keyframes(mCtx, (int)m, dl.data()), "sdm_download_keyframes") ||
-                    !Check(sdm_synchronize(mCtx), "sdm_synchronize"))
-                    return;
-                for (size_t i = 0; i < m; i++) owners[i0 + i]->interKF_depth_flag_ = true;  // :554
-            }
-        }
+        if (!w1.empty() || !w2.empty()) RunLoop(w1, w2);
+        UnpinAll();
     }
 
     // ProbabilityMapping.cc:734-747
@@ -296,7 +291,7 @@ public:
     void UpdateSemiDensePointSet(KeyFrame* kf)
     {
         std::unique_lock<std::mutex> lock(kf->mMutexSemiDensePoints);
-        if (!EnsureUploaded(kf) || !Flush()) return;
+        if (!EnsureResident(kf)) return;
         const int32_t s = mSlot[kf];
         float Tcw[12];
         PoseOf(kf, Tcw);
@@ -311,14 +306,41 @@ public:
     void UpdateAllSemiDensePointSet()
     {
         std::vector<KeyFrame*> vpKFs = mpMap->GetAllKeyFrames();
+        if (vpKFs.size() < 10) return;  // :681
         for (size_t i = 0; i < vpKFs.size(); i++) {
             KeyFrame* kf = vpKFs[i];
-            if (kf->isBad() || !kf->interKF_depth_flag_) continue;
+            kf->SetNotEraseSemiDense();
+            if (kf->isBad() || !kf->semidense_flag_ || !kf->interKF_depth_flag_ || !kf->MappingIdDelay()) {  // :686
+                kf->SetEraseSemiDense();
+                continue;
+            }
             if (kf->PoseChanged()) {
                 UpdateSemiDensePointSet(kf);
                 kf->SetPoseChanged(false);
             }
+            kf->SetEraseSemiDense();
         }
+    }
+
+    // ProbabilityMapping.cc:657-676 (no caller in the reference; host loop, nothing to accelerate)
+    void ApplySigmaThreshold(KeyFrame* kf)
+    {
+        for (int y = 2; y < kf->im_.rows - 2; y++)
+            for (int x = 2; x < kf->im_.cols - 2; x++) {
+                if (kf->depth_map_.at<float>(y, x) < 0.000001) continue;
+                if (kf->depth_sigma_.at<float>(y, x) > 0.025) kf->depth_map_.at<float>(y, x) = 0.0;
+            }
+    }
+
+    // ProbabilityMapping.cc:306-345: marks every good keyframe as mapped (the constant-depth test points it builds are
+    // discarded in the reference as well)
+    void TestSemiDenseViewer()
+    {
+        std::vector<KeyFrame*> vpKFs = mpMap->GetAllKeyFrames();
+        if (vpKFs.size() < 2) return;
+        for (size_t i = 0; i < vpKFs.size(); i++)
+            if (!vpKFs[i]->isBad() && !vpKFs[i]->semidense_flag_) vpKFs[i]->semidense_flag_ = true;
+        std::cout << "semidense_Info:    vpKFs.size()--> " << vpKFs.size() << std::endl;
     }
 
     // The point filter of SaveSemiDensePoints (:156-186), MapDrawer::DrawSemiDense (MapDrawer.cc:88-117) and the CARV
@@ -333,7 +355,8 @@ public:
         std::vector<int32_t> slots;
         for (size_t i = 0; i < vpKFs.size(); i++) {
             KeyFrame* kf = vpKFs[i];
-            if (kf->isBad() || !kf->semidense_flag_ || !kf->interKF_depth_flag_ || !mSlot.count(kf)) continue;  // :159
+            if (kf->isBad() || !kf->semidense_flag_ || !kf->interKF_depth_flag_) continue;  // :159
+            if (!EnsureResident(kf)) return 0;  // a keyframe finished before the arena was rebuilt: planes go back up
             kfs.push_back(kf);
             slots.push_back(mSlot[kf]);
         }
@@ -350,6 +373,64 @@ public:
         if (counts_out) counts_out->swap(counts);
         return pts.size();
     }
+
+    // ProbabilityMapping.cc:136-192: "v x y z r g b" per surviving point into <results dir>/semi_pointcloud.obj, same
+    // order, same filter, same formatting (std::to_string); the points come compacted from the device instead of a
+    // scan over every pixel of every keyframe.  A keyframe without rgb_ (stand-alone tests) writes its grey value.
+    void SaveSemiDensePoints()
+    {
+        const std::string dir = ResultsDir();
+        if (!MakeDirs(dir)) {
+            std::cerr << "Failed to create directory: " << dir << std::endl;
+            return;
+        }
+        const std::string strFileName(dir + "/semi_pointcloud.obj");
+        std::ofstream fileOut(strFileName.c_str(), std::ios::out);
+        if (!fileOut) {
+            std::cerr << "Failed to save semi dense points" << std::endl;
+            return;
+        }
+        std::vector<sdm_point> pts;
+        std::vector<KeyFrame*> kfs;
+        std::vector<uint64_t> counts;
+        ExportSemiDensePoints(0.02, pts, &kfs, &counts);
+        size_t k = 0;
+        for (size_t i = 0; i < kfs.size(); i++) {
+            KeyFrame* kf = kfs[i];
+            const bool colour = !kf->rgb_.empty();
+            for (uint64_t j = 0; j < counts[i]; j++, k++) {
+                const int x = (int)(pts[k].pixel & 0xffffu), y = (int)(pts[k].pixel >> 16);
+                float vr, vg, vb;
+                if (colour) {
+                    float b = kf->rgb_.at<unsigned char>(y, 3 * x) / 255.0;
+                    float g = kf->rgb_.at<unsigned char>(y, 3 * x + 1) / 255.0;
+                    float r = kf->rgb_.at<unsigned char>(y, 3 * x + 2) / 255.0;
+                    vr = r; vg = g; vb = b;
+                } else {
+                    vr = vg = vb = kf->im_.at<unsigned char>(y, x) / 255.0;
+                }
+                fileOut << "v " + std::to_string(pts[k].x) + " " + std::to_string(pts[k].y) + " " + std::to_string(pts[k].z) + " "
+                               + std::to_string(vr) + " " << std::to_string(vg) + " " + std::to_string(vb) << std::endl;
+            }
+        }
+        fileOut.flush();
+        fileOut.close();
+        std::cout << "saved semi dense point cloud" << std::endl;
+    }
+
+#ifdef SDM_HOST_WITH_ORBSLAM2
+    Modeler* GetModeler() { return mpModeler; }  // :113-116
+    void WriteModel()                            // :119-134
+    {
+        const std::string dir = ResultsDir();
+        if (!MakeDirs(dir)) {
+            std::cerr << "Failed to create directory: " << dir << std::endl;
+            return;
+        }
+        mpModeler->WriteModel(dir + "/model.obj");
+        std::cout << "saved mesh model" << std::endl;
+    }
+#endif
 
     // ProbabilityMapping.cc:847-864 (hash join instead of the O(n1*n2) pointer scan; same multiset)
     std::vector<float> GetRotInPlane(KeyFrame* kf1, KeyFrame* kf2) { return sdm_host::RotInPlane(kf1, kf2); }
@@ -371,22 +452,43 @@ public:
     {
         std::unique_lock<std::mutex> l(mMutexReset);
         if (mbResetRequested) {
-            sdm_destroy(mCtx);
-            mCtx = NULL;
-            mSlot.clear();
-            mPending.clear();
-            mPendingKFs.clear();
-            mCapacity = 0;
+            DropContext();
+#ifdef SDM_HOST_WITH_ORBSLAM2
+            mLineDetector.Reset();  // :618-626
+            delete mpModeler;
+            mpModeler = new Modeler(mpMap);
+            mpMap->SetModeler(mpModeler);
+#endif
             mbResetRequested = false;
         }
     }
 
     // per-stage device times of the last loop (the "... took" prints of :389-443, :505-508, :545-565)
     sdm_timing LastTiming() { sdm_timing t = sdm_timing(); if (mCtx) sdm_last_timing(mCtx, &t); return t; }
+    // forget the device copies of all keyframes (the arena stays allocated): the next call uploads what it needs again.
+    // For hosts that rewrite keyframe planes in place, and for timing a cold loop.
+    void ForgetResidentKeyFrames()
+    {
+        if (!mCtx) return;
+        sdm_synchronize(mCtx);
+        mSlot.clear();
+        mPending.clear();
+        mPendingKFs.clear();
+        mFree.clear();
+        for (int s = mCapacity - 2; s >= 0; s--) mFree.push_back(s);
+    }
+    // device slots currently reserved / in use (diagnostics; tests)
+    int ArenaCapacity() const { return mCapacity; }
+    int ResidentKeyFrames() const { return (int)mSlot.size(); }
 
     std::mutex mMutexSemiDense;  // ProbabilityMapping.h:117
 
 private:
+    struct Work {
+        KeyFrame* kf;
+        std::vector<KeyFrame*> nbrs;
+    };
+
     bool Check(int rc, const char* what)
     {
         if (rc == SDM_OK) return true;
@@ -401,47 +503,109 @@ private:
             for (int c = 0; c < 4; c++) Tcw[r * 4 + c] = T.at<float>(r, c);
     }
 
-    bool CreateContext(int W, int H, int capacity)
+    // erase pins of the reference (SetNotEraseSemiDense / SetEraseSemiDense around every use, :357-594): held for the
+    // whole pipelined loop, because the device reads a keyframe's host planes until the loop's synchronise
+    void Pin(KeyFrame* kf) { kf->SetNotEraseSemiDense(); mPinned.push_back(kf); }
+    void UnpinAll()
+    {
+        for (size_t i = 0; i < mPinned.size(); i++) mPinned[i]->SetEraseSemiDense();
+        mPinned.clear();
+    }
+
+    void DetectEdgeMap(KeyFrame* kf)
+    {
+        if (mEdgeHook) { mEdgeHook(kf); return; }
+#ifdef SDM_HOST_WITH_ORBSLAM2
+        mLineDetector.DetectEdgeMap(kf);       // :394
+        mLineDetector.DetectLineSegments(kf);  // :397
+#else
+        (void)kf;
+#endif
+    }
+
+    std::string ResultsDir()
+    {
+        if (!mResultsDir.empty()) return mResultsDir;
+#ifdef SDM_HOST_WITH_ORBSLAM2
+        return "results_line_segments/" + mLineDetector.GetStringDateTime();
+#else
+        char buf[64];
+        const std::time_t t = std::time(NULL);
+        std::strftime(buf, sizeof(buf), "%Y-%m-%d_%H-%M-%S", std::localtime(&t));
+        return std::string("results_line_segments/") + buf;
+#endif
+    }
+    static bool MakeDirs(const std::string& path)  // boost::filesystem::create_directories of :121-127 / :140-146
+    {
+        for (size_t i = 1; i <= path.size(); i++)
+            if (i == path.size() || path[i] == '/') {
+                const std::string p = path.substr(0, i);
+                struct stat st;
+                if (stat(p.c_str(), &st) == 0) continue;
+                if (mkdir(p.c_str(), 0777) != 0 && stat(p.c_str(), &st) != 0) return false;
+            }
+        return true;
+    }
+
+    void DropContext()
     {
         sdm_destroy(mCtx);
         mCtx = NULL;
         mSlot.clear();
+        mFree.clear();
         mPending.clear();
         mPendingKFs.clear();
+        mCapacity = 0;
+    }
+
+    bool CreateContext(int W, int H, int capacity)
+    {
+        DropContext();
         mCfg.width = W;
         mCfg.height = H;
         mCfg.max_keyframes = capacity;
         if (!Check(sdm_create(&mCfg, &mCtx), "sdm_create")) return false;  // no CPU fallback: the loop is skipped
         mW = W; mH = H; mCapacity = capacity;
+        for (int s = capacity - 2; s >= 0; s--) mFree.push_back(s);  // the last slot is the scratch slot of Intra()
         return true;
     }
 
+    // One slot per good keyframe of the map + the scratch slot.  Slots of keyframes that went bad are recycled; when the
+    // map has outgrown the arena a larger one is created - the device state of finished keyframes is not lost with it:
+    // EnsureResident() re-seeds their planes from the cv::Mats the first time they are needed again.
     bool EnsureContext(const std::vector<KeyFrame*>& kfs)
     {
         int W = 0, H = 0;
         for (size_t i = 0; i < kfs.size(); i++)
             if (!kfs[i]->im_.empty()) { W = kfs[i]->im_.cols; H = kfs[i]->im_.rows; break; }
         if (W == 0) return false;
-        if (mCtx && W == mW && H == mH && (int)kfs.size() <= mCapacity) return true;
-        // (re)create with head-room; slots are re-filled on demand (the flags live in the keyframes)
-        return CreateContext(W, H, (int)kfs.size() + (int)kfs.size() / 2 + 16);
+        if (mCtx && W == mW && H == mH) {
+            for (std::unordered_map<KeyFrame*, int>::iterator it = mSlot.begin(); it != mSlot.end();)
+                if (it->first->isBad()) { mFree.push_back(it->second); it = mSlot.erase(it); } else ++it;
+            size_t need = 0;
+            for (size_t i = 0; i < kfs.size(); i++)
+                if (!kfs[i]->isBad() && !mSlot.count(kfs[i])) need++;
+            if (need <= mFree.size()) return true;
+        }
+        return CreateContext(W, H, (int)kfs.size() + 1 + (mHeadroom >= 0 ? mHeadroom : (int)kfs.size() / 2 + 16));
     }
 
-    bool EnsureScratchContext() { return mCtx || CreateContext(64, 64, 1); }
+    bool EnsureScratchContext() { return mCtx || CreateContext(64, 64, 2); }
 
     // Reserve a device slot for kf and queue its planes for upload; the queue goes out as ONE
-    // sdm_upload_keyframes call (Flush) before the next library call that needs the planes.
+    // sdm_upload_keyframes call (Flush, or the upload list of sdm_run_loop) before the planes are needed.
     bool EnsureUploaded(KeyFrame* kf)
     {
         if (!mCtx && !CreateContext(kf->im_.cols, kf->im_.rows, 64)) return false;
         if (mSlot.count(kf)) return true;
-        if ((int)mSlot.size() >= mCapacity - 1) {  // the last slot is the scratch slot of Intra()
+        if (mFree.empty()) {
             std::cerr << "ProbabilityMapping(sdm_b200): device arena full (" << mCapacity << " keyframes)" << std::endl;
             return false;
         }
         sdm_upload_desc u;
         std::memset(&u, 0, sizeof(u));
-        u.kf = (int32_t)mSlot.size();
+        u.kf = (int32_t)mFree.back();
+        mFree.pop_back();
         u.im = kf->im_.ptr<uint8_t>(0);        u.im_step = (size_t)kf->im_.step;
         if (!mDevicePlanes) {
             u.grad = kf->GradImg.ptr<float>(0);    u.grad_step = (size_t)kf->GradImg.step;
@@ -464,15 +628,35 @@ private:
         kfs.swap(mPendingKFs);
         mPending.clear();
         if (!ok) return false;
-        // keyframes mapped in an earlier loop: their pass-1 planes live in the cv::Mats
         for (size_t i = 0; i < kfs.size(); i++)
-            if (kfs[i]->semidense_flag_) PushDepth(kfs[i]);
+            if (!Reseed(kfs[i])) return false;
         return true;
     }
 
+    // a keyframe processed in an earlier loop whose slot is new (first use by a single-method call, arena rebuilt,
+    // reset): its results live in the cv::Mats - pass-1 planes for neighbours' pass 2, depth_map_checked_ for
+    // UpdateSemiDensePointSet / the exporters (the point set is recomputed from it, :700-731)
+    bool Reseed(KeyFrame* kf)
+    {
+        const int32_t s = mSlot[kf];
+        if (kf->semidense_flag_ &&
+            !Check(sdm_upload_depth(mCtx, s, kf->depth_map_.ptr<float>(0), (size_t)kf->depth_map_.step,
+                                    kf->depth_sigma_.ptr<float>(0), (size_t)kf->depth_sigma_.step), "sdm_upload_depth"))
+            return false;
+        if (kf->interKF_depth_flag_) {
+            if (!Check(sdm_upload_checked(mCtx, s, kf->depth_map_checked_.ptr<float>(0), (size_t)kf->depth_map_checked_.step),
+                       "sdm_upload_checked") ||
+                !Check(sdm_update_points(mCtx, 1, &s), "sdm_update_points"))
+                return false;
+        }
+        return true;
+    }
+
+    bool EnsureResident(KeyFrame* kf) { return EnsureUploaded(kf) && Flush(); }
+
     void PushDepth(KeyFrame* kf)
     {
-        if (!EnsureUploaded(kf) || !Flush()) return;
+        if (!EnsureResident(kf)) return;
         Check(sdm_upload_depth(mCtx, mSlot[kf], kf->depth_map_.ptr<float>(0), (size_t)kf->depth_map_.step,
                                kf->depth_sigma_.ptr<float>(0), (size_t)kf->depth_sigma_.step),
               "sdm_upload_depth");
@@ -486,28 +670,24 @@ private:
         return true;
     }
 
-    // :365-384 (pass 1) and :523-542 (pass 2, additionally requires the neighbour's semidense_flag_)
-    bool ClosestMatches(KeyFrame* kf, bool pass2, std::vector<KeyFrame*>& closestMatches)
+    // :365-384 (pass 1) and :523-542 (pass 2, additionally requires the neighbour's semidense_flag_, which pass 1 of
+    // this same loop sets for the keyframes in `mapped_now`, :497)
+    bool ClosestMatches(KeyFrame* kf, bool pass2, const std::unordered_set<KeyFrame*>& mapped_now, std::vector<KeyFrame*>& closestMatches)
     {
         std::vector<KeyFrame*> all = kf->GetVectorCovisibleKeyFrames();
         for (size_t i = 0; i < all.size(); i++) {
             if ((int)closestMatches.size() >= mN) break;
             KeyFrame* k = all[i];
-            k->SetNotEraseSemiDense();
-            if (k->isBad() || !k->Mapped() || (pass2 && !k->semidense_flag_)) {
-                k->SetEraseSemiDense();
-                continue;
-            }
+            Pin(k);
+            if (k->isBad() || !k->Mapped() || (pass2 && !(k->semidense_flag_ || mapped_now.count(k)))) continue;
             closestMatches.push_back(k);
         }
-        if ((int)closestMatches.size() < mN) {
-            for (size_t i = 0; i < closestMatches.size(); i++) closestMatches[i]->SetEraseSemiDense();
-            return false;
-        }
-        return true;
+        return (int)closestMatches.size() >= mN;
     }
 
-    // the per-keyframe set-up of :406-438: rotIs medians, StereoSearchConstraints (F12 is computed in the library)
+    // the per-keyframe set-up of :406-438: rotIs medians, StereoSearchConstraints (F12 is computed in the library from
+    // the poses the slots hold, so resident slots get the keyframes' CURRENT poses first: the reference reads
+    // GetRotation() / GetTranslation() afresh in every loop, and local BA / loop closing move keyframes in between)
     bool BuildItem(KeyFrame* kf, const std::vector<KeyFrame*>& nbrs, bool pass1, sdm_item& it)
     {
         if ((int)nbrs.size() > SDM_MAX_NBR) {
@@ -518,9 +698,11 @@ private:
         std::memset(&it, 0, sizeof(it));
         it.kf = mSlot[kf];
         it.n_nbr = (int32_t)nbrs.size();
+        RefreshPose(kf);
         for (size_t j = 0; j < nbrs.size(); j++) {
             if (!EnsureUploaded(nbrs[j])) return false;
             it.nbr[j] = mSlot[nbrs[j]];
+            RefreshPose(nbrs[j]);
             if (pass1) {
                 std::vector<float> rot = GetRotInPlane(kf, nbrs[j]);
                 std::sort(rot.begin(), rot.end());
@@ -529,6 +711,62 @@ private:
         }
         if (pass1) StereoSearchConstraints(kf, &it.min_depth, &it.max_depth);  // :427
         return true;
+    }
+
+    void RefreshPose(KeyFrame* kf)
+    {
+        float Tcw[12];
+        PoseOf(kf, Tcw);
+        sdm_set_pose(mCtx, mSlot[kf], Tcw);  // host-side bookkeeping of the slot: a 48-byte copy
+        for (size_t i = 0; i < mPending.size(); i++)  // not uploaded yet: the queued descriptor carries the pose
+            if (mPendingKFs[i] == kf) std::memcpy(mPending[i].Tcw, Tcw, sizeof(Tcw));
+    }
+
+    // the device work of one SemiDenseLoop as ONE pipelined library call
+    void RunLoop(const std::vector<Work>& w1, const std::vector<Work>& w2)
+    {
+        // keyframes finished in an earlier loop whose slot is new go up first, with their planes (rare: arena rebuilt)
+        for (size_t pass = 0; pass < 2; pass++) {
+            const std::vector<Work>& w = pass ? w2 : w1;
+            for (size_t i = 0; i < w.size(); i++)
+                for (size_t j = 0; j < w[i].nbrs.size(); j++)
+                    if (w[i].nbrs[j]->semidense_flag_ && !mSlot.count(w[i].nbrs[j]) && !EnsureResident(w[i].nbrs[j])) return;
+        }
+        for (size_t i = 0; i < w2.size(); i++)
+            if (w2[i].kf->semidense_flag_ && !mSlot.count(w2[i].kf) && !EnsureResident(w2[i].kf)) return;
+        if (!Flush()) return;
+        std::vector<sdm_item> it1(w1.size()), it2(w2.size());
+        std::vector<sdm_download_desc> d1(w1.size()), d2(w2.size());
+        for (size_t i = 0; i < w1.size(); i++) {
+            KeyFrame* kf = w1[i].kf;
+            if (!BuildItem(kf, w1[i].nbrs, true, it1[i])) return;
+            std::memset(&d1[i], 0, sizeof(d1[i]));
+            d1[i].kf = it1[i].kf;
+            d1[i].depth = kf->depth_map_.ptr<float>(0);   d1[i].depth_step = (size_t)kf->depth_map_.step;
+            d1[i].sigma = kf->depth_sigma_.ptr<float>(0); d1[i].sigma_step = (size_t)kf->depth_sigma_.step;
+        }
+        for (size_t i = 0; i < w2.size(); i++) {
+            KeyFrame* kf = w2[i].kf;
+            if (!BuildItem(kf, w2[i].nbrs, false, it2[i])) return;
+            std::memset(&d2[i], 0, sizeof(d2[i]));
+            d2[i].kf = it2[i].kf;
+            d2[i].checked = kf->depth_map_checked_.ptr<float>(0); d2[i].checked_step = (size_t)kf->depth_map_checked_.step;
+            d2[i].points = kf->SemiDensePointSets_.ptr<float>(0); d2[i].points_step = (size_t)kf->SemiDensePointSets_.step;
+        }
+        // SemiDensePointSets_ is written by DMA while the loop runs; readers (MapDrawer.cc:92-97) look at a keyframe only
+        // after its interKF_depth_flag_ is set, which happens below, after the synchronise - no keyframe mutex is needed
+        sdm_loop L;
+        std::memset(&L, 0, sizeof(L));
+        std::vector<sdm_upload_desc> up;
+        up.swap(mPending);
+        mPendingKFs.clear();
+        L.n_upload = (int32_t)up.size();  L.upload = up.empty() ? NULL : up.data();
+        L.n_pass1 = (int32_t)it1.size();  L.pass1 = it1.empty() ? NULL : it1.data();  L.down1 = d1.empty() ? NULL : d1.data();
+        L.n_pass2 = (int32_t)it2.size();  L.pass2 = it2.empty() ? NULL : it2.data();  L.down2 = d2.empty() ? NULL : d2.data();
+        L.chunk = mChunk;
+        if (!Check(sdm_run_loop(mCtx, &L), "sdm_run_loop") || !Check(sdm_synchronize(mCtx), "sdm_synchronize")) return;
+        for (size_t i = 0; i < w1.size(); i++) w1[i].kf->semidense_flag_ = true;       // :497
+        for (size_t i = 0; i < w2.size(); i++) w2[i].kf->interKF_depth_flag_ = true;  // :554
     }
 
     void Intra(Mat& depth_map, Mat& depth_sigma, const Mat& gradimg, bool check)
@@ -558,11 +796,19 @@ private:
     Map* mpMap;
     sdm_ctx* mCtx;
     sdm_config mCfg;
-    int mN, mW, mH, mCapacity;
+    int mN, mW, mH, mCapacity, mChunk, mHeadroom;
     bool mDevicePlanes, mOnline;
     std::unordered_map<KeyFrame*, int> mSlot;
+    std::vector<int> mFree;                  // unused device slots
     std::vector<sdm_upload_desc> mPending;   // queued uploads (EnsureUploaded / Flush)
     std::vector<KeyFrame*> mPendingKFs;
+    std::vector<KeyFrame*> mPinned;
+    std::function<void(KeyFrame*)> mEdgeHook;
+    std::string mResultsDir;
+#ifdef SDM_HOST_WITH_ORBSLAM2
+    Modeler* mpModeler;
+    LineDetector mLineDetector;
+#endif
     bool mbFinishRequested, mbFinished, mbResetRequested;
     std::mutex mMutexFinish, mMutexReset;
 };

@@ -73,6 +73,7 @@ public:
         Tcw = Mat(4, 4, sizeof(float));
         for (int i = 0; i < 12; i++) Tcw.ptr<float>(0)[i] = T[i];
         Tcw.at<float>(3, 3) = 1.0f;
+        poseChanged = true;  // KeyFrame.cc:123
     }
     bool isBad() const { return mbBad; }
     // KeyFrame.cc:789-806
@@ -89,7 +90,7 @@ public:
     std::vector<KeyPoint> GetKeyPointsUn() const { return mvKeysUn; }
 
     // KeyFrame.h:155-175
-    Mat im_, GradImg, GradTheta, depth_map_, depth_sigma_, depth_map_checked_, SemiDensePointSets_, mEdgeIndex;
+    Mat im_, rgb_, GradImg, GradTheta, depth_map_, depth_sigma_, depth_map_checked_, SemiDensePointSets_, mEdgeIndex;
     float fx, fy, cx, cy;
     bool semidense_flag_, interKF_depth_flag_;
     float I_stddev;

@@ -81,11 +81,11 @@ EXPORTS = [
     "sdm_default_config", "sdm_create", "sdm_destroy", "sdm_last_error", "sdm_version", "sdm_synchronize",
     "sdm_get_stats", "sdm_scan_generation", "sdm_host_alloc", "sdm_host_free", "sdm_upload_keyframe", "sdm_set_pose",
     "sdm_set_intrinsics", "sdm_candidate_count", "sdm_pass1", "sdm_pass2", "sdm_update_points", "sdm_download", "sdm_download_async", "sdm_upload_keyframes", "sdm_download_keyframes", "sdm_scatter_keyframes", "sdm_export_points", "sdm_download_planes",
-    "sdm_upload_depth", "sdm_depth_plane_ptr", "sdm_export_arena", "sdm_import_peer_arena", "sdm_pull_halo",
+    "sdm_upload_depth", "sdm_upload_checked", "sdm_depth_plane_ptr", "sdm_export_arena", "sdm_import_peer_arena", "sdm_pull_halo",
     "sdm_mark_pass1_done", "sdm_export_peer_handle", "sdm_import_peer", "sdm_set_halo", "sdm_exchange", "sdm_run_loop",
     "sdm_pair_geometry", "sdm_stereo_search_constraints", "sdm_search_range", "sdm_inter_chi_test",
     "sdm_epipolar_search", "sdm_epipolar_search_plane", "sdm_fuse", "sdm_intra_check", "sdm_intra_grow",
-    "sdm_inter_check", "sdm_last_pass_ms", "sdm_launch_count", "sdm_last_timing", "sdm_mark", "sdm_elapsed_ms",
+    "sdm_inter_check", "sdm_last_pass_ms", "sdm_launch_count", "sdm_last_timing", "sdm_last_pack_ms", "sdm_mark", "sdm_elapsed_ms",
 ]
 
 _lib = None
@@ -129,6 +129,7 @@ def load() -> C.CDLL:
     lib.sdm_download_planes.argtypes = [vp, C.c_int, vp, sz, vp, sz]
     lib.sdm_export_points.argtypes = [vp, C.c_int, ip, C.c_double, vp, sz, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.sdm_upload_depth.argtypes = [vp, C.c_int, vp, sz, vp, sz]
+    lib.sdm_upload_checked.argtypes = [vp, C.c_int, vp, sz]
     lib.sdm_depth_plane_ptr.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(sz)]
     lib.sdm_export_arena.argtypes = [vp, vp, C.POINTER(sz)]
     lib.sdm_import_peer_arena.argtypes = [vp, C.c_int, vp]
@@ -154,6 +155,7 @@ def load() -> C.CDLL:
     lib.sdm_launch_count.argtypes = [vp]
     lib.sdm_launch_count.restype = C.c_longlong
     lib.sdm_last_timing.argtypes = [vp, C.POINTER(Timing)]
+    lib.sdm_last_pack_ms.argtypes = [vp, fp]
     lib.sdm_mark.argtypes = [vp, C.c_int]
     lib.sdm_elapsed_ms.argtypes = [vp, C.c_int, C.c_int, fp]
     _lib = lib
@@ -368,6 +370,10 @@ class Context:
         d, s = _f32(depth), _f32(sigma)
         self._chk(self.lib.sdm_upload_depth(self.h, slot, d.ctypes.data, d.strides[0], s.ctypes.data, s.strides[0]))
 
+    def upload_checked(self, slot, checked):
+        c = _f32(checked)
+        self._chk(self.lib.sdm_upload_checked(self.h, slot, c.ctypes.data, c.strides[0]))
+
     def inter_chi_test(self, diff, sigma):
         d, s = _f32(np.ravel(diff)), _f32(np.ravel(sigma))
         out = np.empty(d.size, np.uint8)
@@ -391,6 +397,11 @@ class Context:
         t = Timing()
         self._chk(self.lib.sdm_last_timing(self.h, C.byref(t)))
         return {"pass1_scan_ms": t.pass1_scan_ms, "pass1_intra_ms": t.pass1_intra_ms, "pass2_ms": t.pass2_ms}
+
+    def last_pack_ms(self) -> float:
+        ms = C.c_float()
+        self._chk(self.lib.sdm_last_pack_ms(self.h, C.byref(ms)))
+        return ms.value
 
     def mark(self, idx: int):
         self._chk(self.lib.sdm_mark(self.h, idx))

@@ -190,6 +190,12 @@ int sdm_scatter_keyframes(sdm_ctx* ctx, int n, const sdm_download_desc* desc);
 int sdm_upload_depth(sdm_ctx* ctx, int kf, const float* depth, size_t depth_step,
                      const float* sigma, size_t sigma_step);
 
+/* writes depth_map_checked_ of a keyframe (the pass-2 plane).  For hosts that keep the planes in their own memory and
+ * have to re-create a slot (a larger arena, a reset): with sdm_upload_depth and sdm_update_points this restores
+ * everything a finished keyframe's slot held (SemiDensePointSets_ is a function of this plane and the pose, :700-731);
+ * blocking */
+int sdm_upload_checked(sdm_ctx* ctx, int kf, const float* checked, size_t checked_step);
+
 /* ---- point-cloud export ---------------------------------------------------- */
 /* replaces: the filter loop of SaveSemiDensePoints (ProbabilityMapping.cc:159-186), MapDrawer::DrawSemiDense
  * (MapDrawer.cc:99-117) and the CARV point entry (SFMTranscriptInterface_ORBSLAM.cpp:268-290): for the n
@@ -317,6 +323,9 @@ typedef struct {
     float pass2_ms;
 } sdm_timing;
 int sdm_last_timing(sdm_ctx* ctx, sdm_timing* out);
+/* device time (ms) of the packing / candidate-compaction kernels (k_pack | k_pack_image, k_skip: SURVEY.md 8d counts the
+ * compaction as part of the device-resident loop) of the last sdm_upload_keyframes call, H2D copies excluded */
+int sdm_last_pack_ms(sdm_ctx* ctx, float* pack_ms);
 /* user marks on the context's compute stream (CUDA events), for timing a whole SemiDenseLoop the way
  * :246-254 does with clock_gettime: sdm_mark(idx) records, sdm_elapsed_ms blocks until `to` completed */
 #define SDM_N_MARKS 8

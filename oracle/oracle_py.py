@@ -87,6 +87,8 @@ def _load(name: str) -> C.CDLL:
                                           C.POINTER(C.c_int32), fp, fp, fp, C.POINTER(OracleParams),
                                           C.c_int, C.POINTER(OracleStats)]
     lib.oracle_num_threads.restype = C.c_int
+    lib.oracle_set_num_threads.argtypes = [C.c_int]
+    lib.oracle_set_num_threads.restype = None
     return lib
 
 

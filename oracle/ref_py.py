@@ -76,3 +76,59 @@ def run_reference_intra(which: int, depth, sigma, grad):
     rc = lib().ref_intra(which, W, H, d.ctypes.data_as(C.c_void_p), s.ctypes.data_as(C.c_void_p), g.ctypes.data_as(C.c_void_p))
     assert rc == 0
     return d, s
+
+
+LIB_ONLINE = os.path.join(_HERE, "_ref", "libref_pm_online.so")
+_lib_online = None
+
+
+def lib_online():
+    """the same sources compiled with -DOnlineLoop (the reference's online mode, ProbabilityMapping.cc:42)"""
+    global _lib_online
+    if _lib_online is None:
+        if not os.path.exists(LIB_ONLINE) and not (available() and os.path.exists(LIB_ONLINE)):
+            raise FileNotFoundError(LIB_ONLINE)
+        _lib_online = C.CDLL(LIB_ONLINE)
+        assert _lib_online.ref_online_build() == 1
+    return _lib_online
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def run_reference_online(scene, n1, n2, extra_ids, moved, Tcw_moved):
+    """ref_online_sequence (oracle/refshim/refdriver.cc) of the OnlineLoop build: keyframes arrive in three batches
+    [0,n1), [n1,n2), [n2,n); after each one `SemiDenseLoop(); UpdateAllSemiDensePointSet();` (:224-226); the keyframes
+    in `moved` get new poses before the second round; a final SemiDenseLoop() after `extra_ids` more mapped keyframes."""
+    l = lib_online()
+    n, H, W = scene.im.shape
+    c = np.ascontiguousarray
+    inv = c(np.stack(scene.inv_depths).astype(np.float32))
+    out = {k: np.zeros((n, H, W) + ((3,) if k == "points" else ()), np.float32) for k in ("depth", "sigma", "checked", "points")}
+    flags = np.zeros((n, 2), np.int32)
+    im, g, t = c(scene.im, np.uint8), c(scene.grad, np.float32), c(scene.theta, np.float32)
+    K, T, nb = c(np.asarray(scene.K, np.float32)), c(scene.Tcw.reshape(n, 12), np.float32), c(scene.nbr_idx, np.int32)
+    mv, Tm = c(moved, np.int32), c(np.asarray(Tcw_moved, np.float32).reshape(len(moved), 12))
+    rc = l.ref_online_sequence(n, int(n1), int(n2), W, H, _p(im), _p(g), _p(t), _p(K), _p(T), int(nb.shape[1]), _p(nb), _p(inv),
+                               inv.shape[1], int(extra_ids), len(mv), _p(mv), _p(Tm), _p(out["depth"]), _p(out["sigma"]),
+                               _p(out["checked"]), _p(out["points"]), _p(flags))
+    assert rc == 0
+    out["flags"] = flags
+    return out
+
+
+def reference_save_points(im, sigma, checked, points, flags, bad=None, rgb=None):
+    """the reference's own SaveSemiDensePoints (:136-192) on these planes; writes
+    ./results_line_segments/refshim/semi_pointcloud.obj (the directory must exist) and returns its path"""
+    l = lib()
+    c = np.ascontiguousarray
+    n, H, W = im.shape
+    im, sigma, checked, points = c(im, np.uint8), c(sigma, np.float32), c(checked, np.float32), c(points, np.float32)
+    flags = c(flags, np.int32)
+    badv = c(bad, np.int32) if bad is not None else np.zeros(n, np.int32)
+    os.makedirs(os.path.join("results_line_segments", "refshim"), exist_ok=True)
+    rc = l.ref_save_semidense_points(n, W, H, _p(im), _p(c(rgb, np.uint8)) if rgb is not None else None, _p(sigma), _p(checked),
+                                     _p(points), _p(flags), _p(badv))
+    assert rc == 0
+    return os.path.join("results_line_segments", "refshim", "semi_pointcloud.obj")

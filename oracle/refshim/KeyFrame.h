@@ -46,6 +46,7 @@ public:
         Twc.at<float>(3, 3) = 1.0f;  // cv::Mat::eye
         Rwc.copyTo(Twc.rowRange(0, 3).colRange(0, 3));
         Ow.copyTo(Twc.rowRange(0, 3).col(3));
+        poseChanged = true;  // KeyFrame.cc:123
     }
     cv::Mat GetPose() { unique_lock<mutex> lock(mMutexPose); return Tcw.clone(); }
     cv::Mat GetPoseInverse() { unique_lock<mutex> lock(mMutexPose); return Twc.clone(); }

@@ -81,6 +81,8 @@ public:
     bool empty() const { return data == NULL || rows == 0 || cols == 0; }
     template <class T> T& at(int r, int c) { return *reinterpret_cast<T*>(data + (size_t)r * step + (size_t)c * sizeof(T)); }
     template <class T> const T& at(int r, int c) const { return *reinterpret_cast<const T*>(data + (size_t)r * step + (size_t)c * sizeof(T)); }
+    template <class T> T* ptr(int r = 0) { return reinterpret_cast<T*>(data + (size_t)r * step); }  // cv::Mat::ptr<T>(row)
+    template <class T> const T* ptr(int r = 0) const { return reinterpret_cast<const T*>(data + (size_t)r * step); }
     // single index: element i of a row or column vector (cv::Mat::at(int i0))
     template <class T> T& at(int i) { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }
     template <class T> const T& at(int i) const { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }

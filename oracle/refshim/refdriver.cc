@@ -134,4 +134,121 @@ int ref_intra(int which, int W, int H, float* depth, float* sigma, const float* 
     return 0;
 }
 
+// ---- SaveSemiDensePoints (:136-192) of the reference on caller planes.  Writes results_line_segments/refshim/
+// semi_pointcloud.obj below the current directory (the stand-in boost::filesystem creates nothing: the caller makes the
+// directory).  rgb may be NULL (the keyframes then carry a grey rgb_ built from im).
+int ref_save_semidense_points(int n, int W, int H, const uint8_t* im, const uint8_t* rgb, const float* sigma,
+                              const float* checked, const float* points, const int32_t* flags, const int32_t* bad)
+{
+    using namespace ORB_SLAM2;
+    std::ostringstream sink;
+    std::streambuf* old = std::cout.rdbuf(sink.rdbuf());
+    const size_t P = (size_t)W * H;
+    std::vector<std::unique_ptr<KeyFrame> > kfs;
+    Map map;
+    for (int i = 0; i < n; i++) {
+        kfs.emplace_back(new KeyFrame());
+        KeyFrame* kf = kfs.back().get();
+        kf->im_ = wrap_copy(im + i * P, H, W, CV_8U);
+        kf->rgb_ = cv::Mat(H, W * 3, CV_8U);
+        for (int y = 0; y < H; y++)
+            for (int x = 0; x < W * 3; x++)
+                kf->rgb_.at<uchar>(y, x) = rgb ? rgb[(i * P + (size_t)y * W) * 3 + x] : im[i * P + (size_t)y * W + x / 3];
+        kf->depth_sigma_ = wrap_copy(sigma + i * P, H, W, CV_32F);
+        kf->depth_map_checked_ = wrap_copy(checked + i * P, H, W, CV_32F);
+        kf->SemiDensePointSets_ = wrap_copy(points + i * P * 3, H, W * 3, CV_32F);
+        kf->semidense_flag_ = flags[2 * i] != 0;
+        kf->interKF_depth_flag_ = flags[2 * i + 1] != 0;
+        kf->mbBad = bad && bad[i];
+        map.mvKFs.push_back(kf);
+    }
+    ProbabilityMapping pm(&map);
+    pm.SaveSemiDensePoints();
+    std::cout.rdbuf(old);
+    return 0;
+}
+
+// ---- the online mode (#define OnlineLoop, :42; this file is also built with -DOnlineLoop into libref_pm_online.so).
+// Keyframes arrive in three batches; after each batch the body of Run()'s loop (:223-226) is executed once:
+//     SemiDenseLoop(); UpdateAllSemiDensePointSet();
+// Between the batches the poses of the keyframes listed in moved[] are replaced (SetPose: local BA / loop closing,
+// KeyFrame.cc:108-124 sets poseChanged).  After the last batch extra_ids more keyframes are "mapped" and the final
+// SemiDenseLoop() of :244 runs.  n1 < n2 <= n: batch sizes are n1, n2 - n1, n - n2; Tcw_moved: [n_moved][12].
+int ref_online_sequence(int n, int n1, int n2, int W, int H, const uint8_t* im, const float* grad, const float* theta,
+                        const float* K4, const float* Tcw12, int n_cov, const int32_t* nbr_idx, const float* inv_depths,
+                        int n_inv, int extra_ids, int n_moved, const int32_t* moved, const float* Tcw_moved, float* depth,
+                        float* sigma, float* checked, float* points, int32_t* flags)
+{
+    using namespace ORB_SLAM2;
+    std::ostringstream sink;
+    std::streambuf* old = std::cout.rdbuf(sink.rdbuf());
+    const size_t P = (size_t)W * H;
+    KeyFrame::nNextMappingId = 1;
+    std::vector<std::unique_ptr<KeyFrame> > kfs;
+    Map map;
+    auto pose = [](const float* T12) {
+        cv::Mat T = cv::Mat::zeros(4, 4, CV_32F);
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 4; c++) T.at<float>(r, c) = T12[r * 4 + c];
+        T.at<float>(3, 3) = 1.0f;
+        return T;
+    };
+    for (int i = 0; i < n; i++) {
+        kfs.emplace_back(new KeyFrame());
+        KeyFrame* kf = kfs.back().get();
+        kf->fx = K4[0]; kf->fy = K4[1]; kf->cx = K4[2]; kf->cy = K4[3];
+        kf->mK = cv::Mat::zeros(3, 3, CV_32F);
+        kf->mK.at<float>(0, 0) = K4[0]; kf->mK.at<float>(1, 1) = K4[1];
+        kf->mK.at<float>(0, 2) = K4[2]; kf->mK.at<float>(1, 2) = K4[3]; kf->mK.at<float>(2, 2) = 1.0f;
+        kf->mnMinX = 0; kf->mnMinY = 0; kf->mnMaxX = W; kf->mnMaxY = H;
+        kf->SetPose(pose(Tcw12 + (size_t)i * 12));
+        kf->im_ = wrap_copy(im + i * P, H, W, CV_8U);
+        kf->GradImg = wrap_copy(grad + i * P, H, W, CV_32F);
+        kf->GradTheta = wrap_copy(theta + i * P, H, W, CV_32F);
+        kf->mEdgeIndex = cv::Mat::zeros(H, W, CV_32S);
+        kf->depth_map_ = cv::Mat::zeros(H, W, CV_32F);
+        kf->depth_sigma_ = cv::Mat::zeros(H, W, CV_32F);
+        kf->depth_map_checked_ = cv::Mat::zeros(H, W, CV_32F);
+        kf->SemiDensePointSets_ = cv::Mat::zeros(H, W * 3, CV_32F);
+        kf->mvInvDepths.assign(inv_depths + (size_t)i * n_inv, inv_depths + (size_t)(i + 1) * n_inv);
+    }
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n_cov; j++) kfs[i]->mvpOrderedConnectedKeyFrames.push_back(kfs[nbr_idx[(size_t)i * n_cov + j]].get());
+    ProbabilityMapping pm(&map);
+    const int batch_end[3] = {n1, n2, n};
+    int next = 0;
+    for (int b = 0; b < 3; b++) {
+        for (; next < batch_end[b]; next++) {
+            kfs[next]->IncreaseMappingId();
+            map.mvKFs.push_back(kfs[next].get());
+        }
+        if (b == 1)
+            for (int m = 0; m < n_moved; m++) kfs[moved[m]]->SetPose(pose(Tcw_moved + (size_t)m * 12));
+        pm.SemiDenseLoop();               // :224
+        pm.UpdateAllSemiDensePointSet();  // :226
+    }
+    KeyFrame::nNextMappingId += (long unsigned int)extra_ids;
+    pm.SemiDenseLoop();  // :244
+    for (int i = 0; i < n; i++) {
+        KeyFrame* kf = kfs[i].get();
+        memcpy(depth + i * P, kf->depth_map_.data, P * 4);
+        memcpy(sigma + i * P, kf->depth_sigma_.data, P * 4);
+        memcpy(checked + i * P, kf->depth_map_checked_.data, P * 4);
+        memcpy(points + i * P * 3, kf->SemiDensePointSets_.data, P * 12);
+        flags[2 * i] = kf->semidense_flag_;
+        flags[2 * i + 1] = kf->interKF_depth_flag_;
+    }
+    std::cout.rdbuf(old);
+    return 0;
+}
+
+int ref_online_build(void)
+{
+#ifdef OnlineLoop
+    return 1;
+#else
+    return 0;
+#endif
+}
+
 }  // extern "C"

@@ -44,6 +44,17 @@ int oracle_num_threads(void)
 #endif
 }
 
+/* launchers such as torchrun export OMP_NUM_THREADS=1 to their workers: the CPU baseline sets its thread count
+ * explicitly (the reference runs its omp loops on every core, CMakeLists.txt:47-52) */
+void oracle_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* ------------------------------------------------------------------------------------------
  * OpenCV core primitives, restated (OpenCV 3.x modules/core/src/{matmul,lapack,mathfuncs}.cpp;
  * OpenCV is an un-vendored dependency of the reference: CMakeLists.txt:35-41).

@@ -132,6 +132,7 @@ double oracle_semidense_loop(oracle_kf* kfs, int nkf, int first, int count, int 
                              oracle_stats* st);
 
 int oracle_num_threads(void);
+void oracle_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

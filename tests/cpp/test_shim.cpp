@@ -2,9 +2,15 @@
 // System.cc / the reference's own loop would: keyframes with cv::Mat-like planes in a Map, then
 // SemiDenseLoop(); plus a few single-method calls.  Reads a scene dump written by
 // tests/test_cpp_shim.py, writes the resulting planes back for comparison with the oracle.
+//   test_shim scene.bin out.bin                 offline mode: Run() = one loop + SaveSemiDensePoints (dir: env SDM_SHIM_RESULTS)
+//   test_shim --online scene.bin seq.bin out.bin   the online sequence of oracle/refshim/refdriver.cc::ref_online_sequence
+//   test_shim --time scene.bin out.bin reps     offline loop repeated on fresh flags, wall-clock per SemiDenseLoop()
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <memory>
+#include <string>
 #include <vector>
 
 #include "../../eao-slam_b200/host/ProbabilityMapping.h"
@@ -18,9 +24,35 @@ static void rd(FILE* f, void* p, size_t n)
     if (fread(p, 1, n, f) != n) { fprintf(stderr, "short read\n"); exit(2); }
 }
 
+// planes in pinned host memory (what a cv::Mat backed by cv::cuda::HostMem / cudaHostRegister gives): the timing mode
+// measures the loop the way bench.py's e2e does
+static Mat pinned_mat(int rows, int cols, size_t elem)
+{
+    void* p = NULL;
+    if (sdm_host_alloc(&p, (size_t)rows * cols * elem) != SDM_OK) { fprintf(stderr, "sdm_host_alloc: %s\n", sdm_last_error()); exit(2); }
+    memset(p, 0, (size_t)rows * cols * elem);
+    return Mat(rows, cols, elem, p, (size_t)cols * elem);
+}
+
+static void dump_planes(FILE* o, std::vector<std::unique_ptr<KeyFrame>>& kfs, int W, int H)
+{
+    for (size_t i = 0; i < kfs.size(); i++) {
+        KeyFrame* kf = kfs[i].get();
+        int32_t flags[2] = {kf->semidense_flag_, kf->interKF_depth_flag_};
+        fwrite(flags, 4, 2, o);
+        for (int y = 0; y < H; y++) fwrite(kf->depth_map_.ptr<float>(y), 4, W, o);
+        for (int y = 0; y < H; y++) fwrite(kf->depth_sigma_.ptr<float>(y), 4, W, o);
+        for (int y = 0; y < H; y++) fwrite(kf->depth_map_checked_.ptr<float>(y), 4, W, o);
+        for (int y = 0; y < H; y++) fwrite(kf->SemiDensePointSets_.ptr<float>(y), 4, (size_t)3 * W, o);
+    }
+}
+
 int main(int argc, char** argv)
 {
-    if (argc < 3) { fprintf(stderr, "usage: test_shim scene.bin out.bin\n"); return 2; }
+    const bool online = argc > 1 && std::string(argv[1]) == "--online";
+    const bool timing = argc > 1 && std::string(argv[1]) == "--time";
+    if (online || timing) { argv++; argc--; }
+    if (argc < 3) { fprintf(stderr, "usage: test_shim [--online|--time] scene.bin [seq.bin] out.bin [reps]\n"); return 2; }
     FILE* f = fopen(argv[1], "rb");
     if (!f) { perror("scene"); return 2; }
     // n, W, H, covisN, pitch_pad, n_probe, n_cov (covisibility list length >= covisN), first mapping id, keyframes
@@ -44,11 +76,16 @@ int main(int argc, char** argv)
         kf->fx = K[0]; kf->fy = K[1]; kf->cx = K[2]; kf->cy = K[3];
         // pitched planes, like a cv::Mat ROI: W + pad elements per row
         Mat im(H, W + pad, 1), g(H, W + pad, 4), t(H, W + pad, 4);
+        if (timing) { im = pinned_mat(H, W + pad, 1); g = pinned_mat(H, W + pad, 4); t = pinned_mat(H, W + pad, 4); }
         for (int y = 0; y < H; y++) rd(f, im.ptr<uint8_t>(y), (size_t)W);
         for (int y = 0; y < H; y++) rd(f, g.ptr<float>(y), (size_t)W * 4);
         for (int y = 0; y < H; y++) rd(f, t.ptr<float>(y), (size_t)W * 4);
         im.cols = g.cols = t.cols = W;
         kf->SetPlanes(im, g, t);
+        if (timing) {
+            kf->depth_map_ = pinned_mat(H, W, 4); kf->depth_sigma_ = pinned_mat(H, W, 4);
+            kf->depth_map_checked_ = pinned_mat(H, W, 4); kf->SemiDensePointSets_ = pinned_mat(H, 3 * W, 4);
+        }
         int32_t nd;
         rd(f, &nd, 4);
         kf->mvInvDepths.resize(nd);
@@ -58,8 +95,10 @@ int main(int argc, char** argv)
         int32_t bad;
         rd(f, &bad, 4);
         kf->mbBad = bad != 0;
-        kf->IncreaseMappingId();
-        map.AddKeyFrame(kf);
+        if (!online) {
+            kf->IncreaseMappingId();
+            map.AddKeyFrame(kf);
+        }
     }
     std::vector<int32_t> probes((size_t)n_probe * 4);  // kf1, kf2, x, y
     rd(f, probes.data(), probes.size() * 4);
@@ -74,21 +113,85 @@ int main(int argc, char** argv)
     ProbabilityMapping pm(&map);
     pm.SetCovisN(N);
     if (const char* e = getenv("SDM_SHIM_DEVICE_PLANES")) pm.SetProducePlanesOnDevice(e[0] == '1');
+    if (const char* e = getenv("SDM_SHIM_RESULTS")) pm.SetResultsDir(e);
+    if (const char* e = getenv("SDM_SHIM_CHUNK")) pm.SetPipelineChunk(atoi(e));
+    if (const char* e = getenv("SDM_SHIM_HEADROOM")) pm.SetArenaHeadroom(atoi(e));
+    int hook_calls = 0;
+    pm.SetEdgeMapHook([&hook_calls](KeyFrame*) { ++hook_calls; });  // where the reference calls DetectEdgeMap (:394-397)
+
+    if (online) {  // mirrors ref_online_sequence (oracle/refshim/refdriver.cc)
+        FILE* q = fopen(argv[2], "rb");
+        if (!q) { perror("seq"); return 2; }
+        int32_t sh[4];  // n1, n2, extra_ids, n_moved
+        rd(q, sh, sizeof(sh));
+        std::vector<int32_t> moved(sh[3]);
+        std::vector<float> Tm((size_t)sh[3] * 12);
+        rd(q, moved.data(), moved.size() * 4);
+        rd(q, Tm.data(), Tm.size() * 4);
+        fclose(q);
+        KeyFrame::nNextMappingId() = 1;
+        const int batch_end[3] = {sh[0], sh[1], n};
+        int next = 0, cap0 = 0, regrown = 0;
+        for (int b = 0; b < 3; b++) {
+            for (; next < batch_end[b]; next++) {
+                kfs[next]->IncreaseMappingId();
+                map.AddKeyFrame(kfs[next].get());
+            }
+            if (b == 1)
+                for (int m = 0; m < sh[3]; m++) kfs[moved[m]]->SetPose(&Tm[(size_t)m * 12]);
+            pm.SemiDenseLoop();
+            pm.UpdateAllSemiDensePointSet();
+            if (b == 0) cap0 = pm.ArenaCapacity();
+            else if (pm.ArenaCapacity() != cap0) regrown = 1;
+        }
+        {
+            KeyFrame dummy;
+            for (int i = 0; i < sh[2]; i++) dummy.IncreaseMappingId();
+        }
+        pm.SemiDenseLoop();
+        FILE* o = fopen(argv[3], "wb");
+        if (!o) { perror("out"); return 2; }
+        dump_planes(o, kfs, W, H);
+        // the exporters' filter over everything that is finished, after the arena was rebuilt
+        std::vector<sdm_point> pts;
+        const size_t np = pm.ExportSemiDensePoints(0.02, pts);
+        float tail[3] = {(float)np, (float)regrown, (float)hook_calls};
+        fwrite(tail, 4, 3, o);
+        fwrite(pts.data(), sizeof(sdm_point), np, o);
+        fclose(o);
+        printf("shim online ok: capacity %d -> %d, %zu points\n", cap0, pm.ArenaCapacity(), np);
+        return 0;
+    }
+    if (timing) {  // wall-clock of SemiDenseLoop() itself, the call System.cc's thread makes (bench.py: e2e.api)
+        const int reps = argc > 3 ? atoi(argv[3]) : 3;
+        double best = 1e30, sum = 0;
+        for (int r = 0; r <= reps; r++) {
+            for (int i = 0; i < n; i++) kfs[i]->semidense_flag_ = kfs[i]->interKF_depth_flag_ = false;
+            pm.ForgetResidentKeyFrames();  // every repetition uploads all planes again, like a first loop
+            const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+            pm.SemiDenseLoop();
+            const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+            if (r == 0) continue;  // first call creates the context and uploads through cold staging
+            best = std::min(best, ms);
+            sum += ms;
+        }
+        size_t done = 0;
+        for (int i = 0; i < n; i++) done += kfs[i]->interKF_depth_flag_;
+        printf("{\"semidense_loop_ms_mean\": %.3f, \"semidense_loop_ms_best\": %.3f, \"keyframes\": %d, \"finished\": %zu, \"reps\": %d}\n",
+               sum / reps, best, n, done, reps);
+        FILE* o = fopen(argv[2], "wb");
+        if (!o) { perror("out"); return 2; }
+        dump_planes(o, kfs, W, H);
+        fclose(o);
+        return 0;
+    }
     pm.RequestFinish();
     pm.Run();  // = SemiDenseLoop() once, as in the reference's offline mode
     if (!pm.isFinished()) return 3;
 
     FILE* o = fopen(argv[2], "wb");
     if (!o) { perror("out"); return 2; }
-    for (int i = 0; i < n; i++) {
-        KeyFrame* kf = kfs[i].get();
-        int32_t flags[2] = {kf->semidense_flag_, kf->interKF_depth_flag_};
-        fwrite(flags, 4, 2, o);
-        for (int y = 0; y < H; y++) fwrite(kf->depth_map_.ptr<float>(y), 4, W, o);
-        for (int y = 0; y < H; y++) fwrite(kf->depth_sigma_.ptr<float>(y), 4, W, o);
-        for (int y = 0; y < H; y++) fwrite(kf->depth_map_checked_.ptr<float>(y), 4, W, o);
-        for (int y = 0; y < H; y++) fwrite(kf->SemiDensePointSets_.ptr<float>(y), 4, (size_t)3 * W, o);
-    }
+    dump_planes(o, kfs, W, H);
     // single-method calls, argument order of the reference
     for (int p = 0; p < n_probe; p++) {
         KeyFrame *k1 = kfs[probes[4 * p]].get(), *k2 = kfs[probes[4 * p + 1]].get();

@@ -151,3 +151,117 @@ def test_shim_semidense_loop_matches_oracle(shim_binary, tmp_path):
     assert n_kf == n and list(counts) == exp_counts and n_pts == sum(exp_counts) > 1000
     assert np.array_equal(rec[:, :3].view(np.uint32), np.concatenate(exp_xyz).view(np.uint32))
     assert np.array_equal(rec[:, 3].copy().view(np.uint32), np.concatenate(exp_pix))
+
+
+def test_shim_builds_in_orbslam2_mode(tmp_path):
+    """-DSDM_HOST_WITH_ORBSLAM2: the header compiles and links against ORB_SLAM2::KeyFrame / Map / cv::Mat, Modeler and
+    LineDetector declarations - here the stand-ins of oracle/refshim/, which carry the reference's member names (the
+    same headers the reference's own ProbabilityMapping.cc is compiled against for oracle/_ref)."""
+    src = tmp_path / "orb.cpp"
+    src.write_text('#define SDM_HOST_WITH_ORBSLAM2\n'
+                   f'#include "{ROOT}/eao-slam_b200/host/ProbabilityMapping.h"\n'
+                   'long unsigned int ORB_SLAM2::KeyFrame::nNextMappingId = 1;\n'
+                   'int main() { ORB_SLAM2::Map m; ProbabilityMapping pm(&m); pm.RequestFinish(); pm.Run();\n'
+                   '             pm.GetModeler(); return pm.isFinished() ? 0 : 1; }\n')
+    out = str(tmp_path / "orb")
+    subprocess.run(["g++", "-std=c++11", "-O1", "-Wall", "-I", os.path.join(ROOT, "oracle", "refshim"), "-I",
+                    os.path.join(ROOT, "include"), str(src), "-o", out, "-L", LIBDIR, "-lsdm_b200", f"-Wl,-rpath,{LIBDIR}",
+                    "-lpthread"], check=True)
+    assert os.path.exists(out)
+
+
+def _read_planes(raw, n, W, H):
+    per = 2 + 6 * W * H
+    dev = {k: np.zeros((n, H, W) + ((3,) if k == "points" else ()), np.float32) for k in ("depth", "sigma", "checked", "points")}
+    flags = np.zeros((n, 2), np.int32)
+    for i in range(n):
+        blk = raw[i * per:(i + 1) * per]
+        flags[i] = blk[:2].view(np.int32)
+        p = blk[2:]
+        dev["depth"][i] = p[:W * H].reshape(H, W); dev["sigma"][i] = p[W * H:2 * W * H].reshape(H, W)
+        dev["checked"][i] = p[2 * W * H:3 * W * H].reshape(H, W); dev["points"][i] = p[3 * W * H:].reshape(H, W, 3)
+    return dev, flags, raw[n * per:]
+
+
+@pytest.mark.gpu
+def test_shim_online_mode_matches_the_reference_online_build(shim_binary, tmp_path):
+    """SURVEY 8f-4.  The reference compiled with -DOnlineLoop (oracle/_ref/libref_pm_online.so) and the shim are driven
+    through the same sequence: keyframes arrive in three batches, after each one the body of Run()'s online loop
+    (:224-226: SemiDenseLoop(); UpdateAllSemiDensePointSet();) runs; before the second round local BA "moves" six
+    keyframes (SetPose), some already finished (their point sets must follow, :691-694), some still waiting (their
+    later passes must use the new pose - the reference reads GetRotation()/GetTranslation() afresh in every loop);
+    then the final loop of :244.  The map outgrows the shim's first arena on the way, so finished keyframes are
+    re-seeded from their cv::Mat planes.  Same flags, same planes, bit for bit."""
+    import ref_py
+    if not ref_py.available():
+        pytest.skip("needs /root/reference or a prebuilt oracle/_ref")
+    n, W, H, N, n_cov = 44, 96, 72, 7, 10
+    n1, n2, extra = 24, 34, 11
+    sc = synth.make_scene(n, W, H, n_cov, seed=71, contrast=0.9)
+    rng = np.random.default_rng(3)
+    moved = np.array([3, 7, 11, 20, 26, 30], np.int32)
+    Tm = sc.Tcw[moved].copy()
+    Tm[:, :, 3] += rng.normal(0, 0.004, (len(moved), 3)).astype(np.float32)   # a few millimetres, like a BA update
+    ref = ref_py.run_reference_online(sc, n1, n2, extra, moved, Tm)
+    scene_path, seq_path, out_path = (str(tmp_path / f) for f in ("scene.bin", "seq.bin", "out.bin"))
+    _write_scene(scene_path, sc, N, 0, [], first_id=1, extra_ids=0)
+    with open(seq_path, "wb") as f:
+        f.write(struct.pack("4i", n1, n2, extra, len(moved)))
+        f.write(moved.tobytes()); f.write(np.ascontiguousarray(Tm.reshape(len(moved), 12), np.float32).tobytes())
+    r = subprocess.run([shim_binary, "--online", scene_path, seq_path, out_path], capture_output=True, text=True,
+                       env=dict(os.environ, SDM_SHIM_HEADROOM="3"))  # 24 + 1 + 3 slots: outgrown by the second batch
+    assert r.returncode == 0, r.stdout + r.stderr
+    dev, flags, tail = _read_planes(np.fromfile(out_path, np.float32), n, W, H)
+    assert np.array_equal(flags, ref["flags"]), (flags.T, ref["flags"].T)
+    done1, done2 = ref["flags"][:, 0] == 1, ref["flags"][:, 1] == 1
+    assert done2.sum() >= 25 and done2[moved[:3]].all(), ref["flags"].T
+    for k in ("depth", "sigma", "checked", "points"):
+        assert np.array_equal(dev[k].view(np.uint32), ref[k].view(np.uint32)), k
+    n_pts, regrown, hooks = int(tail[0]), int(tail[1]), int(tail[2])
+    assert regrown == 1, "the scenario is sized so that the map outgrows the first arena"
+    assert hooks == int(done1.sum()), "the edge-map hook runs once per keyframe entering pass 1 (:394-397)"
+    keep = ~(ref["sigma"].astype(np.float64) > 0.02) & (ref["checked"].astype(np.float64) > 0.000001) & done2[:, None, None]
+    assert n_pts == int(keep.sum()) > 1000
+    pts = tail[3:3 + 4 * n_pts].reshape(n_pts, 4)
+    assert np.array_equal(pts[:, :3].view(np.uint32), ref["points"][keep].view(np.uint32))
+
+
+@pytest.mark.gpu
+def test_shim_save_semidense_points_equals_the_reference_writer(shim_binary, tmp_path, monkeypatch):
+    """SaveSemiDensePoints (:136-192): the shim writes the OBJ from the device-compacted point stream; the reference's own
+    function (oracle/_ref) writes it from the same planes with its per-pixel scan.  Byte-identical files."""
+    import ref_py
+    if not ref_py.available():
+        pytest.skip("needs /root/reference or a prebuilt oracle/_ref")
+    n, W, H, N = 12, 160, 120, 6
+    sc = synth.make_scene(n, W, H, N, seed=18, contrast=0.9)
+    scene_path, out_path = str(tmp_path / "scene.bin"), str(tmp_path / "out.bin")
+    bad = np.zeros(n, np.int32); bad[4] = 1
+    _write_scene(scene_path, sc, N, 0, [], bad=bad)
+    res = str(tmp_path / "shim_results")
+    r = subprocess.run([shim_binary, scene_path, out_path], capture_output=True, text=True, cwd=str(tmp_path),
+                       env=dict(os.environ, SDM_SHIM_RESULTS=res))
+    assert r.returncode == 0, r.stdout + r.stderr
+    dev, flags, _ = _read_planes(np.fromfile(out_path, np.float32), n, W, H)
+    monkeypatch.chdir(tmp_path)
+    ref_file = ref_py.reference_save_points(sc.im, dev["sigma"], dev["checked"], dev["points"], flags, bad=bad)
+    a, b = open(os.path.join(res, "semi_pointcloud.obj"), "rb").read(), open(ref_file, "rb").read()
+    assert len(b) > 100000 and a == b
+
+
+@pytest.mark.gpu
+def test_shim_timing_mode_runs_the_pipelined_loop(shim_binary, tmp_path):
+    n, W, H, N = 16, 320, 240, 6
+    sc = synth.make_scene(n, W, H, N, seed=19)
+    scene_path, out_path = str(tmp_path / "scene.bin"), str(tmp_path / "out.bin")
+    _write_scene(scene_path, sc, N, 0, [])
+    outs = []
+    for chunk in ("0", "5"):
+        r = subprocess.run([shim_binary, "--time", scene_path, out_path, "2"], capture_output=True, text=True,
+                           env=dict(os.environ, SDM_SHIM_CHUNK=chunk))
+        assert r.returncode == 0, r.stdout + r.stderr
+        import json
+        t = json.loads(r.stdout.strip().splitlines()[-1])
+        assert t["finished"] == n and t["semidense_loop_ms_best"] > 0
+        outs.append(np.fromfile(out_path, np.float32))
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
