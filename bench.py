@@ -1,18 +1,25 @@
 #!/usr/bin/env python
 """bench.py — semi-dense mapping throughput on B200 (BASELINE.json metric) with roofline + CPU baseline.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--kf KF_PER_GPU]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1..5] [--kf KF_PER_GPU]
 
 One "step" = one full SemiDenseLoop (pass 1: epipolar search + fusion [+ intra checks], halo exchange,
 pass 2: inter-keyframe check + point set) over this rank's shard of a synthetic fr3_long_office-like
-trajectory.  Workload at N=1 = BASELINE config[1]: 200 keyframes, 640x480, TUM fr3 intrinsics, 6
-covisible neighbours, intra + inter depth checks.  N>1 (torchrun): weak scaling, KF_PER_GPU keyframes
-per rank, contiguous shards, halo (rho,sigma) planes pulled from peers over NVLink between the passes.
+trajectory.  Default workload (--config 2) = BASELINE configs[1]: 200 keyframes per GPU, 640x480, TUM fr3
+intrinsics, 6 covisible neighbours, intra + inter depth checks; N>1 (torchrun): weak scaling, contiguous shards,
+halo (rho,sigma) planes pulled from peers over NVLink between the passes, ordered on the devices (sdm_exchange:
+no host synchronisation or barrier inside a step).  The other BASELINE configs:
+  --config 1  configs[0]: 10 keyframes (the reference's CPU-runnable correctness case)
+  --config 3  configs[2]: 1000 keyframes in total, sharded over the GPUs (strong scaling; 125 per GPU on 8)
+  --config 4  configs[3]: 1280x960, 10 neighbours, wide inverse-depth range (long epipolar scans), 48 keyframes per GPU
+  --config 5  configs[4]: 4096 keyframes in total (strong scaling), CPU arm on a 64-keyframe subset
 
 `value`   : candidate pixels (edge & GradImg>8; each is searched against all N neighbours and fused)
             per second, planes resident in HBM, CUDA-event timed on the library's compute stream.
 `e2e`     : the same through the C-ABI with pinned HOST buffers: H2D of every input plane, both passes,
-            D2H of depth_map_/depth_sigma_/depth_map_checked_/SemiDensePointSets_ inside the timed region.
+            D2H of depth_map_/depth_sigma_/depth_map_checked_/SemiDensePointSets_ inside the timed region
+            (sdm_run_loop: the library's own pipelined SemiDenseLoop); `e2e_class` = the same loop through the
+            drop-in C++ class, ProbabilityMapping::SemiDenseLoop() (tests/cpp/test_shim.cpp --time).
 `--impl reference` : the CPU path (oracle/, a restatement of the reference's ProbabilityMapping; the
             reference itself cannot be compiled here) on all host cores, bounded sample.
 """
@@ -36,10 +43,29 @@ import numpy as np  # noqa: E402
 from sdmb200 import shard, synth  # noqa: E402
 
 _REAL_STDOUT = sys.stdout
-METRIC = "semi-dense pixels/sec (searched+fused) at 640x480"
 UNIT = "px/s"
-W, H = 640, 480
+W, H = 640, 480  # set per config in main()
 L2_BYTES = 126 * 2 ** 20
+
+# BASELINE.json configs (1-based like BASELINE.md / VERDICT.md).  kf = keyframes per GPU (weak scaling) or total = keyframes of
+# the whole job divided over the GPUs (strong scaling)
+CONFIGS = {
+    1: dict(tag="configs[0]", W=640, H=480, kf=10, nbr=6, seed=1, wide=False, cpu_kf=10,
+            what="10 synthetic 640x480 keyframes, 6 covisible neighbours (the reference's CPU-runnable correctness case)"),
+    2: dict(tag="configs[1]", W=640, H=480, kf=200, nbr=6, seed=2, wide=False, cpu_kf=12,
+            what="200-keyframe synthetic fr3_long_office-like trajectory per GPU"),
+    3: dict(tag="configs[2]", W=640, H=480, total=1000, nbr=6, seed=3, wide=False, cpu_kf=12,
+            what="1000 keyframes sharded over the GPUs, neighbour depth maps exchanged over NVLink"),
+    4: dict(tag="configs[3]", W=1280, H=960, kf=48, nbr=10, seed=4, wide=True, cpu_kf=12, contrast=1.8,
+            what="1280x960 keyframes, 10 neighbours, wide inverse-depth search range (long epipolar scans); texture contrast 1.8 "
+                 "so that 24 % of the pixels are candidates like in configs[1] (the 0.6 of the VGA scenes leaves 2 % at this resolution)"),
+    5: dict(tag="configs[4]", W=640, H=480, total=4096, nbr=6, seed=5, wide=False, cpu_kf=64,
+            what="4096-keyframe offline re-densification sweep"),
+}
+
+
+def metric_name():
+    return f"semi-dense pixels/sec (searched+fused) at {W}x{H}"
 
 
 def parse():
@@ -48,33 +74,58 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--kf", type=int, default=200, help="keyframes per GPU (BASELINE config[1]: 200)")
-    ap.add_argument("--nbr", type=int, default=6)
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE config, 1-based (default 2 = configs[1])")
+    ap.add_argument("--kf", type=int, default=None, help="keyframes per GPU (overrides the config)")
+    ap.add_argument("--nbr", type=int, default=None)
     ap.add_argument("--intra", type=int, default=1, help="IntraKeyFrameDepthChecking/Growing on (config[1]: full checks)")
-    ap.add_argument("--seed", type=int, default=2)
-    ap.add_argument("--cpu-sample-kf", type=int, default=12, help="keyframes of the bounded CPU-baseline sample")
+    ap.add_argument("--seed", type=int, default=None)
+    ap.add_argument("--cpu-sample-kf", type=int, default=None, help="keyframes of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-e2e-variants", action="store_true", help="skip e2e_scatter / e2e_point_export / e2e_image_in_points_out / e2e_class")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the boundary-keyframe check against the oracle")
     ap.add_argument("--no-hot-spin", action="store_true", help="profiling runs: skip the ~0.6 s of extra untimed steps")
     return ap.parse_args()
+
+
+def apply_config(a, world):
+    """fills a.kf / a.nbr / a.seed / a.cpu_sample_kf from the config, sets the global image size"""
+    global W, H
+    c = CONFIGS[a.config]
+    W, H = c["W"], c["H"]
+    a.scaling = "strong" if "total" in c and a.kf is None else "weak"
+    if a.kf is None:
+        if "total" in c:
+            if c["total"] % world:
+                raise SystemExit(f"config {a.config}: {c['total']} keyframes do not divide over {world} GPUs")
+            a.kf = c["total"] // world
+        else:
+            a.kf = c["kf"]
+    a.nbr = a.nbr if a.nbr is not None else c["nbr"]
+    a.seed = a.seed if a.seed is not None else c["seed"]
+    a.cpu_sample_kf = a.cpu_sample_kf if a.cpu_sample_kf is not None else c["cpu_kf"]
+    a.wide = c["wide"]
+    a.contrast = c.get("contrast", 0.6)
+    return c
 
 
 # ------------------------------------------------------------------------------------------------
 # scene (cached on local disk so the two arms of one box share the render)
 # ------------------------------------------------------------------------------------------------
-def load_scene(n, first, nbr_idx, seed, tag):
+def load_scene(n, first, nbr_idx, seed, tag, wide=False, contrast=0.6):
     cache = os.path.join(os.environ.get("SDM_SCENE_CACHE", "/tmp/sdm_scene_cache"),
-                         f"{tag}_s{seed}_f{first}_n{n}_{W}x{H}")
+                         f"{tag}_s{seed}_f{first}_n{n}_{W}x{H}_N{nbr_idx.shape[1]}{'_wide' if wide else ''}_c{contrast}")
     names = ("im", "grad", "theta", "Tcw", "min_depth", "max_depth")
     if os.path.isdir(cache) and all(os.path.exists(os.path.join(cache, k + ".npy")) for k in names):
         a = {k: np.load(os.path.join(cache, k + ".npy")) for k in names}
-        K = tuple(float(np.float32(v)) for v in synth.TUM3_K)
+        K = tuple(float(np.float32(v * (W / 640.0))) for v in synth.TUM3_K)
         return synth.Scene(im=a["im"], grad=a["grad"], theta=a["theta"], edge=None, K=K, Tcw=a["Tcw"],
                            nbr_idx=nbr_idx, rot=np.zeros(nbr_idx.shape, np.float32),
                            min_depth=a["min_depth"], max_depth=a["max_depth"], meta={"cache": cache})
     world = int(os.environ.get("WORLD_SIZE", "1"))
     workers = max(1, min(16, (os.cpu_count() or 8) // world))
-    sc = synth.make_scene(n, W, H, nbr_idx.shape[1], seed=seed, first=first, workers=workers, nbr_idx=nbr_idx)
+    sc = synth.make_scene(n, W, H, nbr_idx.shape[1], seed=seed, first=first, workers=workers, nbr_idx=nbr_idx, wide_range=wide,
+                          contrast=contrast)
     try:
         os.makedirs(cache, exist_ok=True)
         for k in names:
@@ -168,10 +219,12 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic():
-    """dram bytes per k_pass1 launch from the committed ncu --set full capture of this same command."""
+def ncu_traffic(config):
+    """dram bytes per k_pass1_lane launch from the committed ncu --set full capture of this same command
+    (profiles/traffic.json is written by tools/ncu_summary.py from the capture, not by hand)."""
     try:
-        return json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["k_pass1_dram_bytes_per_launch"]
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return t.get(f"config{config}", {}).get("k_pass1_dram_bytes_per_launch")
     except Exception:
         return None
 
@@ -179,11 +232,15 @@ def ncu_traffic():
 # ------------------------------------------------------------------------------------------------
 # CPU path (oracle) — used ONLY as cpu_baseline and as the --impl reference arm
 # ------------------------------------------------------------------------------------------------
-def cpu_run(sample_kf, nbr, seed, intra, steps, warmup):
+def cpu_run(sample_kf, nbr, seed, intra, steps, warmup, wide=False, contrast=0.6):
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle_py as O
+    # launchers (torchrun) export OMP_NUM_THREADS=1 to their workers: the CPU arm uses every core of the box, as the
+    # reference does (CMakeLists.txt:47-52), whatever the launcher set
+    O.lib("fast").oracle_set_num_threads(os.cpu_count() or 1)
+    sample_kf = max(sample_kf, nbr + 1)
     nb = synth.neighbours(sample_kf, nbr)
-    sc = load_scene(sample_kf, 0, nb, seed, "cpu")
+    sc = load_scene(sample_kf, 0, nb, seed, "cpu", wide, contrast)
     times, cands = [], 0
     for it in range(warmup + steps):
         osc = O.OracleScene(sc, "fast")
@@ -194,29 +251,32 @@ def cpu_run(sample_kf, nbr, seed, intra, steps, warmup):
             times.append(t)
     cores = O.lib("fast").oracle_num_threads()
     sec = sum(times) / len(times)
-    return {"value": cands / sec, "sec_per_step": sec, "cores": cores, "candidates": cands,
+    return {"value": cands / sec, "sec_per_step": sec, "cores": cores, "candidates": cands, "sample_kf": sample_kf,
             "sample": f"full SemiDenseLoop (pass 1 + {'intra + ' if intra else ''}pass 2) over the first {sample_kf} "
-                      f"keyframes of the same synthetic trajectory, {nbr} neighbours, OpenMP over {cores} threads, "
-                      f"gcc -O3 -march=x86-64-v3; ms/KF = {1e3 * sec / sample_kf:.1f}"}
+                      f"keyframes of the same synthetic trajectory ({W}x{H}), {nbr} neighbours, OpenMP over {cores} threads, "
+                      f"gcc -O3 -march=x86-64-v3; ms/KF = {1e3 * sec / sample_kf:.1f} (per-keyframe cost is independent of the "
+                      f"trajectory length, so the job's CPU time extrapolates linearly)"}
 
 
 def main_reference(a, rank):
     if rank != 0:
         return
-    r = cpu_run(a.cpu_sample_kf, a.nbr, a.seed, a.intra, max(1, a.steps), max(0, a.warmup))
+    r = cpu_run(a.cpu_sample_kf, a.nbr, a.seed, a.intra, max(1, a.steps), max(0, a.warmup), a.wide, a.contrast)
     line = {
-        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-        "warmup": a.warmup, "ms_per_step": 1e3 * r["sec_per_step"], "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": metric_name(), "value": r["value"], "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * r["sec_per_step"], "higher_is_better": True, "scaling": a.scaling,
         "vs_baseline": None, "dtype": "f32 (f64 where OpenCV accumulates in double)", "data": "synthetic",
-        "config": workload_config(a, a.kf, note=f"each step = a bounded sample ({a.cpu_sample_kf} keyframes) of the workload; CPU restatement of the "
-                                  "reference path (the reference needs OpenCV/Eigen/Boost/CGAL headers absent here)"),
+        "config": workload_config(a, a.kf),
+        "reference_arm_note": f"each step = a bounded sample ({r['sample_kf']} keyframes) of the workload; CPU restatement of the "
+                              "reference path (the reference needs OpenCV/Eigen/Boost/CGAL headers absent here)",
         "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    src = reference_source_timing(a)
-    if src:
-        line["reference_source"] = src
+    if a.config == 2:
+        src = reference_source_timing(a)
+        if src:
+            line["reference_source"] = src
     print(json.dumps(line), file=_REAL_STDOUT, flush=True)
 
 
@@ -256,13 +316,18 @@ def reference_source_timing(a):
 
 
 def workload_config(a, kf_per_gpu, note=None):
-    c = {"workload": f"BASELINE config[1]: {kf_per_gpu}-keyframe synthetic fr3_long_office-like trajectory per GPU, "
-                     f"640x480, TUM fr3 intrinsics, {a.nbr} covisible neighbours, epipolar search + fusion"
+    cfg = CONFIGS[a.config]
+    in_mb = W * H * 26 / 1e6  # packed planes a keyframe's scan reads per neighbour slot: texel 16 + intensity 2 + skip 8 B/px
+    c = {"workload": f"BASELINE {cfg['tag']}: {cfg['what']}; {kf_per_gpu} keyframes per GPU x {a.gpus} GPU(s), {W}x{H}, TUM fr3 "
+                     f"intrinsics{' x2' if W == 1280 else ''}, {a.nbr} covisible neighbours, epipolar search + fusion"
                      f"{' + intra-keyframe checks' if a.intra else ''} + inter-keyframe check + point set",
-         "keyframes_per_gpu": kf_per_gpu, "neighbours": a.nbr, "intra": bool(a.intra), "seed": a.seed,
-         "l2": f"inputs larger than L2: {kf_per_gpu} keyframes x 8.3 MB of packed planes read per step vs 126 MB L2",
-         "parallelism": f"keyframe shards x{a.gpus}, halo (rho,sigma) planes pulled over NVLink (CUDA IPC peer copies)"
-                        if a.gpus > 1 else "single GPU"}
+         "baseline_config": a.config, "keyframes_per_gpu": kf_per_gpu, "keyframes_total": kf_per_gpu * a.gpus,
+         "neighbours": a.nbr, "intra": bool(a.intra), "seed": a.seed, "image": f"{W}x{H}", "wide_depth_range": bool(a.wide),
+         "l2": f"inputs larger than L2: {kf_per_gpu} keyframes x {in_mb:.1f} MB of packed planes read per step vs 126 MB L2"
+               if kf_per_gpu * in_mb > 126 else
+               f"inputs ({kf_per_gpu} keyframes x {in_mb:.1f} MB) smaller than the 126 MB L2: a 256 MB buffer is overwritten between timed steps",
+         "parallelism": f"keyframe shards x{a.gpus}, halo (rho,sigma) planes pulled over NVLink (CUDA IPC peer copies ordered by "
+                        "flags in peer memory: no host barrier inside a step)" if a.gpus > 1 else "single GPU"}
     if note:
         c["note"] = note
     return c
@@ -280,12 +345,81 @@ def pinned(api_lib, shape, dtype, keep):
     return np.frombuffer(buf, dtype=dtype).reshape(shape)
 
 
+def boundary_parity(a, plan, rank, world, out, owned):
+    """N > 1: the keyframes at the ends of this rank's shard are the ones whose pass 2 read planes pulled from a peer.
+    Recompute each of them with the oracle (canonical build) on a window of the global trajectory around it - its
+    neighbours' pass 1 needs the inputs of THEIR neighbours, i.e. +-N keyframes - and compare the four planes bit for
+    bit.  Returns (keyframes checked, differing 32-bit words)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle_py as O
+    O.lib("canonical").oracle_set_num_threads(max(1, (os.cpu_count() or 1) // world))
+    G = a.kf * world
+    nb_global = synth.neighbours(G, a.nbr)
+    checked, bad = 0, 0
+    for g in sorted({plan.own_lo, plan.own_hi - 1}):
+        if not any(not (plan.own_lo <= int(v) < plan.own_hi) for v in nb_global[g]):
+            continue  # (ends of the whole trajectory: no remote neighbour)
+        lo, hi = max(0, g - a.nbr - 1), min(G, g + a.nbr + 2)
+        nb_win = np.clip(nb_global[lo:hi] - lo, 0, hi - lo - 1).astype(np.int32)  # out-of-window entries: unused keyframes only
+        sc = synth.make_scene(hi - lo, W, H, a.nbr, seed=a.seed, first=lo, nbr_idx=nb_win, wide_range=a.wide, workers=1,
+                              contrast=a.contrast)
+        osc = O.OracleScene(sc)
+        p = O.default_params("canonical", intra_check=a.intra, intra_grow=a.intra)
+        need1 = sorted({g} | {int(v) for v in nb_global[g]})
+        for k in need1:  # pass 1 of the keyframe and of its neighbours (their lists lie inside the window)
+            assert all(lo <= int(v) < hi for v in nb_global[k])
+            osc.run(params=p, first=k - lo, count=1, pass_mask=1)
+        osc.run(params=p, first=g - lo, count=1, pass_mask=2)
+        j = owned.index(g - plan.lo)
+        for name, ref in (("depth", osc.depth), ("sigma", osc.sigma), ("checked", osc.checked), ("points", osc.points)):
+            bad += int((out[name][j].view(np.uint32) != ref[g - lo].view(np.uint32)).sum())
+        checked += 1
+    return checked, bad
+
+
+def class_e2e(a, sc, n_loc):
+    """ProbabilityMapping::SemiDenseLoop() of the drop-in C++ class on the same keyframes (planes in pinned host memory,
+    everything uploaded again in every repetition): tests/cpp/test_shim.cpp --time, compiled here with g++ -std=c++11."""
+    import struct
+    import tempfile
+    tmp = tempfile.mkdtemp(prefix="sdm_class_")
+    exe, scene_path, out_path = (os.path.join(tmp, f) for f in ("test_shim", "scene.bin", "out.bin"))
+    libdir = os.path.join(ROOT, "eao-slam_b200", "lib")
+    r = subprocess.run(["g++", "-std=c++11", "-O2", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "tests", "cpp", "test_shim.cpp"),
+                        "-o", exe, "-L", libdir, "-lsdm_b200", f"-Wl,-rpath,{libdir}", "-lpthread"], capture_output=True, text=True)
+    if r.returncode:
+        return {"unavailable": "g++: " + r.stderr[-200:]}
+    with open(scene_path, "wb") as f:
+        f.write(struct.pack("9i", n_loc, W, H, a.nbr, 0, 0, sc.nbr_idx.shape[1], 1, 11))
+        f.write(np.asarray(sc.K, np.float32).tobytes())
+        for i in range(n_loc):
+            f.write(np.ascontiguousarray(sc.Tcw[i], np.float32).tobytes())
+            f.write(sc.im[i].tobytes()); f.write(sc.grad[i].tobytes()); f.write(sc.theta[i].tobytes())
+            # StereoSearchConstraints input that reproduces this keyframe's search bounds exactly is not kept by the cached
+            # scene: two inverse depths whose mean -+ 2 sigma give them back to within rounding (timing only)
+            lo, hi = 1.0 / float(sc.min_depth[i]), 1.0 / float(sc.max_depth[i])  # mean - 2s, mean + 2s
+            m, sd = 0.5 * (lo + hi), 0.25 * (hi - lo)
+            inv = np.array([m - sd, m + sd], np.float32)
+            f.write(struct.pack("i", 2)); f.write(inv.tobytes())
+            f.write(np.ascontiguousarray(sc.nbr_idx[i], np.int32).tobytes())
+            f.write(struct.pack("i", 0))
+    r = subprocess.run([exe, "--time", scene_path, out_path, str(max(2, a.steps))], capture_output=True, text=True)
+    for f in (scene_path, out_path, exe):
+        try:
+            os.remove(f)
+        except OSError:
+            pass
+    if r.returncode:
+        return {"unavailable": (r.stdout + r.stderr)[-300:]}
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
 def main_ours(a, rank, world, local_rank):
     dist = None
     nb_global = synth.neighbours(a.kf * world, a.nbr)
     plan = shard.make_plan(nb_global, a.kf, rank, world)
     nb_local = np.where(plan.nbr_local >= 0, plan.nbr_local, 0).astype(np.int32)
-    sc = load_scene(plan.n_local, plan.lo, nb_local, a.seed, "gpu")  # before CUDA init (forks workers)
+    sc = load_scene(plan.n_local, plan.lo, nb_local, a.seed, "gpu", a.wide, a.contrast)  # before CUDA init (forks workers)
 
     try:  # bind this rank to the CPUs / NUMA node next to its GPU before any pinned buffer is touched
         import pynvml
@@ -306,20 +440,28 @@ def main_ours(a, rank, world, local_rank):
                       device=local_rank)
     keep = []
     n_loc, owned = plan.n_local, list(plan.owned_local)
+    do_e2e = not a.no_e2e and a.config != 5  # 4096 keyframes: 40 GB of pinned output planes for nothing new
     h_im = pinned(lib, (n_loc, H, W), np.uint8, keep); h_im[:] = sc.im
     h_g = pinned(lib, (n_loc, H, W), np.float32, keep); h_g[:] = sc.grad
     h_t = pinned(lib, (n_loc, H, W), np.float32, keep); h_t[:] = sc.theta
     sc.im, sc.grad, sc.theta = h_im, h_g, h_t
-    out = {k: pinned(lib, (len(owned), H, W) + ((3,) if k == "points" else ()), np.float32, keep)
+    n_out = len(owned) if (do_e2e or world > 1) else 0
+    out = {k: pinned(lib, (max(n_out, 1), H, W) + ((3,) if k == "points" else ()), np.float32, keep)
            for k in ("depth", "sigma", "checked", "points")}
 
-    if world > 1:  # exchange CUDA-IPC handles of the (rho,sigma) arenas once
+    host_exchange = bool(os.environ.get("SDM_BENCH_HOST_EXCHANGE"))  # A/B: round 1's synchronize + barrier + sdm_pull_halo
+    if world > 1:  # exchange CUDA-IPC handles once
         handles = [None] * world
-        dist.all_gather_object(handles, ctx.export_arena())
-        for r in set(int(x) for x in plan.halo_rank):
-            ctx.import_peer_arena(r, handles[r])
-        for s in plan.halo_local:  # halo slots: poses/calibration known locally, planes arrive from the owner
-            pass
+        if host_exchange:
+            dist.all_gather_object(handles, ctx.export_arena())
+            for r in set(int(x) for x in plan.halo_rank):
+                ctx.import_peer_arena(r, handles[r])
+        else:
+            dist.all_gather_object(handles, ctx.export_peer_handle(rank))
+            for r in set(int(x) for x in plan.halo_rank):
+                ctx.import_peer(r, handles[r])
+            ctx.set_halo(plan.halo_local, plan.halo_rank, plan.halo_peer_slot)
+            dist.barrier()  # every import (= puller registration) done before the first exchange
 
     items = api.make_items(owned, sc.nbr_idx, sc.rot, sc.min_depth, sc.max_depth)
 
@@ -333,103 +475,71 @@ def main_ours(a, rank, world, local_rank):
 
     def exchange():
         if world > 1:
-            ctx.synchronize(); barrier()
-            ctx.pull_halo(plan.halo_local, plan.halo_rank, plan.halo_peer_slot)
+            if host_exchange:
+                ctx.synchronize(); barrier()
+                ctx.pull_halo(plan.halo_local, plan.halo_rank, plan.halo_peer_slot)
+            else:
+                ctx.exchange()  # flags in peer memory order the pulls: nothing for the host to wait for
 
-    dbg = bool(os.environ.get("SDM_BENCH_DEBUG"))
+    flush = None
+    if n_loc * W * H * 26 < 2 * L2_BYTES:  # small workloads: overwrite a buffer larger than L2 between timed steps
+        flush = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
 
     def step():
-        t = [time.perf_counter()]
         ctx.pass1(items)
-        if dbg:
-            ctx.synchronize(); t.append(time.perf_counter())
         exchange()
-        if dbg:
-            ctx.synchronize(); t.append(time.perf_counter())
         ctx.pass2(items)
-        if world > 1:
-            ctx.synchronize()
-            if dbg:
-                t.append(time.perf_counter())
-            barrier()
-        if dbg:
-            t.append(time.perf_counter())
-            print(f"rank {rank} step phases ms (pass1, exchange, pass2, barrier):", [round(1e3 * (b - a), 3) for a, b in zip(t, t[1:])],
-                  file=sys.stderr)
+        if world > 1 and host_exchange:
+            ctx.synchronize(); barrier()
 
-    # e2e: the same loop issued in chunks of keyframes so that the library's three streams overlap:
-    # H2D of chunk k+1 under pass 1 of chunk k; depth_map_/depth_sigma_ of chunk k go back to the host as soon
-    # as its pass 1 is queued; pass 2 of chunk k is queued right after pass 1 of chunk k+1 (its neighbours reach
-    # at most N/2 keyframes into chunk k+1) and its depth_map_checked_/SemiDensePointSets_ follow.  Chunks whose
-    # pass 2 needs halo planes of another rank wait for the exchange.  Raw C-ABI calls with prebuilt arguments.
+    # e2e: the whole loop through sdm_run_loop (the library issues uploads, passes and downloads in chunks so that its
+    # three streams overlap: H2D of chunk k+1 under pass 1 of chunk k, depth_map_/depth_sigma_ of a chunk back as soon as
+    # its pass 1 is queued, pass 2 of a keyframe as soon as pass 1 of all its neighbours is queued; work orders that read
+    # halo planes wait for the exchange).  One sdm_upload_desc / sdm_download_desc per keyframe, built once.
     CH = int(os.environ.get("SDM_BENCH_CHUNK", "4"))  # 4 / 6 / 10 / 16 keyframes per chunk: 33.9 / 34.4 / 34.6 / 35.1 ms per loop
-    chunks = [owned[i:i + CH] for i in range(0, len(owned), CH)]
-    chunk_items = [api.make_items(ch, sc.nbr_idx, sc.rot, sc.min_depth, sc.max_depth) for ch in chunks]
-    chunk_need = [max(ch[-1], max(int(v) for s in ch for v in sc.nbr_idx[s])) for ch in chunks]
-    halo_set = set(int(v) for v in plan.halo_local)
-    needs_halo = [any(int(v) in halo_set for s in ch for v in sc.nbr_idx[s]) for ch in chunks]
-    # one sdm_upload_desc / sdm_download_desc per keyframe, built once; a chunk is a slice of these arrays
     up_desc = ctx.upload_descs(sc, range(n_loc))
-    o0 = owned[0]
-    dl1 = (api.DownloadDesc * len(owned))()   # depth_map_, depth_sigma_   (after pass 1)
-    dl2 = (api.DownloadDesc * len(owned))()   # depth_map_checked_, SemiDensePointSets_   (after pass 2)
-    for j, s in enumerate(owned):
-        dl1[j].kf = dl2[j].kf = s
-        dl1[j].depth, dl1[j].depth_step = out["depth"][j].ctypes.data, 4 * W
-        dl1[j].sigma, dl1[j].sigma_step = out["sigma"][j].ctypes.data, 4 * W
-        dl2[j].checked, dl2[j].checked_step = out["checked"][j].ctypes.data, 4 * W
-        dl2[j].points, dl2[j].points_step = out["points"][j].ctypes.data, 12 * W
-    up_sz, dl_sz = C.sizeof(api.UploadDesc), C.sizeof(api.DownloadDesc)
-    up_ptr = lambda i: C.cast(C.byref(up_desc, i * up_sz), C.POINTER(api.UploadDesc))
-    dl_ptr = lambda arr, ch: C.cast(C.byref(arr, (ch[0] - o0) * dl_sz), C.POINTER(api.DownloadDesc))
     chk = ctx._chk
+    dl1 = dl2 = dl4 = None
+    if n_out:
+        dl1 = (api.DownloadDesc * len(owned))()   # depth_map_, depth_sigma_   (after pass 1)
+        dl2 = (api.DownloadDesc * len(owned))()   # depth_map_checked_, SemiDensePointSets_   (after pass 2)
+        dl4 = (api.DownloadDesc * len(owned))()   # all four, for sdm_scatter_keyframes
+        for j, s in enumerate(owned):
+            dl1[j].kf = dl2[j].kf = dl4[j].kf = s
+            dl1[j].depth, dl1[j].depth_step = out["depth"][j].ctypes.data, 4 * W
+            dl1[j].sigma, dl1[j].sigma_step = out["sigma"][j].ctypes.data, 4 * W
+            dl2[j].checked, dl2[j].checked_step = out["checked"][j].ctypes.data, 4 * W
+            dl2[j].points, dl2[j].points_step = out["points"][j].ctypes.data, 12 * W
+            dl4[j].depth, dl4[j].depth_step = dl1[j].depth, 4 * W
+            dl4[j].sigma, dl4[j].sigma_step = dl1[j].sigma, 4 * W
+            dl4[j].checked, dl4[j].checked_step = dl2[j].checked, 4 * W
+            dl4[j].points, dl4[j].points_step = dl2[j].points, 12 * W
+    loop = api.Loop()
+    loop.n_upload, loop.upload = n_loc, up_desc
+    loop.n_pass1, loop.pass1, loop.down1 = len(items), items, dl1
+    loop.n_pass2, loop.pass2, loop.down2 = len(items), items, dl2
+    loop.chunk, loop.exchange = CH, int(world > 1 and not host_exchange)
 
-    t_e2e = [0.0]
-
-    # dl4: all four planes of a keyframe in one descriptor, for sdm_scatter_keyframes (sparse records + host scatter)
-    dl4 = (api.DownloadDesc * len(owned))()
-    for j, s in enumerate(owned):
-        dl4[j].kf = s
-        dl4[j].depth, dl4[j].depth_step = dl1[j].depth, 4 * W
-        dl4[j].sigma, dl4[j].sigma_step = dl1[j].sigma, 4 * W
-        dl4[j].checked, dl4[j].checked_step = dl2[j].checked, 4 * W
-        dl4[j].points, dl4[j].points_step = dl2[j].points, 12 * W
-
-    def e2e_step(sparse=False):
-        t_e2e[0] = time.perf_counter()
-        nxt, deferred = 0, []
-
-        def results(k):  # pass 2 of chunk k, then its results to the host planes
-            chk(lib.sdm_pass2(ctx.h, len(chunk_items[k]), chunk_items[k]))
-            if sparse:
-                chk(lib.sdm_scatter_keyframes(ctx.h, len(chunks[k]), dl_ptr(dl4, chunks[k])))
-            else:
-                chk(lib.sdm_download_keyframes(ctx.h, len(chunks[k]), dl_ptr(dl2, chunks[k])))
-        for k in range(len(chunks)):
-            if nxt <= chunk_need[k]:
-                chk(lib.sdm_upload_keyframes(ctx.h, chunk_need[k] + 1 - nxt, up_ptr(nxt))); nxt = chunk_need[k] + 1
-            chk(lib.sdm_pass1(ctx.h, len(chunk_items[k]), chunk_items[k]))
+    def e2e_step(sparse=False, blocks=True):
+        if not sparse and not host_exchange:
+            # blocks: the destination planes are zero-initialised like KeyFrame's (KeyFrame.cc:78-81), so only the 16-pixel
+            # blocks that hold a candidate cross PCIe (sdm_loop.sparse_download); else the dense DMA of every plane
+            loop.sparse_download = int(blocks)
+            chk(lib.sdm_run_loop(ctx.h, C.byref(loop)))
+        else:  # variants that need a call between the passes: the same order issued from here
+            ctx.upload_keyframes(up_desc)
+            ctx.pass1(items)
             if not sparse:
-                chk(lib.sdm_download_keyframes(ctx.h, len(chunks[k]), dl_ptr(dl1, chunks[k])))
-            if k >= 1:
-                if needs_halo[k - 1]:
-                    deferred.append(k - 1)
-                else:
-                    results(k - 1)
-        if nxt < n_loc:
-            chk(lib.sdm_upload_keyframes(ctx.h, n_loc - nxt, up_ptr(nxt)))
-        exchange()
-        for k in deferred + [len(chunks) - 1]:
-            results(k)
-        if dbg:
-            t_issue = time.perf_counter()
+                ctx.download_keyframes(dl1)
+            exchange()
+            ctx.pass2(items)
+            chk(lib.sdm_scatter_keyframes(ctx.h, len(owned), dl4) if sparse else lib.sdm_download_keyframes(ctx.h, len(owned), dl2))
         ctx.synchronize()
-        if dbg:
-            print(f"e2e issue {1e3 * (t_issue - t_e2e[0]):.2f} ms, total {1e3 * (time.perf_counter() - t_e2e[0]):.2f} ms", file=sys.stderr)
-        if world > 1:
+        if world > 1 and host_exchange:
             barrier()
 
     upload(); ctx.synchronize()
+    pack_ms = ctx.last_pack_ms()
     cands = sum(ctx.candidate_count(s) for s in owned)
     # warm-up: W (>= 3) untimed steps, then keep stepping for ~0.6 s so that the nvidia-smi sampler (started first)
     # is delivering rows and the GPU goes into the timed region hot, with no idle gap in between
@@ -448,27 +558,61 @@ def main_ours(a, rank, world, local_rank):
         step()
     ctx.synchronize(); barrier(); torch.cuda.synchronize()
     l0, t0 = ctx.launch_count(), time.time()
-    ctx.mark(0)
-    for _ in range(a.steps):
-        step()
-    ctx.mark(1)
-    ctx.synchronize(); torch.cuda.synchronize(); barrier()
+    if flush is None:
+        ctx.mark(0)
+        for _ in range(a.steps):
+            step()
+        ctx.mark(1)
+        ctx.synchronize(); torch.cuda.synchronize(); barrier()
+        ms = ctx.elapsed_ms(0, 1) / a.steps
+    else:  # L2 flushed between steps: each step timed on its own (marks 0 / 1), the flush in between is not
+        tot = 0.0
+        for _ in range(a.steps):
+            flush.add_(1); torch.cuda.synchronize()
+            ctx.mark(0); step(); ctx.mark(1)
+            ctx.synchronize()
+            tot += ctx.elapsed_ms(0, 1)
+        barrier()
+        ms = tot / a.steps
     t1 = time.time()
     clocks.nvml_on = False  # the poller only serves the timed region above: keep it out of the host-timed e2e legs
-    ms = ctx.elapsed_ms(0, 1) / a.steps
     launches = ctx.launch_count() - l0
     timing = ctx.last_timing()
+    timing["pack_ms"] = pack_ms
     stats = ctx.stats()
+
+    # ---- multi-GPU parity on the hardware: boundary keyframes (pass 2 read planes that crossed NVLink) against the oracle
+    parity = None
+    if world > 1 and not a.no_parity:
+        ctx.download_keyframes(dl4); ctx.synchronize()  # results of the timed steps
+        parity = boundary_parity(a, plan, rank, world, out, owned)
 
     # ---- end to end through the C-ABI with host buffers
     e2e = None
-    if not a.no_e2e:
+    if do_e2e:
+        # the headline: every plane leaves by DMA, no assumption about the destination planes
+        e2e_step(blocks=False)
+        barrier(); tt = time.perf_counter()
+        for _ in range(a.steps):
+            e2e_step(blocks=False)
+        barrier(); e2e_s = (time.perf_counter() - tt) / a.steps
+        e2e = {"sec": e2e_s, "h2d": int(n_loc * W * H * 9), "d2h": int(len(owned) * W * H * 24)}
+    if do_e2e and not a.no_e2e_variants:
+        # variant: block-sparse download into planes that start zero-initialised like KeyFrame's (KeyFrame.cc:78-81)
+        ref_planes = {k: out[k][::5].copy() for k in out}
+        for k in out:
+            out[k][:] = 0
         e2e_step()
         barrier(); tt = time.perf_counter()
         for _ in range(a.steps):
             e2e_step()
-        barrier(); e2e_s = (time.perf_counter() - tt) / a.steps
-        e2e = {"sec": e2e_s, "h2d": int(n_loc * W * H * 9), "d2h": int(len(owned) * W * H * 24)}
+        barrier(); e2e["blocks_sec"] = (time.perf_counter() - tt) / a.steps
+        e2e["blocks_same"] = all(np.array_equal(out[k][::5].view(np.uint32), ref_planes[k].view(np.uint32)) for k in out)
+        if not e2e["blocks_same"]:
+            print("WARNING: block-sparse download differs from the dense download", file=sys.stderr)
+        del ref_planes
+        e2e["blocks_d2h"] = int(ctx.candidate_blocks(owned) * 16 * 24)
+    if do_e2e and not a.no_e2e_variants:
         # the same loop with sdm_scatter_keyframes: the planes start zero-initialised like KeyFrame.cc:78-81 leaves them
         # and only the candidate pixels' records cross PCIe.  Checked against the dense result on every 7th keyframe.
         ref = {k: out[k][::7].copy() for k in out}
@@ -488,68 +632,57 @@ def main_ours(a, rank, world, local_rank):
         # the same loop for consumers that only need the surviving points (SaveSemiDensePoints / DrawSemiDense / CARV:
         # sigma <= 0.02 and checked > 1e-6): upload + both passes + sdm_export_points instead of the dense downloads
         owned_arr = np.ascontiguousarray(owned, np.int32)
-        pts_buf = pinned(lib, (len(owned) * 40000,), np.dtype([("x", "f4"), ("y", "f4"), ("z", "f4"), ("pixel", "u4")]), keep)
+        pts_buf = pinned(lib, (len(owned) * max(40000, W * H // 6),), np.dtype([("x", "f4"), ("y", "f4"), ("z", "f4"), ("pixel", "u4")]), keep)
         tot = C.c_uint64()
-
-        t_x = [0.0]
-        # larger chunks than the dense-download loop: nothing slow hides the ramp-up / tail of small launches here
-        XCH = int(os.environ.get("SDM_BENCH_XCHUNK", "50"))
-        xchunks = [owned[i:i + XCH] for i in range(0, len(owned), XCH)]
-        xitems = [api.make_items(ch, sc.nbr_idx, sc.rot, sc.min_depth, sc.max_depth) for ch in xchunks]
-        xneed = [max(ch[-1], max(int(v) for s in ch for v in sc.nbr_idx[s])) for ch in xchunks]
-
+        xloop = api.Loop()
+        xloop.n_pass1, xloop.pass1, xloop.n_pass2, xloop.pass2 = len(items), items, len(items), items
+        xloop.chunk, xloop.exchange = int(os.environ.get("SDM_BENCH_XCHUNK", "50")), loop.exchange
         up_img = ctx.upload_descs(sc, range(n_loc), images_only=True)  # grad = theta = NULL: planes made on the device
-        img_ptr = lambda i: C.cast(C.byref(up_img, i * up_sz), C.POINTER(api.UploadDesc))
 
-        def export_step(up_ptr=up_ptr):
-            t_x[0] = time.perf_counter()
-            nxt = 0
-            for k in range(len(xchunks)):  # uploads run ahead of pass 1, chunk by chunk
-                if nxt <= xneed[k]:
-                    chk(lib.sdm_upload_keyframes(ctx.h, xneed[k] + 1 - nxt, up_ptr(nxt))); nxt = xneed[k] + 1
-                chk(lib.sdm_pass1(ctx.h, len(xitems[k]), xitems[k]))
-            if nxt < n_loc:
-                chk(lib.sdm_upload_keyframes(ctx.h, n_loc - nxt, up_ptr(nxt)))
-            exchange()
-            chk(lib.sdm_pass2(ctx.h, len(items), items))
-            if dbg:
-                t_a = time.perf_counter(); ctx.synchronize(); t_b = time.perf_counter()
-                print(f"export_step: issue {1e3 * (t_a - t_x[0]):.2f} ms, passes done {1e3 * (t_b - t_x[0]):.2f} ms", file=sys.stderr)
+        def export_step(up):
+            xloop.n_upload, xloop.upload = n_loc, up
+            if host_exchange:
+                ctx.upload_keyframes(up); ctx.pass1(items); exchange(); ctx.pass2(items)
+            else:
+                chk(lib.sdm_run_loop(ctx.h, C.byref(xloop)))
             chk(lib.sdm_export_points(ctx.h, owned_arr.size, owned_arr.ctypes.data_as(C.POINTER(C.c_int32)), 0.02,
                                       pts_buf.ctypes.data, pts_buf.size, None, C.byref(tot)))
-            barrier()
-        export_step()
-        barrier(); tt = time.perf_counter()
-        for _ in range(a.steps):
-            export_step()
-        e2e["export_sec"] = (time.perf_counter() - tt) / a.steps
-        e2e["export_points"] = int(tot.value)
-        # ... and with only im_ uploaded (1 B/px instead of 9): GradImg / GradTheta produced on the device
-        export_step(img_ptr)
-        barrier(); tt = time.perf_counter()
-        for _ in range(a.steps):
-            export_step(img_ptr)
-        e2e["image_sec"] = (time.perf_counter() - tt) / a.steps
-        e2e["image_points"] = int(tot.value)
+            ctx.synchronize()  # (peers may still pull: the next pass 1 waits for their acknowledgements on the device)
+            if host_exchange:
+                barrier()
+        for name, up in (("export", up_desc), ("image", up_img)):
+            export_step(up)
+            barrier(); tt = time.perf_counter()
+            for _ in range(a.steps):
+                export_step(up)
+            e2e[name + "_sec"] = (time.perf_counter() - tt) / a.steps
+            e2e[name + "_points"] = int(tot.value)
         if e2e["image_points"] != e2e["export_points"]:
             print(f"WARNING: device-produced planes gave {e2e['image_points']} points, uploaded planes {e2e['export_points']}", file=sys.stderr)
     if rank == 0:
         clocks.stop()
 
     tot_cands, ms_max, e2e_max = cands, ms, (e2e["sec"] if e2e else 0.0)
-    sparse_max, sparse_same = (e2e["sparse_sec"] if e2e else 0.0), (1.0 if (e2e and e2e["sparse_same"]) else 0.0)
+    dense_max = e2e.get("blocks_sec", 0.0) if e2e else 0.0  # (block-sparse variant)
+    blocks_ok = 1.0 if (e2e and e2e.get("blocks_same")) else 0.0
+    sparse_max = e2e.get("sparse_sec", 0.0) if e2e else 0.0
+    sparse_same = 1.0 if (e2e and e2e.get("sparse_same")) else 0.0
+    par_n, par_bad = parity if parity else (0, 0)
     if world > 1:
-        v = torch.tensor([float(cands)], device="cuda", dtype=torch.float64)
-        dist.all_reduce(v); tot_cands = int(v.item())
+        v = torch.tensor([float(cands), float(par_n), float(par_bad), 1.0 if parity else 0.0], device="cuda", dtype=torch.float64)
+        dist.all_reduce(v); tot_cands, par_n, par_bad, par_ranks = (int(x) for x in v.tolist())
         xs = [e2e.get("export_sec", 0.0), e2e.get("image_sec", 0.0)] if e2e else [0.0, 0.0]
-        m = torch.tensor([ms, e2e_max, sparse_max, -sparse_same] + xs, device="cuda", dtype=torch.float64)
-        dist.all_reduce(m, op=dist.ReduceOp.MAX); ms_max, e2e_max, sparse_max, sparse_same, x_sec, i_sec = m.tolist()
-        sparse_same = -sparse_same
+        m = torch.tensor([ms, e2e_max, sparse_max, -sparse_same] + xs + [dense_max, -blocks_ok], device="cuda", dtype=torch.float64)
+        dist.all_reduce(m, op=dist.ReduceOp.MAX)
+        ms_max, e2e_max, sparse_max, sparse_same, x_sec, i_sec, dense_max, blocks_ok = m.tolist()
+        sparse_same, blocks_ok = -sparse_same, -blocks_ok
         if e2e and "export_sec" in e2e:
             pv = torch.tensor([float(e2e["export_points"]), float(e2e["image_points"])], device="cuda", dtype=torch.float64)
             dist.all_reduce(pv)
             e2e["export_sec"], e2e["image_sec"] = x_sec, i_sec
             e2e["export_points"], e2e["image_points"] = int(pv[0].item()), int(pv[1].item())
+        pk = torch.tensor([pack_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(pk, op=dist.ReduceOp.MAX); timing["pack_ms"] = pk.item()
     if rank != 0:
         ctx.close()
         if world > 1:
@@ -560,41 +693,64 @@ def main_ours(a, rank, world, local_rank):
     n_own = len(owned)
     p1_bytes = bytes_pass1(n_own, a.nbr)
     ach = p1_bytes / (timing["pass1_scan_ms"] * 1e-3) / 1e9
-    whole = bytes_total(n_own * world, a.nbr, a.intra) / (ms_max * 1e-3) / 1e9 / world
+    whole_bytes = bytes_total(n_own * world, a.nbr, a.intra)
+    whole = whole_bytes / (ms_max * 1e-3) / 1e9 / world
+    whole_c = whole_bytes / ((ms_max + timing["pack_ms"]) * 1e-3) / 1e9 / world
     line = {
-        "metric": METRIC, "value": tot_cands / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
-        "warmup": max(3, a.warmup), "ms_per_step": ms_max, "higher_is_better": True, "scaling": "weak",
+        "metric": metric_name(), "value": tot_cands / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": a.steps,
+        "warmup": max(3, a.warmup), "ms_per_step": ms_max, "higher_is_better": True, "scaling": a.scaling,
         "vs_baseline": None, "dtype": "f32 (f64 where OpenCV accumulates in double)", "data": "synthetic",
         "config": workload_config(a, a.kf),
         "candidates_per_step": tot_cands, "keyframes_per_s": n_own * world / (ms_max * 1e-3),
-        "image_px_per_s": n_own * world * W * H / (ms_max * 1e-3),
+        "image_px_per_s": n_own * world * W * H / (ms_max * 1e-3), "us_per_keyframe_per_gpu": 1e3 * ms_max / n_own,
         "fused_per_step_rank0": stats["fused"], "checked_per_step_rank0": stats["checked"],
         "kernel_ms_rank0": timing,
-        "roofline": {"bound": "hbm", "kernel": "k_pass1 (epipolar scan + hypothesis fusion)", "achieved": ach,
-                     "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": ncu_traffic(),
+        "roofline": {"bound": "hbm", "kernel": "k_pass1_lane (epipolar scan + hypothesis fusion)", "achieved": ach,
+                     "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": ncu_traffic(a.config),
                      "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": p1_bytes,
                      "model": "(17 + 9N) * W*H bytes per keyframe x keyframes per launch (SURVEY.md 8d)",
-                     "whole_path_achieved_per_gpu": whole, "whole_path_frac": whole / peak},
+                     "whole_path_achieved_per_gpu": whole, "whole_path_frac": whole / peak,
+                     "whole_path_frac_with_compaction": whole_c / peak,
+                     "whole_path_note": "whole path = (41 + 17N [+16 intra]) * W*H bytes per keyframe / ms_per_step; with_compaction adds the "
+                                        "device time of the packing + candidate-compaction kernels of one upload of the shard "
+                                        "(kernel_ms_rank0.pack_ms: k_pack, k_skip; run at upload, outside the resident step)"},
         "clocks": clocks.summary(t0, t1),
         "gpu_launches": int(launches),
     }
+    if a.config == 3:
+        budget_ms = 0.5 ** -1 * whole_bytes / world / (peak * 1e9) * 1e3
+        line["north_star"] = {"target": "1000 keyframes / 8 GPUs at >= 50 % of the HBM roofline",
+                              "budget_ms_per_loop_at_50pct": budget_ms, "measured_ms_per_loop": ms_max,
+                              "whole_path_frac": whole / peak,
+                              "note": "the path is bound by instruction issue, not by HBM (DESIGN.md section 5): SURVEY.md 8(d) predicted "
+                                      "5-10 % for this scan length"}
+    if world > 1:
+        line["parity_checked_ranks"] = par_ranks if parity is not None else 0
+        line["parity_boundary_keyframes"] = par_n
+        line["parity_boundary_mismatch_words"] = par_bad
+        line["exchange"] = "host-ordered (synchronize + barrier + sdm_pull_halo)" if host_exchange else "device-ordered (sdm_exchange)"
     if e2e:
-        dense = {"value": tot_cands / e2e_max, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
-                 "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": 1e3 * e2e_max,
-                 "api": "sdm_upload_keyframes / sdm_pass1 / sdm_pass2 / sdm_download_keyframes on pinned host planes, chunks of " + str(CH) + " keyframes"}
-        sparse = {"value": tot_cands / sparse_max, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
-                  "d2h_bytes_per_step": e2e["sparse_d2h"], "ms_per_step": 1e3 * sparse_max,
-                  "identical_to_dense_download": bool(sparse_same > 0.5),
-                  "scatter_threads": int(os.environ.get("SDM_SCATTER_THREADS", "6")),
-                  "api": "sdm_upload_keyframes / sdm_pass1 / sdm_pass2 / sdm_scatter_keyframes: the four output planes of every "
-                         "keyframe in pinned host memory, zero-initialised as KeyFrame.cc:78-81 leaves them; the candidate "
-                         "pixels' records cross PCIe and the library's worker threads write them into the planes; chunks of "
-                         + str(CH) + " keyframes"}
-        # headline = the dense download (no assumption about the destination planes).  The sparse path moves 3.7x fewer
-        # bytes over PCIe but its host-side scatter touches nearly every cache line of the planes at this candidate
-        # density (23 %), so it is host-memory bound and slower here; reported as a variant.
-        line["e2e"], line["e2e_scatter"] = dense, sparse
+        line["e2e"] = {"value": tot_cands / e2e_max, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
+                       "d2h_bytes_per_step": e2e["d2h"], "ms_per_step": 1e3 * e2e_max,
+                       "api": "sdm_run_loop (uploads, sdm_pass1, sdm_exchange, sdm_pass2, downloads pipelined inside the library) on "
+                              "pinned host planes, chunks of " + str(CH) + " keyframes; every plane leaves by DMA"}
+        if "blocks_sec" in e2e:
+            line["e2e_blocks"] = {"value": tot_cands / dense_max, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
+                                  "d2h_bytes_per_step": e2e["blocks_d2h"], "ms_per_step": 1e3 * dense_max,
+                                  "identical_to_dense_download": bool(blocks_ok > 0.5),
+                                  "api": "the same call with sparse_download = 1: the result planes start zero-initialised as "
+                                         "KeyFrame.cc:78-81 leaves them and a kernel writes only the 16-pixel blocks that hold a "
+                                         "candidate pixel over PCIe (rank 0's byte count)"}
+        if "sparse_sec" in e2e:
+            # The sparse path moves 3.7x fewer bytes over PCIe but its host-side scatter touches nearly every cache line of
+            # the planes at this candidate density (23 %), so it is host-memory bound and slower here; a variant.
+            line["e2e_scatter"] = {"value": tot_cands / sparse_max, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
+                                   "d2h_bytes_per_step": e2e["sparse_d2h"], "ms_per_step": 1e3 * sparse_max,
+                                   "identical_to_dense_download": bool(sparse_same > 0.5),
+                                   "scatter_threads": int(os.environ.get("SDM_SCATTER_THREADS", "6")),
+                                   "api": "sdm_upload_keyframes / sdm_pass1 / sdm_pass2 / sdm_scatter_keyframes: candidate records cross "
+                                          "PCIe, library worker threads write them into zero-initialised planes (KeyFrame.cc:78-81)"}
         if "export_sec" in e2e:
             line["e2e_point_export"] = {"value": tot_cands / e2e["export_sec"], "unit": UNIT, "ms_per_step": 1e3 * e2e["export_sec"],
                                         "points_per_step": e2e["export_points"], "d2h_bytes_per_step": 16 * e2e["export_points"],
@@ -609,8 +765,19 @@ def main_ours(a, rank, world, local_rank):
                         "produced on the device by k_pack_image"}
     line["scan_generation"] = ctx.scan_generation()
     ctx.close()
+    if world == 1 and do_e2e and not a.no_e2e_variants:
+        r = class_e2e(a, sc, n_loc)
+        if "semidense_loop_ms_mean" in r:
+            line["e2e_class"] = {"value": tot_cands / (r["semidense_loop_ms_mean"] * 1e-3), "unit": UNIT,
+                                 "ms_per_step": r["semidense_loop_ms_mean"], "ms_best": r["semidense_loop_ms_best"],
+                                 "keyframes_finished": r["finished"],
+                                 "api": "ProbabilityMapping::SemiDenseLoop() of the drop-in C++ class (eao-slam_b200/host/"
+                                        "ProbabilityMapping.h; harness tests/cpp/test_shim.cpp --time): gating, work orders, one "
+                                        "sdm_run_loop, synchronise; planes in pinned host memory, all uploaded again every repetition"}
+        else:
+            line["e2e_class"] = r
     if world == 1 and not a.no_cpu_baseline:
-        r = cpu_run(a.cpu_sample_kf, a.nbr, a.seed, a.intra, 1, 0)
+        r = cpu_run(a.cpu_sample_kf, a.nbr, a.seed, a.intra, 1, 0, a.wide, a.contrast)
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}
     print(json.dumps(line), file=_REAL_STDOUT, flush=True)
     if world > 1:
@@ -635,6 +802,7 @@ def main():
     _REAL_STDOUT = os.fdopen(os.dup(1), "w")
     os.dup2(2, 1)
     a.gpus = world
+    apply_config(a, world)
     if a.impl == "reference":
         main_reference(a, rank)
     else:

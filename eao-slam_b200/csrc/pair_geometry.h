@@ -7,7 +7,8 @@
 //   StereoSearchConstraints :734-747
 //
 // The reference evaluates these with cv::Mat expressions; results depend on where OpenCV uses
-// float or double.  The rules (checked bit-exactly against cv2 in tests/test_host_geometry.py):
+// float or double.  The rules (checked bit-exactly against real cv2 calls: tests/test_abi.py on tests/golden/pair_geometry_cv2.npz,
+// primitives in tests/test_oracle_cv2_kats.py on tests/golden/cv2_kats.npz):
 //   * A * B^T          : general gemm, double accumulation, (float)alpha, result cast to float
 //   * 3x3 * 3x3        : float 3-term dot product, left to right
 //   * 3x3 * 3x1 *a + c : float dot, then float(double(t) * a + double(c)), a rounded to float first

@@ -404,6 +404,7 @@ int build_item(sdm_ctx* c, const sdm_item& in, sdm::DevItem& out, bool pass2, bo
         memcpy(p.t, g.t21.v, sizeof(p.t));
         p.rot = in.rot_deg[j];
         p.slot = s2;
+        memcpy(p.K2, k2.K, sizeof(p.K2));
     }
     return SDM_OK;
 }
@@ -559,7 +560,7 @@ void sdm_destroy(sdm_ctx* c)
     cudaFree(c->xflags);
     if (c->s_halo) cudaStreamDestroy(c->s_halo);
     cudaFree(c->A.tex); cudaFree(c->A.ipair); cudaFree(c->A.texw); cudaFree(c->A.cand); cudaFree(c->A.cand_count);
-    cudaFree(c->A.plane_irregular); cudaFree(c->A.skip);
+    cudaFree(c->A.plane_irregular); cudaFree(c->A.skip); cudaFree(c->A.blk);
     cudaFree(c->A.rs); cudaFree(c->A.chk); cudaFree(c->A.pts); cudaFree(c->A.dpl); cudaFree(c->A.spl); cudaFree(c->A.rs2);
     for (auto& s : c->up) { cudaFree(s.im); cudaFree(s.grad); cudaFree(s.theta); cudaFree(s.edge); }
     for (auto& s : c->down) cudaFree(s.planes);
@@ -635,7 +636,12 @@ static int create_impl(sdm_ctx* c)
 
     CU(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
-    CU(cudaStreamCreateWithFlags(&c->s_down, cudaStreamNonBlocking));
+    {   // the download stream also runs the small block-sparse copy kernel: highest priority, so that its blocks are placed
+        // as soon as a persistent pass kernel's block retires instead of queueing behind the next pass
+        int lo = 0, hi = 0;
+        CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CU(cudaStreamCreateWithPriority(&c->s_down, cudaStreamNonBlocking, hi));
+    }
     CU(cudaStreamCreateWithFlags(&c->s_halo, cudaStreamNonBlocking));
     CU(cudaMalloc(&c->xflags, sizeof(sdm::XFlags)));
     CU(cudaMemset(c->xflags, 0, sizeof(sdm::XFlags)));
@@ -658,6 +664,9 @@ static int create_impl(sdm_ctx* c)
     CU(cudaMalloc(&A.cand_count, n * sizeof(int)));
     CU(cudaMalloc(&A.plane_irregular, n * sizeof(int)));
     CU(cudaMemsetAsync(A.plane_irregular, 0, n * sizeof(int), c->s_compute));
+    A.blk_words = ((cfg.width + sdm::kBlkPx - 1) / sdm::kBlkPx + 31) / 32;
+    CU(cudaMalloc(&A.blk, n * (size_t)cfg.height * A.blk_words * sizeof(uint32_t)));
+    CU(cudaMemsetAsync(A.blk, 0, n * (size_t)cfg.height * A.blk_words * sizeof(uint32_t), c->s_compute));
     CU(cudaMalloc(&A.rs, n * P * sizeof(float2)));
     CU(cudaMalloc(&A.chk, n * P * sizeof(float)));
     CU(cudaMalloc(&A.pts, n * P * 3 * sizeof(float)));
@@ -781,7 +790,7 @@ int sdm_synchronize(sdm_ctx* c)
     return SDM_OK;
 }
 
-int sdm_scan_generation(sdm_ctx* c) { return c ? (c->P.scan2 ? c->P.scan2 : 1) : 0; }
+int sdm_scan_generation(sdm_ctx* c) { return !c || c->scan_warp_per_pixel ? 0 : (c->P.scan2 ? c->P.scan2 : 1); }
 
 int sdm_get_stats(sdm_ctx* c, sdm_stats* out)
 {
@@ -856,20 +865,30 @@ int sdm_upload_keyframes(sdm_ctx* c, int n, const sdm_upload_desc* d)
             c->ev_pack.push_back(e);
         }
         CU(cudaEventRecord(c->ev_pack[c->n_pack_ev], c->s_compute));
-        for (int i = 0; i < m; ++i) {
-            const sdm_upload_desc& u = d[i0 + i];
-            UpStage& st = c->up[(first_stage + i) % kUpStages];
-            CU(cudaMemsetAsync(c->A.cand_count + u.kf, 0, sizeof(int), c->s_compute));
-            CU(cudaMemsetAsync(c->A.plane_irregular + u.kf, 0, sizeof(int), c->s_compute));
-            if (u.grad)
-                sdm::k_pack<<<dim3((c->cfg.width + sdm::kTileW - 1) / sdm::kTileW, (c->cfg.height + sdm::kTileH - 1) / sdm::kTileH),
-                              dim3(32, 8), 0, c->s_compute>>>(c->A, c->P, u.kf, st.im, st.grad, st.theta, u.edge ? st.edge : nullptr);
-            else  // GradImg / GradTheta produced on the device from im_ (KeyFrame.cc:69-74)
-                sdm::k_pack_image<<<tile_grid(c), dim3(32, 8), 0, c->s_compute>>>(c->A, c->P, u.kf, st.im, u.edge ? st.edge : nullptr);
-            if (c->A.skip) {  // skip distances of the third-generation scan loop, from the texels just packed
-                sdm::k_skip<<<(H + sdm::kSkipWarps - 1) / sdm::kSkipWarps, 32 * sdm::kSkipWarps, 0, c->s_compute>>>(c->A, c->P, u.kf);
-                c->launches++;
+        {   // the whole batch with one launch per kernel (grid.z = keyframe)
+            static_assert(kUpStages / 2 <= sdm::kPackBatch, "pack batch");
+            sdm::PackBatch B;
+            memset(&B, 0, sizeof(B));
+            bool any_planes = false, any_image = false;
+            for (int i = 0; i < m; ++i) {
+                const sdm_upload_desc& u = d[i0 + i];
+                UpStage& st = c->up[(first_stage + i) % kUpStages];
+                B.slot[i] = u.kf;
+                B.im[i] = st.im;
+                B.grad[i] = u.grad ? st.grad : nullptr;
+                B.theta[i] = u.grad ? st.theta : nullptr;
+                B.edge[i] = u.edge ? st.edge : nullptr;
+                (u.grad ? any_planes : any_image) = true;
             }
+            sdm::k_pack_reset<<<m, 256, 0, c->s_compute>>>(c->A, c->P, B);
+            if (any_planes)
+                sdm::k_pack<<<dim3((W + sdm::kTileW - 1) / sdm::kTileW, (H + sdm::kTileH - 1) / sdm::kTileH, m), dim3(32, 8), 0,
+                              c->s_compute>>>(c->A, c->P, B);
+            if (any_image)  // GradImg / GradTheta produced on the device from im_ (KeyFrame.cc:69-74)
+                sdm::k_pack_image<<<tile_grid(c, m), dim3(32, 8), 0, c->s_compute>>>(c->A, c->P, B);
+            if (c->A.skip)  // skip distances of the third-generation scan loop, from the texels just packed
+                sdm::k_skip<<<dim3((W + sdm::kSkipSpan - 1) / sdm::kSkipSpan, H, m), sdm::kSkipSpan, 0, c->s_compute>>>(c->A, c->P, B);
+            c->launches += 1 + (any_planes ? 1 : 0) + (any_image ? 1 : 0) + (c->A.skip ? 1 : 0);
         }
         static_assert(kUpStages / 2 <= sdm::kSlotList, "slot list of k_publish_counts");
         sdm::SlotList sl;
@@ -879,7 +898,7 @@ int sdm_upload_keyframes(sdm_ctx* c, int n, const sdm_upload_desc* d)
         CU(cudaEventRecord(c->ev_pack[c->n_pack_ev + 1], c->s_compute));
         c->n_pack_ev += 2;
         trace_end(c, c->s_compute);
-        c->launches += m + 1;
+        c->launches += 1;
         uint64_t id = 0;
         RC(c->r_compute.record(c->s_compute, &id));
         for (int i = 0; i < m; ++i) {
@@ -944,6 +963,23 @@ int sdm_candidate_count(sdm_ctx* c, int kf, int* count)
     return SDM_OK;
 }
 
+int sdm_candidate_blocks(sdm_ctx* c, int n, const int32_t* kfs, uint64_t* blocks)
+{
+    if (!c || (n > 0 && !kfs) || !blocks) return fail(SDM_ERR_ARG, "null argument");
+    *blocks = 0;
+    CU(cudaSetDevice(c->cfg.device));
+    const size_t words = (size_t)c->cfg.height * c->A.blk_words;
+    std::vector<uint32_t> h(words);
+    for (int i = 0; i < n; ++i) {
+        if (!slot_ok(c, kfs[i])) return fail(SDM_ERR_ARG, "keyframe slot %d out of range", kfs[i]);
+        if (!c->kf[kfs[i]].uploaded) return fail(SDM_ERR_STATE, "keyframe slot %d not uploaded", kfs[i]);
+        CU(cudaMemcpyAsync(h.data(), c->A.blk + (size_t)kfs[i] * words, words * 4, cudaMemcpyDeviceToHost, c->s_compute));
+        CU(cudaStreamSynchronize(c->s_compute));
+        for (size_t w = 0; w < words; ++w) *blocks += (uint64_t)__builtin_popcount(h[w]);
+    }
+    return SDM_OK;
+}
+
 // ---- the two hot loops ---------------------------------------------------------------------------
 int sdm_pass1(sdm_ctx* c, int n, const sdm_item* items)
 {
@@ -957,6 +993,7 @@ int sdm_pass1(sdm_ctx* c, int n, const sdm_item* items)
         KfState& k = c->kf[items[i].kf];
         if (k.rs_dense) {  // the slot's outputs were produced by the dense pass 2: drop stale non-candidate values
             const size_t P = c->npix, s = (size_t)items[i].kf;
+            RC(c->r_down.wait(c->s_compute, k.down_cp_id));  // a download of chk / pts may still be in flight (prepare_batch waited for rho / sigma only)
             CU(cudaMemsetAsync(c->A.rs + s * P, 0, P * sizeof(float2), c->s_compute));
             CU(cudaMemsetAsync(c->A.dpl + s * P, 0, P * sizeof(float), c->s_compute));
             CU(cudaMemsetAsync(c->A.spl + s * P, 0, P * sizeof(float), c->s_compute));
@@ -1126,6 +1163,53 @@ int sdm_download_keyframes(sdm_ctx* c, int n, const sdm_download_desc* d)
     return SDM_OK;
 }
 
+// device-visible address of a host pointer if it lies in pinned memory (cudaMallocHost / cudaHostRegister), else nullptr
+static float* pinned_dev_ptr(float* host)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    if (at.type != cudaMemoryTypeHost || !at.devicePointer) return nullptr;
+    return (float*)at.devicePointer;
+}
+
+// returns 1 when a destination plane is not pinned (nothing was enqueued), else SDM_OK / an error
+static int sparse_to_pinned(sdm_ctx* c, int n, const sdm_download_desc* d)
+{
+    std::vector<sdm::SparseDst> dst((size_t)n);
+    uint64_t need = 0;
+    for (int i = 0; i < n; ++i) {
+        sdm::SparseDst& t = dst[i];
+        t.slot = d[i].kf;
+        t.depth = t.sigma = t.checked = t.points = nullptr;
+        t.depth_step = d[i].depth_step; t.sigma_step = d[i].sigma_step;
+        t.checked_step = d[i].checked_step; t.points_step = d[i].points_step;
+        if (d[i].depth && !(t.depth = pinned_dev_ptr(d[i].depth))) return 1;
+        if (d[i].sigma && !(t.sigma = pinned_dev_ptr(d[i].sigma))) return 1;
+        if (d[i].checked && !(t.checked = pinned_dev_ptr(d[i].checked))) return 1;
+        if (d[i].points && !(t.points = pinned_dev_ptr(d[i].points))) return 1;
+        need = std::max(need, c->kf[d[i].kf].comp_id);
+    }
+    cudaStream_t s = c->s_down;
+    RC(c->r_compute.wait(s, need));
+    const int H = c->cfg.height;
+    for (int i0 = 0; i0 < n; i0 += sdm::kSparseBatch) {
+        const int m = std::min(sdm::kSparseBatch, n - i0);
+        sdm::SparseBatch B;
+        memset(&B, 0, sizeof(B));
+        for (int i = 0; i < m; ++i) B.d[i] = dst[i0 + i];
+        sdm::k_sparse_rows<<<dim3(H, m), 32, 0, s>>>(c->A, c->P, B);
+        c->launches++;
+    }
+    CU(cudaGetLastError());
+    uint64_t id = 0;
+    RC(c->r_down.record(s, &id));
+    for (int i = 0; i < n; ++i) {
+        if (d[i].depth || d[i].sigma) c->kf[d[i].kf].down_ds_id = id;
+        if (d[i].checked || d[i].points) c->kf[d[i].kf].down_cp_id = id;
+    }
+    return SDM_OK;
+}
+
 static int scatter_init(sdm_ctx* c)
 {
     Scatter* S = new (std::nothrow) Scatter();
@@ -1161,6 +1245,11 @@ int sdm_scatter_keyframes(sdm_ctx* c, int n, const sdm_download_desc* d)
     }
     if (n <= 0) return SDM_OK;
     CU(cudaSetDevice(c->cfg.device));
+    {   // destination planes in pinned (device-visible) host memory: a kernel writes the candidate blocks of every row
+        // straight into them over PCIe - no staging, no host threads
+        int rc = sparse_to_pinned(c, n, d);
+        if (rc != 1) return rc;  // 1 = some plane is pageable: candidate records + host-side scatter below
+    }
     if (!c->scat) RC(scatter_init(c));
     Scatter* S = c->scat;
     cudaStream_t s = c->s_down;
@@ -1179,14 +1268,27 @@ int sdm_scatter_keyframes(sdm_ctx* c, int n, const sdm_download_desc* d)
             S->next = (stage + 1) % kScatStages;
         }
         ScatStage& st = S->st[stage];
-        RC(c->r_compute.wait(s, k.comp_id));
-        sdm::k_gather_sparse<<<(cnt + 255) / 256, 256, 0, s>>>(c->A, c->P, q.kf, cnt, st.dev);
-        CU(cudaGetLastError());
-        c->launches++;
-        CU(cudaMemcpyAsync(st.host, st.dev, (size_t)cnt * 28, cudaMemcpyDeviceToHost, s));
-        CU(cudaEventRecord(st.ev, s));
+        // from here until the job is queued a failure must hand the stage back, or the ring blocks when it wraps
+        auto release = [&](int rc) {
+            {
+                std::lock_guard<std::mutex> lk(S->mu);
+                st.free_ = true;
+            }
+            S->cv_free.notify_all();
+            return rc;
+        };
         uint64_t id = 0;
-        RC(c->r_down.record(s, &id));
+        int rc = c->r_compute.wait(s, k.comp_id);
+        if (rc == SDM_OK) {
+            sdm::k_gather_sparse<<<(cnt + 255) / 256, 256, 0, s>>>(c->A, c->P, q.kf, cnt, st.dev);
+            cudaError_t e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaMemcpyAsync(st.host, st.dev, (size_t)cnt * 28, cudaMemcpyDeviceToHost, s);
+            if (e == cudaSuccess) e = cudaEventRecord(st.ev, s);
+            if (e != cudaSuccess) rc = fail(SDM_ERR_CUDA, "sdm_scatter_keyframes: %s", cudaGetErrorString(e));
+        }
+        if (rc == SDM_OK) rc = c->r_down.record(s, &id);
+        if (rc != SDM_OK) return release(rc);
+        c->launches++;
         k.down_ds_id = id;
         k.down_cp_id = id;
         {
@@ -1540,6 +1642,22 @@ int sdm_exchange(sdm_ctx* c)
     return SDM_OK;
 }
 
+// results of a chunk to the host: the block-sparse kernel when the caller vouches for zero-initialised destination planes
+// and they are pinned, the dense DMA otherwise
+static int download(sdm_ctx* c, int n, const sdm_download_desc* d, bool sparse)
+{
+    if (sparse) {
+        bool ok = true;
+        for (int i = 0; i < n && ok; ++i) ok = slot_ok(c, d[i].kf) && !c->kf[d[i].kf].rs_dense && !c->kf[d[i].kf].split_stale;
+        if (ok) {
+            CU(cudaSetDevice(c->cfg.device));
+            const int rc = sparse_to_pinned(c, n, d);
+            if (rc != 1) return rc;
+        }
+    }
+    return sdm_download_keyframes(c, n, d);
+}
+
 // ---- one SemiDenseLoop as a pipeline ---------------------------------------------------------------
 int sdm_run_loop(sdm_ctx* c, const sdm_loop* L)
 {
@@ -1595,7 +1713,7 @@ int sdm_run_loop(sdm_ctx* c, const sdm_loop* L)
                 if (L->down2) dl.push_back(L->down2[idx[i0 + i]]);
             }
             RC(sdm_pass2(c, (int)m, batch.data()));
-            if (!dl.empty()) RC(sdm_download_keyframes(c, (int)dl.size(), dl.data()));
+            if (!dl.empty()) RC(download(c, (int)dl.size(), dl.data(), L->sparse_download != 0));
         }
         return SDM_OK;
     };
@@ -1614,7 +1732,7 @@ int sdm_run_loop(sdm_ctx* c, const sdm_loop* L)
                 next_up = need + 1;
             }
             RC(sdm_pass1(c, m, L->pass1 + i0));
-            if (L->down1) RC(sdm_download_keyframes(c, m, L->down1 + i0));
+            if (L->down1) RC(download(c, m, L->down1 + i0, L->sparse_download != 0));
         }
         // pass 2 of the work orders whose pass-1 inputs are all queued, one chunk behind: the newest chunk's pass 1 is
         // queued first so that the SMs never wait for a download

@@ -64,6 +64,8 @@ struct DevArena {
     float* dpl;  // dense depth_map_ plane   } copies of rs.x / rs.y kept for the D2H path, so a download is
     float* spl;  // dense depth_sigma_ plane } pure DMA (no de-interleave kernel competing for SMs)
     float2* rs2;  // second (rho,sigma) plane of the intra ping-pong: zero outside the candidate pixels
+    uint32_t* blk;  // [slot][H][blk_words] bit b of a row: the 16-pixel block b holds a candidate pixel (k_pack; k_sparse_rows)
+    int blk_words;  // words per row = ceil(ceil(W / 16) / 32)
     uint8_t* skip;  // [slot][kSkipBins][P] skip distances of the third-generation scan loop (k_skip); nullptr = not built
     size_t P;  // pixels per plane
 };
@@ -74,8 +76,8 @@ struct DevPair {
     float t[3];
     float rot;
     int slot;
-    int pad[3];
-};  // 26 words
+    float K2[4];  // the neighbour's own fx fy cx cy: InterKeyFrameDepthChecking projects with pKFj->GetCalibrationMatrix() (:1172)
+};  // 27 words
 
 struct DevItem {
     int kf;
@@ -344,10 +346,53 @@ __device__ __forceinline__ float2 encode_theta_pair(float a0, float a1)
 #endif
 constexpr int kTileW = SDM_TILE_W, kTileH = 256 / SDM_TILE_W;
 
-__global__ void __launch_bounds__(256) k_pack(DevArena A, DevParams P, int slot, const uint8_t* __restrict__ im,
-                                              const float* __restrict__ grad, const float* __restrict__ theta,
-                                              const int32_t* __restrict__ edge)
+// A batch of keyframes packed by ONE launch of each packing kernel (grid.z = keyframe): per keyframe the slot and the
+// staging planes its H2D landed in.  (One launch per keyframe left the stream idle between 5 launches per keyframe:
+// 6.9 ms of stream time per 200 keyframes for 1.9 ms of kernel time.)
+constexpr int kPackBatch = 24;
+struct PackBatch {
+    int slot[kPackBatch];
+    const uint8_t* im[kPackBatch];
+    const float* grad[kPackBatch];   // nullptr: GradImg / GradTheta are produced from im (k_pack_image)
+    const float* theta[kPackBatch];
+    const int32_t* edge[kPackBatch];  // nullptr: every pixel passes :454
+};
+
+// per-slot counters and block masks back to zero before a batch is packed
+__global__ void __launch_bounds__(256) k_pack_reset(DevArena A, DevParams P, PackBatch B)
 {
+    const int slot = B.slot[blockIdx.x];
+    if (threadIdx.x == 0) { A.cand_count[slot] = 0; A.plane_irregular[slot] = 0; }
+    uint32_t* blk = A.blk + (size_t)slot * P.H * A.blk_words;
+    for (int i = threadIdx.x; i < P.H * A.blk_words; i += blockDim.x) blk[i] = 0u;
+}
+
+// Which 16-pixel blocks of each row hold a candidate: every output plane of the path is zero outside the candidate
+// pixels, so a download into zero-initialised host planes only has to move these blocks (k_sparse_rows).
+constexpr int kBlkPx = 16;
+__device__ __forceinline__ void mark_blocks(const DevArena& A, const DevParams& P, int slot, int x, int y, bool in, bool is_cand,
+                                            unsigned bal, int lane)
+{
+    if (!A.blk) return;
+    uint32_t* row = A.blk + ((size_t)slot * P.H + (in ? y : 0)) * A.blk_words;
+    if (kTileW == 32) {  // a warp = 32 consecutive pixels of one row = two blocks: one atomic per warp
+        const unsigned two = ((bal & 0xffffu) ? 1u : 0u) | ((bal >> 16) ? 2u : 0u);
+        const int b0 = (x - lane) / kBlkPx;  // lane 0's block (x - lane is a multiple of 32)
+        if (lane == 0 && two && y < P.H) atomicOr(&row[b0 >> 5], two << (b0 & 31));
+    } else if (is_cand) {
+        const int b = x / kBlkPx;
+        atomicOr(&row[b >> 5], 1u << (b & 31));
+    }
+}
+
+__global__ void __launch_bounds__(256) k_pack(DevArena A, DevParams P, PackBatch B)
+{
+    const int slot = B.slot[blockIdx.z];
+    const uint8_t* __restrict__ im = B.im[blockIdx.z];
+    const float* __restrict__ grad = B.grad[blockIdx.z];
+    const float* __restrict__ theta = B.theta[blockIdx.z];
+    const int32_t* __restrict__ edge = B.edge[blockIdx.z];
+    if (grad == nullptr) return;  // this keyframe belongs to k_pack_image
     __shared__ int s_wcount[8];
     __shared__ int s_base;
     // a block packs one tile of kTileW x kTileH pixels; a warp covers kTileW x (32 / kTileW) of them
@@ -380,6 +425,7 @@ __global__ void __launch_bounds__(256) k_pack(DevArena A, DevParams P, int slot,
         is_cand = (edge == nullptr || edge[i0] >= 0) && !(g0 <= P.lambdaG);
     }
     const unsigned bal = __ballot_sync(SDM_FULL, is_cand);
+    mark_blocks(A, P, slot, x, y, in, is_cand, bal, lane);
     // scan_pixel_lane<2> relies on orientations in [0, 360] (what cv::phase produces) and finite gradients; anything
     // else selects the first-generation loop for the keyframes that touch this slot
     if (__any_sync(SDM_FULL, irregular) && lane == 0) atomicOr(&A.plane_irregular[slot], 1);
@@ -424,9 +470,12 @@ __device__ __forceinline__ float2 scharr_mag_phase(const uint8_t* __restrict__ i
     return make_float2(sqrtf(gx * gx + gy * gy), fast_atan2_deg(gy, gx));
 }
 
-__global__ void __launch_bounds__(256)
-k_pack_image(DevArena A, DevParams P, int slot, const uint8_t* __restrict__ im, const int32_t* __restrict__ edge)
+__global__ void __launch_bounds__(256) k_pack_image(DevArena A, DevParams P, PackBatch B)
 {
+    const int slot = B.slot[blockIdx.z];
+    const uint8_t* __restrict__ im = B.im[blockIdx.z];
+    const int32_t* __restrict__ edge = B.edge[blockIdx.z];
+    if (B.grad[blockIdx.z] != nullptr) return;  // this keyframe's planes were uploaded: k_pack
     __shared__ float2 s_gt[9][32];
     __shared__ int s_wcount[8];
     __shared__ int s_base;
@@ -466,6 +515,7 @@ k_pack_image(DevArena A, DevParams P, int slot, const uint8_t* __restrict__ im, 
         is_cand = (edge == nullptr || edge[i0] >= 0) && !(g0.x <= P.lambdaG);
     }
     const unsigned bal = __ballot_sync(SDM_FULL, is_cand);
+    mark_blocks(A, P, slot, x, y, in, is_cand, bal, lane);
     if (lane == 0) s_wcount[warp] = __popc(bal);
     __syncthreads();
     if (warp == 0 && lane == 0) {
@@ -503,19 +553,20 @@ __global__ void k_split_tex(const float4* __restrict__ tex, float* __restrict__ 
 // ---------------------------------------------------------------------------------------------
 constexpr float kSkipBinDeg = 360.0f / kSkipBins;
 
-constexpr int kSkipWarps = 4;
-__global__ void __launch_bounds__(32 * kSkipWarps) k_skip(DevArena A, DevParams P, int slot)
+// One block = 256 consecutive pixels of one row: each warp evaluates the texels of its own 32-pixel chunk and of the
+// chunk 256 pixels further right (the look-ahead a capped distance needs), one ballot per orientation bin into shared
+// memory; then every thread reads its distances off the mask words.  No serial dependency between chunks.
+constexpr int kSkipSpan = 256;
+__global__ void __launch_bounds__(kSkipSpan) k_skip(DevArena A, DevParams P, PackBatch B)
 {
-    const int lane = threadIdx.x & 31;
-    const int y = blockIdx.x * kSkipWarps + (threadIdx.x >> 5);
-    if (y >= P.H) return;
+    const int slot = B.slot[blockIdx.z];
+    __shared__ unsigned s_m[kSkipBins][2 * kSkipSpan / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int y = blockIdx.y, x0 = blockIdx.x * kSkipSpan;
     const float4* __restrict__ row = A.tex + (size_t)slot * A.P + (size_t)y * P.W;
-    uint8_t* __restrict__ out = A.skip + (size_t)slot * kSkipBins * A.P + (size_t)y * P.W;  // + q * A.P: plane of bin q
-    int carry[kSkipBins];  // per bin: distance from the first column right of the current chunk to the next set texel
-#pragma unroll
-    for (int q = 0; q < kSkipBins; ++q) carry[q] = 255;
-    for (int c0 = ((P.W - 1) / 32) * 32; c0 >= 0; c0 -= 32) {
-        const int x = c0 + lane;
+    for (int half = 0; half < 2; ++half) {
+        const int ch = warp + half * (kSkipSpan / 32);
+        const int x = x0 + ch * 32 + lane;
         bool g1 = false;
         float c = 0.f, h = 0.f;
         if (x < P.W) {
@@ -531,13 +582,30 @@ __global__ void __launch_bounds__(32 * kSkipWarps) k_skip(DevArena A, DevParams 
             float dist = fabsf(c - ((float)q + 0.5f) * kSkipBinDeg);  // c in [0, 540), bin centre in (0, 360)
             if (dist > 360.f) dist -= 360.f;
             if (dist > 180.f) dist = 360.f - dist;
-            const bool m = g1 && (dist < h + (0.5f * kSkipBinDeg + 45.f + 0.05f));
-            const unsigned bal = __ballot_sync(SDM_FULL, m);
-            const unsigned higher = (bal >> lane) >> 1;
-            const int sd = min(higher ? __ffs(higher) : 32 - lane + carry[q], 255);
-            if (x < P.W) out[(size_t)q * A.P + x] = (uint8_t)sd;
-            carry[q] = bal ? __ffs(bal) - 1 : min(carry[q] + 32, 255);
+            const unsigned bal = __ballot_sync(SDM_FULL, g1 && (dist < h + (0.5f * kSkipBinDeg + 45.f + 0.05f)));
+            if (lane == 0) s_m[q][ch] = bal;
         }
+    }
+    __syncthreads();
+    const int x = x0 + warp * 32 + lane;
+    if (x >= P.W) return;
+    uint8_t* __restrict__ out = A.skip + (size_t)slot * kSkipBins * A.P + (size_t)y * P.W + x;  // + q * A.P: plane of bin q
+#pragma unroll
+    for (int q = 0; q < kSkipBins; ++q) {
+        const unsigned higher = (s_m[q][warp] >> lane) >> 1;
+        int sd;
+        if (higher) {
+            sd = __ffs(higher);
+        } else {
+            sd = 32 - lane;
+            int k = warp + 1;
+            for (; k < 2 * kSkipSpan / 32; ++k) {
+                const unsigned v = s_m[q][k];
+                if (v) { sd += __ffs(v) - 1; break; }
+                sd += 32;
+            }
+        }
+        out[(size_t)q * A.P] = (uint8_t)min(sd, 255);  // (nothing set within the look-ahead: >= 257 - lane + ... > 255)
     }
 }
 
@@ -977,18 +1045,11 @@ __device__ __forceinline__ int scan_columns3(const float4* __restrict__ texw2, c
     unsigned idxn = __float_as_uint(r) * Wm + k;
     float4 tn = __ldg(reinterpret_cast<const float4*>(tb + (size_t)idxn * 16));
     unsigned sn = __ldg(reinterpret_cast<const uint8_t*>(sb + (size_t)idxn));
-#ifdef SDM_SCAN3_PREFETCH_IM
-    uchar2 in = __ldg(reinterpret_cast<const uchar2*>(ib + (size_t)idxn * 2));
-#endif
 #pragma unroll kScan2Unroll
     while (n > 0) {
         const float4 t = tn;
         const float w1 = w1n, w0 = 1.0f - w1n;
-#ifdef SDM_SCAN3_PREFETCH_IM
-        const uchar2 i2 = in;
-#else
         const unsigned idx = idxn;
-#endif
         const int ncur = n;
         // advance: as far as the skip byte and the row allow, never past column ub + 1 (the last valid address)
         const float rem = up ? w0 : w1;
@@ -1003,9 +1064,6 @@ __device__ __forceinline__ int scan_columns3(const float4* __restrict__ texw2, c
         idxn = __float_as_uint(r) * Wm + k;
         tn = __ldg(reinterpret_cast<const float4*>(tb + (size_t)idxn * 16));
         sn = __ldg(reinterpret_cast<const uint8_t*>(sb + (size_t)idxn));
-#ifdef SDM_SCAN3_PREFETCH_IM
-        in = __ldg(reinterpret_cast<const uchar2*>(ib + (size_t)idxn * 2));
-#endif
         const float2 w01 = make_float2(w0, w1);
         const float2 gp = __fmul2_rn(make_float2(t.x, t.y), w01);
         const float g2 = gp.x + gp.y;
@@ -1019,9 +1077,7 @@ __device__ __forceinline__ int scan_columns3(const float4* __restrict__ texw2, c
         const float d2 = gth - th_line;
         const float ang = d2 < 0.f ? d2 + 360.f : d2;  // condition 2
         if (fabsf(fabsf(ang - 180.f) - 90.f) <= 10.f) continue;
-#ifndef SDM_SCAN3_PREFETCH_IM
         const uchar2 i2 = __ldg(reinterpret_cast<const uchar2*>(ib + (size_t)idx * 2));
-#endif
         const float2 ip = __fmul2_rn(make_float2((float)i2.x, (float)i2.y), w01);
         const float2 res = __fadd2_rn(make_float2(pixel, gradc), make_float2(-(ip.x + ip.y), -g2));
         const float2 sq = __fmul2_rn(res, res);
@@ -1621,8 +1677,8 @@ __device__ __forceinline__ float inter_check_pixel(const DevArena& A, const DevP
         const float X0 = (float)((double)s0 * alpha + (double)g.t[0]);
         const float X1 = (float)((double)s1 * alpha + (double)g.t[1]);
         const float X2 = (float)((double)s2 * alpha + (double)g.t[2]);
-        const float U = fx * X0 + 0.f * X1 + cx * X2;
-        const float V = 0.f * X0 + fy * X1 + cy * X2;
+        const float U = g.K2[0] * X0 + 0.f * X1 + g.K2[2] * X2;
+        const float V = 0.f * X0 + g.K2[1] * X1 + g.K2[3] * X2;
         const float Wz = 0.f * X0 + 0.f * X1 + 1.0f * X2;
         // (float)(1.0 / (double)Wz) == 1.0f / Wz: rounding a double quotient of two floats to float cannot differ
         // from the float quotient (53 >= 2*24 + 2: double rounding is innocuous for division, Figueroa 1995)
@@ -1874,7 +1930,59 @@ __global__ void __launch_bounds__(256) k_gather_sparse(DevArena A, DevParams P, 
     f[4 * (size_t)n + 3 * (size_t)i + 2] = A.pts[3 * pi + 2];
 }
 
-// candidate counts of freshly packed slots into host-mapped pinned memory (no DMA engine involved)
+// ---------------------------------------------------------------------------------------------
+// Block-sparse download straight into the caller's PINNED host planes (sdm_scatter_keyframes, sdm_run_loop with
+// sparse_download): for every row only the 16-pixel blocks that hold a candidate (A.blk) are written, with coalesced
+// stores over PCIe; everything else of the destination keeps its zeros (KeyFrame.cc:78-81).  On the bench scene 53 % of
+// the blocks hold a candidate, i.e. 47 % of the D2H bytes of a dense DMA never move.  One warp per (keyframe, row):
+// two blocks per step for the 4-byte planes (lanes 0-15 / 16-31), one block of 48 floats per 1.5 steps for the points.
+// ---------------------------------------------------------------------------------------------
+constexpr int kSparseBatch = 16;
+struct SparseDst {
+    int slot;
+    float *depth, *sigma, *checked, *points;  // device-visible addresses of the pinned host planes (or nullptr)
+    size_t depth_step, sigma_step, checked_step, points_step;
+};
+struct SparseBatch {
+    SparseDst d[kSparseBatch];
+};
+// One warp (= one block: small enough to slip in next to the resident blocks of a persistent pass kernel) per
+// (keyframe, row); it walks the row in 32-pixel chunks (two blocks), skips chunks whose two mask bits are clear, and
+// every lane moves its own pixel of the 4-byte planes and three floats of the chunk's 96 point floats.
+__global__ void __launch_bounds__(32) k_sparse_rows(DevArena A, DevParams P, SparseBatch B)
+{
+    const int lane = threadIdx.x;
+    const int y = blockIdx.x;
+    const SparseDst& D = B.d[blockIdx.y];
+    const size_t src = (size_t)D.slot * A.P + (size_t)y * P.W;
+    const uint32_t* mrow = A.blk + ((size_t)D.slot * P.H + y) * A.blk_words;
+    float* dd = D.depth ? reinterpret_cast<float*>(reinterpret_cast<char*>(D.depth) + (size_t)y * D.depth_step) : nullptr;
+    float* ds = D.sigma ? reinterpret_cast<float*>(reinterpret_cast<char*>(D.sigma) + (size_t)y * D.sigma_step) : nullptr;
+    float* dc = D.checked ? reinterpret_cast<float*>(reinterpret_cast<char*>(D.checked) + (size_t)y * D.checked_step) : nullptr;
+    float* dp = D.points ? reinterpret_cast<float*>(reinterpret_cast<char*>(D.points) + (size_t)y * D.points_step) : nullptr;
+    const int nchunk = (P.W + 31) / 32;
+    unsigned word = 0;
+    for (int c = 0; c < nchunk; ++c) {
+        if ((c & 15) == 0) word = mrow[c >> 4];  // 32 blocks = 16 chunks per mask word
+        const unsigned two = (word >> (2 * (c & 15))) & 3u;
+        if (!two) continue;
+        const int x = c * 32 + lane;
+        if (((two >> (lane >> 4)) & 1u) && x < P.W) {
+            if (dd) dd[x] = A.dpl[src + x];
+            if (ds) ds[x] = A.spl[src + x];
+            if (dc) dc[x] = A.chk[src + x];
+        }
+        if (dp) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int f = k * 32 + lane;            // float f of the chunk's 96 belongs to pixel f / 3
+                const int px = c * 32 + f / 3;
+                if (((two >> (f / 48)) & 1u) && px < P.W) dp[3 * c * 32 + f] = A.pts[3 * (src + c * 32) + f];
+            }
+        }
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Cross-GPU ordering of the inter-pass exchange without the host (sdm_exchange).  Every rank owns one XFlags block
 // in device memory that its peers map through CUDA IPC.  Owner: `done` = number of the last step whose pass-1 planes
@@ -1934,6 +2042,7 @@ __global__ void k_xwait_acks(XFlags* mine, unsigned step)
 }
 __global__ void k_xregister(XFlags* peer, int my_rank) { atomicOr_system(&peer->puller_mask, 1u << my_rank); }
 
+// candidate counts of freshly packed slots into host-mapped pinned memory (no DMA engine involved)
 constexpr int kSlotList = 24;
 struct SlotList {
     int s[kSlotList];

@@ -62,7 +62,7 @@ class DownloadDesc(C.Structure):
 class Loop(C.Structure):
     _fields_ = [("n_upload", C.c_int32), ("upload", C.POINTER(UploadDesc)), ("n_pass1", C.c_int32), ("pass1", C.POINTER(Item)),
                 ("down1", C.POINTER(DownloadDesc)), ("n_pass2", C.c_int32), ("pass2", C.POINTER(Item)),
-                ("down2", C.POINTER(DownloadDesc)), ("chunk", C.c_int32), ("exchange", C.c_int32)]
+                ("down2", C.POINTER(DownloadDesc)), ("chunk", C.c_int32), ("exchange", C.c_int32), ("sparse_download", C.c_int32)]
 
 
 SDM_PEER_HANDLE_BYTES = 192
@@ -80,7 +80,7 @@ class Stats(C.Structure):
 EXPORTS = [
     "sdm_default_config", "sdm_create", "sdm_destroy", "sdm_last_error", "sdm_version", "sdm_synchronize",
     "sdm_get_stats", "sdm_scan_generation", "sdm_host_alloc", "sdm_host_free", "sdm_upload_keyframe", "sdm_set_pose",
-    "sdm_set_intrinsics", "sdm_candidate_count", "sdm_pass1", "sdm_pass2", "sdm_update_points", "sdm_download", "sdm_download_async", "sdm_upload_keyframes", "sdm_download_keyframes", "sdm_scatter_keyframes", "sdm_export_points", "sdm_download_planes",
+    "sdm_set_intrinsics", "sdm_candidate_count", "sdm_candidate_blocks", "sdm_pass1", "sdm_pass2", "sdm_update_points", "sdm_download", "sdm_download_async", "sdm_upload_keyframes", "sdm_download_keyframes", "sdm_scatter_keyframes", "sdm_export_points", "sdm_download_planes",
     "sdm_upload_depth", "sdm_upload_checked", "sdm_depth_plane_ptr", "sdm_export_arena", "sdm_import_peer_arena", "sdm_pull_halo",
     "sdm_mark_pass1_done", "sdm_export_peer_handle", "sdm_import_peer", "sdm_set_halo", "sdm_exchange", "sdm_run_loop",
     "sdm_pair_geometry", "sdm_stereo_search_constraints", "sdm_search_range", "sdm_inter_chi_test",
@@ -117,6 +117,7 @@ def load() -> C.CDLL:
     lib.sdm_set_pose.argtypes = [vp, C.c_int, fp]
     lib.sdm_set_intrinsics.argtypes = [vp, C.c_int, fp]
     lib.sdm_candidate_count.argtypes = [vp, C.c_int, C.POINTER(C.c_int)]
+    lib.sdm_candidate_blocks.argtypes = [vp, C.c_int, ip, C.POINTER(C.c_uint64)]
     lib.sdm_pass1.argtypes = [vp, C.c_int, C.POINTER(Item)]
     lib.sdm_pass2.argtypes = [vp, C.c_int, C.POINTER(Item)]
     lib.sdm_update_points.argtypes = [vp, C.c_int, ip]
@@ -307,6 +308,12 @@ class Context:
         self._chk(self.lib.sdm_candidate_count(self.h, slot, C.byref(n)))
         return n.value
 
+    def candidate_blocks(self, slots) -> int:
+        a = np.ascontiguousarray(slots, np.int32)
+        n = C.c_uint64()
+        self._chk(self.lib.sdm_candidate_blocks(self.h, a.size, a.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(n)))
+        return int(n.value)
+
     # ---- passes
     def pass1(self, items):
         self._chk(self.lib.sdm_pass1(self.h, len(items), items))
@@ -489,7 +496,7 @@ class Context:
     def exchange(self):
         self._chk(self.lib.sdm_exchange(self.h))
 
-    def run_loop(self, upload=None, pass1=None, down1=None, pass2=None, down2=None, chunk=0, exchange=False):
+    def run_loop(self, upload=None, pass1=None, down1=None, pass2=None, down2=None, chunk=0, exchange=False, sparse=False):
         """sdm_run_loop: ctypes arrays (UploadDesc / Item / DownloadDesc) or None; enqueue only"""
         L = Loop()
         L.n_upload = len(upload) if upload is not None else 0
@@ -500,7 +507,7 @@ class Context:
         L.n_pass2 = len(pass2) if pass2 is not None else 0
         L.pass2 = pass2 if pass2 is not None else None
         L.down2 = down2 if down2 is not None else None
-        L.chunk, L.exchange = int(chunk), int(bool(exchange))
+        L.chunk, L.exchange, L.sparse_download = int(chunk), int(bool(exchange)), int(bool(sparse))
         self._keep_loop = (upload, pass1, down1, pass2, down2)
         self._chk(self.lib.sdm_run_loop(self.h, C.byref(L)))
 

@@ -101,7 +101,8 @@ int sdm_get_stats(sdm_ctx* ctx, sdm_stats* out);
  * arithmetic, but a lane jumps over columns that its skip-distance planes rule out), 2 = second generation (reference
  * thresholds lambdaL = 80 / lambdaTheta = 45 and the reciprocal form of x / theta verified for this theta at
  * sdm_create), 1 = first generation (any thresholds; also used per keyframe when an orientation plane holds values
- * outside [0, 360] or |rot| > 360).  env SDM_SCAN=lane1 | lane2 | lane3 forces one.  Results are bit-identical. */
+ * outside [0, 360] or |rot| > 360).  env SDM_SCAN=lane1 | lane2 | lane3 forces one; SDM_SCAN=warp selects the
+ * warp-per-pixel kernel of the survey's plan (kept for A/B, 2-4x slower; reported as 0).  Results are bit-identical. */
 int sdm_scan_generation(sdm_ctx* ctx);
 
 /* pinned host memory for asynchronous uploads/downloads (optional; any host pointer is accepted) */
@@ -145,6 +146,10 @@ int sdm_set_pose(sdm_ctx* ctx, int kf, const float Tcw[12]);
  * halo slot needs when only its pass-1 planes arrive over NVLink (no image upload) */
 int sdm_set_intrinsics(sdm_ctx* ctx, int kf, const float K[4]);
 int sdm_candidate_count(sdm_ctx* ctx, int kf, int* count); /* blocking */
+/* number of 16-pixel row blocks of the n keyframes that hold at least one candidate pixel: what a block-sparse download
+ * (sdm_scatter_keyframes into pinned planes, sdm_loop.sparse_download) moves, 16 * 24 bytes per block for the four planes;
+ * blocking */
+int sdm_candidate_blocks(sdm_ctx* ctx, int n, const int32_t* kfs, uint64_t* blocks);
 
 /* ---- the two hot loops --------------------------------------------------------------------- */
 /* replaces: SemiDenseLoop pass 1 body, :424-497 — ComputeFundamental, the omp pixel loop with
@@ -182,6 +187,9 @@ int sdm_download_keyframes(sdm_ctx* ctx, int n, const sdm_download_desc* desc);
  * (the stores of :483-484, :1290 and :725-727 all sit behind the candidate test of :454-456), so only those
  * pixels' records (28 bytes each instead of 24 bytes for every pixel) cross PCIe, and worker threads of the library
  * (env SDM_SCATTER_THREADS, default 6) write them into the caller's planes; every other element is left untouched.
+ * Destination planes in PINNED host memory (sdm_host_alloc, cudaHostRegister) take a faster route with the same
+ * contract: a kernel writes the 16-pixel blocks of every row that hold a candidate straight into them over PCIe (no
+ * records, no host threads).
  * On zero-initialised planes the result is identical to sdm_download_keyframes.  Asynchronous: the planes are
  * complete after sdm_synchronize.  Slots whose planes were written from outside (sdm_upload_depth) are refused
  * (SDM_ERR_STATE).  Blocks the caller only until the slot's candidate count is known (its upload has been packed). */
@@ -273,6 +281,11 @@ typedef struct {
     const sdm_download_desc* down2;
     int32_t chunk;    /* keyframes per pipeline chunk; <= 0: 4 (measured optimum on B200 + PCIe 5) */
     int32_t exchange; /* != 0: sdm_exchange between the passes; pass-2 work orders that read halo planes wait for it */
+    int32_t sparse_download; /* != 0: the destination planes are ZERO-INITIALISED the way KeyFrame's constructor leaves them
+                              * (KeyFrame.cc:78-81) - the contract of sdm_scatter_keyframes.  Planes in pinned host memory then
+                              * receive only the 16-pixel blocks that hold a candidate pixel, written by a kernel over PCIe
+                              * (about half the bytes of the dense DMA on textured scenes, far less with an edge mask);
+                              * pageable planes get the dense DMA.  Identical host planes either way. */
 } sdm_loop;
 int sdm_run_loop(sdm_ctx* ctx, const sdm_loop* loop);
 

@@ -116,6 +116,7 @@ int main(int argc, char** argv)
     if (const char* e = getenv("SDM_SHIM_RESULTS")) pm.SetResultsDir(e);
     if (const char* e = getenv("SDM_SHIM_CHUNK")) pm.SetPipelineChunk(atoi(e));
     if (const char* e = getenv("SDM_SHIM_HEADROOM")) pm.SetArenaHeadroom(atoi(e));
+    if (const char* e = getenv("SDM_SHIM_SPARSE")) pm.SetSparseDownloads(e[0] == '1');
     int hook_calls = 0;
     pm.SetEdgeMapHook([&hook_calls](KeyFrame*) { ++hook_calls; });  // where the reference calls DetectEdgeMap (:394-397)
 

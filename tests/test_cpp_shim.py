@@ -233,8 +233,8 @@ def test_shim_save_semidense_points_equals_the_reference_writer(shim_binary, tmp
     import ref_py
     if not ref_py.available():
         pytest.skip("needs /root/reference or a prebuilt oracle/_ref")
-    n, W, H, N = 12, 160, 120, 6
-    sc = synth.make_scene(n, W, H, N, seed=18, contrast=0.9)
+    n, W, H, N = 14, 160, 120, 6
+    sc = synth.make_scene(n, W, H, 9, seed=18, contrast=0.9)   # covisibility lists of 9: the bad keyframe is skipped over
     scene_path, out_path = str(tmp_path / "scene.bin"), str(tmp_path / "out.bin")
     bad = np.zeros(n, np.int32); bad[4] = 1
     _write_scene(scene_path, sc, N, 0, [], bad=bad)
@@ -246,6 +246,7 @@ def test_shim_save_semidense_points_equals_the_reference_writer(shim_binary, tmp
     monkeypatch.chdir(tmp_path)
     ref_file = ref_py.reference_save_points(sc.im, dev["sigma"], dev["checked"], dev["points"], flags, bad=bad)
     a, b = open(os.path.join(res, "semi_pointcloud.obj"), "rb").read(), open(ref_file, "rb").read()
+    assert flags[:, 1].sum() >= 8 and flags[4].sum() == 0
     assert len(b) > 100000 and a == b
 
 

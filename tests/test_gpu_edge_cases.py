@@ -104,7 +104,7 @@ def test_slot_reuse_and_partial_batches():
 
 def test_scan_generations_agree(monkeypatch):
     """the three generations of the column loop (SDM_SCAN=lane1 | lane2 | lane3; the first is also what any other
-    threshold set runs) give the oracle's bits"""
+    threshold set runs) and the warp-per-pixel kernel (SDM_SCAN=warp) give the oracle's bits"""
     sc = synth.make_scene(10, 320, 240, 6, seed=21, contrast=0.9)
     osc = run_oracle(sc)
     zero = {"depth": 0, "sigma": 0, "checked": 0, "points": 0}
@@ -112,7 +112,7 @@ def test_scan_generations_agree(monkeypatch):
     with api.Context(width=320, height=240, max_keyframes=sc.n) as ctx:
         assert ctx.scan_generation() in (2, 3)     # k_verify_div passed for THETA = 0.23f
         assert _bit_equal(run_device(sc, ctx=ctx), osc) == zero
-    for env, gen in (("lane1", 1), ("lane2", 2), ("lane3", 3)):
+    for env, gen in (("lane1", 1), ("lane2", 2), ("lane3", 3), ("warp", 0)):  # warp = the warp-per-pixel A/B kernel
         monkeypatch.setenv("SDM_SCAN", env)
         with api.Context(width=320, height=240, max_keyframes=sc.n) as ctx:
             assert ctx.scan_generation() == gen

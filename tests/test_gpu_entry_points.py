@@ -130,6 +130,49 @@ def test_planes_produced_on_the_device(scene):
         assert _bits(g, sc2.grad[0]) == 0 and _bits(t, sc2.theta[0]) == 0
 
 
+def test_device_planes_against_real_cv2_magnitude_and_phase(scene):
+    """SURVEY 8f-1 pinned to OpenCV itself: the planes k_pack_image produces from im_ against the REAL calls of
+    KeyFrame.cc:69-74 (cv2.Scharr x2, cv2.magnitude, cv2.phase(angleInDegrees=True); cv2 4.x of this image).  OpenCV's
+    SIMD magnitude / phase are not the scalar forms (and differ between calls on a multi-threaded host), so the bar is
+    what can be measured: <= 2 ulp on GradImg (SURVEY 8(c) saw 1 on its samples; cv2 4.13's magnitude reaches 2 on these
+    images), <= 3.1e-5 degrees on GradTheta - and, downstream, the accepted sets of a whole loop on OpenCV's planes vs
+    the device's planes differ by at most BASELINE's 0.1 %."""
+    cv2 = pytest.importorskip("cv2")
+    sc = scene
+    H, W = sc.shape
+    mag, ph = np.zeros_like(sc.grad), np.zeros_like(sc.theta)
+    for i in range(sc.n):
+        gx = cv2.Scharr(sc.im[i], cv2.CV_32F, 1, 0, scale=1 / 32.0)
+        gy = cv2.Scharr(sc.im[i], cv2.CV_32F, 0, 1, scale=1 / 32.0)
+        mag[i] = cv2.magnitude(gx, gy)
+        ph[i] = cv2.phase(gx, gy, angleInDegrees=True)
+    import copy
+    sc_cv = copy.copy(sc)
+    sc_cv.grad, sc_cv.theta = mag, ph
+    with api.Context(width=W, height=H, max_keyframes=sc.n) as ctx:
+        ctx.upload_keyframes(ctx.upload_descs(sc, range(sc.n), images_only=True))
+        worst_ulp, worst_deg = 0, 0.0
+        for i in range(sc.n):
+            g, t = ctx.download_planes(i)
+            ulp = np.abs(g.view(np.int32).astype(np.int64) - mag[i].view(np.int32).astype(np.int64))  # both >= +0
+            worst_ulp = max(worst_ulp, int(ulp.max()))
+            d = np.abs(t.astype(np.float64) - ph[i].astype(np.float64))
+            worst_deg = max(worst_deg, float(np.minimum(d, 360.0 - d).max()))
+        assert worst_ulp <= 2, worst_ulp
+        assert worst_deg <= 3.1e-5, worst_deg
+        items = api.make_items(range(sc.n), sc.nbr_idx, sc.rot, sc.min_depth, sc.max_depth)
+        ctx.pass1(items); ctx.pass2(items)
+        dev = [ctx.download(i) for i in range(sc.n)]
+        ctx.upload_keyframes(ctx.upload_descs(sc_cv, range(sc.n)))   # OpenCV's own planes through the same loop
+        ctx.pass1(items); ctx.pass2(items)
+        ocv = [ctx.download(i) for i in range(sc.n)]
+    for key in ("depth", "checked"):
+        a = np.stack([d[key] for d in dev]) > 0
+        b = np.stack([d[key] for d in ocv]) > 0
+        assert b.sum() > 10000
+        assert (a != b).sum() <= 1e-3 * b.sum(), (key, int((a != b).sum()), int(b.sum()))
+
+
 def test_scatter_download_equals_dense_download(scene):
     """sdm_scatter_keyframes (candidate records over PCIe + host-side scatter by the library's worker threads) into
     zero-initialised planes == sdm_download_keyframes == the oracle, bit for bit; row-pitched destination planes;

@@ -65,3 +65,64 @@ def test_run_loop_with_different_pass_lists_and_resident_planes():
             bad = api.make_items([0], sc.nbr_idx, sc.rot, sc.min_depth, sc.max_depth)
             bad[0].nbr[0] = 99
             ctx.run_loop(pass1=bad)
+
+
+def _pinned(lib, shape, keep):
+    n = int(np.prod(shape)) * 4
+    p = C.c_void_p()
+    assert lib.sdm_host_alloc(C.byref(p), n) == 0
+    keep.append(p)
+    a = np.frombuffer((C.c_char * n).from_address(p.value), dtype=np.float32).reshape(shape)
+    a[:] = 0
+    return a
+
+
+@pytest.mark.parametrize("W,H", [(320, 240), (203, 77)])
+def test_block_sparse_download_into_pinned_planes(W, H):
+    """sdm_loop.sparse_download / sdm_scatter_keyframes with PINNED zero-initialised destination planes: a kernel writes
+    only the 16-pixel row blocks that hold a candidate over PCIe.  Same host planes as the dense DMA, bit for bit (odd
+    width: partial last block, rows whose mask word is empty); row-pitched destinations; fewer bytes than the dense copy;
+    pageable planes with the same flag fall back to the dense DMA."""
+    sc = synth.make_scene(10, W, H, 6, seed=33, contrast=0.9)
+    ref = run_device(sc)
+    keep = []
+    lib = api.load()
+    pad = 8
+    out = {k: _pinned(lib, (sc.n, H, (W + pad) * (3 if k == "points" else 1)), keep) for k in ("depth", "sigma", "checked", "points")}
+    view = {k: (out[k][:, :, :3 * W].reshape(sc.n, H, W, 3) if k == "points" else out[k][:, :, :W]) for k in out}
+    try:
+        with api.Context(width=W, height=H, max_keyframes=sc.n) as ctx:
+            items = api.make_items(range(sc.n), sc.nbr_idx, sc.rot, sc.min_depth, sc.max_depth)
+            up = ctx.upload_descs(sc, range(sc.n))
+            d1 = (api.DownloadDesc * sc.n)(); d2 = (api.DownloadDesc * sc.n)(); d4 = (api.DownloadDesc * sc.n)()
+            for j in range(sc.n):
+                d1[j].kf = d2[j].kf = d4[j].kf = j
+                for d, names in ((d1[j], ("depth", "sigma")), (d2[j], ("checked", "points")), (d4[j], ("depth", "sigma", "checked", "points"))):
+                    for nm in names:
+                        setattr(d, nm, out[nm][j].ctypes.data)
+                        setattr(d, nm + "_step", out[nm][j].strides[0])
+            ctx.run_loop(upload=up, pass1=items, down1=d1, pass2=items, down2=d2, chunk=3, sparse=True)
+            ctx.synchronize()
+            for k in out:
+                assert np.array_equal(view[k].view(np.uint32), ref[k].view(np.uint32)), k
+                assert not out[k][:, :, (3 * W if k == "points" else W):].any(), "padding columns untouched"
+            nblk = ctx.candidate_blocks(range(sc.n))
+            assert 0 < nblk <= sc.n * H * ((W + 15) // 16)
+            for k in out:
+                out[k][:] = 0
+            ctx.scatter_keyframes(d4)            # the entry point itself: pinned planes take the kernel route
+            ctx.synchronize()
+            for k in out:
+                assert np.array_equal(view[k].view(np.uint32), ref[k].view(np.uint32)), k
+            # pageable destination + sparse flag: dense DMA
+            pg = {k: np.full((sc.n, H, W) + ((3,) if k == "points" else ()), np.nan, np.float32) for k in ("checked",)}
+            d3 = (api.DownloadDesc * sc.n)()
+            for j in range(sc.n):
+                d3[j].kf = j
+                d3[j].checked, d3[j].checked_step = pg["checked"][j].ctypes.data, pg["checked"][j].strides[0]
+            ctx.run_loop(pass1=items, pass2=items, down2=d3, sparse=True)
+            ctx.synchronize()
+            assert np.array_equal(pg["checked"].view(np.uint32), ref["checked"].view(np.uint32))
+    finally:
+        for p in keep:
+            lib.sdm_host_free(p)

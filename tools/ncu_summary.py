@@ -1,5 +1,7 @@
 """Summarise an .ncu-rep (read here, no GPU needed) into profiles/<name>.md + .json.
-usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r01_scan"""
+usage: python tools/ncu_summary.py gpurun_out/prof.ncu-rep profiles/r01_scan [--traffic-config N]
+--traffic-config N also records the scan kernel's DRAM bytes per launch in profiles/traffic.json under "configN":
+bench.py reports that number as roofline.traffic for BASELINE config N."""
 import csv
 import io
 import json
@@ -57,5 +59,28 @@ def main(rep, out):
     print(json.dumps([{k: v for k, v in d.items() if "@" not in k} for d in res], indent=1)[:3000])
 
 
+def record_traffic(out, config):
+    import os
+    res = json.load(open(out + ".json"))
+    scan = [d for d in res if "k_pass1" in d["kernel"] and "dram_bytes_per_launch" in d]
+    if not scan:
+        return
+    path = os.path.join(os.path.dirname(os.path.abspath(out)), "traffic.json")
+    try:
+        t = json.load(open(path))
+        if "k_pass1_dram_bytes_per_launch" in t:  # round-1 layout
+            t = {}
+    except Exception:
+        t = {}
+    t[f"config{config}"] = {"k_pass1_dram_bytes_per_launch": scan[0]["dram_bytes_per_launch"], "kernel": scan[0]["kernel"],
+                            "duration_ms_under_ncu": scan[0].get("gpu__time_duration.sum"),
+                            "source": os.path.basename(out) + ".json (tools/ncu_summary.py from the .ncu-rep of `ncu --set full "
+                                      f"--clock-control none ... python bench.py --config {config} --steps 1 --warmup 3 --no-e2e "
+                                      "--no-cpu-baseline --no-hot-spin`)"}
+    json.dump(t, open(path, "w"), indent=1)
+
+
 if __name__ == "__main__":
     main(sys.argv[1], sys.argv[2])
+    if "--traffic-config" in sys.argv:
+        record_traffic(sys.argv[2], int(sys.argv[sys.argv.index("--traffic-config") + 1]))
