@@ -485,10 +485,23 @@ def main_ours(a, rank, world, local_rank):
     if n_loc * W * H * 26 < 2 * L2_BYTES:  # small workloads: overwrite a buffer larger than L2 between timed steps
         flush = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device=f"cuda:{local_rank}")
 
+    dbg = bool(os.environ.get("SDM_BENCH_DEBUG"))
+
     def step():
+        if dbg:
+            ctx.mark(2); t = [time.perf_counter()]
         ctx.pass1(items)
+        if dbg:
+            ctx.mark(3); t.append(time.perf_counter())
         exchange()
+        if dbg:
+            ctx.mark(4); t.append(time.perf_counter())
         ctx.pass2(items)
+        if dbg:
+            ctx.mark(5); t.append(time.perf_counter())
+            ctx.synchronize()
+            print(f"rank {rank} step: host issue ms (pass1, exchange, pass2) {[round(1e3 * (b - a_), 2) for a_, b in zip(t, t[1:])]}, "
+                  f"device ms {[round(ctx.elapsed_ms(i, i + 1), 2) for i in (2, 3, 4)]}", file=sys.stderr)
         if world > 1 and host_exchange:
             ctx.synchronize(); barrier()
 

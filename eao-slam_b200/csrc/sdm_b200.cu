@@ -282,7 +282,10 @@ struct sdm_ctx {
     bool trace = false;
     cudaEvent_t trace_base = nullptr;
     std::vector<TraceRec> trace_recs;
-    int scan_warp_per_pixel = 0;  // developer A/B knob (env SDM_SCAN=warp): the warp-per-pixel scan kernel
+    int scan_warp_per_pixel = 0;  // developer A/B knob (env SDM_SCAN=warp): the warp-per-pixel scan kernel; 2 = warp_tma:
+                                  // the same with neighbour tiles staged in shared memory by TMA (k_pass1_tma)
+    CUtensorMap tex_map;          // the texel arena as a TMA tensor {4 floats, W, slots * H} (warp_tma only)
+    int grid_pass1_tma = 0;
 };
 
 namespace {
@@ -347,11 +350,15 @@ int ensure_items(sdm_ctx* c, int n)
 // staging for n work orders whose previous user (a pass) has finished
 int acquire_item_stage(sdm_ctx* c, int n, ItemStage** out)
 {
+    // a free stage that is already large enough, else any free one (allocated below): in steady state a loop cycles
+    // through the two or three stages its passes keep in flight instead of growing all kItemStages (each allocation is a
+    // cudaMallocHost + two cudaMallocs, milliseconds with the device idle, for work orders of a thousand keyframes)
     ItemStage* st = nullptr;
-    for (int k = 0; k < kItemStages; ++k) {
-        ItemStage& cand = c->ist[(c->ist_next + k) % kItemStages];
-        if (c->r_compute.done(cand.busy)) { st = &cand; break; }
-    }
+    for (int pass = 0; pass < 2 && !st; ++pass)
+        for (int k = 0; k < kItemStages; ++k) {
+            ItemStage& cand = c->ist[(c->ist_next + k) % kItemStages];
+            if ((pass == 1 || cand.cap >= n) && c->r_compute.done(cand.busy)) { st = &cand; break; }
+        }
     if (!st) {
         st = &c->ist[c->ist_next];
         RC(c->r_compute.host_sync(st->busy));
@@ -613,7 +620,7 @@ static int create_impl(sdm_ctx* c)
     const size_t P = (size_t)cfg.width * cfg.height;
     const size_t n = (size_t)cfg.max_keyframes;
     c->npix = P;
-    if (const char* e = getenv("SDM_SCAN")) c->scan_warp_per_pixel = (strcmp(e, "warp") == 0);
+    if (const char* e = getenv("SDM_SCAN")) c->scan_warp_per_pixel = strcmp(e, "warp") == 0 ? 1 : (strcmp(e, "warp_tma") == 0 ? 2 : 0);
     if (const char* e = getenv("SDM_TRACE")) c->trace = (e[0] == '1');
     c->kf.assign(n, KfState());
     sdm::DevParams& D = c->P;
@@ -705,6 +712,28 @@ static int create_impl(sdm_ctx* c)
     c->grid_pass2 = std::max(1, occ) * prop.multiProcessorCount;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sdm::k_intra_cand, sdm::kChunk, 0));
     c->grid_intra = std::max(1, occ) * prop.multiProcessorCount;
+    if (c->scan_warp_per_pixel == 2) {
+        // TMA descriptor of the texel arena; cuTensorMapEncodeTiled comes from the driver through the runtime (no -lcuda)
+        typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        if (!fn || qres != cudaDriverEntryPointSuccess) return fail(SDM_ERR_CUDA, "cuTensorMapEncodeTiled not available");
+        const cuuint64_t dims[3] = {4, (cuuint64_t)cfg.width, (cuuint64_t)n * cfg.height};
+        const cuuint64_t strides[2] = {16, (cuuint64_t)16 * cfg.width};  // bytes, dims 1 and 2
+        const cuuint32_t box[3] = {4, (cuuint32_t)sdm::kTmaBW, (cuuint32_t)sdm::kTmaBH};
+        const cuuint32_t estr[3] = {1, 1, 1};
+        const CUresult r = ((EncodeFn)fn)(&c->tex_map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, A.tex, dims, strides, box, estr,
+                                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return fail(SDM_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+        const int smem = sdm::kTmaWarps * sdm::kTmaTileBytes;
+        CU(cudaFuncSetAttribute(sdm::k_pass1_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sdm::k_pass1_tma, sdm::kTmaWarps * 32, smem));
+        c->grid_pass1_tma = std::max(1, occ) * prop.multiProcessorCount;
+    }
     // second-generation scan loop (scan_pixel_lane<2>): the reference's constants only, and only if its reciprocal
     // form of x / 0.23f is IEEE-exact over the whole range the loop can produce (checked here, ~2 ms)
     D.scan2 = 0;
@@ -1014,7 +1043,10 @@ int sdm_pass1(sdm_ctx* c, int n, const sdm_item* items)
     sdm::k_plan<<<1, 1024, 0, c->s_compute>>>(plan, c->d_items, c->A.cand_count, c->d_stats);
     CU(cudaEventRecord(c->ev_p1[0], c->s_compute));
     trace_begin(c, c->s_compute, "pass1", n);
-    if (c->scan_warp_per_pixel)
+    if (c->scan_warp_per_pixel == 2)
+        sdm::k_pass1_tma<<<c->grid_pass1_tma, sdm::kTmaWarps * 32, sdm::kTmaWarps * sdm::kTmaTileBytes, c->s_compute>>>(
+            c->A, c->P, c->d_items, plan, c->d_stats, c->tex_map);
+    else if (c->scan_warp_per_pixel)
         sdm::k_pass1<<<c->grid_pass1_warp, sdm::kPass1Warps * 32, 0, c->s_compute>>>(c->A, c->P, c->d_items, plan, c->d_stats);
     else {
         int max_n = 1;

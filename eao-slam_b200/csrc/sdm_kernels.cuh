@@ -25,6 +25,7 @@
 // k_intra_cand / k_intra_check / k_intra_grow, k_pass2_cand / k_pass2, k_export_*, single-method helpers.
 #pragma once
 
+#include <cuda.h>  // CUtensorMap (type only: the encode entry point is fetched through the runtime, no -lcuda)
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -227,10 +228,9 @@ __device__ __forceinline__ PairSetup pair_setup(const DevPair& g, const float* K
 }
 
 // one candidate column of the scan body (:772-821).  Returns false if the candidate is skipped.
-__device__ __forceinline__ bool eval_candidate(const float4* __restrict__ tex2, const uchar2* __restrict__ ip2,
-                                               const DevParams& P, float Hm1, int u, float ab, float cb,
-                                               float th_line, float ang_pi_rot, float pixel, float gradc,
-                                               float& err, float& pe, float& ge)
+// cand_rows: the row tests of :773-785 and the interpolation weights; cand_gates: conditions 1-3 and the residual on the
+// column's texel (fetched by the caller: global memory, or a shared-memory tile staged by TMA in k_pass1_tma).
+__device__ __forceinline__ bool cand_rows(const DevParams& P, float Hm1, int u, float ab, float cb, RowW& r, size_t& idx)
 {
     const float uf = (float)u;
     const float v = -(ab * uf + cb);
@@ -238,9 +238,14 @@ __device__ __forceinline__ bool eval_candidate(const float4* __restrict__ tex2, 
     const float vm = -(ab * (uf - 1.0f) + cb);
     // floor(v) < 0 || ceil(v) >= rows  <=>  !(0 <= v <= rows-1), same for vj_plus / vj_minus
     if (!(v >= 0.f && v <= Hm1 && vp >= 0.f && vp <= Hm1 && vm >= 0.f && vm <= Hm1)) return false;
-    const RowW r = row_weights(v);
-    const size_t idx = (size_t)r.y0 * P.W + u;
-    const float4 t = __ldg(&tex2[idx]);
+    r = row_weights(v);
+    idx = (size_t)r.y0 * P.W + u;
+    return true;
+}
+__device__ __forceinline__ bool cand_gates(const float4 t, const RowW& r, const uchar2* __restrict__ ip2, size_t idx,
+                                           const DevParams& P, float th_line, float ang_pi_rot, float pixel, float gradc,
+                                           float& err, float& pe, float& ge)
+{
     const float g2 = t.x * r.w0 + t.y * r.w1;
     if (g2 <= P.lambdaG) return false;  // condition 1
     const float gth = yangle_interp(t.z, t.w, r.w0, r.w1);
@@ -260,6 +265,16 @@ __device__ __forceinline__ bool eval_candidate(const float4* __restrict__ tex2, 
     ge = gradc - g2;
     err = pe * pe + (ge * ge) / P.theta;
     return true;
+}
+__device__ __forceinline__ bool eval_candidate(const float4* __restrict__ tex2, const uchar2* __restrict__ ip2,
+                                               const DevParams& P, float Hm1, int u, float ab, float cb,
+                                               float th_line, float ang_pi_rot, float pixel, float gradc,
+                                               float& err, float& pe, float& ge)
+{
+    RowW r;
+    size_t idx;
+    if (!cand_rows(P, Hm1, u, ab, cb, r, idx)) return false;
+    return cand_gates(__ldg(&tex2[idx]), r, ip2, idx, P, th_line, ang_pi_rot, pixel, gradc, err, pe, ge);
 }
 
 // GetPixelDepth, equation 8 (:1568-1596).  s2d/s0d are the double-accumulated row products.
@@ -713,7 +728,42 @@ __device__ __forceinline__ bool next_chunk(const DevPlan& plan, const DevItem* _
 // ---------------------------------------------------------------------------------------------
 constexpr int kPass1Warps = 8;
 
-__device__ __forceinline__ bool scan_pixel_warp(const DevArena& A, const DevParams& P, const DevItem& s_item, int ci, int lane)
+// --- the north star's wording of this kernel: "warp-per-pixel ... stages neighbour-keyframe tiles in shared memory via
+// TMA" (k_pass1_tma, env SDM_SCAN=warp_tma; an A/B variant like k_pass1).  The texel arena is described to the TMA unit as
+// a 3-D tensor {4 floats, W, slots * H}; for every 64-column segment of a search range whose line positions span at most
+// kTmaBH row pairs, one elected lane requests the box {4, 64, kTmaBH} into the warp's shared-memory tile
+// (cp.async.bulk.tensor.3d ... mbarrier::complete_tx::bytes) and the lanes read their texels from it; segments that do not
+// fit the box (steep lines) and the intensity pairs come from global memory as before.  Same arithmetic, same bits.
+// What the A/B measures (profiles/README.md): a box is a rectangle, an epipolar line is not - the box holds
+// 64 x kTmaBH texels of which the 64 on the line are used.
+constexpr int kTmaBW = 64, kTmaBH = 16, kTmaWarps = 4;
+constexpr int kTmaTileBytes = kTmaBW * kTmaBH * 16;
+struct TmaTile {
+    float4* tile;        // this warp's [kTmaBH][kTmaBW] texels
+    uint64_t* mbar;      // this warp's mbarrier
+    const CUtensorMap* map;
+    unsigned phase;
+    int rows_per_slot;   // H
+};
+__device__ __forceinline__ void tma_load_box(const TmaTile& T, int x0, int y0_global)
+{
+    const unsigned dst = (unsigned)__cvta_generic_to_shared(T.tile), bar = (unsigned)__cvta_generic_to_shared(T.mbar);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(kTmaTileBytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"(dst), "l"(T.map), "r"(0), "r"(x0), "r"(y0_global), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_wait(const TmaTile& T)
+{
+    const unsigned bar = (unsigned)__cvta_generic_to_shared(T.mbar);
+    unsigned done = 0;
+    while (!done)
+        asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                     : "=r"(done) : "r"(bar), "r"(T.phase) : "memory");
+}
+
+template <bool kTma>
+__device__ __forceinline__ bool scan_pixel_warp(const DevArena& A, const DevParams& P, const DevItem& s_item, int ci, int lane,
+                                                TmaTile* T = nullptr)
 {
     const int kf = s_item.kf;
     const int N = s_item.n_nbr;
@@ -747,6 +797,31 @@ __device__ __forceinline__ bool scan_pixel_warp(const DevArena& A, const DevPara
         const uchar2* ip2 = A.ipair + nb;
         float best_err = 100000.0f;
         int best_u = 0x7fffffff;
+        if (kTma) {
+            for (int us = u_lo; us <= u_hi; us += kTmaBW) {
+                const int ue = min(us + kTmaBW - 1, u_hi);
+                // row pairs the segment touches (v is monotone in u): only if every line position is inside the image
+                const float v0 = -(ab * (float)us + cb), v1 = -(ab * (float)ue + cb);
+                const float vlo = fminf(v0, v1), vhi = fmaxf(v0, v1);
+                const int ya = (int)floorf(vlo), yb = (int)floorf(vhi);
+                const bool boxed = vlo >= 0.f && vhi <= Hm1 && yb - ya < kTmaBH;  // (NaN: false)
+                if (boxed) {
+                    __syncwarp();  // everybody is done with the previous tile
+                    if (lane == 0) tma_load_box(*T, us, s_item.pair[j].slot * T->rows_per_slot + ya);
+                    tma_wait(*T);
+                    T->phase ^= 1u;
+                }
+                for (int u = us + lane; u <= ue; u += 32) {
+                    float err, pe, ge;
+                    RowW r;
+                    size_t idx;
+                    if (!cand_rows(P, Hm1, u, ab, cb, r, idx)) continue;
+                    const float4 t = boxed ? T->tile[(r.y0 - ya) * kTmaBW + (u - us)] : __ldg(&tex2[idx]);
+                    if (cand_gates(t, r, ip2, idx, P, th_line, apr, pixel, gradc, err, pe, ge))
+                        if (err < best_err) { best_err = err; best_u = u; }
+                }
+            }
+        } else
         for (int u = u_lo + lane; u <= u_hi; u += 32) {
             float err, pe, ge;
             if (eval_candidate(tex2, ip2, P, Hm1, u, ab, cb, th_line, apr, pixel, gradc, err, pe, ge)) {
@@ -837,7 +912,41 @@ k_pass1(DevArena A, DevParams P, const DevItem* __restrict__ items, DevPlan plan
         for (int k = warp; k < kChunk; k += kPass1Warps) {
             const int ci = first + k;
             if (ci >= cnt) break;
-            if (scan_pixel_warp(A, P, s_item, ci, lane)) ++n_fused;
+            if (scan_pixel_warp<false>(A, P, s_item, ci, lane)) ++n_fused;
+        }
+    }
+    if (stats && lane == 0 && n_fused) atomicAdd(&stats->fused, n_fused);
+}
+
+__global__ void __launch_bounds__(kTmaWarps * 32)
+k_pass1_tma(DevArena A, DevParams P, const DevItem* __restrict__ items, DevPlan plan, DevStats* stats,
+            const __grid_constant__ CUtensorMap tex_map)
+{
+    __shared__ DevItem s_item;
+    __shared__ int s_chunk;
+    __shared__ __align__(8) uint64_t s_bar[kTmaWarps];
+    extern __shared__ __align__(128) unsigned char s_tiles[];  // kTmaWarps tiles of kTmaTileBytes
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        const unsigned bar = (unsigned)__cvta_generic_to_shared(&s_bar[warp]);
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    TmaTile T;
+    T.tile = reinterpret_cast<float4*>(s_tiles + (size_t)warp * kTmaTileBytes);
+    T.mbar = &s_bar[warp];
+    T.map = &tex_map;
+    T.phase = 0;
+    T.rows_per_slot = P.H;
+    int cur_entry = -1, first = 0;
+    unsigned long long n_fused = 0;
+    while (next_chunk(plan, items, s_item, s_chunk, cur_entry, first)) {
+        const int cnt = A.cand_count[s_item.kf];
+        for (int k = warp; k < kChunk; k += kTmaWarps) {
+            const int ci = first + k;
+            if (ci >= cnt) break;
+            if (scan_pixel_warp<true>(A, P, s_item, ci, lane, &T)) ++n_fused;
         }
     }
     if (stats && lane == 0 && n_fused) atomicAdd(&stats->fused, n_fused);

@@ -112,7 +112,8 @@ def test_scan_generations_agree(monkeypatch):
     with api.Context(width=320, height=240, max_keyframes=sc.n) as ctx:
         assert ctx.scan_generation() in (2, 3)     # k_verify_div passed for THETA = 0.23f
         assert _bit_equal(run_device(sc, ctx=ctx), osc) == zero
-    for env, gen in (("lane1", 1), ("lane2", 2), ("lane3", 3), ("warp", 0)):  # warp = the warp-per-pixel A/B kernel
+    # warp / warp_tma = the warp-per-pixel A/B kernels (the second stages neighbour tiles in shared memory by TMA)
+    for env, gen in (("lane1", 1), ("lane2", 2), ("lane3", 3), ("warp", 0), ("warp_tma", 0)):
         monkeypatch.setenv("SDM_SCAN", env)
         with api.Context(width=320, height=240, max_keyframes=sc.n) as ctx:
             assert ctx.scan_generation() == gen
