@@ -266,6 +266,12 @@ struct sdm_ctx {
     size_t exp_cap = 0;
     sdm_point* exp_pts = nullptr;
     size_t exp_pts_cap = 0;
+    void* lf_buf = nullptr;  // sdm_line_fit: chain lists, worst-case line slots, compacted lines
+    size_t lf_cap = 0;
+    void* lf_host = nullptr;  // pinned staging of the chain lists
+    size_t lf_host_cap = 0;
+    cudaEvent_t lf_ev[2] = {nullptr, nullptr};
+    float lf_ms = 0.f;
     void* peer_rs[kMaxPeers] = {nullptr};
     // sdm_exchange: flag blocks (own + IPC-mapped peers), halo plan, step counter
     sdm::XFlags* xflags = nullptr;
@@ -593,7 +599,9 @@ void sdm_destroy(sdm_ctx* c)
     if (c->h_count) cudaFreeHost(c->h_count);
     if (c->h_cand) cudaFreeHost(c->h_cand);
     cudaFree(c->d_chunk_off); cudaFree(c->d_counter); cudaFree(c->d_stats);
-    cudaFree(c->tmp_rs); cudaFree(c->xfer); cudaFree(c->dbg); cudaFree(c->exp_buf); cudaFree(c->exp_pts);
+    cudaFree(c->tmp_rs); cudaFree(c->xfer); cudaFree(c->dbg); cudaFree(c->exp_buf); cudaFree(c->exp_pts); cudaFree(c->lf_buf);
+    if (c->lf_host) cudaFreeHost(c->lf_host);
+    for (auto& e : c->lf_ev) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : {c->ev_p1[0], c->ev_p1[1], c->ev_p2[0], c->ev_p2[1], c->ev_p1_scan})
         if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : c->marks)
@@ -1484,6 +1492,134 @@ int sdm_export_points(sdm_ctx* c, int n, const int32_t* kfs, double sigma_max, s
     uint64_t id = 0;
     RC(c->r_down.record(s, &id));
     for (int i = 0; i < n; ++i) c->kf[kfs[i]].down_ds_id = c->kf[kfs[i]].down_cp_id = id;
+    return SDM_OK;
+}
+
+// ---- LineDetector::LineFitting over caller-supplied edge chains (LineDetector.cc:884-900) ----
+int sdm_line_fit(sdm_ctx* c, int n, const sdm_edge_chains* sets, sdm_line3d* out, size_t capacity, uint64_t* counts, uint64_t* total)
+{
+    if (!c || (n > 0 && !sets) || !total || (capacity > 0 && !out)) return fail(SDM_ERR_ARG, "sdm_line_fit: null argument");
+    *total = 0;
+    if (n <= 0) return SDM_OK;
+    if (c->cfg.width > 65535 || c->cfg.height > 65535) return fail(SDM_ERR_ARG, "sdm_line_fit: planes larger than 65535");
+    const int min_len = 10;  // MIN_LINE_LENGTH (LineDetector.cc:20)
+    size_t n_chains = 0, n_pix = 0, n_slots = 0;
+    uint64_t need = 0;
+    for (int i = 0; i < n; ++i) {
+        const sdm_edge_chains& e = sets[i];
+        if (!slot_ok(c, e.kf)) return fail(SDM_ERR_ARG, "keyframe slot %d out of range", e.kf);
+        if (!c->kf[e.kf].pass1_done) return fail(SDM_ERR_STATE, "slot %d has no depth planes", e.kf);
+        if (e.n_chains < 0 || (e.n_chains > 0 && (!e.offsets || !e.pixels))) return fail(SDM_ERR_ARG, "chain set %d: null list", i);
+        for (int k = 0; k < e.n_chains; ++k) {
+            const int len = e.offsets[k + 1] - e.offsets[k];
+            if (len < 0) return fail(SDM_ERR_ARG, "chain set %d: offsets not ascending at %d", i, k);
+            n_slots += (size_t)(len / min_len);
+        }
+        n_chains += (size_t)e.n_chains;
+        n_pix += e.n_chains > 0 ? (size_t)e.offsets[e.n_chains] : 0;
+        need = std::max(need, c->kf[e.kf].comp_id);
+    }
+    if (counts) for (int i = 0; i < n; ++i) counts[i] = 0;
+    if (n_chains == 0) return SDM_OK;
+    if (n_chains > 0x7fffffffULL || n_pix > 0x7fffffffULL || n_slots > 0x7fffffffULL) return fail(SDM_ERR_ARG, "line-fit batch too large");
+    CU(cudaSetDevice(c->cfg.device));
+    cudaStream_t s = c->s_down;  // reads the planes only; ordered after the last kernel on the slots
+    RC(c->r_compute.wait(s, need));
+    // host staging: kfs[n] | off[n_chains + 1] | kfi[n_chains] | slot0[n_chains] | pix[n_pix]
+    auto al = [](size_t v) { return (v + 15) & ~(size_t)15; };
+    const size_t o_kfs = 0, o_off = al(o_kfs + (size_t)n * sizeof(sdm::LineFitKf)), o_kfi = al(o_off + (n_chains + 1) * 4),
+                 o_slot0 = al(o_kfi + n_chains * 4), o_pix = al(o_slot0 + n_chains * 4), in_bytes = al(o_pix + n_pix * 4);
+    // device only: n_out[n_chains] | offs[n_chains + 1] u64 | kf_totals[n] u64 | raw lines[n_slots] | compacted lines
+    const size_t o_nout = in_bytes, o_offs = al(o_nout + n_chains * 4), o_tot = al(o_offs + (n_chains + 1) * 8),
+                 o_raw = al(o_tot + (size_t)n * 8), o_cmp = al(o_raw + n_slots * sizeof(sdm::DevLine)),
+                 bytes = o_cmp + n_slots * sizeof(sdm::DevLine);
+    if (c->lf_host_cap < in_bytes) {
+        CU(cudaStreamSynchronize(s));
+        if (c->lf_host) cudaFreeHost(c->lf_host);
+        c->lf_host = nullptr; c->lf_host_cap = 0;
+        CU(cudaMallocHost(&c->lf_host, in_bytes));
+        c->lf_host_cap = in_bytes;
+    }
+    if (c->lf_cap < bytes) {
+        CU(cudaStreamSynchronize(s));
+        cudaFree(c->lf_buf);
+        c->lf_buf = nullptr; c->lf_cap = 0;
+        CU(cudaMalloc(&c->lf_buf, bytes));
+        c->lf_cap = bytes;
+    }
+    for (auto& e : c->lf_ev) if (!e) CU(cudaEventCreate(&e));
+    char* h = (char*)c->lf_host;
+    sdm::LineFitKf* h_kfs = (sdm::LineFitKf*)(h + o_kfs);
+    int* h_off = (int*)(h + o_off);
+    int* h_kfi = (int*)(h + o_kfi);
+    int* h_slot0 = (int*)(h + o_slot0);
+    uint32_t* h_pix = (uint32_t*)(h + o_pix);
+    size_t ck = 0, cp = 0, cs = 0;
+    for (int i = 0; i < n; ++i) {
+        const sdm_edge_chains& e = sets[i];
+        const KfState& k = c->kf[e.kf];
+        h_kfs[i].slot = e.kf;
+        h_kfs[i].chain0 = (int)ck;
+        memcpy(h_kfs[i].K, k.K, sizeof(k.K));
+        sdm::pose_inverse(k.Tcw, h_kfs[i].Twc);
+        for (int j = 0; j < e.n_chains; ++j, ++ck) {
+            const int len = e.offsets[j + 1] - e.offsets[j];
+            h_off[ck] = (int)cp + (e.offsets[j] - e.offsets[0]);
+            h_kfi[ck] = i;
+            h_slot0[ck] = (int)cs;
+            cs += (size_t)(len / min_len);
+        }
+        const size_t m = e.n_chains > 0 ? (size_t)(e.offsets[e.n_chains] - e.offsets[0]) : 0;
+        for (size_t q = 0; q < m; ++q) {
+            const uint32_t rc = e.pixels[e.offsets[0] + q];
+            if ((int)(rc >> 16) >= c->cfg.height || (int)(rc & 0xffffu) >= c->cfg.width)
+                return fail(SDM_ERR_ARG, "chain set %d: pixel (%u, %u) outside the plane", i, rc >> 16, rc & 0xffffu);
+            h_pix[cp + q] = rc;
+        }
+        cp += m;
+    }
+    h_off[ck] = (int)cp;
+    char* d = (char*)c->lf_buf;
+    CU(cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, s));
+    sdm::LineFitParams L;
+    memset(&L, 0, sizeof(L));
+    L.min_len = min_len; L.max_len = 1000; L.init_depth_count = 3;  // LineDetector.cc:20-22
+    L.min_angle = 30.f; L.e1 = 1.0f; L.e2 = 1.5f;                   // :23-25
+    L.sigma_lt = 0.02f;                                             // :29 (float against float)
+    const int nc = (int)n_chains;
+    CU(cudaEventRecord(c->lf_ev[0], s));
+    sdm::k_line_fit<<<(nc + 63) / 64, 64, 0, s>>>(c->A, c->P, L, (const sdm::LineFitKf*)(d + o_kfs), nc, (const int*)(d + o_off),
+                                                  (const int*)(d + o_kfi), (const uint32_t*)(d + o_pix), (const int*)(d + o_slot0),
+                                                  (sdm::DevLine*)(d + o_raw), (int*)(d + o_nout));
+    sdm::k_line_scan<<<1, 1024, 0, s>>>((const int*)(d + o_nout), nc, (const sdm::LineFitKf*)(d + o_kfs), n,
+                                        (unsigned long long*)(d + o_offs), (unsigned long long*)(d + o_tot));
+    sdm::k_line_compact<<<(nc + 255) / 256, 256, 0, s>>>((const sdm::DevLine*)(d + o_raw), (const int*)(d + o_slot0),
+                                                         (const int*)(d + o_nout), (const unsigned long long*)(d + o_offs), nc,
+                                                         (sdm::DevLine*)(d + o_cmp), (unsigned long long)n_slots);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(c->lf_ev[1], s));
+    c->launches += 3;
+    std::vector<unsigned long long> h_tot((size_t)n + 1);
+    CU(cudaMemcpyAsync(h_tot.data(), d + o_tot, (size_t)n * 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(&h_tot[n], d + o_offs + (size_t)nc * 8, 8, cudaMemcpyDeviceToHost, s));
+    CU(cudaStreamSynchronize(s));
+    CU(cudaEventElapsedTime(&c->lf_ms, c->lf_ev[0], c->lf_ev[1]));
+    *total = (uint64_t)h_tot[n];
+    if (counts) for (int i = 0; i < n; ++i) counts[i] = (uint64_t)h_tot[i];
+    const size_t m = (size_t)std::min<uint64_t>(*total, capacity);
+    if (m > 0) {
+        CU(cudaMemcpyAsync(out, d + o_cmp, m * sizeof(sdm_line3d), cudaMemcpyDeviceToHost, s));
+        CU(cudaStreamSynchronize(s));
+    }
+    uint64_t id = 0;
+    RC(c->r_down.record(s, &id));
+    for (int i = 0; i < n; ++i) c->kf[sets[i].kf].down_ds_id = c->kf[sets[i].kf].down_cp_id = id;
+    return SDM_OK;
+}
+int sdm_last_line_fit_ms(sdm_ctx* c, float* ms)
+{
+    if (!c || !ms) return fail(SDM_ERR_ARG, "null argument");
+    *ms = c->lf_ms;
     return SDM_OK;
 }
 

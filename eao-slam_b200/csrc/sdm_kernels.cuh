@@ -2174,4 +2174,307 @@ __global__ void k_merge_rs(float2* __restrict__ rs, const float* __restrict__ d,
     if (i < n) rs[i] = make_float2(d[i], s[i]);
 }
 
+// ---------------------------------------------------------------------------------------------
+// edge-aided 3-D line fitting, the immediate consumer of depth_map_checked_ / depth_sigma_ -
+// LineDetector::LineFit and its helpers (LineDetector.cc:578-840; constants :20-29) over the edge chains of a
+// keyframe (LineFitting, :884-900), reading the planes where pass 2 left them.  One thread per chain (the algorithm
+// is a greedy walk along the chain; its tail recursion at :838 is a loop here).  The two least-squares problems are
+// solved in closed form in double precision:
+//   LeastSquaresLineFit (:601-624, cv::SVD::solveZ): the unit vector (a, b, c) minimising sum (a x + b y + c)^2 = the
+//     eigenvector of the smallest eigenvalue of the 3x3 moment matrix (cyclic Jacobi on exact integer sums);
+//   LeastSquaresDepthFit (:627-678, cv::solve DECOMP_SVD): z = u1 d + u2 by the 2x2 normal equations (minimum-norm
+//     solution when all d coincide).
+// OpenCV solves both with a float Jacobi SVD, so decisions that sit on a threshold can differ: parity with the oracle
+// (oracle/linefit_oracle.py, real cv2 calls) is tolerance-level - tests/test_gpu_linefit.py bounds the share of
+// differing segments and the end-point error.  Everything else is float arithmetic in the reference's order.
+// ---------------------------------------------------------------------------------------------
+struct LineFitParams {
+    int min_len, max_len, init_depth_count;  // MIN_LINE_LENGTH 10, MAX_LINE_LENGTH 1000, INIT_DEPTH_COUNT 3
+    float min_angle, e1, e2;                 // MIN_SEGMENT_ANGLE 30, E1 1.0, E2 1.5
+    float sigma_lt;                          // x < this <=> x < sigma_limit (0.02f)
+    float fx, fy, cx, cy;                    // filled per keyframe from LineFitKf
+    float Twc[12];
+};
+struct LineFitKf {  // one keyframe of a sdm_line_fit batch
+    int slot;
+    int chain0;     // first chain of the keyframe in the batch's chain list
+    float K[4];
+    float Twc[12];
+};
+struct DevLine {    // = sdm_line3d
+    float seg[4];   // s.x s.y e.x e.y   (mLinesSeg row)
+    float xyz[6];   // Pws, Pwe          (mLines3D row)
+    int chain;      // chain index inside its keyframe
+    int kf_index;   // index of the keyframe in the batch
+};
+static_assert(sizeof(DevLine) == sizeof(sdm_line3d), "DevLine is the ABI's sdm_line3d");
+
+__device__ __forceinline__ void lf_closest(float a, float b, float c, int x, int y, float& cx, float& cy)
+{
+    const float den = a * a + b * b;
+    cx = (b * (b * (float)x - a * (float)y) - a * c) / den;
+    cy = (a * (-b * (float)x + a * (float)y) - b * c) / den;
+}
+__device__ __forceinline__ float lf_norm2(float px, float py, float qx, float qy)
+{
+    const float dx = px - qx, dy = py - qy;
+    return (float)sqrt((double)dx * (double)dx + (double)dy * (double)dy);
+}
+struct LfPlanes {
+    const float* chk;
+    const float2* rs;   // depth_sigma_ = rs[].y (the authoritative pass-1 plane)
+    int W;
+    float eps_gt, sigma_lt;
+};
+__device__ __forceinline__ bool lf_has_depth(const LfPlanes& Q, uint32_t rc)
+{
+    const size_t i = (size_t)(rc >> 16) * Q.W + (rc & 0xffffu);
+    return Q.chk[i] > Q.eps_gt && Q.rs[i].y < Q.sigma_lt;
+}
+__device__ __forceinline__ int lf_count(const LfPlanes& Q, const uint32_t* ch, int n)
+{
+    int k = 0;
+    for (int i = 0; i < n; ++i) k += lf_has_depth(Q, ch[i]);
+    return k;
+}
+// smallest eigenpair of the symmetric 3x3 M (cyclic Jacobi, double)
+__device__ __forceinline__ void lf_smallest_eigvec(double M[3][3], double v[3], double& lam)
+{
+    double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+    for (int sweep = 0; sweep < 12; ++sweep) {
+        const double off = fabs(M[0][1]) + fabs(M[0][2]) + fabs(M[1][2]);
+        if (off < 1e-300) break;
+        for (int p = 0; p < 2; ++p)
+            for (int q = p + 1; q < 3; ++q) {
+                if (M[p][q] == 0.0) continue;
+                const double theta = (M[q][q] - M[p][p]) / (2.0 * M[p][q]);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
+                for (int k = 0; k < 3; ++k) {
+                    const double mkp = M[k][p], mkq = M[k][q];
+                    M[k][p] = cs * mkp - sn * mkq;
+                    M[k][q] = sn * mkp + cs * mkq;
+                }
+                for (int k = 0; k < 3; ++k) {
+                    const double mpk = M[p][k], mqk = M[q][k];
+                    M[p][k] = cs * mpk - sn * mqk;
+                    M[q][k] = sn * mpk + cs * mqk;
+                }
+                for (int k = 0; k < 3; ++k) {
+                    const double vkp = V[k][p], vkq = V[k][q];
+                    V[k][p] = cs * vkp - sn * vkq;
+                    V[k][q] = sn * vkp + cs * vkq;
+                }
+            }
+    }
+    int m = 0;
+    if (M[1][1] < M[m][m]) m = 1;
+    if (M[2][2] < M[m][m]) m = 2;
+    lam = M[m][m];
+    v[0] = V[0][m]; v[1] = V[1][m]; v[2] = V[2][m];
+}
+__device__ __forceinline__ void lf_line(const uint32_t* ch, int n, float& a, float& b, float& c, float& err)
+{
+    long long sxx = 0, sxy = 0, syy = 0, sx = 0, sy = 0;
+    for (int i = 0; i < n; ++i) {
+        const long long x = ch[i] & 0xffffu, y = ch[i] >> 16;
+        sxx += x * x; sxy += x * y; syy += y * y; sx += x; sy += y;
+    }
+    double M[3][3] = {{(double)sxx, (double)sxy, (double)sx}, {(double)sxy, (double)syy, (double)sy}, {(double)sx, (double)sy, (double)n}};
+    double v[3], lam;
+    lf_smallest_eigvec(M, v, lam);
+    a = (float)v[0]; b = (float)v[1]; c = (float)v[2];
+    double r2 = 0.0;  // cv::norm(A*u): residuals of the float solution
+    for (int i = 0; i < n; ++i) {
+        const double r = (double)a * (double)(ch[i] & 0xffffu) + (double)b * (double)(ch[i] >> 16) + (double)c;
+        r2 += r * r;
+    }
+    err = (float)sqrt(r2);
+}
+__device__ __forceinline__ void lf_depth(const LfPlanes& Q, const LineFitParams& L, const uint32_t* ch, int n, float la, float lb,
+                                         float lc, float& u1, float& u2, float& err)
+{
+    float sx, sy;
+    lf_closest(la, lb, lc, (int)(ch[0] & 0xffffu), (int)(ch[0] >> 16), sx, sy);
+    const float half = (L.fx + L.fy) / 2;
+    double Sdd = 0, Sd = 0, Sn = 0, Sdz = 0, Sz = 0;
+    for (int i = 0; i < n; ++i) {
+        if (!lf_has_depth(Q, ch[i])) continue;
+        float cx, cy;
+        lf_closest(la, lb, lc, (int)(ch[i] & 0xffffu), (int)(ch[i] >> 16), cx, cy);
+        const double d = lf_norm2(cx, cy, sx, sy);
+        const size_t pi = (size_t)(ch[i] >> 16) * Q.W + (ch[i] & 0xffffu);
+        const double z = (double)((1.0f / Q.chk[pi]) * half);
+        Sdd += d * d; Sd += d; Sn += 1.0; Sdz += d * z; Sz += z;
+    }
+    const double det = Sdd * Sn - Sd * Sd;
+    double x1, x2;
+    if (Sn > 0 && det > 1e-9 * (Sdd * Sn + 1e-30)) {
+        x1 = (Sdz * Sn - Sd * Sz) / det;
+        x2 = (Sdd * Sz - Sd * Sdz) / det;
+    } else if (Sn > 0) {  // every row equals (d, 1): minimum-norm solution along that row
+        const double d = Sd / Sn, s = Sz / (Sn * (d * d + 1.0));
+        x1 = d * s; x2 = s;
+    } else {
+        x1 = x2 = 0.0;
+    }
+    u1 = (float)x1; u2 = (float)x2;
+    double r2 = 0.0;
+    for (int i = 0; i < n; ++i) {
+        if (!lf_has_depth(Q, ch[i])) continue;
+        float cx, cy;
+        lf_closest(la, lb, lc, (int)(ch[i] & 0xffffu), (int)(ch[i] >> 16), cx, cy);
+        const float d = lf_norm2(cx, cy, sx, sy);
+        const size_t pi = (size_t)(ch[i] >> 16) * Q.W + (ch[i] & 0xffffu);
+        const float z = (1.0f / Q.chk[pi]) * half;
+        const double r = (double)u1 * (double)d + (double)u2 - (double)z;
+        r2 += r * r;
+    }
+    err = (float)sqrt(r2);
+}
+__device__ __forceinline__ float lf_point_depth(const LfPlanes& Q, const LineFitParams& L, const uint32_t* ch, float a, float b,
+                                                float c, float alpha, float beta, uint32_t rc)
+{
+    const size_t pi = (size_t)(rc >> 16) * Q.W + (rc & 0xffffu);
+    float z = 1.0f / Q.chk[pi];
+    if ((double)z < 0.000001) return -1.f;
+    if (Q.rs[pi].y > 0.02f) return -1.f;
+    float sx, sy, cx, cy;
+    lf_closest(a, b, c, (int)(ch[0] & 0xffffu), (int)(ch[0] >> 16), sx, sy);
+    lf_closest(a, b, c, (int)(rc & 0xffffu), (int)(rc >> 16), cx, cy);
+    const float t = lf_norm2(cx, cy, sx, sy);
+    z *= (L.fx + L.fy) / 2;
+    return fabsf(alpha * t - z + beta) / sqrtf(alpha * alpha + 1.0f);
+}
+
+// chains of a batch of keyframes: pixels packed (r << 16 | c); chain k = pix[off[k] .. off[k+1]) belongs to keyframe kfi[k];
+// its lines go to out[slot0[k] ..) (slot0 = prefix sum of len / min_len, the most lines a chain can hold), count in n_out[k]
+__global__ void __launch_bounds__(64) k_line_fit(DevArena A, DevParams P, LineFitParams L, const LineFitKf* __restrict__ kfs,
+                                                 int n_chains, const int* __restrict__ off, const int* __restrict__ kfi,
+                                                 const uint32_t* __restrict__ pix, const int* __restrict__ slot0,
+                                                 DevLine* __restrict__ out, int* __restrict__ n_out)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_chains) return;
+    const int ki = kfi[k];
+    const LineFitKf F = kfs[ki];
+    L.fx = F.K[0]; L.fy = F.K[1]; L.cx = F.K[2]; L.cy = F.K[3];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) L.Twc[i] = F.Twc[i];
+    LfPlanes Q;
+    Q.chk = A.chk + (size_t)F.slot * A.P; Q.rs = A.rs + (size_t)F.slot * A.P; Q.W = P.W; Q.eps_gt = P.eps_gt; Q.sigma_lt = L.sigma_lt;
+    const uint32_t* ch = pix + off[k];
+    int n = off[k + 1] - off[k];
+    DevLine* o = out + slot0[k];
+    int no = 0;
+    const float inf = __int_as_float(0x7f800000);
+    for (;;) {
+        float err_l = inf, err_d = inf, a = 0, b = 0, c = 0, alpha = 0, beta = 0;
+        const int init = L.min_len;
+        while (n > init && init < L.max_len) {
+            if (lf_count(Q, ch, 1) < 1 || lf_count(Q, ch, init) < L.init_depth_count) { ++ch; --n; continue; }
+            lf_line(ch, init, a, b, c, err_l);
+            lf_depth(Q, L, ch, init, a, b, c, alpha, beta, err_d);
+            if ((double)err_l <= 1.0 && (double)err_d <= 1.0) break;
+            ++ch; --n;
+        }
+        if (err_l > L.e1 || err_d > L.e2) break;  // (inf when no window was ever fitted; NaN compares false like :739-741)
+        int interval = 0, len = init;
+        while (len < L.max_len && len < n) {
+            const uint32_t rc = ch[len];
+            const float dist = fabsf(a * (float)(rc & 0xffffu) + b * (float)(rc >> 16) + c) / sqrtf(a * a + b * b);
+            if (dist > L.e1) break;
+            ++len; ++interval;
+            if (interval >= L.min_len) {
+                interval = 0;
+                if (lf_count(Q, ch + len - L.min_len, L.min_len) < 1) { len -= L.min_len; break; }
+                int prev = len - L.min_len;
+                bool stop = false;
+                for (int i = prev, i_end = len; i < i_end; ++i) {
+                    const float dept = lf_point_depth(Q, L, ch, a, b, c, alpha, beta, ch[i]);
+                    if (dept > L.e2) { len = prev; stop = true; break; }
+                    if ((double)dept >= 0.0) prev = i;
+                }
+                if (stop) break;
+            }
+        }
+        lf_line(ch, len, a, b, c, err_l);
+        if ((float)lf_count(Q, ch, len) / (float)len > (float)L.init_depth_count / (float)L.min_len) {
+            lf_depth(Q, L, ch, len, a, b, c, alpha, beta, err_d);
+            float sx, sy, ex, ey;
+            lf_closest(a, b, c, (int)(ch[0] & 0xffffu), (int)(ch[0] >> 16), sx, sy);
+            lf_closest(a, b, c, (int)(ch[len - 1] & 0xffffu), (int)(ch[len - 1] >> 16), ex, ey);
+            const float half = (L.fx + L.fy) / 2;
+            float Zs = beta;
+            Zs /= half;
+            const float Xs = Zs * (sx - L.cx) / L.fx, Ys = Zs * (sy - L.cy) / L.fy;
+            float Ze = alpha * lf_norm2(ex, ey, sx, sy) + beta;
+            Ze /= half;
+            const float Xe = Ze * (ex - L.cx) / L.fx, Ye = Ze * (ey - L.cy) / L.fy;
+            const double dx = (double)(Xe - Xs), dy = (double)(Ye - Ys), dz = (double)(Ze - Zs);
+            const double nd = sqrt(dx * dx + dy * dy + dz * dz);
+            const double ns = sqrt((double)Xs * Xs + (double)Ys * Ys + (double)Zs * Zs);
+            const double ne = sqrt((double)Xe * Xe + (double)Ye * Ye + (double)Ze * Ze);
+            const double cosS = (dx * Xs + dy * Ys + dz * Zs) / nd / ns, cosE = (dx * Xe + dy * Ye + dz * Ze) / nd / ne;
+            const double angS = acos(fabs(cosS)) * 180.0 / 3.1415926535897932384626433832795;
+            const double angE = acos(fabs(cosE)) * 180.0 / 3.1415926535897932384626433832795;
+            if (angS > (double)L.min_angle && angE > (double)L.min_angle) {
+                DevLine d;
+                d.seg[0] = sx; d.seg[1] = sy; d.seg[2] = ex; d.seg[3] = ey;
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    d.xyz[r] = L.Twc[4 * r] * Xs + L.Twc[4 * r + 1] * Ys + L.Twc[4 * r + 2] * Zs + L.Twc[4 * r + 3] * 1.0f;
+                    d.xyz[3 + r] = L.Twc[4 * r] * Xe + L.Twc[4 * r + 1] * Ye + L.Twc[4 * r + 2] * Ze + L.Twc[4 * r + 3] * 1.0f;
+                }
+                d.chain = k - F.chain0;
+                d.kf_index = ki;
+                o[no++] = d;
+            }
+        }
+        ch += len;
+        n -= len;
+    }
+    n_out[k] = no;
+}
+
+// exclusive scan of the per-chain line counts (one block) + per-keyframe totals; then the compaction: chain k copies its
+// lines from the worst-case slots to their final place (chain order = the reference's push_back order, :822-823)
+__global__ void __launch_bounds__(1024) k_line_scan(const int* __restrict__ n_out, int n_chains, const LineFitKf* __restrict__ kfs,
+                                                    int n_kf, unsigned long long* __restrict__ offs,
+                                                    unsigned long long* __restrict__ kf_totals)
+{
+    __shared__ unsigned long long part[1024];
+    const int t = threadIdx.x, per = (n_chains + 1023) / 1024;
+    const int i0 = min(t * per, n_chains), i1 = min(i0 + per, n_chains);
+    unsigned long long s = 0;
+    for (int i = i0; i < i1; ++i) s += (unsigned long long)n_out[i];
+    part[t] = s;
+    __syncthreads();
+    for (int d = 1; d < 1024; d <<= 1) {
+        const unsigned long long v = t >= d ? part[t - d] : 0ull;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    unsigned long long run = part[t] - s;
+    for (int i = i0; i < i1; ++i) { offs[i] = run; run += (unsigned long long)n_out[i]; }
+    if (t == 1023) offs[n_chains] = part[1023];
+    __syncthreads();
+    for (int i = t; i < n_kf; i += 1024) {
+        const int c0 = kfs[i].chain0, c1 = i + 1 < n_kf ? kfs[i + 1].chain0 : n_chains;
+        kf_totals[i] = offs[c1] - offs[c0];
+    }
+}
+__global__ void __launch_bounds__(256) k_line_compact(const DevLine* __restrict__ in, const int* __restrict__ slot0,
+                                                     const int* __restrict__ n_out, const unsigned long long* __restrict__ offs,
+                                                     int n_chains, DevLine* __restrict__ out, unsigned long long capacity)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_chains) return;
+    const DevLine* src = in + slot0[k];
+    const unsigned long long o = offs[k];
+    for (int i = 0; i < n_out[k]; ++i)
+        if (o + i < capacity) out[o + i] = src[i];
+}
+
 }  // namespace sdm

@@ -425,6 +425,89 @@ public:
         std::cout << "saved semi dense point cloud" << std::endl;
     }
 
+    // the per-keyframe LineDetector::LineFitting of LineFittingOffline (LineDetector.cc:484-523, :884-900) for
+    // every finished keyframe of the map in ONE device call, on the planes pass 2 left in the arena.  `chains(kf, offsets,
+    // pixels)` supplies the keyframe's edge chains (EdgeMap::segments of kf->mEdgeMap in the reference: offsets.size() =
+    // chains + 1 starting at 0, pixels packed (row << 16) | col).  lines[k] are the rows the reference appends to
+    // kf->mLinesSeg / kf->mLines3D for kfs[i], counts[i] of them, in the reference's order.  Returns the number of lines.
+    typedef std::function<void(KeyFrame*, std::vector<int32_t>&, std::vector<uint32_t>&)> ChainSource;
+    size_t FitLines(const ChainSource& chains, std::vector<sdm_line3d>& lines, std::vector<KeyFrame*>* kfs_out = NULL,
+                    std::vector<uint64_t>* counts_out = NULL)
+    {
+        lines.clear();
+        std::vector<KeyFrame*> vpKFs = mpMap->GetAllKeyFrames(), kfs;
+        std::vector<std::vector<int32_t> > offs;
+        std::vector<std::vector<uint32_t> > pix;
+        std::vector<sdm_edge_chains> sets;
+        for (size_t i = 0; i < vpKFs.size(); i++) {
+            KeyFrame* kf = vpKFs[i];
+            if (kf->isBad() || !kf->semidense_flag_ || !kf->interKF_depth_flag_) continue;  // LineDetector.cc:495
+            if (!EnsureResident(kf)) return 0;
+            kfs.push_back(kf);
+            offs.push_back(std::vector<int32_t>());
+            pix.push_back(std::vector<uint32_t>());
+            chains(kf, offs.back(), pix.back());
+            if (offs.back().empty()) offs.back().push_back(0);
+        }
+        if (kfs.empty() || !mCtx || !Flush()) return 0;
+        for (size_t i = 0; i < kfs.size(); i++) {
+            sdm_edge_chains e;
+            e.kf = mSlot[kfs[i]];
+            e.n_chains = (int32_t)offs[i].size() - 1;
+            e.offsets = offs[i].data();
+            e.pixels = pix[i].data();
+            sets.push_back(e);
+        }
+        size_t cap = 0;
+        for (size_t i = 0; i < offs.size(); i++)
+            for (size_t k = 0; k + 1 < offs[i].size(); k++) cap += (size_t)((offs[i][k + 1] - offs[i][k]) / 10);
+        lines.resize(cap);
+        std::vector<uint64_t> counts(kfs.size());
+        uint64_t total = 0;
+        if (!Check(sdm_line_fit(mCtx, (int)sets.size(), sets.data(), lines.data(), lines.size(), counts.data(), &total), "sdm_line_fit")) {
+            lines.clear();
+            return 0;
+        }
+        lines.resize((size_t)total);
+        if (kfs_out) kfs_out->swap(kfs);
+        if (counts_out) counts_out->swap(counts);
+        return lines.size();
+    }
+
+#ifdef SDM_HOST_WITH_ORBSLAM2
+    // the device counterpart of `mLineDetector.LineFittingOffline(vpKFs, mpModeler)` (:263): kf->mEdgeMap in, kf->mLinesSeg /
+    // kf->mLines3D out (LineDetector.cc:822-823), then the reference's own MergeLines per keyframe (:514)
+    void LineFittingOnDevice()
+    {
+        std::vector<sdm_line3d> lines;
+        std::vector<KeyFrame*> kfs;
+        std::vector<uint64_t> counts;
+        FitLines([](KeyFrame* kf, std::vector<int32_t>& off, std::vector<uint32_t>& pix) {
+            off.push_back(0);
+            if (kf->mEdgeMap == NULL) { std::cerr << "error: no edge map" << std::endl; return; }  // :889-892
+            for (int i = 0; i < kf->mEdgeMap->noSegments; i++) {
+                for (int j = 0; j < kf->mEdgeMap->segments[i].noPixels; j++)
+                    pix.push_back(((uint32_t)kf->mEdgeMap->segments[i].pixels[j].r << 16) | (uint32_t)kf->mEdgeMap->segments[i].pixels[j].c);
+                off.push_back((int32_t)pix.size());
+            }
+        }, lines, &kfs, &counts);
+        size_t k = 0;
+        for (size_t i = 0; i < kfs.size(); i++) {
+            KeyFrame* kf = kfs[i];
+            kf->SetNotEraseSemiDense();
+            for (uint64_t j = 0; j < counts[i]; j++, k++) {
+                cv::Mat line(1, 6, CV_32F), line2D(1, 4, CV_32F);
+                for (int q = 0; q < 6; q++) line.at<float>(0, q) = lines[k].xyz[q];
+                for (int q = 0; q < 4; q++) line2D.at<float>(0, q) = lines[k].seg[q];
+                kf->mLines3D.push_back(line);
+                kf->mLinesSeg.push_back(line2D);
+            }
+            mLineDetector.MergeLines(kf, mpModeler);
+            kf->SetEraseSemiDense();
+        }
+    }
+#endif
+
 #ifdef SDM_HOST_WITH_ORBSLAM2
     Modeler* GetModeler() { return mpModeler; }  // :113-116
     void WriteModel()                            // :119-134

@@ -68,6 +68,13 @@ class Loop(C.Structure):
 SDM_PEER_HANDLE_BYTES = 192
 
 
+class EdgeChains(C.Structure):  # sdm_edge_chains
+    _fields_ = [("kf", C.c_int32), ("n_chains", C.c_int32), ("offsets", C.POINTER(C.c_int32)), ("pixels", C.POINTER(C.c_uint32))]
+
+
+LINE3D = np.dtype([("seg", "f4", 4), ("xyz", "f4", 6), ("chain", "i4"), ("kf_index", "i4")])  # sdm_line3d
+
+
 class Timing(C.Structure):
     _fields_ = [("pass1_scan_ms", C.c_float), ("pass1_intra_ms", C.c_float), ("pass2_ms", C.c_float)]
 
@@ -86,6 +93,7 @@ EXPORTS = [
     "sdm_pair_geometry", "sdm_stereo_search_constraints", "sdm_search_range", "sdm_inter_chi_test",
     "sdm_epipolar_search", "sdm_epipolar_search_plane", "sdm_fuse", "sdm_intra_check", "sdm_intra_grow",
     "sdm_inter_check", "sdm_last_pass_ms", "sdm_launch_count", "sdm_last_timing", "sdm_last_pack_ms", "sdm_mark", "sdm_elapsed_ms",
+    "sdm_line_fit", "sdm_last_line_fit_ms",
 ]
 
 _lib = None
@@ -129,6 +137,8 @@ def load() -> C.CDLL:
     lib.sdm_inter_chi_test.argtypes = [vp, C.c_int, vp, vp, vp]
     lib.sdm_download_planes.argtypes = [vp, C.c_int, vp, sz, vp, sz]
     lib.sdm_export_points.argtypes = [vp, C.c_int, ip, C.c_double, vp, sz, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.sdm_line_fit.argtypes = [vp, C.c_int, C.POINTER(EdgeChains), vp, sz, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+    lib.sdm_last_line_fit_ms.argtypes = [vp, fp]
     lib.sdm_upload_depth.argtypes = [vp, C.c_int, vp, sz, vp, sz]
     lib.sdm_upload_checked.argtypes = [vp, C.c_int, vp, sz]
     lib.sdm_depth_plane_ptr.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(sz)]
@@ -367,6 +377,30 @@ class Context:
         self._chk(self.lib.sdm_export_points(self.h, a.size, a.ctypes.data_as(ip), sigma_max, pts.ctypes.data, capacity,
                                              counts.ctypes.data_as(up), C.byref(total)))
         return pts[:min(capacity, int(total.value))], counts, int(total.value)
+
+    def line_fit(self, slots, offsets, pixels):
+        """LineDetector::LineFitting for keyframes `slots`; offsets[i] (n_chains + 1 int32) / pixels[i] (uint32, row << 16 | col)
+        are the edge chains of slots[i].  Returns (lines: structured array seg[4], xyz[6], chain, kf_index; per-set counts)"""
+        n = len(slots)
+        keep = [(np.ascontiguousarray(o, np.int32), np.ascontiguousarray(p, np.uint32)) for o, p in zip(offsets, pixels)]
+        sets = (EdgeChains * max(n, 1))()
+        cap = 0
+        for i, (o, p) in enumerate(keep):
+            sets[i].kf, sets[i].n_chains = int(slots[i]), o.size - 1
+            sets[i].offsets = o.ctypes.data_as(C.POINTER(C.c_int32))
+            sets[i].pixels = p.ctypes.data_as(C.POINTER(C.c_uint32))
+            cap += int((np.diff(o) // 10).sum())
+        out = np.zeros(max(cap, 1), LINE3D)
+        counts = np.zeros(max(n, 1), np.uint64)
+        total = C.c_uint64()
+        self._chk(self.lib.sdm_line_fit(self.h, n, sets, out.ctypes.data, cap, counts.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                        C.byref(total)))
+        return out[:int(total.value)], counts[:n]
+
+    def last_line_fit_ms(self) -> float:
+        ms = C.c_float()
+        self._chk(self.lib.sdm_last_line_fit_ms(self.h, C.byref(ms)))
+        return float(ms.value)
 
     def download_planes(self, slot):
         g, t = np.empty((self.H, self.W), np.float32), np.empty((self.H, self.W), np.float32)

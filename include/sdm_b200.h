@@ -219,6 +219,34 @@ typedef struct {
 int sdm_export_points(sdm_ctx* ctx, int n, const int32_t* kfs, double sigma_max, sdm_point* out, size_t capacity,
                       uint64_t* counts, uint64_t* total);
 
+/* ---- edge-aided 3-D line fitting -------------------------------------------- */
+/* replaces: LineDetector::LineFitting / LineFit / LeastSquaresLineFit / LeastSquaresDepthFit / CountDepth /
+ * ComputePointDistance2Line / ComputePointDepth2Line (LineDetector.cc:578-840, :884-900; called from
+ * ProbabilityMapping.cc:262-268 once the loop is done) for a batch of keyframes, reading depth_map_checked_ and
+ * depth_sigma_ where pass 2 left them on the device.  The edge chains are an INPUT: the reference gets them from the
+ * closed-source EDLib (DetectEdgesByED, LineDetector.cc:855) on the host and keeps them in kf->mEdgeMap; a set lists
+ * the pixels of EdgeMap::segments[i] in order, packed (row << 16) | col, offsets[i] .. offsets[i + 1].
+ * Output = the rows the reference appends to kf->mLinesSeg (seg) and kf->mLines3D (xyz), in its order (keyframes in
+ * list order, chains in order, lines along the chain); `chain` / `kf_index` say where a row came from.
+ * Writes min(total, capacity) rows (out may be NULL with capacity 0 to count only), per-set counts to counts[n] (may be
+ * NULL), their sum to *total.  Blocking.  The two least-squares fits are closed-form double precision where OpenCV runs a
+ * float Jacobi SVD: results agree to rounding, decisions that sit exactly on a threshold may differ. */
+typedef struct {
+    int32_t kf;              /* slot whose planes are read (pass 2 done) */
+    int32_t n_chains;
+    const int32_t* offsets;  /* n_chains + 1 entries, offsets[0] = 0 */
+    const uint32_t* pixels;  /* offsets[n_chains] entries */
+} sdm_edge_chains;
+typedef struct {
+    float seg[4];   /* s.x s.y e.x e.y */
+    float xyz[6];   /* Pws, Pwe */
+    int32_t chain, kf_index;
+} sdm_line3d;
+int sdm_line_fit(sdm_ctx* ctx, int n, const sdm_edge_chains* sets, sdm_line3d* out, size_t capacity, uint64_t* counts,
+                 uint64_t* total);
+/* device time of the last sdm_line_fit (its three kernels), ms */
+int sdm_last_line_fit_ms(sdm_ctx* ctx, float* ms);
+
 /* ---- multi-GPU: pass-1 planes of halo keyframes over NVLink (the dependency of :1202-1249) -- */
 /* device pointer + byte size of the (rho, sigma) float2 plane of a slot, for NCCL / peer copies */
 int sdm_depth_plane_ptr(sdm_ctx* ctx, int kf, void** dev_ptr, size_t* bytes);

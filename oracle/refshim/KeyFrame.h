@@ -23,6 +23,11 @@
 // float overloads), so the compile environment must have it too.
 using namespace std;
 
+// stand-in for Thirdparty/EDTest/EdgeMap.h (the closed-source Edge Drawing library's result type, KeyFrame.h:175)
+struct Pixel { int r, c; };
+struct EdgeSegment { Pixel* pixels; int noPixels; };
+struct EdgeMap { Pixel* pixels; EdgeSegment* segments; int noSegments; };
+
 namespace DBoW2 {
 typedef std::map<unsigned int, std::vector<unsigned int> > FeatureVector;
 }
@@ -32,7 +37,7 @@ namespace ORB_SLAM2 {
 class KeyFrame {
 public:
     KeyFrame() : fx(0), fy(0), cx(0), cy(0), mnMinX(0), mnMinY(0), mnMaxX(0), mnMaxY(0), semidense_flag_(false),
-                 interKF_depth_flag_(false), I_stddev(20.0f), poseChanged(false), mnMappingId(0), mbBad(false) {}
+                 interKF_depth_flag_(false), I_stddev(20.0f), poseChanged(false), mnMappingId(0), mEdgeMap(NULL), mbBad(false) {}
 
     void SetPose(const cv::Mat& Tcw_)  // KeyFrame.cc:108-124
     {
@@ -91,6 +96,8 @@ public:
     long unsigned int mnMappingId;
     std::mutex mMutexMappingId;
     cv::Mat mEdgeIndex;
+    cv::Mat mLinesSeg, mLines3D;  // KeyFrame.h:172-173
+    EdgeMap* mEdgeMap;            // KeyFrame.h:175 (Thirdparty/EDTest/EdgeMap.h)
 
     // filled by the driver in place of the ORB-SLAM2 graph
     std::vector<KeyFrame*> mvpOrderedConnectedKeyFrames;

@@ -109,6 +109,14 @@ public:
     {
         for (int i = 0; i < rows; i++) memcpy(dst.data + (size_t)i * dst.step, data + (size_t)i * step, (size_t)cols * elemSize());
     }
+    void push_back(const Mat& m)  // cv::Mat::push_back(const Mat&): append the rows of m
+    {
+        Mat n;
+        n.create(rows + m.rows, m.cols, m.type_);
+        for (int i = 0; i < rows; i++) memcpy(n.data + (size_t)i * n.step, data + (size_t)i * step, (size_t)cols * elemSize());
+        for (int i = 0; i < m.rows; i++) memcpy(n.data + (size_t)(rows + i) * n.step, m.data + (size_t)i * m.step, (size_t)m.cols * m.elemSize());
+        *this = n;
+    }
     double dot(const Mat&) const { stub_dead("Mat::dot"); }
     MatExpr t() const;
     MatExpr inv(int method = DECOMP_LU) const;

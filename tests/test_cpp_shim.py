@@ -162,7 +162,7 @@ def test_shim_builds_in_orbslam2_mode(tmp_path):
                    f'#include "{ROOT}/eao-slam_b200/host/ProbabilityMapping.h"\n'
                    'long unsigned int ORB_SLAM2::KeyFrame::nNextMappingId = 1;\n'
                    'int main() { ORB_SLAM2::Map m; ProbabilityMapping pm(&m); pm.RequestFinish(); pm.Run();\n'
-                   '             pm.GetModeler(); return pm.isFinished() ? 0 : 1; }\n')
+                   '             pm.GetModeler(); pm.LineFittingOnDevice(); return pm.isFinished() ? 0 : 1; }\n')
     out = str(tmp_path / "orb")
     subprocess.run(["g++", "-std=c++11", "-O1", "-Wall", "-I", os.path.join(ROOT, "oracle", "refshim"), "-I",
                     os.path.join(ROOT, "include"), str(src), "-o", out, "-L", LIBDIR, "-lsdm_b200", f"-Wl,-rpath,{LIBDIR}",
