@@ -44,10 +44,10 @@ def ed_chains(images):
     return res
 
 
-def main(out):
-    sc = synth.make_scene(SCENE["n_kf"], SCENE["W"], SCENE["H"], SCENE["n_nbr"], seed=SCENE["seed"])
+def main(out, scene=SCENE):
+    sc = synth.make_scene(scene["n_kf"], scene["W"], scene["H"], scene["n_nbr"], seed=scene["seed"], workers=8)
     chains = ed_chains(sc.im)
-    d = dict(scene=np.array([SCENE[k] for k in ("n_kf", "W", "H", "n_nbr", "seed")], np.int32),
+    d = dict(scene=np.array([scene[k] for k in ("n_kf", "W", "H", "n_nbr", "seed")], np.int32),
              im_crc=np.array([zlib.crc32(sc.im.tobytes())], np.uint32))
     for i, ch in enumerate(chains):
         lens = np.array([len(c) for c in ch], np.int32)
@@ -60,4 +60,9 @@ def main(out):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, "..", "tests", "golden", "ed_chains_small.npz"))
+    if len(sys.argv) > 1 and sys.argv[1] == "--bench":
+        # chains for tools/linefit_bench.py: 32 VGA keyframes of the bench trajectory (config 2's seed); 5 MB, kept out of
+        # git under oracle/_ref/ (travels to the GPU box with gpurun)
+        main(os.path.join(HERE, "_ref", "ed_chains_vga.npz"), dict(n_kf=32, W=640, H=480, n_nbr=6, seed=2))
+    else:
+        main(sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, "..", "tests", "golden", "ed_chains_small.npz"))
