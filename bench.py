@@ -377,7 +377,7 @@ def boundary_parity(a, plan, rank, world, out, owned):
     return checked, bad
 
 
-def class_e2e(a, sc, n_loc):
+def class_e2e(a, sc, n_loc, mode="--time"):
     """ProbabilityMapping::SemiDenseLoop() of the drop-in C++ class on the same keyframes (planes in pinned host memory,
     everything uploaded again in every repetition): tests/cpp/test_shim.cpp --time, compiled here with g++ -std=c++11."""
     import struct
@@ -390,7 +390,7 @@ def class_e2e(a, sc, n_loc):
     if r.returncode:
         return {"unavailable": "g++: " + r.stderr[-200:]}
     with open(scene_path, "wb") as f:
-        f.write(struct.pack("9i", n_loc, W, H, a.nbr, 0, 0, sc.nbr_idx.shape[1], 1, 11))
+        f.write(struct.pack("9i", n_loc, W, H, a.nbr, 0, 0, sc.nbr_idx.shape[1], 1, 11))  # (neighbour lists index < n_loc)
         f.write(np.asarray(sc.K, np.float32).tobytes())
         for i in range(n_loc):
             f.write(np.ascontiguousarray(sc.Tcw[i], np.float32).tobytes())
@@ -403,7 +403,7 @@ def class_e2e(a, sc, n_loc):
             f.write(struct.pack("i", 2)); f.write(inv.tobytes())
             f.write(np.ascontiguousarray(sc.nbr_idx[i], np.int32).tobytes())
             f.write(struct.pack("i", 0))
-    r = subprocess.run([exe, "--time", scene_path, out_path, str(max(2, a.steps))], capture_output=True, text=True)
+    r = subprocess.run([exe, mode, scene_path, out_path, str(max(2, a.steps))], capture_output=True, text=True)
     for f in (scene_path, out_path, exe):
         try:
             os.remove(f)
@@ -789,6 +789,18 @@ def main_ours(a, rank, world, local_rank):
                                         "sdm_run_loop, synchronise; planes in pinned host memory, all uploaded again every repetition"}
         else:
             line["e2e_class"] = r
+        # online mode (#define OnlineLoop, ProbabilityMapping.cc:42/:223-234): keyframes arrive one at a time
+        n_on = min(n_loc, 64)
+        nb_on = np.clip(sc.nbr_idx[:n_on], 0, n_on - 1).astype(np.int32)  # (the last keyframes never reach pass 2: not timed)
+        sc_on = synth.Scene(im=sc.im[:n_on], grad=sc.grad[:n_on], theta=sc.theta[:n_on], edge=None, K=sc.K, Tcw=sc.Tcw[:n_on],
+                            nbr_idx=nb_on, rot=sc.rot[:n_on], min_depth=sc.min_depth[:n_on], max_depth=sc.max_depth[:n_on])
+        r = class_e2e(a, sc_on, n_on, "--time-online")
+        if "ms_per_arrival_median" in r:
+            r["api"] = ("drop-in C++ class in online mode (harness tests/cpp/test_shim.cpp --time-online): one keyframe is added to the "
+                        "map, then SemiDenseLoop() + UpdateAllSemiDensePointSet() as the reference's Run() does per iteration; steady "
+                        "state = arrivals that finish exactly one keyframe (upload of the new planes, pass 1 of one keyframe, pass 2 "
+                        "of another, their planes back to pinned host memory); wall clock per arrival")
+        line["e2e_online"] = r
     if world == 1 and not a.no_cpu_baseline:
         r = cpu_run(a.cpu_sample_kf, a.nbr, a.seed, a.intra, 1, 0, a.wide, a.contrast)
         line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]}

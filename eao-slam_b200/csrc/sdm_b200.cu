@@ -1588,7 +1588,7 @@ int sdm_line_fit(sdm_ctx* c, int n, const sdm_edge_chains* sets, sdm_line3d* out
     L.sigma_lt = 0.02f;                                             // :29 (float against float)
     const int nc = (int)n_chains;
     CU(cudaEventRecord(c->lf_ev[0], s));
-    sdm::k_line_fit<<<(nc + 63) / 64, 64, 0, s>>>(c->A, c->P, L, (const sdm::LineFitKf*)(d + o_kfs), nc, (const int*)(d + o_off),
+    sdm::k_line_fit<<<(unsigned)(((size_t)nc * 32 + sdm::kLineFitBlock - 1) / sdm::kLineFitBlock), sdm::kLineFitBlock, 0, s>>>(c->A, c->P, L, (const sdm::LineFitKf*)(d + o_kfs), nc, (const int*)(d + o_off),
                                                   (const int*)(d + o_kfi), (const uint32_t*)(d + o_pix), (const int*)(d + o_slot0),
                                                   (sdm::DevLine*)(d + o_raw), (int*)(d + o_nout));
     sdm::k_line_scan<<<1, 1024, 0, s>>>((const int*)(d + o_nout), nc, (const sdm::LineFitKf*)(d + o_kfs), n,

@@ -2244,22 +2244,27 @@ __device__ __forceinline__ void lf_smallest_eigvec(double M[3][3], double v[3], 
     for (int sweep = 0; sweep < 12; ++sweep) {
         const double off = fabs(M[0][1]) + fabs(M[0][2]) + fabs(M[1][2]);
         if (off < 1e-300) break;
+#pragma unroll
         for (int p = 0; p < 2; ++p)
-            for (int q = p + 1; q < 3; ++q) {
+#pragma unroll
+            for (int q = p + 1; q < 3; ++q) {  // (compile-time indices: the matrices stay in registers)
                 if (M[p][q] == 0.0) continue;
                 const double theta = (M[q][q] - M[p][p]) / (2.0 * M[p][q]);
                 const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
                 const double cs = 1.0 / sqrt(t * t + 1.0), sn = t * cs;
+#pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     const double mkp = M[k][p], mkq = M[k][q];
                     M[k][p] = cs * mkp - sn * mkq;
                     M[k][q] = sn * mkp + cs * mkq;
                 }
+#pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     const double mpk = M[p][k], mqk = M[q][k];
                     M[p][k] = cs * mpk - sn * mqk;
                     M[q][k] = sn * mpk + cs * mqk;
                 }
+#pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     const double vkp = V[k][p], vkq = V[k][q];
                     V[k][p] = cs * vkp - sn * vkq;
@@ -2267,11 +2272,13 @@ __device__ __forceinline__ void lf_smallest_eigvec(double M[3][3], double v[3], 
                 }
             }
     }
-    int m = 0;
-    if (M[1][1] < M[m][m]) m = 1;
-    if (M[2][2] < M[m][m]) m = 2;
-    lam = M[m][m];
-    v[0] = V[0][m]; v[1] = V[1][m]; v[2] = V[2][m];
+    // the smallest diagonal entry (first one on ties), its eigenvector = that column of V
+    const bool m1 = M[1][1] < M[0][0];
+    const double d01 = m1 ? M[1][1] : M[0][0];
+    const bool m2 = M[2][2] < d01;
+    lam = m2 ? M[2][2] : d01;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) v[r] = m2 ? V[r][2] : (m1 ? V[r][1] : V[r][0]);
 }
 __device__ __forceinline__ void lf_line(const uint32_t* ch, int n, float& a, float& b, float& c, float& err)
 {
@@ -2348,14 +2355,21 @@ __device__ __forceinline__ float lf_point_depth(const LfPlanes& Q, const LineFit
 }
 
 // chains of a batch of keyframes: pixels packed (r << 16 | c); chain k = pix[off[k] .. off[k+1]) belongs to keyframe kfi[k];
-// its lines go to out[slot0[k] ..) (slot0 = prefix sum of len / min_len, the most lines a chain can hold), count in n_out[k]
-__global__ void __launch_bounds__(64) k_line_fit(DevArena A, DevParams P, LineFitParams L, const LineFitKf* __restrict__ kfs,
-                                                 int n_chains, const int* __restrict__ off, const int* __restrict__ kfi,
-                                                 const uint32_t* __restrict__ pix, const int* __restrict__ slot0,
-                                                 DevLine* __restrict__ out, int* __restrict__ n_out)
+// its lines go to out[slot0[k] ..) (slot0 = prefix sum of len / min_len, the most lines a chain can hold), count in n_out[k].
+// One WARP per chain.  What costs time in LineFit is the search for the first window of min_len pixels whose two fits both
+// stay below 1.0 (:723-744): on most chains hundreds of start positions are fitted and rejected (two least-squares problems
+// each), one after the other in the reference.  Here the 32 lanes fit 32 consecutive start positions at once and the
+// ballots below restore the sequential semantics (the first accepted position wins; without one the state of the LAST
+// fitted position is what :739-741 test).  The greedy growth and the final fits are short and stay on lane 0.
+// One thread per chain took 17.6 ms for the 28 527 chains of 32 VGA keyframes (its longest chain), this form 0.x ms.
+constexpr int kLineFitBlock = 128;
+__global__ void __launch_bounds__(kLineFitBlock) k_line_fit(DevArena A, DevParams P, LineFitParams L, const LineFitKf* __restrict__ kfs,
+                                                            int n_chains, const int* __restrict__ off, const int* __restrict__ kfi,
+                                                            const uint32_t* __restrict__ pix, const int* __restrict__ slot0,
+                                                            DevLine* __restrict__ out, int* __restrict__ n_out)
 {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= n_chains) return;
+    const int k = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
+    if (k >= n_chains) return;  // (a whole warp)
     const int ki = kfi[k];
     const LineFitKf F = kfs[ki];
     L.fx = F.K[0]; L.fy = F.K[1]; L.cx = F.K[2]; L.cy = F.K[3];
@@ -2369,17 +2383,40 @@ __global__ void __launch_bounds__(64) k_line_fit(DevArena A, DevParams P, LineFi
     int no = 0;
     const float inf = __int_as_float(0x7f800000);
     for (;;) {
-        float err_l = inf, err_d = inf, a = 0, b = 0, c = 0, alpha = 0, beta = 0;
+        float err_l = inf, err_d = inf, a = 0, b = 0, c = 0, alpha = 0, beta = 0;  // warp-uniform
         const int init = L.min_len;
         while (n > init && init < L.max_len) {
-            if (lf_count(Q, ch, 1) < 1 || lf_count(Q, ch, init) < L.init_depth_count) { ++ch; --n; continue; }
-            lf_line(ch, init, a, b, c, err_l);
-            lf_depth(Q, L, ch, init, a, b, c, alpha, beta, err_d);
-            if ((double)err_l <= 1.0 && (double)err_d <= 1.0) break;
-            ++ch; --n;
+            const bool valid = n - lane > init;  // start positions ch + 0 .. that the sequential loop would still visit
+            bool ev = false, ok = false;
+            float la = 0, lb = 0, lc = 0, lel = inf, lal = 0, lbe = 0, led = inf;
+            if (valid) {
+                const uint32_t* w = ch + lane;
+                if (lf_count(Q, w, 1) >= 1 && lf_count(Q, w, init) >= L.init_depth_count) {
+                    ev = true;
+                    lf_line(w, init, la, lb, lc, lel);
+                    lf_depth(Q, L, w, init, la, lb, lc, lal, lbe, led);
+                    ok = (double)lel <= 1.0 && (double)led <= 1.0;
+                }
+            }
+            const unsigned b_ok = __ballot_sync(SDM_FULL, ok), b_ev = __ballot_sync(SDM_FULL, ev);
+            const unsigned b_val = __ballot_sync(SDM_FULL, valid);
+            // the first accepted position ends the search there; otherwise every valid position was consumed and the
+            // state is the one of the last position that was fitted (if any)
+            const int src = b_ok ? __ffs(b_ok) - 1 : (b_ev ? 31 - __clz(b_ev) : -1);
+            const int adv = b_ok ? src : __popc(b_val);
+            if (src >= 0) {
+                a = __shfl_sync(SDM_FULL, la, src); b = __shfl_sync(SDM_FULL, lb, src); c = __shfl_sync(SDM_FULL, lc, src);
+                alpha = __shfl_sync(SDM_FULL, lal, src); beta = __shfl_sync(SDM_FULL, lbe, src);
+                err_l = __shfl_sync(SDM_FULL, lel, src); err_d = __shfl_sync(SDM_FULL, led, src);
+            }
+            ch += adv;
+            n -= adv;
+            if (b_ok) break;
         }
         if (err_l > L.e1 || err_d > L.e2) break;  // (inf when no window was ever fitted; NaN compares false like :739-741)
-        int interval = 0, len = init;
+        int len = init;
+        if (lane == 0) {
+        int interval = 0;
         while (len < L.max_len && len < n) {
             const uint32_t rc = ch[len];
             const float dist = fabsf(a * (float)(rc & 0xffffu) + b * (float)(rc >> 16) + c) / sqrtf(a * a + b * b);
@@ -2431,10 +2468,12 @@ __global__ void __launch_bounds__(64) k_line_fit(DevArena A, DevParams P, LineFi
                 o[no++] = d;
             }
         }
+        }
+        len = __shfl_sync(SDM_FULL, len, 0);
         ch += len;
         n -= len;
     }
-    n_out[k] = no;
+    if (lane == 0) n_out[k] = no;
 }
 
 // exclusive scan of the per-chain line counts (one block) + per-keyframe totals; then the compaction: chain k copies its

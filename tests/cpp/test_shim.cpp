@@ -5,6 +5,8 @@
 //   test_shim scene.bin out.bin                 offline mode: Run() = one loop + SaveSemiDensePoints (dir: env SDM_SHIM_RESULTS)
 //   test_shim --online scene.bin seq.bin out.bin   the online sequence of oracle/refshim/refdriver.cc::ref_online_sequence
 //   test_shim --time scene.bin out.bin reps     offline loop repeated on fresh flags, wall-clock per SemiDenseLoop()
+//   test_shim --time-online scene.bin out.bin   online mode (#define OnlineLoop, ProbabilityMapping.cc:42/:223-234): keyframes arrive
+//                                               one at a time, wall-clock of SemiDenseLoop() + UpdateAllSemiDensePointSet() per arrival
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -50,7 +52,8 @@ static void dump_planes(FILE* o, std::vector<std::unique_ptr<KeyFrame>>& kfs, in
 int main(int argc, char** argv)
 {
     const bool online = argc > 1 && std::string(argv[1]) == "--online";
-    const bool timing = argc > 1 && std::string(argv[1]) == "--time";
+    const bool timing_online = argc > 1 && std::string(argv[1]) == "--time-online";
+    const bool timing = timing_online || (argc > 1 && std::string(argv[1]) == "--time");
     if (online || timing) { argv++; argc--; }
     if (argc < 3) { fprintf(stderr, "usage: test_shim [--online|--time] scene.bin [seq.bin] out.bin [reps]\n"); return 2; }
     FILE* f = fopen(argv[1], "rb");
@@ -95,7 +98,7 @@ int main(int argc, char** argv)
         int32_t bad;
         rd(f, &bad, 4);
         kf->mbBad = bad != 0;
-        if (!online) {
+        if (!online && !timing_online) {
             kf->IncreaseMappingId();
             map.AddKeyFrame(kf);
         }
@@ -161,6 +164,45 @@ int main(int argc, char** argv)
         fwrite(pts.data(), sizeof(sdm_point), np, o);
         fclose(o);
         printf("shim online ok: capacity %d -> %d, %zu points\n", cap0, pm.ArenaCapacity(), np);
+        return 0;
+    }
+    if (timing_online) {  // one keyframe arrives, the semi-dense thread runs its loop body (Run(), :223-234)
+        pm.SetOnline(true);
+        KeyFrame::nNextMappingId() = 1;
+        std::vector<double> ms;
+        std::vector<int> done_after, cap_after;
+        for (int i = 0; i < n; i++) {
+            kfs[i]->IncreaseMappingId();
+            map.AddKeyFrame(kfs[i].get());
+            const std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+            pm.SemiDenseLoop();
+            pm.UpdateAllSemiDensePointSet();
+            ms.push_back(std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+            int d = 0;
+            for (int k = 0; k < n; k++) d += kfs[k]->interKF_depth_flag_;
+            done_after.push_back(d);
+            cap_after.push_back(pm.ArenaCapacity());
+        }
+        // steady state = arrivals that finished exactly one more keyframe (pass 1 of one keyframe + pass 2 of another) on an
+        // arena that did not have to grow; arrivals that outgrew the arena (a larger context is created and the finished
+        // keyframes are re-seeded on first use) are reported separately
+        std::vector<double> steady;
+        double regrow_ms = 0;
+        int regrows = 0;
+        for (int i = 1; i < n; i++) {
+            if (cap_after[i] != cap_after[i - 1] && cap_after[i - 1] > 0) { regrows++; regrow_ms = std::max(regrow_ms, ms[i]); continue; }
+            if (done_after[i] == done_after[i - 1] + 1 && done_after[i - 1] > 0) steady.push_back(ms[i]);
+        }
+        std::sort(steady.begin(), steady.end());
+        const size_t m = steady.size();
+        printf("{\"ms_per_arrival_median\": %.3f, \"ms_per_arrival_p90\": %.3f, \"ms_per_arrival_max\": %.3f, \"steady_arrivals\": %zu, "
+               "\"arrivals\": %d, \"finished\": %d, \"arena_regrows\": %d, \"ms_worst_arrival_with_regrow\": %.1f}\n",
+               m ? steady[m / 2] : 0.0, m ? steady[(m * 9) / 10] : 0.0, m ? steady[m - 1] : 0.0, m, n, done_after.back(), regrows,
+               regrow_ms);
+        FILE* o = fopen(argv[2], "wb");
+        if (!o) { perror("out"); return 2; }
+        dump_planes(o, kfs, W, H);
+        fclose(o);
         return 0;
     }
     if (timing) {  // wall-clock of SemiDenseLoop() itself, the call System.cc's thread makes (bench.py: e2e.api)

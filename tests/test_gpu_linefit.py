@@ -126,6 +126,45 @@ def test_line_fit_on_dense_planes_batched_and_single(golden):
     print("dense planes:", len(lines), "lines (oracle", n_ref, ");", same, "of", tot, "chains identical")
 
 
+def edge_index_from_chains(off, pix, H, W):
+    """LineDetector::DetectEdgeMap's mask (LineDetector.cc:857-866): mEdgeIndex starts at -1 (KeyFrame.h:174) and
+    mEdgeIndex(r, c) = i for every pixel of chain i, in chain order (a later chain overwrites an earlier one)"""
+    e = np.full((H, W), -1, np.int32)
+    ids = np.repeat(np.arange(len(off) - 1, dtype=np.int32), np.diff(off))
+    e[(pix >> 16).astype(np.int64), (pix & 0xffff).astype(np.int64)] = ids  # numpy assigns in order: last write wins
+    return e
+
+
+def test_loop_with_the_real_edge_drawing_mask_then_line_fit(golden):
+    """What the reference actually runs: the candidate filter of ProbabilityMapping.cc:454 on the mEdgeIndex plane of the
+    real edge detector (golden chains from EDLib.a), the whole SemiDenseLoop bit for bit against the oracle, then the
+    line fitting over the same chains on the planes that loop left on the device - depth now sits exactly on the chains."""
+    from helpers import compare_planes, run_oracle
+    sc, offs, pix = golden
+    H, W = sc.shape
+    sc = synth.Scene(im=sc.im, grad=sc.grad, theta=sc.theta,
+                     edge=np.stack([edge_index_from_chains(offs[i], pix[i], H, W) for i in range(sc.n)]), K=sc.K, Tcw=sc.Tcw,
+                     nbr_idx=sc.nbr_idx, rot=sc.rot, min_depth=sc.min_depth, max_depth=sc.max_depth)
+    assert 0.05 < (sc.edge >= 0).mean() < 0.3
+    osc = run_oracle(sc)   # the shipped loop: intra-keyframe stages commented out (:491-494)
+    with api.Context(width=W, height=H, max_keyframes=sc.n) as ctx:
+        ctx.upload_scene(sc)
+        for i in range(sc.n):
+            assert ctx.candidate_count(i) == int(((sc.grad[i] > 8) & (sc.edge[i] >= 0)).sum())
+        items = api.make_items(range(sc.n), sc.nbr_idx, sc.rot, sc.min_depth, sc.max_depth)
+        ctx.pass1(items); ctx.pass2(items)
+        lines, counts = ctx.line_fit(list(range(sc.n)), offs, pix)
+        planes = [ctx.download(i) for i in range(sc.n)]
+    dev = {k: np.stack([p[k] for p in planes]) for k in ("depth", "sigma", "checked", "points")}
+    rep = compare_planes(dev, osc)
+    assert all(rep[k + "_bit_mismatch"] == 0 for k in ("depth", "sigma", "checked", "points")), rep
+    assert not (dev["checked"] > 0)[sc.edge < 0].any(), "depth only on edge-chain pixels"
+    ref = [LO.line_fitting(LO.Planes(osc.checked[i], osc.sigma[i], sc.K, _twc(sc.Tcw[i])), _chains(offs[i], pix[i]))
+           for i in range(sc.n)]
+    same, tot = _compare(lines, counts, ref, min_chains=12, min_share=0.85)
+    print("real ED mask:", rep["pass2_accepted_ref"], "checked pixels;", len(lines), "lines;", same, "of", tot, "chains identical")
+
+
 def test_line_fit_rejects_bad_arguments(golden):
     sc, offs, pix = golden
     H, W = sc.shape
