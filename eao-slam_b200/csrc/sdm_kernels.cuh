@@ -2237,8 +2237,8 @@ __device__ __forceinline__ int lf_count(const LfPlanes& Q, const uint32_t* ch, i
     for (int i = 0; i < n; ++i) k += lf_has_depth(Q, ch[i]);
     return k;
 }
-// smallest eigenpair of the symmetric 3x3 M (cyclic Jacobi, double)
-__device__ __forceinline__ void lf_smallest_eigvec(double M[3][3], double v[3], double& lam)
+// smallest eigenpair of the symmetric 3x3 M (cyclic Jacobi, double): the robust form, used where the direct one below declines
+__device__ __noinline__ void lf_smallest_eigvec_jacobi(double M[3][3], double v[3], double& lam)
 {
     double V[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
     for (int sweep = 0; sweep < 12; ++sweep) {
@@ -2279,6 +2279,49 @@ __device__ __forceinline__ void lf_smallest_eigvec(double M[3][3], double v[3], 
     lam = m2 ? M[2][2] : d01;
 #pragma unroll
     for (int r = 0; r < 3; ++r) v[r] = m2 ? V[r][2] : (m1 ? V[r][1] : V[r][0]);
+}
+// The same eigenvector without iterating: the smallest root of the characteristic cubic in its trigonometric form, one
+// Rayleigh-quotient correction of it, and the eigenvector as the largest cross product of two rows of M - lambda I.  For
+// windows of pixel chains (eigenvalues ~ 1e-4 / 25 / 5e5, relative gap between the two small ones >= 7e-7) the unit vector
+// agrees with Jacobi's / LAPACK's to 5e-12, i.e. (a, b, c) are the same floats except for an occasional last bit; ten times
+// fewer double-precision operations than the sweeps (which dominated k_line_fit: 2.59 -> 0.54 ms per 32 VGA keyframes).  When
+// the two small eigenvalues (nearly) coincide - repeated pixels, fewer than two distinct points - the cross products
+// vanish and Jacobi takes over.  The sign of the vector is arbitrary here as in any SVD; every use is sign-invariant.
+__device__ __forceinline__ void lf_smallest_eigvec(double M[3][3], double v[3], double& lam)
+{
+    const double m00 = M[0][0], m01 = M[0][1], m02 = M[0][2], m11 = M[1][1], m12 = M[1][2], m22 = M[2][2];
+    const double p1 = m01 * m01 + m02 * m02 + m12 * m12;
+    const double q = (m00 + m11 + m22) / 3.0;
+    const double b00 = m00 - q, b11 = m11 - q, b22 = m22 - q;
+    const double p2 = b00 * b00 + b11 * b11 + b22 * b22 + 2.0 * p1;
+    bool ok = p2 > 0.0;
+    if (ok) {
+        const double pp = sqrt(p2 / 6.0), ip = 1.0 / pp;
+        const double c00 = b00 * ip, c11 = b11 * ip, c22 = b22 * ip, c01 = m01 * ip, c02 = m02 * ip, c12 = m12 * ip;
+        double r = 0.5 * (c00 * (c11 * c22 - c12 * c12) - c01 * (c01 * c22 - c12 * c02) + c02 * (c01 * c12 - c11 * c02));
+        r = fmin(1.0, fmax(-1.0, r));
+        double l = q + 2.0 * pp * cos(acos(r) / 3.0 + 2.0943951023931954923084289221863);
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const double r0x = m00 - l, r0y = m01, r0z = m02, r1x = m01, r1y = m11 - l, r1z = m12, r2x = m02, r2y = m12, r2z = m22 - l;
+            double ax = r0y * r1z - r0z * r1y, ay = r0z * r1x - r0x * r1z, az = r0x * r1y - r0y * r1x;  // row0 x row1
+            const double bx = r0y * r2z - r0z * r2y, by = r0z * r2x - r0x * r2z, bz = r0x * r2y - r0y * r2x;  // row0 x row2
+            const double cx = r1y * r2z - r1z * r2y, cy = r1z * r2x - r1x * r2z, cz = r1x * r2y - r1y * r2x;  // row1 x row2
+            double na = ax * ax + ay * ay + az * az;
+            const double nb = bx * bx + by * by + bz * bz, nc = cx * cx + cy * cy + cz * cz;
+            if (nb > na) { ax = bx; ay = by; az = bz; na = nb; }
+            if (nc > na) { ax = cx; ay = cy; az = cz; na = nc; }
+            ok = na > 1e-18 * p2 * p2;  // |cross| ~ (largest - l) * (middle - l): the two small eigenvalues are apart
+            if (!ok) break;
+            const double in = 1.0 / sqrt(na);
+            v[0] = ax * in; v[1] = ay * in; v[2] = az * in;
+            if (it == 0)
+                l = v[0] * (m00 * v[0] + m01 * v[1] + m02 * v[2]) + v[1] * (m01 * v[0] + m11 * v[1] + m12 * v[2]) +
+                    v[2] * (m02 * v[0] + m12 * v[1] + m22 * v[2]);
+        }
+        lam = l;
+    }
+    if (!ok) lf_smallest_eigvec_jacobi(M, v, lam);
 }
 __device__ __forceinline__ void lf_line(const uint32_t* ch, int n, float& a, float& b, float& c, float& err)
 {
@@ -2361,7 +2404,8 @@ __device__ __forceinline__ float lf_point_depth(const LfPlanes& Q, const LineFit
 // each), one after the other in the reference.  Here the 32 lanes fit 32 consecutive start positions at once and the
 // ballots below restore the sequential semantics (the first accepted position wins; without one the state of the LAST
 // fitted position is what :739-741 test).  The greedy growth and the final fits are short and stay on lane 0.
-// One thread per chain took 17.6 ms for the 28 527 chains of 32 VGA keyframes (its longest chain), this form 0.x ms.
+// One thread per chain took 17.6 ms for the 28 527 chains of 32 VGA keyframes (its longest chain), this form 2.6 ms,
+// 0.54 ms with the direct eigenvector (lf_smallest_eigvec).
 constexpr int kLineFitBlock = 128;
 __global__ void __launch_bounds__(kLineFitBlock) k_line_fit(DevArena A, DevParams P, LineFitParams L, const LineFitKf* __restrict__ kfs,
                                                             int n_chains, const int* __restrict__ off, const int* __restrict__ kfi,
