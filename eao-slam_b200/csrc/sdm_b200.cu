@@ -924,7 +924,7 @@ int sdm_upload_keyframes(sdm_ctx* c, int n, const sdm_upload_desc* d)
             if (any_image)  // GradImg / GradTheta produced on the device from im_ (KeyFrame.cc:69-74)
                 sdm::k_pack_image<<<tile_grid(c, m), dim3(32, 8), 0, c->s_compute>>>(c->A, c->P, B);
             if (c->A.skip)  // skip distances of the third-generation scan loop, from the texels just packed
-                sdm::k_skip<<<dim3((W + sdm::kSkipSpan - 1) / sdm::kSkipSpan, H, m), sdm::kSkipSpan, 0, c->s_compute>>>(c->A, c->P, B);
+                sdm::k_skip<<<dim3(1, H, m), sdm::kSkipSpan, 0, c->s_compute>>>(c->A, c->P, B);
             c->launches += 1 + (any_planes ? 1 : 0) + (any_image ? 1 : 0) + (c->A.skip ? 1 : 0);
         }
         static_assert(kUpStages / 2 <= sdm::kSlotList, "slot list of k_publish_counts");
