@@ -777,6 +777,7 @@ def main_ours(a, rank, world, local_rank):
                 "note": "as e2e_point_export, but only im_ is uploaded: GradImg / GradTheta (KeyFrame.cc:69-74) are "
                         "produced on the device by k_pack_image"}
     line["scan_generation"] = ctx.scan_generation()
+    line["scan_long_build"] = ctx.last_scan_long()
     ctx.close()
     if world == 1 and do_e2e and not a.no_e2e_variants:
         r = class_e2e(a, sc, n_loc)

@@ -68,6 +68,7 @@ constexpr int kUpStages = 48;   // upload staging sets (im, grad, theta, edge): 
 constexpr int kDownStages = 6;  // (rho | sigma) split staging sets
 constexpr int kItemStages = 32;  // pinned work-order staging buffers (how many passes the host may run ahead)
 constexpr int kMaxPeers = 16;
+constexpr int kLongScanColumns = 128;  // mean search range (columns) above which sdm_pass1 launches k_pass1_lane's long-scan build
 constexpr int kIntraChunk = 64;  // keyframes per batched intra launch (bounds the tmp arena)
 
 // A ring of CUDA events addressed by monotonically increasing ids.  id 0 = "never".  An id that has
@@ -288,6 +289,7 @@ struct sdm_ctx {
     bool trace = false;
     cudaEvent_t trace_base = nullptr;
     std::vector<TraceRec> trace_recs;
+    bool last_scan_long = false;  // the last sdm_pass1 ran the long-scan instantiation of k_pass1_lane
     int scan_warp_per_pixel = 0;  // developer A/B knob (env SDM_SCAN=warp): the warp-per-pixel scan kernel; 2 = warp_tma:
                                   // the same with neighbour tiles staged in shared memory by TMA (k_pass1_tma)
     CUtensorMap tex_map;          // the texel arena as a TMA tensor {4 floats, W, slots * H} (warp_tma only)
@@ -828,6 +830,7 @@ int sdm_synchronize(sdm_ctx* c)
 }
 
 int sdm_scan_generation(sdm_ctx* c) { return !c || c->scan_warp_per_pixel ? 0 : (c->P.scan2 ? c->P.scan2 : 1); }
+int sdm_last_scan_long(sdm_ctx* c) { return c && c->last_scan_long ? 1 : 0; }
 
 int sdm_get_stats(sdm_ctx* c, sdm_stats* out)
 {
@@ -1065,7 +1068,34 @@ int sdm_pass1(sdm_ctx* c, int n, const sdm_item* items)
         int occ = 0;  // persistent grid: fill every SM to this launch's occupancy
         // the exact short forms of the two direction gates exist for the reference's thresholds only
         const bool fast = (c->cfg.lambdaL == 80 && c->cfg.lambdaTheta == 45);
-        auto kern = !fast ? sdm::k_pass1_lane<false, 2> : (c->P.scan2 == 3 ? sdm::k_pass1_lane<true, 3> : sdm::k_pass1_lane<true, 2>);
+        // long scans: the 64-register instantiation (k_pass1_lane's kLong).  Mean search range of the batch's pairs, taken at
+        // the principal point: u(d) = fx * X / Z + cx of R21 * (0, 0, 1) * d + t21 at the two depth bounds (GetSearchRange, :1598-1631)
+        bool long_scans = false;
+        if (fast && c->P.scan2 == 3) {
+            const char* env = getenv("SDM_SCAN_LONG");  // developer knob: 0 / 1 forces the choice
+            if (env && (env[0] == '0' || env[0] == '1')) {
+                long_scans = env[0] == '1';
+            } else {
+                const sdm::DevItem* h_items = (const sdm::DevItem*)b.stage->host;
+                double sum = 0;
+                long cnt = 0;
+                for (int i = 0; i < n; ++i)
+                    for (int j = 0; j < h_items[i].n_nbr; ++j) {
+                        const sdm::DevPair& p = h_items[i].pair[j];
+                        const float z0 = p.R[8] * h_items[i].min_depth + p.t[2], z1 = p.R[8] * h_items[i].max_depth + p.t[2];
+                        if (!(z0 > 0.f) || !(z1 > 0.f)) continue;
+                        const float u0 = h_items[i].K[0] * (p.R[2] * h_items[i].min_depth + p.t[0]) / z0;
+                        const float u1 = h_items[i].K[0] * (p.R[2] * h_items[i].max_depth + p.t[0]) / z1;
+                        sum += std::min((double)fabsf(u1 - u0), (double)c->cfg.width);
+                        ++cnt;
+                    }
+                long_scans = cnt > 0 && sum / (double)cnt > (double)kLongScanColumns;
+            }
+        }
+        c->last_scan_long = long_scans;
+        auto kern = !fast ? sdm::k_pass1_lane<false, 2>
+                          : (c->P.scan2 == 3 ? (long_scans ? sdm::k_pass1_lane<true, 3, true> : sdm::k_pass1_lane<true, 3, false>)
+                                             : sdm::k_pass1_lane<true, 2>);
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, sdm::kLaneBlock, smem));
         kern<<<std::max(1, occ) * c->n_sm, sdm::kLaneBlock, smem, c->s_compute>>>(c->A, c->P, c->d_items, plan, c->d_stats, item_bytes);
     }

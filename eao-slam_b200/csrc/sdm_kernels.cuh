@@ -1434,8 +1434,16 @@ __device__ __forceinline__ bool next_piece(const DevPlan& plan, const DevItem* _
     return true;
 }
 
-template <bool kFastGates, int kGen = 2>
-__global__ void __launch_bounds__(kLaneBlock, kGen == 3 ? SDM_LANE3_MINB : SDM_LANE_MINB)
+// kLong: the build for long scans (hundreds of columns per (pixel, neighbour): large images, wide depth ranges).  There the
+// skip walk is bound by the latency of its dependent loads, not by issue slots, and 64 registers / 8 blocks per SM (no
+// spill, a larger share of L1 per warp) beat 48 registers / 10 blocks: 27.9 vs 30.4 ms per 48 keyframes of BASELINE config 4
+// (7 / 6 / 5 / 4 blocks: 29.1 / 29.1 / 31.6 / 31.7), while config 2 (55 columns per scan) measures 8.46 vs 8.02 ms the other
+// way round.  sdm_pass1 picks the instantiation per launch from the mean search range of the batch's pairs.
+#ifndef SDM_LANE3_LONG_MINB
+#define SDM_LANE3_LONG_MINB 8
+#endif
+template <bool kFastGates, int kGen = 2, bool kLong = false>
+__global__ void __launch_bounds__(kLaneBlock, kGen == 3 ? (kLong ? SDM_LANE3_LONG_MINB : SDM_LANE3_MINB) : SDM_LANE_MINB)
 k_pass1_lane(DevArena A, DevParams P, const DevItem* __restrict__ items, DevPlan plan, DevStats* stats, int item_bytes)
 {
     // dynamic shared memory, sized at launch for the largest neighbour count of the batch (the rest stays L1):

@@ -93,7 +93,7 @@ EXPORTS = [
     "sdm_pair_geometry", "sdm_stereo_search_constraints", "sdm_search_range", "sdm_inter_chi_test",
     "sdm_epipolar_search", "sdm_epipolar_search_plane", "sdm_fuse", "sdm_intra_check", "sdm_intra_grow",
     "sdm_inter_check", "sdm_last_pass_ms", "sdm_launch_count", "sdm_last_timing", "sdm_last_pack_ms", "sdm_mark", "sdm_elapsed_ms",
-    "sdm_line_fit", "sdm_last_line_fit_ms",
+    "sdm_line_fit", "sdm_last_line_fit_ms", "sdm_last_scan_long",
 ]
 
 _lib = None
@@ -139,6 +139,7 @@ def load() -> C.CDLL:
     lib.sdm_export_points.argtypes = [vp, C.c_int, ip, C.c_double, vp, sz, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.sdm_line_fit.argtypes = [vp, C.c_int, C.POINTER(EdgeChains), vp, sz, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
     lib.sdm_last_line_fit_ms.argtypes = [vp, fp]
+    lib.sdm_last_scan_long.argtypes = [vp]
     lib.sdm_upload_depth.argtypes = [vp, C.c_int, vp, sz, vp, sz]
     lib.sdm_upload_checked.argtypes = [vp, C.c_int, vp, sz]
     lib.sdm_depth_plane_ptr.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(sz)]
@@ -423,6 +424,9 @@ class Context:
 
     def scan_generation(self) -> int:
         return int(self.lib.sdm_scan_generation(self.h))
+
+    def last_scan_long(self) -> bool:
+        return bool(self.lib.sdm_last_scan_long(self.h))
 
     def stats(self) -> dict:
         st = Stats()

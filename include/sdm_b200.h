@@ -104,6 +104,9 @@ int sdm_get_stats(sdm_ctx* ctx, sdm_stats* out);
  * outside [0, 360] or |rot| > 360).  env SDM_SCAN=lane1 | lane2 | lane3 forces one; SDM_SCAN=warp selects the
  * warp-per-pixel kernel of the survey's plan (kept for A/B, 2-4x slower; reported as 0).  Results are bit-identical. */
 int sdm_scan_generation(sdm_ctx* ctx);
+/* 1 if the last sdm_pass1 ran the scan kernel's build for long scans (mean search range of the batch above 128 columns:
+ * 64 registers / 8 blocks per SM instead of 48 / 10; same arithmetic, same results); env SDM_SCAN_LONG=0|1 forces it */
+int sdm_last_scan_long(sdm_ctx* ctx);
 
 /* pinned host memory for asynchronous uploads/downloads (optional; any host pointer is accepted) */
 int sdm_host_alloc(void** ptr, size_t bytes);

@@ -119,6 +119,23 @@ def test_scan_generations_agree(monkeypatch):
             assert ctx.scan_generation() == gen
             assert _bit_equal(run_device(sc, ctx=ctx), osc) == zero
     monkeypatch.delenv("SDM_SCAN")
+    # the two builds of the third-generation kernel (48 registers / 10 blocks per SM; 64 / 8 for long scans): forced, then
+    # chosen by sdm_pass1 from the batch's mean search range (this scene: short; a wide depth range: long)
+    for force, want in (("0", False), ("1", True)):
+        monkeypatch.setenv("SDM_SCAN_LONG", force)
+        with api.Context(width=320, height=240, max_keyframes=sc.n) as ctx:
+            assert _bit_equal(run_device(sc, ctx=ctx), osc) == zero
+            assert ctx.last_scan_long() is want
+    monkeypatch.delenv("SDM_SCAN_LONG")
+    with api.Context(width=320, height=240, max_keyframes=sc.n) as ctx:
+        run_device(sc, ctx=ctx)
+        assert ctx.last_scan_long() is False
+    wide = synth.make_scene(8, 640, 480, 6, seed=21, contrast=0.9, wide_range=True)
+    with api.Context(width=640, height=480, max_keyframes=wide.n) as ctx:
+        dev = run_device(wide, ctx=ctx)
+        picked = ctx.last_scan_long()
+    assert _bit_equal(dev, run_oracle(wide)) == zero
+    print("wide-range scene: long-scan build picked:", picked)
     with api.Context(width=320, height=240, max_keyframes=sc.n, lambdaG=9) as ctx:
         assert ctx.scan_generation() == 1          # not the reference's constants
 
