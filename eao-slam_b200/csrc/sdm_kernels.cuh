@@ -1123,6 +1123,39 @@ __device__ __forceinline__ int scan_columns2(const float4* __restrict__ texw2, c
     return best_n > 0 ? ub + 1 - best_n : -1;
 }
 
+// Cache policies of the walk's three loads, A/B-timed on one box (scan ms, config 2 / config 4; plain ld.global.nc everywhere:
+// 8.012 / 28.08): skip byte L1::evict_last 7.977 / 27.93 (kept: the byte's sector serves the next ~12 visits of the lane),
+// intensity pair L1::no_allocate 8.436 / 30.87, both 8.415 / 30.71, texel L1::evict_first 8.721 / 33.42.
+__device__ __forceinline__ unsigned ld_skip(const char* p)
+{
+#if !defined(SDM_SKIP_PLAIN_LOAD)
+    unsigned v;
+    asm volatile("ld.global.nc.L1::evict_last.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(reinterpret_cast<const uint8_t*>(p));
+#endif
+}
+__device__ __forceinline__ uchar2 ld_ipair(const char* p)
+{
+#if defined(SDM_IPAIR_NOALLOC)
+    unsigned short v;
+    asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(v) : "l"(p));
+    return make_uchar2((unsigned char)(v & 0xffu), (unsigned char)(v >> 8));
+#else
+    return __ldg(reinterpret_cast<const uchar2*>(p));
+#endif
+}
+__device__ __forceinline__ float4 ld_texel(const char* p)
+{
+#if defined(SDM_TEXEL_EVICT_FIRST)
+    float4 v;
+    asm volatile("ld.global.nc.L1::evict_first.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+    return v;
+#else
+    return __ldg(reinterpret_cast<const float4*>(p));
+#endif
+}
 // ---------------------------------------------------------------------------------------------
 // Third-generation column loop (kMode 3): scan_columns2's arithmetic on the columns that can matter.  The loop of
 // scan_columns2 is bound by instruction issue and evaluates every column of the search range although 53 % of them
@@ -1162,8 +1195,8 @@ __device__ __forceinline__ int scan_columns3(const float4* __restrict__ texw2, c
     float r = __fadd_rd(vn, kMagic);
     float w1n = vn - (r - kMagic);
     unsigned idxn = __float_as_uint(r) * Wm + k;
-    float4 tn = __ldg(reinterpret_cast<const float4*>(tb + (size_t)idxn * 16));
-    unsigned sn = __ldg(reinterpret_cast<const uint8_t*>(sb + (size_t)idxn));
+    float4 tn = ld_texel(tb + (size_t)idxn * 16);
+    unsigned sn = ld_skip(sb + (size_t)idxn);
 #pragma unroll kScan2Unroll
     while (n > 0) {
         const float4 t = tn;
@@ -1181,8 +1214,8 @@ __device__ __forceinline__ int scan_columns3(const float4* __restrict__ texw2, c
         r = __fadd_rd(vn, kMagic);
         w1n = vn - (r - kMagic);
         idxn = __float_as_uint(r) * Wm + k;
-        tn = __ldg(reinterpret_cast<const float4*>(tb + (size_t)idxn * 16));
-        sn = __ldg(reinterpret_cast<const uint8_t*>(sb + (size_t)idxn));
+        tn = ld_texel(tb + (size_t)idxn * 16);
+        sn = ld_skip(sb + (size_t)idxn);
         const float2 w01 = make_float2(w0, w1);
         const float2 gp = __fmul2_rn(make_float2(t.x, t.y), w01);
         const float g2 = gp.x + gp.y;
@@ -1196,7 +1229,7 @@ __device__ __forceinline__ int scan_columns3(const float4* __restrict__ texw2, c
         const float d2 = gth - th_line;
         const float ang = d2 < 0.f ? d2 + 360.f : d2;  // condition 2
         if (fabsf(fabsf(ang - 180.f) - 90.f) <= 10.f) continue;
-        const uchar2 i2 = __ldg(reinterpret_cast<const uchar2*>(ib + (size_t)idx * 2));
+        const uchar2 i2 = ld_ipair(ib + (size_t)idx * 2);
         const float2 ip = __fmul2_rn(make_float2((float)i2.x, (float)i2.y), w01);
         const float2 res = __fadd2_rn(make_float2(pixel, gradc), make_float2(-(ip.x + ip.y), -g2));
         const float2 sq = __fmul2_rn(res, res);
