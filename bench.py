@@ -83,6 +83,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-e2e-variants", action="store_true", help="skip e2e_scatter / e2e_point_export / e2e_image_in_points_out / e2e_class")
+    ap.add_argument("--no-balance", action="store_true", help="strong-scaling configs at N > 1: equal keyframe counts per rank instead of equal estimated cost")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the boundary-keyframe check against the oracle")
     ap.add_argument("--no-hot-spin", action="store_true", help="profiling runs: skip the ~0.6 s of extra untimed steps")
     return ap.parse_args()
@@ -414,10 +415,49 @@ def class_e2e(a, sc, n_loc, mode="--time"):
     return json.loads(r.stdout.strip().splitlines()[-1])
 
 
+def balance_bounds(a, rank, world):
+    """Strong scaling: cut the trajectory into contiguous ranges of equal estimated COST instead of equal keyframe counts.
+    Every rank renders the keyframes of its equal-count range, reports per keyframe the candidate pixels and the width of
+    the inverse-depth search interval (what the scan length is proportional to); the ranks swap these through files in the
+    node's tmp directory (before CUDA / NCCL are initialised, like the render itself) and all compute the same bounds."""
+    import tempfile
+    G = a.kf * world
+    own_lo = rank * a.kf
+    sc = load_scene(a.kf, own_lo, np.zeros((a.kf, a.nbr), np.int32), a.seed, "gpu_own", a.wide, a.contrast)
+    cands = (sc.grad > 8).reshape(a.kf, -1).sum(1).astype(np.float64)
+    width = (1.0 / sc.max_depth.astype(np.float64) - 1.0 / sc.min_depth.astype(np.float64))
+    d = os.path.join(tempfile.gettempdir(), f"sdm_balance_{os.getppid()}_{os.environ.get('MASTER_PORT', '0')}_c{a.config}_s{a.seed}_{G}_{world}")
+    os.makedirs(d, exist_ok=True)
+    tmp = os.path.join(d, f".r{rank}.npy")
+    np.save(tmp, np.stack([cands, width]))
+    os.replace(tmp, os.path.join(d, f"r{rank}.npy"))
+    parts, t0 = [], time.time()
+    for r in range(world):
+        f = os.path.join(d, f"r{r}.npy")
+        while not os.path.exists(f):
+            if time.time() - t0 > 900:
+                raise RuntimeError(f"rank {rank}: no shard weights from rank {r} after 900 s")
+            time.sleep(0.05)
+        parts.append(np.load(f))
+    allc = np.concatenate([p[0] for p in parts])
+    allw = np.concatenate([p[1] for p in parts])
+    # 70 % of the scan kernel's instructions are in the column loop (proportional to the search range), the rest per candidate
+    weights = allc * (0.3 + 0.7 * allw / max(allw.mean(), 1e-30))
+    return shard.balanced_bounds(weights, world), weights
+
+
 def main_ours(a, rank, world, local_rank):
     dist = None
     nb_global = synth.neighbours(a.kf * world, a.nbr)
-    plan = shard.make_plan(nb_global, a.kf, rank, world)
+    bounds, shard_note = None, None
+    if world > 1 and a.scaling == "strong" and not a.no_balance:
+        bounds, wts = balance_bounds(a, rank, world)
+        cost = [float(wts[bounds[r]:bounds[r + 1]].sum()) for r in range(world)]
+        eq = [float(wts[r * a.kf:(r + 1) * a.kf].sum()) for r in range(world)]
+        shard_note = {"bounds": [int(b) for b in bounds], "estimated_cost_max_over_mean": max(cost) / (sum(cost) / world),
+                      "equal_count_shards_would_be": max(eq) / (sum(eq) / world),
+                      "weights": "candidate pixels x (0.3 + 0.7 x width of the inverse-depth search interval / its mean)"}
+    plan = shard.make_plan(nb_global, a.kf, rank, world, bounds)
     nb_local = np.where(plan.nbr_local >= 0, plan.nbr_local, 0).astype(np.int32)
     sc = load_scene(plan.n_local, plan.lo, nb_local, a.seed, "gpu", a.wide, a.contrast)  # before CUDA init (forks workers)
 
@@ -706,7 +746,8 @@ def main_ours(a, rank, world, local_rank):
     n_own = len(owned)
     p1_bytes = bytes_pass1(n_own, a.nbr)
     ach = p1_bytes / (timing["pass1_scan_ms"] * 1e-3) / 1e9
-    whole_bytes = bytes_total(n_own * world, a.nbr, a.intra)
+    G_total = a.kf * world
+    whole_bytes = bytes_total(G_total, a.nbr, a.intra)
     whole = whole_bytes / (ms_max * 1e-3) / 1e9 / world
     whole_c = whole_bytes / ((ms_max + timing["pack_ms"]) * 1e-3) / 1e9 / world
     line = {
@@ -714,8 +755,8 @@ def main_ours(a, rank, world, local_rank):
         "warmup": max(3, a.warmup), "ms_per_step": ms_max, "higher_is_better": True, "scaling": a.scaling,
         "vs_baseline": None, "dtype": "f32 (f64 where OpenCV accumulates in double)", "data": "synthetic",
         "config": workload_config(a, a.kf),
-        "candidates_per_step": tot_cands, "keyframes_per_s": n_own * world / (ms_max * 1e-3),
-        "image_px_per_s": n_own * world * W * H / (ms_max * 1e-3), "us_per_keyframe_per_gpu": 1e3 * ms_max / n_own,
+        "candidates_per_step": tot_cands, "keyframes_per_s": G_total / (ms_max * 1e-3),
+        "image_px_per_s": G_total * W * H / (ms_max * 1e-3), "us_per_keyframe_per_gpu": 1e3 * ms_max / a.kf,
         "fused_per_step_rank0": stats["fused"], "checked_per_step_rank0": stats["checked"],
         "kernel_ms_rank0": timing,
         "roofline": {"bound": "hbm", "kernel": "k_pass1_lane (epipolar scan + hypothesis fusion)", "achieved": ach,
@@ -731,6 +772,8 @@ def main_ours(a, rank, world, local_rank):
         "clocks": clocks.summary(t0, t1),
         "gpu_launches": int(launches),
     }
+    if shard_note:
+        line["sharding"] = shard_note
     if a.config == 3:
         budget_ms = 0.5 ** -1 * whole_bytes / world / (peak * 1e9) * 1e3
         line["north_star"] = {"target": "1000 keyframes / 8 GPUs at >= 50 % of the HBM roofline",
