@@ -663,8 +663,20 @@ def main_ours(a, rank, world, local_rank):
         e2e["blocks_same"] = all(np.array_equal(out[k][::5].view(np.uint32), ref_planes[k].view(np.uint32)) for k in out)
         if not e2e["blocks_same"]:
             print("WARNING: block-sparse download differs from the dense download", file=sys.stderr)
-        del ref_planes
         e2e["blocks_d2h"] = int(ctx.candidate_blocks(owned) * 16 * 24)
+        # variant: dense DMA of the three 4-byte planes, block-sparse kernel for SemiDensePointSets_ only (sparse_download = 2)
+        for k in out:
+            out[k][:] = 0
+        e2e_step(blocks=2)
+        barrier(); tt = time.perf_counter()
+        for _ in range(a.steps):
+            e2e_step(blocks=2)
+        barrier(); e2e["hybrid_sec"] = (time.perf_counter() - tt) / a.steps
+        e2e["hybrid_same"] = all(np.array_equal(out[k][::5].view(np.uint32), ref_planes[k].view(np.uint32)) for k in out)
+        if not e2e["hybrid_same"]:
+            print("WARNING: hybrid download differs from the dense download", file=sys.stderr)
+        e2e["hybrid_d2h"] = int(len(owned) * W * H * 12 + e2e["blocks_d2h"] // 2)
+        del ref_planes
     if do_e2e and not a.no_e2e_variants:
         # the same loop with sdm_scatter_keyframes: the planes start zero-initialised like KeyFrame.cc:78-81 leaves them
         # and only the candidate pixels' records cross PCIe.  Checked against the dense result on every 7th keyframe.
@@ -720,14 +732,15 @@ def main_ours(a, rank, world, local_rank):
     blocks_ok = 1.0 if (e2e and e2e.get("blocks_same")) else 0.0
     sparse_max = e2e.get("sparse_sec", 0.0) if e2e else 0.0
     sparse_same = 1.0 if (e2e and e2e.get("sparse_same")) else 0.0
+    hyb_max = e2e.get("hybrid_sec", 0.0) if e2e else 0.0
     par_n, par_bad = parity if parity else (0, 0)
     if world > 1:
         v = torch.tensor([float(cands), float(par_n), float(par_bad), 1.0 if parity else 0.0], device="cuda", dtype=torch.float64)
         dist.all_reduce(v); tot_cands, par_n, par_bad, par_ranks = (int(x) for x in v.tolist())
         xs = [e2e.get("export_sec", 0.0), e2e.get("image_sec", 0.0)] if e2e else [0.0, 0.0]
-        m = torch.tensor([ms, e2e_max, sparse_max, -sparse_same] + xs + [dense_max, -blocks_ok], device="cuda", dtype=torch.float64)
+        m = torch.tensor([ms, e2e_max, sparse_max, -sparse_same] + xs + [dense_max, -blocks_ok, hyb_max], device="cuda", dtype=torch.float64)
         dist.all_reduce(m, op=dist.ReduceOp.MAX)
-        ms_max, e2e_max, sparse_max, sparse_same, x_sec, i_sec, dense_max, blocks_ok = m.tolist()
+        ms_max, e2e_max, sparse_max, sparse_same, x_sec, i_sec, dense_max, blocks_ok, hyb_max = m.tolist()
         sparse_same, blocks_ok = -sparse_same, -blocks_ok
         if e2e and "export_sec" in e2e:
             pv = torch.tensor([float(e2e["export_points"]), float(e2e["image_points"])], device="cuda", dtype=torch.float64)
@@ -798,6 +811,13 @@ def main_ours(a, rank, world, local_rank):
                                   "api": "the same call with sparse_download = 1: the result planes start zero-initialised as "
                                          "KeyFrame.cc:78-81 leaves them and a kernel writes only the 16-pixel blocks that hold a "
                                          "candidate pixel over PCIe (rank 0's byte count)"}
+        if "hybrid_sec" in e2e:
+            line["e2e_points_blocks"] = {"value": tot_cands / hyb_max, "unit": UNIT, "h2d_bytes_per_step": e2e["h2d"],
+                                         "d2h_bytes_per_step": e2e["hybrid_d2h"], "ms_per_step": 1e3 * hyb_max,
+                                         "identical_to_dense_download": bool(e2e["hybrid_same"]),
+                                         "api": "the same call with sparse_download = 2: depth_map_, depth_sigma_, depth_map_checked_ leave "
+                                                "by DMA, SemiDensePointSets_ (zero-initialised like KeyFrame.cc:81) receives only its "
+                                                "16-pixel blocks that hold a candidate, written by a kernel on a second stream"}
         if "sparse_sec" in e2e:
             # The sparse path moves 3.7x fewer bytes over PCIe but its host-side scatter touches nearly every cache line of
             # the planes at this candidate density (23 %), so it is host-memory bound and slower here; a variant.

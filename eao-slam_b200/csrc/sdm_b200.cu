@@ -284,6 +284,8 @@ struct sdm_ctx {
     std::vector<int32_t> halo_local, halo_rank, halo_slot;
     std::vector<char> is_halo;  // per slot
     cudaStream_t s_halo = nullptr;
+    cudaStream_t s_down_k = nullptr;  // sparse_download = 2: the block-sparse kernel for SemiDensePointSets_ runs here, next to the DMAs of s_down
+    cudaEvent_t ev_down_k = nullptr;
     int grid_pass1_warp = 0, grid_pass2 = 0, grid_intra = 0, n_sm = 0;  // persistent grids (blocks)
     long long launches = 0;
     bool trace = false;
@@ -574,6 +576,8 @@ void sdm_destroy(sdm_ctx* c)
     }
     cudaFree(c->xflags);
     if (c->s_halo) cudaStreamDestroy(c->s_halo);
+    if (c->s_down_k) cudaStreamDestroy(c->s_down_k);
+    if (c->ev_down_k) cudaEventDestroy(c->ev_down_k);
     cudaFree(c->A.tex); cudaFree(c->A.ipair); cudaFree(c->A.texw); cudaFree(c->A.cand); cudaFree(c->A.cand_count);
     cudaFree(c->A.plane_irregular); cudaFree(c->A.skip); cudaFree(c->A.blk);
     cudaFree(c->A.rs); cudaFree(c->A.chk); cudaFree(c->A.pts); cudaFree(c->A.dpl); cudaFree(c->A.spl); cudaFree(c->A.rs2);
@@ -658,6 +662,8 @@ static int create_impl(sdm_ctx* c)
         int lo = 0, hi = 0;
         CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
         CU(cudaStreamCreateWithPriority(&c->s_down, cudaStreamNonBlocking, hi));
+        CU(cudaStreamCreateWithPriority(&c->s_down_k, cudaStreamNonBlocking, hi));
+        CU(cudaEventCreateWithFlags(&c->ev_down_k, cudaEventDisableTiming));
     }
     CU(cudaStreamCreateWithFlags(&c->s_halo, cudaStreamNonBlocking));
     CU(cudaMalloc(&c->xflags, sizeof(sdm::XFlags)));
@@ -1243,7 +1249,7 @@ static float* pinned_dev_ptr(float* host)
 }
 
 // returns 1 when a destination plane is not pinned (nothing was enqueued), else SDM_OK / an error
-static int sparse_to_pinned(sdm_ctx* c, int n, const sdm_download_desc* d)
+static int sparse_to_pinned(sdm_ctx* c, int n, const sdm_download_desc* d, cudaStream_t s)
 {
     std::vector<sdm::SparseDst> dst((size_t)n);
     uint64_t need = 0;
@@ -1259,7 +1265,6 @@ static int sparse_to_pinned(sdm_ctx* c, int n, const sdm_download_desc* d)
         if (d[i].points && !(t.points = pinned_dev_ptr(d[i].points))) return 1;
         need = std::max(need, c->kf[d[i].kf].comp_id);
     }
-    cudaStream_t s = c->s_down;
     RC(c->r_compute.wait(s, need));
     const int H = c->cfg.height;
     for (int i0 = 0; i0 < n; i0 += sdm::kSparseBatch) {
@@ -1271,8 +1276,12 @@ static int sparse_to_pinned(sdm_ctx* c, int n, const sdm_download_desc* d)
         c->launches++;
     }
     CU(cudaGetLastError());
+    if (s != c->s_down) {  // the download ring lives on s_down: it continues behind this stream's kernels
+        CU(cudaEventRecord(c->ev_down_k, s));
+        CU(cudaStreamWaitEvent(c->s_down, c->ev_down_k, 0));
+    }
     uint64_t id = 0;
-    RC(c->r_down.record(s, &id));
+    RC(c->r_down.record(c->s_down, &id));
     for (int i = 0; i < n; ++i) {
         if (d[i].depth || d[i].sigma) c->kf[d[i].kf].down_ds_id = id;
         if (d[i].checked || d[i].points) c->kf[d[i].kf].down_cp_id = id;
@@ -1317,7 +1326,7 @@ int sdm_scatter_keyframes(sdm_ctx* c, int n, const sdm_download_desc* d)
     CU(cudaSetDevice(c->cfg.device));
     {   // destination planes in pinned (device-visible) host memory: a kernel writes the candidate blocks of every row
         // straight into them over PCIe - no staging, no host threads
-        int rc = sparse_to_pinned(c, n, d);
+        int rc = sparse_to_pinned(c, n, d, c->s_down);
         if (rc != 1) return rc;  // 1 = some plane is pageable: candidate records + host-side scatter below
     }
     if (!c->scat) RC(scatter_init(c));
@@ -1842,15 +1851,32 @@ int sdm_exchange(sdm_ctx* c)
 
 // results of a chunk to the host: the block-sparse kernel when the caller vouches for zero-initialised destination planes
 // and they are pinned, the dense DMA otherwise
-static int download(sdm_ctx* c, int n, const sdm_download_desc* d, bool sparse)
+// mode 0: dense DMA of every plane; 1: block-sparse kernel for every plane (pinned, zero-initialised destinations);
+// 2: dense DMA of the three 4-byte planes + block-sparse kernel for SemiDensePointSets_ (61 % of the dense bytes) on its
+// own stream, so that the copy engine and the SM-issued writes share the link
+static int download(sdm_ctx* c, int n, const sdm_download_desc* d, int mode)
 {
-    if (sparse) {
+    if (mode) {
         bool ok = true;
         for (int i = 0; i < n && ok; ++i) ok = slot_ok(c, d[i].kf) && !c->kf[d[i].kf].rs_dense && !c->kf[d[i].kf].split_stale;
-        if (ok) {
+        if (ok && mode == 1) {
             CU(cudaSetDevice(c->cfg.device));
-            const int rc = sparse_to_pinned(c, n, d);
+            const int rc = sparse_to_pinned(c, n, d, c->s_down);
             if (rc != 1) return rc;
+        } else if (ok) {
+            bool any_pts = false;
+            std::vector<sdm_download_desc> dense(d, d + n), pts(d, d + n);
+            for (int i = 0; i < n; ++i) {
+                any_pts |= d[i].points != nullptr;
+                dense[i].points = nullptr;
+                pts[i].depth = pts[i].sigma = pts[i].checked = nullptr;
+            }
+            if (any_pts) {
+                CU(cudaSetDevice(c->cfg.device));
+                const int rc = sparse_to_pinned(c, n, pts.data(), c->s_down_k);
+                if (rc < 0) return rc;
+                if (rc == 0) return sdm_download_keyframes(c, n, dense.data());
+            }
         }
     }
     return sdm_download_keyframes(c, n, d);
@@ -1911,7 +1937,7 @@ int sdm_run_loop(sdm_ctx* c, const sdm_loop* L)
                 if (L->down2) dl.push_back(L->down2[idx[i0 + i]]);
             }
             RC(sdm_pass2(c, (int)m, batch.data()));
-            if (!dl.empty()) RC(download(c, (int)dl.size(), dl.data(), L->sparse_download != 0));
+            if (!dl.empty()) RC(download(c, (int)dl.size(), dl.data(), L->sparse_download));
         }
         return SDM_OK;
     };
@@ -1930,7 +1956,7 @@ int sdm_run_loop(sdm_ctx* c, const sdm_loop* L)
                 next_up = need + 1;
             }
             RC(sdm_pass1(c, m, L->pass1 + i0));
-            if (L->down1) RC(download(c, m, L->down1 + i0, L->sparse_download != 0));
+            if (L->down1) RC(download(c, m, L->down1 + i0, L->sparse_download));
         }
         // pass 2 of the work orders whose pass-1 inputs are all queued, one chunk behind: the newest chunk's pass 1 is
         // queued first so that the SMs never wait for a download

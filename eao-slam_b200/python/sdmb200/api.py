@@ -545,7 +545,7 @@ class Context:
         L.n_pass2 = len(pass2) if pass2 is not None else 0
         L.pass2 = pass2 if pass2 is not None else None
         L.down2 = down2 if down2 is not None else None
-        L.chunk, L.exchange, L.sparse_download = int(chunk), int(bool(exchange)), int(bool(sparse))
+        L.chunk, L.exchange, L.sparse_download = int(chunk), int(bool(exchange)), int(sparse)  # sparse: 0 | 1 (True) | 2
         self._keep_loop = (upload, pass1, down1, pass2, down2)
         self._chk(self.lib.sdm_run_loop(self.h, C.byref(L)))
 

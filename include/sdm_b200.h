@@ -316,7 +316,10 @@ typedef struct {
                               * (KeyFrame.cc:78-81) - the contract of sdm_scatter_keyframes.  Planes in pinned host memory then
                               * receive only the 16-pixel blocks that hold a candidate pixel, written by a kernel over PCIe
                               * (about half the bytes of the dense DMA on textured scenes, far less with an edge mask);
-                              * pageable planes get the dense DMA.  Identical host planes either way. */
+                              * pageable planes get the dense DMA.  Identical host planes either way.
+                              * 2: the same contract for SemiDensePointSets_ only (61 % of the dense bytes): the three 4-byte
+                              * planes leave by DMA while a kernel on a second stream writes the point blocks, so the copy
+                              * engine and the SM-issued writes share the link. */
 } sdm_loop;
 int sdm_run_loop(sdm_ctx* ctx, const sdm_loop* loop);
 

@@ -108,6 +108,14 @@ def test_block_sparse_download_into_pinned_planes(W, H):
                 assert not out[k][:, :, (3 * W if k == "points" else W):].any(), "padding columns untouched"
             nblk = ctx.candidate_blocks(range(sc.n))
             assert 0 < nblk <= sc.n * H * ((W + 15) // 16)
+            # sparse_download = 2: the 4-byte planes by DMA, SemiDensePointSets_ block-sparse on a second stream
+            for k in out:
+                out[k][:] = 0
+            ctx.run_loop(upload=up, pass1=items, down1=d1, pass2=items, down2=d2, chunk=4, sparse=2)
+            ctx.synchronize()
+            for k in out:
+                assert np.array_equal(view[k].view(np.uint32), ref[k].view(np.uint32)), ("mode 2", k)
+                assert not out[k][:, :, (3 * W if k == "points" else W):].any(), "padding columns untouched"
             for k in out:
                 out[k][:] = 0
             ctx.scatter_keyframes(d4)            # the entry point itself: pinned planes take the kernel route
