@@ -117,7 +117,13 @@ public:
         for (int i = 0; i < m.rows; i++) memcpy(n.data + (size_t)(rows + i) * n.step, m.data + (size_t)i * m.step, (size_t)m.cols * m.elemSize());
         *this = n;
     }
-    double dot(const Mat&) const { stub_dead("Mat::dot"); }
+    double dot(const Mat& m) const  // cv::Mat::dot: products accumulated in double (the semi-dense path never calls it; LineFit does, :809-810)
+    {
+        double s = 0;
+        for (int i = 0; i < rows; i++)
+            for (int j = 0; j < cols; j++) s += (double)at<float>(i, j) * (double)m.at<float>(i, j);
+        return s;
+    }
     MatExpr t() const;
     MatExpr inv(int method = DECOMP_LU) const;
 
@@ -390,6 +396,7 @@ inline void phase(const Mat&, const Mat&, Mat&, bool) { stub_dead("cv::phase"); 
 struct SVD {
     enum { MODIFY_A = 1, FULL_UV = 4 };
     static void compute(const Mat&, Mat&, Mat&, Mat&, int) { stub_dead("cv::SVD::compute"); }
+    static void solveZ(const Mat& A, Mat& u);  // defined in cvstub_linefit.h (exact stand-in), used by LineDetector::LeastSquaresLineFit only
 };
 
 }  // namespace cv

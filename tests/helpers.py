@@ -112,3 +112,30 @@ def planes_that_grow(depth, sigma, seed):
     s = np.where(hole & (kind == 3), np.float32(0.5), s)
     d = np.where(hole, np.where(rng.random(d.shape) < 0.5, np.float32(0.0), np.float32(9.9e-7)), d)
     return np.ascontiguousarray(d, np.float32), np.ascontiguousarray(s, np.float32)
+
+
+def linefit_dense_planes(H, W, n, seed=5):
+    """depth_map_checked_ / depth_sigma_ planes on which LineFit finds thousands of lines: piecewise-planar inverse depth
+    (80 x 80 blocks) with 0.2 % noise, 30 % holes and 10 % wide-sigma pixels.  Shared by tests/test_gpu_linefit.py and
+    oracle/make_linefit_golden.py (same seed = same planes)."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    bx, by = (xx // 80).astype(int) % 5, (yy // 80).astype(int) % 4
+    chk, sig = [], []
+    for _ in range(n):
+        a, b = rng.uniform(-1e-3, 1e-3, (2, 4, 5)).astype(np.float32)
+        c0 = rng.uniform(0.3, 1.2, (4, 5)).astype(np.float32)
+        inv = (c0[by, bx] + a[by, bx] * (xx % 80) + b[by, bx] * (yy % 80)).astype(np.float32)
+        inv *= (1 + rng.normal(0, 2e-3, inv.shape)).astype(np.float32)
+        chk.append(np.where(rng.random(inv.shape) < 0.3, 0, inv).astype(np.float32))
+        sig.append(np.where(rng.random(inv.shape) < 0.1, 0.03, 0.01).astype(np.float32))
+    return chk, sig
+
+
+def edge_index_from_chains(off, pix, H, W):
+    """LineDetector::DetectEdgeMap's mask (LineDetector.cc:857-866): mEdgeIndex starts at -1 (KeyFrame.h:174) and
+    mEdgeIndex(r, c) = i for every pixel of chain i, in chain order (a later chain overwrites an earlier one)"""
+    e = np.full((H, W), -1, np.int32)
+    ids = np.repeat(np.arange(len(off) - 1, dtype=np.int32), np.diff(off))
+    e[(pix >> 16).astype(np.int64), (pix & 0xffff).astype(np.int64)] = ids  # numpy assigns in order: last write wins
+    return e

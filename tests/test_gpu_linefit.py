@@ -7,7 +7,12 @@ Parity level: the device solves the two least-squares problems in closed form in
 Jacobi SVD, so the fitted (a, b, c) / (alpha, beta) agree to float rounding and a decision that sits within ~1e-2 of a
 threshold (lineFitError <= 1, depthFitError <= 1, point-depth distance > 1.5) can flip.  Stated bars: >= 97 % of the
 chains that produce a line on either side give the same number of lines with end points within 0.02 px and 3-D end
-points within 1e-3 relative; counting and ordering (per-keyframe counts, chain order) are exact properties."""
+points within 1e-3 relative; counting and ordering (per-keyframe counts, chain order) are exact properties.
+
+Second checker, without the solver noise: tests/golden/linefit_ref_small.npz holds the rows of the REFERENCE'S OWN LineFit
+text (LineDetector.cc:578-840 compiled where it lies, oracle/Makefile target ref_linefit, oracle/make_linefit_golden.py) with
+exact stand-ins for the two OpenCV solver calls - the kernel's control flow against the reference's source: >= 99.8 % of the
+chains identical on the dense planes, all of them on the loop's own planes."""
 import ctypes as C
 import os
 from collections import defaultdict
@@ -93,17 +98,7 @@ def test_line_fit_on_dense_planes_batched_and_single(golden):
     lines; a batch over all keyframes equals the per-keyframe calls row for row"""
     sc, offs, pix = golden
     H, W = sc.shape
-    rng = np.random.default_rng(5)
-    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
-    bx, by = (xx // 80).astype(int) % 5, (yy // 80).astype(int) % 4
-    chk, sig = [], []
-    for _ in range(sc.n):
-        a, b = rng.uniform(-1e-3, 1e-3, (2, 4, 5)).astype(np.float32)
-        c0 = rng.uniform(0.3, 1.2, (4, 5)).astype(np.float32)
-        inv = (c0[by, bx] + a[by, bx] * (xx % 80) + b[by, bx] * (yy % 80)).astype(np.float32)
-        inv *= (1 + rng.normal(0, 2e-3, inv.shape)).astype(np.float32)
-        chk.append(np.where(rng.random(inv.shape) < 0.3, 0, inv).astype(np.float32))
-        sig.append(np.where(rng.random(inv.shape) < 0.1, 0.03, 0.01).astype(np.float32))
+    chk, sig = linefit_dense_planes(H, W, sc.n)
     with api.Context(width=W, height=H, max_keyframes=sc.n) as ctx:
         ctx.upload_scene(sc)
         for i in range(sc.n):
@@ -124,15 +119,21 @@ def test_line_fit_on_dense_planes_batched_and_single(golden):
     assert n_ref > 1500 and abs(len(lines) - n_ref) <= 0.01 * n_ref
     same, tot = _compare(lines, counts, ref, min_chains=1000)
     print("dense planes:", len(lines), "lines (oracle", n_ref, ");", same, "of", tot, "chains identical")
+    # against the reference's own text with exact solvers: the control flow itself, no solver noise
+    gref = _golden_ref("dense", sc.n)
+    same_r, tot_r = _compare(lines, counts, gref, min_chains=1000, min_share=0.998)
+    assert len(lines) == sum(len(r) for r in gref)
+    print("dense planes vs the reference's LineFit text (exact solvers):", same_r, "of", tot_r, "chains identical")
 
 
-def edge_index_from_chains(off, pix, H, W):
-    """LineDetector::DetectEdgeMap's mask (LineDetector.cc:857-866): mEdgeIndex starts at -1 (KeyFrame.h:174) and
-    mEdgeIndex(r, c) = i for every pixel of chain i, in chain order (a later chain overwrites an earlier one)"""
-    e = np.full((H, W), -1, np.int32)
-    ids = np.repeat(np.arange(len(off) - 1, dtype=np.int32), np.diff(off))
-    e[(pix >> 16).astype(np.int64), (pix & 0xffff).astype(np.int64)] = ids  # numpy assigns in order: last write wins
-    return e
+from helpers import edge_index_from_chains, linefit_dense_planes  # noqa: E402
+
+
+def _golden_ref(tag, n):
+    """rows of the REFERENCE'S OWN LineFit text with exact solver stand-ins (oracle/make_linefit_golden.py), in the oracle's format"""
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "linefit_ref_small.npz"))
+    return [[(int(c), list(s), list(x)) for c, s, x in zip(gold[f"{tag}_chain_{i}"], gold[f"{tag}_seg_{i}"], gold[f"{tag}_xyz_{i}"])]
+            for i in range(n)]
 
 
 def test_loop_with_the_real_edge_drawing_mask_then_line_fit(golden):
@@ -162,7 +163,9 @@ def test_loop_with_the_real_edge_drawing_mask_then_line_fit(golden):
     ref = [LO.line_fitting(LO.Planes(osc.checked[i], osc.sigma[i], sc.K, _twc(sc.Tcw[i])), _chains(offs[i], pix[i]))
            for i in range(sc.n)]
     same, tot = _compare(lines, counts, ref, min_chains=12, min_share=0.85)
-    print("real ED mask:", rep["pass2_accepted_ref"], "checked pixels;", len(lines), "lines;", same, "of", tot, "chains identical")
+    same_r, tot_r = _compare(lines, counts, _golden_ref("mask", sc.n), min_chains=12, min_share=1.0)
+    print("real ED mask:", rep["pass2_accepted_ref"], "checked pixels;", len(lines), "lines;", same, "of", tot, "chains identical to the cv2 "
+          "oracle,", same_r, "of", tot_r, "to the reference's LineFit text")
 
 
 def test_line_fit_rejects_bad_arguments(golden):
