@@ -40,11 +40,34 @@ def main():
         for i in range(n):
             ctx.line_fit([i], [offs[i]], [pix[i]])
         per_kf_wall = (time.perf_counter() - t) * 1e3 / n
-        planes = [ctx.download(i) for i in range(2)]
+        planes = [ctx.download(i) for i in range(min(n, 8))]
     out = dict(what="sdm_line_fit over real ED chains, one call for all keyframes", keyframes=n, image=f"{W}x{H}",
                chains=int(sum(len(o) - 1 for o in offs)), chain_pixels=int(sum(p.size for p in pix)), lines=int(len(lines)),
                device_ms_per_call=float(np.median(dev)), wall_ms_per_call=float(np.median(wall)),
                device_us_per_keyframe=float(np.median(dev)) * 1e3 / n, wall_ms_per_keyframe_single_calls=per_kf_wall)
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libref_linefit.so")
+    if os.path.exists(ref_so):  # the reference's own LineFit text (exact solver stand-ins), one thread like LineFitting (:884-900)
+        import ctypes as C
+        lib = C.CDLL(ref_so)
+        lib.ref_line_fitting.restype = C.c_int
+        fp, ip = C.POINTER(C.c_float), C.POINTER(C.c_int32)
+        m = min(n, 8)
+        t, nl = time.perf_counter(), 0
+        for i in range(m):
+            rc = np.stack([(pix[i] >> 16).astype(np.int32), (pix[i] & 0xffff).astype(np.int32)], 1).copy()
+            cap = int((np.diff(offs[i]) // 10).sum()) + 1
+            seg, xyz, chn = np.zeros((cap, 4), np.float32), np.zeros((cap, 6), np.float32), np.zeros(cap, np.int32)
+            pl = planes[i] if i < len(planes) else None
+            if pl is None:
+                break
+            nl += lib.ref_line_fitting(W, H, np.ascontiguousarray(pl["checked"]).ctypes.data_as(fp), np.ascontiguousarray(pl["sigma"]).ctypes.data_as(fp),
+                                       np.asarray(sc.K, np.float32).ctypes.data_as(fp), np.ascontiguousarray(sc.Tcw[i], np.float32).ctypes.data_as(fp),
+                                       len(offs[i]) - 1, np.ascontiguousarray(offs[i], np.int32).ctypes.data_as(ip), rc.ctypes.data_as(ip), cap,
+                                       seg.ctypes.data_as(fp), xyz.ctypes.data_as(fp), chn.ctypes.data_as(ip))
+        out["reference_source_cpu_ms_per_keyframe"] = (time.perf_counter() - t) * 1e3 / m
+        out["reference_source_note"] = (f"LineDetector.cc:578-840 compiled where it lies (oracle/_ref/libref_linefit.so, exact solver stand-ins instead "
+                                        f"of OpenCV's SVD), one host thread, {m} keyframes, {nl} lines; device lines of the same keyframes: "
+                                        f"{int((lines['kf_index'] < m).sum())}")
     try:
         import ctypes as C
         import linefit_oracle as LO
