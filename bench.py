@@ -10,7 +10,8 @@ intrinsics, 6 covisible neighbours, intra + inter depth checks; N>1 (torchrun): 
 halo (rho,sigma) planes pulled from peers over NVLink between the passes, ordered on the devices (sdm_exchange:
 no host synchronisation or barrier inside a step).  The other BASELINE configs:
   --config 1  configs[0]: 10 keyframes (the reference's CPU-runnable correctness case)
-  --config 3  configs[2]: 1000 keyframes in total, sharded over the GPUs (strong scaling; 125 per GPU on 8)
+  --config 3  configs[2]: 1000 keyframes in total, sharded over the GPUs (strong scaling; contiguous shards of equal estimated
+              cost - candidate pixels x search-interval width, shard.balanced_bounds - unless --no-balance: 121-134 per GPU on 8)
   --config 4  configs[3]: 1280x960, 10 neighbours, wide inverse-depth range (long epipolar scans), 48 keyframes per GPU
   --config 5  configs[4]: 4096 keyframes in total (strong scaling), CPU arm on a 64-keyframe subset
 
@@ -19,7 +20,10 @@ no host synchronisation or barrier inside a step).  The other BASELINE configs:
 `e2e`     : the same through the C-ABI with pinned HOST buffers: H2D of every input plane, both passes,
             D2H of depth_map_/depth_sigma_/depth_map_checked_/SemiDensePointSets_ inside the timed region
             (sdm_run_loop: the library's own pipelined SemiDenseLoop); `e2e_class` = the same loop through the
-            drop-in C++ class, ProbabilityMapping::SemiDenseLoop() (tests/cpp/test_shim.cpp --time).
+            drop-in C++ class, ProbabilityMapping::SemiDenseLoop() (tests/cpp/test_shim.cpp --time); `e2e_online` = the class in
+            online mode, wall clock per arriving keyframe (--time-online).  Further variants in the same line, each checked
+            against the dense planes: e2e_blocks / e2e_points_blocks (sdm_loop.sparse_download = 1 / 2), e2e_scatter,
+            e2e_point_export, e2e_image_in_points_out.
 `--impl reference` : the CPU path (oracle/, a restatement of the reference's ProbabilityMapping; the
             reference itself cannot be compiled here) on all host cores, bounded sample.
 """
