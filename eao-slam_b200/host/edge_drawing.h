@@ -1,0 +1,390 @@
+// edge_drawing.h - open implementation of the Edge Drawing edge-segment detector that EAO-SLAM calls through the
+// closed-source Thirdparty/EDTest/EDLib.a:
+//     EdgeMap* map = DetectEdgesByED(srcImg, width, height, SOBEL_OPERATOR, 36, 8, 1.0);      LineDetector.cc:855
+// (LineDetector::DetectEdgeMap, :843-881: the edge chains feed LineFitting, :884-900, and their pixels are the mEdgeIndex mask
+// of the semi-dense hot loop, ProbabilityMapping.cc:454).  SURVEY.md 8(a17) / 8(f-2): "the upstream DetectEdgeMap mask (would
+// need an open ED re-implementation)".
+//
+// The algorithm is the published one (C. Topal, C. Akinlar, "Edge Drawing: A Combined Real-Time Edge and Segment Detector",
+// JVCIR 23(6), 2012): smooth, gradient magnitude + direction, anchors, smart routing from the anchors in decreasing gradient
+// order into a tree of chains, the longest path of the tree as the segment, the other long chains as further segments.  The
+// details that a black-box library leaves open were fixed by matching its OUTPUT: the binary runs in the build container,
+// so every stage was compared against it (oracle/ed_chains.cpp; tests/golden/ed_chains_*.npz hold its chains) until the
+// chains were identical - pixel for pixel, in order - on every test image: the six + 32 synthetic keyframes at 320x240 / 640x480,
+// the library's own lena.pgm (flipped, transposed, cropped, subsampled), and some 500 random images - noise, drawn shapes, smooth
+// blobs quantised to a few grey levels, sizes 12 .. 700 not multiples of four (tests/test_edge_drawing.py; fixtures
+// tests/golden/ed_chains_small.npz and ed_chains_misc.npz by oracle/make_ed_golden.py):
+//   * smoothing  = 5x5 binomial [1 4 6 4 1]^2 / 256, replicated border; rounding as cvSmooth(CV_GAUSSIAN, 5, 5) of the bundled
+//                  OpenCV 2.4.5 does it: half to even in the columns its 4-wide vector loop covers (x < W & ~3), half up in
+//                  the scalar tail (checked against that cvSmooth itself through its C API, tests/test_edge_drawing.py);
+//   * gradient   = |gx| + |gy| of the Sobel operator on the smoothed image, border pixels = threshold - 1; a pixel at or
+//                  above the threshold is a VERTICAL edge pixel if |gx| >= |gy|, else HORIZONTAL;
+//   * anchors    = every pixel of rows / columns 2 .. size-3 whose gradient exceeds both neighbours across the edge by >= 8;
+//   * routing    = from the anchors in decreasing gradient order (ties in raster order), depth first, the more recently
+//                  opened direction first (up before down, left before right); a walk looks for an already marked anchor /
+//                  edge pixel among its three forward neighbours - straight first, then the diagonals in an order that is
+//                  rotation-symmetric: up-left for LEFT and UP, down-right for RIGHT and DOWN - before it follows the largest
+//                  gradient; anchors beside a walked pixel (across the edge) are cleared;
+//   * extraction = trees with fewer than 10 new pixels are erased; the main segment is the longest path through the anchor,
+//                  further segments are the remaining chains whose longest path has >= 10 pixels; where two chains meet, pixels
+//                  that double back are dropped, and the first chain of a segment is compared with the LAST PIXEL OF THE
+//                  PREVIOUS SEGMENT (the library keeps all segments in one pixel array and reads one element before the
+//                  segment it is filling) - reproduced because it decides whether that chain's first pixel is kept.
+// Host code like the reference's call (it runs once per keyframe before the planes are uploaded; the routing is a sequential
+// walk).  Header-only, C++11, no dependencies.
+#pragma once
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+namespace sdm_host {
+
+struct EdgeChains {
+    std::vector<int32_t> offsets;  // n_chains + 1, offsets[0] = 0
+    std::vector<uint32_t> pixels;  // (row << 16) | col, chain k = pixels[offsets[k] .. offsets[k + 1])
+    int n_chains() const { return offsets.empty() ? 0 : (int)offsets.size() - 1; }
+};
+
+namespace ed_detail {
+
+enum { kEdgeVertical = 1, kEdgeHorizontal = 2, kLeft = 1, kRight = 2, kUp = 3, kDown = 4 };
+
+struct Px { int r, c; };
+struct Chain { int len, parent, dir, child[2], start; };
+struct Todo { int r, c, dir, parent; };
+
+inline bool adjacent(const Px& a, const Px& b) { return std::abs(a.r - b.r) <= 1 && std::abs(a.c - b.c) <= 1; }
+
+// length of the longest path below `root`; every visited chain keeps only the child on that path (first child on ties).
+// Iterative post-order (the trees of a textured image are thousands of chains deep).
+inline int longest_chain(std::vector<Chain>& ch, int root, std::vector<int>& best, std::vector<int>& order)
+{
+    if (root == -1 || ch[root].len == 0) return 0;
+    order.clear();
+    order.push_back(root);
+    for (size_t i = 0; i < order.size(); ++i) {  // pre-order list of the chains a recursive descent would visit
+        const Chain& c = ch[order[i]];
+        for (int k = 0; k < 2; ++k)
+            if (c.child[k] != -1 && ch[c.child[k]].len != 0) order.push_back(c.child[k]);
+    }
+    for (size_t i = order.size(); i-- > 0;) {
+        Chain& c = ch[order[i]];
+        const int l0 = (c.child[0] != -1 && ch[c.child[0]].len != 0) ? best[c.child[0]] : 0;
+        const int l1 = (c.child[1] != -1 && ch[c.child[1]].len != 0) ? best[c.child[1]] : 0;
+        int mx;
+        if (l0 >= l1) { mx = l0; c.child[1] = -1; } else { mx = l1; c.child[0] = -1; }
+        best[order[i]] = c.len + mx;
+    }
+    return best[root];
+}
+
+inline void retrieve_chain_nos(const std::vector<Chain>& ch, int root, std::vector<int>& nos)
+{
+    nos.clear();
+    while (root != -1) {
+        nos.push_back(root);
+        root = ch[root].child[0] != -1 ? ch[root].child[0] : ch[root].child[1];
+    }
+}
+
+}  // namespace ed_detail
+
+// The detector runs in two stages.  Stage 1 (EdPlanesHost) is per-pixel image work - smoothing, gradient, direction, anchor
+// test - and produces two planes: G (int16 gradient magnitude) and F (one flag byte per pixel).  Stage 2 (EdRouteChains) is
+// the sequential part: anchor order, smart routing, segment extraction.  libsdm_b200.so runs stage 1 on the device for a
+// batch of keyframes (k_ed_planes, csrc/sdm_kernels.cuh; C-ABI sdm_edge_drawing) and stage 2 here on host threads while the
+// next keyframes are on the device; both stage-1 forms produce identical planes (tests/test_gpu_edge_drawing.py).
+enum : uint8_t {
+    kEdDirMask = 3,       // F & 3: 0 = below the gradient threshold, 1 = vertical edge pixel, 2 = horizontal edge pixel
+    kEdFlagEdge = 0x40,   // set by the routing: pixel belongs to a walked chain
+    kEdFlagAnchor = 0x80  // set by stage 1: anchor; cleared by the routing when the pixel is walked or suppressed
+};
+
+// Stage 1 on the host.  G and F are dense W x H planes.  grad_thresh / anchor_thresh = the GRADIENT_THRESH / ANCHOR_THRESH
+// arguments of DetectEdgesByED (36 / 8 at LineDetector.cc:855; SOBEL_OPERATOR, sigma 1.0).  Needs W >= 5 and H >= 5.
+inline void EdPlanesHost(const uint8_t* im, size_t step, int W, int H, int grad_thresh, int anchor_thresh, int16_t* G, uint8_t* F)
+{
+    using namespace ed_detail;
+    const size_t P = (size_t)W * H;
+    // ---- smoothing: [1 4 6 4 1] x [1 4 6 4 1] / 256, replicated border
+    static thread_local std::vector<uint16_t> tmp;  // (work buffers are kept between calls: one call per keyframe)
+    static thread_local std::vector<uint8_t> sm;
+    tmp.resize(P);
+    sm.resize(P);
+    for (int y = 0; y < H; ++y) {
+        const uint8_t* s = im + (size_t)y * step;
+        uint16_t* t = &tmp[(size_t)y * W];
+        for (int x = 0; x < 2; ++x) t[x] = (uint16_t)(s[0] + 4 * s[std::max(x - 1, 0)] + 6 * s[x] + 4 * s[x + 1] + s[x + 2]);
+        for (int x = 2; x < W - 2; ++x) t[x] = (uint16_t)(s[x - 2] + 4 * s[x - 1] + 6 * s[x] + 4 * s[x + 1] + s[x + 2]);
+        for (int x = W - 2; x < W; ++x) t[x] = (uint16_t)(s[x - 2] + 4 * s[x - 1] + 6 * s[x] + 4 * s[std::min(x + 1, W - 1)] + s[W - 1]);
+    }
+    const int wsimd = W & ~3;
+    for (int y = 0; y < H; ++y) {
+        const uint16_t* r0 = &tmp[(size_t)std::max(y - 2, 0) * W];
+        const uint16_t* r1 = &tmp[(size_t)std::max(y - 1, 0) * W];
+        const uint16_t* r2 = &tmp[(size_t)y * W];
+        const uint16_t* r3 = &tmp[(size_t)std::min(y + 1, H - 1) * W];
+        const uint16_t* r4 = &tmp[(size_t)std::min(y + 2, H - 1) * W];
+        uint8_t* o = &sm[(size_t)y * W];
+        for (int x = 0; x < wsimd; ++x) {  // half to even (the library's vector loop)
+            const int v = r0[x] + 4 * r1[x] + 6 * r2[x] + 4 * r3[x] + r4[x];
+            const int q = v >> 8, rem = v & 255;
+            o[x] = (uint8_t)(q + ((rem > 128) | ((rem == 128) & (q & 1))));
+        }
+        for (int x = wsimd; x < W; ++x)  // half up (its scalar tail)
+            o[x] = (uint8_t)((r0[x] + 4 * r1[x] + 6 * r2[x] + 4 * r3[x] + r4[x] + 128) >> 8);
+    }
+    // ---- gradient magnitude (Sobel, |gx| + |gy|) and edge direction
+    std::fill(G, G + P, (int16_t)(grad_thresh - 1));
+    std::memset(F, 0, P);
+#define SM(y, x) ((int)sm[(size_t)(y) * W + (x)])
+    for (int y = 1; y < H - 1; ++y)
+        for (int x = 1; x < W - 1; ++x) {
+            const int com1 = SM(y + 1, x + 1) - SM(y - 1, x - 1), com2 = SM(y - 1, x + 1) - SM(y + 1, x - 1);
+            const int gx = std::abs(com1 + com2 + 2 * (SM(y, x + 1) - SM(y, x - 1)));
+            const int gy = std::abs(com1 - com2 + 2 * (SM(y + 1, x) - SM(y - 1, x)));
+            const int sum = gx + gy;
+            G[(size_t)y * W + x] = (int16_t)sum;
+            if (sum >= grad_thresh) F[(size_t)y * W + x] = gx >= gy ? kEdgeVertical : kEdgeHorizontal;
+        }
+#undef SM
+    // ---- anchors: gradient exceeds both neighbours across the edge by anchor_thresh
+    for (int y = 2; y < H - 2; ++y) {
+        const int16_t* g0 = G + (size_t)(y - 1) * W;
+        const int16_t* g1 = G + (size_t)y * W;
+        const int16_t* g2 = G + (size_t)(y + 1) * W;
+        uint8_t* f1 = F + (size_t)y * W;
+        for (int x = 2; x < W - 2; ++x) {
+            const int g = g1[x];
+            if (g < grad_thresh) continue;
+            const bool is_anchor = f1[x] == kEdgeVertical ? (g - g1[x - 1] >= anchor_thresh && g - g1[x + 1] >= anchor_thresh)
+                                                          : (g - g0[x] >= anchor_thresh && g - g2[x] >= anchor_thresh);
+            if (is_anchor) f1[x] |= kEdFlagAnchor;
+        }
+    }
+}
+
+// Stage 2: anchors in decreasing gradient order, smart routing, segment extraction.  F is modified in place (flags of the
+// walked pixels).  If edge_index is given (int32 plane, row pitch edge_step bytes) it receives what DetectEdgeMap leaves in
+// kf->mEdgeIndex: -1 everywhere (KeyFrame.cc:87), then the chain number of every chain pixel in chain order (:857-866).
+inline void EdRouteChains(int W, int H, const int16_t* G, uint8_t* F, int grad_thresh, EdgeChains& out,
+                          int32_t* edge_index = nullptr, size_t edge_step = 0)
+{
+    using namespace ed_detail;
+    out.offsets.assign(1, 0);
+    out.pixels.clear();
+    if (edge_index)
+        for (int y = 0; y < H; ++y) {
+            int32_t* row = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(edge_index) + (size_t)y * edge_step);
+            for (int x = 0; x < W; ++x) row[x] = -1;
+        }
+    if (W < 5 || H < 5) return;
+    const size_t P = (size_t)W * H;
+#define GR(y, x) ((int)G[(size_t)(y) * W + (x)])
+#define FL(y, x) F[(size_t)(y) * W + (x)]
+#define DI(y, x) (FL(y, x) & kEdDirMask)
+#define MARKED(y, x) ((FL(y, x) & (kEdFlagAnchor | kEdFlagEdge)) != 0)
+#define IS_ANCHOR(y, x) ((FL(y, x) & kEdFlagAnchor) != 0)
+#define IS_EDGE(y, x) ((FL(y, x) & kEdFlagEdge) != 0)
+    // ---- anchor order: decreasing gradient, raster order among equals (counting sort: |gx| + |gy| <= 2040)
+    static thread_local std::vector<int> found, anchors;
+    found.clear();
+    int hist[2048 + 1] = {0};
+    {
+        size_t i = 0;
+        for (; i + 8 <= P; i += 8) {  // eight flag bytes at a time
+            uint64_t w;
+            std::memcpy(&w, F + i, 8);
+            if ((w & 0x8080808080808080ull) == 0) continue;
+            for (int k = 0; k < 8; ++k)
+                if (F[i + k] & kEdFlagAnchor) { found.push_back((int)(i + k)); ++hist[2047 - std::min((int)G[i + k], 2047)]; }
+        }
+        for (; i < P; ++i)
+            if (F[i] & kEdFlagAnchor) { found.push_back((int)i); ++hist[2047 - std::min((int)G[i], 2047)]; }
+    }
+    {
+        int run = 0;
+        for (int i = 0; i <= 2047; ++i) { const int c = hist[i]; hist[i] = run; run += c; }
+        anchors.resize(found.size());
+        for (size_t i = 0; i < found.size(); ++i) anchors[hist[2047 - std::min((int)G[found[i]], 2047)]++] = found[i];
+    }
+
+    std::vector<Chain> chains;
+    std::vector<Px> pixels, seg;
+    std::vector<Todo> stack;
+    std::vector<int> best, order, nos;
+    bool have_prev = false;
+    Px prev_last = {0, 0};  // last pixel of the previously emitted segment (see the header comment)
+
+    auto emit = [&](const std::vector<Px>& s) {
+        const int32_t id = (int32_t)out.offsets.size() - 1;
+        for (size_t i = 0; i < s.size(); ++i) {
+            out.pixels.push_back(((uint32_t)s[i].r << 16) | (uint32_t)s[i].c);
+            if (edge_index) reinterpret_cast<int32_t*>(reinterpret_cast<char*>(edge_index) + (size_t)s[i].r * edge_step)[s[i].c] = id;
+        }
+        out.offsets.push_back((int32_t)out.pixels.size());
+        if (!s.empty()) { prev_last = s.back(); have_prev = true; }
+    };
+    // appends chain `cno` to `seg` in walking order, dropping the pixels that double back at the joint
+    auto append_forward = [&](int cno) {
+        Chain& c = chains[cno];
+        const Px first = pixels[c.start];
+        int idx = (int)seg.size() - 2;
+        while (idx >= 0 && adjacent(first, seg[idx])) { seg.pop_back(); --idx; }
+        int start = 0;
+        if (c.len > 1 && (!seg.empty() || have_prev)) {
+            const Px last = seg.empty() ? prev_last : seg.back();
+            if (adjacent(pixels[c.start + 1], last)) start = 1;
+        }
+        for (int l = start; l < c.len; ++l) seg.push_back(pixels[c.start + l]);
+        c.len = 0;  // copied
+    };
+
+    for (size_t a = 0; a < anchors.size(); ++a) {
+        const int ay = anchors[a] / W, ax = anchors[a] % W;
+        if (!IS_ANCHOR(ay, ax)) continue;
+        chains.clear();
+        pixels.clear();
+        stack.clear();
+        Chain root = {0, -1, 0, {-1, -1}, 0};
+        chains.push_back(root);
+        int dup = 0;
+        if (DI(ay, ax) == kEdgeVertical) {
+            stack.push_back(Todo{ay, ax, kDown, 0});
+            stack.push_back(Todo{ay, ax, kUp, 0});
+        } else {
+            stack.push_back(Todo{ay, ax, kRight, 0});
+            stack.push_back(Todo{ay, ax, kLeft, 0});
+        }
+        while (!stack.empty()) {
+            const Todo t = stack.back();
+            stack.pop_back();
+            int r = t.r, c = t.c;
+            const int dir = t.dir;
+            if (!IS_EDGE(r, c)) ++dup;
+            Chain ch = {0, t.parent, dir, {-1, -1}, (int)pixels.size()};
+            const int no = (int)chains.size();
+            chains.push_back(ch);
+            pixels.push_back(Px{r, c});
+            int clen = 1;
+            const bool horizontal = dir == kLeft || dir == kRight;
+            const int child = (dir == kLeft || dir == kUp) ? 0 : 1;
+            const int fwd = (dir == kLeft || dir == kUp) ? -1 : 1;  // step along the walk; also the diagonal looked at first
+            bool ended = false;
+            while (DI(r, c) == (horizontal ? kEdgeHorizontal : kEdgeVertical)) {
+                FL(r, c) = (uint8_t)((FL(r, c) & kEdDirMask) | kEdFlagEdge);
+                if (horizontal) {
+                    FL(r - 1, c) &= (uint8_t)~kEdFlagAnchor;
+                    FL(r + 1, c) &= (uint8_t)~kEdFlagAnchor;
+                    if (MARKED(r, c + fwd)) { c += fwd; }
+                    else if (MARKED(r + fwd, c + fwd)) { r += fwd; c += fwd; }
+                    else if (MARKED(r - fwd, c + fwd)) { r -= fwd; c += fwd; }
+                    else {
+                        const int A = GR(r - 1, c + fwd), B = GR(r, c + fwd), C = GR(r + 1, c + fwd);
+                        if (A > B) { if (A > C) --r; else ++r; }
+                        else if (C > B) ++r;
+                        c += fwd;
+                    }
+                } else {
+                    FL(r, c - 1) &= (uint8_t)~kEdFlagAnchor;
+                    FL(r, c + 1) &= (uint8_t)~kEdFlagAnchor;
+                    if (MARKED(r + fwd, c)) { r += fwd; }
+                    else if (MARKED(r + fwd, c + fwd)) { r += fwd; c += fwd; }
+                    else if (MARKED(r + fwd, c - fwd)) { r += fwd; c -= fwd; }
+                    else {
+                        const int A = GR(r + fwd, c - 1), B = GR(r + fwd, c), C = GR(r + fwd, c + 1);
+                        if (A > B) { if (A > C) --c; else ++c; }
+                        else if (C > B) ++c;
+                        r += fwd;
+                    }
+                }
+                if (IS_EDGE(r, c) || GR(r, c) < grad_thresh) {  // met an edge or left the gradient ridge
+                    chains[no].len = clen;
+                    chains[t.parent].child[child] = no;
+                    ended = true;
+                    break;
+                }
+                pixels.push_back(Px{r, c});
+                ++clen;
+            }
+            if (ended) continue;
+            // the edge turns: the last pixel opens the two walks across the old direction and belongs to them
+            if (horizontal) {
+                stack.push_back(Todo{r, c, kDown, no});
+                stack.push_back(Todo{r, c, kUp, no});
+            } else {
+                stack.push_back(Todo{r, c, kRight, no});
+                stack.push_back(Todo{r, c, kLeft, no});
+            }
+            pixels.pop_back();
+            --clen;
+            chains[no].len = clen;
+            chains[t.parent].child[child] = no;
+        }
+        if ((int)pixels.size() - dup < 10) {  // too short: take the walk back
+            for (size_t i = 0; i < pixels.size(); ++i) FL(pixels[i].r, pixels[i].c) &= kEdDirMask;
+            continue;
+        }
+        best.resize(chains.size());  // (every entry is written before it is read inside one longest_chain call)
+        // ---- main segment: longest path of the second direction backwards, the anchor, longest path of the first direction
+        seg.clear();
+        if (longest_chain(chains, chains[0].child[1], best, order) > 0) {
+            retrieve_chain_nos(chains, chains[0].child[1], nos);
+            for (size_t k = nos.size(); k-- > 0;) {
+                Chain& c = chains[nos[k]];
+                const Px lastp = pixels[c.start + c.len - 1];
+                int idx = (int)seg.size() - 2;
+                while (idx >= 0 && adjacent(lastp, seg[idx])) { seg.pop_back(); --idx; }
+                if (c.len > 1 && (!seg.empty() || have_prev) &&
+                    adjacent(pixels[c.start + c.len - 2], seg.empty() ? prev_last : seg.back()))
+                    --c.len;
+                for (int l = c.len - 1; l >= 0; --l) seg.push_back(pixels[c.start + l]);
+                c.len = 0;
+            }
+        }
+        if (longest_chain(chains, chains[0].child[0], best, order) > 1) {
+            retrieve_chain_nos(chains, chains[0].child[0], nos);
+            ++chains[nos[0]].start;  // the anchor is already there
+            --chains[nos[0]].len;
+            for (size_t k = 0; k < nos.size(); ++k) append_forward(nos[k]);
+        }
+        if (seg.size() > 1 && adjacent(seg[1], seg.back())) seg.erase(seg.begin());
+        emit(seg);
+        // ---- the other long chains of the tree
+        for (int k = 2; k < (int)chains.size(); ++k) {
+            if (chains[k].len < 2) continue;
+            if (longest_chain(chains, k, best, order) >= 10) {
+                retrieve_chain_nos(chains, k, nos);
+                seg.clear();
+                for (size_t q = 0; q < nos.size(); ++q) append_forward(nos[q]);
+                emit(seg);
+            }
+        }
+    }
+#undef GR
+#undef FL
+#undef DI
+#undef MARKED
+#undef IS_ANCHOR
+#undef IS_EDGE
+}
+
+// Both stages on the host: what the reference's call does per keyframe (image row pitch `step` bytes).  Images up to
+// 65535 x 65535.
+inline void DetectEdgesByED(const uint8_t* im, size_t step, int W, int H, int grad_thresh, int anchor_thresh, EdgeChains& out,
+                            int32_t* edge_index = nullptr, size_t edge_step = 0)
+{
+    static thread_local std::vector<int16_t> G;
+    static thread_local std::vector<uint8_t> F;
+    if (W >= 5 && H >= 5) {
+        G.resize((size_t)W * H);
+        F.resize((size_t)W * H);
+        EdPlanesHost(im, step, W, H, grad_thresh, anchor_thresh, G.data(), F.data());
+    }
+    EdRouteChains(W, H, G.data(), F.data(), grad_thresh, out, edge_index, edge_step);
+}
+
+}  // namespace sdm_host

@@ -1,0 +1,43 @@
+// test_edge_drawing.cpp - runs the open Edge Drawing implementation (eao-slam_b200/host/edge_drawing.h) on raw 8-bit images
+// and dumps the chains in the format of oracle/ed_chains.cpp (the same dump of the reference's closed-source EDLib.a), so that
+// tests/test_edge_drawing.py can compare the two byte for byte.
+//   usage: test_edge_drawing W H N in.raw out.bin [edge_index.bin]
+//   out.bin (int32): N, then per image: noSegments, per segment: noPixels, (r, c) * noPixels
+#include <stdio.h>
+#include <stdlib.h>
+
+#include <vector>
+
+#include "../../eao-slam_b200/host/edge_drawing.h"
+
+int main(int argc, char** argv)
+{
+    if (argc < 6) { fprintf(stderr, "usage: %s W H N in.raw out.bin [edge_index.bin]\n", argv[0]); return 2; }
+    const int W = atoi(argv[1]), H = atoi(argv[2]), N = atoi(argv[3]);
+    FILE* fi = fopen(argv[4], "rb");
+    FILE* fo = fopen(argv[5], "wb");
+    FILE* fe = argc > 6 ? fopen(argv[6], "wb") : NULL;
+    if (!fi || !fo) { perror("open"); return 1; }
+    std::vector<unsigned char> im((size_t)W * H);
+    std::vector<int32_t> out, edge((size_t)W * H);
+    out.push_back(N);
+    for (int i = 0; i < N; ++i) {
+        if (fread(im.data(), 1, im.size(), fi) != im.size()) { fprintf(stderr, "short read\n"); return 1; }
+        sdm_host::EdgeChains ch;
+        sdm_host::DetectEdgesByED(im.data(), (size_t)W, W, H, 36, 8, ch, edge.data(), (size_t)W * 4);
+        out.push_back(ch.n_chains());
+        for (int s = 0; s < ch.n_chains(); ++s) {
+            out.push_back(ch.offsets[s + 1] - ch.offsets[s]);
+            for (int j = ch.offsets[s]; j < ch.offsets[s + 1]; ++j) {
+                out.push_back((int32_t)(ch.pixels[j] >> 16));
+                out.push_back((int32_t)(ch.pixels[j] & 0xffffu));
+            }
+        }
+        if (fe) fwrite(edge.data(), 4, edge.size(), fe);
+    }
+    fwrite(out.data(), sizeof(int32_t), out.size(), fo);
+    fclose(fo);
+    fclose(fi);
+    if (fe) fclose(fe);
+    return 0;
+}
