@@ -18,6 +18,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
@@ -33,6 +35,8 @@
 #include "../../include/sdm_b200.h"
 #include "pair_geometry.h"
 #include "sdm_kernels.cuh"
+#include "edge_drawing_kernels.cuh"
+#include "../host/edge_drawing.h"
 
 namespace {
 
@@ -273,6 +277,13 @@ struct sdm_ctx {
     size_t lf_host_cap = 0;
     cudaEvent_t lf_ev[2] = {nullptr, nullptr};
     float lf_ms = 0.f;
+    // sdm_edge_drawing: device planes (im | G | F) and their pinned mirrors for up to ed_cap keyframes
+    uint8_t* ed_dev = nullptr;
+    uint8_t* ed_host = nullptr;
+    int ed_cap = 0;
+    cudaStream_t s_ed = nullptr;
+    std::vector<cudaEvent_t> ed_ev;  // per chunk: kernel start, kernel stop, planes on the host
+    float ed_kernel_ms = 0.f, ed_wall_ms = 0.f, ed_route_ms = 0.f;
     void* peer_rs[kMaxPeers] = {nullptr};
     // sdm_exchange: flag blocks (own + IPC-mapped peers), halo plan, step counter
     sdm::XFlags* xflags = nullptr;
@@ -607,6 +618,10 @@ void sdm_destroy(sdm_ctx* c)
     cudaFree(c->d_chunk_off); cudaFree(c->d_counter); cudaFree(c->d_stats);
     cudaFree(c->tmp_rs); cudaFree(c->xfer); cudaFree(c->dbg); cudaFree(c->exp_buf); cudaFree(c->exp_pts); cudaFree(c->lf_buf);
     if (c->lf_host) cudaFreeHost(c->lf_host);
+    cudaFree(c->ed_dev);
+    if (c->ed_host) cudaFreeHost(c->ed_host);
+    if (c->s_ed) cudaStreamDestroy(c->s_ed);
+    for (auto& e : c->ed_ev) cudaEventDestroy(e);
     for (auto& e : c->lf_ev) if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : {c->ev_p1[0], c->ev_p1[1], c->ev_p2[0], c->ev_p2[1], c->ev_p1_scan})
         if (e) cudaEventDestroy(e);
@@ -1659,6 +1674,207 @@ int sdm_last_line_fit_ms(sdm_ctx* c, float* ms)
 {
     if (!c || !ms) return fail(SDM_ERR_ARG, "null argument");
     *ms = c->lf_ms;
+    return SDM_OK;
+}
+
+// ---- Edge Drawing: stage 1 on the device, the routing walk on host threads ------------------------
+struct sdm_ed_result {
+    std::vector<sdm_host::EdgeChains> chains;
+};
+
+namespace {
+
+constexpr int kEdChunk = 8;     // keyframes per device chunk (H2D, k_ed_planes, D2H; the unit the routing threads wait for)
+constexpr int kEdMaxBatch = 256;  // keyframes whose planes are resident at once (pinned + device: 4 bytes per pixel each)
+
+size_t ed_bytes(int cap, size_t P);
+
+int ed_reserve(sdm_ctx* c, int n_kf)
+{
+    if (!c->s_ed) CU(cudaStreamCreateWithFlags(&c->s_ed, cudaStreamNonBlocking));
+    if (c->ed_cap >= n_kf) return SDM_OK;
+    CU(cudaStreamSynchronize(c->s_ed));
+    cudaFree(c->ed_dev);
+    if (c->ed_host) cudaFreeHost(c->ed_host);
+    c->ed_dev = nullptr; c->ed_host = nullptr; c->ed_cap = 0;
+    const size_t bytes = ed_bytes(n_kf, c->npix);
+    CU(cudaMalloc((void**)&c->ed_dev, bytes));
+    CU(cudaMallocHost((void**)&c->ed_host, bytes));
+    c->ed_cap = n_kf;
+    return SDM_OK;
+}
+
+// planes of up to `cap` keyframes inside the (device or pinned) block: im[cap][P] u8 | G[cap][P] i16 | F[cap][P] u8, every
+// section on a 256-byte boundary
+inline size_t ed_align(size_t v) { return (v + 255) & ~(size_t)255; }
+size_t ed_bytes(int cap, size_t P) { return ed_align((size_t)cap * P) + ed_align((size_t)cap * P * 2) + ed_align((size_t)cap * P); }
+struct EdLayout {
+    uint8_t* im; int16_t* G; uint8_t* F;
+    EdLayout(uint8_t* base, int cap, size_t P)
+        : im(base), G((int16_t*)(base + ed_align((size_t)cap * P))), F(base + ed_align((size_t)cap * P) + ed_align((size_t)cap * P * 2)) {}
+};
+
+int ed_launch(sdm_ctx* c, const EdLayout& d, int first, int count, int grad_thresh, int anchor_thresh)
+{
+    const int W = c->cfg.width, H = c->cfg.height;
+    const dim3 grid((W + sdm::kEdTW - 1) / sdm::kEdTW, (H + sdm::kEdTH - 1) / sdm::kEdTH, count);
+    sdm::k_ed_planes<<<grid, sdm::kEdThreads, 0, c->s_ed>>>(d.im + (size_t)first * c->npix, W, H, grad_thresh, anchor_thresh,
+                                                           d.G + (size_t)first * c->npix, d.F + (size_t)first * c->npix);
+    CU(cudaGetLastError());
+    ++c->launches;
+    return SDM_OK;
+}
+
+}  // namespace
+
+int sdm_edge_drawing(sdm_ctx* c, int n, const sdm_ed_image* images, int grad_thresh, int anchor_thresh, int n_threads,
+                     sdm_ed_result** result)
+{
+    if (!c || !result || (n > 0 && !images)) return fail(SDM_ERR_ARG, "sdm_edge_drawing: null argument");
+    *result = nullptr;
+    if (n < 0) return fail(SDM_ERR_ARG, "sdm_edge_drawing: negative count");
+    if (grad_thresh < 1 || grad_thresh > 2047 || anchor_thresh < 0) return fail(SDM_ERR_ARG, "sdm_edge_drawing: thresholds out of range");
+    for (int i = 0; i < n; ++i)
+        if (!images[i].im || images[i].im_step < (size_t)c->cfg.width ||
+            (images[i].edge_index && images[i].edge_step < (size_t)c->cfg.width * 4))
+            return fail(SDM_ERR_ARG, "sdm_edge_drawing: image %d: null plane or row pitch below the width", i);
+    sdm_ed_result* res = new (std::nothrow) sdm_ed_result();
+    if (!res) return fail(SDM_ERR_NOMEM, "out of host memory");
+    res->chains.resize((size_t)n);
+    c->ed_kernel_ms = c->ed_wall_ms = c->ed_route_ms = 0.f;
+    if (n == 0) { *result = res; return SDM_OK; }
+    const auto wall0 = std::chrono::steady_clock::now();
+    const int W = c->cfg.width, H = c->cfg.height;
+    const size_t P = c->npix;
+    int rc = SDM_OK;
+    auto body = [&]() -> int {
+        CU(cudaSetDevice(c->cfg.device));
+        RC(ed_reserve(c, std::min(n, kEdMaxBatch)));
+        const int n_chunks_max = (std::min(n, kEdMaxBatch) + kEdChunk - 1) / kEdChunk;
+        while ((int)c->ed_ev.size() < 3 * n_chunks_max) {
+            cudaEvent_t e;
+            CU(cudaEventCreate(&e));
+            c->ed_ev.push_back(e);
+        }
+        unsigned hw = std::thread::hardware_concurrency();
+        if (hw == 0) hw = 1;
+        const int nt = std::max(1, std::min(n_threads > 0 ? n_threads : (int)std::min(hw, 32u), n));
+        const EdLayout dv(c->ed_dev, c->ed_cap, P), hv(c->ed_host, c->ed_cap, P);
+        for (int base = 0; base < n; base += kEdMaxBatch) {
+            const int nb = std::min(kEdMaxBatch, n - base), n_chunks = (nb + kEdChunk - 1) / kEdChunk;
+            std::atomic<int> next(0), issued(0), failed(0);
+            std::atomic<long long> route_ns(0);
+            std::mutex mu;
+            std::condition_variable cv;
+            std::vector<std::thread> workers;
+            for (int t = 0; t < nt; ++t)
+                workers.emplace_back([&]() {
+                    cudaSetDevice(c->cfg.device);
+                    for (;;) {
+                        const int i = next.fetch_add(1);
+                        if (i >= nb) return;
+                        const int chunk = i / kEdChunk;
+                        {
+                            std::unique_lock<std::mutex> lk(mu);
+                            cv.wait(lk, [&] { return issued.load() > chunk || failed.load(); });
+                        }
+                        if (failed.load()) return;
+                        if (cudaEventSynchronize(c->ed_ev[3 * chunk + 2]) != cudaSuccess) { failed.store(1); return; }
+                        const auto t0 = std::chrono::steady_clock::now();
+                        const sdm_ed_image& im = images[base + i];
+                        sdm_host::EdRouteChains(W, H, hv.G + (size_t)i * P, hv.F + (size_t)i * P, grad_thresh,
+                                                res->chains[(size_t)(base + i)], im.edge_index, im.edge_step);
+                        route_ns.fetch_add(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count());
+                    }
+                });
+            auto issue = [&]() -> int {
+                for (int ch = 0; ch < n_chunks; ++ch) {
+                    const int first = ch * kEdChunk, count = std::min(kEdChunk, nb - first);
+                    for (int i = first; i < first + count; ++i) {  // pack the rows into the pinned mirror
+                        const sdm_ed_image& im = images[base + i];
+                        uint8_t* dst = hv.im + (size_t)i * P;
+                        if (im.im_step == (size_t)W) std::memcpy(dst, im.im, P);
+                        else for (int y = 0; y < H; ++y) std::memcpy(dst + (size_t)y * W, im.im + (size_t)y * im.im_step, (size_t)W);
+                    }
+                    CU(cudaMemcpyAsync(dv.im + (size_t)first * P, hv.im + (size_t)first * P, (size_t)count * P, cudaMemcpyHostToDevice, c->s_ed));
+                    CU(cudaEventRecord(c->ed_ev[3 * ch], c->s_ed));
+                    RC(ed_launch(c, dv, first, count, grad_thresh, anchor_thresh));
+                    CU(cudaEventRecord(c->ed_ev[3 * ch + 1], c->s_ed));
+                    CU(cudaMemcpyAsync(hv.G + (size_t)first * P, dv.G + (size_t)first * P, (size_t)count * P * 2, cudaMemcpyDeviceToHost, c->s_ed));
+                    CU(cudaMemcpyAsync(hv.F + (size_t)first * P, dv.F + (size_t)first * P, (size_t)count * P, cudaMemcpyDeviceToHost, c->s_ed));
+                    CU(cudaEventRecord(c->ed_ev[3 * ch + 2], c->s_ed));
+                    {
+                        std::lock_guard<std::mutex> lk(mu);
+                        issued.store(ch + 1);
+                    }
+                    cv.notify_all();
+                }
+                return SDM_OK;
+            };
+            int irc = issue();
+            if (irc != SDM_OK) {
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    failed.store(1);
+                }
+                cv.notify_all();
+            }
+            for (auto& t : workers) t.join();
+            if (irc != SDM_OK) return irc;
+            if (failed.load()) return fail(SDM_ERR_CUDA, "sdm_edge_drawing: device stage failed: %s", cudaGetErrorString(cudaGetLastError()));
+            CU(cudaStreamSynchronize(c->s_ed));
+            for (int ch = 0; ch < n_chunks; ++ch) {
+                float ms = 0.f;
+                CU(cudaEventElapsedTime(&ms, c->ed_ev[3 * ch], c->ed_ev[3 * ch + 1]));
+                c->ed_kernel_ms += ms;
+            }
+            c->ed_route_ms += (float)((double)route_ns.load() * 1e-6);
+        }
+        return SDM_OK;
+    };
+    rc = body();
+    c->ed_wall_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+    if (rc != SDM_OK) { delete res; return rc; }
+    *result = res;
+    return SDM_OK;
+}
+
+int sdm_ed_chains(const sdm_ed_result* r, int i, int32_t* n_chains, const int32_t** offsets, const uint32_t** pixels)
+{
+    if (!r || !n_chains || !offsets || !pixels) return fail(SDM_ERR_ARG, "sdm_ed_chains: null argument");
+    if (i < 0 || i >= (int)r->chains.size()) return fail(SDM_ERR_ARG, "sdm_ed_chains: keyframe %d out of range", i);
+    const sdm_host::EdgeChains& e = r->chains[(size_t)i];
+    *n_chains = e.n_chains();
+    *offsets = e.offsets.data();
+    *pixels = e.pixels.data();
+    return SDM_OK;
+}
+
+void sdm_ed_free(sdm_ed_result* r) { delete r; }
+
+int sdm_last_edge_drawing_ms(sdm_ctx* c, float* kernel_ms, float* wall_ms, float* route_thread_ms)
+{
+    if (!c) return fail(SDM_ERR_ARG, "null argument");
+    if (kernel_ms) *kernel_ms = c->ed_kernel_ms;
+    if (wall_ms) *wall_ms = c->ed_wall_ms;
+    if (route_thread_ms) *route_thread_ms = c->ed_route_ms;
+    return SDM_OK;
+}
+
+int sdm_ed_planes(sdm_ctx* c, const uint8_t* im, size_t im_step, int grad_thresh, int anchor_thresh, int16_t* G, uint8_t* F)
+{
+    if (!c || !im || !G || !F) return fail(SDM_ERR_ARG, "sdm_ed_planes: null argument");
+    if (im_step < (size_t)c->cfg.width) return fail(SDM_ERR_ARG, "sdm_ed_planes: row pitch below the width");
+    if (grad_thresh < 1 || grad_thresh > 2047 || anchor_thresh < 0) return fail(SDM_ERR_ARG, "sdm_ed_planes: thresholds out of range");
+    CU(cudaSetDevice(c->cfg.device));
+    RC(ed_reserve(c, 1));
+    const size_t P = c->npix;
+    const EdLayout dv(c->ed_dev, c->ed_cap, P);
+    CU(cudaMemcpy2DAsync(dv.im, (size_t)c->cfg.width, im, im_step, (size_t)c->cfg.width, (size_t)c->cfg.height, cudaMemcpyHostToDevice, c->s_ed));
+    RC(ed_launch(c, dv, 0, 1, grad_thresh, anchor_thresh));
+    CU(cudaMemcpyAsync(G, dv.G, P * 2, cudaMemcpyDeviceToHost, c->s_ed));
+    CU(cudaMemcpyAsync(F, dv.F, P, cudaMemcpyDeviceToHost, c->s_ed));
+    CU(cudaStreamSynchronize(c->s_ed));
     return SDM_OK;
 }
 

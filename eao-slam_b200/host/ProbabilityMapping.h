@@ -50,10 +50,15 @@ typedef cv::Mat Mat;
 typedef ORB_SLAM2::KeyFrame KeyFrame;
 typedef ORB_SLAM2::Map Map;
 inline Mat zeros32f(int rows, int cols) { return cv::Mat::zeros(rows, cols, CV_32F); }
+inline Mat plane32s(int rows, int cols) { return cv::Mat(rows, cols, CV_32S); }
 }  // namespace sdm_host
 #else
 #include "host_types.h"
+namespace sdm_host {
+inline Mat plane32s(int rows, int cols) { return Mat(rows, cols, sizeof(int32_t)); }
+}
 #endif
+#include "edge_drawing.h"
 
 namespace sdm_host {
 // ProbabilityMapping::GetRotInPlane (:847-864): angle2 - angle1 of the ORB keypoints of every map point
@@ -104,7 +109,7 @@ public:
 
     explicit ProbabilityMapping(Map* pMap)
         : mMutexSemiDense(), mpMap(pMap), mCtx(NULL), mN(covisN), mW(0), mH(0), mCapacity(0), mChunk(0), mHeadroom(-1), mDevicePlanes(false), mSparse(false),
-          mOnline(false), mbFinishRequested(false), mbFinished(false), mbResetRequested(false)
+          mOnline(false), mEdgeDrawing(false), mEdThreads(0), mEdGrad(36), mEdAnchor(8), mbFinishRequested(false), mbFinished(false), mbResetRequested(false)
     {
         sdm_default_config(&mCfg);
 #ifdef SDM_HOST_WITH_ORBSLAM2
@@ -137,6 +142,27 @@ public:
     // SDM_HOST_WITH_ORBSLAM2 the class calls its own mLineDetector exactly there; a hook replaces that call (stand-alone
     // builds have no LineDetector: without a hook mEdgeIndex is used as the caller left it, empty = every pixel passes).
     void SetEdgeMapHook(const std::function<void(KeyFrame*)>& f) { mEdgeHook = f; }
+    // The open Edge Drawing implementation instead of the closed-source EDLib.a behind LineDetector::DetectEdgeMap
+    // (LineDetector.cc:843-881): the edge maps of ALL keyframes pass 1 is about to process in one sdm_edge_drawing call
+    // (smoothing / gradient / anchors on the device, the routing walks on `threads` host threads) right where the
+    // reference detects them one by one (:394).  Fills kf->mEdgeIndex (allocated if empty) exactly as :857-866 does - the
+    // chains are the library's, pixel for pixel (tests/test_edge_drawing.py) - and keeps the chains for FitLines
+    // (EdgeChainsOf); with SDM_HOST_WITH_ORBSLAM2 kf->mEdgeMap is built from them as well (:869), so the reference's own
+    // consumers of the edge map run unchanged.  Off by default: a hook, then the reference's LineDetector, come first.
+    void SetEdgeDrawing(bool on, int threads = 0, int grad_thresh = 36, int anchor_thresh = 8)
+    {
+        mEdgeDrawing = on; mEdThreads = threads; mEdGrad = grad_thresh; mEdAnchor = anchor_thresh;
+    }
+    const sdm_host::EdgeChains* EdgeChainsOf(KeyFrame* kf) const
+    {
+        std::unordered_map<KeyFrame*, sdm_host::EdgeChains>::const_iterator it = mEdgeChains.find(kf);
+        return it == mEdgeChains.end() ? NULL : &it->second;
+    }
+    // wall / device / routing-thread time of the last batch (ms)
+    void LastEdgeDrawingMs(float* kernel_ms, float* wall_ms, float* route_thread_ms)
+    {
+        if (mCtx) sdm_last_edge_drawing_ms(mCtx, kernel_ms, wall_ms, route_thread_ms);
+    }
     // where SaveSemiDensePoints / WriteModel put their files; default "results_line_segments/<date-time>" (:138, :121)
     void SetResultsDir(const std::string& d) { mResultsDir = d; }
 
@@ -206,9 +232,10 @@ public:
             Work w;
             w.kf = kf;
             if (!ClosestMatches(kf, false, will_be_mapped, w.nbrs)) continue;  // :365-384
-            DetectEdgeMap(kf);                                                 // :394-397
+            if (!BatchedEdgeDrawing()) DetectEdgeMap(kf);                      // :394-397
             w1.push_back(w);
         }
+        if (BatchedEdgeDrawing() && !DetectEdgeMaps(w1)) { UnpinAll(); return; }  // :394 for every keyframe of pass 1 at once
         for (size_t i = 0; i < w1.size(); i++) will_be_mapped.insert(w1[i].kf);
         for (size_t i = 0; i < vpKFs.size(); i++) {
             KeyFrame* kf = vpKFs[i];
@@ -602,6 +629,49 @@ private:
         mPinned.clear();
     }
 
+    bool BatchedEdgeDrawing() const { return mEdgeDrawing && !mEdgeHook; }
+    bool DetectEdgeMaps(const std::vector<Work>& w1)
+    {
+        if (w1.empty()) return true;
+        std::vector<sdm_ed_image> ims(w1.size());
+        for (size_t i = 0; i < w1.size(); i++) {
+            KeyFrame* kf = w1[i].kf;
+            if (kf->mEdgeIndex.empty()) kf->mEdgeIndex = sdm_host::plane32s(kf->im_.rows, kf->im_.cols);  // KeyFrame.cc:87
+            ims[i].im = kf->im_.ptr<uint8_t>(0);
+            ims[i].im_step = (size_t)kf->im_.step;
+            ims[i].edge_index = kf->mEdgeIndex.ptr<int32_t>(0);
+            ims[i].edge_step = (size_t)kf->mEdgeIndex.step;
+        }
+        sdm_ed_result* res = NULL;
+        if (!Check(sdm_edge_drawing(mCtx, (int)ims.size(), ims.data(), mEdGrad, mEdAnchor, mEdThreads, &res), "sdm_edge_drawing"))
+            return false;
+        for (size_t i = 0; i < w1.size(); i++) {
+            int32_t n = 0;
+            const int32_t* off = NULL;
+            const uint32_t* pix = NULL;
+            sdm_ed_chains(res, (int)i, &n, &off, &pix);
+            sdm_host::EdgeChains& e = mEdgeChains[w1[i].kf];
+            e.offsets.assign(off, off + n + 1);
+            e.pixels.assign(pix, pix + off[n]);
+#ifdef SDM_HOST_WITH_ORBSLAM2
+            {   // kf->mEdgeMap = map (:869), in the library's result type
+                KeyFrame* kf = w1[i].kf;
+                EdgeMap* map = new EdgeMap(kf->im_.cols, kf->im_.rows);
+                for (int k = 0; k < n; k++) {
+                    map->segments[k].pixels = map->pixels + off[k];
+                    map->segments[k].noPixels = off[k + 1] - off[k];
+                }
+                for (int q = 0; q < off[n]; q++) { map->pixels[q].r = (int)(pix[q] >> 16); map->pixels[q].c = (int)(pix[q] & 0xffffu); }
+                map->noSegments = n;
+                kf->mEdgeMap = map;
+                mLineDetector.DetectLineSegments(kf);  // :397
+            }
+#endif
+        }
+        sdm_ed_free(res);
+        return true;
+    }
+
     void DetectEdgeMap(KeyFrame* kf)
     {
         if (mEdgeHook) { mEdgeHook(kf); return; }
@@ -895,6 +965,9 @@ private:
     std::vector<KeyFrame*> mPendingKFs;
     std::vector<KeyFrame*> mPinned;
     std::function<void(KeyFrame*)> mEdgeHook;
+    bool mEdgeDrawing;
+    int mEdThreads, mEdGrad, mEdAnchor;
+    std::unordered_map<KeyFrame*, sdm_host::EdgeChains> mEdgeChains;
     std::string mResultsDir;
 #ifdef SDM_HOST_WITH_ORBSLAM2
     Modeler* mpModeler;

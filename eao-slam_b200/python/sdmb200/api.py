@@ -75,6 +75,10 @@ class EdgeChains(C.Structure):  # sdm_edge_chains
 LINE3D = np.dtype([("seg", "f4", 4), ("xyz", "f4", 6), ("chain", "i4"), ("kf_index", "i4")])  # sdm_line3d
 
 
+class EdImage(C.Structure):  # sdm_ed_image
+    _fields_ = [("im", C.c_void_p), ("im_step", C.c_size_t), ("edge_index", C.c_void_p), ("edge_step", C.c_size_t)]
+
+
 class Timing(C.Structure):
     _fields_ = [("pass1_scan_ms", C.c_float), ("pass1_intra_ms", C.c_float), ("pass2_ms", C.c_float)]
 
@@ -94,6 +98,7 @@ EXPORTS = [
     "sdm_epipolar_search", "sdm_epipolar_search_plane", "sdm_fuse", "sdm_intra_check", "sdm_intra_grow",
     "sdm_inter_check", "sdm_last_pass_ms", "sdm_launch_count", "sdm_last_timing", "sdm_last_pack_ms", "sdm_mark", "sdm_elapsed_ms",
     "sdm_line_fit", "sdm_last_line_fit_ms", "sdm_last_scan_long",
+    "sdm_edge_drawing", "sdm_ed_chains", "sdm_ed_free", "sdm_last_edge_drawing_ms", "sdm_ed_planes",
 ]
 
 _lib = None
@@ -119,6 +124,12 @@ def load() -> C.CDLL:
     lib.sdm_synchronize.argtypes = [vp]
     lib.sdm_get_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.sdm_scan_generation.argtypes = [vp]
+    lib.sdm_edge_drawing.argtypes = [vp, C.c_int, C.POINTER(EdImage), C.c_int, C.c_int, C.c_int, C.POINTER(vp)]
+    lib.sdm_ed_chains.argtypes = [vp, C.c_int, ip, C.POINTER(ip), C.POINTER(C.POINTER(C.c_uint32))]
+    lib.sdm_ed_free.argtypes = [vp]
+    lib.sdm_ed_free.restype = None
+    lib.sdm_last_edge_drawing_ms.argtypes = [vp, fp, fp, fp]
+    lib.sdm_ed_planes.argtypes = [vp, vp, sz, C.c_int, C.c_int, vp, vp]
     lib.sdm_host_alloc.argtypes = [C.POINTER(vp), sz]
     lib.sdm_host_free.argtypes = [vp]
     lib.sdm_upload_keyframe.argtypes = [vp, C.c_int, vp, sz, vp, sz, vp, sz, vp, sz, fp, fp]
@@ -397,6 +408,46 @@ class Context:
         self._chk(self.lib.sdm_line_fit(self.h, n, sets, out.ctypes.data, cap, counts.ctypes.data_as(C.POINTER(C.c_uint64)),
                                         C.byref(total)))
         return out[:int(total.value)], counts[:n]
+
+    def edge_drawing(self, images, grad_thresh=36, anchor_thresh=8, n_threads=0, edge_index=True):
+        """LineDetector::DetectEdgeMap for a batch of 8-bit images [n, H, W] (or a list of [H, W], rows may be pitched).
+        Returns (offsets list, pixels list, edge_index [n, H, W] int32 or None): chains of image i = pixels[i][offsets[i][k] :
+        offsets[i][k + 1]], packed (row << 16) | col - the layout line_fit takes; edge_index = kf->mEdgeIndex."""
+        ims = [images[i] for i in range(len(images))]
+        n = len(ims)
+        for a in ims:
+            assert a.dtype == np.uint8 and a.shape == (self.H, self.W) and a.strides[1] == 1
+        edge = np.empty((n, self.H, self.W), np.int32) if edge_index else None
+        descs = (EdImage * max(n, 1))()
+        for i, a in enumerate(ims):
+            descs[i].im, descs[i].im_step = a.ctypes.data, a.strides[0]
+            if edge is not None:
+                descs[i].edge_index, descs[i].edge_step = edge[i].ctypes.data, edge[i].strides[0]
+        res = C.c_void_p()
+        self._chk(self.lib.sdm_edge_drawing(self.h, n, descs, grad_thresh, anchor_thresh, n_threads, C.byref(res)))
+        offs, pix = [], []
+        try:
+            for i in range(n):
+                nc, po, pp = C.c_int32(), C.POINTER(C.c_int32)(), C.POINTER(C.c_uint32)()
+                self._chk(self.lib.sdm_ed_chains(res, i, C.byref(nc), C.byref(po), C.byref(pp)))
+                o = np.ctypeslib.as_array(po, shape=(nc.value + 1,)).copy()
+                offs.append(o)
+                pix.append(np.ctypeslib.as_array(pp, shape=(int(o[-1]),)).copy() if o[-1] > 0 else np.zeros(0, np.uint32))
+        finally:
+            self.lib.sdm_ed_free(res)
+        return offs, pix, edge
+
+    def last_edge_drawing_ms(self) -> dict:
+        k, w, r = C.c_float(), C.c_float(), C.c_float()
+        self._chk(self.lib.sdm_last_edge_drawing_ms(self.h, C.byref(k), C.byref(w), C.byref(r)))
+        return dict(kernel_ms=float(k.value), wall_ms=float(w.value), route_thread_ms=float(r.value))
+
+    def ed_planes(self, im, grad_thresh=36, anchor_thresh=8):
+        """stage-1 planes of one image as k_ed_planes computes them: (G int16, F uint8)"""
+        assert im.dtype == np.uint8 and im.shape == (self.H, self.W) and im.strides[1] == 1
+        G, F = np.empty((self.H, self.W), np.int16), np.empty((self.H, self.W), np.uint8)
+        self._chk(self.lib.sdm_ed_planes(self.h, im.ctypes.data, im.strides[0], grad_thresh, anchor_thresh, G.ctypes.data, F.ctypes.data))
+        return G, F
 
     def last_line_fit_ms(self) -> float:
         ms = C.c_float()

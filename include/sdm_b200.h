@@ -250,6 +250,37 @@ int sdm_line_fit(sdm_ctx* ctx, int n, const sdm_edge_chains* sets, sdm_line3d* o
 /* device time of the last sdm_line_fit (its three kernels), ms */
 int sdm_last_line_fit_ms(sdm_ctx* ctx, float* ms);
 
+/* ---- Edge Drawing: the candidate mask and the edge chains --------------- */
+/* replaces: LineDetector::DetectEdgeMap (LineDetector.cc:843-881), which the reference calls per keyframe inside pass 1
+ * (ProbabilityMapping.cc:394) and which hands the image to the closed-source EDLib.a:
+ *     EdgeMap* map = DetectEdgesByED(srcImg, width, height, SOBEL_OPERATOR, 36, 8, 1.0);                 (:855)
+ *     kf->mEdgeIndex.at<int>(r, c) = i for every pixel of map->segments[i];  kf->mEdgeMap = map;          (:857-869)
+ * for a batch of keyframes.  Stage 1 (smoothing, Sobel gradient, direction, anchors: k_ed_planes) runs on the device in
+ * chunks of keyframes, stage 2 (the sequential smart-routing walk from the anchors, host/edge_drawing.h) on n_threads host
+ * threads while the next chunk is on the device.  The chains are the library's, pixel for pixel and in order
+ * (tests/test_edge_drawing.py, tests/test_gpu_edge_drawing.py).
+ * images[i].im = kf->im_ (8-bit, ctx width x height, row pitch im_step bytes); images[i].edge_index, if not NULL,
+ * receives kf->mEdgeIndex: -1, then the chain number of every chain pixel (int32 plane, row pitch edge_step bytes) -
+ * the `edge` plane of sdm_upload_keyframes.  *result owns the chains of the batch until sdm_ed_free; sdm_ed_chains
+ * returns keyframe i's lists in the layout sdm_line_fit takes (sdm_edge_chains.offsets / .pixels).
+ * grad_thresh in 1 .. 2047 (the reference: 36), anchor_thresh >= 0 (8), n_threads <= 0: one per host core, at most 32.
+ * Blocking. */
+typedef struct {
+    const uint8_t* im;    size_t im_step;
+    int32_t* edge_index;  size_t edge_step;  /* edge_index may be NULL */
+} sdm_ed_image;
+typedef struct sdm_ed_result sdm_ed_result;
+int sdm_edge_drawing(sdm_ctx* ctx, int n, const sdm_ed_image* images, int grad_thresh, int anchor_thresh, int n_threads,
+                     sdm_ed_result** result);
+int sdm_ed_chains(const sdm_ed_result* result, int i, int32_t* n_chains, const int32_t** offsets, const uint32_t** pixels);
+void sdm_ed_free(sdm_ed_result* result);
+/* timing of the last sdm_edge_drawing: device time of its k_ed_planes launches, host wall time of the call, and the
+ * summed thread time of the routing walks (all ms; any pointer may be NULL) */
+int sdm_last_edge_drawing_ms(sdm_ctx* ctx, float* kernel_ms, float* wall_ms, float* route_thread_ms);
+/* the stage-1 planes of one image as the device computes them (G int16, F uint8, dense width x height; see
+ * csrc/edge_drawing_kernels.cuh) - for tests and tools */
+int sdm_ed_planes(sdm_ctx* ctx, const uint8_t* im, size_t im_step, int grad_thresh, int anchor_thresh, int16_t* G, uint8_t* F);
+
 /* ---- multi-GPU: pass-1 planes of halo keyframes over NVLink (the dependency of :1202-1249) -- */
 /* device pointer + byte size of the (rho, sigma) float2 plane of a slot, for NCCL / peer copies */
 int sdm_depth_plane_ptr(sdm_ctx* ctx, int kf, void** dev_ptr, size_t* bytes);

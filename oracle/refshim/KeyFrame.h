@@ -26,7 +26,16 @@ using namespace std;
 // stand-in for Thirdparty/EDTest/EdgeMap.h (the closed-source Edge Drawing library's result type, KeyFrame.h:175)
 struct Pixel { int r, c; };
 struct EdgeSegment { Pixel* pixels; int noPixels; };
-struct EdgeMap { Pixel* pixels; EdgeSegment* segments; int noSegments; };
+struct EdgeMap {
+    int width, height;
+    unsigned char* edgeImg;
+    Pixel* pixels;
+    EdgeSegment* segments;
+    int noSegments;
+    EdgeMap(int w, int h) : width(w), height(h), edgeImg(new unsigned char[w * h]), pixels(new Pixel[w * h]),
+                            segments(new EdgeSegment[w * h]), noSegments(0) {}
+    ~EdgeMap() { delete[] edgeImg; delete[] pixels; delete[] segments; }
+};
 
 namespace DBoW2 {
 typedef std::map<unsigned int, std::vector<unsigned int> > FeatureVector;

@@ -121,7 +121,9 @@ int main(int argc, char** argv)
     if (const char* e = getenv("SDM_SHIM_HEADROOM")) pm.SetArenaHeadroom(atoi(e));
     if (const char* e = getenv("SDM_SHIM_SPARSE")) pm.SetSparseDownloads(e[0] == '1');
     int hook_calls = 0;
-    pm.SetEdgeMapHook([&hook_calls](KeyFrame*) { ++hook_calls; });  // where the reference calls DetectEdgeMap (:394-397)
+    const char* edge_out = getenv("SDM_SHIM_EDGE_OUT");  // open Edge Drawing where the reference calls DetectEdgeMap; dump file
+    if (edge_out) pm.SetEdgeDrawing(true, 4);
+    else pm.SetEdgeMapHook([&hook_calls](KeyFrame*) { ++hook_calls; });  // where the reference calls DetectEdgeMap (:394-397)
 
     if (online) {  // mirrors ref_online_sequence (oracle/refshim/refdriver.cc)
         FILE* q = fopen(argv[2], "rb");
@@ -232,6 +234,27 @@ int main(int argc, char** argv)
     pm.Run();  // = SemiDenseLoop() once, as in the reference's offline mode
     if (!pm.isFinished()) return 3;
 
+    if (edge_out) {  // per keyframe: chain count, pixel count, offsets, pixels, then kf->mEdgeIndex; then the fitted lines
+        FILE* e = fopen(edge_out, "wb");
+        if (!e) { perror("edge out"); return 2; }
+        for (size_t i = 0; i < kfs.size(); i++) {
+            const sdm_host::EdgeChains* c = pm.EdgeChainsOf(kfs[i].get());
+            int32_t h2[2] = {c ? c->n_chains() : -1, c ? (int32_t)c->pixels.size() : 0};
+            fwrite(h2, 4, 2, e);
+            if (c) { fwrite(c->offsets.data(), 4, c->offsets.size(), e); fwrite(c->pixels.data(), 4, c->pixels.size(), e); }
+            for (int y = 0; c && y < H; y++) fwrite(kfs[i]->mEdgeIndex.ptr<int32_t>(y), 4, W, e);
+        }
+        std::vector<sdm_line3d> lines;
+        std::vector<uint64_t> counts;
+        pm.FitLines([&pm](KeyFrame* kf, std::vector<int32_t>& off, std::vector<uint32_t>& pix) {
+            const sdm_host::EdgeChains* c = pm.EdgeChainsOf(kf);
+            if (c) { off = c->offsets; pix = c->pixels; }
+        }, lines, NULL, &counts);
+        int32_t nl = (int32_t)lines.size();
+        fwrite(&nl, 4, 1, e);
+        fwrite(lines.data(), sizeof(sdm_line3d), lines.size(), e);
+        fclose(e);
+    }
     FILE* o = fopen(argv[2], "wb");
     if (!o) { perror("out"); return 2; }
     dump_planes(o, kfs, W, H);

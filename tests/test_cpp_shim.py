@@ -184,6 +184,55 @@ def _read_planes(raw, n, W, H):
 
 
 @pytest.mark.gpu
+def test_shim_with_open_edge_drawing(shim_binary, tmp_path):
+    """SetEdgeDrawing(true): the class detects the edge maps of the pass-1 keyframes itself, where the reference calls
+    LineDetector::DetectEdgeMap (ProbabilityMapping.cc:394, LineDetector.cc:843-881) - mEdgeIndex and the chains equal the
+    C-ABI's (pinned to the reference's EDLib.a in tests/test_gpu_edge_drawing.py), the loop's planes equal the oracle's
+    on that mask (the candidate filter of :454), and FitLines over the kept chains equals sdm_line_fit."""
+    from helpers import run_oracle
+    from sdmb200 import api
+    n, W, H, N = 12, 320, 240, 6
+    sc = synth.make_scene(n, W, H, N, seed=17)
+    lib = O.lib()
+    for i in range(n):
+        a, b = C.c_float(), C.c_float()
+        lib.oracle_stereo_search_constraints(O.fptr(sc.inv_depths[i]), len(sc.inv_depths[i]), C.byref(a), C.byref(b))
+        sc.min_depth[i], sc.max_depth[i] = a.value, b.value
+    scene_path, out_path, edge_path = (str(tmp_path / f) for f in ("scene.bin", "out.bin", "edge.bin"))
+    _write_scene(scene_path, sc, N, 16, [])
+    r = subprocess.run([shim_binary, scene_path, out_path], capture_output=True, text=True,
+                       env=dict(os.environ, SDM_SHIM_EDGE_OUT=edge_path))
+    assert r.returncode == 0, r.stdout + r.stderr
+    with api.Context(width=W, height=H, max_keyframes=n) as ctx:
+        offs, pix, edge = ctx.edge_drawing(sc.im)
+        e = np.fromfile(edge_path, np.int32)
+        p = 0
+        for i in range(n):
+            nc, npx = int(e[p]), int(e[p + 1]); p += 2
+            assert nc == len(offs[i]) - 1 > 100
+            assert np.array_equal(e[p:p + nc + 1], offs[i]); p += nc + 1
+            assert np.array_equal(e[p:p + npx].view(np.uint32), pix[i]); p += npx
+            assert np.array_equal(e[p:p + W * H].reshape(H, W), edge[i]); p += W * H
+        n_lines = int(e[p]); p += 1
+        shim_lines = e[p:].view(api.LINE3D)
+        assert len(shim_lines) == n_lines > 50
+        sce = synth.Scene(im=sc.im, grad=sc.grad, theta=sc.theta, edge=edge, K=sc.K, Tcw=sc.Tcw, nbr_idx=sc.nbr_idx, rot=sc.rot,
+                          min_depth=sc.min_depth, max_depth=sc.max_depth)
+        osc = run_oracle(sce)
+        raw = np.fromfile(out_path, np.float32)
+        dev, flags, _ = _read_planes(raw, n, W, H)
+        assert (flags == 1).all()
+        rep = compare_planes(dev, osc)
+        assert all(rep[k + "_bit_mismatch"] == 0 for k in ("depth", "sigma", "checked", "points")), rep
+        assert rep["pass2_accepted_ref"] > 1000 and not (dev["checked"] > 0)[edge < 0].any()
+        ctx.upload_scene(sce)
+        items = api.make_items(range(n), sc.nbr_idx, sc.rot, sc.min_depth, sc.max_depth)
+        ctx.pass1(items); ctx.pass2(items)
+        lines, _ = ctx.line_fit(list(range(n)), offs, pix)
+        assert lines.tobytes() == shim_lines.tobytes()
+
+
+@pytest.mark.gpu
 def test_shim_online_mode_matches_the_reference_online_build(shim_binary, tmp_path):
     """SURVEY 8f-4.  The reference compiled with -DOnlineLoop (oracle/_ref/libref_pm_online.so) and the shim are driven
     through the same sequence: keyframes arrive in three batches, after each one the body of Run()'s online loop

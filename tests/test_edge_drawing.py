@@ -182,7 +182,12 @@ def test_live_against_the_library(ed_bin, tmp_path):
 
 @pytest.mark.skipif(not have_ref, reason="needs the reference's bundled OpenCV 2.4.5 (build container only)")
 def test_smoothing_stage_against_the_bundled_cvSmooth():
-    """cvSmooth(src, dst, CV_GAUSSIAN, 5, 5) through the C API of Thirdparty/EDTest/libopencv_imgproc.so.2.4.5"""
+    """cvSmooth(src, dst, CV_GAUSSIAN, 5, 5) through the C API of Thirdparty/EDTest/libopencv_imgproc.so.2.4.5.  In a child
+    process: the library's cv:: symbols are loaded RTLD_GLOBAL and would interpose the stand-in cv::Mat of oracle/_ref."""
+    subprocess.run([sys.executable, os.path.abspath(__file__), "--smoothing-check"], check=True)
+
+
+def _smoothing_check():
     import ed_oracle
     core = ctypes.CDLL(os.path.join(ED_REF, "libopencv_core.so.2.4.5"), mode=ctypes.RTLD_GLOBAL)
     imgproc = ctypes.CDLL(os.path.join(ED_REF, "libopencv_imgproc.so.2.4.5"))
@@ -202,3 +207,7 @@ def test_smoothing_stage_against_the_bundled_cvSmooth():
         core.cvSetData(b, dst.ctypes.data, W)
         imgproc.cvSmooth(a, b, 2, 5, 5, 0.0, 0.0)
         assert np.array_equal(dst, ed_oracle.smooth(im)), (H, W)
+
+
+if __name__ == "__main__" and sys.argv[1:] == ["--smoothing-check"]:
+    _smoothing_check()
