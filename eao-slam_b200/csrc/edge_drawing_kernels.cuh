@@ -5,7 +5,7 @@
 // are the mEdgeIndex candidate mask of the hot loop (ProbabilityMapping.cc:454) and the input of the 3-D line fitting
 // (:884-900).  eao-slam_b200/host/edge_drawing.h documents the open implementation and how every open detail was pinned to the
 // library's output.  The detector has two stages: per-pixel image work (smoothing, Sobel gradient, edge direction, anchor test)
-// and a sequential walk from the anchors.  This kernel is the first stage, the walk runs on host threads (sdm_edge_drawing in
+// and a sequential walk from the anchors.  These kernels are the first stage, the walk runs on host threads (sdm_edge_drawing in
 // sdm_b200.cu) while the next chunk of keyframes is on the device.
 //
 //   in : im  [n][H][W] u8                                                  1 byte per pixel
@@ -20,15 +20,254 @@
 // as u16, column pass with the library's rounding: half to even where its 4-wide vector loop runs, half up in the last W % 4
 // columns) -> gradient + direction (packed in one u16) -> anchor test -> 8-byte (G) and 4-byte (F) stores per thread.
 // HBM-bound by construction (4 algorithmic bytes per pixel, no re-reads besides the apron, which L2 serves).
+//
+// Two kernels.  k_ed_planes4 (widths that are multiples of four: every camera format) works on FOUR pixels per thread in
+// every phase with two 16-bit lanes per 32-bit register: 32-bit image loads, the 1-4-6-4-1 sums as packed multiply-adds (a
+// row sum is at most 16 * 255 and a column sum at most 256 * 255, both fit 16 bits, so no carry crosses the lanes), the
+// rounding, the Sobel taps and |a - b| = max - min (VIMNMX.U16x2) all lane-wise - 3.2x fewer issued instructions than the
+// byte-per-thread form, which was issue-bound (profiles/r02l_ed_planes.md: 80 % issue, 242 thread instructions per pixel).
+// The phases are host-callable functions of (tile, thread index), so tests/cpp/test_edge_drawing.cpp replays the kernel
+// thread by thread on the CPU against EdPlanesHost.  k_ed_planes (any width) is the byte-per-thread form.
 #pragma once
 
+#include <algorithm>
+#include <cstddef>
 #include <cstdint>
 
+#if defined(__CUDACC__)
+#define SDM_ED_HD __host__ __device__ __forceinline__
+#define SDM_ED_UNROLL _Pragma("unroll")
+#else
+#define SDM_ED_HD inline
+#define SDM_ED_UNROLL
+#endif
+
 namespace sdm {
+
+#if !defined(__CUDACC__)
+using std::max;
+using std::min;
+#endif
 
 constexpr int kEdTW = 64, kEdTH = 16, kEdThreads = 256;
 constexpr int kEdFlagAnchor = 0x80;
 
+// ---- four pixels per thread (W % 4 == 0) ----------------------------------------------------------------------------------
+// Two 16-bit lanes per register.  A group of four neighbouring values v0 v1 v2 v3 is kept as the pair of registers
+// (v0 | v2 << 16, v1 | v3 << 16): byte b of a 32-bit image word lands in lane (b & 1) of register (b >> 1) with one AND / shift.
+constexpr int kEdImRows = kEdTH + 8;   // image rows y0 - 4 .. y0 + TH + 3
+constexpr int kEdImWords = 18;         // image columns x0 - 4 .. x0 + 67 as 32-bit words
+constexpr int kEdGroups = 17;          // groups of four columns: from x0 - 2 (row sums, smoothed image), from x0 - 1 (gradient)
+constexpr int kEdGWords = 2 * kEdGroups;  // gradient row: 68 u16 = 34 words, columns x0 - 1 .. x0 + 66
+
+struct EdPair { uint32_t x, y; };
+struct alignas(16) EdTile {
+    uint32_t im[kEdImRows][kEdImWords];
+    EdPair row[kEdImRows][kEdGroups];          // row sums 1 4 6 4 1, lanes (o0, o2) / (o1, o3)
+    uint32_t sm[kEdTH + 4][kEdImWords];        // smoothed bytes in natural order; word 17 is padding the last gradient group reads
+    uint32_t g[kEdTH + 2][kEdGWords];          // gradient | direction << 12, u16 in natural order
+};
+
+SDM_ED_HD uint32_t ed_funnel_r(uint32_t lo, uint32_t hi, int s)
+{
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, s);
+#else
+    return (uint32_t)(((((uint64_t)hi) << 32) | lo) >> s);
+#endif
+}
+SDM_ED_HD uint32_t ed_absdiff2(uint32_t a, uint32_t b)  // |a - b| in both 16-bit lanes
+{
+#if defined(__CUDA_ARCH__)
+    return __vmaxu2(a, b) - __vminu2(a, b);
+#else
+    const uint32_t al = a & 0xffffu, bl = b & 0xffffu, ah = a >> 16, bh = b >> 16;
+    return (al > bl ? al - bl : bl - al) | ((ah > bh ? ah - bh : bh - ah) << 16);
+#endif
+}
+SDM_ED_HD uint32_t ed_lo_pair(uint32_t a, uint32_t b) { return (a & 0xffffu) | (b << 16); }        // (a.lo, b.lo)
+SDM_ED_HD uint32_t ed_hi_pair(uint32_t a, uint32_t b) { return (a >> 16) | (b & 0xffff0000u); }    // (a.hi, b.hi)
+
+struct EdArgs {
+    const uint8_t* src;  // the keyframe's image, dense W x H
+    int16_t* G;
+    uint8_t* F;
+    int W, H, x0, y0, grad_thresh, anchor_thresh;
+};
+
+// image tile, replicated border (the smoothing's border rule); items: kEdImRows * kEdImWords
+SDM_ED_HD void ed4_load(EdTile& t, const EdArgs& a, int i)
+{
+    const int j = i / kEdImWords, w = i - j * kEdImWords;
+    const int y = min(max(a.y0 - 4 + j, 0), a.H - 1), x = a.x0 - 4 + 4 * w;
+    const uint8_t* r = a.src + (size_t)y * a.W;
+    uint32_t v;
+    if (x < 0) v = r[0] * 0x01010101u;
+    else if (x >= a.W) v = r[a.W - 1] * 0x01010101u;
+    else {
+#if defined(__CUDA_ARCH__)
+        v = __ldg(reinterpret_cast<const uint32_t*>(r + x));
+#else
+        v = (uint32_t)r[x] | ((uint32_t)r[x + 1] << 8) | ((uint32_t)r[x + 2] << 16) | ((uint32_t)r[x + 3] << 24);
+#endif
+    }
+    t.im[j][w] = v;
+}
+
+// row sums at x = x0 - 2 + 4 g + q from image bytes b0 .. b7 = columns x0 - 4 + 4 g ..; items: kEdImRows * kEdGroups
+SDM_ED_HD void ed4_rows(EdTile& t, int i)
+{
+    const int j = i / kEdGroups, g = i - j * kEdGroups;
+    const uint32_t m = 0x00ff00ffu;
+    const uint32_t w0 = t.im[j][g], w1 = t.im[j][g + 1];
+    const uint32_t E = w0 & m, O = (w0 >> 8) & m;                                  // (b0, b2) (b1, b3)
+    const uint32_t S16 = ed_funnel_r(w0, w1, 16) & m, S24 = ed_funnel_r(w0, w1, 24) & m;  // (b2, b4) (b3, b5)
+    const uint32_t E1 = w1 & m, O1 = (w1 >> 8) & m;                                // (b4, b6) (b5, b7)
+    EdPair r;
+    r.x = E + 4 * O + 6 * S16 + 4 * S24 + E1;   // o0 = b0 + 4 b1 + 6 b2 + 4 b3 + b4,  o2 = b2 + .. + b6
+    r.y = O + 4 * S16 + 6 * S24 + 4 * E1 + O1;  // o1, o3
+    t.row[j][g] = r;
+}
+
+// column pass at y = y0 - 2 + j with the library's half-to-even rounding of v / 256; items: (kEdTH + 4) * kEdGroups
+SDM_ED_HD uint32_t ed4_round(uint32_t v) { return ((v + 0x007f007fu + ((v >> 8) & 0x00010001u)) >> 8) & 0x00ff00ffu; }
+SDM_ED_HD void ed4_cols(EdTile& t, int i)
+{
+    const int j = i / kEdGroups, g = i - j * kEdGroups;
+    const EdPair a = t.row[j][g], b = t.row[j + 1][g], c = t.row[j + 2][g], d = t.row[j + 3][g], e = t.row[j + 4][g];
+    const uint32_t s02 = ed4_round(a.x + 4 * b.x + 6 * c.x + 4 * d.x + e.x);
+    const uint32_t s13 = ed4_round(a.y + 4 * b.y + 6 * c.y + 4 * d.y + e.y);
+    t.sm[j][g] = s02 | (s13 << 8);
+    if (g == kEdGroups - 1) t.sm[j][kEdGroups] = 0;
+}
+
+// gradient + direction at y = y0 - 1 + j, x = x0 - 1 + 4 g + q; items: (kEdTH + 2) * kEdGroups
+SDM_ED_HD void ed4_grad(EdTile& t, const EdArgs& a, int i)
+{
+    const int j = i / kEdGroups, g = i - j * kEdGroups;
+    const uint32_t m = 0x00ff00ffu;
+    uint32_t E[3], O[3], S16[3], S24[3];
+    SDM_ED_UNROLL
+    for (int r = 0; r < 3; ++r) {
+        const uint32_t w0 = t.sm[j + r][g], w1 = t.sm[j + r][g + 1];
+        E[r] = w0 & m;
+        O[r] = (w0 >> 8) & m;
+        S16[r] = ed_funnel_r(w0, w1, 16) & m;
+        S24[r] = ed_funnel_r(w0, w1, 24) & m;
+    }
+    // |gy|: the 1 2 1 row taps of the row below minus those of the row above, centres at bytes 1 .. 4
+    const uint32_t gy02 = ed_absdiff2(E[2] + 2 * O[2] + S16[2], E[0] + 2 * O[0] + S16[0]);
+    const uint32_t gy13 = ed_absdiff2(O[2] + 2 * S16[2] + S24[2], O[0] + 2 * S16[0] + S24[0]);
+    // |gx|: the 1 2 1 column taps of the column to the right minus those of the column to the left
+    const uint32_t cE = E[0] + 2 * E[1] + E[2], cO = O[0] + 2 * O[1] + O[2];
+    const uint32_t cS16 = S16[0] + 2 * S16[1] + S16[2], cS24 = S24[0] + 2 * S24[1] + S24[2];
+    const uint32_t gx02 = ed_absdiff2(cS16, cE), gx13 = ed_absdiff2(cS24, cO);
+    const uint32_t th = (uint32_t)a.grad_thresh * 0x00010001u;
+    uint32_t code[2];
+    {
+        const uint32_t gx[2] = {gx02, gx13}, gy[2] = {gy02, gy13};
+    SDM_ED_UNROLL
+        for (int k = 0; k < 2; ++k) {
+            const uint32_t v = gx[k] + gy[k];                                                   // <= 2040 per lane
+            const uint32_t ge = (((gx[k] | 0x80008000u) - gy[k]) >> 15) & 0x00010001u;          // |gx| >= |gy|
+            const uint32_t on = (((v | 0x80008000u) - th) >> 15) & 0x00010001u;                 // v >= grad_thresh
+            code[k] = v | (((0x00020002u - ge) & (on * 3u)) << 12);                             // direction 1 vertical, 2 horizontal
+        }
+    }
+    uint32_t lo = ed_lo_pair(code[0], code[1]), hi = ed_hi_pair(code[0], code[1]);  // (o0, o1) (o2, o3)
+    const int y = a.y0 - 1 + j, xs = a.x0 - 1 + 4 * g;
+    const uint32_t border = (uint32_t)(a.grad_thresh - 1);
+    if (y < 1 || y > a.H - 2) lo = hi = border * 0x00010001u;
+    else if (xs < 1 || xs + 3 > a.W - 2) {
+        if (xs < 1 || xs > a.W - 2) lo = (lo & 0xffff0000u) | border;
+        if (xs + 1 < 1 || xs + 1 > a.W - 2) lo = (lo & 0x0000ffffu) | (border << 16);
+        if (xs + 2 < 1 || xs + 2 > a.W - 2) hi = (hi & 0xffff0000u) | border;
+        if (xs + 3 < 1 || xs + 3 > a.W - 2) hi = (hi & 0x0000ffffu) | (border << 16);
+    }
+    t.g[j][2 * g] = lo;
+    t.g[j][2 * g + 1] = hi;
+}
+
+// anchor test and stores: thread i -> row i / 16 of the tile, four pixels from column 4 * (i % 16)
+SDM_ED_HD void ed4_store(const EdTile& t, const EdArgs& a, int i)
+{
+    const int ty = i >> 4, tw = (i & 15) << 1;  // first gradient word of the group (u16 index 4 * (i % 16))
+    const int y = a.y0 + ty, x = a.x0 + 2 * tw;
+    if (y >= a.H || x >= a.W) return;
+    // u16 lanes c[0 .. 5] of the pixel's row = columns x - 1 .. x + 4, u[..] / d[..] the rows above / below
+    const uint32_t c0 = t.g[ty + 1][tw], c1 = t.g[ty + 1][tw + 1], c2 = t.g[ty + 1][tw + 2];
+    const uint32_t u0 = t.g[ty][tw], u1 = t.g[ty][tw + 1], u2 = t.g[ty][tw + 2];
+    const uint32_t d0 = t.g[ty + 2][tw], d1 = t.g[ty + 2][tw + 1], d2 = t.g[ty + 2][tw + 2];
+    const uint32_t cw[3] = {c0, c1, c2}, uw[3] = {u0, u1, u2}, dw[3] = {d0, d1, d2};
+    uint32_t f = 0;
+    SDM_ED_UNROLL
+    for (int q = 0; q < 4; ++q) {
+#define SDM_ED_LANE(w, k) (((w)[(k) >> 1] >> (((k) & 1) * 16)) & 0xffffu)
+        const int v = (int)SDM_ED_LANE(cw, q + 1);
+        const int gq = v & 0xfff, dir = v >> 12;
+        int fq = dir;
+        const int xx = x + q;
+        if (dir != 0 && y >= 2 && y <= a.H - 3 && xx >= 2 && xx <= a.W - 3) {
+            const int n0 = (int)(dir == 1 ? SDM_ED_LANE(cw, q) : SDM_ED_LANE(uw, q + 1)) & 0xfff;
+            const int n1 = (int)(dir == 1 ? SDM_ED_LANE(cw, q + 2) : SDM_ED_LANE(dw, q + 1)) & 0xfff;
+            if (gq - n0 >= a.anchor_thresh && gq - n1 >= a.anchor_thresh) fq |= kEdFlagAnchor;
+        }
+#undef SDM_ED_LANE
+        f |= (uint32_t)fq << (8 * q);
+    }
+    const uint32_t g01 = ed_funnel_r(c0, c1, 16) & 0x0fff0fffu, g23 = ed_funnel_r(c1, c2, 16) & 0x0fff0fffu;
+    const size_t o = (size_t)y * a.W + x;
+#if defined(__CUDA_ARCH__)
+    *reinterpret_cast<uint2*>(a.G + o) = make_uint2(g01, g23);
+    *reinterpret_cast<uint32_t*>(a.F + o) = f;
+#else
+    a.G[o] = (int16_t)(g01 & 0xffffu); a.G[o + 1] = (int16_t)(g01 >> 16);
+    a.G[o + 2] = (int16_t)(g23 & 0xffffu); a.G[o + 3] = (int16_t)(g23 >> 16);
+    for (int q = 0; q < 4; ++q) a.F[o + q] = (uint8_t)(f >> (8 * q));
+#endif
+}
+
+constexpr int kEd4Items0 = kEdImRows * kEdImWords, kEd4Items1 = kEdImRows * kEdGroups, kEd4Items2 = (kEdTH + 4) * kEdGroups,
+              kEd4Items3 = (kEdTH + 2) * kEdGroups;
+
+#if defined(__CUDACC__)
+__global__ void __launch_bounds__(kEdThreads)
+k_ed_planes4(const uint8_t* __restrict__ im, int W, int H, int grad_thresh, int anchor_thresh, int16_t* __restrict__ G,
+             uint8_t* __restrict__ F)
+{
+    __shared__ EdTile t;
+    const int tid = threadIdx.x;
+    const size_t plane = (size_t)blockIdx.z * (size_t)W * (size_t)H;
+    const EdArgs a = {im + plane, G + plane, F + plane, W, H, (int)blockIdx.x * kEdTW, (int)blockIdx.y * kEdTH, grad_thresh, anchor_thresh};
+    for (int i = tid; i < kEd4Items0; i += kEdThreads) ed4_load(t, a, i);
+    __syncthreads();
+    for (int i = tid; i < kEd4Items1; i += kEdThreads) ed4_rows(t, i);
+    __syncthreads();
+    for (int i = tid; i < kEd4Items2; i += kEdThreads) ed4_cols(t, i);
+    __syncthreads();
+    for (int i = tid; i < kEd4Items3; i += kEdThreads) ed4_grad(t, a, i);
+    __syncthreads();
+    ed4_store(t, a, tid);
+}
+#endif
+
+// the same kernel thread by thread on the host (tests): every phase for every thread of every tile, in order
+inline void EdPlanes4Replay(const uint8_t* im, int W, int H, int grad_thresh, int anchor_thresh, int16_t* G, uint8_t* F)
+{
+    static EdTile t;
+    for (int by = 0; by < (H + kEdTH - 1) / kEdTH; ++by)
+        for (int bx = 0; bx < (W + kEdTW - 1) / kEdTW; ++bx) {
+            const EdArgs a = {im, G, F, W, H, bx * kEdTW, by * kEdTH, grad_thresh, anchor_thresh};
+            for (int i = 0; i < kEd4Items0; ++i) ed4_load(t, a, i);
+            for (int i = 0; i < kEd4Items1; ++i) ed4_rows(t, i);
+            for (int i = 0; i < kEd4Items2; ++i) ed4_cols(t, i);
+            for (int i = 0; i < kEd4Items3; ++i) ed4_grad(t, a, i);
+            for (int i = 0; i < kEdThreads; ++i) ed4_store(t, a, i);
+        }
+}
+
+// ---- one byte per thread (any width) ----------------------------------------------------------------------------------------
+#if defined(__CUDACC__)
 __global__ void __launch_bounds__(kEdThreads)
 k_ed_planes(const uint8_t* __restrict__ im, int W, int H, int grad_thresh, int anchor_thresh, int16_t* __restrict__ G,
             uint8_t* __restrict__ F)
@@ -118,5 +357,6 @@ k_ed_planes(const uint8_t* __restrict__ im, int W, int H, int grad_thresh, int a
         }
     }
 }
+#endif
 
 }  // namespace sdm

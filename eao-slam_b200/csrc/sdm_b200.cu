@@ -1684,7 +1684,11 @@ struct sdm_ed_result {
 
 namespace {
 
-constexpr int kEdChunk = 8;     // keyframes per device chunk (H2D, k_ed_planes, D2H; the unit the routing threads wait for)
+// keyframes per device chunk (H2D, stage-1 kernel, D2H; the unit the routing threads wait for): two chunks of 8 so that the
+// host threads start walking after ~100 us, 16, then 32 per launch (39 MB of planes at VGA: enough to fill the device)
+inline int ed_chunk_first(int ch) { return ch < 2 ? 8 * ch : (ch == 2 ? 16 : 32 * (ch - 2)); }
+inline int ed_chunk_of(int i) { return i < 16 ? i / 8 : (i < 32 ? 2 : 2 + i / 32); }
+inline int ed_chunk_count(int n) { return n <= 0 ? 0 : ed_chunk_of(n - 1) + 1; }
 constexpr int kEdMaxBatch = 256;  // keyframes whose planes are resident at once (pinned + device: 4 bytes per pixel each)
 
 size_t ed_bytes(int cap, size_t P);
@@ -1718,8 +1722,11 @@ int ed_launch(sdm_ctx* c, const EdLayout& d, int first, int count, int grad_thre
 {
     const int W = c->cfg.width, H = c->cfg.height;
     const dim3 grid((W + sdm::kEdTW - 1) / sdm::kEdTW, (H + sdm::kEdTH - 1) / sdm::kEdTH, count);
-    sdm::k_ed_planes<<<grid, sdm::kEdThreads, 0, c->s_ed>>>(d.im + (size_t)first * c->npix, W, H, grad_thresh, anchor_thresh,
-                                                           d.G + (size_t)first * c->npix, d.F + (size_t)first * c->npix);
+    const uint8_t* im = d.im + (size_t)first * c->npix;
+    int16_t* G = d.G + (size_t)first * c->npix;
+    uint8_t* F = d.F + (size_t)first * c->npix;
+    if ((W & 3) == 0) sdm::k_ed_planes4<<<grid, sdm::kEdThreads, 0, c->s_ed>>>(im, W, H, grad_thresh, anchor_thresh, G, F);
+    else sdm::k_ed_planes<<<grid, sdm::kEdThreads, 0, c->s_ed>>>(im, W, H, grad_thresh, anchor_thresh, G, F);
     CU(cudaGetLastError());
     ++c->launches;
     return SDM_OK;
@@ -1750,7 +1757,7 @@ int sdm_edge_drawing(sdm_ctx* c, int n, const sdm_ed_image* images, int grad_thr
     auto body = [&]() -> int {
         CU(cudaSetDevice(c->cfg.device));
         RC(ed_reserve(c, std::min(n, kEdMaxBatch)));
-        const int n_chunks_max = (std::min(n, kEdMaxBatch) + kEdChunk - 1) / kEdChunk;
+        const int n_chunks_max = ed_chunk_count(std::min(n, kEdMaxBatch));
         while ((int)c->ed_ev.size() < 3 * n_chunks_max) {
             cudaEvent_t e;
             CU(cudaEventCreate(&e));
@@ -1761,7 +1768,7 @@ int sdm_edge_drawing(sdm_ctx* c, int n, const sdm_ed_image* images, int grad_thr
         const int nt = std::max(1, std::min(n_threads > 0 ? n_threads : (int)std::min(hw, 32u), n));
         const EdLayout dv(c->ed_dev, c->ed_cap, P), hv(c->ed_host, c->ed_cap, P);
         for (int base = 0; base < n; base += kEdMaxBatch) {
-            const int nb = std::min(kEdMaxBatch, n - base), n_chunks = (nb + kEdChunk - 1) / kEdChunk;
+            const int nb = std::min(kEdMaxBatch, n - base), n_chunks = ed_chunk_count(nb);
             std::atomic<int> next(0), issued(0), failed(0);
             std::atomic<long long> route_ns(0);
             std::mutex mu;
@@ -1773,7 +1780,7 @@ int sdm_edge_drawing(sdm_ctx* c, int n, const sdm_ed_image* images, int grad_thr
                     for (;;) {
                         const int i = next.fetch_add(1);
                         if (i >= nb) return;
-                        const int chunk = i / kEdChunk;
+                        const int chunk = ed_chunk_of(i);
                         {
                             std::unique_lock<std::mutex> lk(mu);
                             cv.wait(lk, [&] { return issued.load() > chunk || failed.load(); });
@@ -1789,7 +1796,7 @@ int sdm_edge_drawing(sdm_ctx* c, int n, const sdm_ed_image* images, int grad_thr
                 });
             auto issue = [&]() -> int {
                 for (int ch = 0; ch < n_chunks; ++ch) {
-                    const int first = ch * kEdChunk, count = std::min(kEdChunk, nb - first);
+                    const int first = ed_chunk_first(ch), count = std::min(ed_chunk_first(ch + 1), nb) - first;
                     for (int i = first; i < first + count; ++i) {  // pack the rows into the pinned mirror
                         const sdm_ed_image& im = images[base + i];
                         uint8_t* dst = hv.im + (size_t)i * P;

@@ -2,7 +2,9 @@
 // and dumps the chains in the format of oracle/ed_chains.cpp (the same dump of the reference's closed-source EDLib.a), so that
 // tests/test_edge_drawing.py can compare the two byte for byte.
 //   usage: test_edge_drawing W H N in.raw out.bin [edge_index.bin [planes.bin]]      ("-" skips edge_index.bin)
-//   planes.bin: per image the stage-1 planes of EdPlanesHost, G (int16 W*H) then F (uint8 W*H)
+//   planes.bin: per image the stage-1 planes of EdPlanesHost, G (int16 W*H) then F (uint8 W*H); for widths that are multiples
+//   of four (and >= 8 x 8, the library's minimum) the device kernel k_ed_planes4 is replayed thread by thread on the CPU
+//   (sdm::EdPlanes4Replay, csrc/edge_drawing_kernels.cuh) and must give the same planes: exit code 4 otherwise
 //   prints the host time of the detector per image (both stages, one thread) on stderr
 //   out.bin (int32): N, then per image: noSegments, per segment: noPixels, (r, c) * noPixels
 #include <stdio.h>
@@ -12,6 +14,7 @@
 #include <vector>
 
 #include "../../eao-slam_b200/host/edge_drawing.h"
+#include "../../eao-slam_b200/csrc/edge_drawing_kernels.cuh"
 
 int main(int argc, char** argv)
 {
@@ -49,6 +52,18 @@ int main(int argc, char** argv)
             sdm_host::EdPlanesHost(im.data(), (size_t)W, W, H, 36, 8, G.data(), F.data());
             fwrite(G.data(), 2, G.size(), fp);
             fwrite(F.data(), 1, F.size(), fp);
+            if ((W & 3) == 0 && W >= 8 && H >= 8) {
+                std::vector<int16_t> G4((size_t)W * H, (int16_t)-1);
+                std::vector<uint8_t> F4((size_t)W * H, (uint8_t)0xee);
+                sdm::EdPlanes4Replay(im.data(), W, H, 36, 8, G4.data(), F4.data());
+                if (G4 != G || F4 != F) {
+                    size_t k = 0;
+                    while (k < G.size() && G4[k] == G[k] && F4[k] == F[k]) ++k;
+                    fprintf(stderr, "k_ed_planes4 replay differs at image %d, pixel (%d, %d): G %d / %d, F %02x / %02x\n", i,
+                            (int)(k / W), (int)(k % W), (int)G4[k], (int)G[k], (unsigned)F4[k], (unsigned)F[k]);
+                    return 4;
+                }
+            }
         }
     }
     fprintf(stderr, "host_ms_per_image %.4f\n", N > 0 ? det_ms / N : 0.0);

@@ -180,6 +180,29 @@ def test_live_against_the_library(ed_bin, tmp_path):
     assert n_chains > 3000
 
 
+def test_device_kernel_replayed_on_the_cpu_matches_the_host_planes(ed_bin, tmp_path):
+    """k_ed_planes4 (csrc/edge_drawing_kernels.cuh: four pixels per thread, two 16-bit lanes per register) is written as
+    host-callable phases; the driver replays them thread by thread for every tile and compares G / F with EdPlanesHost (exit
+    code 4 on the first differing pixel).  Scene keyframes, noise (the worst case for the lane arithmetic: sums near the
+    16-bit limit), few-level images (exact .5 ties of the rounding), saturated images, tile-edge sizes."""
+    from sdmb200 import synth
+    rng = np.random.default_rng(11)
+    cases = [np.ascontiguousarray(synth.make_scene(8, 320, 240, 6, seed=5, workers=4).im[:3])]
+    for H, W in [(8, 8), (16, 64), (17, 68), (48, 64), (150, 200), (33, 8), (9, 132), (100, 60), (31, 128), (64, 252)]:
+        im = rng.integers(0, 256, (4, H, W)).astype(np.uint8)
+        im[1] = im[1] // 64 * 64
+        im[2] = np.where(im[2] > 127, 255, 0)
+        im[3] = 255
+        cases.append(im)
+    for im in cases:
+        n, H, W = im.shape
+        raw = str(tmp_path / "in.raw")
+        im.tofile(raw)
+        r = subprocess.run([ed_bin, str(W), str(H), str(n), raw, str(tmp_path / "out.bin"), "-", str(tmp_path / "planes.bin")],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, (H, W, r.stderr)
+
+
 @pytest.mark.skipif(not have_ref, reason="needs the reference's bundled OpenCV 2.4.5 (build container only)")
 def test_smoothing_stage_against_the_bundled_cvSmooth():
     """cvSmooth(src, dst, CV_GAUSSIAN, 5, 5) through the C API of Thirdparty/EDTest/libopencv_imgproc.so.2.4.5.  In a child
