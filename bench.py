@@ -845,6 +845,27 @@ def main_ours(a, rank, world, local_rank):
                         "produced on the device by k_pack_image"}
     line["scan_generation"] = ctx.scan_generation()
     line["scan_long_build"] = ctx.last_scan_long()
+    if world == 1 and do_e2e and not a.no_e2e_variants:
+        # what the reference does per keyframe inside pass 1 before the pixel loop (LineDetector::DetectEdgeMap,
+        # ProbabilityMapping.cc:394 -> LineDetector.cc:843-881, closed-source EDLib.a): sdm_edge_drawing over this rank's images
+        n_ed = min(n_loc, 256)
+        ims = sc.im[:n_ed]
+        ctx.edge_drawing(ims[:32], edge_index=False)
+        best = None
+        for _ in range(3):
+            offs, _pix, _edge = ctx.edge_drawing(ims, edge_index=True)
+            t = ctx.last_edge_drawing_ms()
+            if best is None or t["wall_ms"] < best["wall_ms"]:
+                best = t
+        k_s = best["kernel_ms"] * 1e-3 / n_ed
+        line["edge_drawing"] = {"keyframes": n_ed, "wall_ms_per_keyframe": best["wall_ms"] / n_ed,
+                                "stage1_kernel_us_per_keyframe": 1e6 * k_s,
+                                "stage1_roofline": {"bound": "hbm", "achieved": 4.0 * W * H / k_s / 1e9, "peak": peak, "unit": "GB/s",
+                                                    "frac": 4.0 * W * H / k_s / 1e9 / peak},
+                                "routing_thread_ms_per_keyframe": best["route_thread_ms"] / n_ed,
+                                "chains": int(sum(len(o) - 1 for o in offs)),
+                                "api": "sdm_edge_drawing: smoothing / Sobel / direction / anchors on the device (k_ed_planes4, 4 algorithmic "
+                                       "bytes per pixel), the sequential routing walk on host threads; chains identical to the reference's EDLib.a"}
     ctx.close()
     if world == 1 and do_e2e and not a.no_e2e_variants:
         r = class_e2e(a, sc, n_loc)
