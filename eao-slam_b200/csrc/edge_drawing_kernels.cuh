@@ -34,6 +34,8 @@
 #include <cstddef>
 #include <cstdint>
 
+#include "../host/edge_drawing.h"
+
 #if defined(__CUDACC__)
 #define SDM_ED_HD __host__ __device__ __forceinline__
 #define SDM_ED_UNROLL _Pragma("unroll")
@@ -355,6 +357,51 @@ k_ed_planes(const uint8_t* __restrict__ im, int W, int H, int grad_thresh, int a
                 for (int q = 0; q < 4 && x + q < W; ++q) { go[q] = gq[q]; fo[q] = fq[q]; }
             }
         }
+    }
+}
+
+// ---- stage 2 on the device: one warp per image ------------------------------------------------------------------------------
+// The routing walk is sequential per image (a step depends on the marks the previous walks left), so an image is one thread's
+// work: lane 0 of the image's warp runs sdm_host::EdRouteFixed - the same source the host threads run, on fixed arrays in
+// global memory - after the 32 lanes have filled the image's edge-index plane with -1.  One warp per block: the device takes
+// 32 resident images per SM, 4736 in flight on a B200; a step costs a few dependent L2 / HBM round trips (about 1 us), which
+// only pays when many images are routed at once - the host threads need 1.4 ms per image and thread, but there are 16-32 of
+// them against thousands of warps.  result[img] = {chains, chain pixels, 1 if complete (0: a capacity ran out, the host routes
+// the image instead), 0}.
+struct EdRouteBatch {
+    int W, H, grad_thresh;
+    const int16_t* G;      // [n][H][W] stage-1 planes
+    uint8_t* F;            // [n][H][W], modified in place
+    uint8_t* scratch;      // n * scratch_stride bytes
+    size_t scratch_stride;
+    sdm_host::EdRouteCaps caps;
+    int32_t* offsets;      // [n][caps.offsets]
+    uint32_t* pixels;      // [n][caps.out_pixels]
+    int32_t* edge_index;   // [n][H][W] or NULL
+    int4* result;          // [n]
+};
+
+__global__ void __launch_bounds__(32) k_ed_route(EdRouteBatch b)
+{
+    const int img = blockIdx.x, lane = threadIdx.x;
+    const size_t P = (size_t)b.W * b.H;
+    int32_t* edge = b.edge_index ? b.edge_index + (size_t)img * P : nullptr;
+    if (edge) {
+        if ((P & 3) == 0) {
+            int4* e4 = reinterpret_cast<int4*>(edge);
+            for (size_t i = lane; i < P / 4; i += 32) e4[i] = make_int4(-1, -1, -1, -1);
+        } else {
+            for (size_t i = lane; i < P; i += 32) edge[i] = -1;
+        }
+    }
+    __syncwarp();
+    if (lane == 0) {
+        int nc = 0, np = 0;
+        const bool ok = sdm_host::EdRouteFixed(b.W, b.H, b.G + (size_t)img * P, b.F + (size_t)img * P, b.grad_thresh,
+                                               b.scratch + (size_t)img * b.scratch_stride, b.caps,
+                                               b.offsets + (size_t)img * b.caps.offsets, b.pixels + (size_t)img * b.caps.out_pixels, edge,
+                                               (size_t)b.W * 4, &nc, &np);
+        b.result[img] = make_int4(nc, np, ok ? 1 : 0, 0);
     }
 }
 #endif

@@ -284,6 +284,13 @@ struct sdm_ctx {
     cudaStream_t s_ed = nullptr;
     std::vector<cudaEvent_t> ed_ev;  // per chunk: kernel start, kernel stop, planes on the host
     float ed_kernel_ms = 0.f, ed_wall_ms = 0.f, ed_route_ms = 0.f;
+    // device routing (sdm_set_edge_drawing_route): per-image scratch, chain lists, edge-index planes, results
+    int ed_route_mode = 0;
+    uint8_t* edr_dev = nullptr;
+    int4* edr_result_host = nullptr;
+    int edr_cap = 0;
+    int edr_fallbacks = 0;
+    cudaEvent_t edr_ev[2] = {nullptr, nullptr};
     void* peer_rs[kMaxPeers] = {nullptr};
     // sdm_exchange: flag blocks (own + IPC-mapped peers), halo plan, step counter
     sdm::XFlags* xflags = nullptr;
@@ -619,6 +626,9 @@ void sdm_destroy(sdm_ctx* c)
     cudaFree(c->tmp_rs); cudaFree(c->xfer); cudaFree(c->dbg); cudaFree(c->exp_buf); cudaFree(c->exp_pts); cudaFree(c->lf_buf);
     if (c->lf_host) cudaFreeHost(c->lf_host);
     cudaFree(c->ed_dev);
+    cudaFree(c->edr_dev);
+    if (c->edr_result_host) cudaFreeHost(c->edr_result_host);
+    for (auto& e : c->edr_ev) if (e) cudaEventDestroy(e);
     if (c->ed_host) cudaFreeHost(c->ed_host);
     if (c->s_ed) cudaStreamDestroy(c->s_ed);
     for (auto& e : c->ed_ev) cudaEventDestroy(e);
@@ -1699,6 +1709,9 @@ int ed_reserve(sdm_ctx* c, int n_kf)
     if (c->ed_cap >= n_kf) return SDM_OK;
     CU(cudaStreamSynchronize(c->s_ed));
     cudaFree(c->ed_dev);
+    cudaFree(c->edr_dev);
+    if (c->edr_result_host) cudaFreeHost(c->edr_result_host);
+    for (auto& e : c->edr_ev) if (e) cudaEventDestroy(e);
     if (c->ed_host) cudaFreeHost(c->ed_host);
     c->ed_dev = nullptr; c->ed_host = nullptr; c->ed_cap = 0;
     const size_t bytes = ed_bytes(n_kf, c->npix);
@@ -1734,6 +1747,172 @@ int ed_launch(sdm_ctx* c, const EdLayout& d, int first, int count, int grad_thre
 
 }  // namespace
 
+namespace {
+
+constexpr int kEdDevBatch = 1024;  // images routed by one k_ed_route launch (27 bytes of scratch + 9 of results per pixel each)
+
+// sections of the device block of the routing kernel for `cap` images
+struct EdRouteLayout {
+    sdm_host::EdRouteCaps caps;
+    size_t scratch_stride, o_scratch, o_off, o_px, o_edge, o_res, bytes;
+    EdRouteLayout(int cap, size_t P)
+    {
+        caps = sdm_host::EdRouteCapsFor(P);
+        if (const char* e = getenv("SDM_ED_ROUTE_TEST_CAPS")) {  // test hook: tiny per-tree capacities force the host fall-back
+            const int v = atoi(e);
+            if (v > 0) { caps.pixels = std::min(caps.pixels, v); caps.chains = std::min(caps.chains, std::max(4, v / 4)); }
+        }
+        scratch_stride = ed_align(sdm_host::EdRouteScratchBytes(caps));
+        o_scratch = 0;
+        o_off = o_scratch + (size_t)cap * scratch_stride;
+        o_px = ed_align(o_off + (size_t)cap * caps.offsets * 4);
+        o_edge = ed_align(o_px + (size_t)cap * caps.out_pixels * 4);
+        o_res = ed_align(o_edge + (size_t)cap * P * 4);
+        bytes = ed_align(o_res + (size_t)cap * sizeof(int4));
+    }
+};
+
+int edr_reserve(sdm_ctx* c, int n_img)
+{
+    for (auto& e : c->edr_ev) if (!e) CU(cudaEventCreate(&e));
+    if (c->edr_cap >= n_img) return SDM_OK;
+    CU(cudaStreamSynchronize(c->s_ed));
+    cudaFree(c->edr_dev);
+    if (c->edr_result_host) cudaFreeHost(c->edr_result_host);
+    c->edr_dev = nullptr; c->edr_result_host = nullptr; c->edr_cap = 0;
+    const EdRouteLayout L(n_img, c->npix);
+    CU(cudaMalloc((void**)&c->edr_dev, L.bytes));
+    CU(cudaMallocHost((void**)&c->edr_result_host, (size_t)n_img * sizeof(int4)));
+    c->edr_cap = n_img;
+    return SDM_OK;
+}
+
+// sdm_edge_drawing with both stages on the device: batches of up to kEdDevBatch images - images up, k_ed_planes(4) over the
+// batch, k_ed_route (one warp per image), the per-image counts down, then exactly the chain lists (through the pinned
+// mirror) and the requested edge-index planes.  Images whose routing ran out of a capacity are routed on the host.
+int ed_run_device(sdm_ctx* c, int n, const sdm_ed_image* images, int grad_thresh, int anchor_thresh, sdm_ed_result* res)
+{
+    const int W = c->cfg.width, H = c->cfg.height;
+    const size_t P = c->npix;
+    CU(cudaSetDevice(c->cfg.device));
+    const int cap = std::min(n, kEdDevBatch);
+    RC(ed_reserve(c, cap));
+    RC(edr_reserve(c, cap));
+    while ((int)c->ed_ev.size() < 3) {
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        c->ed_ev.push_back(e);
+    }
+    const EdLayout dv(c->ed_dev, c->ed_cap, P), hv(c->ed_host, c->ed_cap, P);
+    const EdRouteLayout L(c->edr_cap, P);
+    c->edr_fallbacks = 0;
+    for (int base = 0; base < n; base += cap) {
+        const int nb = std::min(cap, n - base);
+        bool want_edge = false;
+        for (int i = 0; i < nb; ++i) {
+            const sdm_ed_image& im = images[base + i];
+            want_edge = want_edge || im.edge_index != nullptr;
+            uint8_t* dst = hv.im + (size_t)i * P;
+            if (im.im_step == (size_t)W) std::memcpy(dst, im.im, P);
+            else for (int y = 0; y < H; ++y) std::memcpy(dst + (size_t)y * W, im.im + (size_t)y * im.im_step, (size_t)W);
+        }
+        CU(cudaMemcpyAsync(dv.im, hv.im, (size_t)nb * P, cudaMemcpyHostToDevice, c->s_ed));
+        CU(cudaEventRecord(c->ed_ev[0], c->s_ed));
+        RC(ed_launch(c, dv, 0, nb, grad_thresh, anchor_thresh));
+        CU(cudaEventRecord(c->ed_ev[1], c->s_ed));
+        sdm::EdRouteBatch b;
+        b.W = W; b.H = H; b.grad_thresh = grad_thresh;
+        b.G = dv.G; b.F = dv.F;
+        b.scratch = c->edr_dev + L.o_scratch; b.scratch_stride = L.scratch_stride;
+        b.caps = L.caps;
+        b.offsets = (int32_t*)(c->edr_dev + L.o_off);
+        b.pixels = (uint32_t*)(c->edr_dev + L.o_px);
+        b.edge_index = want_edge ? (int32_t*)(c->edr_dev + L.o_edge) : nullptr;
+        b.result = (int4*)(c->edr_dev + L.o_res);
+        CU(cudaEventRecord(c->edr_ev[0], c->s_ed));
+        sdm::k_ed_route<<<nb, 32, 0, c->s_ed>>>(b);
+        CU(cudaGetLastError());
+        ++c->launches;
+        CU(cudaEventRecord(c->edr_ev[1], c->s_ed));
+        CU(cudaMemcpyAsync(c->edr_result_host, b.result, (size_t)nb * sizeof(int4), cudaMemcpyDeviceToHost, c->s_ed));
+        CU(cudaStreamSynchronize(c->s_ed));
+        // the chain lists, exactly as long as they are, through the pinned mirror's G / F sections (unused in this mode)
+        uint8_t* bounce = (uint8_t*)hv.G;
+        const size_t bounce_bytes = (size_t)((uint8_t*)hv.im + ed_bytes(c->ed_cap, P) - bounce);
+        std::vector<size_t> at((size_t)nb + 1, 0);
+        int first = 0;
+        while (first < nb) {  // groups of images whose lists fit the mirror together
+            size_t used = 0;
+            int last = first;
+            for (; last < nb; ++last) {
+                const int4 r = c->edr_result_host[last];
+                const size_t need = r.z ? ((size_t)r.x + 1 + (size_t)r.y) * 4 : 0;
+                if (used + need > bounce_bytes && last > first) break;
+                if (need > bounce_bytes) return fail(SDM_ERR_NOMEM, "sdm_edge_drawing: chain list of image %d exceeds the staging area", base + last);
+                at[(size_t)last] = used;
+                used += need;
+            }
+            for (int i = first; i < last; ++i) {
+                const int4 r = c->edr_result_host[i];
+                if (!r.z) continue;
+                CU(cudaMemcpyAsync(bounce + at[(size_t)i], b.offsets + (size_t)i * L.caps.offsets, ((size_t)r.x + 1) * 4, cudaMemcpyDeviceToHost, c->s_ed));
+                if (r.y > 0)
+                    CU(cudaMemcpyAsync(bounce + at[(size_t)i] + ((size_t)r.x + 1) * 4, b.pixels + (size_t)i * L.caps.out_pixels, (size_t)r.y * 4,
+                                       cudaMemcpyDeviceToHost, c->s_ed));
+            }
+            CU(cudaStreamSynchronize(c->s_ed));
+            for (int i = first; i < last; ++i) {
+                const int4 r = c->edr_result_host[i];
+                if (!r.z) continue;
+                sdm_host::EdgeChains& e = res->chains[(size_t)(base + i)];
+                const int32_t* po = (const int32_t*)(bounce + at[(size_t)i]);
+                const uint32_t* pp = (const uint32_t*)(po + r.x + 1);
+                e.offsets.assign(po, po + r.x + 1);
+                e.pixels.assign(pp, pp + r.y);
+            }
+            first = last;
+        }
+        // edge-index planes of the images that asked for one
+        for (int i = 0; i < nb; ++i) {
+            const sdm_ed_image& im = images[base + i];
+            if (!im.edge_index || !c->edr_result_host[i].z) continue;
+            CU(cudaMemcpy2DAsync(im.edge_index, im.edge_step, b.edge_index + (size_t)i * P, (size_t)W * 4, (size_t)W * 4, (size_t)H,
+                                 cudaMemcpyDeviceToHost, c->s_ed));
+        }
+        CU(cudaStreamSynchronize(c->s_ed));
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, c->ed_ev[0], c->ed_ev[1]));
+        c->ed_kernel_ms += ms;
+        CU(cudaEventElapsedTime(&ms, c->edr_ev[0], c->edr_ev[1]));
+        c->ed_route_ms += ms;
+        // images that ran out of a capacity on the device: stage 1 again (the kernel has modified F), stage 2 on the host
+        for (int i = 0; i < nb; ++i) {
+            if (c->edr_result_host[i].z) continue;
+            ++c->edr_fallbacks;
+            RC(ed_launch(c, dv, i, 1, grad_thresh, anchor_thresh));
+            CU(cudaMemcpyAsync(hv.G + (size_t)i * P, dv.G + (size_t)i * P, P * 2, cudaMemcpyDeviceToHost, c->s_ed));
+            CU(cudaMemcpyAsync(hv.F + (size_t)i * P, dv.F + (size_t)i * P, P, cudaMemcpyDeviceToHost, c->s_ed));
+            CU(cudaStreamSynchronize(c->s_ed));
+            const sdm_ed_image& im = images[base + i];
+            sdm_host::EdRouteChains(W, H, hv.G + (size_t)i * P, hv.F + (size_t)i * P, grad_thresh, res->chains[(size_t)(base + i)],
+                                    im.edge_index, im.edge_step);
+        }
+    }
+    return SDM_OK;
+}
+
+}  // namespace
+
+int sdm_set_edge_drawing_route(sdm_ctx* c, int mode)
+{
+    if (!c) return fail(SDM_ERR_ARG, "null context");
+    if (mode != SDM_ED_ROUTE_HOST && mode != SDM_ED_ROUTE_DEVICE) return fail(SDM_ERR_ARG, "sdm_set_edge_drawing_route: unknown mode %d", mode);
+    c->ed_route_mode = mode;
+    return SDM_OK;
+}
+
+int sdm_last_edge_drawing_fallbacks(sdm_ctx* c) { return c ? c->edr_fallbacks : 0; }
+
 int sdm_edge_drawing(sdm_ctx* c, int n, const sdm_ed_image* images, int grad_thresh, int anchor_thresh, int n_threads,
                      sdm_ed_result** result)
 {
@@ -1751,6 +1930,14 @@ int sdm_edge_drawing(sdm_ctx* c, int n, const sdm_ed_image* images, int grad_thr
     c->ed_kernel_ms = c->ed_wall_ms = c->ed_route_ms = 0.f;
     if (n == 0) { *result = res; return SDM_OK; }
     const auto wall0 = std::chrono::steady_clock::now();
+    if (c->ed_route_mode == SDM_ED_ROUTE_DEVICE) {
+        if (!c->s_ed) CU(cudaStreamCreateWithFlags(&c->s_ed, cudaStreamNonBlocking));
+        const int drc = ed_run_device(c, n, images, grad_thresh, anchor_thresh, res);
+        c->ed_wall_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - wall0).count();
+        if (drc != SDM_OK) { delete res; return drc; }
+        *result = res;
+        return SDM_OK;
+    }
     const int W = c->cfg.width, H = c->cfg.height;
     const size_t P = c->npix;
     int rc = SDM_OK;

@@ -48,6 +48,12 @@ struct EdgeChains {
     int n_chains() const { return offsets.empty() ? 0 : (int)offsets.size() - 1; }
 };
 
+#if defined(__CUDACC__)
+#define SDM_EDR_HD __host__ __device__
+#else
+#define SDM_EDR_HD
+#endif
+
 namespace ed_detail {
 
 enum { kEdgeVertical = 1, kEdgeHorizontal = 2, kLeft = 1, kRight = 2, kUp = 3, kDown = 4 };
@@ -56,21 +62,59 @@ struct Px { int r, c; };
 struct Chain { int len, parent, dir, child[2], start; };
 struct Todo { int r, c, dir, parent; };
 
-inline bool adjacent(const Px& a, const Px& b) { return std::abs(a.r - b.r) <= 1 && std::abs(a.c - b.c) <= 1; }
+SDM_EDR_HD inline int iabs(int v) { return v < 0 ? -v : v; }
+SDM_EDR_HD inline bool adjacent(const Px& a, const Px& b) { return iabs(a.r - b.r) <= 1 && iabs(a.c - b.c) <= 1; }
+
+// The routing core (EdRouteCore below) is written once against this small vector interface: on the host it runs on
+// std::vector (HostVec), on the device - one image per warp, k_ed_route in csrc/edge_drawing_kernels.cuh - on fixed arrays in
+// global memory (FixedVec), where a push beyond the capacity is dropped and flagged; the core gives up on the image as soon as
+// a flag is up, and the library routes that image on the host instead.
+template <class T>
+struct HostVec {
+    std::vector<T> v;
+    int size() const { return (int)v.size(); }
+    bool empty() const { return v.empty(); }
+    void clear() { v.clear(); }
+    void push_back(const T& x) { v.push_back(x); }
+    void pop_back() { v.pop_back(); }
+    T& back() { return v.back(); }
+    T& operator[](int i) { return v[(size_t)i]; }
+    const T& operator[](int i) const { return v[(size_t)i]; }
+    void resize(int n) { v.resize((size_t)n); }
+    bool overflow() const { return false; }
+};
+template <class T>
+struct FixedVec {
+    T* p;
+    int n, cap;
+    bool ovf;
+    SDM_EDR_HD FixedVec(T* mem, int capacity) : p(mem), n(0), cap(capacity), ovf(false) {}
+    SDM_EDR_HD int size() const { return n; }
+    SDM_EDR_HD bool empty() const { return n == 0; }
+    SDM_EDR_HD void clear() { n = 0; }
+    SDM_EDR_HD void push_back(const T& x) { if (n < cap) p[n++] = x; else ovf = true; }
+    SDM_EDR_HD void pop_back() { if (n > 0) --n; }
+    SDM_EDR_HD T& back() { return p[n > 0 ? n - 1 : 0]; }
+    SDM_EDR_HD T& operator[](int i) { return p[i]; }
+    SDM_EDR_HD const T& operator[](int i) const { return p[i]; }
+    SDM_EDR_HD void resize(int m) { if (m <= cap) n = m; else { n = cap; ovf = true; } }
+    SDM_EDR_HD bool overflow() const { return ovf; }
+};
 
 // length of the longest path below `root`; every visited chain keeps only the child on that path (first child on ties).
 // Iterative post-order (the trees of a textured image are thousands of chains deep).
-inline int longest_chain(std::vector<Chain>& ch, int root, std::vector<int>& best, std::vector<int>& order)
+template <class ChainVec, class IntVec>
+SDM_EDR_HD inline int longest_chain(ChainVec& ch, int root, IntVec& best, IntVec& order)
 {
     if (root == -1 || ch[root].len == 0) return 0;
     order.clear();
     order.push_back(root);
-    for (size_t i = 0; i < order.size(); ++i) {  // pre-order list of the chains a recursive descent would visit
+    for (int i = 0; i < order.size(); ++i) {  // pre-order list of the chains a recursive descent would visit
         const Chain& c = ch[order[i]];
         for (int k = 0; k < 2; ++k)
             if (c.child[k] != -1 && ch[c.child[k]].len != 0) order.push_back(c.child[k]);
     }
-    for (size_t i = order.size(); i-- > 0;) {
+    for (int i = order.size(); i-- > 0;) {
         Chain& c = ch[order[i]];
         const int l0 = (c.child[0] != -1 && ch[c.child[0]].len != 0) ? best[c.child[0]] : 0;
         const int l1 = (c.child[1] != -1 && ch[c.child[1]].len != 0) ? best[c.child[1]] : 0;
@@ -81,7 +125,8 @@ inline int longest_chain(std::vector<Chain>& ch, int root, std::vector<int>& bes
     return best[root];
 }
 
-inline void retrieve_chain_nos(const std::vector<Chain>& ch, int root, std::vector<int>& nos)
+template <class ChainVec, class IntVec>
+SDM_EDR_HD inline void retrieve_chain_nos(const ChainVec& ch, int root, IntVec& nos)
 {
     nos.clear();
     while (root != -1) {
@@ -168,20 +213,21 @@ inline void EdPlanesHost(const uint8_t* im, size_t step, int W, int H, int grad_
 }
 
 // Stage 2: anchors in decreasing gradient order, smart routing, segment extraction.  F is modified in place (flags of the
-// walked pixels).  If edge_index is given (int32 plane, row pitch edge_step bytes) it receives what DetectEdgeMap leaves in
-// kf->mEdgeIndex: -1 everywhere (KeyFrame.cc:87), then the chain number of every chain pixel in chain order (:857-866).
-inline void EdRouteChains(int W, int H, const int16_t* G, uint8_t* F, int grad_thresh, EdgeChains& out,
-                          int32_t* edge_index = nullptr, size_t edge_step = 0)
+// walked pixels).  If edge_index is given (int32 plane, row pitch edge_step bytes, ALREADY FILLED WITH -1 by the caller:
+// KeyFrame.cc:87) every chain pixel receives its chain number in chain order (LineDetector.cc:857-866).
+// Storage (see HostVec / FixedVec): found / anchors: anchor positions; chains, pixels, stack, seg: the tree being walked;
+// best / order / nos: work lists of the segment extraction; out_offsets / out_pixels: the result, offsets[0] = 0 pushed here.
+// Returns false if a FixedVec ran out of capacity (the outputs are then incomplete and must be discarded).
+template <class IntVec, class ChainVec, class PxVec, class TodoVec, class OffVec, class PixVec>
+SDM_EDR_HD inline bool EdRouteCore(int W, int H, const int16_t* G, uint8_t* F, int grad_thresh, IntVec& found, IntVec& anchors,
+                                   ChainVec& chains, PxVec& pixels, PxVec& seg, TodoVec& stack, IntVec& best, IntVec& order, IntVec& nos,
+                                   OffVec& out_offsets, PixVec& out_pixels, int32_t* edge_index, size_t edge_step, int* hist /* [2049] */)
 {
     using namespace ed_detail;
-    out.offsets.assign(1, 0);
-    out.pixels.clear();
-    if (edge_index)
-        for (int y = 0; y < H; ++y) {
-            int32_t* row = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(edge_index) + (size_t)y * edge_step);
-            for (int x = 0; x < W; ++x) row[x] = -1;
-        }
-    if (W < 5 || H < 5) return;
+    out_offsets.clear();
+    out_offsets.push_back(0);
+    out_pixels.clear();
+    if (W < 5 || H < 5) return true;
     const size_t P = (size_t)W * H;
 #define GR(y, x) ((int)G[(size_t)(y) * W + (x)])
 #define FL(y, x) F[(size_t)(y) * W + (x)]
@@ -189,61 +235,68 @@ inline void EdRouteChains(int W, int H, const int16_t* G, uint8_t* F, int grad_t
 #define MARKED(y, x) ((FL(y, x) & (kEdFlagAnchor | kEdFlagEdge)) != 0)
 #define IS_ANCHOR(y, x) ((FL(y, x) & kEdFlagAnchor) != 0)
 #define IS_EDGE(y, x) ((FL(y, x) & kEdFlagEdge) != 0)
+#define SDM_EDR_OVERFLOW() (found.overflow() || anchors.overflow() || chains.overflow() || pixels.overflow() || seg.overflow() || \
+                            stack.overflow() || best.overflow() || order.overflow() || nos.overflow() || out_offsets.overflow() ||  \
+                            out_pixels.overflow())
     // ---- anchor order: decreasing gradient, raster order among equals (counting sort: |gx| + |gy| <= 2040)
-    static thread_local std::vector<int> found, anchors;
     found.clear();
-    int hist[2048 + 1] = {0};
+    for (int i = 0; i <= 2048; ++i) hist[i] = 0;
     {
         size_t i = 0;
+        while (i < P && ((size_t)(F + i) & 7) != 0) {
+            if (F[i] & kEdFlagAnchor) { found.push_back((int)i); ++hist[2047 - (G[i] < 2047 ? (int)G[i] : 2047)]; }
+            ++i;
+        }
         for (; i + 8 <= P; i += 8) {  // eight flag bytes at a time
-            uint64_t w;
-            std::memcpy(&w, F + i, 8);
+            const uint64_t w = *reinterpret_cast<const uint64_t*>(F + i);
             if ((w & 0x8080808080808080ull) == 0) continue;
             for (int k = 0; k < 8; ++k)
-                if (F[i + k] & kEdFlagAnchor) { found.push_back((int)(i + k)); ++hist[2047 - std::min((int)G[i + k], 2047)]; }
+                if (F[i + k] & kEdFlagAnchor) { found.push_back((int)(i + k)); ++hist[2047 - (G[i + k] < 2047 ? (int)G[i + k] : 2047)]; }
         }
         for (; i < P; ++i)
-            if (F[i] & kEdFlagAnchor) { found.push_back((int)i); ++hist[2047 - std::min((int)G[i], 2047)]; }
+            if (F[i] & kEdFlagAnchor) { found.push_back((int)i); ++hist[2047 - (G[i] < 2047 ? (int)G[i] : 2047)]; }
     }
+    if (found.overflow()) return false;
     {
         int run = 0;
         for (int i = 0; i <= 2047; ++i) { const int c = hist[i]; hist[i] = run; run += c; }
         anchors.resize(found.size());
-        for (size_t i = 0; i < found.size(); ++i) anchors[hist[2047 - std::min((int)G[found[i]], 2047)]++] = found[i];
+        if (anchors.overflow()) return false;
+        for (int i = 0; i < found.size(); ++i) { const int g = G[found[i]]; anchors[hist[2047 - (g < 2047 ? g : 2047)]++] = found[i]; }
     }
 
-    std::vector<Chain> chains;
-    std::vector<Px> pixels, seg;
-    std::vector<Todo> stack;
-    std::vector<int> best, order, nos;
     bool have_prev = false;
     Px prev_last = {0, 0};  // last pixel of the previously emitted segment (see the header comment)
 
-    auto emit = [&](const std::vector<Px>& s) {
-        const int32_t id = (int32_t)out.offsets.size() - 1;
-        for (size_t i = 0; i < s.size(); ++i) {
-            out.pixels.push_back(((uint32_t)s[i].r << 16) | (uint32_t)s[i].c);
-            if (edge_index) reinterpret_cast<int32_t*>(reinterpret_cast<char*>(edge_index) + (size_t)s[i].r * edge_step)[s[i].c] = id;
-        }
-        out.offsets.push_back((int32_t)out.pixels.size());
-        if (!s.empty()) { prev_last = s.back(); have_prev = true; }
-    };
-    // appends chain `cno` to `seg` in walking order, dropping the pixels that double back at the joint
-    auto append_forward = [&](int cno) {
-        Chain& c = chains[cno];
-        const Px first = pixels[c.start];
-        int idx = (int)seg.size() - 2;
-        while (idx >= 0 && adjacent(first, seg[idx])) { seg.pop_back(); --idx; }
-        int start = 0;
-        if (c.len > 1 && (!seg.empty() || have_prev)) {
-            const Px last = seg.empty() ? prev_last : seg.back();
-            if (adjacent(pixels[c.start + 1], last)) start = 1;
-        }
-        for (int l = start; l < c.len; ++l) seg.push_back(pixels[c.start + l]);
-        c.len = 0;  // copied
-    };
+    // emits `seg` as the next chain
+#define SDM_EDR_EMIT()                                                                                                       \
+    do {                                                                                                                     \
+        const int32_t id = (int32_t)out_offsets.size() - 1;                                                                  \
+        for (int i_ = 0; i_ < seg.size(); ++i_) {                                                                            \
+            out_pixels.push_back(((uint32_t)seg[i_].r << 16) | (uint32_t)seg[i_].c);                                         \
+            if (edge_index)                                                                                                  \
+                reinterpret_cast<int32_t*>(reinterpret_cast<char*>(edge_index) + (size_t)seg[i_].r * edge_step)[seg[i_].c] = id; \
+        }                                                                                                                    \
+        out_offsets.push_back((int32_t)out_pixels.size());                                                                   \
+        if (!seg.empty()) { prev_last = seg.back(); have_prev = true; }                                                      \
+    } while (0)
+    // appends chain `cno_` to `seg` in walking order, dropping the pixels that double back at the joint
+#define SDM_EDR_APPEND_FORWARD(cno_)                                                                                         \
+    do {                                                                                                                     \
+        Chain& c_ = chains[cno_];                                                                                            \
+        const Px first_ = pixels[c_.start];                                                                                  \
+        int idx_ = seg.size() - 2;                                                                                           \
+        while (idx_ >= 0 && adjacent(first_, seg[idx_])) { seg.pop_back(); --idx_; }                                         \
+        int start_ = 0;                                                                                                      \
+        if (c_.len > 1 && (!seg.empty() || have_prev)) {                                                                     \
+            const Px last_ = seg.empty() ? prev_last : seg.back();                                                           \
+            if (adjacent(pixels[c_.start + 1], last_)) start_ = 1;                                                           \
+        }                                                                                                                    \
+        for (int l_ = start_; l_ < c_.len; ++l_) seg.push_back(pixels[c_.start + l_]);                                       \
+        c_.len = 0; /* copied */                                                                                             \
+    } while (0)
 
-    for (size_t a = 0; a < anchors.size(); ++a) {
+    for (int a = 0; a < anchors.size(); ++a) {
         const int ay = anchors[a] / W, ax = anchors[a] % W;
         if (!IS_ANCHOR(ay, ax)) continue;
         chains.clear();
@@ -253,11 +306,13 @@ inline void EdRouteChains(int W, int H, const int16_t* G, uint8_t* F, int grad_t
         chains.push_back(root);
         int dup = 0;
         if (DI(ay, ax) == kEdgeVertical) {
-            stack.push_back(Todo{ay, ax, kDown, 0});
-            stack.push_back(Todo{ay, ax, kUp, 0});
+            Todo t0 = {ay, ax, kDown, 0}, t1 = {ay, ax, kUp, 0};
+            stack.push_back(t0);
+            stack.push_back(t1);
         } else {
-            stack.push_back(Todo{ay, ax, kRight, 0});
-            stack.push_back(Todo{ay, ax, kLeft, 0});
+            Todo t0 = {ay, ax, kRight, 0}, t1 = {ay, ax, kLeft, 0};
+            stack.push_back(t0);
+            stack.push_back(t1);
         }
         while (!stack.empty()) {
             const Todo t = stack.back();
@@ -265,10 +320,12 @@ inline void EdRouteChains(int W, int H, const int16_t* G, uint8_t* F, int grad_t
             int r = t.r, c = t.c;
             const int dir = t.dir;
             if (!IS_EDGE(r, c)) ++dup;
-            Chain ch = {0, t.parent, dir, {-1, -1}, (int)pixels.size()};
-            const int no = (int)chains.size();
+            Chain ch = {0, t.parent, dir, {-1, -1}, pixels.size()};
+            const int no = chains.size();
             chains.push_back(ch);
-            pixels.push_back(Px{r, c});
+            Px p0 = {r, c};
+            pixels.push_back(p0);
+            if (chains.overflow() || pixels.overflow() || stack.overflow()) return false;
             int clen = 1;
             const bool horizontal = dir == kLeft || dir == kRight;
             const int child = (dir == kLeft || dir == kUp) ? 0 : 1;
@@ -307,36 +364,41 @@ inline void EdRouteChains(int W, int H, const int16_t* G, uint8_t* F, int grad_t
                     ended = true;
                     break;
                 }
-                pixels.push_back(Px{r, c});
+                Px pn = {r, c};
+                pixels.push_back(pn);
+                if (pixels.overflow()) return false;
                 ++clen;
             }
             if (ended) continue;
             // the edge turns: the last pixel opens the two walks across the old direction and belongs to them
             if (horizontal) {
-                stack.push_back(Todo{r, c, kDown, no});
-                stack.push_back(Todo{r, c, kUp, no});
+                Todo t0 = {r, c, kDown, no}, t1 = {r, c, kUp, no};
+                stack.push_back(t0);
+                stack.push_back(t1);
             } else {
-                stack.push_back(Todo{r, c, kRight, no});
-                stack.push_back(Todo{r, c, kLeft, no});
+                Todo t0 = {r, c, kRight, no}, t1 = {r, c, kLeft, no};
+                stack.push_back(t0);
+                stack.push_back(t1);
             }
             pixels.pop_back();
             --clen;
             chains[no].len = clen;
             chains[t.parent].child[child] = no;
         }
-        if ((int)pixels.size() - dup < 10) {  // too short: take the walk back
-            for (size_t i = 0; i < pixels.size(); ++i) FL(pixels[i].r, pixels[i].c) &= kEdDirMask;
+        if (pixels.size() - dup < 10) {  // too short: take the walk back
+            for (int i = 0; i < pixels.size(); ++i) FL(pixels[i].r, pixels[i].c) &= kEdDirMask;
             continue;
         }
         best.resize(chains.size());  // (every entry is written before it is read inside one longest_chain call)
+        if (best.overflow()) return false;
         // ---- main segment: longest path of the second direction backwards, the anchor, longest path of the first direction
         seg.clear();
         if (longest_chain(chains, chains[0].child[1], best, order) > 0) {
             retrieve_chain_nos(chains, chains[0].child[1], nos);
-            for (size_t k = nos.size(); k-- > 0;) {
+            for (int k = nos.size(); k-- > 0;) {
                 Chain& c = chains[nos[k]];
                 const Px lastp = pixels[c.start + c.len - 1];
-                int idx = (int)seg.size() - 2;
+                int idx = seg.size() - 2;
                 while (idx >= 0 && adjacent(lastp, seg[idx])) { seg.pop_back(); --idx; }
                 if (c.len > 1 && (!seg.empty() || have_prev) &&
                     adjacent(pixels[c.start + c.len - 2], seg.empty() ? prev_last : seg.back()))
@@ -349,27 +411,111 @@ inline void EdRouteChains(int W, int H, const int16_t* G, uint8_t* F, int grad_t
             retrieve_chain_nos(chains, chains[0].child[0], nos);
             ++chains[nos[0]].start;  // the anchor is already there
             --chains[nos[0]].len;
-            for (size_t k = 0; k < nos.size(); ++k) append_forward(nos[k]);
+            for (int k = 0; k < nos.size(); ++k) SDM_EDR_APPEND_FORWARD(nos[k]);
         }
-        if (seg.size() > 1 && adjacent(seg[1], seg.back())) seg.erase(seg.begin());
-        emit(seg);
+        if (seg.size() > 1 && adjacent(seg[1], seg.back())) {  // drop the first pixel
+            for (int i = 1; i < seg.size(); ++i) seg[i - 1] = seg[i];
+            seg.pop_back();
+        }
+        SDM_EDR_EMIT();
         // ---- the other long chains of the tree
-        for (int k = 2; k < (int)chains.size(); ++k) {
+        for (int k = 2; k < chains.size(); ++k) {
             if (chains[k].len < 2) continue;
             if (longest_chain(chains, k, best, order) >= 10) {
                 retrieve_chain_nos(chains, k, nos);
                 seg.clear();
-                for (size_t q = 0; q < nos.size(); ++q) append_forward(nos[q]);
-                emit(seg);
+                for (int q = 0; q < nos.size(); ++q) SDM_EDR_APPEND_FORWARD(nos[q]);
+                SDM_EDR_EMIT();
             }
         }
+        if (SDM_EDR_OVERFLOW()) return false;
     }
+    return !SDM_EDR_OVERFLOW();
+#undef SDM_EDR_EMIT
+#undef SDM_EDR_APPEND_FORWARD
+#undef SDM_EDR_OVERFLOW
 #undef GR
 #undef FL
 #undef DI
 #undef MARKED
 #undef IS_ANCHOR
 #undef IS_EDGE
+}
+
+// The core on std::vector: what the routing threads of sdm_edge_drawing and the host-only detector call.  Fills edge_index
+// with -1 first (KeyFrame.cc:87).
+inline void EdRouteChains(int W, int H, const int16_t* G, uint8_t* F, int grad_thresh, EdgeChains& out,
+                          int32_t* edge_index = nullptr, size_t edge_step = 0)
+{
+    using namespace ed_detail;
+    if (edge_index)
+        for (int y = 0; y < H; ++y) {
+            int32_t* row = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(edge_index) + (size_t)y * edge_step);
+            for (int x = 0; x < W; ++x) row[x] = -1;
+        }
+    static thread_local HostVec<int> found, anchors, best, order, nos;  // (work lists are kept between calls)
+    static thread_local HostVec<Chain> chains;
+    static thread_local HostVec<Px> pixels, seg;
+    static thread_local HostVec<Todo> stack;
+    HostVec<int32_t> offsets;
+    HostVec<uint32_t> px;
+    int hist[2048 + 1];
+    offsets.v.swap(out.offsets);
+    px.v.swap(out.pixels);
+    EdRouteCore(W, H, G, F, grad_thresh, found, anchors, chains, pixels, seg, stack, best, order, nos, offsets, px, edge_index, edge_step, hist);
+    offsets.v.swap(out.offsets);
+    px.v.swap(out.pixels);
+}
+
+// The core on fixed arrays: what one warp of k_ed_route runs per image (lane 0), and what tests/cpp/test_edge_drawing.cpp
+// replays on the CPU against the std::vector form.  Capacities are generous for real images (a VGA keyframe of the bench
+// scene needs 12 k anchors, ~30 chains and ~300 pixels per tree, 31 k chain pixels); an image that exceeds one returns false.
+struct EdRouteCaps {
+    int anchors, chains, pixels, offsets, out_pixels;
+};
+SDM_EDR_HD inline EdRouteCaps EdRouteCapsFor(size_t P)
+{
+    EdRouteCaps c;
+    c.anchors = (int)(P / 2) + 16;     // an anchor exceeds both neighbours across its edge: no two are adjacent in that direction
+    c.chains = (int)(P / 8) + 16;      // chains / open walks of ONE tree
+    c.pixels = (int)(P / 2) + 16;      // walked pixels of ONE tree
+    c.offsets = (int)(P / 8) + 16;     // chains of the image + 1
+    c.out_pixels = (int)(P / 2) + 16;  // chain pixels of the image
+    return c;
+}
+SDM_EDR_HD inline size_t EdRouteAlign(size_t v) { return (v + 15) & ~(size_t)15; }
+SDM_EDR_HD inline size_t EdRouteScratchBytes(const EdRouteCaps& c)
+{
+    using namespace ed_detail;
+    return 2 * EdRouteAlign((size_t)c.anchors * sizeof(int)) + EdRouteAlign((size_t)c.chains * sizeof(Chain)) +
+           2 * EdRouteAlign((size_t)c.pixels * sizeof(Px)) + EdRouteAlign((size_t)c.chains * sizeof(Todo)) +
+           3 * EdRouteAlign((size_t)c.chains * sizeof(int)) + EdRouteAlign(2049 * sizeof(int));
+}
+// scratch: EdRouteScratchBytes(caps) bytes, 16-byte aligned; out_offsets[caps.offsets], out_pixels[caps.out_pixels];
+// edge_index (may be NULL) already filled with -1.  *n_chains / *n_pixels are valid when true is returned.
+SDM_EDR_HD inline bool EdRouteFixed(int W, int H, const int16_t* G, uint8_t* F, int grad_thresh, uint8_t* scratch, const EdRouteCaps& caps,
+                                    int32_t* out_offsets, uint32_t* out_pixels, int32_t* edge_index, size_t edge_step, int* n_chains,
+                                    int* n_pixels)
+{
+    using namespace ed_detail;
+    uint8_t* p = scratch;
+    FixedVec<int> found(reinterpret_cast<int*>(p), caps.anchors);      p += EdRouteAlign((size_t)caps.anchors * sizeof(int));
+    FixedVec<int> anchors(reinterpret_cast<int*>(p), caps.anchors);    p += EdRouteAlign((size_t)caps.anchors * sizeof(int));
+    FixedVec<Chain> chains(reinterpret_cast<Chain*>(p), caps.chains);  p += EdRouteAlign((size_t)caps.chains * sizeof(Chain));
+    FixedVec<Px> pixels(reinterpret_cast<Px*>(p), caps.pixels);        p += EdRouteAlign((size_t)caps.pixels * sizeof(Px));
+    FixedVec<Px> seg(reinterpret_cast<Px*>(p), caps.pixels);           p += EdRouteAlign((size_t)caps.pixels * sizeof(Px));
+    FixedVec<Todo> stack(reinterpret_cast<Todo*>(p), caps.chains);     p += EdRouteAlign((size_t)caps.chains * sizeof(Todo));
+    FixedVec<int> best(reinterpret_cast<int*>(p), caps.chains);        p += EdRouteAlign((size_t)caps.chains * sizeof(int));
+    FixedVec<int> order(reinterpret_cast<int*>(p), caps.chains);       p += EdRouteAlign((size_t)caps.chains * sizeof(int));
+    FixedVec<int> nos(reinterpret_cast<int*>(p), caps.chains);         p += EdRouteAlign((size_t)caps.chains * sizeof(int));
+    int* hist = reinterpret_cast<int*>(p);
+    FixedVec<int32_t> offs(out_offsets, caps.offsets);
+    FixedVec<uint32_t> px(out_pixels, caps.out_pixels);
+    const bool ok = EdRouteCore(W, H, G, F, grad_thresh, found, anchors, chains, pixels, seg, stack, best, order, nos, offs, px,
+                                edge_index, edge_step, hist);
+    *n_chains = offs.size() - 1;
+    *n_pixels = px.size();
+    return ok;
 }
 
 // Both stages on the host: what the reference's call does per keyframe (image row pitch `step` bytes).  Images up to

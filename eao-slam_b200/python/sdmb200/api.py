@@ -99,6 +99,7 @@ EXPORTS = [
     "sdm_inter_check", "sdm_last_pass_ms", "sdm_launch_count", "sdm_last_timing", "sdm_last_pack_ms", "sdm_mark", "sdm_elapsed_ms",
     "sdm_line_fit", "sdm_last_line_fit_ms", "sdm_last_scan_long",
     "sdm_edge_drawing", "sdm_ed_chains", "sdm_ed_free", "sdm_last_edge_drawing_ms", "sdm_ed_planes",
+    "sdm_set_edge_drawing_route", "sdm_last_edge_drawing_fallbacks",
 ]
 
 _lib = None
@@ -129,6 +130,8 @@ def load() -> C.CDLL:
     lib.sdm_ed_free.argtypes = [vp]
     lib.sdm_ed_free.restype = None
     lib.sdm_last_edge_drawing_ms.argtypes = [vp, fp, fp, fp]
+    lib.sdm_set_edge_drawing_route.argtypes = [vp, C.c_int]
+    lib.sdm_last_edge_drawing_fallbacks.argtypes = [vp]
     lib.sdm_ed_planes.argtypes = [vp, vp, sz, C.c_int, C.c_int, vp, vp]
     lib.sdm_host_alloc.argtypes = [C.POINTER(vp), sz]
     lib.sdm_host_free.argtypes = [vp]
@@ -409,7 +412,7 @@ class Context:
                                         C.byref(total)))
         return out[:int(total.value)], counts[:n]
 
-    def edge_drawing(self, images, grad_thresh=36, anchor_thresh=8, n_threads=0, edge_index=True):
+    def edge_drawing(self, images, grad_thresh=36, anchor_thresh=8, n_threads=0, edge_index=True, edge_out=None):
         """LineDetector::DetectEdgeMap for a batch of 8-bit images [n, H, W] (or a list of [H, W], rows may be pitched).
         Returns (offsets list, pixels list, edge_index [n, H, W] int32 or None): chains of image i = pixels[i][offsets[i][k] :
         offsets[i][k + 1]], packed (row << 16) | col - the layout line_fit takes; edge_index = kf->mEdgeIndex."""
@@ -418,6 +421,9 @@ class Context:
         for a in ims:
             assert a.dtype == np.uint8 and a.shape == (self.H, self.W) and a.strides[1] == 1
         edge = np.empty((n, self.H, self.W), np.int32) if edge_index else None
+        if edge_out is not None:  # caller's planes (e.g. pinned memory)
+            assert edge_out.dtype == np.int32 and edge_out.shape == (n, self.H, self.W) and edge_out.strides[2] == 4
+            edge = edge_out
         descs = (EdImage * max(n, 1))()
         for i, a in enumerate(ims):
             descs[i].im, descs[i].im_step = a.ctypes.data, a.strides[0]
@@ -436,6 +442,13 @@ class Context:
         finally:
             self.lib.sdm_ed_free(res)
         return offs, pix, edge
+
+    def set_edge_drawing_route(self, device: bool):
+        """stage 2 of edge_drawing on host threads (False, default) or on the device, one warp per image (True)"""
+        self._chk(self.lib.sdm_set_edge_drawing_route(self.h, 1 if device else 0))
+
+    def last_edge_drawing_fallbacks(self) -> int:
+        return int(self.lib.sdm_last_edge_drawing_fallbacks(self.h))
 
     def last_edge_drawing_ms(self) -> dict:
         k, w, r = C.c_float(), C.c_float(), C.c_float()

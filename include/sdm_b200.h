@@ -274,8 +274,18 @@ int sdm_edge_drawing(sdm_ctx* ctx, int n, const sdm_ed_image* images, int grad_t
                      sdm_ed_result** result);
 int sdm_ed_chains(const sdm_ed_result* result, int i, int32_t* n_chains, const int32_t** offsets, const uint32_t** pixels);
 void sdm_ed_free(sdm_ed_result* result);
+/* where stage 2 (the routing walk) of sdm_edge_drawing runs.  SDM_ED_ROUTE_HOST (default): host threads, overlapped with
+ * stage 1 of the following chunks - the fast choice for a few hundred keyframes on one GPU (0.12 ms per VGA keyframe on 16
+ * cores).  SDM_ED_ROUTE_DEVICE: k_ed_route, one warp per keyframe, up to 1024 keyframes per launch - the walk is sequential
+ * per image and a device thread walks ~30 x slower than a host core, but thousands of images walk at once and the host
+ * cores stay free (one process per GPU shares them); chains and edge index are identical in both modes.  An image whose
+ * walk exceeds the kernel's fixed capacities is routed on the host (sdm_last_edge_drawing_fallbacks counts them). */
+enum { SDM_ED_ROUTE_HOST = 0, SDM_ED_ROUTE_DEVICE = 1 };
+int sdm_set_edge_drawing_route(sdm_ctx* ctx, int mode);
+int sdm_last_edge_drawing_fallbacks(sdm_ctx* ctx);
 /* timing of the last sdm_edge_drawing: device time of its k_ed_planes launches, host wall time of the call, and the
- * summed thread time of the routing walks (all ms; any pointer may be NULL) */
+ * summed thread time of the routing walks - in SDM_ED_ROUTE_DEVICE mode the device time of k_ed_route (all ms; any
+ * pointer may be NULL) */
 int sdm_last_edge_drawing_ms(sdm_ctx* ctx, float* kernel_ms, float* wall_ms, float* route_thread_ms);
 /* the stage-1 planes of one image as the device computes them (G int16, F uint8, dense width x height; see
  * csrc/edge_drawing_kernels.cuh) - for tests and tools */

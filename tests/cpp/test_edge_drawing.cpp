@@ -5,6 +5,8 @@
 //   planes.bin: per image the stage-1 planes of EdPlanesHost, G (int16 W*H) then F (uint8 W*H); for widths that are multiples
 //   of four (and >= 8 x 8, the library's minimum) the device kernel k_ed_planes4 is replayed thread by thread on the CPU
 //   (sdm::EdPlanes4Replay, csrc/edge_drawing_kernels.cuh) and must give the same planes: exit code 4 otherwise
+//   every image is also routed by the fixed-capacity form of the routing core (sdm_host::EdRouteFixed: what one warp of
+//   k_ed_route runs on the device) and must give the same chains and the same edge index: exit code 5 otherwise
 //   prints the host time of the detector per image (both stages, one thread) on stderr
 //   out.bin (int32): N, then per image: noSegments, per segment: noPixels, (r, c) * noPixels
 #include <stdio.h>
@@ -48,6 +50,22 @@ int main(int argc, char** argv)
             }
         }
         if (fe) fwrite(edge.data(), 4, edge.size(), fe);
+        if (W >= 5 && H >= 5) {
+            sdm_host::EdPlanesHost(im.data(), (size_t)W, W, H, 36, 8, G.data(), F.data());
+            const sdm_host::EdRouteCaps caps = sdm_host::EdRouteCapsFor((size_t)W * H);
+            std::vector<uint8_t> scratch(sdm_host::EdRouteScratchBytes(caps) + 16);
+            uint8_t* sp = scratch.data() + ((16 - ((size_t)scratch.data() & 15)) & 15);
+            std::vector<int32_t> fo_(caps.offsets), edge2((size_t)W * H, -1);
+            std::vector<uint32_t> fp_(caps.out_pixels);
+            int nc = -1, np = -1;
+            const bool ok = sdm_host::EdRouteFixed(W, H, G.data(), F.data(), 36, sp, caps, fo_.data(), fp_.data(), edge2.data(), (size_t)W * 4, &nc, &np);
+            if (!ok || nc != ch.n_chains() || np != (int)ch.pixels.size() || !std::equal(ch.offsets.begin(), ch.offsets.end(), fo_.begin()) ||
+                !std::equal(ch.pixels.begin(), ch.pixels.end(), fp_.begin()) || edge2 != edge) {
+                fprintf(stderr, "fixed-capacity routing differs at image %d (ok %d, chains %d / %d, pixels %d / %d)\n", i, (int)ok, nc,
+                        ch.n_chains(), np, (int)ch.pixels.size());
+                return 5;
+            }
+        }
         if (fp && W >= 5 && H >= 5) {
             sdm_host::EdPlanesHost(im.data(), (size_t)W, W, H, 36, 8, G.data(), F.data());
             fwrite(G.data(), 2, G.size(), fp);

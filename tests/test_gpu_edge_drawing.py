@@ -74,14 +74,19 @@ def test_stage1_planes_match_the_host_form(scene, ed_bin, tmp_path):
         assert np.array_equal(g, G[0]) and np.array_equal(f, F[0]), name
 
 
-@pytest.mark.parametrize("threads", [1, 4])
+@pytest.mark.parametrize("threads", [1, 4, "device"])
 def test_chains_and_mask_match_the_library_on_the_scene(scene, threads):
+    """threads = "device": stage 2 in k_ed_route (one warp per image) instead of host threads"""
     sc, g = scene
     n, H, W = sc.im.shape
     with ctx_for(W, H) as ctx:
+        if threads == "device":
+            ctx.set_edge_drawing_route(True)
+            threads = 0
         offs, pix, edge = ctx.edge_drawing(sc.im, n_threads=threads)
         t = ctx.last_edge_drawing_ms()
-    assert t["kernel_ms"] > 0 and t["wall_ms"] > 0
+        assert ctx.last_edge_drawing_fallbacks() == 0
+    assert t["kernel_ms"] > 0 and t["wall_ms"] > 0 and t["route_thread_ms"] > 0
     for i in range(n):
         assert same((offs[i], pix[i]), (g[f"off_{i}"], g[f"pix_{i}"])), i
         want = np.full((H, W), -1, np.int32)   # LineDetector.cc:857-866 on KeyFrame.cc:87's plane of -1
@@ -90,7 +95,8 @@ def test_chains_and_mask_match_the_library_on_the_scene(scene, threads):
         assert np.array_equal(edge[i], want)
 
 
-def test_chains_match_the_library_on_the_odd_images():
+@pytest.mark.parametrize("device_route", [False, True])
+def test_chains_match_the_library_on_the_odd_images(device_route):
     m = np.load(os.path.join(GOLD, "ed_chains_misc.npz"))
     done = 0
     for name in m["names"]:
@@ -99,14 +105,21 @@ def test_chains_match_the_library_on_the_odd_images():
         if W < 8 or H < 8:   # below the smallest context (sdm_create)
             continue
         with ctx_for(W, H) as ctx:
-            offs, pix, _ = ctx.edge_drawing(im[None], edge_index=False)
+            ctx.set_edge_drawing_route(device_route)
+            offs, pix, edge = ctx.edge_drawing(im[None], edge_index=device_route)
         assert same((offs[0], pix[0]), (m["off_" + name], m["pix_" + name])), name
+        if device_route:
+            want = np.full((H, W), -1, np.int32)
+            want[pix[0] >> 16, pix[0] & 0xffff] = np.repeat(np.arange(len(offs[0]) - 1, dtype=np.int32), np.diff(offs[0]))
+            assert np.array_equal(edge[0], want), name
         done += 1
     assert done >= 12
 
 
-def test_large_pitched_batch_matches_the_host_form(scene, ed_bin, tmp_path):
-    """more keyframes than one device chunk, rows with a pitch, more threads than chunks"""
+@pytest.mark.parametrize("device_route", [False, True])
+def test_large_pitched_batch_matches_the_host_form(scene, ed_bin, tmp_path, device_route):
+    """more keyframes than one device chunk, rows with a pitch, more threads than chunks; pitched edge-index planes of
+    every second image in the device mode"""
     sc, _ = scene
     n, H, W = sc.im.shape
     ims = np.concatenate([sc.im, sc.im[:, ::-1], sc.im[:, :, ::-1], 255 - sc.im, sc.im[:, ::-1, ::-1]])[:27]
@@ -114,11 +127,32 @@ def test_large_pitched_batch_matches_the_host_form(scene, ed_bin, tmp_path):
     pitched = np.zeros((len(ims), H, W + 24), np.uint8)
     pitched[:, :, :W] = ims
     with ctx_for(W, H) as ctx:
+        ctx.set_edge_drawing_route(device_route)
         offs, pix, _ = ctx.edge_drawing([pitched[i, :, :W] for i in range(len(ims))], n_threads=16, edge_index=False)
+        assert ctx.last_edge_drawing_fallbacks() == 0
         empty = ctx.edge_drawing(np.zeros((0, H, W), np.uint8))
     assert empty[0] == [] and empty[1] == []
     for i in range(len(ims)):
         assert same((offs[i], pix[i]), want[i]), i
+
+
+def test_device_route_falls_back_to_the_host_when_a_capacity_runs_out(scene, monkeypatch):
+    """SDM_ED_ROUTE_TEST_CAPS shrinks k_ed_route's per-tree arrays (120 walked pixels, 30 chains): most keyframes run out of
+    room on the device, are routed on the host instead, and still give the library's chains and mask; the rest stay on the
+    device path"""
+    sc, g = scene
+    n, H, W = sc.im.shape
+    monkeypatch.setenv("SDM_ED_ROUTE_TEST_CAPS", "120")
+    with ctx_for(W, H) as ctx:
+        ctx.set_edge_drawing_route(True)
+        offs, pix, edge = ctx.edge_drawing(sc.im)
+        fb = ctx.last_edge_drawing_fallbacks()
+    assert 0 < fb <= n
+    for i in range(n):
+        assert same((offs[i], pix[i]), (g[f"off_{i}"], g[f"pix_{i}"])), i
+        w = np.full((H, W), -1, np.int32)
+        w[pix[i] >> 16, pix[i] & 0xffff] = np.repeat(np.arange(len(offs[i]) - 1, dtype=np.int32), np.diff(offs[i]))
+        assert np.array_equal(edge[i], w), i
 
 
 def test_argument_errors():

@@ -22,6 +22,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n", type=int, default=200)
     ap.add_argument("--out", default=None)
+    ap.add_argument("--n-device", type=int, nargs="*", default=[200, 1000], help="batch sizes of the device-routing runs")
     a = ap.parse_args()
     W, H = 640, 480
     sc = synth.make_scene(32, W, H, 6, seed=2, workers=16)
@@ -47,6 +48,28 @@ def main():
                                     kernel_gbps=4.0 * W * H / (k_us * 1e-6) / 1e9, kernel_roofline_frac=4.0 * W * H / (k_us * 1e-6) / 1e9 / hbm,
                                     route_thread_ms_per_kf=best["route_thread_ms"] / a.n))
         res["chains"] = n_chains
+    # stage 2 on the device (k_ed_route, one warp per keyframe): wall time per keyframe against the batch size; the edge-index
+    # planes land in pinned memory (the host-thread runs above write them from the routing threads)
+    res["device_route"] = []
+    for nd in a.n_device:
+        imd = np.ascontiguousarray(np.concatenate([ims] * ((nd + len(ims) - 1) // len(ims)))[:nd])
+        with api.Context(width=W, height=H, max_keyframes=2) as ctx:
+            ctx.set_edge_drawing_route(True)
+            ptr = api.C.c_void_p()
+            ctx._chk(ctx.lib.sdm_host_alloc(api.C.byref(ptr), nd * H * W * 4))
+            edge = np.ctypeslib.as_array(api.C.cast(ptr, api.C.POINTER(api.C.c_int32)), shape=(nd, H, W))
+            ctx.edge_drawing(imd[:8], edge_index=False)
+            best = None
+            for _ in range(3):
+                offs, pix, _e = ctx.edge_drawing(imd, edge_out=edge)
+                t = ctx.last_edge_drawing_ms()
+                if best is None or t["wall_ms"] < best["wall_ms"]:
+                    best = t
+            res["device_route"].append(dict(keyframes=nd, wall_ms_per_kf=best["wall_ms"] / nd, route_kernel_ms=best["route_thread_ms"],
+                                            stage1_kernel_us_per_kf=best["kernel_ms"] * 1e3 / nd, fallbacks=ctx.last_edge_drawing_fallbacks(),
+                                            chains=int(sum(len(o) - 1 for o in offs))))
+            del edge
+            ctx.lib.sdm_host_free(ptr)
     with tempfile.TemporaryDirectory() as tmp:
         exe = os.path.join(tmp, "ed")
         subprocess.run(["g++", "-O2", "-std=c++11", "-o", exe, os.path.join(ROOT, "tests", "cpp", "test_edge_drawing.cpp")], check=True)
