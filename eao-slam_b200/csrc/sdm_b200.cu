@@ -1709,9 +1709,6 @@ int ed_reserve(sdm_ctx* c, int n_kf)
     if (c->ed_cap >= n_kf) return SDM_OK;
     CU(cudaStreamSynchronize(c->s_ed));
     cudaFree(c->ed_dev);
-    cudaFree(c->edr_dev);
-    if (c->edr_result_host) cudaFreeHost(c->edr_result_host);
-    for (auto& e : c->edr_ev) if (e) cudaEventDestroy(e);
     if (c->ed_host) cudaFreeHost(c->ed_host);
     c->ed_dev = nullptr; c->ed_host = nullptr; c->ed_cap = 0;
     const size_t bytes = ed_bytes(n_kf, c->npix);

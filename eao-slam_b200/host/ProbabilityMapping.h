@@ -109,7 +109,7 @@ public:
 
     explicit ProbabilityMapping(Map* pMap)
         : mMutexSemiDense(), mpMap(pMap), mCtx(NULL), mN(covisN), mW(0), mH(0), mCapacity(0), mChunk(0), mHeadroom(-1), mDevicePlanes(false), mSparse(false),
-          mOnline(false), mEdgeDrawing(false), mEdThreads(0), mEdGrad(36), mEdAnchor(8), mbFinishRequested(false), mbFinished(false), mbResetRequested(false)
+          mOnline(false), mEdgeDrawing(false), mEdRouteDevice(false), mEdThreads(0), mEdGrad(36), mEdAnchor(8), mbFinishRequested(false), mbFinished(false), mbResetRequested(false)
     {
         sdm_default_config(&mCfg);
 #ifdef SDM_HOST_WITH_ORBSLAM2
@@ -149,9 +149,11 @@ public:
     // chains are the library's, pixel for pixel (tests/test_edge_drawing.py) - and keeps the chains for FitLines
     // (EdgeChainsOf); with SDM_HOST_WITH_ORBSLAM2 kf->mEdgeMap is built from them as well (:869), so the reference's own
     // consumers of the edge map run unchanged.  Off by default: a hook, then the reference's LineDetector, come first.
-    void SetEdgeDrawing(bool on, int threads = 0, int grad_thresh = 36, int anchor_thresh = 8)
+    // route_on_device: the routing walks in k_ed_route (one warp per keyframe) instead of host threads - for maps of a
+    // thousand keyframes and more, or when the host cores are shared by several GPU processes (sdm_set_edge_drawing_route).
+    void SetEdgeDrawing(bool on, int threads = 0, int grad_thresh = 36, int anchor_thresh = 8, bool route_on_device = false)
     {
-        mEdgeDrawing = on; mEdThreads = threads; mEdGrad = grad_thresh; mEdAnchor = anchor_thresh;
+        mEdgeDrawing = on; mEdThreads = threads; mEdGrad = grad_thresh; mEdAnchor = anchor_thresh; mEdRouteDevice = route_on_device;
     }
     const sdm_host::EdgeChains* EdgeChainsOf(KeyFrame* kf) const
     {
@@ -643,6 +645,8 @@ private:
             ims[i].edge_step = (size_t)kf->mEdgeIndex.step;
         }
         sdm_ed_result* res = NULL;
+        if (!Check(sdm_set_edge_drawing_route(mCtx, mEdRouteDevice ? SDM_ED_ROUTE_DEVICE : SDM_ED_ROUTE_HOST), "sdm_set_edge_drawing_route"))
+            return false;
         if (!Check(sdm_edge_drawing(mCtx, (int)ims.size(), ims.data(), mEdGrad, mEdAnchor, mEdThreads, &res), "sdm_edge_drawing"))
             return false;
         for (size_t i = 0; i < w1.size(); i++) {
@@ -965,7 +969,7 @@ private:
     std::vector<KeyFrame*> mPendingKFs;
     std::vector<KeyFrame*> mPinned;
     std::function<void(KeyFrame*)> mEdgeHook;
-    bool mEdgeDrawing;
+    bool mEdgeDrawing, mEdRouteDevice;
     int mEdThreads, mEdGrad, mEdAnchor;
     std::unordered_map<KeyFrame*, sdm_host::EdgeChains> mEdgeChains;
     std::string mResultsDir;

@@ -122,7 +122,7 @@ int main(int argc, char** argv)
     if (const char* e = getenv("SDM_SHIM_SPARSE")) pm.SetSparseDownloads(e[0] == '1');
     int hook_calls = 0;
     const char* edge_out = getenv("SDM_SHIM_EDGE_OUT");  // open Edge Drawing where the reference calls DetectEdgeMap; dump file
-    if (edge_out) pm.SetEdgeDrawing(true, 4);
+    if (edge_out) pm.SetEdgeDrawing(true, 4, 36, 8, getenv("SDM_SHIM_EDGE_DEVICE") != NULL);
     else pm.SetEdgeMapHook([&hook_calls](KeyFrame*) { ++hook_calls; });  // where the reference calls DetectEdgeMap (:394-397)
 
     if (online) {  // mirrors ref_online_sequence (oracle/refshim/refdriver.cc)

@@ -184,7 +184,8 @@ def _read_planes(raw, n, W, H):
 
 
 @pytest.mark.gpu
-def test_shim_with_open_edge_drawing(shim_binary, tmp_path):
+@pytest.mark.parametrize("route_on_device", [False, True])
+def test_shim_with_open_edge_drawing(shim_binary, tmp_path, route_on_device):
     """SetEdgeDrawing(true): the class detects the edge maps of the pass-1 keyframes itself, where the reference calls
     LineDetector::DetectEdgeMap (ProbabilityMapping.cc:394, LineDetector.cc:843-881) - mEdgeIndex and the chains equal the
     C-ABI's (pinned to the reference's EDLib.a in tests/test_gpu_edge_drawing.py), the loop's planes equal the oracle's
@@ -201,7 +202,7 @@ def test_shim_with_open_edge_drawing(shim_binary, tmp_path):
     scene_path, out_path, edge_path = (str(tmp_path / f) for f in ("scene.bin", "out.bin", "edge.bin"))
     _write_scene(scene_path, sc, N, 16, [])
     r = subprocess.run([shim_binary, scene_path, out_path], capture_output=True, text=True,
-                       env=dict(os.environ, SDM_SHIM_EDGE_OUT=edge_path))
+                       env=dict(os.environ, SDM_SHIM_EDGE_OUT=edge_path, **({"SDM_SHIM_EDGE_DEVICE": "1"} if route_on_device else {})))
     assert r.returncode == 0, r.stdout + r.stderr
     with api.Context(width=W, height=H, max_keyframes=n) as ctx:
         offs, pix, edge = ctx.edge_drawing(sc.im)

@@ -128,6 +128,7 @@ def test_large_pitched_batch_matches_the_host_form(scene, ed_bin, tmp_path, devi
     pitched[:, :, :W] = ims
     with ctx_for(W, H) as ctx:
         ctx.set_edge_drawing_route(device_route)
+        ctx.edge_drawing(ims[:3])  # (the buffers of a context grow with the batch)
         offs, pix, _ = ctx.edge_drawing([pitched[i, :, :W] for i in range(len(ims))], n_threads=16, edge_index=False)
         assert ctx.last_edge_drawing_fallbacks() == 0
         empty = ctx.edge_drawing(np.zeros((0, H, W), np.uint8))
