@@ -404,6 +404,42 @@ __global__ void __launch_bounds__(32) k_ed_route(EdRouteBatch b)
         b.result[img] = make_int4(nc, np, ok ? 1 : 0, 0);
     }
 }
+
+// chain lists of a batch as one contiguous block (one D2H copy instead of two per image): at[i] = first int32 of image i's
+// list - its offsets (chains + 1) followed by its pixels - at[n] = total; images that did not complete take no room
+__global__ void __launch_bounds__(1024) k_ed_chain_offsets(const int4* __restrict__ result, int n, unsigned long long* __restrict__ at)
+{
+    __shared__ unsigned long long warp_sum[32];
+    const int i = threadIdx.x, lane = i & 31, w = i >> 5;
+    unsigned long long v = 0;
+    if (i < n) { const int4 r = result[i]; v = r.z ? (unsigned long long)r.x + 1ull + (unsigned long long)r.y : 0ull; }
+    unsigned long long inc = v;
+    for (int d = 1; d < 32; d <<= 1) { const unsigned long long o = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += o; }
+    if (lane == 31) warp_sum[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        unsigned long long s = warp_sum[lane], t = s;
+        for (int d = 1; d < 32; d <<= 1) { const unsigned long long o = __shfl_up_sync(0xffffffffu, t, d); if (lane >= d) t += o; }
+        warp_sum[lane] = t - s;  // exclusive
+    }
+    __syncthreads();
+    const unsigned long long excl = warp_sum[w] + inc - v;
+    if (i < n) at[i] = excl;
+    if (i == n - 1) at[n] = excl + v;
+}
+
+__global__ void __launch_bounds__(256) k_ed_chain_gather(EdRouteBatch b, const unsigned long long* __restrict__ at, int32_t* __restrict__ dst)
+{
+    const int img = blockIdx.y;
+    const int4 r = b.result[img];
+    if (!r.z) return;
+    const int32_t* off = b.offsets + (size_t)img * b.caps.offsets;
+    const uint32_t* px = b.pixels + (size_t)img * b.caps.out_pixels;
+    int32_t* d = dst + at[img];
+    const int n_off = r.x + 1, total = n_off + r.y;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
+        d[i] = i < n_off ? off[i] : (int32_t)px[i - n_off];
+}
 #endif
 
 }  // namespace sdm

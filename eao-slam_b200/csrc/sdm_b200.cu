@@ -1689,7 +1689,11 @@ int sdm_last_line_fit_ms(sdm_ctx* c, float* ms)
 
 // ---- Edge Drawing: stage 1 on the device, the routing walk on host threads ------------------------
 struct sdm_ed_result {
-    std::vector<sdm_host::EdgeChains> chains;
+    std::vector<sdm_host::EdgeChains> chains;  // host routing (and device-mode fall-backs): one pair of lists per image
+    // device routing: the lists of all images in one block (image i: offsets at blob[at[i]], n_chains + 1 of them, then its pixels)
+    std::vector<int32_t> blob;
+    std::vector<size_t> at;
+    std::vector<int32_t> blob_chains;  // chains of image i, -1: the image is in `chains`
 };
 
 namespace {
@@ -1751,7 +1755,7 @@ constexpr int kEdDevBatch = 1024;  // images routed by one k_ed_route launch (27
 // sections of the device block of the routing kernel for `cap` images
 struct EdRouteLayout {
     sdm_host::EdRouteCaps caps;
-    size_t scratch_stride, o_scratch, o_off, o_px, o_edge, o_res, bytes;
+    size_t scratch_stride, o_scratch, o_off, o_px, o_edge, o_res, o_at, bytes;
     EdRouteLayout(int cap, size_t P)
     {
         caps = sdm_host::EdRouteCapsFor(P);
@@ -1765,7 +1769,8 @@ struct EdRouteLayout {
         o_px = ed_align(o_off + (size_t)cap * caps.offsets * 4);
         o_edge = ed_align(o_px + (size_t)cap * caps.out_pixels * 4);
         o_res = ed_align(o_edge + (size_t)cap * P * 4);
-        bytes = ed_align(o_res + (size_t)cap * sizeof(int4));
+        o_at = ed_align(o_res + (size_t)cap * sizeof(int4));
+        bytes = ed_align(o_at + ((size_t)cap + 1) * sizeof(unsigned long long));
     }
 };
 
@@ -1779,14 +1784,15 @@ int edr_reserve(sdm_ctx* c, int n_img)
     c->edr_dev = nullptr; c->edr_result_host = nullptr; c->edr_cap = 0;
     const EdRouteLayout L(n_img, c->npix);
     CU(cudaMalloc((void**)&c->edr_dev, L.bytes));
-    CU(cudaMallocHost((void**)&c->edr_result_host, (size_t)n_img * sizeof(int4)));
+    CU(cudaMallocHost((void**)&c->edr_result_host, (size_t)n_img * sizeof(int4) + ((size_t)n_img + 1) * sizeof(unsigned long long)));
     c->edr_cap = n_img;
     return SDM_OK;
 }
 
 // sdm_edge_drawing with both stages on the device: batches of up to kEdDevBatch images - images up, k_ed_planes(4) over the
-// batch, k_ed_route (one warp per image), the per-image counts down, then exactly the chain lists (through the pinned
-// mirror) and the requested edge-index planes.  Images whose routing ran out of a capacity are routed on the host.
+// batch, k_ed_route (one warp per image), the chain lists gathered into one block (k_ed_chain_offsets / k_ed_chain_gather,
+// into the G / F planes, which are spent by then) and brought down in ONE copy together with the per-image counts, then the
+// requested edge-index planes.  Images whose routing ran out of a capacity are routed on the host.
 int ed_run_device(sdm_ctx* c, int n, const sdm_ed_image* images, int grad_thresh, int anchor_thresh, sdm_ed_result* res)
 {
     const int W = c->cfg.width, H = c->cfg.height;
@@ -1802,16 +1808,31 @@ int ed_run_device(sdm_ctx* c, int n, const sdm_ed_image* images, int grad_thresh
     }
     const EdLayout dv(c->ed_dev, c->ed_cap, P), hv(c->ed_host, c->ed_cap, P);
     const EdRouteLayout L(c->edr_cap, P);
+    const size_t list_room = (size_t)(c->ed_dev + ed_bytes(c->ed_cap, P) - (uint8_t*)dv.G) / 4;  // int32 the G / F planes hold
+    unsigned long long* at_host = reinterpret_cast<unsigned long long*>(c->edr_result_host + c->edr_cap);
     c->edr_fallbacks = 0;
+    res->blob_chains.assign((size_t)n, -1);
+    res->at.assign((size_t)n, 0);
     for (int base = 0; base < n; base += cap) {
         const int nb = std::min(cap, n - base);
         bool want_edge = false;
-        for (int i = 0; i < nb; ++i) {
-            const sdm_ed_image& im = images[base + i];
-            want_edge = want_edge || im.edge_index != nullptr;
-            uint8_t* dst = hv.im + (size_t)i * P;
-            if (im.im_step == (size_t)W) std::memcpy(dst, im.im, P);
-            else for (int y = 0; y < H; ++y) std::memcpy(dst + (size_t)y * W, im.im + (size_t)y * im.im_step, (size_t)W);
+        for (int i = 0; i < nb; ++i) want_edge = want_edge || images[base + i].edge_index != nullptr;
+        {   // rows into the pinned mirror, a few threads for a large batch (a single memcpy stream runs at ~10 GB/s)
+            auto pack = [&](int i0, int i1) {
+                for (int i = i0; i < i1; ++i) {
+                    const sdm_ed_image& im = images[base + i];
+                    uint8_t* dst = hv.im + (size_t)i * P;
+                    if (im.im_step == (size_t)W) std::memcpy(dst, im.im, P);
+                    else for (int y = 0; y < H; ++y) std::memcpy(dst + (size_t)y * W, im.im + (size_t)y * im.im_step, (size_t)W);
+                }
+            };
+            const int pt = nb >= 64 ? (int)std::max(1u, std::min(8u, std::thread::hardware_concurrency())) : 1;
+            if (pt == 1) pack(0, nb);
+            else {
+                std::vector<std::thread> th;
+                for (int t = 0; t < pt; ++t) th.emplace_back(pack, (int)((long long)nb * t / pt), (int)((long long)nb * (t + 1) / pt));
+                for (auto& t : th) t.join();
+            }
         }
         CU(cudaMemcpyAsync(dv.im, hv.im, (size_t)nb * P, cudaMemcpyHostToDevice, c->s_ed));
         CU(cudaEventRecord(c->ed_ev[0], c->s_ed));
@@ -1826,63 +1847,55 @@ int ed_run_device(sdm_ctx* c, int n, const sdm_ed_image* images, int grad_thresh
         b.pixels = (uint32_t*)(c->edr_dev + L.o_px);
         b.edge_index = want_edge ? (int32_t*)(c->edr_dev + L.o_edge) : nullptr;
         b.result = (int4*)(c->edr_dev + L.o_res);
+        unsigned long long* at_dev = (unsigned long long*)(c->edr_dev + L.o_at);
         CU(cudaEventRecord(c->edr_ev[0], c->s_ed));
         sdm::k_ed_route<<<nb, 32, 0, c->s_ed>>>(b);
         CU(cudaGetLastError());
-        ++c->launches;
         CU(cudaEventRecord(c->edr_ev[1], c->s_ed));
+        sdm::k_ed_chain_offsets<<<1, 1024, 0, c->s_ed>>>(b.result, nb, at_dev);
+        CU(cudaGetLastError());
+        sdm::k_ed_chain_gather<<<dim3(8, nb), 256, 0, c->s_ed>>>(b, at_dev, (int32_t*)dv.G);
+        CU(cudaGetLastError());
+        c->launches += 3;
         CU(cudaMemcpyAsync(c->edr_result_host, b.result, (size_t)nb * sizeof(int4), cudaMemcpyDeviceToHost, c->s_ed));
-        CU(cudaStreamSynchronize(c->s_ed));
-        // the chain lists, exactly as long as they are, through the pinned mirror's G / F sections (unused in this mode)
-        uint8_t* bounce = (uint8_t*)hv.G;
-        const size_t bounce_bytes = (size_t)((uint8_t*)hv.im + ed_bytes(c->ed_cap, P) - bounce);
-        std::vector<size_t> at((size_t)nb + 1, 0);
-        int first = 0;
-        while (first < nb) {  // groups of images whose lists fit the mirror together
-            size_t used = 0;
-            int last = first;
-            for (; last < nb; ++last) {
-                const int4 r = c->edr_result_host[last];
-                const size_t need = r.z ? ((size_t)r.x + 1 + (size_t)r.y) * 4 : 0;
-                if (used + need > bounce_bytes && last > first) break;
-                if (need > bounce_bytes) return fail(SDM_ERR_NOMEM, "sdm_edge_drawing: chain list of image %d exceeds the staging area", base + last);
-                at[(size_t)last] = used;
-                used += need;
-            }
-            for (int i = first; i < last; ++i) {
-                const int4 r = c->edr_result_host[i];
-                if (!r.z) continue;
-                CU(cudaMemcpyAsync(bounce + at[(size_t)i], b.offsets + (size_t)i * L.caps.offsets, ((size_t)r.x + 1) * 4, cudaMemcpyDeviceToHost, c->s_ed));
-                if (r.y > 0)
-                    CU(cudaMemcpyAsync(bounce + at[(size_t)i] + ((size_t)r.x + 1) * 4, b.pixels + (size_t)i * L.caps.out_pixels, (size_t)r.y * 4,
-                                       cudaMemcpyDeviceToHost, c->s_ed));
-            }
-            CU(cudaStreamSynchronize(c->s_ed));
-            for (int i = first; i < last; ++i) {
-                const int4 r = c->edr_result_host[i];
-                if (!r.z) continue;
-                sdm_host::EdgeChains& e = res->chains[(size_t)(base + i)];
-                const int32_t* po = (const int32_t*)(bounce + at[(size_t)i]);
-                const uint32_t* pp = (const uint32_t*)(po + r.x + 1);
-                e.offsets.assign(po, po + r.x + 1);
-                e.pixels.assign(pp, pp + r.y);
-            }
-            first = last;
-        }
-        // edge-index planes of the images that asked for one
-        for (int i = 0; i < nb; ++i) {
+        CU(cudaMemcpyAsync(at_host, at_dev, ((size_t)nb + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->s_ed));
+        // the edge-index planes: one copy when the caller's planes are dense and consecutive, one per image otherwise (the
+        // planes of images that fell back are overwritten by the host routing below)
+        bool dense_edges = want_edge;
+        for (int i = 0; i < nb && dense_edges; ++i) {
             const sdm_ed_image& im = images[base + i];
-            if (!im.edge_index || !c->edr_result_host[i].z) continue;
-            CU(cudaMemcpy2DAsync(im.edge_index, im.edge_step, b.edge_index + (size_t)i * P, (size_t)W * 4, (size_t)W * 4, (size_t)H,
-                                 cudaMemcpyDeviceToHost, c->s_ed));
+            dense_edges = im.edge_index && im.edge_step == (size_t)W * 4 && (i == 0 || im.edge_index == images[base + i - 1].edge_index + P);
         }
+        if (dense_edges)
+            CU(cudaMemcpyAsync(images[base].edge_index, b.edge_index, (size_t)nb * P * 4, cudaMemcpyDeviceToHost, c->s_ed));
+        else if (want_edge)
+            for (int i = 0; i < nb; ++i) {
+                const sdm_ed_image& im = images[base + i];
+                if (!im.edge_index) continue;
+                CU(cudaMemcpy2DAsync(im.edge_index, im.edge_step, b.edge_index + (size_t)i * P, (size_t)W * 4, (size_t)W * 4, (size_t)H,
+                                     cudaMemcpyDeviceToHost, c->s_ed));
+            }
+        CU(cudaStreamSynchronize(c->s_ed));  // (the gather ran before the copies on the same stream; its writes are bounded by the
+                                             //  capacities: at most (P / 8 + P / 2 + 32) int32 per image)
+        const size_t total = (size_t)at_host[nb];
+        if (total > list_room) return fail(SDM_ERR_NOMEM, "sdm_edge_drawing: chain lists (%zu words) exceed the staging planes", total);
+        if (total > 0) CU(cudaMemcpyAsync(hv.G, dv.G, total * 4, cudaMemcpyDeviceToHost, c->s_ed));
         CU(cudaStreamSynchronize(c->s_ed));
+        const size_t blob0 = res->blob.size();
+        res->blob.resize(blob0 + total);
+        if (total > 0) std::memcpy(res->blob.data() + blob0, hv.G, total * 4);
+        for (int i = 0; i < nb; ++i) {
+            const int4 r = c->edr_result_host[i];
+            if (!r.z) continue;
+            res->at[(size_t)(base + i)] = blob0 + (size_t)at_host[i];
+            res->blob_chains[(size_t)(base + i)] = r.x;
+        }
         float ms = 0.f;
         CU(cudaEventElapsedTime(&ms, c->ed_ev[0], c->ed_ev[1]));
         c->ed_kernel_ms += ms;
         CU(cudaEventElapsedTime(&ms, c->edr_ev[0], c->edr_ev[1]));
         c->ed_route_ms += ms;
-        // images that ran out of a capacity on the device: stage 1 again (the kernel has modified F), stage 2 on the host
+        // images that ran out of a capacity on the device: stage 1 again (the planes are spent), stage 2 on the host
         for (int i = 0; i < nb; ++i) {
             if (c->edr_result_host[i].z) continue;
             ++c->edr_fallbacks;
@@ -2034,6 +2047,12 @@ int sdm_ed_chains(const sdm_ed_result* r, int i, int32_t* n_chains, const int32_
 {
     if (!r || !n_chains || !offsets || !pixels) return fail(SDM_ERR_ARG, "sdm_ed_chains: null argument");
     if (i < 0 || i >= (int)r->chains.size()) return fail(SDM_ERR_ARG, "sdm_ed_chains: keyframe %d out of range", i);
+    if ((size_t)i < r->blob_chains.size() && r->blob_chains[(size_t)i] >= 0) {
+        *n_chains = r->blob_chains[(size_t)i];
+        *offsets = r->blob.data() + r->at[(size_t)i];
+        *pixels = reinterpret_cast<const uint32_t*>(*offsets + *n_chains + 1);
+        return SDM_OK;
+    }
     const sdm_host::EdgeChains& e = r->chains[(size_t)i];
     *n_chains = e.n_chains();
     *offsets = e.offsets.data();

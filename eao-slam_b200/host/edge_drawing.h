@@ -35,6 +35,7 @@
 #pragma once
 
 #include <algorithm>
+#include <cstddef>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -50,8 +51,13 @@ struct EdgeChains {
 
 #if defined(__CUDACC__)
 #define SDM_EDR_HD __host__ __device__
+#define SDM_EDR_UNROLL4 _Pragma("unroll 4")
+// the routing templates are __host__ __device__ and are instantiated on std::vector for the host threads: nvcc warns about the
+// host-only calls of that (host-only) instantiation
+#pragma nv_diag_suppress 20011, 20014
 #else
 #define SDM_EDR_HD
+#define SDM_EDR_UNROLL4
 #endif
 
 namespace ed_detail {
@@ -81,6 +87,13 @@ struct HostVec {
     T& operator[](int i) { return v[(size_t)i]; }
     const T& operator[](int i) const { return v[(size_t)i]; }
     void resize(int n) { v.resize((size_t)n); }
+    void append(const T* src, int count, int step)  // count elements from src, walking by step (+1 / -1)
+    {
+        const size_t n0 = v.size();
+        v.resize(n0 + (size_t)count);
+        T* d = v.data() + n0;
+        for (int i = 0; i < count; ++i) d[i] = src[(ptrdiff_t)i * step];
+    }
     bool overflow() const { return false; }
 };
 template <class T>
@@ -98,6 +111,14 @@ struct FixedVec {
     SDM_EDR_HD T& operator[](int i) { return p[i]; }
     SDM_EDR_HD const T& operator[](int i) const { return p[i]; }
     SDM_EDR_HD void resize(int m) { if (m <= cap) n = m; else { n = cap; ovf = true; } }
+    SDM_EDR_HD void append(const T* src, int count, int step)  // independent iterations: the loads of four are in flight together
+    {
+        if (count > cap - n) { ovf = true; return; }
+        T* d = p + n;
+        SDM_EDR_UNROLL4
+        for (int i = 0; i < count; ++i) d[i] = src[(ptrdiff_t)i * step];
+        n += count;
+    }
     SDM_EDR_HD bool overflow() const { return ovf; }
 };
 
@@ -272,10 +293,16 @@ SDM_EDR_HD inline bool EdRouteCore(int W, int H, const int16_t* G, uint8_t* F, i
 #define SDM_EDR_EMIT()                                                                                                       \
     do {                                                                                                                     \
         const int32_t id = (int32_t)out_offsets.size() - 1;                                                                  \
-        for (int i_ = 0; i_ < seg.size(); ++i_) {                                                                            \
-            out_pixels.push_back(((uint32_t)seg[i_].r << 16) | (uint32_t)seg[i_].c);                                         \
-            if (edge_index)                                                                                                  \
-                reinterpret_cast<int32_t*>(reinterpret_cast<char*>(edge_index) + (size_t)seg[i_].r * edge_step)[seg[i_].c] = id; \
+        const int base_ = out_pixels.size(), cnt_ = seg.size();                                                              \
+        out_pixels.resize(base_ + cnt_);                                                                                     \
+        if (!out_pixels.overflow()) {                                                                                        \
+            SDM_EDR_UNROLL4                                                                                                  \
+            for (int i_ = 0; i_ < cnt_; ++i_) out_pixels[base_ + i_] = ((uint32_t)seg[i_].r << 16) | (uint32_t)seg[i_].c;    \
+            if (edge_index) {                                                                                                \
+                SDM_EDR_UNROLL4                                                                                              \
+                for (int i_ = 0; i_ < cnt_; ++i_)                                                                            \
+                    reinterpret_cast<int32_t*>(reinterpret_cast<char*>(edge_index) + (size_t)seg[i_].r * edge_step)[seg[i_].c] = id; \
+            }                                                                                                                \
         }                                                                                                                    \
         out_offsets.push_back((int32_t)out_pixels.size());                                                                   \
         if (!seg.empty()) { prev_last = seg.back(); have_prev = true; }                                                      \
@@ -292,7 +319,7 @@ SDM_EDR_HD inline bool EdRouteCore(int W, int H, const int16_t* G, uint8_t* F, i
             const Px last_ = seg.empty() ? prev_last : seg.back();                                                           \
             if (adjacent(pixels[c_.start + 1], last_)) start_ = 1;                                                           \
         }                                                                                                                    \
-        for (int l_ = start_; l_ < c_.len; ++l_) seg.push_back(pixels[c_.start + l_]);                                       \
+        if (c_.len > start_) seg.append(&pixels[c_.start + start_], c_.len - start_, 1);                                     \
         c_.len = 0; /* copied */                                                                                             \
     } while (0)
 
@@ -331,34 +358,34 @@ SDM_EDR_HD inline bool EdRouteCore(int W, int H, const int16_t* G, uint8_t* F, i
             const int child = (dir == kLeft || dir == kUp) ? 0 : 1;
             const int fwd = (dir == kLeft || dir == kUp) ? -1 : 1;  // step along the walk; also the diagonal looked at first
             bool ended = false;
-            while (DI(r, c) == (horizontal ? kEdgeHorizontal : kEdgeVertical)) {
-                FL(r, c) = (uint8_t)((FL(r, c) & kEdDirMask) | kEdFlagEdge);
-                if (horizontal) {
-                    FL(r - 1, c) &= (uint8_t)~kEdFlagAnchor;
-                    FL(r + 1, c) &= (uint8_t)~kEdFlagAnchor;
-                    if (MARKED(r, c + fwd)) { c += fwd; }
-                    else if (MARKED(r + fwd, c + fwd)) { r += fwd; c += fwd; }
-                    else if (MARKED(r - fwd, c + fwd)) { r -= fwd; c += fwd; }
-                    else {
-                        const int A = GR(r - 1, c + fwd), B = GR(r, c + fwd), C = GR(r + 1, c + fwd);
-                        if (A > B) { if (A > C) --r; else ++r; }
-                        else if (C > B) ++r;
-                        c += fwd;
-                    }
-                } else {
-                    FL(r, c - 1) &= (uint8_t)~kEdFlagAnchor;
-                    FL(r, c + 1) &= (uint8_t)~kEdFlagAnchor;
-                    if (MARKED(r + fwd, c)) { r += fwd; }
-                    else if (MARKED(r + fwd, c + fwd)) { r += fwd; c += fwd; }
-                    else if (MARKED(r + fwd, c - fwd)) { r += fwd; c -= fwd; }
-                    else {
-                        const int A = GR(r + fwd, c - 1), B = GR(r + fwd, c), C = GR(r + fwd, c + 1);
-                        if (A > B) { if (A > C) --c; else ++c; }
-                        else if (C > B) ++c;
-                        r += fwd;
-                    }
-                }
-                if (IS_EDGE(r, c) || GR(r, c) < grad_thresh) {  // met an edge or left the gradient ridge
+            // One step: mark the pixel, clear the anchors beside it (across the edge), look at the three forward neighbours.
+            // Their flags and gradients are loaded together up front and the chosen neighbour's values are carried into the
+            // next step (nothing this step writes touches them): one round trip to memory per step instead of a chain of
+            // dependent ones - what a step costs on the device, where a load is an L2 access.
+            const int want = horizontal ? kEdgeHorizontal : kEdgeVertical;
+            const ptrdiff_t along = horizontal ? (ptrdiff_t)fwd : (ptrdiff_t)fwd * W;  // one pixel forward
+            const ptrdiff_t across = horizontal ? (ptrdiff_t)W : (ptrdiff_t)1;         // one pixel down / right
+            size_t at = (size_t)r * W + c;
+            uint8_t fcur = F[at];
+            while ((fcur & kEdDirMask) == want) {
+                const size_t nx = at + along;
+                // forward neighbours: straight, the diagonal on the `fwd` side, the other diagonal
+                const uint8_t f0 = F[nx], f1 = F[nx + fwd * across], f2 = F[nx - fwd * across];
+                const int gA = G[nx - across], gB = G[nx], gC = G[nx + across];
+                F[at] = (uint8_t)((fcur & kEdDirMask) | kEdFlagEdge);
+                F[at - across] &= (uint8_t)~kEdFlagAnchor;
+                F[at + across] &= (uint8_t)~kEdFlagAnchor;
+                int side;  // -1 / 0 / +1: offset across the walk of the pixel taken
+                if (f0 & (kEdFlagAnchor | kEdFlagEdge)) side = 0;
+                else if (f1 & (kEdFlagAnchor | kEdFlagEdge)) side = fwd;
+                else if (f2 & (kEdFlagAnchor | kEdFlagEdge)) side = -fwd;
+                else if (gA > gB) side = gA > gC ? -1 : 1;
+                else side = gC > gB ? 1 : 0;
+                at = nx + side * across;
+                if (horizontal) { r += side; c += fwd; } else { r += fwd; c += side; }
+                fcur = side == 0 ? f0 : (side == fwd ? f1 : f2);
+                const int gcur = side == 0 ? gB : (side < 0 ? gA : gC);
+                if ((fcur & kEdFlagEdge) || gcur < grad_thresh) {  // met an edge or left the gradient ridge
                     chains[no].len = clen;
                     chains[t.parent].child[child] = no;
                     ended = true;
@@ -386,6 +413,7 @@ SDM_EDR_HD inline bool EdRouteCore(int W, int H, const int16_t* G, uint8_t* F, i
             chains[t.parent].child[child] = no;
         }
         if (pixels.size() - dup < 10) {  // too short: take the walk back
+            SDM_EDR_UNROLL4
             for (int i = 0; i < pixels.size(); ++i) FL(pixels[i].r, pixels[i].c) &= kEdDirMask;
             continue;
         }
@@ -403,7 +431,7 @@ SDM_EDR_HD inline bool EdRouteCore(int W, int H, const int16_t* G, uint8_t* F, i
                 if (c.len > 1 && (!seg.empty() || have_prev) &&
                     adjacent(pixels[c.start + c.len - 2], seg.empty() ? prev_last : seg.back()))
                     --c.len;
-                for (int l = c.len - 1; l >= 0; --l) seg.push_back(pixels[c.start + l]);
+                if (c.len > 0) seg.append(&pixels[c.start + c.len - 1], c.len, -1);
                 c.len = 0;
             }
         }
