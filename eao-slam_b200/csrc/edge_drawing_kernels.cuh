@@ -383,8 +383,12 @@ struct EdRouteBatch {
 
 __global__ void __launch_bounds__(32) k_ed_route(EdRouteBatch b)
 {
+    __shared__ int hist[2048];
     const int img = blockIdx.x, lane = threadIdx.x;
     const size_t P = (size_t)b.W * b.H;
+    const int16_t* G = b.G + (size_t)img * P;
+    uint8_t* F = b.F + (size_t)img * P;
+    uint8_t* scratch = b.scratch + (size_t)img * b.scratch_stride;
     int32_t* edge = b.edge_index ? b.edge_index + (size_t)img * P : nullptr;
     if (edge) {
         if ((P & 3) == 0) {
@@ -394,13 +398,52 @@ __global__ void __launch_bounds__(32) k_ed_route(EdRouteBatch b)
             for (size_t i = lane; i < P; i += 32) edge[i] = -1;
         }
     }
+    // ---- the anchors in walking order - decreasing gradient, raster order among equals - by the whole warp: a stable
+    // counting sort over the 2048 gradient values (one thread doing this alone pays two dependent memory round trips per
+    // anchor, twice: half of the kernel's time in its first form).  Lane l looks at pixel i0 + l, so lane order = raster order.
+    for (int k = lane; k < 2048; k += 32) hist[k] = 0;
+    __syncwarp();
+    for (size_t i0 = 0; i0 < P; i0 += 32) {
+        const size_t i = i0 + lane;
+        if (i < P && (F[i] & kEdFlagAnchor)) atomicAdd(&hist[2047 - min((int)G[i], 2047)], 1);
+    }
+    __syncwarp();
+    int total;
+    {   // exclusive prefix over the bins: 64 consecutive bins per lane
+        int sum = 0;
+        for (int k = 0; k < 64; ++k) sum += hist[64 * lane + k];
+        int incl = sum;
+        for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+        int run = incl - sum;
+        for (int k = 0; k < 64; ++k) { const int c = hist[64 * lane + k]; hist[64 * lane + k] = run; run += c; }
+        total = __shfl_sync(0xffffffffu, incl, 31);
+    }
+    __syncwarp();
+    if (total > b.caps.anchors) {  // (cannot happen with EdRouteCapsFor's P / 2; the host routes the image if it does)
+        if (lane == 0) b.result[img] = make_int4(0, 0, 0, 0);
+        return;
+    }
+    int* anchors = sdm_host::EdRouteAnchorSlots(scratch, b.caps);
+    for (size_t i0 = 0; i0 < P; i0 += 32) {
+        const size_t i = i0 + lane;
+        const bool is_anchor = i < P && (F[i] & kEdFlagAnchor);
+        const unsigned m = __ballot_sync(0xffffffffu, is_anchor);
+        if (is_anchor) {
+            const int key = 2047 - min((int)G[i], 2047);
+            const unsigned peers = __match_any_sync(m, key);   // the lanes of this group with the same gradient
+            const int leader = __ffs(peers) - 1;
+            int pos = 0;
+            if (lane == leader) { pos = hist[key]; hist[key] = pos + __popc(peers); }
+            pos = __shfl_sync(peers, pos, leader);
+            anchors[pos + __popc(peers & ((1u << lane) - 1u))] = (int)i;
+        }
+        __syncwarp();
+    }
     __syncwarp();
     if (lane == 0) {
         int nc = 0, np = 0;
-        const bool ok = sdm_host::EdRouteFixed(b.W, b.H, b.G + (size_t)img * P, b.F + (size_t)img * P, b.grad_thresh,
-                                               b.scratch + (size_t)img * b.scratch_stride, b.caps,
-                                               b.offsets + (size_t)img * b.caps.offsets, b.pixels + (size_t)img * b.caps.out_pixels, edge,
-                                               (size_t)b.W * 4, &nc, &np);
+        const bool ok = sdm_host::EdRouteFixed(b.W, b.H, G, F, b.grad_thresh, scratch, b.caps, b.offsets + (size_t)img * b.caps.offsets,
+                                               b.pixels + (size_t)img * b.caps.out_pixels, edge, (size_t)b.W * 4, &nc, &np, total);
         b.result[img] = make_int4(nc, np, ok ? 1 : 0, 0);
     }
 }

@@ -242,7 +242,8 @@ inline void EdPlanesHost(const uint8_t* im, size_t step, int W, int H, int grad_
 template <class IntVec, class ChainVec, class PxVec, class TodoVec, class OffVec, class PixVec>
 SDM_EDR_HD inline bool EdRouteCore(int W, int H, const int16_t* G, uint8_t* F, int grad_thresh, IntVec& found, IntVec& anchors,
                                    ChainVec& chains, PxVec& pixels, PxVec& seg, TodoVec& stack, IntVec& best, IntVec& order, IntVec& nos,
-                                   OffVec& out_offsets, PixVec& out_pixels, int32_t* edge_index, size_t edge_step, int* hist /* [2049] */)
+                                   OffVec& out_offsets, PixVec& out_pixels, int32_t* edge_index, size_t edge_step, int* hist /* [2049] */,
+                                   int presorted = -1 /* >= 0: `anchors` already holds that many positions in walking order */)
 {
     using namespace ed_detail;
     out_offsets.clear();
@@ -260,30 +261,36 @@ SDM_EDR_HD inline bool EdRouteCore(int W, int H, const int16_t* G, uint8_t* F, i
                             stack.overflow() || best.overflow() || order.overflow() || nos.overflow() || out_offsets.overflow() ||  \
                             out_pixels.overflow())
     // ---- anchor order: decreasing gradient, raster order among equals (counting sort: |gx| + |gy| <= 2040)
-    found.clear();
-    for (int i = 0; i <= 2048; ++i) hist[i] = 0;
-    {
-        size_t i = 0;
-        while (i < P && ((size_t)(F + i) & 7) != 0) {
-            if (F[i] & kEdFlagAnchor) { found.push_back((int)i); ++hist[2047 - (G[i] < 2047 ? (int)G[i] : 2047)]; }
-            ++i;
-        }
-        for (; i + 8 <= P; i += 8) {  // eight flag bytes at a time
-            const uint64_t w = *reinterpret_cast<const uint64_t*>(F + i);
-            if ((w & 0x8080808080808080ull) == 0) continue;
-            for (int k = 0; k < 8; ++k)
-                if (F[i + k] & kEdFlagAnchor) { found.push_back((int)(i + k)); ++hist[2047 - (G[i + k] < 2047 ? (int)G[i + k] : 2047)]; }
-        }
-        for (; i < P; ++i)
-            if (F[i] & kEdFlagAnchor) { found.push_back((int)i); ++hist[2047 - (G[i] < 2047 ? (int)G[i] : 2047)]; }
-    }
-    if (found.overflow()) return false;
-    {
-        int run = 0;
-        for (int i = 0; i <= 2047; ++i) { const int c = hist[i]; hist[i] = run; run += c; }
-        anchors.resize(found.size());
+    if (presorted >= 0) {
+        anchors.resize(presorted);
         if (anchors.overflow()) return false;
-        for (int i = 0; i < found.size(); ++i) { const int g = G[found[i]]; anchors[hist[2047 - (g < 2047 ? g : 2047)]++] = found[i]; }
+    } else {
+        found.clear();
+        for (int i = 0; i <= 2048; ++i) hist[i] = 0;
+        {
+            size_t i = 0;
+            while (i < P && ((size_t)(F + i) & 7) != 0) {
+                if (F[i] & kEdFlagAnchor) { found.push_back((int)i); ++hist[2047 - (G[i] < 2047 ? (int)G[i] : 2047)]; }
+                ++i;
+            }
+            for (; i + 8 <= P; i += 8) {  // eight flag bytes at a time
+                const uint64_t w = *reinterpret_cast<const uint64_t*>(F + i);
+                if ((w & 0x8080808080808080ull) == 0) continue;
+                for (int k = 0; k < 8; ++k)
+                    if (F[i + k] & kEdFlagAnchor) { found.push_back((int)(i + k)); ++hist[2047 - (G[i + k] < 2047 ? (int)G[i + k] : 2047)]; }
+            }
+            for (; i < P; ++i)
+                if (F[i] & kEdFlagAnchor) { found.push_back((int)i); ++hist[2047 - (G[i] < 2047 ? (int)G[i] : 2047)]; }
+        }
+        if (found.overflow()) return false;
+        {
+            int run = 0;
+            for (int i = 0; i <= 2047; ++i) { const int c = hist[i]; hist[i] = run; run += c; }
+            anchors.resize(found.size());
+            if (anchors.overflow()) return false;
+            for (int i = 0; i < found.size(); ++i) { const int g = G[found[i]]; anchors[hist[2047 - (g < 2047 ? g : 2047)]++] = found[i]; }
+        }
+
     }
 
     bool have_prev = false;
@@ -519,11 +526,16 @@ SDM_EDR_HD inline size_t EdRouteScratchBytes(const EdRouteCaps& c)
            2 * EdRouteAlign((size_t)c.pixels * sizeof(Px)) + EdRouteAlign((size_t)c.chains * sizeof(Todo)) +
            3 * EdRouteAlign((size_t)c.chains * sizeof(int)) + EdRouteAlign(2049 * sizeof(int));
 }
+// where a caller that sorts the anchors itself (k_ed_route: all 32 lanes of the warp) leaves them: caps.anchors ints
+SDM_EDR_HD inline int* EdRouteAnchorSlots(uint8_t* scratch, const EdRouteCaps& caps)
+{
+    return reinterpret_cast<int*>(scratch + EdRouteAlign((size_t)caps.anchors * sizeof(int)));
+}
 // scratch: EdRouteScratchBytes(caps) bytes, 16-byte aligned; out_offsets[caps.offsets], out_pixels[caps.out_pixels];
 // edge_index (may be NULL) already filled with -1.  *n_chains / *n_pixels are valid when true is returned.
 SDM_EDR_HD inline bool EdRouteFixed(int W, int H, const int16_t* G, uint8_t* F, int grad_thresh, uint8_t* scratch, const EdRouteCaps& caps,
                                     int32_t* out_offsets, uint32_t* out_pixels, int32_t* edge_index, size_t edge_step, int* n_chains,
-                                    int* n_pixels)
+                                    int* n_pixels, int presorted = -1 /* see EdRouteAnchorSlots */)
 {
     using namespace ed_detail;
     uint8_t* p = scratch;
@@ -540,7 +552,7 @@ SDM_EDR_HD inline bool EdRouteFixed(int W, int H, const int16_t* G, uint8_t* F, 
     FixedVec<int32_t> offs(out_offsets, caps.offsets);
     FixedVec<uint32_t> px(out_pixels, caps.out_pixels);
     const bool ok = EdRouteCore(W, H, G, F, grad_thresh, found, anchors, chains, pixels, seg, stack, best, order, nos, offs, px,
-                                edge_index, edge_step, hist);
+                                edge_index, edge_step, hist, presorted);
     *n_chains = offs.size() - 1;
     *n_pixels = px.size();
     return ok;
