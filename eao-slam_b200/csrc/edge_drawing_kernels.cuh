@@ -379,6 +379,7 @@ struct EdRouteBatch {
     uint32_t* pixels;      // [n][caps.out_pixels]
     int32_t* edge_index;   // [n][H][W] or NULL
     int4* result;          // [n]
+    long long* prof;       // [n][8] or NULL: cycles of {edge fill + anchor sort, pass over the anchors, walks, extraction}, walked pixels, trees
 };
 
 __global__ void __launch_bounds__(32) k_ed_route(EdRouteBatch b)
@@ -390,6 +391,7 @@ __global__ void __launch_bounds__(32) k_ed_route(EdRouteBatch b)
     uint8_t* F = b.F + (size_t)img * P;
     uint8_t* scratch = b.scratch + (size_t)img * b.scratch_stride;
     int32_t* edge = b.edge_index ? b.edge_index + (size_t)img * P : nullptr;
+    const long long t_start = clock64();
     if (edge) {
         if ((P & 3) == 0) {
             int4* e4 = reinterpret_cast<int4*>(edge);
@@ -400,12 +402,32 @@ __global__ void __launch_bounds__(32) k_ed_route(EdRouteBatch b)
     }
     // ---- the anchors in walking order - decreasing gradient, raster order among equals - by the whole warp: a stable
     // counting sort over the 2048 gradient values (one thread doing this alone pays two dependent memory round trips per
-    // anchor, twice: half of the kernel's time in its first form).  Lane l looks at pixel i0 + l, so lane order = raster order.
+    // anchor, twice: a quarter of the kernel's time in its first form).  Lane l holds 16 consecutive pixels of a 512-pixel
+    // window (one 16-byte load of the flags, two of the gradients, all in flight together), so raster order = lane order,
+    // then byte order.
     for (int k = lane; k < 2048; k += 32) hist[k] = 0;
     __syncwarp();
-    for (size_t i0 = 0; i0 < P; i0 += 32) {
-        const size_t i = i0 + lane;
-        if (i < P && (F[i] & kEdFlagAnchor)) atomicAdd(&hist[2047 - min((int)G[i], 2047)], 1);
+    const bool wide = (P & 15) == 0;  // (plane bases are 256-byte aligned and P is a multiple of 16: aligned 16-byte loads)
+    const size_t win = wide ? 512 : 32;
+    for (size_t i0 = 0; i0 < P; i0 += win) {
+        if (wide) {
+            const size_t i = i0 + 16 * (size_t)lane;
+            if (i < P) {
+                const uint4 f = *reinterpret_cast<const uint4*>(F + i);
+                const uint32_t fw[4] = {f.x, f.y, f.z, f.w};
+                if ((f.x | f.y | f.z | f.w) & 0x80808080u) {
+                    const uint4 g0 = *reinterpret_cast<const uint4*>(G + i), g1 = *reinterpret_cast<const uint4*>(G + i + 8);
+                    const uint32_t gw[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+#pragma unroll
+                    for (int k = 0; k < 16; ++k)
+                        if ((fw[k >> 2] >> (8 * (k & 3))) & 0x80u)
+                            atomicAdd(&hist[2047 - min((int)(short)((gw[k >> 1] >> (16 * (k & 1))) & 0xffffu), 2047)], 1);
+                }
+            }
+        } else {
+            const size_t i = i0 + lane;
+            if (i < P && (F[i] & kEdFlagAnchor)) atomicAdd(&hist[2047 - min((int)G[i], 2047)], 1);
+        }
     }
     __syncwarp();
     int total;
@@ -424,26 +446,59 @@ __global__ void __launch_bounds__(32) k_ed_route(EdRouteBatch b)
         return;
     }
     int* anchors = sdm_host::EdRouteAnchorSlots(scratch, b.caps);
-    for (size_t i0 = 0; i0 < P; i0 += 32) {
-        const size_t i = i0 + lane;
-        const bool is_anchor = i < P && (F[i] & kEdFlagAnchor);
-        const unsigned m = __ballot_sync(0xffffffffu, is_anchor);
-        if (is_anchor) {
-            const int key = 2047 - min((int)G[i], 2047);
-            const unsigned peers = __match_any_sync(m, key);   // the lanes of this group with the same gradient
-            const int leader = __ffs(peers) - 1;
-            int pos = 0;
-            if (lane == leader) { pos = hist[key]; hist[key] = pos + __popc(peers); }
-            pos = __shfl_sync(peers, pos, leader);
-            anchors[pos + __popc(peers & ((1u << lane) - 1u))] = (int)i;
+    for (size_t i0 = 0; i0 < P; i0 += win) {
+        if (wide) {
+            const size_t i = i0 + 16 * (size_t)lane;
+            uint32_t fw[4] = {0, 0, 0, 0}, gw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            bool any = false;
+            if (i < P) {
+                const uint4 f = *reinterpret_cast<const uint4*>(F + i);
+                fw[0] = f.x; fw[1] = f.y; fw[2] = f.z; fw[3] = f.w;
+                any = ((f.x | f.y | f.z | f.w) & 0x80808080u) != 0;
+                if (any) {
+                    const uint4 g0 = *reinterpret_cast<const uint4*>(G + i), g1 = *reinterpret_cast<const uint4*>(G + i + 8);
+                    gw[0] = g0.x; gw[1] = g0.y; gw[2] = g0.z; gw[3] = g0.w; gw[4] = g1.x; gw[5] = g1.y; gw[6] = g1.z; gw[7] = g1.w;
+                }
+            }
+            // the lanes that hold anchors take their turn in lane order; a lane places its own anchors in byte order
+            unsigned m = __ballot_sync(0xffffffffu, any);
+            while (m) {
+                const int turn = __ffs(m) - 1;
+                if (lane == turn) {
+#pragma unroll
+                    for (int k = 0; k < 16; ++k)
+                        if ((fw[k >> 2] >> (8 * (k & 3))) & 0x80u) {
+                            const int key = 2047 - min((int)(short)((gw[k >> 1] >> (16 * (k & 1))) & 0xffffu), 2047);
+                            anchors[hist[key]++] = (int)(i + k);
+                        }
+                }
+                __syncwarp();
+                m &= m - 1;
+            }
+        } else {
+            const size_t i = i0 + lane;
+            const bool is_anchor = i < P && (F[i] & kEdFlagAnchor);
+            const unsigned m = __ballot_sync(0xffffffffu, is_anchor);
+            if (is_anchor) {
+                const int key = 2047 - min((int)G[i], 2047);
+                const unsigned peers = __match_any_sync(m, key);   // the lanes of this group with the same gradient
+                const int leader = __ffs(peers) - 1;
+                int pos = 0;
+                if (lane == leader) { pos = hist[key]; hist[key] = pos + __popc(peers); }
+                pos = __shfl_sync(peers, pos, leader);
+                anchors[pos + __popc(peers & ((1u << lane) - 1u))] = (int)i;
+            }
+            __syncwarp();
         }
-        __syncwarp();
     }
     __syncwarp();
     if (lane == 0) {
         int nc = 0, np = 0;
+        long long* prof = b.prof ? b.prof + (size_t)img * 8 : nullptr;
+        if (prof) prof[5] = clock64() - t_start;
         const bool ok = sdm_host::EdRouteFixed(b.W, b.H, G, F, b.grad_thresh, scratch, b.caps, b.offsets + (size_t)img * b.caps.offsets,
-                                               b.pixels + (size_t)img * b.caps.out_pixels, edge, (size_t)b.W * 4, &nc, &np, total);
+                                               b.pixels + (size_t)img * b.caps.out_pixels, edge, (size_t)b.W * 4, &nc, &np, total, prof);
+        if (prof) prof[6] = clock64() - t_start;
         b.result[img] = make_int4(nc, np, ok ? 1 : 0, 0);
     }
 }

@@ -1755,7 +1755,7 @@ constexpr int kEdDevBatch = 1024;  // images routed by one k_ed_route launch (27
 // sections of the device block of the routing kernel for `cap` images
 struct EdRouteLayout {
     sdm_host::EdRouteCaps caps;
-    size_t scratch_stride, o_scratch, o_off, o_px, o_edge, o_res, o_at, bytes;
+    size_t scratch_stride, o_scratch, o_off, o_px, o_edge, o_res, o_at, o_prof, bytes;
     EdRouteLayout(int cap, size_t P)
     {
         caps = sdm_host::EdRouteCapsFor(P);
@@ -1770,7 +1770,8 @@ struct EdRouteLayout {
         o_edge = ed_align(o_px + (size_t)cap * caps.out_pixels * 4);
         o_res = ed_align(o_edge + (size_t)cap * P * 4);
         o_at = ed_align(o_res + (size_t)cap * sizeof(int4));
-        bytes = ed_align(o_at + ((size_t)cap + 1) * sizeof(unsigned long long));
+        o_prof = ed_align(o_at + ((size_t)cap + 1) * sizeof(unsigned long long));
+        bytes = ed_align(o_prof + (size_t)cap * 8 * sizeof(long long));
     }
 };
 
@@ -1847,6 +1848,8 @@ int ed_run_device(sdm_ctx* c, int n, const sdm_ed_image* images, int grad_thresh
         b.pixels = (uint32_t*)(c->edr_dev + L.o_px);
         b.edge_index = want_edge ? (int32_t*)(c->edr_dev + L.o_edge) : nullptr;
         b.result = (int4*)(c->edr_dev + L.o_res);
+        const bool prof = getenv("SDM_ED_ROUTE_PROF") != nullptr;  // per-image cycle counts of the routing kernel on stderr
+        b.prof = prof ? (long long*)(c->edr_dev + L.o_prof) : nullptr;
         unsigned long long* at_dev = (unsigned long long*)(c->edr_dev + L.o_at);
         CU(cudaEventRecord(c->edr_ev[0], c->s_ed));
         sdm::k_ed_route<<<nb, 32, 0, c->s_ed>>>(b);
@@ -1895,6 +1898,16 @@ int ed_run_device(sdm_ctx* c, int n, const sdm_ed_image* images, int grad_thresh
         c->ed_kernel_ms += ms;
         CU(cudaEventElapsedTime(&ms, c->edr_ev[0], c->edr_ev[1]));
         c->ed_route_ms += ms;
+        if (prof) {
+            std::vector<long long> h((size_t)nb * 8);
+            CU(cudaMemcpy(h.data(), b.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+            double mean[8] = {0}, mx[8] = {0};
+            for (int i = 0; i < nb; ++i)
+                for (int k = 0; k < 8; ++k) { mean[k] += (double)h[(size_t)i * 8 + k] / nb; mx[k] = std::max(mx[k], (double)h[(size_t)i * 8 + k]); }
+            fprintf(stderr, "k_ed_route %d images, %.2f ms: mean / max kcycles: sort %.0f / %.0f, anchor pass %.0f / %.0f, walks %.0f / %.0f, extraction %.0f / %.0f, "
+                            "whole %.0f / %.0f; walked pixels %.0f / %.0f, trees %.0f / %.0f\n", nb, ms, mean[5] / 1e3, mx[5] / 1e3, mean[0] / 1e3, mx[0] / 1e3,
+                    mean[1] / 1e3, mx[1] / 1e3, mean[2] / 1e3, mx[2] / 1e3, mean[6] / 1e3, mx[6] / 1e3, mean[3], mx[3], mean[4], mx[4]);
+        }
         // images that ran out of a capacity on the device: stage 1 again (the planes are spent), stage 2 on the host
         for (int i = 0; i < nb; ++i) {
             if (c->edr_result_host[i].z) continue;

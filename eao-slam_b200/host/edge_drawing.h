@@ -52,12 +52,20 @@ struct EdgeChains {
 #if defined(__CUDACC__)
 #define SDM_EDR_HD __host__ __device__
 #define SDM_EDR_UNROLL4 _Pragma("unroll 4")
+#define SDM_EDR_UNROLL8 _Pragma("unroll 8")
+#if defined(__CUDA_ARCH__)
+#define SDM_EDR_CLOCK() clock64()
+#else
+#define SDM_EDR_CLOCK() 0ll
+#endif
 // the routing templates are __host__ __device__ and are instantiated on std::vector for the host threads: nvcc warns about the
 // host-only calls of that (host-only) instantiation
 #pragma nv_diag_suppress 20011, 20014
 #else
 #define SDM_EDR_HD
 #define SDM_EDR_UNROLL4
+#define SDM_EDR_UNROLL8
+#define SDM_EDR_CLOCK() 0ll
 #endif
 
 namespace ed_detail {
@@ -243,7 +251,8 @@ template <class IntVec, class ChainVec, class PxVec, class TodoVec, class OffVec
 SDM_EDR_HD inline bool EdRouteCore(int W, int H, const int16_t* G, uint8_t* F, int grad_thresh, IntVec& found, IntVec& anchors,
                                    ChainVec& chains, PxVec& pixels, PxVec& seg, TodoVec& stack, IntVec& best, IntVec& order, IntVec& nos,
                                    OffVec& out_offsets, PixVec& out_pixels, int32_t* edge_index, size_t edge_step, int* hist /* [2049] */,
-                                   int presorted = -1 /* >= 0: `anchors` already holds that many positions in walking order */)
+                                   int presorted = -1 /* >= 0: `anchors` already holds that many positions in walking order */,
+                                   long long* prof = nullptr /* device: cycles {anchor scan, walks, extraction}, walked pixels, trees */)
 {
     using namespace ed_detail;
     out_offsets.clear();
@@ -330,9 +339,29 @@ SDM_EDR_HD inline bool EdRouteCore(int W, int H, const int16_t* G, uint8_t* F, i
         c_.len = 0; /* copied */                                                                                             \
     } while (0)
 
+    long long t_walk = 0, t_extract = 0, n_walked = 0, n_trees = 0;
+    const long long t_begin = SDM_EDR_CLOCK();
+    // The pass over the anchor list reads eight positions and their flags at a time (independent loads, in flight together).
+    // An anchor flag is only ever cleared: a clear bit in the batch's copy is final; a set bit is read again if a walk has
+    // run since the batch was loaded.
+    int batch_pos[8];
+    uint8_t batch_flag[8];
+    bool walked_since = false;
     for (int a = 0; a < anchors.size(); ++a) {
-        const int ay = anchors[a] / W, ax = anchors[a] % W;
-        if (!IS_ANCHOR(ay, ax)) continue;
+        const int ab = a & 7;
+        if (ab == 0) {
+            const int nb8 = anchors.size() - a < 8 ? anchors.size() - a : 8;
+            SDM_EDR_UNROLL8
+            for (int k = 0; k < 8; ++k) batch_pos[k] = k < nb8 ? anchors[a + k] : 0;
+            SDM_EDR_UNROLL8
+            for (int k = 0; k < 8; ++k) batch_flag[k] = F[batch_pos[k]];
+            walked_since = false;
+        }
+        if (!(batch_flag[ab] & kEdFlagAnchor)) continue;
+        const int ay = batch_pos[ab] / W, ax = batch_pos[ab] % W;
+        if (walked_since && !IS_ANCHOR(ay, ax)) continue;
+        walked_since = true;
+        const long long t_a = SDM_EDR_CLOCK();
         chains.clear();
         pixels.clear();
         stack.clear();
@@ -419,9 +448,14 @@ SDM_EDR_HD inline bool EdRouteCore(int W, int H, const int16_t* G, uint8_t* F, i
             chains[no].len = clen;
             chains[t.parent].child[child] = no;
         }
+        const long long t_b = SDM_EDR_CLOCK();
+        t_walk += t_b - t_a;
+        n_walked += pixels.size();
+        ++n_trees;
         if (pixels.size() - dup < 10) {  // too short: take the walk back
             SDM_EDR_UNROLL4
             for (int i = 0; i < pixels.size(); ++i) FL(pixels[i].r, pixels[i].c) &= kEdDirMask;
+            t_extract += SDM_EDR_CLOCK() - t_b;
             continue;
         }
         best.resize(chains.size());  // (every entry is written before it is read inside one longest_chain call)
@@ -463,7 +497,15 @@ SDM_EDR_HD inline bool EdRouteCore(int W, int H, const int16_t* G, uint8_t* F, i
                 SDM_EDR_EMIT();
             }
         }
+        t_extract += SDM_EDR_CLOCK() - t_b;
         if (SDM_EDR_OVERFLOW()) return false;
+    }
+    if (prof) {
+        prof[0] = SDM_EDR_CLOCK() - t_begin - t_walk - t_extract;  // the pass over the anchor list
+        prof[1] = t_walk;
+        prof[2] = t_extract;
+        prof[3] = n_walked;
+        prof[4] = n_trees;
     }
     return !SDM_EDR_OVERFLOW();
 #undef SDM_EDR_EMIT
@@ -535,7 +577,7 @@ SDM_EDR_HD inline int* EdRouteAnchorSlots(uint8_t* scratch, const EdRouteCaps& c
 // edge_index (may be NULL) already filled with -1.  *n_chains / *n_pixels are valid when true is returned.
 SDM_EDR_HD inline bool EdRouteFixed(int W, int H, const int16_t* G, uint8_t* F, int grad_thresh, uint8_t* scratch, const EdRouteCaps& caps,
                                     int32_t* out_offsets, uint32_t* out_pixels, int32_t* edge_index, size_t edge_step, int* n_chains,
-                                    int* n_pixels, int presorted = -1 /* see EdRouteAnchorSlots */)
+                                    int* n_pixels, int presorted = -1 /* see EdRouteAnchorSlots */, long long* prof = nullptr)
 {
     using namespace ed_detail;
     uint8_t* p = scratch;
@@ -552,7 +594,7 @@ SDM_EDR_HD inline bool EdRouteFixed(int W, int H, const int16_t* G, uint8_t* F, 
     FixedVec<int32_t> offs(out_offsets, caps.offsets);
     FixedVec<uint32_t> px(out_pixels, caps.out_pixels);
     const bool ok = EdRouteCore(W, H, G, F, grad_thresh, found, anchors, chains, pixels, seg, stack, best, order, nos, offs, px,
-                                edge_index, edge_step, hist, presorted);
+                                edge_index, edge_step, hist, presorted, prof);
     *n_chains = offs.size() - 1;
     *n_pixels = px.size();
     return ok;
