@@ -384,7 +384,8 @@ struct EdRouteBatch {
 
 __global__ void __launch_bounds__(32) k_ed_route(EdRouteBatch b)
 {
-    __shared__ int hist[2048];
+    __shared__ __align__(16) int hist[2048];
+    static_assert(sizeof(int) * 2048 >= sdm_host::kEdRouteFastBytes, "the fast block of EdRouteFixed reuses the histogram");
     const int img = blockIdx.x, lane = threadIdx.x;
     const size_t P = (size_t)b.W * b.H;
     const int16_t* G = b.G + (size_t)img * P;
@@ -414,9 +415,9 @@ __global__ void __launch_bounds__(32) k_ed_route(EdRouteBatch b)
             const size_t i = i0 + 16 * (size_t)lane;
             if (i < P) {
                 const uint4 f = *reinterpret_cast<const uint4*>(F + i);
+                const uint4 g0 = *reinterpret_cast<const uint4*>(G + i), g1 = *reinterpret_cast<const uint4*>(G + i + 8);  // (with f: one round trip)
                 const uint32_t fw[4] = {f.x, f.y, f.z, f.w};
                 if ((f.x | f.y | f.z | f.w) & 0x80808080u) {
-                    const uint4 g0 = *reinterpret_cast<const uint4*>(G + i), g1 = *reinterpret_cast<const uint4*>(G + i + 8);
                     const uint32_t gw[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
 #pragma unroll
                     for (int k = 0; k < 16; ++k)
@@ -453,10 +454,10 @@ __global__ void __launch_bounds__(32) k_ed_route(EdRouteBatch b)
             bool any = false;
             if (i < P) {
                 const uint4 f = *reinterpret_cast<const uint4*>(F + i);
+                const uint4 g0 = *reinterpret_cast<const uint4*>(G + i), g1 = *reinterpret_cast<const uint4*>(G + i + 8);
                 fw[0] = f.x; fw[1] = f.y; fw[2] = f.z; fw[3] = f.w;
                 any = ((f.x | f.y | f.z | f.w) & 0x80808080u) != 0;
                 if (any) {
-                    const uint4 g0 = *reinterpret_cast<const uint4*>(G + i), g1 = *reinterpret_cast<const uint4*>(G + i + 8);
                     gw[0] = g0.x; gw[1] = g0.y; gw[2] = g0.z; gw[3] = g0.w; gw[4] = g1.x; gw[5] = g1.y; gw[6] = g1.z; gw[7] = g1.w;
                 }
             }
@@ -497,7 +498,8 @@ __global__ void __launch_bounds__(32) k_ed_route(EdRouteBatch b)
         long long* prof = b.prof ? b.prof + (size_t)img * 8 : nullptr;
         if (prof) prof[5] = clock64() - t_start;
         const bool ok = sdm_host::EdRouteFixed(b.W, b.H, G, F, b.grad_thresh, scratch, b.caps, b.offsets + (size_t)img * b.caps.offsets,
-                                               b.pixels + (size_t)img * b.caps.out_pixels, edge, (size_t)b.W * 4, &nc, &np, total, prof);
+                                               b.pixels + (size_t)img * b.caps.out_pixels, edge, (size_t)b.W * 4, &nc, &np, total, prof,
+                                               reinterpret_cast<uint8_t*>(hist) /* the sort is done with it: the tree's lists */);
         if (prof) prof[6] = clock64() - t_start;
         b.result[img] = make_int4(nc, np, ok ? 1 : 0, 0);
     }
