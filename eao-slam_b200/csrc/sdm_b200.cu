@@ -290,6 +290,7 @@ struct sdm_ctx {
     int4* edr_result_host = nullptr;
     int edr_cap = 0;
     int edr_fallbacks = 0;
+    int edr_last_base = 0, edr_last_n = 0;  // images of the last device-routed batch whose edge-index planes are still in edr_dev
     cudaEvent_t edr_ev[2] = {nullptr, nullptr};
     void* peer_rs[kMaxPeers] = {nullptr};
     // sdm_exchange: flag blocks (own + IPC-mapped peers), halo plan, step counter
@@ -920,7 +921,7 @@ int sdm_upload_keyframes(sdm_ctx* c, int n, const sdm_upload_desc* d)
                 RC(copy2d(st.grad, row, u.grad, u.grad_step, row, H, cudaMemcpyHostToDevice, c->s_copy));
                 RC(copy2d(st.theta, row, u.theta, u.theta_step, row, H, cudaMemcpyHostToDevice, c->s_copy));
             }
-            if (u.edge) RC(copy2d(st.edge, row, u.edge, u.edge_step, row, H, cudaMemcpyHostToDevice, c->s_copy));
+            if (u.edge) RC(copy2d(st.edge, row, u.edge, u.edge_step, row, H, cudaMemcpyDefault, c->s_copy));  // host or device plane
             need_down = std::max(need_down, std::max(c->kf[u.kf].down_ds_id, c->kf[u.kf].down_cp_id));
         }
         trace_end(c, c->s_copy);
@@ -1812,6 +1813,7 @@ int ed_run_device(sdm_ctx* c, int n, const sdm_ed_image* images, int grad_thresh
     const size_t list_room = (size_t)(c->ed_dev + ed_bytes(c->ed_cap, P) - (uint8_t*)dv.G) / 4;  // int32 the G / F planes hold
     unsigned long long* at_host = reinterpret_cast<unsigned long long*>(c->edr_result_host + c->edr_cap);
     c->edr_fallbacks = 0;
+    c->edr_last_n = 0;
     res->blob_chains.assign((size_t)n, -1);
     res->at.assign((size_t)n, 0);
     for (int base = 0; base < n; base += cap) {
@@ -1846,7 +1848,7 @@ int ed_run_device(sdm_ctx* c, int n, const sdm_ed_image* images, int grad_thresh
         b.caps = L.caps;
         b.offsets = (int32_t*)(c->edr_dev + L.o_off);
         b.pixels = (uint32_t*)(c->edr_dev + L.o_px);
-        b.edge_index = want_edge ? (int32_t*)(c->edr_dev + L.o_edge) : nullptr;
+        b.edge_index = (int32_t*)(c->edr_dev + L.o_edge);  // always: sdm_ed_device_edge_plane hands them to sdm_upload_keyframes
         b.result = (int4*)(c->edr_dev + L.o_res);
         const bool prof = getenv("SDM_ED_ROUTE_PROF") != nullptr;  // per-image cycle counts of the routing kernel on stderr
         b.prof = prof ? (long long*)(c->edr_dev + L.o_prof) : nullptr;
@@ -1917,9 +1919,16 @@ int ed_run_device(sdm_ctx* c, int n, const sdm_ed_image* images, int grad_thresh
             CU(cudaMemcpyAsync(hv.F + (size_t)i * P, dv.F + (size_t)i * P, P, cudaMemcpyDeviceToHost, c->s_ed));
             CU(cudaStreamSynchronize(c->s_ed));
             const sdm_ed_image& im = images[base + i];
+            std::vector<int32_t> plane((size_t)P);  // the device's copy of the plane comes from the host routing as well
             sdm_host::EdRouteChains(W, H, hv.G + (size_t)i * P, hv.F + (size_t)i * P, grad_thresh, res->chains[(size_t)(base + i)],
-                                    im.edge_index, im.edge_step);
+                                    plane.data(), (size_t)W * 4);
+            if (im.edge_index)
+                for (int y = 0; y < H; ++y)
+                    std::memcpy(reinterpret_cast<char*>(im.edge_index) + (size_t)y * im.edge_step, plane.data() + (size_t)y * W, (size_t)W * 4);
+            CU(cudaMemcpy(b.edge_index + (size_t)i * P, plane.data(), P * 4, cudaMemcpyHostToDevice));
         }
+        c->edr_last_base = base;
+        c->edr_last_n = nb;
     }
     return SDM_OK;
 }
@@ -1935,6 +1944,18 @@ int sdm_set_edge_drawing_route(sdm_ctx* c, int mode)
 }
 
 int sdm_last_edge_drawing_fallbacks(sdm_ctx* c) { return c ? c->edr_fallbacks : 0; }
+
+int sdm_ed_device_edge_plane(sdm_ctx* c, int i, const int32_t** dev_plane)
+{
+    if (!c || !dev_plane) return fail(SDM_ERR_ARG, "sdm_ed_device_edge_plane: null argument");
+    *dev_plane = nullptr;
+    if (!c->edr_dev || i < c->edr_last_base || i >= c->edr_last_base + c->edr_last_n)
+        return fail(SDM_ERR_STATE, "sdm_ed_device_edge_plane: image %d is not in the last batch routed on the device (%d .. %d)", i,
+                    c->edr_last_base, c->edr_last_base + c->edr_last_n - 1);
+    const EdRouteLayout L(c->edr_cap, c->npix);
+    *dev_plane = (const int32_t*)(c->edr_dev + L.o_edge) + (size_t)(i - c->edr_last_base) * c->npix;
+    return SDM_OK;
+}
 
 int sdm_edge_drawing(sdm_ctx* c, int n, const sdm_ed_image* images, int grad_thresh, int anchor_thresh, int n_threads,
                      sdm_ed_result** result)

@@ -123,8 +123,15 @@ struct FixedVec {
     {
         if (count > cap - n) { ovf = true; return; }
         T* d = p + n;
-        SDM_EDR_UNROLL4
-        for (int i = 0; i < count; ++i) d[i] = src[(ptrdiff_t)i * step];
+        int i = 0;
+        for (; i + 8 <= count; i += 8) {  // eight loads, then eight stores (src and d may alias for all the compiler knows)
+            T v[8];
+            SDM_EDR_UNROLL8
+            for (int k = 0; k < 8; ++k) v[k] = src[(ptrdiff_t)(i + k) * step];
+            SDM_EDR_UNROLL8
+            for (int k = 0; k < 8; ++k) d[i + k] = v[k];
+        }
+        for (; i < count; ++i) d[i] = src[(ptrdiff_t)i * step];
         n += count;
     }
     SDM_EDR_HD bool overflow() const { return ovf; }
@@ -335,12 +342,22 @@ SDM_EDR_HD inline bool EdRouteCore(int W, int H, const int16_t* G, uint8_t* F, i
         const int base_ = out_pixels.size(), cnt_ = seg.size();                                                              \
         out_pixels.resize(base_ + cnt_);                                                                                     \
         if (!out_pixels.overflow()) {                                                                                        \
-            SDM_EDR_UNROLL4                                                                                                  \
-            for (int i_ = 0; i_ < cnt_; ++i_) out_pixels[base_ + i_] = ((uint32_t)seg[i_].r << 16) | (uint32_t)seg[i_].c;    \
-            if (edge_index) {                                                                                                \
-                SDM_EDR_UNROLL4                                                                                              \
-                for (int i_ = 0; i_ < cnt_; ++i_)                                                                            \
-                    reinterpret_cast<int32_t*>(reinterpret_cast<char*>(edge_index) + (size_t)seg[i_].r * edge_step)[seg[i_].c] = id; \
+            int i_ = 0;                                                                                                      \
+            for (; i_ + 8 <= cnt_; i_ += 8) { /* eight loads, then the stores */                                             \
+                Px v_[8];                                                                                                    \
+                SDM_EDR_UNROLL8                                                                                              \
+                for (int k_ = 0; k_ < 8; ++k_) v_[k_] = seg[i_ + k_];                                                        \
+                SDM_EDR_UNROLL8                                                                                              \
+                for (int k_ = 0; k_ < 8; ++k_) {                                                                             \
+                    out_pixels[base_ + i_ + k_] = ((uint32_t)v_[k_].r << 16) | (uint32_t)v_[k_].c;                           \
+                    if (edge_index)                                                                                          \
+                        reinterpret_cast<int32_t*>(reinterpret_cast<char*>(edge_index) + (size_t)v_[k_].r * edge_step)[v_[k_].c] = id; \
+                }                                                                                                            \
+            }                                                                                                                \
+            for (; i_ < cnt_; ++i_) {                                                                                        \
+                const Px v_ = seg[i_];                                                                                       \
+                out_pixels[base_ + i_] = ((uint32_t)v_.r << 16) | (uint32_t)v_.c;                                            \
+                if (edge_index) reinterpret_cast<int32_t*>(reinterpret_cast<char*>(edge_index) + (size_t)v_.r * edge_step)[v_.c] = id; \
             }                                                                                                                \
         }                                                                                                                    \
         out_offsets.push_back((int32_t)out_pixels.size());                                                                   \
@@ -431,9 +448,10 @@ SDM_EDR_HD inline bool EdRouteCore(int W, int H, const int16_t* G, uint8_t* F, i
                 // forward neighbours: straight, the diagonal on the `fwd` side, the other diagonal
                 const uint8_t f0 = F[nx], f1 = F[nx + fwd * across], f2 = F[nx - fwd * across];
                 const int gA = G[nx - across], gB = G[nx], gC = G[nx + across];
+                const uint8_t s0 = F[at - across], s1 = F[at + across];  // (all eight loads before the first store: one round trip)
                 F[at] = (uint8_t)((fcur & kEdDirMask) | kEdFlagEdge);
-                F[at - across] &= (uint8_t)~kEdFlagAnchor;
-                F[at + across] &= (uint8_t)~kEdFlagAnchor;
+                F[at - across] = (uint8_t)(s0 & ~kEdFlagAnchor);
+                F[at + across] = (uint8_t)(s1 & ~kEdFlagAnchor);
                 int side;  // -1 / 0 / +1: offset across the walk of the pixel taken
                 if (f0 & (kEdFlagAnchor | kEdFlagEdge)) side = 0;
                 else if (f1 & (kEdFlagAnchor | kEdFlagEdge)) side = fwd;
@@ -476,8 +494,21 @@ SDM_EDR_HD inline bool EdRouteCore(int W, int H, const int16_t* G, uint8_t* F, i
         n_walked += pixels.size();
         ++n_trees;
         if (pixels.size() - dup < 10) {  // too short: take the walk back
-            SDM_EDR_UNROLL4
-            for (int i = 0; i < pixels.size(); ++i) FL(pixels[i].r, pixels[i].c) &= kEdDirMask;
+            {
+                int i = 0;
+                for (; i + 4 <= pixels.size(); i += 4) {  // positions, then flags, then the stores: two round trips per four pixels
+                    size_t q[4];
+                    uint8_t v[4];
+                    SDM_EDR_UNROLL4
+                    for (int k = 0; k < 4; ++k) q[k] = (size_t)pixels[i + k].r * W + pixels[i + k].c;
+                    SDM_EDR_UNROLL4
+                    for (int k = 0; k < 4; ++k) v[k] = F[q[k]];
+                    // (a pixel may be in the list twice - the pixel a chain turned at starts both children: the stores are idempotent)
+                    SDM_EDR_UNROLL4
+                    for (int k = 0; k < 4; ++k) F[q[k]] = (uint8_t)(v[k] & kEdDirMask);
+                }
+                for (; i < pixels.size(); ++i) FL(pixels[i].r, pixels[i].c) &= kEdDirMask;
+            }
             t_extract += SDM_EDR_CLOCK() - t_b;
             continue;
         }

@@ -99,7 +99,7 @@ EXPORTS = [
     "sdm_inter_check", "sdm_last_pass_ms", "sdm_launch_count", "sdm_last_timing", "sdm_last_pack_ms", "sdm_mark", "sdm_elapsed_ms",
     "sdm_line_fit", "sdm_last_line_fit_ms", "sdm_last_scan_long",
     "sdm_edge_drawing", "sdm_ed_chains", "sdm_ed_free", "sdm_last_edge_drawing_ms", "sdm_ed_planes",
-    "sdm_set_edge_drawing_route", "sdm_last_edge_drawing_fallbacks",
+    "sdm_set_edge_drawing_route", "sdm_last_edge_drawing_fallbacks", "sdm_ed_device_edge_plane",
 ]
 
 _lib = None
@@ -132,6 +132,7 @@ def load() -> C.CDLL:
     lib.sdm_last_edge_drawing_ms.argtypes = [vp, fp, fp, fp]
     lib.sdm_set_edge_drawing_route.argtypes = [vp, C.c_int]
     lib.sdm_last_edge_drawing_fallbacks.argtypes = [vp]
+    lib.sdm_ed_device_edge_plane.argtypes = [vp, C.c_int, C.POINTER(vp)]
     lib.sdm_ed_planes.argtypes = [vp, vp, sz, C.c_int, C.c_int, vp, vp]
     lib.sdm_host_alloc.argtypes = [C.POINTER(vp), sz]
     lib.sdm_host_free.argtypes = [vp]
@@ -272,9 +273,10 @@ class Context:
             edge.ctypes.data if edge is not None else None, edge.strides[0] if edge is not None else 0,
             _fp(Kf), _fp(Tf)))
 
-    def upload_descs(self, scene, indices, slot_of=None, images_only=False):
+    def upload_descs(self, scene, indices, slot_of=None, images_only=False, edge_dev=None):
         """sdm_upload_desc array for keyframes `indices` of a scene (arrays must stay alive until synchronize).
-        images_only: leave grad / theta NULL so that the planes are produced on the device."""
+        images_only: leave grad / theta NULL so that the planes are produced on the device.
+        edge_dev: per entry the device address of its edge-index plane (ed_device_edge_plane) instead of scene.edge."""
         idx = list(indices)
         arr = (UploadDesc * len(idx))()
         for a, i in zip(arr, idx):
@@ -283,7 +285,9 @@ class Context:
             if not images_only:
                 a.grad, a.grad_step = scene.grad[i].ctypes.data, scene.grad[i].strides[0]
                 a.theta, a.theta_step = scene.theta[i].ctypes.data, scene.theta[i].strides[0]
-            if scene.edge is not None:
+            if edge_dev is not None:
+                a.edge, a.edge_step = int(edge_dev[idx.index(i)]), 4 * self.W
+            elif scene.edge is not None:
                 a.edge, a.edge_step = scene.edge[i].ctypes.data, scene.edge[i].strides[0]
             for j, v in enumerate(scene.K):
                 a.K[j] = float(v)
@@ -446,6 +450,12 @@ class Context:
     def set_edge_drawing_route(self, device: bool):
         """stage 2 of edge_drawing on host threads (False, default) or on the device, one warp per image (True)"""
         self._chk(self.lib.sdm_set_edge_drawing_route(self.h, 1 if device else 0))
+
+    def ed_device_edge_plane(self, i: int) -> int:
+        """device address of kf->mEdgeIndex of image i of the last device-routed edge_drawing batch (an `edge` plane for uploads)"""
+        p = C.c_void_p()
+        self._chk(self.lib.sdm_ed_device_edge_plane(self.h, int(i), C.byref(p)))
+        return int(p.value)
 
     def last_edge_drawing_fallbacks(self) -> int:
         return int(self.lib.sdm_last_edge_drawing_fallbacks(self.h))

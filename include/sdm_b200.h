@@ -136,7 +136,7 @@ typedef struct {
     const uint8_t* im;    size_t im_step;
     const float* grad;    size_t grad_step;
     const float* theta;   size_t theta_step;
-    const int32_t* edge;  size_t edge_step; /* edge may be NULL */
+    const int32_t* edge;  size_t edge_step; /* edge may be NULL; host plane or device plane (sdm_ed_device_edge_plane) */
     float K[4];
     float Tcw[12];
 } sdm_upload_desc;
@@ -283,6 +283,12 @@ void sdm_ed_free(sdm_ed_result* result);
 enum { SDM_ED_ROUTE_HOST = 0, SDM_ED_ROUTE_DEVICE = 1 };
 int sdm_set_edge_drawing_route(sdm_ctx* ctx, int mode);
 int sdm_last_edge_drawing_fallbacks(sdm_ctx* ctx);
+/* SDM_ED_ROUTE_DEVICE keeps kf->mEdgeIndex of every image of its last batch on the device (dense int32 plane, row pitch
+ * 4 * width): *dev_plane is a DEVICE pointer that sdm_upload_desc.edge / sdm_upload_keyframe's edge accept like a host
+ * plane (edge_step = 4 * width), so the candidate mask of :454 goes from the detector to the packing kernel without
+ * crossing PCIe (images[i].edge_index may then be NULL).  Valid until the next sdm_edge_drawing or sdm_destroy on this
+ * context; calls with more than 1024 images keep the last 1024-image batch only. */
+int sdm_ed_device_edge_plane(sdm_ctx* ctx, int i, const int32_t** dev_plane);
 /* timing of the last sdm_edge_drawing: device time of its k_ed_planes launches, host wall time of the call, and the
  * summed thread time of the routing walks - in SDM_ED_ROUTE_DEVICE mode the device time of k_ed_route (all ms; any
  * pointer may be NULL) */

@@ -156,6 +156,39 @@ def test_device_route_falls_back_to_the_host_when_a_capacity_runs_out(scene, mon
         assert np.array_equal(edge[i], w), i
 
 
+def test_mask_goes_from_the_detector_to_the_loop_on_the_device():
+    """SDM_ED_ROUTE_DEVICE keeps kf->mEdgeIndex on the device; sdm_upload_keyframes takes the device planes as `edge`
+    (sdm_ed_device_edge_plane).  Both passes over images + device masks give the planes of the same loop fed with the
+    host copies of those masks, bit for bit - and the masks are the library's (the golden chains)."""
+    from sdmb200 import api, synth
+    n, W, H, N = 12, 320, 240, 6
+    sc = synth.make_scene(n, W, H, N, seed=23)
+    items = api.make_items(range(n), sc.nbr_idx, sc.rot, sc.min_depth, sc.max_depth)
+    with api.Context(width=W, height=H, max_keyframes=n) as ctx:
+        ctx.set_edge_drawing_route(True)
+        offs, pix, edge = ctx.edge_drawing(sc.im)
+        assert ctx.last_edge_drawing_fallbacks() == 0 and (edge >= 0).sum() > 10000
+        dev = [ctx.ed_device_edge_plane(i) for i in range(n)]
+        with pytest.raises(api.SdmError):
+            ctx.ed_device_edge_plane(n)
+        ctx.upload_keyframes(ctx.upload_descs(sc, range(n), images_only=True, edge_dev=dev))
+        ctx.pass1(items); ctx.pass2(items)
+        def planes():
+            per = [ctx.download(i) for i in range(n)]
+            return {k: np.stack([q[k] for q in per]) for k in ("depth", "sigma", "checked", "points")}
+        got = planes()
+        cands = [ctx.candidate_count(i) for i in range(n)]
+        sce = synth.Scene(im=sc.im, grad=sc.grad, theta=sc.theta, edge=edge, K=sc.K, Tcw=sc.Tcw, nbr_idx=sc.nbr_idx, rot=sc.rot,
+                          min_depth=sc.min_depth, max_depth=sc.max_depth)
+        ctx.upload_keyframes(ctx.upload_descs(sce, range(n), images_only=True))
+        ctx.pass1(items); ctx.pass2(items)
+        want = planes()
+        assert cands == [ctx.candidate_count(i) for i in range(n)] and 0 < sum(cands) < (edge >= 0).sum() + 1
+    for k in ("depth", "sigma", "checked", "points"):
+        assert np.array_equal(got[k].view(np.uint32), want[k].view(np.uint32)), k
+    assert (want["checked"] > 0).sum() > 1000 and not (want["checked"] > 0)[edge < 0].any()
+
+
 def test_argument_errors():
     from sdmb200 import api
     with ctx_for(64, 48) as ctx:
