@@ -728,6 +728,38 @@ def main_ours(a, rank, world, local_rank):
             e2e[name + "_points"] = int(tot.value)
         if e2e["image_points"] != e2e["export_points"]:
             print(f"WARNING: device-produced planes gave {e2e['image_points']} points, uploaded planes {e2e['export_points']}", file=sys.stderr)
+        if world == 1 and not host_exchange:
+            # the reference's complete loop: it detects the edge map of every keyframe inside pass 1 (ProbabilityMapping.cc:394,
+            # LineDetector::DetectEdgeMap -> closed-source EDLib.a) and only edge pixels are candidates (:454).  Here: im_ up,
+            # sdm_edge_drawing with the routing walks on the device, the masks handed to the upload as device planes
+            # (sdm_ed_device_edge_plane), both passes, the point cloud back.
+            ctx.set_edge_drawing_route(True)
+            ed_imgs = (api.EdImage * n_loc)()
+            for i in range(n_loc):
+                ed_imgs[i].im, ed_imgs[i].im_step = h_im[i].ctypes.data, h_im[i].strides[0]
+            up_edge = ctx.upload_descs(sc, range(n_loc), images_only=True)
+            ed_ms = []
+
+            def edge_step():
+                res = C.c_void_p()
+                chk(lib.sdm_edge_drawing(ctx.h, n_loc, ed_imgs, 36, 8, 0, C.byref(res)))
+                lib.sdm_ed_free(res)
+                ed_ms.append(ctx.last_edge_drawing_ms()["wall_ms"])
+                for i in range(n_loc):
+                    up_edge[i].edge, up_edge[i].edge_step = ctx.ed_device_edge_plane(i), 4 * W
+                export_step(up_edge)
+            edge_step()
+            e2e["edge_candidates"] = int(sum(ctx.candidate_count(s) for s in owned))
+            ed_ms.clear()
+            tt = time.perf_counter()
+            for _ in range(a.steps):
+                edge_step()
+            e2e["edge_sec"] = (time.perf_counter() - tt) / a.steps
+            e2e["edge_points"] = int(tot.value)
+            e2e["edge_drawing_ms"] = float(np.mean(ed_ms))
+            e2e["edge_fallbacks"] = ctx.last_edge_drawing_fallbacks()
+            ctx.set_edge_drawing_route(False)
+            upload(); ctx.synchronize()  # back to the bench's own planes and mask for what follows
     if rank == 0:
         clocks.stop()
 
@@ -843,6 +875,15 @@ def main_ours(a, rank, world, local_rank):
                 "d2h_bytes_per_step": 16 * e2e["image_points"],
                 "note": "as e2e_point_export, but only im_ is uploaded: GradImg / GradTheta (KeyFrame.cc:69-74) are "
                         "produced on the device by k_pack_image"}
+        if "edge_sec" in e2e:
+            line["e2e_image_in_edge_drawing_points_out"] = {
+                "ms_per_step": 1e3 * e2e["edge_sec"], "edge_drawing_ms_per_step": e2e["edge_drawing_ms"],
+                "value": e2e["edge_candidates"] / e2e["edge_sec"], "unit": UNIT, "candidates_per_step": e2e["edge_candidates"],
+                "points_per_step": e2e["edge_points"], "h2d_bytes_per_step": int(n_loc * W * H), "d2h_bytes_per_step": 16 * e2e["edge_points"],
+                "host_routed_keyframes": e2e["edge_fallbacks"],
+                "note": "the reference's complete loop, detector included (DetectEdgeMap inside pass 1, ProbabilityMapping.cc:394: only edge "
+                        "pixels are candidates, :454): im_ up, sdm_edge_drawing with the routing walks on the device (k_ed_planes4, k_ed_route), "
+                        "kf->mEdgeIndex handed to the packing kernel as a device plane, both passes, sdm_export_points"}
     line["scan_generation"] = ctx.scan_generation()
     line["scan_long_build"] = ctx.last_scan_long()
     if world == 1 and do_e2e and not a.no_e2e_variants:
@@ -864,8 +905,21 @@ def main_ours(a, rank, world, local_rank):
                                                     "frac": 4.0 * W * H / k_s / 1e9 / peak},
                                 "routing_thread_ms_per_keyframe": best["route_thread_ms"] / n_ed,
                                 "chains": int(sum(len(o) - 1 for o in offs)),
+                                "device_route": None,
                                 "api": "sdm_edge_drawing: smoothing / Sobel / direction / anchors on the device (k_ed_planes4, 4 algorithmic "
                                        "bytes per pixel), the sequential routing walk on host threads; chains identical to the reference's EDLib.a"}
+        ctx.set_edge_drawing_route(True)  # stage 2 in k_ed_route (one warp per keyframe) instead of host threads
+        ctx.edge_drawing(ims[:32], edge_index=False)
+        best = None
+        for _ in range(3):
+            ctx.edge_drawing(ims, edge_index=False)
+            t = ctx.last_edge_drawing_ms()
+            if best is None or t["wall_ms"] < best["wall_ms"]:
+                best = t
+        line["edge_drawing"]["device_route"] = {"wall_ms_per_keyframe": best["wall_ms"] / n_ed, "route_kernel_ms": best["route_thread_ms"],
+                                                "host_routed_keyframes": ctx.last_edge_drawing_fallbacks(),
+                                                "note": "chains only (the mask stays on the device); one launch walks all keyframes at once, "
+                                                        "its duration is that of the slowest image"}
     ctx.close()
     if world == 1 and do_e2e and not a.no_e2e_variants:
         r = class_e2e(a, sc, n_loc)
