@@ -733,31 +733,38 @@ def main_ours(a, rank, world, local_rank):
             # LineDetector::DetectEdgeMap -> closed-source EDLib.a) and only edge pixels are candidates (:454).  Here: im_ up,
             # sdm_edge_drawing with the routing walks on the device, the masks handed to the upload as device planes
             # (sdm_ed_device_edge_plane), both passes, the point cloud back.
-            ctx.set_edge_drawing_route(True)
             ed_imgs = (api.EdImage * n_loc)()
             for i in range(n_loc):
                 ed_imgs[i].im, ed_imgs[i].im_step = h_im[i].ctypes.data, h_im[i].strides[0]
             up_edge = ctx.upload_descs(sc, range(n_loc), images_only=True)
+            h_edge = pinned(lib, (n_loc, H, W), np.int32, keep)
             ed_ms = []
 
-            def edge_step():
+            def edge_step(on_device):
+                # on_device: routing walks in k_ed_route, masks stay on the device; else host threads, masks through pinned planes
+                for i in range(n_loc):
+                    ed_imgs[i].edge_index, ed_imgs[i].edge_step = (None, 0) if on_device else (h_edge[i].ctypes.data, 4 * W)
                 res = C.c_void_p()
                 chk(lib.sdm_edge_drawing(ctx.h, n_loc, ed_imgs, 36, 8, 0, C.byref(res)))
                 lib.sdm_ed_free(res)
                 ed_ms.append(ctx.last_edge_drawing_ms()["wall_ms"])
                 for i in range(n_loc):
-                    up_edge[i].edge, up_edge[i].edge_step = ctx.ed_device_edge_plane(i), 4 * W
+                    up_edge[i].edge, up_edge[i].edge_step = (ctx.ed_device_edge_plane(i) if on_device else h_edge[i].ctypes.data), 4 * W
                 export_step(up_edge)
-            edge_step()
-            e2e["edge_candidates"] = int(sum(ctx.candidate_count(s) for s in owned))
-            ed_ms.clear()
-            tt = time.perf_counter()
-            for _ in range(a.steps):
-                edge_step()
-            e2e["edge_sec"] = (time.perf_counter() - tt) / a.steps
-            e2e["edge_points"] = int(tot.value)
-            e2e["edge_drawing_ms"] = float(np.mean(ed_ms))
-            e2e["edge_fallbacks"] = ctx.last_edge_drawing_fallbacks()
+            for on_device in (True, False):
+                ctx.set_edge_drawing_route(on_device)
+                edge_step(on_device)
+                key = "edge_dev" if on_device else "edge_host"
+                e2e[key + "_candidates"] = int(sum(ctx.candidate_count(s) for s in owned))
+                ed_ms.clear()
+                tt = time.perf_counter()
+                for _ in range(a.steps):
+                    edge_step(on_device)
+                e2e[key + "_sec"] = (time.perf_counter() - tt) / a.steps
+                e2e[key + "_points"] = int(tot.value)
+                e2e[key + "_ed_ms"] = float(np.mean(ed_ms))
+                if on_device:
+                    e2e["edge_fallbacks"] = ctx.last_edge_drawing_fallbacks()
             ctx.set_edge_drawing_route(False)
             upload(); ctx.synchronize()  # back to the bench's own planes and mask for what follows
     if rank == 0:
@@ -875,15 +882,23 @@ def main_ours(a, rank, world, local_rank):
                 "d2h_bytes_per_step": 16 * e2e["image_points"],
                 "note": "as e2e_point_export, but only im_ is uploaded: GradImg / GradTheta (KeyFrame.cc:69-74) are "
                         "produced on the device by k_pack_image"}
-        if "edge_sec" in e2e:
+        if "edge_dev_sec" in e2e:
+            best = "edge_dev" if e2e["edge_dev_sec"] <= e2e["edge_host_sec"] else "edge_host"
             line["e2e_image_in_edge_drawing_points_out"] = {
-                "ms_per_step": 1e3 * e2e["edge_sec"], "edge_drawing_ms_per_step": e2e["edge_drawing_ms"],
-                "value": e2e["edge_candidates"] / e2e["edge_sec"], "unit": UNIT, "candidates_per_step": e2e["edge_candidates"],
-                "points_per_step": e2e["edge_points"], "h2d_bytes_per_step": int(n_loc * W * H), "d2h_bytes_per_step": 16 * e2e["edge_points"],
-                "host_routed_keyframes": e2e["edge_fallbacks"],
+                "ms_per_step": 1e3 * e2e[best + "_sec"], "edge_drawing_ms_per_step": e2e[best + "_ed_ms"],
+                "routing": "device (k_ed_route)" if best == "edge_dev" else "host threads",
+                "value": e2e[best + "_candidates"] / e2e[best + "_sec"], "unit": UNIT, "candidates_per_step": e2e[best + "_candidates"],
+                "points_per_step": e2e[best + "_points"], "d2h_bytes_per_step": 16 * e2e[best + "_points"],
+                "routing_on_device": {"ms_per_step": 1e3 * e2e["edge_dev_sec"], "edge_drawing_ms_per_step": e2e["edge_dev_ed_ms"],
+                                      "h2d_bytes_per_step": int(n_loc * W * H), "host_routed_keyframes": e2e["edge_fallbacks"],
+                                      "same_result": bool(e2e["edge_dev_points"] == e2e["edge_host_points"] and
+                                                          e2e["edge_dev_candidates"] == e2e["edge_host_candidates"])},
+                "routing_on_host_threads": {"ms_per_step": 1e3 * e2e["edge_host_sec"], "edge_drawing_ms_per_step": e2e["edge_host_ed_ms"],
+                                            "h2d_bytes_per_step": int(5 * n_loc * W * H), "d2h_bytes_extra_per_step": int(3 * n_loc * W * H)},
                 "note": "the reference's complete loop, detector included (DetectEdgeMap inside pass 1, ProbabilityMapping.cc:394: only edge "
-                        "pixels are candidates, :454): im_ up, sdm_edge_drawing with the routing walks on the device (k_ed_planes4, k_ed_route), "
-                        "kf->mEdgeIndex handed to the packing kernel as a device plane, both passes, sdm_export_points"}
+                        "pixels are candidates, :454): im_ up, sdm_edge_drawing, kf->mEdgeIndex to the packing kernel (a device plane when the "
+                        "routing walks run on the device, a pinned host plane when they run on host threads), both passes, sdm_export_points; "
+                        "the faster routing mode at this batch size is the line's value"}
     line["scan_generation"] = ctx.scan_generation()
     line["scan_long_build"] = ctx.last_scan_long()
     if world == 1 and do_e2e and not a.no_e2e_variants:
