@@ -528,11 +528,12 @@ __global__ void __launch_bounds__(1024) k_ed_chain_offsets(const int4* __restric
     if (i == n - 1) at[n] = excl + v;
 }
 
-__global__ void __launch_bounds__(256) k_ed_chain_gather(EdRouteBatch b, const unsigned long long* __restrict__ at, int32_t* __restrict__ dst)
+__global__ void __launch_bounds__(256) k_ed_chain_gather(EdRouteBatch b, const unsigned long long* __restrict__ at, int32_t* __restrict__ dst,
+                                                         unsigned long long room /* int32 the block holds */)
 {
     const int img = blockIdx.y;
     const int4 r = b.result[img];
-    if (!r.z) return;
+    if (!r.z || at[img] + (unsigned long long)r.x + 1ull + (unsigned long long)r.y > room) return;  // (the host checks the total)
     const int32_t* off = b.offsets + (size_t)img * b.caps.offsets;
     const uint32_t* px = b.pixels + (size_t)img * b.caps.out_pixels;
     int32_t* d = dst + at[img];

@@ -1785,7 +1785,11 @@ int edr_reserve(sdm_ctx* c, int n_img)
     if (c->edr_result_host) cudaFreeHost(c->edr_result_host);
     c->edr_dev = nullptr; c->edr_result_host = nullptr; c->edr_cap = 0;
     const EdRouteLayout L(n_img, c->npix);
-    CU(cudaMalloc((void**)&c->edr_dev, L.bytes));
+    if (cudaMalloc((void**)&c->edr_dev, L.bytes) != cudaSuccess) {  // the caller retries with a smaller batch
+        cudaGetLastError();
+        c->edr_dev = nullptr;
+        return fail(SDM_ERR_NOMEM, "sdm_edge_drawing: %zu bytes of routing buffers for %d images do not fit the device", L.bytes, n_img);
+    }
     CU(cudaMallocHost((void**)&c->edr_result_host, (size_t)n_img * sizeof(int4) + ((size_t)n_img + 1) * sizeof(unsigned long long)));
     c->edr_cap = n_img;
     return SDM_OK;
@@ -1800,9 +1804,14 @@ int ed_run_device(sdm_ctx* c, int n, const sdm_ed_image* images, int grad_thresh
     const int W = c->cfg.width, H = c->cfg.height;
     const size_t P = c->npix;
     CU(cudaSetDevice(c->cfg.device));
-    const int cap = std::min(n, kEdDevBatch);
+    int cap = std::min(n, kEdDevBatch);
     RC(ed_reserve(c, cap));
-    RC(edr_reserve(c, cap));
+    for (;;) {  // 25 bytes per pixel and image: halve the batch until the buffers fit beside the keyframe arena
+        const int rrc = edr_reserve(c, cap);
+        if (rrc == SDM_OK) break;
+        if (rrc != SDM_ERR_NOMEM || cap == 1) return rrc;
+        cap = (cap + 1) / 2;
+    }
     while ((int)c->ed_ev.size() < 3) {
         cudaEvent_t e;
         CU(cudaEventCreate(&e));
@@ -1859,7 +1868,7 @@ int ed_run_device(sdm_ctx* c, int n, const sdm_ed_image* images, int grad_thresh
         CU(cudaEventRecord(c->edr_ev[1], c->s_ed));
         sdm::k_ed_chain_offsets<<<1, 1024, 0, c->s_ed>>>(b.result, nb, at_dev);
         CU(cudaGetLastError());
-        sdm::k_ed_chain_gather<<<dim3(8, nb), 256, 0, c->s_ed>>>(b, at_dev, (int32_t*)dv.G);
+        sdm::k_ed_chain_gather<<<dim3(8, nb), 256, 0, c->s_ed>>>(b, at_dev, (int32_t*)dv.G, (unsigned long long)list_room);
         CU(cudaGetLastError());
         c->launches += 3;
         CU(cudaMemcpyAsync(c->edr_result_host, b.result, (size_t)nb * sizeof(int4), cudaMemcpyDeviceToHost, c->s_ed));
@@ -1972,6 +1981,8 @@ int sdm_edge_drawing(sdm_ctx* c, int n, const sdm_ed_image* images, int grad_thr
     if (!res) return fail(SDM_ERR_NOMEM, "out of host memory");
     res->chains.resize((size_t)n);
     c->ed_kernel_ms = c->ed_wall_ms = c->ed_route_ms = 0.f;
+    c->edr_last_n = 0;  // (sdm_ed_device_edge_plane: the planes of an earlier call are no longer handed out)
+    c->edr_fallbacks = 0;
     if (n == 0) { *result = res; return SDM_OK; }
     const auto wall0 = std::chrono::steady_clock::now();
     if (c->ed_route_mode == SDM_ED_ROUTE_DEVICE) {
