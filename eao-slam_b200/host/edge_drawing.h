@@ -439,39 +439,47 @@ SDM_EDR_HD inline bool EdRouteCore(int W, int H, const int16_t* G, uint8_t* F, i
             // next step (nothing this step writes touches them): one round trip to memory per step instead of a chain of
             // dependent ones - what a step costs on the device, where a load is an L2 access.
             const int want = horizontal ? kEdgeHorizontal : kEdgeVertical;
-            const ptrdiff_t along = horizontal ? (ptrdiff_t)fwd : (ptrdiff_t)fwd * W;  // one pixel forward
-            const ptrdiff_t across = horizontal ? (ptrdiff_t)W : (ptrdiff_t)1;         // one pixel down / right
-            size_t at = (size_t)r * W + c;
-            uint8_t fcur = F[at];
+            // offsets in pixels (the planes hold fewer than 2^31): one pixel forward, one pixel down / right, the two diagonals
+            const int along = horizontal ? fwd : fwd * W, across = horizontal ? W : 1;
+            const int o_f1 = along + fwd * across, o_f2 = along - fwd * across, o_gA = along - across, o_gC = along + across;
+            const uint8_t* pf = F + ((size_t)r * W + c);
+            const int16_t* pg = G + ((size_t)r * W + c);
+            uint8_t fcur = *pf;
+            bool full = false;
             while ((fcur & kEdDirMask) == want) {
-                const size_t nx = at + along;
                 // forward neighbours: straight, the diagonal on the `fwd` side, the other diagonal
-                const uint8_t f0 = F[nx], f1 = F[nx + fwd * across], f2 = F[nx - fwd * across];
-                const int gA = G[nx - across], gB = G[nx], gC = G[nx + across];
-                const uint8_t s0 = F[at - across], s1 = F[at + across];  // (all eight loads before the first store: one round trip)
-                F[at] = (uint8_t)((fcur & kEdDirMask) | kEdFlagEdge);
-                F[at - across] = (uint8_t)(s0 & ~kEdFlagAnchor);
-                F[at + across] = (uint8_t)(s1 & ~kEdFlagAnchor);
+                const uint8_t f0 = pf[along], f1 = pf[o_f1], f2 = pf[o_f2];
+                const int gA = pg[o_gA], gB = pg[along], gC = pg[o_gC];
+                const uint8_t s0 = pf[-across], s1 = pf[across];  // (all eight loads before the first store: one round trip)
+                uint8_t* wf = const_cast<uint8_t*>(pf);
+                wf[0] = (uint8_t)((fcur & kEdDirMask) | kEdFlagEdge);
+                wf[-across] = (uint8_t)(s0 & ~kEdFlagAnchor);
+                wf[across] = (uint8_t)(s1 & ~kEdFlagAnchor);
                 int side;  // -1 / 0 / +1: offset across the walk of the pixel taken
                 if (f0 & (kEdFlagAnchor | kEdFlagEdge)) side = 0;
                 else if (f1 & (kEdFlagAnchor | kEdFlagEdge)) side = fwd;
                 else if (f2 & (kEdFlagAnchor | kEdFlagEdge)) side = -fwd;
                 else if (gA > gB) side = gA > gC ? -1 : 1;
                 else side = gC > gB ? 1 : 0;
-                at = nx + side * across;
+                const int step = along + side * across;
+                pf += step;
+                pg += step;
                 if (horizontal) { r += side; c += fwd; } else { r += fwd; c += side; }
                 fcur = side == 0 ? f0 : (side == fwd ? f1 : f2);
                 const int gcur = side == 0 ? gB : (side < 0 ? gA : gC);
                 if ((fcur & kEdFlagEdge) || gcur < grad_thresh) {  // met an edge or left the gradient ridge
-                    chains[no].len = clen;
-                    chains[t.parent].child[child] = no;
                     ended = true;
                     break;
                 }
                 Px pn = {r, c};
                 pixels.push_back(pn);
-                if (pixels.overflow()) return false;
+                if (pixels.overflow()) { full = true; break; }  // (one-level exits only inside the step loop: it is the hot path)
                 ++clen;
+            }
+            if (full) return false;
+            if (ended) {
+                chains[no].len = clen;
+                chains[t.parent].child[child] = no;
             }
             if (ended) continue;
             // the edge turns: the last pixel opens the two walks across the old direction and belongs to them
