@@ -384,8 +384,7 @@ struct EdRouteBatch {
 
 __global__ void __launch_bounds__(32) k_ed_route(EdRouteBatch b)
 {
-    __shared__ __align__(16) int hist[2048];
-    static_assert(sizeof(int) * 2048 >= sdm_host::kEdRouteFastBytes, "the fast block of EdRouteFixed reuses the histogram");
+    __shared__ int hist[2048];
     const int img = blockIdx.x, lane = threadIdx.x;
     const size_t P = (size_t)b.W * b.H;
     const int16_t* G = b.G + (size_t)img * P;
@@ -498,8 +497,7 @@ __global__ void __launch_bounds__(32) k_ed_route(EdRouteBatch b)
         long long* prof = b.prof ? b.prof + (size_t)img * 8 : nullptr;
         if (prof) prof[5] = clock64() - t_start;
         const bool ok = sdm_host::EdRouteFixed(b.W, b.H, G, F, b.grad_thresh, scratch, b.caps, b.offsets + (size_t)img * b.caps.offsets,
-                                               b.pixels + (size_t)img * b.caps.out_pixels, edge, (size_t)b.W * 4, &nc, &np, total, prof,
-                                               reinterpret_cast<uint8_t*>(hist) /* the sort is done with it: the tree's lists */);
+                                               b.pixels + (size_t)img * b.caps.out_pixels, edge, (size_t)b.W * 4, &nc, &np, total, prof);
         if (prof) prof[6] = clock64() - t_start;
         b.result[img] = make_int4(nc, np, ok ? 1 : 0, 0);
     }

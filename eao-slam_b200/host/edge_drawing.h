@@ -137,29 +137,6 @@ struct FixedVec {
     SDM_EDR_HD bool overflow() const { return ovf; }
 };
 
-// FixedVec whose first `kfast` elements live in a second, faster block (shared memory on the device: the chains, the open
-// walks and the work lists of ONE tree are small - a dozen chains on average - and are read by pointer chasing, where every
-// access to global memory is a full round trip)
-template <class T>
-struct HybridVec {
-    T* fast;
-    T* slow;
-    int kfast, n, cap;
-    bool ovf;
-    SDM_EDR_HD HybridVec(T* fast_mem, int fast_count, T* slow_mem, int capacity)
-        : fast(fast_mem), slow(slow_mem), kfast(fast_mem ? fast_count : 0), n(0), cap(capacity), ovf(false) {}
-    SDM_EDR_HD int size() const { return n; }
-    SDM_EDR_HD bool empty() const { return n == 0; }
-    SDM_EDR_HD void clear() { n = 0; }
-    SDM_EDR_HD T& operator[](int i) { return i < kfast ? fast[i] : slow[i]; }
-    SDM_EDR_HD const T& operator[](int i) const { return i < kfast ? fast[i] : slow[i]; }
-    SDM_EDR_HD void push_back(const T& x) { if (n < cap) { (*this)[n] = x; ++n; } else ovf = true; }
-    SDM_EDR_HD void pop_back() { if (n > 0) --n; }
-    SDM_EDR_HD T& back() { return (*this)[n > 0 ? n - 1 : 0]; }
-    SDM_EDR_HD void resize(int m) { if (m <= cap) n = m; else { n = cap; ovf = true; } }
-    SDM_EDR_HD bool overflow() const { return ovf; }
-};
-
 // length of the longest path below `root`; every visited chain keeps only the child on that path (first child on ties).
 // Iterative post-order (the trees of a textured image are thousands of chains deep).
 template <class ChainVec, class IntVec>
@@ -637,32 +614,22 @@ SDM_EDR_HD inline int* EdRouteAnchorSlots(uint8_t* scratch, const EdRouteCaps& c
 }
 // scratch: EdRouteScratchBytes(caps) bytes, 16-byte aligned; out_offsets[caps.offsets], out_pixels[caps.out_pixels];
 // edge_index (may be NULL) already filled with -1.  *n_chains / *n_pixels are valid when true is returned.
-// bytes of fast memory EdRouteFixed can use (see HybridVec): 160 chains, 64 open walks, 3 x 256 work-list entries
-enum { kEdRouteFastChains = 160, kEdRouteFastStack = 64, kEdRouteFastLists = 256, kEdRouteFastBytes = 160 * 24 + 64 * 16 + 3 * 256 * 4 };
 SDM_EDR_HD inline bool EdRouteFixed(int W, int H, const int16_t* G, uint8_t* F, int grad_thresh, uint8_t* scratch, const EdRouteCaps& caps,
                                     int32_t* out_offsets, uint32_t* out_pixels, int32_t* edge_index, size_t edge_step, int* n_chains,
-                                    int* n_pixels, int presorted = -1 /* see EdRouteAnchorSlots */, long long* prof = nullptr,
-                                    uint8_t* fast = nullptr /* kEdRouteFastBytes, 16-byte aligned, or NULL */)
+                                    int* n_pixels, int presorted = -1 /* see EdRouteAnchorSlots */, long long* prof = nullptr)
 {
     using namespace ed_detail;
-    static_assert(sizeof(Chain) == 24 && sizeof(Todo) == 16, "layout of the fast block");
     uint8_t* p = scratch;
     FixedVec<int> found(reinterpret_cast<int*>(p), caps.anchors);      p += EdRouteAlign((size_t)caps.anchors * sizeof(int));
     FixedVec<int> anchors(reinterpret_cast<int*>(p), caps.anchors);    p += EdRouteAlign((size_t)caps.anchors * sizeof(int));
-    Chain* chains_mem = reinterpret_cast<Chain*>(p);                   p += EdRouteAlign((size_t)caps.chains * sizeof(Chain));
+    FixedVec<Chain> chains(reinterpret_cast<Chain*>(p), caps.chains);  p += EdRouteAlign((size_t)caps.chains * sizeof(Chain));
     FixedVec<Px> pixels(reinterpret_cast<Px*>(p), caps.pixels);        p += EdRouteAlign((size_t)caps.pixels * sizeof(Px));
     FixedVec<Px> seg(reinterpret_cast<Px*>(p), caps.pixels);           p += EdRouteAlign((size_t)caps.pixels * sizeof(Px));
-    Todo* stack_mem = reinterpret_cast<Todo*>(p);                      p += EdRouteAlign((size_t)caps.chains * sizeof(Todo));
-    int* best_mem = reinterpret_cast<int*>(p);                         p += EdRouteAlign((size_t)caps.chains * sizeof(int));
-    int* order_mem = reinterpret_cast<int*>(p);                        p += EdRouteAlign((size_t)caps.chains * sizeof(int));
-    int* nos_mem = reinterpret_cast<int*>(p);                          p += EdRouteAlign((size_t)caps.chains * sizeof(int));
+    FixedVec<Todo> stack(reinterpret_cast<Todo*>(p), caps.chains);     p += EdRouteAlign((size_t)caps.chains * sizeof(Todo));
+    FixedVec<int> best(reinterpret_cast<int*>(p), caps.chains);        p += EdRouteAlign((size_t)caps.chains * sizeof(int));
+    FixedVec<int> order(reinterpret_cast<int*>(p), caps.chains);       p += EdRouteAlign((size_t)caps.chains * sizeof(int));
+    FixedVec<int> nos(reinterpret_cast<int*>(p), caps.chains);         p += EdRouteAlign((size_t)caps.chains * sizeof(int));
     int* hist = reinterpret_cast<int*>(p);
-    uint8_t* f = fast;
-    HybridVec<Chain> chains(reinterpret_cast<Chain*>(f), kEdRouteFastChains, chains_mem, caps.chains);  if (f) f += kEdRouteFastChains * sizeof(Chain);
-    HybridVec<Todo> stack(reinterpret_cast<Todo*>(f), kEdRouteFastStack, stack_mem, caps.chains);       if (f) f += kEdRouteFastStack * sizeof(Todo);
-    HybridVec<int> best(reinterpret_cast<int*>(f), kEdRouteFastLists, best_mem, caps.chains);           if (f) f += kEdRouteFastLists * sizeof(int);
-    HybridVec<int> order(reinterpret_cast<int*>(f), kEdRouteFastLists, order_mem, caps.chains);         if (f) f += kEdRouteFastLists * sizeof(int);
-    HybridVec<int> nos(reinterpret_cast<int*>(f), kEdRouteFastLists, nos_mem, caps.chains);
     FixedVec<int32_t> offs(out_offsets, caps.offsets);
     FixedVec<uint32_t> px(out_pixels, caps.out_pixels);
     const bool ok = EdRouteCore(W, H, G, F, grad_thresh, found, anchors, chains, pixels, seg, stack, best, order, nos, offs, px,

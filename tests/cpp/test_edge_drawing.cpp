@@ -58,10 +58,7 @@ int main(int argc, char** argv)
             std::vector<int32_t> fo_(caps.offsets), edge2((size_t)W * H, -1);
             std::vector<uint32_t> fp_(caps.out_pixels);
             int nc = -1, np = -1;
-            // (odd images: with the fast block of the tree-local lists, as the kernel runs it; even images: without)
-            alignas(16) static uint8_t fast[sdm_host::kEdRouteFastBytes];
-            const bool ok = sdm_host::EdRouteFixed(W, H, G.data(), F.data(), 36, sp, caps, fo_.data(), fp_.data(), edge2.data(), (size_t)W * 4, &nc, &np,
-                                                   -1, NULL, (i & 1) ? fast : NULL);
+            const bool ok = sdm_host::EdRouteFixed(W, H, G.data(), F.data(), 36, sp, caps, fo_.data(), fp_.data(), edge2.data(), (size_t)W * 4, &nc, &np);
             if (!ok || nc != ch.n_chains() || np != (int)ch.pixels.size() || !std::equal(ch.offsets.begin(), ch.offsets.end(), fo_.begin()) ||
                 !std::equal(ch.pixels.begin(), ch.pixels.end(), fp_.begin()) || edge2 != edge) {
                 fprintf(stderr, "fixed-capacity routing differs at image %d (ok %d, chains %d / %d, pixels %d / %d)\n", i, (int)ok, nc,
