@@ -1896,8 +1896,8 @@ int ed_run_device(sdm_ctx* c, int n, const sdm_ed_image* images, int grad_thresh
         if (total > 0) CU(cudaMemcpyAsync(hv.G, dv.G, total * 4, cudaMemcpyDeviceToHost, c->s_ed));
         CU(cudaStreamSynchronize(c->s_ed));
         const size_t blob0 = res->blob.size();
-        res->blob.resize(blob0 + total);
-        if (total > 0) std::memcpy(res->blob.data() + blob0, hv.G, total * 4);
+        if (total > 0)  // (one pass: no zero-fill before the copy)
+            res->blob.insert(res->blob.end(), reinterpret_cast<const int32_t*>(hv.G), reinterpret_cast<const int32_t*>(hv.G) + total);
         for (int i = 0; i < nb; ++i) {
             const int4 r = c->edr_result_host[i];
             if (!r.z) continue;
