@@ -360,46 +360,11 @@ k_ed_planes(const uint8_t* __restrict__ im, int W, int H, int grad_thresh, int a
     }
 }
 
-// ---- stage 2 on the device: one warp per image ------------------------------------------------------------------------------
-// The routing walk is sequential per image (a step depends on the marks the previous walks left), so an image is one thread's
-// work: lane 0 of the image's warp runs sdm_host::EdRouteFixed - the same source the host threads run, on fixed arrays in
-// global memory - after the 32 lanes have filled the image's edge-index plane with -1.  One warp per block: the device takes
-// 32 resident images per SM, 4736 in flight on a B200; a step costs a few dependent L2 / HBM round trips (about 1 us), which
-// only pays when many images are routed at once - the host threads need 1.4 ms per image and thread, but there are 16-32 of
-// them against thousands of warps.  result[img] = {chains, chain pixels, 1 if complete (0: a capacity ran out, the host routes
-// the image instead), 0}.
-struct EdRouteBatch {
-    int W, H, grad_thresh;
-    const int16_t* G;      // [n][H][W] stage-1 planes
-    uint8_t* F;            // [n][H][W], modified in place
-    uint8_t* scratch;      // n * scratch_stride bytes
-    size_t scratch_stride;
-    sdm_host::EdRouteCaps caps;
-    int32_t* offsets;      // [n][caps.offsets]
-    uint32_t* pixels;      // [n][caps.out_pixels]
-    int32_t* edge_index;   // [n][H][W] or NULL
-    int4* result;          // [n]
-    long long* prof;       // [n][8] or NULL: cycles of {edge fill + anchor sort, pass over the anchors, walks, extraction}, walked pixels, trees
-};
-
-__global__ void __launch_bounds__(32) k_ed_route(EdRouteBatch b)
+// The anchors of one image in walking order - decreasing gradient, raster order among equals - by a whole warp; hist = 2048
+// ints of shared memory.  Returns their number, or -1 (and writes nothing) if the list holds fewer than that.
+__device__ __forceinline__ int ed_warp_sort_anchors(const uint8_t* __restrict__ F, const int16_t* __restrict__ G, size_t P, int* hist,
+                                                    int* __restrict__ anchors, int cap, int lane)
 {
-    __shared__ int hist[2048];
-    const int img = blockIdx.x, lane = threadIdx.x;
-    const size_t P = (size_t)b.W * b.H;
-    const int16_t* G = b.G + (size_t)img * P;
-    uint8_t* F = b.F + (size_t)img * P;
-    uint8_t* scratch = b.scratch + (size_t)img * b.scratch_stride;
-    int32_t* edge = b.edge_index ? b.edge_index + (size_t)img * P : nullptr;
-    const long long t_start = clock64();
-    if (edge) {
-        if ((P & 3) == 0) {
-            int4* e4 = reinterpret_cast<int4*>(edge);
-            for (size_t i = lane; i < P / 4; i += 32) e4[i] = make_int4(-1, -1, -1, -1);
-        } else {
-            for (size_t i = lane; i < P; i += 32) edge[i] = -1;
-        }
-    }
     // ---- the anchors in walking order - decreasing gradient, raster order among equals - by the whole warp: a stable
     // counting sort over the 2048 gradient values (one thread doing this alone pays two dependent memory round trips per
     // anchor, twice: a quarter of the kernel's time in its first form).  Lane l holds 16 consecutive pixels of a 512-pixel
@@ -441,11 +406,7 @@ __global__ void __launch_bounds__(32) k_ed_route(EdRouteBatch b)
         total = __shfl_sync(0xffffffffu, incl, 31);
     }
     __syncwarp();
-    if (total > b.caps.anchors) {  // (cannot happen with EdRouteCapsFor's P / 2; the host routes the image if it does)
-        if (lane == 0) b.result[img] = make_int4(0, 0, 0, 0);
-        return;
-    }
-    int* anchors = sdm_host::EdRouteAnchorSlots(scratch, b.caps);
+    if (total > cap) return -1;  // the caller's list is too short: nothing is written
     for (size_t i0 = 0; i0 < P; i0 += win) {
         if (wide) {
             const size_t i = i0 + 16 * (size_t)lane;
@@ -492,6 +453,54 @@ __global__ void __launch_bounds__(32) k_ed_route(EdRouteBatch b)
         }
     }
     __syncwarp();
+    return total;
+}
+
+// ---- stage 2 on the device: one warp per image ------------------------------------------------------------------------------
+// The routing walk is sequential per image (a step depends on the marks the previous walks left), so an image is one thread's
+// work: lane 0 of the image's warp runs sdm_host::EdRouteFixed - the same source the host threads run, on fixed arrays in
+// global memory - after the 32 lanes have filled the image's edge-index plane with -1.  One warp per block: the device takes
+// 32 resident images per SM, 4736 in flight on a B200; a step costs a few dependent L2 / HBM round trips (about 1 us), which
+// only pays when many images are routed at once - the host threads need 1.4 ms per image and thread, but there are 16-32 of
+// them against thousands of warps.  result[img] = {chains, chain pixels, 1 if complete (0: a capacity ran out, the host routes
+// the image instead), 0}.
+struct EdRouteBatch {
+    int W, H, grad_thresh;
+    const int16_t* G;      // [n][H][W] stage-1 planes
+    uint8_t* F;            // [n][H][W], modified in place
+    uint8_t* scratch;      // n * scratch_stride bytes
+    size_t scratch_stride;
+    sdm_host::EdRouteCaps caps;
+    int32_t* offsets;      // [n][caps.offsets]
+    uint32_t* pixels;      // [n][caps.out_pixels]
+    int32_t* edge_index;   // [n][H][W] or NULL
+    int4* result;          // [n]
+    long long* prof;       // [n][8] or NULL: cycles of {edge fill + anchor sort, pass over the anchors, walks, extraction}, walked pixels, trees
+};
+
+__global__ void __launch_bounds__(32) k_ed_route(EdRouteBatch b)
+{
+    __shared__ int hist[2048];
+    const int img = blockIdx.x, lane = threadIdx.x;
+    const size_t P = (size_t)b.W * b.H;
+    const int16_t* G = b.G + (size_t)img * P;
+    uint8_t* F = b.F + (size_t)img * P;
+    uint8_t* scratch = b.scratch + (size_t)img * b.scratch_stride;
+    int32_t* edge = b.edge_index ? b.edge_index + (size_t)img * P : nullptr;
+    const long long t_start = clock64();
+    if (edge) {
+        if ((P & 3) == 0) {
+            int4* e4 = reinterpret_cast<int4*>(edge);
+            for (size_t i = lane; i < P / 4; i += 32) e4[i] = make_int4(-1, -1, -1, -1);
+        } else {
+            for (size_t i = lane; i < P; i += 32) edge[i] = -1;
+        }
+    }
+    const int total = ed_warp_sort_anchors(F, G, P, hist, sdm_host::EdRouteAnchorSlots(scratch, b.caps), b.caps.anchors, lane);
+    if (total < 0) {  // (cannot happen with EdRouteCapsFor's P / 2; the host routes the image if it does)
+        if (lane == 0) b.result[img] = make_int4(0, 0, 0, 0);
+        return;
+    }
     if (lane == 0) {
         int nc = 0, np = 0;
         long long* prof = b.prof ? b.prof + (size_t)img * 8 : nullptr;
