@@ -11,6 +11,9 @@
 //   in : im  [n][H][W] u8                                                  1 byte per pixel
 //   out: G   [n][H][W] i16  |gx| + |gy| of Sobel on the smoothed image; border pixels = grad_thresh - 1
 //        F   [n][H][W] u8   bits 0-1: 0 below grad_thresh, 1 vertical edge pixel (|gx| >= |gy|), 2 horizontal;
+//                           bits 2-3 / 4-5: where an unguided walk goes from the pixel backwards / forwards along its direction
+//                           (the largest of the three gradients ahead: the smart-routing step, decided here for all pixels at
+//                           once so that the sequential walk never touches the gradient plane);
 //                           bit 7: anchor (rows / columns 2 .. size-3: G exceeds both neighbours across the edge by
 //                           anchor_thresh)                                 3 bytes per pixel
 // Integer arithmetic throughout: the planes are bit-identical to sdm_host::EdPlanesHost.
@@ -209,10 +212,19 @@ SDM_ED_HD void ed4_store(const EdTile& t, const EdArgs& a, int i)
         const int gq = v & 0xfff, dir = v >> 12;
         int fq = dir;
         const int xx = x + q;
-        if (dir != 0 && y >= 2 && y <= a.H - 3 && xx >= 2 && xx <= a.W - 3) {
-            const int n0 = (int)(dir == 1 ? SDM_ED_LANE(cw, q) : SDM_ED_LANE(uw, q + 1)) & 0xfff;
-            const int n1 = (int)(dir == 1 ? SDM_ED_LANE(cw, q + 2) : SDM_ED_LANE(dw, q + 1)) & 0xfff;
-            if (gq - n0 >= a.anchor_thresh && gq - n1 >= a.anchor_thresh) fq |= kEdFlagAnchor;
+        if (dir != 0) {
+            // the eight neighbours' gradients (an edge pixel is never on the image border, so all of them exist)
+            const int ul = (int)SDM_ED_LANE(uw, q) & 0xfff, uc = (int)SDM_ED_LANE(uw, q + 1) & 0xfff, ur = (int)SDM_ED_LANE(uw, q + 2) & 0xfff;
+            const int cl = (int)SDM_ED_LANE(cw, q) & 0xfff, cr = (int)SDM_ED_LANE(cw, q + 2) & 0xfff;
+            const int dl = (int)SDM_ED_LANE(dw, q) & 0xfff, dc = (int)SDM_ED_LANE(dw, q + 1) & 0xfff, dr = (int)SDM_ED_LANE(dw, q + 2) & 0xfff;
+            // where an unguided walk goes from here, backwards and forwards along the pixel's direction (sdm_host::ed_route_code)
+            const int back = dir == 2 ? sdm_host::ed_route_code(ul, cl, dl) : sdm_host::ed_route_code(ul, uc, ur);
+            const int fwd = dir == 2 ? sdm_host::ed_route_code(ur, cr, dr) : sdm_host::ed_route_code(dl, dc, dr);
+            fq |= (back << sdm_host::kEdRouteShiftBack) | (fwd << sdm_host::kEdRouteShiftFwd);
+            if (y >= 2 && y <= a.H - 3 && xx >= 2 && xx <= a.W - 3) {
+                const int n0 = dir == 1 ? cl : uc, n1 = dir == 1 ? cr : dc;
+                if (gq - n0 >= a.anchor_thresh && gq - n1 >= a.anchor_thresh) fq |= kEdFlagAnchor;
+            }
         }
 #undef SDM_ED_LANE
         f |= (uint32_t)fq << (8 * q);
@@ -340,10 +352,17 @@ k_ed_planes(const uint8_t* __restrict__ im, int W, int H, int grad_thresh, int a
                 const int g = v & 0xfff, dir = v >> 12;
                 int f = dir;
                 const int xx = x + q;
-                if (dir != 0 && y >= 2 && y <= H - 3 && xx >= 2 && xx <= W - 3) {
-                    const int n0 = dir == 1 ? (s_g[ty + 1][tx + q] & 0xfff) : (s_g[ty][tx + q + 1] & 0xfff);
-                    const int n1 = dir == 1 ? (s_g[ty + 1][tx + q + 2] & 0xfff) : (s_g[ty + 2][tx + q + 1] & 0xfff);
-                    if (g - n0 >= anchor_thresh && g - n1 >= anchor_thresh) f |= kEdFlagAnchor;
+                if (dir != 0) {
+                    const int ul = s_g[ty][tx + q] & 0xfff, uc = s_g[ty][tx + q + 1] & 0xfff, ur = s_g[ty][tx + q + 2] & 0xfff;
+                    const int cl = s_g[ty + 1][tx + q] & 0xfff, cr = s_g[ty + 1][tx + q + 2] & 0xfff;
+                    const int dl = s_g[ty + 2][tx + q] & 0xfff, dc = s_g[ty + 2][tx + q + 1] & 0xfff, dr = s_g[ty + 2][tx + q + 2] & 0xfff;
+                    const int back = dir == 2 ? sdm_host::ed_route_code(ul, cl, dl) : sdm_host::ed_route_code(ul, uc, ur);
+                    const int fwd = dir == 2 ? sdm_host::ed_route_code(ur, cr, dr) : sdm_host::ed_route_code(dl, dc, dr);
+                    f |= (back << sdm_host::kEdRouteShiftBack) | (fwd << sdm_host::kEdRouteShiftFwd);
+                    if (y >= 2 && y <= H - 3 && xx >= 2 && xx <= W - 3) {
+                        const int n0 = dir == 1 ? cl : uc, n1 = dir == 1 ? cr : dc;
+                        if (g - n0 >= anchor_thresh && g - n1 >= anchor_thresh) f |= kEdFlagAnchor;
+                    }
                 }
                 gq[q] = (short)g;
                 fq[q] = (uint8_t)f;

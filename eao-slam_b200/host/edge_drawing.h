@@ -180,9 +180,17 @@ SDM_EDR_HD inline void retrieve_chain_nos(const ChainVec& ch, int root, IntVec& 
 // next keyframes are on the device; both stage-1 forms produce identical planes (tests/test_gpu_edge_drawing.py).
 enum : uint8_t {
     kEdDirMask = 3,       // F & 3: 0 = below the gradient threshold, 1 = vertical edge pixel, 2 = horizontal edge pixel
+    // bits 2-3 / 4-5: where a walk that finds no marked pixel ahead goes from this pixel when it walks backwards (left / up) /
+    // forwards (right / down) along the pixel's own edge direction - the largest of the three gradients ahead, decided in
+    // stage 1 where all pixels are decided at once (ed_route_code); the walk itself then never reads the gradient plane
+    kEdRouteShiftBack = 2, kEdRouteShiftFwd = 4, kEdRouteMask = 3,
+    kEdStaticMask = 0x3f, // direction + routes: what stage 1 writes and the routing never changes
     kEdFlagEdge = 0x40,   // set by the routing: pixel belongs to a walked chain
     kEdFlagAnchor = 0x80  // set by stage 1: anchor; cleared by the routing when the pixel is walked or suppressed
 };
+// A, B, C = gradients of the three pixels ahead, A on the up / left side, B straight, C on the down / right side:
+// 0 = straight, 1 = to A's side, 2 = to C's side (the rule of the smart-routing step)
+SDM_EDR_HD inline int ed_route_code(int A, int B, int C) { return A > B ? (A > C ? 1 : 2) : (C > B ? 2 : 0); }
 
 // Stage 1 on the host.  G and F are dense W x H planes.  grad_thresh / anchor_thresh = the GRADIENT_THRESH / ANCHOR_THRESH
 // arguments of DetectEdgesByED (36 / 8 at LineDetector.cc:855; SOBEL_OPERATOR, sigma 1.0).  Needs W >= 5 and H >= 5.
@@ -232,6 +240,17 @@ inline void EdPlanesHost(const uint8_t* im, size_t step, int W, int H, int grad_
             if (sum >= grad_thresh) F[(size_t)y * W + x] = gx >= gy ? kEdgeVertical : kEdgeHorizontal;
         }
 #undef SM
+    // ---- where an unguided walk goes from each edge pixel (both senses along its direction)
+    for (int y = 1; y < H - 1; ++y)
+        for (int x = 1; x < W - 1; ++x) {
+            uint8_t& f = F[(size_t)y * W + x];
+            if (f == 0) continue;
+            const int16_t* g = G + (size_t)y * W + x;
+            int back, fwd;
+            if (f == kEdgeHorizontal) { back = ed_route_code(g[-W - 1], g[-1], g[W - 1]); fwd = ed_route_code(g[-W + 1], g[1], g[W + 1]); }
+            else { back = ed_route_code(g[-W - 1], g[-W], g[-W + 1]); fwd = ed_route_code(g[W - 1], g[W], g[W + 1]); }
+            f = (uint8_t)(f | (back << kEdRouteShiftBack) | (fwd << kEdRouteShiftFwd));
+        }
     // ---- anchors: gradient exceeds both neighbours across the edge by anchor_thresh
     for (int y = 2; y < H - 2; ++y) {
         const int16_t* g0 = G + (size_t)(y - 1) * W;
@@ -241,7 +260,7 @@ inline void EdPlanesHost(const uint8_t* im, size_t step, int W, int H, int grad_
         for (int x = 2; x < W - 2; ++x) {
             const int g = g1[x];
             if (g < grad_thresh) continue;
-            const bool is_anchor = f1[x] == kEdgeVertical ? (g - g1[x - 1] >= anchor_thresh && g - g1[x + 1] >= anchor_thresh)
+            const bool is_anchor = (f1[x] & kEdDirMask) == kEdgeVertical ? (g - g1[x - 1] >= anchor_thresh && g - g1[x + 1] >= anchor_thresh)
                                                           : (g - g0[x] >= anchor_thresh && g - g2[x] >= anchor_thresh);
             if (is_anchor) f1[x] |= kEdFlagAnchor;
         }
@@ -262,6 +281,7 @@ SDM_EDR_HD inline bool EdRouteCore(int W, int H, const int16_t* G, uint8_t* F, i
                                    long long* prof = nullptr /* device: cycles {anchor scan, walks, extraction}, walked pixels, trees */)
 {
     using namespace ed_detail;
+    (void)grad_thresh;  // (direction 0 in F = below the threshold: the walk reads nothing else)
     out_offsets.clear();
     out_offsets.push_back(0);
     out_pixels.clear();
@@ -418,33 +438,30 @@ SDM_EDR_HD inline bool EdRouteCore(int W, int H, const int16_t* G, uint8_t* F, i
             const int want = horizontal ? kEdgeHorizontal : kEdgeVertical;
             // offsets in pixels (the planes hold fewer than 2^31): one pixel forward, one pixel down / right, the two diagonals
             const int along = horizontal ? fwd : fwd * W, across = horizontal ? W : 1;
-            const int o_f1 = along + fwd * across, o_f2 = along - fwd * across, o_gA = along - across, o_gC = along + across;
-            const uint8_t* pf = F + ((size_t)r * W + c);
-            const int16_t* pg = G + ((size_t)r * W + c);
+            const int o_f1 = along + fwd * across, o_f2 = along - fwd * across;
+            const int route_shift = fwd < 0 ? kEdRouteShiftBack : kEdRouteShiftFwd;
+            uint8_t* pf = F + ((size_t)r * W + c);
             uint8_t fcur = *pf;
             bool full = false;
             while ((fcur & kEdDirMask) == want) {
-                // forward neighbours: straight, the diagonal on the `fwd` side, the other diagonal
+                // forward neighbours: straight, the diagonal on the `fwd` side, the other diagonal; the two pixels beside this one
                 const uint8_t f0 = pf[along], f1 = pf[o_f1], f2 = pf[o_f2];
-                const int gA = pg[o_gA], gB = pg[along], gC = pg[o_gC];
-                const uint8_t s0 = pf[-across], s1 = pf[across];  // (all eight loads before the first store: one round trip)
-                uint8_t* wf = const_cast<uint8_t*>(pf);
-                wf[0] = (uint8_t)((fcur & kEdDirMask) | kEdFlagEdge);
-                wf[-across] = (uint8_t)(s0 & ~kEdFlagAnchor);
-                wf[across] = (uint8_t)(s1 & ~kEdFlagAnchor);
+                const uint8_t s0 = pf[-across], s1 = pf[across];  // (all five loads before the first store: one round trip)
+                pf[0] = (uint8_t)((fcur & kEdStaticMask) | kEdFlagEdge);
+                pf[-across] = (uint8_t)(s0 & ~kEdFlagAnchor);
+                pf[across] = (uint8_t)(s1 & ~kEdFlagAnchor);
                 int side;  // -1 / 0 / +1: offset across the walk of the pixel taken
                 if (f0 & (kEdFlagAnchor | kEdFlagEdge)) side = 0;
                 else if (f1 & (kEdFlagAnchor | kEdFlagEdge)) side = fwd;
                 else if (f2 & (kEdFlagAnchor | kEdFlagEdge)) side = -fwd;
-                else if (gA > gB) side = gA > gC ? -1 : 1;
-                else side = gC > gB ? 1 : 0;
-                const int step = along + side * across;
-                pf += step;
-                pg += step;
+                else {  // the largest gradient ahead, as stage 1 found it
+                    const int code = (fcur >> route_shift) & kEdRouteMask;
+                    side = code == 0 ? 0 : (code == 1 ? -1 : 1);
+                }
+                pf += along + side * across;
                 if (horizontal) { r += side; c += fwd; } else { r += fwd; c += side; }
                 fcur = side == 0 ? f0 : (side == fwd ? f1 : f2);
-                const int gcur = side == 0 ? gB : (side < 0 ? gA : gC);
-                if ((fcur & kEdFlagEdge) || gcur < grad_thresh) {  // met an edge or left the gradient ridge
+                if ((fcur & kEdFlagEdge) || (fcur & kEdDirMask) == 0) {  // met an edge or left the gradient ridge (direction 0 = below the threshold)
                     ended = true;
                     break;
                 }
@@ -490,9 +507,9 @@ SDM_EDR_HD inline bool EdRouteCore(int W, int H, const int16_t* G, uint8_t* F, i
                     for (int k = 0; k < 4; ++k) v[k] = F[q[k]];
                     // (a pixel may be in the list twice - the pixel a chain turned at starts both children: the stores are idempotent)
                     SDM_EDR_UNROLL4
-                    for (int k = 0; k < 4; ++k) F[q[k]] = (uint8_t)(v[k] & kEdDirMask);
+                    for (int k = 0; k < 4; ++k) F[q[k]] = (uint8_t)(v[k] & kEdStaticMask);
                 }
-                for (; i < pixels.size(); ++i) FL(pixels[i].r, pixels[i].c) &= kEdDirMask;
+                for (; i < pixels.size(); ++i) FL(pixels[i].r, pixels[i].c) &= kEdStaticMask;
             }
             t_extract += SDM_EDR_CLOCK() - t_b;
             continue;
