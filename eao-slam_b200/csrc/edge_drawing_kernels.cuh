@@ -379,106 +379,127 @@ k_ed_planes(const uint8_t* __restrict__ im, int W, int H, int grad_thresh, int a
     }
 }
 
-// The anchors of one image in walking order - decreasing gradient, raster order among equals - by a whole warp; hist = 2048
-// ints of shared memory.  Returns their number, or -1 (and writes nothing) if the list holds fewer than that.
-__device__ __forceinline__ int ed_warp_sort_anchors(const uint8_t* __restrict__ F, const int16_t* __restrict__ G, size_t P, int* hist,
-                                                    int* __restrict__ anchors, int cap, int lane)
+// ---- the anchors of every image in walking order: decreasing gradient, raster order among equals ---------------------------
+// A stable counting sort over the 2048 gradient values, one block of eight warps per image (the walk's own thread would pay two
+// dependent memory round trips per anchor, twice: a quarter of the routing kernel in its first form; one warp: 3 ms per image).
+// The image is cut into eight consecutive pieces, warp w counts piece w into its own histogram, the block turns the eight
+// histograms into start positions (all smaller keys of all pieces first, then the same key of the earlier pieces), and every
+// warp places the anchors of its piece.  Inside a piece, lane l holds 16 consecutive pixels of a 512-pixel window (one 16-byte
+// load of the flags, two of the gradients, in flight together) and the lanes take turns in lane order, so raster order is kept.
+constexpr int kEdSortWarps = 8, kEdSortThreads = 32 * kEdSortWarps, kEdSortSmem = kEdSortWarps * 2048 * (int)sizeof(int);
+
+__device__ __forceinline__ int ed_anchor_key(uint32_t gword, int half) { return 2047 - min((int)(short)((gword >> (16 * half)) & 0xffffu), 2047); }
+
+// pass 1 (count) or pass 2 (place) of one warp over pixels [begin, end) of one image; hist = this warp's 2048 counters
+template <bool kPlace>
+__device__ __forceinline__ void ed_warp_anchor_pass(const uint8_t* __restrict__ F, const int16_t* __restrict__ G, size_t begin, size_t end, bool wide,
+                                                    int* hist, int* __restrict__ anchors, int lane)
 {
-    // ---- the anchors in walking order - decreasing gradient, raster order among equals - by the whole warp: a stable
-    // counting sort over the 2048 gradient values (one thread doing this alone pays two dependent memory round trips per
-    // anchor, twice: a quarter of the kernel's time in its first form).  Lane l holds 16 consecutive pixels of a 512-pixel
-    // window (one 16-byte load of the flags, two of the gradients, all in flight together), so raster order = lane order,
-    // then byte order.
-    for (int k = lane; k < 2048; k += 32) hist[k] = 0;
-    __syncwarp();
-    const bool wide = (P & 15) == 0;  // (plane bases are 256-byte aligned and P is a multiple of 16: aligned 16-byte loads)
     const size_t win = wide ? 512 : 32;
-    for (size_t i0 = 0; i0 < P; i0 += win) {
-        if (wide) {
-            const size_t i = i0 + 16 * (size_t)lane;
-            if (i < P) {
-                const uint4 f = *reinterpret_cast<const uint4*>(F + i);
-                const uint4 g0 = *reinterpret_cast<const uint4*>(G + i), g1 = *reinterpret_cast<const uint4*>(G + i + 8);  // (with f: one round trip)
-                const uint32_t fw[4] = {f.x, f.y, f.z, f.w};
-                if ((f.x | f.y | f.z | f.w) & 0x80808080u) {
-                    const uint32_t gw[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-#pragma unroll
-                    for (int k = 0; k < 16; ++k)
-                        if ((fw[k >> 2] >> (8 * (k & 3))) & 0x80u)
-                            atomicAdd(&hist[2047 - min((int)(short)((gw[k >> 1] >> (16 * (k & 1))) & 0xffffu), 2047)], 1);
-                }
-            }
-        } else {
-            const size_t i = i0 + lane;
-            if (i < P && (F[i] & kEdFlagAnchor)) atomicAdd(&hist[2047 - min((int)G[i], 2047)], 1);
-        }
-    }
-    __syncwarp();
-    int total;
-    {   // exclusive prefix over the bins: 64 consecutive bins per lane
-        int sum = 0;
-        for (int k = 0; k < 64; ++k) sum += hist[64 * lane + k];
-        int incl = sum;
-        for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
-        int run = incl - sum;
-        for (int k = 0; k < 64; ++k) { const int c = hist[64 * lane + k]; hist[64 * lane + k] = run; run += c; }
-        total = __shfl_sync(0xffffffffu, incl, 31);
-    }
-    __syncwarp();
-    if (total > cap) return -1;  // the caller's list is too short: nothing is written
-    for (size_t i0 = 0; i0 < P; i0 += win) {
+    for (size_t i0 = begin; i0 < end; i0 += win) {
         if (wide) {
             const size_t i = i0 + 16 * (size_t)lane;
             uint32_t fw[4] = {0, 0, 0, 0}, gw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             bool any = false;
-            if (i < P) {
+            if (i < end) {
                 const uint4 f = *reinterpret_cast<const uint4*>(F + i);
                 const uint4 g0 = *reinterpret_cast<const uint4*>(G + i), g1 = *reinterpret_cast<const uint4*>(G + i + 8);
                 fw[0] = f.x; fw[1] = f.y; fw[2] = f.z; fw[3] = f.w;
                 any = ((f.x | f.y | f.z | f.w) & 0x80808080u) != 0;
-                if (any) {
-                    gw[0] = g0.x; gw[1] = g0.y; gw[2] = g0.z; gw[3] = g0.w; gw[4] = g1.x; gw[5] = g1.y; gw[6] = g1.z; gw[7] = g1.w;
-                }
+                gw[0] = g0.x; gw[1] = g0.y; gw[2] = g0.z; gw[3] = g0.w; gw[4] = g1.x; gw[5] = g1.y; gw[6] = g1.z; gw[7] = g1.w;
             }
-            // the lanes that hold anchors take their turn in lane order; a lane places its own anchors in byte order
-            unsigned m = __ballot_sync(0xffffffffu, any);
-            while (m) {
-                const int turn = __ffs(m) - 1;
-                if (lane == turn) {
+            if (!kPlace) {
+                if (any) {
 #pragma unroll
                     for (int k = 0; k < 16; ++k)
-                        if ((fw[k >> 2] >> (8 * (k & 3))) & 0x80u) {
-                            const int key = 2047 - min((int)(short)((gw[k >> 1] >> (16 * (k & 1))) & 0xffffu), 2047);
-                            anchors[hist[key]++] = (int)(i + k);
-                        }
+                        if ((fw[k >> 2] >> (8 * (k & 3))) & 0x80u) atomicAdd(&hist[ed_anchor_key(gw[k >> 1], k & 1)], 1);
                 }
-                __syncwarp();
-                m &= m - 1;
+            } else {
+                // the lanes that hold anchors take their turn in lane order; a lane places its own anchors in byte order
+                unsigned m = __ballot_sync(0xffffffffu, any);
+                while (m) {
+                    const int turn = __ffs(m) - 1;
+                    if (lane == turn) {
+#pragma unroll
+                        for (int k = 0; k < 16; ++k)
+                            if ((fw[k >> 2] >> (8 * (k & 3))) & 0x80u) anchors[hist[ed_anchor_key(gw[k >> 1], k & 1)]++] = (int)(i + k);
+                    }
+                    __syncwarp();
+                    m &= m - 1;
+                }
             }
         } else {
             const size_t i = i0 + lane;
-            const bool is_anchor = i < P && (F[i] & kEdFlagAnchor);
-            const unsigned m = __ballot_sync(0xffffffffu, is_anchor);
-            if (is_anchor) {
-                const int key = 2047 - min((int)G[i], 2047);
-                const unsigned peers = __match_any_sync(m, key);   // the lanes of this group with the same gradient
-                const int leader = __ffs(peers) - 1;
-                int pos = 0;
-                if (lane == leader) { pos = hist[key]; hist[key] = pos + __popc(peers); }
-                pos = __shfl_sync(peers, pos, leader);
-                anchors[pos + __popc(peers & ((1u << lane) - 1u))] = (int)i;
+            const bool is_anchor = i < end && (F[i] & kEdFlagAnchor);
+            if (!kPlace) {
+                if (is_anchor) atomicAdd(&hist[2047 - min((int)G[i], 2047)], 1);
+            } else {
+                const unsigned m = __ballot_sync(0xffffffffu, is_anchor);
+                if (is_anchor) {
+                    const int key = 2047 - min((int)G[i], 2047);
+                    const unsigned peers = __match_any_sync(m, key);   // the lanes of this group with the same gradient
+                    const int leader = __ffs(peers) - 1;
+                    int pos = 0;
+                    if (lane == leader) { pos = hist[key]; hist[key] = pos + __popc(peers); }
+                    pos = __shfl_sync(peers, pos, leader);
+                    anchors[pos + __popc(peers & ((1u << lane) - 1u))] = (int)i;
+                }
+                __syncwarp();
             }
-            __syncwarp();
         }
     }
-    __syncwarp();
-    return total;
+}
+
+// list + img * stride: the image's anchors (room for `cap`); count[img] = their number, or -1 (nothing written) if more than cap
+__global__ void __launch_bounds__(kEdSortThreads)
+k_ed_sort(const int16_t* __restrict__ Gall, const uint8_t* __restrict__ Fall, int W, int H, int* __restrict__ list, size_t stride, int cap,
+          int* __restrict__ count)
+{
+    extern __shared__ int hist[];  // [kEdSortWarps][2048]
+    __shared__ int warp_tot[kEdSortWarps];
+    const int img = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const size_t P = (size_t)W * H;
+    const uint8_t* F = Fall + (size_t)img * P;
+    const int16_t* G = Gall + (size_t)img * P;
+    const bool wide = (P & 15) == 0;  // (plane bases are 256-byte aligned and P is a multiple of 16: aligned 16-byte loads)
+    const size_t unit = wide ? 512 : 32;
+    const size_t piece = ((P + kEdSortWarps - 1) / kEdSortWarps + unit - 1) / unit * unit;
+    const size_t begin = min((size_t)w * piece, P), end = min(begin + piece, P);
+    for (int k = tid; k < kEdSortWarps * 2048; k += kEdSortThreads) hist[k] = 0;
+    __syncthreads();
+    ed_warp_anchor_pass<false>(F, G, begin, end, wide, hist + w * 2048, nullptr, lane);
+    __syncthreads();
+    // start positions: thread t owns keys 8 t .. 8 t + 7
+    int tot[8], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        int c = 0;
+        for (int q = 0; q < kEdSortWarps; ++q) c += hist[q * 2048 + 8 * tid + k];
+        tot[k] = c;
+        sum += c;
+    }
+    int incl = sum;
+    for (int d = 1; d < 32; d <<= 1) { const int o = __shfl_up_sync(0xffffffffu, incl, d); if (lane >= d) incl += o; }
+    if (lane == 31) warp_tot[w] = incl;
+    __syncthreads();
+    int base = incl - sum, total = 0;
+    for (int q = 0; q < kEdSortWarps; ++q) { if (q < w) base += warp_tot[q]; total += warp_tot[q]; }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        int run = base;
+        for (int q = 0; q < kEdSortWarps; ++q) { const int c = hist[q * 2048 + 8 * tid + k]; hist[q * 2048 + 8 * tid + k] = run; run += c; }
+        base += tot[k];
+    }
+    __syncthreads();
+    if (tid == 0) count[img] = total <= cap ? total : -1;
+    if (total > cap) return;
+    ed_warp_anchor_pass<true>(F, G, begin, end, wide, hist + w * 2048, list + (size_t)img * stride, lane);
 }
 
 // ---- stage 2 on the device: one warp per image ------------------------------------------------------------------------------
 // The routing walk is sequential per image (a step depends on the marks the previous walks left), so an image is one thread's
 // work: lane 0 of the image's warp runs sdm_host::EdRouteFixed - the same source the host threads run, on fixed arrays in
-// global memory - after the 32 lanes have filled the image's edge-index plane with -1.  One warp per block: the device takes
+// global memory - on the anchors k_ed_sort has put in order, after the 32 lanes have filled the image's edge-index plane with -1.  One warp per block: the device takes
 // 32 resident images per SM, 4736 in flight on a B200; a step costs a few dependent L2 / HBM round trips (about 1 us), which
 // only pays when many images are routed at once - the host threads need 1.4 ms per image and thread, but there are 16-32 of
 // them against thousands of warps.  result[img] = {chains, chain pixels, 1 if complete (0: a capacity ran out, the host routes
@@ -494,12 +515,12 @@ struct EdRouteBatch {
     uint32_t* pixels;      // [n][caps.out_pixels]
     int32_t* edge_index;   // [n][H][W] or NULL
     int4* result;          // [n]
+    const int* n_anchors;  // [n] from k_ed_sort
     long long* prof;       // [n][8] or NULL: cycles of {edge fill + anchor sort, pass over the anchors, walks, extraction}, walked pixels, trees
 };
 
 __global__ void __launch_bounds__(32) k_ed_route(EdRouteBatch b)
 {
-    __shared__ int hist[2048];
     const int img = blockIdx.x, lane = threadIdx.x;
     const size_t P = (size_t)b.W * b.H;
     const int16_t* G = b.G + (size_t)img * P;
@@ -515,11 +536,12 @@ __global__ void __launch_bounds__(32) k_ed_route(EdRouteBatch b)
             for (size_t i = lane; i < P; i += 32) edge[i] = -1;
         }
     }
-    const int total = ed_warp_sort_anchors(F, G, P, hist, sdm_host::EdRouteAnchorSlots(scratch, b.caps), b.caps.anchors, lane);
+    const int total = b.n_anchors[img];  // k_ed_sort left the anchors in the scratch block's anchor slots, in walking order
     if (total < 0) {  // (cannot happen with EdRouteCapsFor's P / 2; the host routes the image if it does)
         if (lane == 0) b.result[img] = make_int4(0, 0, 0, 0);
         return;
     }
+    __syncwarp();
     if (lane == 0) {
         int nc = 0, np = 0;
         long long* prof = b.prof ? b.prof + (size_t)img * 8 : nullptr;

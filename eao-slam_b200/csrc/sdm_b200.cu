@@ -1725,13 +1725,37 @@ int ed_reserve(sdm_ctx* c, int n_kf)
 
 // planes of up to `cap` keyframes inside the (device or pinned) block: im[cap][P] u8 | G[cap][P] i16 | F[cap][P] u8, every
 // section on a 256-byte boundary
+// ... | NA[cap] int32 (rounded up to 64): number of anchors per keyframe (k_ed_sort; -1: more than fit) | A[cap][ed_anchor_stride]
+// int32: their positions in walking order (host routing: the host thread's own counting sort is a fifth of its time)
 inline size_t ed_align(size_t v) { return (v + 255) & ~(size_t)255; }
-size_t ed_bytes(int cap, size_t P) { return ed_align((size_t)cap * P) + ed_align((size_t)cap * P * 2) + ed_align((size_t)cap * P); }
+inline size_t ed_anchor_stride(size_t P) { return (P / 8 + 16 + 3) & ~(size_t)3; }  // ints; a VGA keyframe of the bench scene has 12 k anchors
+size_t ed_bytes(int cap, size_t P)
+{
+    return ed_align((size_t)cap * P) + ed_align((size_t)cap * P * 2) + ed_align((size_t)cap * P) +
+           ed_align(((((size_t)cap + 63) & ~(size_t)63) + (size_t)cap * ed_anchor_stride(P)) * 4);
+}
 struct EdLayout {
-    uint8_t* im; int16_t* G; uint8_t* F;
+    uint8_t* im; int16_t* G; uint8_t* F; int32_t* NA; int32_t* A;
     EdLayout(uint8_t* base, int cap, size_t P)
-        : im(base), G((int16_t*)(base + ed_align((size_t)cap * P))), F(base + ed_align((size_t)cap * P) + ed_align((size_t)cap * P * 2)) {}
+        : im(base), G((int16_t*)(base + ed_align((size_t)cap * P))), F(base + ed_align((size_t)cap * P) + ed_align((size_t)cap * P * 2)),
+          NA((int32_t*)(base + ed_align((size_t)cap * P) + ed_align((size_t)cap * P * 2) + ed_align((size_t)cap * P))),
+          A(NA + (((size_t)cap + 63) & ~(size_t)63)) {}
 };
+
+// k_ed_sort over `count` keyframes from `first`: lists of `cap` positions at list + i * stride, numbers at n_anchors + i
+int ed_launch_sort(sdm_ctx* c, const EdLayout& d, int first, int count, int32_t* list, size_t stride, int cap, int32_t* n_anchors)
+{
+    static bool attr_set = false;
+    if (!attr_set) {
+        CU(cudaFuncSetAttribute(sdm::k_ed_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, sdm::kEdSortSmem));
+        attr_set = true;
+    }
+    sdm::k_ed_sort<<<count, sdm::kEdSortThreads, sdm::kEdSortSmem, c->s_ed>>>(d.G + (size_t)first * c->npix, d.F + (size_t)first * c->npix, c->cfg.width,
+                                                                               c->cfg.height, list, stride, cap, n_anchors);
+    CU(cudaGetLastError());
+    ++c->launches;
+    return SDM_OK;
+}
 
 int ed_launch(sdm_ctx* c, const EdLayout& d, int first, int count, int grad_thresh, int anchor_thresh)
 {
@@ -1756,7 +1780,7 @@ constexpr int kEdDevBatch = 1024;  // images routed by one k_ed_route launch (27
 // sections of the device block of the routing kernel for `cap` images
 struct EdRouteLayout {
     sdm_host::EdRouteCaps caps;
-    size_t scratch_stride, o_scratch, o_off, o_px, o_edge, o_res, o_at, o_prof, bytes;
+    size_t scratch_stride, o_scratch, o_off, o_px, o_edge, o_res, o_at, o_prof, o_na, bytes;
     EdRouteLayout(int cap, size_t P)
     {
         caps = sdm_host::EdRouteCapsFor(P);
@@ -1772,7 +1796,8 @@ struct EdRouteLayout {
         o_res = ed_align(o_edge + (size_t)cap * P * 4);
         o_at = ed_align(o_res + (size_t)cap * sizeof(int4));
         o_prof = ed_align(o_at + ((size_t)cap + 1) * sizeof(unsigned long long));
-        bytes = ed_align(o_prof + (size_t)cap * 8 * sizeof(long long));
+        o_na = ed_align(o_prof + (size_t)cap * 8 * sizeof(long long));
+        bytes = ed_align(o_na + (size_t)cap * sizeof(int32_t));
     }
 };
 
@@ -1819,7 +1844,7 @@ int ed_run_device(sdm_ctx* c, int n, const sdm_ed_image* images, int grad_thresh
     }
     const EdLayout dv(c->ed_dev, c->ed_cap, P), hv(c->ed_host, c->ed_cap, P);
     const EdRouteLayout L(c->edr_cap, P);
-    const size_t list_room = (size_t)(c->ed_dev + ed_bytes(c->ed_cap, P) - (uint8_t*)dv.G) / 4;  // int32 the G / F planes hold
+    const size_t list_room = (size_t)((uint8_t*)dv.NA - (uint8_t*)dv.G) / 4;  // int32 the G / F planes hold
     unsigned long long* at_host = reinterpret_cast<unsigned long long*>(c->edr_result_host + c->edr_cap);
     c->edr_fallbacks = 0;
     c->edr_last_n = 0;
@@ -1862,7 +1887,11 @@ int ed_run_device(sdm_ctx* c, int n, const sdm_ed_image* images, int grad_thresh
         const bool prof = getenv("SDM_ED_ROUTE_PROF") != nullptr;  // per-image cycle counts of the routing kernel on stderr
         b.prof = prof ? (long long*)(c->edr_dev + L.o_prof) : nullptr;
         unsigned long long* at_dev = (unsigned long long*)(c->edr_dev + L.o_at);
+        int32_t* na_dev = (int32_t*)(c->edr_dev + L.o_na);
+        b.n_anchors = na_dev;
         CU(cudaEventRecord(c->edr_ev[0], c->s_ed));
+        static_assert(sizeof(int) == 4, "anchor slots");
+        RC(ed_launch_sort(c, dv, 0, nb, (int32_t*)sdm_host::EdRouteAnchorSlots(b.scratch, L.caps), L.scratch_stride / 4, L.caps.anchors, na_dev));
         sdm::k_ed_route<<<nb, 32, 0, c->s_ed>>>(b);
         CU(cudaGetLastError());
         CU(cudaEventRecord(c->edr_ev[1], c->s_ed));
@@ -2009,6 +2038,7 @@ int sdm_edge_drawing(sdm_ctx* c, int n, const sdm_ed_image* images, int grad_thr
         if (hw == 0) hw = 1;
         const int nt = std::max(1, std::min(n_threads > 0 ? n_threads : (int)std::min(hw, 32u), n));
         const EdLayout dv(c->ed_dev, c->ed_cap, P), hv(c->ed_host, c->ed_cap, P);
+        const size_t sa = ed_anchor_stride(P);
         for (int base = 0; base < n; base += kEdMaxBatch) {
             const int nb = std::min(kEdMaxBatch, n - base), n_chunks = ed_chunk_count(nb);
             std::atomic<int> next(0), issued(0), failed(0);
@@ -2031,8 +2061,9 @@ int sdm_edge_drawing(sdm_ctx* c, int n, const sdm_ed_image* images, int grad_thr
                         if (cudaEventSynchronize(c->ed_ev[3 * chunk + 2]) != cudaSuccess) { failed.store(1); return; }
                         const auto t0 = std::chrono::steady_clock::now();
                         const sdm_ed_image& im = images[base + i];
+                        const int n_sorted = chunk >= 2 ? hv.NA[i] : -1;  // (-1: the host sorts the anchors)
                         sdm_host::EdRouteChains(W, H, hv.G + (size_t)i * P, hv.F + (size_t)i * P, grad_thresh,
-                                                res->chains[(size_t)(base + i)], im.edge_index, im.edge_step);
+                                                res->chains[(size_t)(base + i)], im.edge_index, im.edge_step, hv.A + (size_t)i * sa, n_sorted);
                         route_ns.fetch_add(std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now() - t0).count());
                     }
                 });
@@ -2051,6 +2082,11 @@ int sdm_edge_drawing(sdm_ctx* c, int n, const sdm_ed_image* images, int grad_thr
                     CU(cudaEventRecord(c->ed_ev[3 * ch + 1], c->s_ed));
                     CU(cudaMemcpyAsync(hv.G + (size_t)first * P, dv.G + (size_t)first * P, (size_t)count * P * 2, cudaMemcpyDeviceToHost, c->s_ed));
                     CU(cudaMemcpyAsync(hv.F + (size_t)first * P, dv.F + (size_t)first * P, (size_t)count * P, cudaMemcpyDeviceToHost, c->s_ed));
+                    if (ch >= 2) {  // (the first 16 keyframes go to the host threads at once: they sort their anchors themselves)
+                        RC(ed_launch_sort(c, dv, first, count, dv.A + (size_t)first * sa, sa, (int)sa, dv.NA + first));
+                        CU(cudaMemcpyAsync(hv.NA + first, dv.NA + first, (size_t)count * 4, cudaMemcpyDeviceToHost, c->s_ed));
+                        CU(cudaMemcpyAsync(hv.A + (size_t)first * sa, dv.A + (size_t)first * sa, (size_t)count * sa * 4, cudaMemcpyDeviceToHost, c->s_ed));
+                    }
                     CU(cudaEventRecord(c->ed_ev[3 * ch + 2], c->s_ed));
                     {
                         std::lock_guard<std::mutex> lk(mu);

@@ -577,8 +577,9 @@ SDM_EDR_HD inline bool EdRouteCore(int W, int H, const int16_t* G, uint8_t* F, i
 
 // The core on std::vector: what the routing threads of sdm_edge_drawing and the host-only detector call.  Fills edge_index
 // with -1 first (KeyFrame.cc:87).
+// sorted_anchors / n_sorted (>= 0): the anchors already in walking order (k_ed_sort on the device), else they are sorted here.
 inline void EdRouteChains(int W, int H, const int16_t* G, uint8_t* F, int grad_thresh, EdgeChains& out,
-                          int32_t* edge_index = nullptr, size_t edge_step = 0)
+                          int32_t* edge_index = nullptr, size_t edge_step = 0, const int32_t* sorted_anchors = nullptr, int n_sorted = -1)
 {
     using namespace ed_detail;
     if (edge_index)
@@ -595,7 +596,10 @@ inline void EdRouteChains(int W, int H, const int16_t* G, uint8_t* F, int grad_t
     int hist[2048 + 1];
     offsets.v.swap(out.offsets);
     px.v.swap(out.pixels);
-    EdRouteCore(W, H, G, F, grad_thresh, found, anchors, chains, pixels, seg, stack, best, order, nos, offsets, px, edge_index, edge_step, hist);
+    if (sorted_anchors && n_sorted >= 0) anchors.v.assign(sorted_anchors, sorted_anchors + n_sorted);
+    else n_sorted = -1;
+    EdRouteCore(W, H, G, F, grad_thresh, found, anchors, chains, pixels, seg, stack, best, order, nos, offsets, px, edge_index, edge_step, hist,
+                n_sorted);
     offsets.v.swap(out.offsets);
     px.v.swap(out.pixels);
 }
