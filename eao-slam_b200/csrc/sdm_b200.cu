@@ -1745,11 +1745,8 @@ struct EdLayout {
 // k_ed_sort over `count` keyframes from `first`: lists of `cap` positions at list + i * stride, numbers at n_anchors + i
 int ed_launch_sort(sdm_ctx* c, const EdLayout& d, int first, int count, int32_t* list, size_t stride, int cap, int32_t* n_anchors)
 {
-    static bool attr_set = false;
-    if (!attr_set) {
-        CU(cudaFuncSetAttribute(sdm::k_ed_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, sdm::kEdSortSmem));
-        attr_set = true;
-    }
+    // (per device, and cheap: set before every launch rather than remembered per process)
+    CU(cudaFuncSetAttribute(sdm::k_ed_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, sdm::kEdSortSmem));
     sdm::k_ed_sort<<<count, sdm::kEdSortThreads, sdm::kEdSortSmem, c->s_ed>>>(d.G + (size_t)first * c->npix, d.F + (size_t)first * c->npix, c->cfg.width,
                                                                                c->cfg.height, list, stride, cap, n_anchors);
     CU(cudaGetLastError());
