@@ -255,9 +255,10 @@ int sdm_last_line_fit_ms(sdm_ctx* ctx, float* ms);
  * (ProbabilityMapping.cc:394) and which hands the image to the closed-source EDLib.a:
  *     EdgeMap* map = DetectEdgesByED(srcImg, width, height, SOBEL_OPERATOR, 36, 8, 1.0);                 (:855)
  *     kf->mEdgeIndex.at<int>(r, c) = i for every pixel of map->segments[i];  kf->mEdgeMap = map;          (:857-869)
- * for a batch of keyframes.  Stage 1 (smoothing, Sobel gradient, direction, anchors: k_ed_planes) runs on the device in
- * chunks of keyframes, stage 2 (the sequential smart-routing walk from the anchors, host/edge_drawing.h) on n_threads host
- * threads while the next chunk is on the device.  The chains are the library's, pixel for pixel and in order
+ * for a batch of keyframes.  Stage 1 (smoothing, Sobel gradient, direction, the routing choice of every edge pixel,
+ * anchors: k_ed_planes4 / k_ed_planes; the anchors in walking order: k_ed_sort) runs on the device in chunks of keyframes,
+ * stage 2 (the sequential smart-routing walk from the anchors, host/edge_drawing.h) on n_threads host threads while the
+ * next chunk is on the device - or on the device as well, see sdm_set_edge_drawing_route.  The chains are the library's, pixel for pixel and in order
  * (tests/test_edge_drawing.py, tests/test_gpu_edge_drawing.py).
  * images[i].im = kf->im_ (8-bit, ctx width x height, row pitch im_step bytes); images[i].edge_index, if not NULL,
  * receives kf->mEdgeIndex: -1, then the chain number of every chain pixel (int32 plane, row pitch edge_step bytes) -
@@ -277,7 +278,7 @@ void sdm_ed_free(sdm_ed_result* result);
 /* where stage 2 (the routing walk) of sdm_edge_drawing runs.  SDM_ED_ROUTE_HOST (default): host threads, overlapped with
  * stage 1 of the following chunks - the fast choice for a few hundred keyframes on one GPU (0.12 ms per VGA keyframe on 16
  * cores).  SDM_ED_ROUTE_DEVICE: k_ed_route, one warp per keyframe, up to 1024 keyframes per launch - the walk is sequential
- * per image and a device thread walks ~30 x slower than a host core, but thousands of images walk at once and the host
+ * per image and a device thread walks ~15 x slower than a host core, but thousands of images walk at once and the host
  * cores stay free (one process per GPU shares them); chains and edge index are identical in both modes.  An image whose
  * walk exceeds the kernel's fixed capacities is routed on the host (sdm_last_edge_drawing_fallbacks counts them). */
 enum { SDM_ED_ROUTE_HOST = 0, SDM_ED_ROUTE_DEVICE = 1 };
@@ -290,8 +291,8 @@ int sdm_last_edge_drawing_fallbacks(sdm_ctx* ctx);
  * context; calls with more than 1024 images keep the last 1024-image batch only. */
 int sdm_ed_device_edge_plane(sdm_ctx* ctx, int i, const int32_t** dev_plane);
 /* timing of the last sdm_edge_drawing: device time of its k_ed_planes launches, host wall time of the call, and the
- * summed thread time of the routing walks - in SDM_ED_ROUTE_DEVICE mode the device time of k_ed_route (all ms; any
- * pointer may be NULL) */
+ * summed thread time of the routing walks - in SDM_ED_ROUTE_DEVICE mode the device time of k_ed_sort + k_ed_route (all
+ * ms; any pointer may be NULL) */
 int sdm_last_edge_drawing_ms(sdm_ctx* ctx, float* kernel_ms, float* wall_ms, float* route_thread_ms);
 /* the stage-1 planes of one image as the device computes them (G int16, F uint8, dense width x height; see
  * csrc/edge_drawing_kernels.cuh) - for tests and tools */
