@@ -173,11 +173,13 @@ SDM_EDR_HD inline void retrieve_chain_nos(const ChainVec& ch, int root, IntVec& 
 
 }  // namespace ed_detail
 
-// The detector runs in two stages.  Stage 1 (EdPlanesHost) is per-pixel image work - smoothing, gradient, direction, anchor
-// test - and produces two planes: G (int16 gradient magnitude) and F (one flag byte per pixel).  Stage 2 (EdRouteChains) is
-// the sequential part: anchor order, smart routing, segment extraction.  libsdm_b200.so runs stage 1 on the device for a
-// batch of keyframes (k_ed_planes, csrc/sdm_kernels.cuh; C-ABI sdm_edge_drawing) and stage 2 here on host threads while the
-// next keyframes are on the device; both stage-1 forms produce identical planes (tests/test_gpu_edge_drawing.py).
+// The detector runs in two stages.  Stage 1 (EdPlanesHost) is per-pixel image work - smoothing, gradient, direction, the routing
+// choice of every edge pixel, anchor test - and produces two planes: G (int16 gradient magnitude) and F (one flag byte per
+// pixel).  Stage 2 (EdRouteChains / EdRouteCore) is the sequential part: anchor order, smart routing, segment extraction.
+// libsdm_b200.so runs stage 1 on the device for a batch of keyframes (k_ed_planes4 / k_ed_planes, k_ed_sort:
+// csrc/edge_drawing_kernels.cuh; C-ABI sdm_edge_drawing) and stage 2 either here on host threads while the next keyframes are
+// on the device, or on the device as well (k_ed_route: one warp per keyframe running EdRouteFixed, the same source); both
+// stage-1 forms produce identical planes and both stage-2 forms identical chains (tests/test_gpu_edge_drawing.py).
 enum : uint8_t {
     kEdDirMask = 3,       // F & 3: 0 = below the gradient threshold, 1 = vertical edge pixel, 2 = horizontal edge pixel
     // bits 2-3 / 4-5: where a walk that finds no marked pixel ahead goes from this pixel when it walks backwards (left / up) /
