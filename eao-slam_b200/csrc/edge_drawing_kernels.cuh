@@ -516,7 +516,7 @@ struct EdRouteBatch {
     int32_t* edge_index;   // [n][H][W] or NULL
     int4* result;          // [n]
     const int* n_anchors;  // [n] from k_ed_sort
-    long long* prof;       // [n][8] or NULL: cycles of {edge fill + anchor sort, pass over the anchors, walks, extraction}, walked pixels, trees
+    long long* prof;       // [n][16] or NULL: cycles of {edge fill + anchor sort, pass over the anchors, walks, extraction}, walked pixels, trees
 };
 
 __global__ void __launch_bounds__(32) k_ed_route(EdRouteBatch b)
@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(32) k_ed_route(EdRouteBatch b)
     __syncwarp();
     if (lane == 0) {
         int nc = 0, np = 0;
-        long long* prof = b.prof ? b.prof + (size_t)img * 8 : nullptr;
+        long long* prof = b.prof ? b.prof + (size_t)img * 16 : nullptr;
         if (prof) prof[5] = clock64() - t_start;
         const bool ok = sdm_host::EdRouteFixed(b.W, b.H, G, F, b.grad_thresh, scratch, b.caps, b.offsets + (size_t)img * b.caps.offsets,
                                                b.pixels + (size_t)img * b.caps.out_pixels, edge, (size_t)b.W * 4, &nc, &np, total, prof);

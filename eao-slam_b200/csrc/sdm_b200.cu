@@ -1793,7 +1793,7 @@ struct EdRouteLayout {
         o_res = ed_align(o_edge + (size_t)cap * P * 4);
         o_at = ed_align(o_res + (size_t)cap * sizeof(int4));
         o_prof = ed_align(o_at + ((size_t)cap + 1) * sizeof(unsigned long long));
-        o_na = ed_align(o_prof + (size_t)cap * 8 * sizeof(long long));
+        o_na = ed_align(o_prof + (size_t)cap * 16 * sizeof(long long));
         bytes = ed_align(o_na + (size_t)cap * sizeof(int32_t));
     }
 };
@@ -1936,14 +1936,16 @@ int ed_run_device(sdm_ctx* c, int n, const sdm_ed_image* images, int grad_thresh
         CU(cudaEventElapsedTime(&ms, c->edr_ev[0], c->edr_ev[1]));
         c->ed_route_ms += ms;
         if (prof) {
-            std::vector<long long> h((size_t)nb * 8);
+            std::vector<long long> h((size_t)nb * 16);
             CU(cudaMemcpy(h.data(), b.prof, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
-            double mean[8] = {0}, mx[8] = {0};
+            double mean[16] = {0}, mx[16] = {0};
             for (int i = 0; i < nb; ++i)
-                for (int k = 0; k < 8; ++k) { mean[k] += (double)h[(size_t)i * 8 + k] / nb; mx[k] = std::max(mx[k], (double)h[(size_t)i * 8 + k]); }
+                for (int k = 0; k < 16; ++k) { mean[k] += (double)h[(size_t)i * 16 + k] / nb; mx[k] = std::max(mx[k], (double)h[(size_t)i * 16 + k]); }
             fprintf(stderr, "k_ed_route %d images, %.2f ms: mean / max kcycles: sort %.0f / %.0f, anchor pass %.0f / %.0f, walks %.0f / %.0f, extraction %.0f / %.0f, "
-                            "whole %.0f / %.0f; walked pixels %.0f / %.0f, trees %.0f / %.0f\n", nb, ms, mean[5] / 1e3, mx[5] / 1e3, mean[0] / 1e3, mx[0] / 1e3,
-                    mean[1] / 1e3, mx[1] / 1e3, mean[2] / 1e3, mx[2] / 1e3, mean[6] / 1e3, mx[6] / 1e3, mean[3], mx[3], mean[4], mx[4]);
+                            "whole %.0f / %.0f; walked pixels %.0f / %.0f, trees %.0f / %.0f; extraction split (mean): 2nd-direction path %.0f, + copies %.0f, "
+                            "1st direction %.0f, emit %.0f, other chains %.0f\n", nb, ms, mean[5] / 1e3, mx[5] / 1e3, mean[0] / 1e3, mx[0] / 1e3,
+                    mean[1] / 1e3, mx[1] / 1e3, mean[2] / 1e3, mx[2] / 1e3, mean[6] / 1e3, mx[6] / 1e3, mean[3], mx[3], mean[4], mx[4], mean[8] / 1e3,
+                    (mean[9] - mean[8]) / 1e3, mean[10] / 1e3, mean[11] / 1e3, mean[12] / 1e3);
         }
         // images that ran out of a capacity on the device: stage 1 again (the planes are spent), stage 2 on the host
         for (int i = 0; i < nb; ++i) {

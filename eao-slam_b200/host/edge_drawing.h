@@ -137,26 +137,35 @@ struct FixedVec {
     SDM_EDR_HD bool overflow() const { return ovf; }
 };
 
-// length of the longest path below `root`; every visited chain keeps only the child on that path (first child on ties).
-// Iterative post-order (the trees of a textured image are thousands of chains deep).
+// best[k] for every chain of a finished tree: the chain's length plus the longer of the two paths below it, a zero-length child
+// counting - with everything below it - as absent.  A child is created after its parent, so one pass from the last chain down
+// sees every child before its parent: no traversal, no pointer chasing (the recursive descent this replaces - one per queried
+// chain, each visiting the whole subtree - was two fifths of the segment extraction).
 template <class ChainVec, class IntVec>
-SDM_EDR_HD inline int longest_chain(ChainVec& ch, int root, IntVec& best, IntVec& order)
+SDM_EDR_HD inline void longest_paths(const ChainVec& ch, IntVec& best)
 {
-    if (root == -1 || ch[root].len == 0) return 0;
-    order.clear();
-    order.push_back(root);
-    for (int i = 0; i < order.size(); ++i) {  // pre-order list of the chains a recursive descent would visit
-        const Chain& c = ch[order[i]];
-        for (int k = 0; k < 2; ++k)
-            if (c.child[k] != -1 && ch[c.child[k]].len != 0) order.push_back(c.child[k]);
-    }
-    for (int i = order.size(); i-- > 0;) {
-        Chain& c = ch[order[i]];
+    for (int k = ch.size() - 1; k >= 1; --k) {
+        const Chain& c = ch[k];
         const int l0 = (c.child[0] != -1 && ch[c.child[0]].len != 0) ? best[c.child[0]] : 0;
         const int l1 = (c.child[1] != -1 && ch[c.child[1]].len != 0) ? best[c.child[1]] : 0;
-        int mx;
-        if (l0 >= l1) { mx = l0; c.child[1] = -1; } else { mx = l1; c.child[0] = -1; }
-        best[order[i]] = c.len + mx;
+        best[k] = c.len + (l0 >= l1 ? l0 : l1);
+    }
+}
+
+// Length of the longest path below `root` (from longest_paths); every chain ON that path keeps only the child the path continues
+// with (first child on ties; the last chain keeps its first child link whatever it points to) - what retrieve_chain_nos follows.
+// Valid as long as no chain below `root` has been copied since longest_paths ran, which holds for every query the extraction
+// makes: the chains it copies in between lie on paths that do not meet the queried subtree.
+template <class ChainVec, class IntVec>
+SDM_EDR_HD inline int longest_chain(ChainVec& ch, int root, const IntVec& best)
+{
+    if (root == -1 || ch[root].len == 0) return 0;
+    for (int k = root; k != -1;) {
+        Chain& c = ch[k];
+        const int l0 = (c.child[0] != -1 && ch[c.child[0]].len != 0) ? best[c.child[0]] : 0;
+        const int l1 = (c.child[1] != -1 && ch[c.child[1]].len != 0) ? best[c.child[1]] : 0;
+        if (l0 >= l1) { c.child[1] = -1; k = l0 > 0 ? c.child[0] : -1; }
+        else { c.child[0] = -1; k = c.child[1]; }
     }
     return best[root];
 }
@@ -284,6 +293,7 @@ SDM_EDR_HD inline bool EdRouteCore(int W, int H, const int16_t* G, uint8_t* F, i
 {
     using namespace ed_detail;
     (void)grad_thresh;  // (direction 0 in F = below the threshold: the walk reads nothing else)
+    (void)order;        // (work list of the recursive form of longest_chain; kept in the interface)
     out_offsets.clear();
     out_offsets.push_back(0);
     out_pixels.clear();
@@ -378,7 +388,7 @@ SDM_EDR_HD inline bool EdRouteCore(int W, int H, const int16_t* G, uint8_t* F, i
         c_.len = 0; /* copied */                                                                                             \
     } while (0)
 
-    long long t_walk = 0, t_extract = 0, n_walked = 0, n_trees = 0;
+    long long t_walk = 0, t_extract = 0, n_walked = 0, n_trees = 0, t_x[5] = {0, 0, 0, 0, 0};
     const long long t_begin = SDM_EDR_CLOCK();
     // The pass over the anchor list reads eight positions and their flags at a time (independent loads, in flight together).
     // An anchor flag is only ever cleared: a clear bit in the batch's copy is final; a set bit is read again if a walk has
@@ -516,11 +526,15 @@ SDM_EDR_HD inline bool EdRouteCore(int W, int H, const int16_t* G, uint8_t* F, i
             t_extract += SDM_EDR_CLOCK() - t_b;
             continue;
         }
-        best.resize(chains.size());  // (every entry is written before it is read inside one longest_chain call)
+        best.resize(chains.size());
         if (best.overflow()) return false;
+        longest_paths(chains, best);
         // ---- main segment: longest path of the second direction backwards, the anchor, longest path of the first direction
         seg.clear();
-        if (longest_chain(chains, chains[0].child[1], best, order) > 0) {
+        const long long t_x0 = SDM_EDR_CLOCK();
+        const int l_second = longest_chain(chains, chains[0].child[1], best);
+        t_x[0] += SDM_EDR_CLOCK() - t_x0;
+        if (l_second > 0) {
             retrieve_chain_nos(chains, chains[0].child[1], nos);
             for (int k = nos.size(); k-- > 0;) {
                 Chain& c = chains[nos[k]];
@@ -534,7 +548,9 @@ SDM_EDR_HD inline bool EdRouteCore(int W, int H, const int16_t* G, uint8_t* F, i
                 c.len = 0;
             }
         }
-        if (longest_chain(chains, chains[0].child[0], best, order) > 1) {
+        const long long t_x1 = SDM_EDR_CLOCK();
+        t_x[1] += t_x1 - t_x0;  // (selection of the second direction + its copies)
+        if (longest_chain(chains, chains[0].child[0], best) > 1) {
             retrieve_chain_nos(chains, chains[0].child[0], nos);
             ++chains[nos[0]].start;  // the anchor is already there
             --chains[nos[0]].len;
@@ -544,17 +560,22 @@ SDM_EDR_HD inline bool EdRouteCore(int W, int H, const int16_t* G, uint8_t* F, i
             for (int i = 1; i < seg.size(); ++i) seg[i - 1] = seg[i];
             seg.pop_back();
         }
+        const long long t_x2 = SDM_EDR_CLOCK();
+        t_x[2] += t_x2 - t_x1;  // (first direction + the closing test)
         SDM_EDR_EMIT();
+        const long long t_x3 = SDM_EDR_CLOCK();
+        t_x[3] += t_x3 - t_x2;  // (emit of the main segment)
         // ---- the other long chains of the tree
         for (int k = 2; k < chains.size(); ++k) {
             if (chains[k].len < 2) continue;
-            if (longest_chain(chains, k, best, order) >= 10) {
+            if (longest_chain(chains, k, best) >= 10) {
                 retrieve_chain_nos(chains, k, nos);
                 seg.clear();
                 for (int q = 0; q < nos.size(); ++q) SDM_EDR_APPEND_FORWARD(nos[q]);
                 SDM_EDR_EMIT();
             }
         }
+        t_x[4] += SDM_EDR_CLOCK() - t_x3;  // (the other chains)
         t_extract += SDM_EDR_CLOCK() - t_b;
         if (SDM_EDR_OVERFLOW()) return false;
     }
@@ -564,6 +585,7 @@ SDM_EDR_HD inline bool EdRouteCore(int W, int H, const int16_t* G, uint8_t* F, i
         prof[2] = t_extract;
         prof[3] = n_walked;
         prof[4] = n_trees;
+        for (int k = 0; k < 5; ++k) prof[8 + k] = t_x[k];  // extraction: longest path 2nd direction / + its copies / 1st direction / emit / other chains
     }
     return !SDM_EDR_OVERFLOW();
 #undef SDM_EDR_EMIT
