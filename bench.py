@@ -741,7 +741,8 @@ def main_ours(a, rank, world, local_rank):
             ed_ms = []
 
             def edge_step(on_device):
-                # on_device: routing walks in k_ed_route, masks stay on the device; else host threads, masks through pinned planes
+                # on_device 1: routing walks in k_ed_route, masks stay on the device; 2: walks on host threads, masks scattered on
+                # the device from the chains (n_loc <= 256: one batch); 0: host threads, masks through pinned host planes
                 for i in range(n_loc):
                     ed_imgs[i].edge_index, ed_imgs[i].edge_step = (None, 0) if on_device else (h_edge[i].ctypes.data, 4 * W)
                 res = C.c_void_p()
@@ -751,10 +752,10 @@ def main_ours(a, rank, world, local_rank):
                 for i in range(n_loc):
                     up_edge[i].edge, up_edge[i].edge_step = (ctx.ed_device_edge_plane(i) if on_device else h_edge[i].ctypes.data), 4 * W
                 export_step(up_edge)
-            for on_device in (True, False):
+            for on_device in ((1, 0, 2) if n_loc <= 256 else (1, 0)):
                 ctx.set_edge_drawing_route(on_device)
                 edge_step(on_device)
-                key = "edge_dev" if on_device else "edge_host"
+                key = {1: "edge_dev", 0: "edge_host", 2: "edge_hostdev"}[on_device]
                 e2e[key + "_candidates"] = int(sum(ctx.candidate_count(s) for s in owned))
                 ed_ms.clear()
                 tt = time.perf_counter()
@@ -763,7 +764,7 @@ def main_ours(a, rank, world, local_rank):
                 e2e[key + "_sec"] = (time.perf_counter() - tt) / a.steps
                 e2e[key + "_points"] = int(tot.value)
                 e2e[key + "_ed_ms"] = float(np.mean(ed_ms))
-                if on_device:
+                if on_device == 1:
                     e2e["edge_fallbacks"] = ctx.last_edge_drawing_fallbacks()
             ctx.set_edge_drawing_route(False)
             upload(); ctx.synchronize()  # back to the bench's own planes and mask for what follows
@@ -883,10 +884,11 @@ def main_ours(a, rank, world, local_rank):
                 "note": "as e2e_point_export, but only im_ is uploaded: GradImg / GradTheta (KeyFrame.cc:69-74) are "
                         "produced on the device by k_pack_image"}
         if "edge_dev_sec" in e2e:
-            best = "edge_dev" if e2e["edge_dev_sec"] <= e2e["edge_host_sec"] else "edge_host"
+            best = min((k for k in ("edge_dev", "edge_host", "edge_hostdev") if k + "_sec" in e2e), key=lambda k: e2e[k + "_sec"])
             line["e2e_image_in_edge_drawing_points_out"] = {
                 "ms_per_step": 1e3 * e2e[best + "_sec"], "edge_drawing_ms_per_step": e2e[best + "_ed_ms"],
-                "routing": "device (k_ed_route)" if best == "edge_dev" else "host threads",
+                "routing": {"edge_dev": "device (k_ed_route)", "edge_host": "host threads, masks through host planes",
+                            "edge_hostdev": "host threads, masks scattered on the device from the chains (k_ed_mask)"}[best],
                 "value": e2e[best + "_candidates"] / e2e[best + "_sec"], "unit": UNIT, "candidates_per_step": e2e[best + "_candidates"],
                 "points_per_step": e2e[best + "_points"], "d2h_bytes_per_step": 16 * e2e[best + "_points"],
                 "routing_on_device": {"ms_per_step": 1e3 * e2e["edge_dev_sec"], "edge_drawing_ms_per_step": e2e["edge_dev_ed_ms"],
@@ -895,6 +897,10 @@ def main_ours(a, rank, world, local_rank):
                                                           e2e["edge_dev_candidates"] == e2e["edge_host_candidates"])},
                 "routing_on_host_threads": {"ms_per_step": 1e3 * e2e["edge_host_sec"], "edge_drawing_ms_per_step": e2e["edge_host_ed_ms"],
                                             "h2d_bytes_per_step": int(5 * n_loc * W * H), "d2h_bytes_extra_per_step": int(3 * n_loc * W * H)},
+                "routing_on_host_threads_masks_on_device": (
+                    {"ms_per_step": 1e3 * e2e["edge_hostdev_sec"], "edge_drawing_ms_per_step": e2e["edge_hostdev_ed_ms"],
+                     "same_result": bool(e2e["edge_hostdev_points"] == e2e["edge_host_points"] and
+                                         e2e["edge_hostdev_candidates"] == e2e["edge_host_candidates"])} if "edge_hostdev_sec" in e2e else None),
                 "note": "the reference's complete loop, detector included (DetectEdgeMap inside pass 1, ProbabilityMapping.cc:394: only edge "
                         "pixels are candidates, :454): im_ up, sdm_edge_drawing, kf->mEdgeIndex to the packing kernel (a device plane when the "
                         "routing walks run on the device, a pinned host plane when they run on host threads), both passes, sdm_export_points; "

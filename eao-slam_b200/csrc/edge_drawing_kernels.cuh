@@ -553,6 +553,27 @@ __global__ void __launch_bounds__(32) k_ed_route(EdRouteBatch b)
     }
 }
 
+// kf->mEdgeIndex of a batch on the device from its chain lists (host routing, masks kept on the device): the planes hold -1
+// already; pixel j of image `img` gets the number of the chain it belongs to (binary search in the image's chain offsets)
+struct EdMaskImage { unsigned long long pix_begin, off_begin; int n_chains, n_pixels; };
+__global__ void __launch_bounds__(256) k_ed_mask(const EdMaskImage* __restrict__ images, const uint32_t* __restrict__ pixels,
+                                                 const int32_t* __restrict__ offsets, int W, int H, int32_t* __restrict__ masks)
+{
+    const EdMaskImage im = images[blockIdx.y];
+    const uint32_t* px = pixels + im.pix_begin;
+    const int32_t* off = offsets + im.off_begin;  // n_chains + 1 entries, off[0] = 0
+    int32_t* mask = masks + (size_t)blockIdx.y * (size_t)W * (size_t)H;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < im.n_pixels; j += gridDim.x * blockDim.x) {
+        int lo = 0, hi = im.n_chains;  // the chain with off[c] <= j < off[c + 1]
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (off[mid] <= j) lo = mid; else hi = mid;
+        }
+        const uint32_t p = px[j];
+        mask[(size_t)(p >> 16) * W + (p & 0xffffu)] = lo;
+    }
+}
+
 // chain lists of a batch as one contiguous block (one D2H copy instead of two per image): at[i] = first int32 of image i's
 // list - its offsets (chains + 1) followed by its pixels - at[n] = total; images that did not complete take no room
 __global__ void __launch_bounds__(1024) k_ed_chain_offsets(const int4* __restrict__ result, int n, unsigned long long* __restrict__ at)

@@ -291,6 +291,10 @@ struct sdm_ctx {
     int edr_cap = 0;
     int edr_fallbacks = 0;
     int edr_last_base = 0, edr_last_n = 0;  // images of the last device-routed batch whose edge-index planes are still in edr_dev
+    // SDM_ED_ROUTE_HOST_MASKS_ON_DEVICE: edge-index planes of the last batch, scattered from the chains by k_ed_mask
+    uint8_t* edm_dev = nullptr;
+    size_t edm_bytes = 0;
+    int edm_last_base = 0, edm_last_n = 0;
     cudaEvent_t edr_ev[2] = {nullptr, nullptr};
     void* peer_rs[kMaxPeers] = {nullptr};
     // sdm_exchange: flag blocks (own + IPC-mapped peers), halo plan, step counter
@@ -628,6 +632,7 @@ void sdm_destroy(sdm_ctx* c)
     if (c->lf_host) cudaFreeHost(c->lf_host);
     cudaFree(c->ed_dev);
     cudaFree(c->edr_dev);
+    cudaFree(c->edm_dev);
     if (c->edr_result_host) cudaFreeHost(c->edr_result_host);
     for (auto& e : c->edr_ev) if (e) cudaEventDestroy(e);
     if (c->ed_host) cudaFreeHost(c->ed_host);
@@ -1975,7 +1980,8 @@ int ed_run_device(sdm_ctx* c, int n, const sdm_ed_image* images, int grad_thresh
 int sdm_set_edge_drawing_route(sdm_ctx* c, int mode)
 {
     if (!c) return fail(SDM_ERR_ARG, "null context");
-    if (mode != SDM_ED_ROUTE_HOST && mode != SDM_ED_ROUTE_DEVICE) return fail(SDM_ERR_ARG, "sdm_set_edge_drawing_route: unknown mode %d", mode);
+    if (mode != SDM_ED_ROUTE_HOST && mode != SDM_ED_ROUTE_DEVICE && mode != SDM_ED_ROUTE_HOST_MASKS_ON_DEVICE)
+        return fail(SDM_ERR_ARG, "sdm_set_edge_drawing_route: unknown mode %d", mode);
     c->ed_route_mode = mode;
     return SDM_OK;
 }
@@ -1986,8 +1992,12 @@ int sdm_ed_device_edge_plane(sdm_ctx* c, int i, const int32_t** dev_plane)
 {
     if (!c || !dev_plane) return fail(SDM_ERR_ARG, "sdm_ed_device_edge_plane: null argument");
     *dev_plane = nullptr;
+    if (c->edm_dev && i >= c->edm_last_base && i < c->edm_last_base + c->edm_last_n) {  // host routing, masks scattered on the device
+        *dev_plane = (const int32_t*)c->edm_dev + (size_t)(i - c->edm_last_base) * c->npix;
+        return SDM_OK;
+    }
     if (!c->edr_dev || i < c->edr_last_base || i >= c->edr_last_base + c->edr_last_n)
-        return fail(SDM_ERR_STATE, "sdm_ed_device_edge_plane: image %d is not in the last batch routed on the device (%d .. %d)", i,
+        return fail(SDM_ERR_STATE, "sdm_ed_device_edge_plane: image %d is not in the last batch whose masks are on the device (%d .. %d)", i,
                     c->edr_last_base, c->edr_last_base + c->edr_last_n - 1);
     const EdRouteLayout L(c->edr_cap, c->npix);
     *dev_plane = (const int32_t*)(c->edr_dev + L.o_edge) + (size_t)(i - c->edr_last_base) * c->npix;
@@ -2009,7 +2019,7 @@ int sdm_edge_drawing(sdm_ctx* c, int n, const sdm_ed_image* images, int grad_thr
     if (!res) return fail(SDM_ERR_NOMEM, "out of host memory");
     res->chains.resize((size_t)n);
     c->ed_kernel_ms = c->ed_wall_ms = c->ed_route_ms = 0.f;
-    c->edr_last_n = 0;  // (sdm_ed_device_edge_plane: the planes of an earlier call are no longer handed out)
+    c->edr_last_n = c->edm_last_n = 0;  // (sdm_ed_device_edge_plane: the planes of an earlier call are no longer handed out)
     c->edr_fallbacks = 0;
     if (n == 0) { *result = res; return SDM_OK; }
     const auto wall0 = std::chrono::steady_clock::now();
@@ -2113,6 +2123,46 @@ int sdm_edge_drawing(sdm_ctx* c, int n, const sdm_ed_image* images, int grad_thr
                 c->ed_kernel_ms += ms;
             }
             c->ed_route_ms += (float)((double)route_ns.load() * 1e-6);
+            if (c->ed_route_mode == SDM_ED_ROUTE_HOST_MASKS_ON_DEVICE) {
+                // kf->mEdgeIndex of this batch on the device: the chain lists go up (a tenth of the planes' bytes), k_ed_mask
+                // writes the chain numbers into planes of -1
+                std::vector<sdm::EdMaskImage> desc((size_t)nb);
+                size_t n_pix = 0, n_off = 0;
+                for (int i = 0; i < nb; ++i) {
+                    const sdm_host::EdgeChains& e = res->chains[(size_t)(base + i)];
+                    desc[(size_t)i].pix_begin = n_pix; desc[(size_t)i].off_begin = n_off;
+                    desc[(size_t)i].n_chains = e.n_chains(); desc[(size_t)i].n_pixels = (int)e.pixels.size();
+                    n_pix += e.pixels.size(); n_off += e.offsets.size();
+                }
+                const size_t o_pix = ed_align((size_t)nb * P * 4), o_off = ed_align(o_pix + n_pix * 4), o_desc = ed_align(o_off + n_off * 4),
+                             bytes = ed_align(o_desc + (size_t)nb * sizeof(sdm::EdMaskImage));
+                if (bytes > c->edm_bytes) {
+                    cudaFree(c->edm_dev);
+                    c->edm_dev = nullptr; c->edm_bytes = 0;
+                    CU(cudaMalloc((void**)&c->edm_dev, bytes + bytes / 4));
+                    c->edm_bytes = bytes + bytes / 4;
+                }
+                CU(cudaMemsetAsync(c->edm_dev, 0xff, (size_t)nb * P * 4, c->s_ed));
+                int max_pix = 0;
+                for (int i = 0; i < nb; ++i) {
+                    const sdm_host::EdgeChains& e = res->chains[(size_t)(base + i)];
+                    if (!e.pixels.empty())
+                        CU(cudaMemcpyAsync(c->edm_dev + o_pix + desc[(size_t)i].pix_begin * 4, e.pixels.data(), e.pixels.size() * 4, cudaMemcpyHostToDevice, c->s_ed));
+                    CU(cudaMemcpyAsync(c->edm_dev + o_off + desc[(size_t)i].off_begin * 4, e.offsets.data(), e.offsets.size() * 4, cudaMemcpyHostToDevice, c->s_ed));
+                    max_pix = std::max(max_pix, desc[(size_t)i].n_pixels);
+                }
+                CU(cudaMemcpyAsync(c->edm_dev + o_desc, desc.data(), (size_t)nb * sizeof(sdm::EdMaskImage), cudaMemcpyHostToDevice, c->s_ed));
+                if (max_pix > 0) {
+                    sdm::k_ed_mask<<<dim3((unsigned)std::min(64, (max_pix + 255) / 256), (unsigned)nb), 256, 0, c->s_ed>>>(
+                        (const sdm::EdMaskImage*)(c->edm_dev + o_desc), (const uint32_t*)(c->edm_dev + o_pix), (const int32_t*)(c->edm_dev + o_off), W, H,
+                        (int32_t*)c->edm_dev);
+                    CU(cudaGetLastError());
+                    ++c->launches;
+                }
+                CU(cudaStreamSynchronize(c->s_ed));  // (the copies read the result's own vectors: done before the call returns)
+                c->edm_last_base = base;
+                c->edm_last_n = nb;
+            }
         }
         return SDM_OK;
     };

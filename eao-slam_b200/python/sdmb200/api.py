@@ -447,9 +447,10 @@ class Context:
             self.lib.sdm_ed_free(res)
         return offs, pix, edge
 
-    def set_edge_drawing_route(self, device: bool):
-        """stage 2 of edge_drawing on host threads (False, default) or on the device, one warp per image (True)"""
-        self._chk(self.lib.sdm_set_edge_drawing_route(self.h, 1 if device else 0))
+    def set_edge_drawing_route(self, device):
+        """stage 2 of edge_drawing on host threads (False / 0, default), on the device, one warp per image (True / 1), or on
+        host threads with the masks built on the device from the chains (2)"""
+        self._chk(self.lib.sdm_set_edge_drawing_route(self.h, int(device)))
 
     def ed_device_edge_plane(self, i: int) -> int:
         """device address of kf->mEdgeIndex of image i of the last device-routed edge_drawing batch (an `edge` plane for uploads)"""

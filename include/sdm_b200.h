@@ -281,14 +281,17 @@ void sdm_ed_free(sdm_ed_result* result);
  * per image and a device thread walks ~15 x slower than a host core, but thousands of images walk at once and the host
  * cores stay free (one process per GPU shares them); chains and edge index are identical in both modes.  An image whose
  * walk exceeds the kernel's fixed capacities is routed on the host (sdm_last_edge_drawing_fallbacks counts them). */
-enum { SDM_ED_ROUTE_HOST = 0, SDM_ED_ROUTE_DEVICE = 1 };
+/* SDM_ED_ROUTE_HOST_MASKS_ON_DEVICE: the walks on host threads as in SDM_ED_ROUTE_HOST, but kf->mEdgeIndex is (also) built on
+ * the device from the chain lists (k_ed_mask) for sdm_ed_device_edge_plane: with images[i].edge_index = NULL the host threads
+ * skip filling and scattering the 4-byte planes and the masks reach sdm_upload_keyframes without crossing PCIe as planes. */
+enum { SDM_ED_ROUTE_HOST = 0, SDM_ED_ROUTE_DEVICE = 1, SDM_ED_ROUTE_HOST_MASKS_ON_DEVICE = 2 };
 int sdm_set_edge_drawing_route(sdm_ctx* ctx, int mode);
 int sdm_last_edge_drawing_fallbacks(sdm_ctx* ctx);
-/* SDM_ED_ROUTE_DEVICE keeps kf->mEdgeIndex of every image of its last batch on the device (dense int32 plane, row pitch
+/* SDM_ED_ROUTE_DEVICE and SDM_ED_ROUTE_HOST_MASKS_ON_DEVICE keep kf->mEdgeIndex of every image of their last batch on the device (dense int32 plane, row pitch
  * 4 * width): *dev_plane is a DEVICE pointer that sdm_upload_desc.edge / sdm_upload_keyframe's edge accept like a host
  * plane (edge_step = 4 * width), so the candidate mask of :454 goes from the detector to the packing kernel without
  * crossing PCIe (images[i].edge_index may then be NULL).  Valid until the next sdm_edge_drawing or sdm_destroy on this
- * context; calls with more than 1024 images keep the last 1024-image batch only. */
+ * context; calls with more than 1024 images (256 with the walks on host threads) keep the planes of the last batch only. */
 int sdm_ed_device_edge_plane(sdm_ctx* ctx, int i, const int32_t** dev_plane);
 /* timing of the last sdm_edge_drawing: device time of its k_ed_planes launches, host wall time of the call, and the
  * summed thread time of the routing walks - in SDM_ED_ROUTE_DEVICE mode the device time of k_ed_sort + k_ed_route (all

@@ -156,23 +156,32 @@ def test_device_route_falls_back_to_the_host_when_a_capacity_runs_out(scene, mon
         assert np.array_equal(edge[i], w), i
 
 
-def test_mask_goes_from_the_detector_to_the_loop_on_the_device():
-    """SDM_ED_ROUTE_DEVICE keeps kf->mEdgeIndex on the device; sdm_upload_keyframes takes the device planes as `edge`
-    (sdm_ed_device_edge_plane).  Both passes over images + device masks give the planes of the same loop fed with the
-    host copies of those masks, bit for bit - and the masks are the library's (the golden chains)."""
+@pytest.mark.parametrize("mode", [1, 2])
+def test_mask_goes_from_the_detector_to_the_loop_on_the_device(mode):
+    """SDM_ED_ROUTE_DEVICE (1: walks in k_ed_route) and SDM_ED_ROUTE_HOST_MASKS_ON_DEVICE (2: walks on host threads, k_ed_mask
+    scatters the chain numbers) keep kf->mEdgeIndex on the device; sdm_upload_keyframes takes the device planes as `edge`
+    (sdm_ed_device_edge_plane).  Both passes over images + device masks give the planes of the same loop fed with the host
+    planes of the default mode, bit for bit, and the chains of the two calls are the same."""
     from sdmb200 import api, synth
     n, W, H, N = 12, 320, 240, 6
     sc = synth.make_scene(n, W, H, N, seed=23)
     items = api.make_items(range(n), sc.nbr_idx, sc.rot, sc.min_depth, sc.max_depth)
     with api.Context(width=W, height=H, max_keyframes=n) as ctx:
-        ctx.set_edge_drawing_route(True)
-        offs, pix, edge = ctx.edge_drawing(sc.im)
-        assert ctx.last_edge_drawing_fallbacks() == 0 and (edge >= 0).sum() > 10000
+        offs0, pix0, edge = ctx.edge_drawing(sc.im)  # default mode: host threads, host planes
+        assert (edge >= 0).sum() > 10000
+        with pytest.raises(api.SdmError):
+            ctx.ed_device_edge_plane(0)  # no masks on the device after a default-mode call
+        ctx.set_edge_drawing_route(mode)
+        offs, pix, none = ctx.edge_drawing(sc.im, edge_index=False)
+        assert none is None and ctx.last_edge_drawing_fallbacks() == 0
+        for i in range(n):
+            assert same((offs[i], pix[i]), (offs0[i], pix0[i])), i
         dev = [ctx.ed_device_edge_plane(i) for i in range(n)]
         with pytest.raises(api.SdmError):
             ctx.ed_device_edge_plane(n)
         ctx.upload_keyframes(ctx.upload_descs(sc, range(n), images_only=True, edge_dev=dev))
         ctx.pass1(items); ctx.pass2(items)
+
         def planes():
             per = [ctx.download(i) for i in range(n)]
             return {k: np.stack([q[k] for q in per]) for k in ("depth", "sigma", "checked", "points")}
